@@ -1,0 +1,165 @@
+"""Generate the committed golden fixtures under tests/golden from the SHIMMED, UNMODIFIED reference.
+
+Run once in the build container (needs /root/reference):   python -m oracle.make_golden
+TEST INFRASTRUCTURE ONLY; never imported by the product, the gpu tests, smoke() or bench.py.
+
+What is pinned (the reference itself has no tests / golden vectors):
+  tests/golden/schedule_kat.json   - KScheduler tables, get_sigmas(karras|linear|exp|quad|vp), sigma_to_t
+                                     integer indices (cpd/scheduler/k.py run as-is).
+  tests/golden/ref_sampling.npz    - reference Denoiser + Euler / Euler Ancestral / DPM++ 2m samplers driving
+                                     the reference UNetModel (tiny config, seeded non-zero weights) for
+                                     one image with N=3 weighted sub-prompts (2 conjunctions incl. a spatial
+                                     mask, 1 negation): inputs, per-step denoised tensors and final latents.
+Runtime repairs applied to the reference objects (no source edits), see SURVEY.md 8-c:
+  D1  SigmaScheduler.append_zero added (discrete.py:107 calls it, it is defined on another class, :765).
+  D2  SigmaScheduler.sigmas is given KScheduler's training table and get_sigmas no longer overwrites it.
+  D3  _process_conditioning receives sigma once (denoiser.py:508 passes it positionally AND in kwargs).
+  D4-D6 in oracle/ref_shim.py.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def schedule_kats(K):
+    ks = K.KScheduler()
+    out = {
+        "n_distinct_betas": int(torch.unique(ks.betas).numel()),
+        "betas": {str(i): float(ks.betas[i]) for i in (0, 1, 499, 998, 999)},
+        "alphas_cumprod": {str(i): float(ks.alphas_cumprod[i]) for i in (0, 1, 499, 998, 999)},
+        "sigmas_table": {str(i): float(ks.sigmas[i]) for i in (0, 1, 2, 250, 499, 750, 998, 999)},
+        "sigmas_table_sum": float(ks.sigmas.sum()),
+        "get_sigmas": {},
+        "sigma_to_t": {},
+    }
+    for alg, n in (("karras", 10), ("karras", 20), ("karras", 30), ("linear", 10), ("linear", 20),
+                   ("exp", 10), ("quad", 10), ("vp", 10)):
+        s = ks.get_sigmas(alg, n, device="cpu")
+        key = f"{alg}_{n}"
+        out["get_sigmas"][key] = {"dtype": str(s.dtype), "values": [float(v) for v in s],
+                                  "bits": [int(v) for v in s.view(torch.int32 if s.dtype == torch.float32 else torch.int64)]}
+        sig = s[:-1]
+        dists = torch.abs(sig.cpu() - ks.sigmas[:, None])
+        low_idx, high_idx = torch.sort(torch.topk(dists, dim=0, k=2, largest=False).indices, dim=0)[0]
+        t = ks.sigma_to_t(sig, device="cpu")
+        out["sigma_to_t"][key] = {"low_idx": low_idx.tolist(), "high_idx": high_idx.tolist(),
+                                  "t": [float(v) for v in t], "t_dtype": str(t.dtype)}
+    # t_to_sigma at a few fractional points
+    tt = torch.tensor([0.0, 0.5, 10.25, 499.75, 998.5, 999.0])
+    out["t_to_sigma"] = {"t": tt.tolist(), "sigma": [float(v) for v in ks.t_to_sigma(tt, device="cpu")]}
+    return out
+
+
+def build_reference_sampler(cls_name, unet):
+    """Construct the reference sampler (registry name) around a UNet module with repairs D1-D3."""
+    import cpd.samplers as S
+    import cpd.scheduler.discrete as D
+    import cpd.scheduler.k as K
+    import cpd.samplers.extension.denoiser as DN
+
+    if not hasattr(D.SigmaScheduler, "append_zero"):  # D1
+        D.SigmaScheduler.append_zero = lambda self, x: torch.cat([x, x.new_zeros([1])])
+    if not getattr(D.SigmaScheduler, "_d2", False):  # D2
+        orig = D.SigmaScheduler.get_sigmas
+
+        def get_sigmas(self, algorithm, n, **kw):
+            table = self.sigmas
+            out = orig(self, algorithm, n, **kw)
+            self.sigmas = table
+            return out
+
+        D.SigmaScheduler.get_sigmas = get_sigmas
+        D.SigmaScheduler._d2 = True
+    if not getattr(DN.Denoiser, "_d3", False):  # D3
+        orig_pc = DN.Denoiser._process_conditioning
+
+        def _pc(self, x, c, *args, **kwargs):
+            kwargs.pop("sigma", None)
+            return orig_pc(self, x, c, args[0], **kwargs)
+
+        DN.Denoiser._process_conditioning = _pc
+        DN.Denoiser._d3 = True
+    model = {"unet": unet, "vae": None, "tokenizer": None, "clip_new_model": torch.nn.Module(), "decode": None}
+    wrapper = S.make({"name": cls_name, "args": {}}, {"model": model})
+    wrapper.sampler.denoiser.scheduler.sigmas = K.KScheduler().sigmas  # D2: the 1000-entry training table
+    return wrapper
+
+
+def make_case_inputs(cfg, hw, seed=1234):
+    g = torch.Generator().manual_seed(seed)
+    D = cfg.context_dim
+    uc = torch.randn(1, 77, D, generator=g)
+    embs = [torch.randn(1, 77, D, generator=g) for _ in range(3)]
+    mask = torch.zeros(1, 1, hw, hw, dtype=torch.uint8)
+    mask[..., : hw // 2] = 1  # "left half valid" style mask (prompts.py:807-818)
+    c = {"and": [(1.0, embs[0], None, 1), (0.6, embs[1], None, mask)], "not": [(0.4, embs[2], None, 1)]}
+    x_T = torch.randn(1, 4, hw, hw, generator=g)
+    return uc, embs, mask, c, x_T
+
+
+def reference_sampling(ref_shim):
+    from oracle.unet import UNetConfig, make_weights
+
+    cfg = UNetConfig.tiny()
+    hw, steps = 8, 6
+    unet = ref_shim.build_reference_unet(cfg)
+    unet.load_state_dict(make_weights(cfg, seed=0), strict=True)
+    unet.eval()
+    uc, embs, mask, c, x_T = make_case_inputs(cfg, hw)
+    out = {"x_T": x_T.numpy(), "uc": uc.numpy(), "embs": torch.cat(embs).numpy(), "mask": mask.numpy(),
+           "scales": np.array([1.0, 0.6, 0.4]), "steps": np.array(steps), "hw": np.array(hw), "guidance": np.array(7.5)}
+    for name, sched, pred in (("Euler", "karras", "epsilon"), ("DPM++ 2m", "karras", "epsilon"),
+                              ("Euler Ancestral", "karras", "epsilon"), ("Euler", "exp", "velocity"),
+                              ("DPM++ 2m", "linear", "velocity")):
+        # NB ("Euler", "linear") cannot be generated: get_sigmas_linear returns fp64 sigmas, to_ode's
+        # append_dims (euler.py:103-111) turns the 0-dim sigma into a 4-D fp64 tensor, x is promoted to fp64
+        # and the second UNet call raises "Input type (double) and bias type (float)" (defect D9).
+        wrapper = build_reference_sampler(name, unet)
+        dens, noises = [], []
+        real_randn_like = torch.randn_like
+
+        def rec_randn_like(x, *a, **k):
+            n = real_randn_like(x, *a, **k)
+            noises.append(n.clone())
+            return n
+
+        torch.randn_like = rec_randn_like
+        torch.manual_seed(77)
+        try:
+            res = wrapper.sampler.sample(steps=steps, batch_size=1, shape=[4, hw, hw], x_T=x_T.clone(), conditioning=c,
+                                         unconditional_conditioning=uc, unconditional_guidance_scale=7.5,
+                                         scheduler=sched, device="cpu", silent=True, pred_type=pred,
+                                         callback=lambda d: dens.append(d["eps"].clone()))
+        finally:
+            torch.randn_like = real_randn_like
+        key = f"{name}|{sched}|{pred}".replace(" ", "_")
+        out[key + "|final"] = res.numpy()
+        out[key + "|denoised"] = torch.stack(dens).numpy()
+        if noises:
+            out[key + "|noise"] = torch.stack(noises).numpy()
+        print(key, "final std", float(res.std()), "n noise draws", len(noises))
+    return out
+
+
+def main():
+    sys.path.insert(0, os.path.dirname(HERE))
+    from oracle import ref_shim
+
+    ref_shim.install()
+    import cpd.scheduler.k as K
+
+    os.makedirs(GOLD, exist_ok=True)
+    with open(os.path.join(GOLD, "schedule_kat.json"), "w") as f:
+        json.dump(schedule_kats(K), f, indent=1)
+    np.savez_compressed(os.path.join(GOLD, "ref_sampling.npz"), **reference_sampling(ref_shim))
+    print("golden fixtures written to", GOLD)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,124 @@
+"""Pin the CPU oracle against fixtures produced by the shimmed, unmodified reference
+(oracle/make_golden.py) and against the known-answer values of SURVEY.md section 8-c."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.schedule import OracleSchedule
+from oracle.unet import UNetConfig, OracleUNet, make_weights, count_flops
+from oracle.denoiser import OracleDenoiser
+from oracle import samplers as OS
+
+
+@pytest.fixture(scope="module")
+def kat(golden_dir):
+    with open(os.path.join(golden_dir, "schedule_kat.json")) as f:
+        return json.load(f)
+
+
+def test_training_tables(kat):
+    s = OracleSchedule()
+    assert int(torch.unique(s.betas).numel()) == kat["n_distinct_betas"] == 113
+    for i, v in kat["betas"].items():
+        assert float(s.betas[int(i)]) == v
+    for i, v in kat["alphas_cumprod"].items():
+        assert float(s.alphas_cumprod[int(i)]) == v
+    for i, v in kat["sigmas_table"].items():
+        assert float(s.sigmas[int(i)]) == v
+    assert float(s.sigmas.sum()) == kat["sigmas_table_sum"]
+    # SURVEY 8-c known answers
+    assert float(s.sigmas[0]) == 0.028295591748715043
+    assert float(s.sigmas[999]) == 14.259975589529
+    assert float(s.alphas_cumprod[999]) == 0.004893639107497308
+
+
+@pytest.mark.parametrize("key", ["karras_10", "karras_20", "karras_30", "linear_10", "linear_20", "exp_10", "quad_10", "vp_10"])
+def test_get_sigmas_and_indices_bit_exact(kat, key):
+    alg, n = key.split("_")
+    s = OracleSchedule()
+    sig = s.get_sigmas(alg, int(n))
+    g = kat["get_sigmas"][key]
+    assert str(sig.dtype) == g["dtype"]
+    bits = sig.view(torch.int32 if sig.dtype == torch.float32 else torch.int64).tolist()
+    assert bits == g["bits"]
+    t, low, high = s.sigma_to_t_idx(sig[:-1])
+    assert low.tolist() == kat["sigma_to_t"][key]["low_idx"]
+    assert high.tolist() == kat["sigma_to_t"][key]["high_idx"]
+    assert [float(v) for v in t] == kat["sigma_to_t"][key]["t"]
+
+
+def test_survey_known_answers():
+    s = OracleSchedule()
+    sig = s.get_sigmas("karras", 10)
+    _, low, high = s.sigma_to_t_idx(sig[:-1])
+    assert low.tolist() == [937, 864, 778, 673, 545, 396, 243, 117, 42, 11]
+    assert (high - low).tolist() == [1] * 10
+    _, low20, _ = s.sigma_to_t_idx(s.get_sigmas("karras", 20)[:-1])
+    assert low20.tolist() == [937, 904, 869, 830, 788, 741, 691, 635, 574, 508, 437, 364, 290, 220, 158, 106, 67, 39, 21, 11]
+    t = s.sigma_to_t(sig[:-1])
+    assert float(t[0]) == 937.9314529721662 and float(t[-1]) == 11.278044358791906
+
+
+def test_t_to_sigma(kat):
+    s = OracleSchedule()
+    got = s.t_to_sigma(torch.tensor(kat["t_to_sigma"]["t"]))
+    assert [float(v) for v in got] == kat["t_to_sigma"]["sigma"]
+
+
+def test_flop_enumerator_matches_baseline():
+    # BASELINE.md section 3 (FlopCounterMode on the reference module)
+    assert abs(count_flops(UNetConfig.sd15(), 32, 32)["total"] / 1e12 - 0.1801) < 1e-4
+    assert abs(count_flops(UNetConfig.sd15(), 64, 64)["total"] / 1e12 - 0.8033) < 1e-4
+    assert abs(count_flops(UNetConfig.sd21(), 96, 96)["total"] / 1e12 - 2.1491) < 1e-4
+
+
+def _load_case(golden_dir):
+    z = np.load(os.path.join(golden_dir, "ref_sampling.npz"))
+    embs = torch.from_numpy(z["embs"])
+    mask = torch.from_numpy(z["mask"])
+    sc = z["scales"]
+    c = {"and": [(float(sc[0]), embs[0:1], None, 1), (float(sc[1]), embs[1:2], None, mask)],
+         "not": [(float(sc[2]), embs[2:3], None, 1)]}
+    return z, c
+
+
+@pytest.mark.parametrize("name,sched,pred", [("Euler", "karras", "epsilon"), ("DPM++ 2m", "karras", "epsilon"),
+                                             ("Euler Ancestral", "karras", "epsilon"), ("Euler", "exp", "velocity"),
+                                             ("DPM++ 2m", "linear", "velocity")])
+def test_oracle_sampling_matches_reference(golden_dir, name, sched, pred):
+    z, c = _load_case(golden_dir)
+    cfg = UNetConfig.tiny()
+    den = OracleDenoiser(OracleUNet(cfg, make_weights(cfg, seed=0)))
+    key = f"{name}|{sched}|{pred}".replace(" ", "_")
+    noises = list(torch.from_numpy(z[key + "|noise"])) if (key + "|noise") in z.files else []
+    dens = []
+    out = OS.sample(den, name, int(z["steps"]), torch.from_numpy(z["x_T"]).clone(),
+                    noise_sampler=(lambda x: noises.pop(0)) if noises else None,
+                    callback=lambda d: dens.append(d["eps"].clone()),
+                    conditioning=c, unconditional_conditioning=torch.from_numpy(z["uc"]),
+                    unconditional_guidance_scale=float(z["guidance"]), scheduler=sched, pred_type=pred)
+    ref_final = torch.from_numpy(z[key + "|final"])
+    ref_den = torch.from_numpy(z[key + "|denoised"])
+    for i, d in enumerate(dens):
+        rel = ((d - ref_den[i]).norm() / ref_den[i].norm()).item()
+        assert rel < 2e-4, (i, rel)  # fp16-delta rounding flips amplify ~1e-6 UNet differences
+    rel = ((out - ref_final).norm() / ref_final.norm()).item()
+    assert rel < 5e-4, rel
+
+
+def test_fp16_delta_differs_from_exact_combine():
+    """the reference computes the weighted delta in fp16 (denoiser.py:450-460); the
+    implementation must match THAT, which differs from the exact fp32 combine by ~2e-3 rel-L2."""
+    from oracle.denoiser import combine_fp16
+    g = torch.Generator().manual_seed(0)
+    e_u = torch.randn(1, 4, 64, 64, generator=g)
+    e_k = [e_u + 0.3 * torch.randn(1, 4, 64, 64, generator=g) for _ in range(3)]
+    w = [torch.tensor([1.0]), torch.tensor([0.6]), torch.tensor([-0.4])]
+    m = [torch.tensor([1.0])] * 3
+    got = e_u + 7.5 * combine_fp16(e_k, e_u, w, m)
+    exact = e_u + 7.5 * sum(wk * (ek - e_u) for wk, ek in zip(w, e_k))
+    rel = ((got - exact).norm() / exact.norm()).item()
+    assert 1e-4 < rel < 1e-2

@@ -9,7 +9,7 @@ What is pinned (the reference itself has no tests / golden vectors, SURVEY.md se
   tests/golden/ref_sampling.npz    - reference Denoiser + Euler / Euler Ancestral / DPM++ 2m samplers driving
                                      the reference UNetModel (tiny config, seeded non-zero weights) for
                                      one image with N=3 weighted sub-prompts (2 conjunctions incl. a spatial
-                                     mask, 1 negation): inputs, per-step denoised tensors and final latents.
+                                     mask, 1 negation): inputs, per-step UNet inputs/outputs, denoised tensors and final latents.
 Runtime repairs applied to the reference objects (no source edits), see SURVEY.md 8-c:
   D1  SigmaScheduler.append_zero added (discrete.py:107 calls it, it is defined on another class, :765).
   D2  SigmaScheduler.sigmas is given KScheduler's training table and get_sigmas no longer overwrites it.
@@ -121,7 +121,15 @@ def reference_sampling(ref_shim):
         # append_dims (euler.py:103-111) turns the 0-dim sigma into a 4-D fp64 tensor, x is promoted to fp64
         # and the second UNet call raises "Input type (double) and bias type (float)" (defect D9).
         wrapper = build_reference_sampler(name, unet)
-        dens, noises = [], []
+        dens, noises, u_x, u_t, u_out = [], [], [], [], []
+        orig_forward = unet.forward
+
+        def rec_forward(x, t, ctx, **k):
+            r = orig_forward(x, t, ctx, **k)
+            u_x.append(x.clone()); u_t.append(t.clone()); u_out.append(r[0].clone())
+            return r
+
+        unet.forward = rec_forward
         real_randn_like = torch.randn_like
 
         def rec_randn_like(x, *a, **k):
@@ -138,9 +146,13 @@ def reference_sampling(ref_shim):
                                          callback=lambda d: dens.append(d["eps"].clone()))
         finally:
             torch.randn_like = real_randn_like
+            unet.forward = orig_forward
         key = f"{name}|{sched}|{pred}".replace(" ", "_")
         out[key + "|final"] = res.numpy()
         out[key + "|denoised"] = torch.stack(dens).numpy()
+        out[key + "|unet_x"] = torch.stack(u_x).numpy()
+        out[key + "|unet_t"] = torch.stack(u_t).numpy()
+        out[key + "|unet_out"] = torch.stack(u_out).numpy()
         if noises:
             out[key + "|noise"] = torch.stack(noises).numpy()
         print(key, "final std", float(res.std()), "n noise draws", len(noises))

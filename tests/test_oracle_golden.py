@@ -88,7 +88,7 @@ def _load_case(golden_dir):
 @pytest.mark.parametrize("name,sched,pred", [("Euler", "karras", "epsilon"), ("DPM++ 2m", "karras", "epsilon"),
                                              ("Euler Ancestral", "karras", "epsilon"), ("Euler", "exp", "velocity"),
                                              ("DPM++ 2m", "linear", "velocity")])
-def test_oracle_sampling_matches_reference(golden_dir, name, sched, pred):
+def test_oracle_sampling_end_to_end_close_to_reference(golden_dir, name, sched, pred):
     z, c = _load_case(golden_dir)
     cfg = UNetConfig.tiny()
     den = OracleDenoiser(OracleUNet(cfg, make_weights(cfg, seed=0)))
@@ -104,9 +104,59 @@ def test_oracle_sampling_matches_reference(golden_dir, name, sched, pred):
     ref_den = torch.from_numpy(z[key + "|denoised"])
     for i, d in enumerate(dens):
         rel = ((d - ref_den[i]).norm() / ref_den[i].norm()).item()
-        assert rel < 2e-4, (i, rel)  # fp16-delta rounding flips amplify ~1e-6 UNet differences
+        assert rel < 5e-3, (i, rel)  # fp16-delta rounding flips amplify the ~1e-6 UNet difference (bit-exact test above)
     rel = ((out - ref_final).norm() / ref_final.norm()).item()
-    assert rel < 5e-4, rel
+    assert rel < 5e-3, rel
+
+
+CASES = [("Euler", "karras", "epsilon"), ("DPM++ 2m", "karras", "epsilon"), ("Euler Ancestral", "karras", "epsilon"),
+         ("Euler", "exp", "velocity"), ("DPM++ 2m", "linear", "velocity")]
+
+
+class _ReplayUNet:
+    """Returns the reference UNet's recorded outputs, so the denoiser/sampler restatement is checked BIT-EXACTLY."""
+
+    def __init__(self, outs, xs, ts):
+        self.outs, self.xs, self.ts, self.i = outs, xs, ts, 0
+
+    def parameters(self):
+        return iter([torch.zeros(1)])
+
+    def __call__(self, x, t, ctx, **kw):
+        assert torch.equal(x, self.xs[self.i]), "UNet input x differs from the reference's"
+        assert torch.equal(t, self.ts[self.i]), "UNet input t differs from the reference's"
+        o = self.outs[self.i]
+        self.i += 1
+        return o, [o] * 12
+
+
+@pytest.mark.parametrize("name,sched,pred", CASES)
+def test_oracle_denoiser_and_samplers_bit_exact_on_replayed_unet(golden_dir, name, sched, pred):
+    z, c = _load_case(golden_dir)
+    key = f"{name}|{sched}|{pred}".replace(" ", "_")
+    unet = _ReplayUNet(torch.from_numpy(z[key + "|unet_out"]), torch.from_numpy(z[key + "|unet_x"]), torch.from_numpy(z[key + "|unet_t"]))
+    den = OracleDenoiser(unet, dtype=torch.float32)
+    noises = list(torch.from_numpy(z[key + "|noise"])) if (key + "|noise") in z.files else []
+    dens = []
+    out = OS.sample(den, name, int(z["steps"]), torch.from_numpy(z["x_T"]).clone(),
+                    noise_sampler=(lambda x: noises.pop(0)) if noises else None,
+                    callback=lambda d: dens.append(d["eps"].clone()),
+                    conditioning=c, unconditional_conditioning=torch.from_numpy(z["uc"]),
+                    unconditional_guidance_scale=float(z["guidance"]), scheduler=sched, pred_type=pred)
+    assert torch.equal(torch.stack(dens), torch.from_numpy(z[key + "|denoised"]))
+    assert torch.equal(out, torch.from_numpy(z[key + "|final"]))
+
+
+def test_oracle_unet_matches_reference_unet(golden_dir):
+    z, _ = _load_case(golden_dir)
+    cfg = UNetConfig.tiny()
+    unet = OracleUNet(cfg, make_weights(cfg, seed=0))
+    key = "Euler|karras|epsilon"
+    ctx = torch.cat([torch.from_numpy(z["uc"]), torch.from_numpy(z["embs"])])
+    for i in (0, 3, 5):
+        out = unet(torch.from_numpy(z[key + "|unet_x"][i]), torch.from_numpy(z[key + "|unet_t"][i]), ctx)
+        ref = torch.from_numpy(z[key + "|unet_out"][i])
+        assert ((out - ref).norm() / ref.norm()).item() < 1e-5
 
 
 def test_fp16_delta_differs_from_exact_combine():

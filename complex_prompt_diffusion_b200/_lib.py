@@ -1,0 +1,108 @@
+"""ctypes binding of libcpd_b200.so (the C ABI declared in include/cpd_b200.h).
+
+There is NO fallback: if the CUDA library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcpd_b200.so")
+
+CPD_F32, CPD_F16, CPD_BF16 = 0, 1, 2
+CPD_EULER, CPD_EULER_ANCESTRAL, CPD_DPMPP_2M = 0, 1, 2
+CPD_PRED_EPSILON, CPD_PRED_VELOCITY = 0, 1
+CPD_EPI_NONE, CPD_EPI_GEGLU = 0, 1
+CPD_MAX_SUBPROMPTS = 16
+
+DTYPE_CODE = {torch.float32: CPD_F32, torch.float16: CPD_F16, torch.bfloat16: CPD_BF16}
+
+
+class StepParams(C.Structure):
+    _fields_ = [
+        ("eps", C.c_void_p), ("eps_dtype", C.c_int), ("eps_image_stride", C.c_int64), ("eps_row_stride", C.c_int64),
+        ("x", C.c_void_p), ("old_denoised", C.c_void_p), ("noise", C.c_void_p), ("denoised_out", C.c_void_p),
+        ("eps_out", C.c_void_p),
+        ("n_images", C.c_int), ("n_sub", C.c_int), ("hw", C.c_int),
+        ("weights", C.c_float * CPD_MAX_SUBPROMPTS), ("mask_scalar", C.c_float * CPD_MAX_SUBPROMPTS),
+        ("masks", C.c_void_p * CPD_MAX_SUBPROMPTS),
+        ("guidance", C.c_float), ("sampler", C.c_int), ("pred_type", C.c_int),
+        ("sigma_hat", C.c_float), ("v_c_eps", C.c_float), ("v_c_x_div", C.c_float), ("dt", C.c_float),
+        ("sigma_up", C.c_float), ("dpm_ratio", C.c_float), ("dpm_expm1", C.c_float), ("dpm_c1", C.c_float),
+        ("dpm_c2", C.c_float), ("dpm_first", C.c_int), ("write_old", C.c_int),
+    ]
+
+
+class GemmParams(C.Structure):
+    _fields_ = [
+        ("a0", C.c_void_p), ("a1", C.c_void_p), ("c0", C.c_int), ("c1", C.c_int),
+        ("n_img", C.c_int), ("h_in", C.c_int), ("w_in", C.c_int), ("ksize", C.c_int), ("stride", C.c_int),
+        ("wt", C.c_void_p), ("n_out", C.c_int), ("bias", C.c_void_p),
+        ("rowvec", C.c_void_p), ("rowvec_stride", C.c_int),
+        ("residual", C.c_void_p), ("ld_res", C.c_int),
+        ("d", C.c_void_p), ("ldd", C.c_int), ("epilogue", C.c_int), ("variant", C.c_int), ("m_valid", C.c_int),
+    ]
+
+
+class AttnParams(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("ldq", C.c_int), ("k", C.c_void_p), ("ldk", C.c_int), ("vt", C.c_void_p), ("ldvt", C.c_int),
+        ("o", C.c_void_p), ("ldo", C.c_int),
+        ("batch", C.c_int), ("heads", C.c_int), ("nq", C.c_int), ("nk", C.c_int), ("nk_pad", C.c_int), ("dpad", C.c_int),
+        ("scale", C.c_float), ("kv_batch", C.c_int),
+    ]
+
+
+_SIGS = {
+    "cpd_last_error": (C.c_char_p, []),
+    "cpd_abi_version": (C.c_int, []),
+    "cpd_sampler_step": (C.c_int, [C.POINTER(StepParams), C.c_void_p]),
+    "cpd_gemm_conv": (C.c_int, [C.POINTER(GemmParams), C.c_void_p]),
+    "cpd_groupnorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cpd_layernorm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
+    "cpd_timestep_embedding": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "cpd_small_linear": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                   C.c_void_p, C.c_int, C.c_void_p]),
+    "cpd_conv_in": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float,
+                              C.c_int, C.c_void_p, C.c_void_p]),
+    "cpd_conv_out": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                               C.c_int, C.c_void_p]),
+    "cpd_upsample2x": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "cpd_attention": (C.c_int, [C.POINTER(AttnParams), C.c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGS)
+_lib = None
+
+
+def load():
+    """Load libcpd_b200.so; raises RuntimeError (no fallback) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU or PyTorch fallback for the hot path)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = load().cpd_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (status {status}): {msg}")
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)

@@ -1,0 +1,418 @@
+// Implicit-GEMM convolution / GEMM for sm_100a: tcgen05.mma with the accumulator in TMEM, operands staged
+// into 128B-swizzled shared memory by TMA (cp.async.bulk.tensor), mbarrier producer/consumer pipeline,
+// warp-specialised roles (warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 = epilogue).
+//
+// One CTA computes a 128 x BN output tile.  The A operand (activations, NHWC bf16) is addressed through a
+// rank-5 tensor map (c, x, parity, y, n): a 3x3 tap is just a shifted TMA box whose out-of-bounds part is
+// zero-filled by the TMA unit (= the conv's zero padding), so no im2col buffer ever exists.  Stride-2 convs
+// use the parity view [n][h/2][2][w/2][2*C] of the same buffer.  The skip-concat input of the UNet output
+// blocks (unet.py:814) is read through two tensor maps without materialising the concatenation.
+//
+// Replaces the cuDNN/cuBLAS calls behind nn.Conv2d / nn.Linear in cpd/models/unet.py:105,153-160,210,236,247
+// and cpd/models/attention.py:92-118,183-190,508-524.
+#include "../../include/cpd_b200.h"
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;      // output rows per CTA (UMMA M)
+constexpr int BK = 64;       // K elements per pipeline stage (one 128-byte swizzle atom of bf16)
+constexpr int UMMA_K = 16;   // K per tcgen05.mma for 16-bit inputs
+constexpr int NUM_THREADS = 192;
+
+struct ConvGeom {
+  int taps;        // 1 or 9
+  int cb0, cb1;    // 64-channel blocks from source 0 / 1
+  int c0;          // channels of source 0 (stride-2 parity offset)
+  int c1;
+  int stride;      // 1 or 2
+  int tw, th, nbox;   // box = th x tw output pixels, nbox boxes per 128-row tile
+  int bx_count, by_count;
+  int n_img, h_out, w_out;
+  int m_valid;     // plain GEMM: valid rows; 0 = all
+  int n_out;       // GEMM N
+  int n_store;     // columns of D (n_out, or n_out/2 for GEGLU)
+  int epilogue;
+  int rowvec_stride, ld_res, ldd;
+};
+
+struct GemmArgs {
+  CUtensorMap map_a0, map_a1, map_b;
+  ConvGeom g;
+  const float* bias;
+  const float* rowvec;
+  const bf16* residual;
+  bf16* d;
+};
+
+template <int BN, int STAGES>
+struct SmemLayout {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // + barriers + alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_conv_kernel(const __grid_constant__ GemmArgs args) {
+  using L = SmemLayout<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const ConvGeom& g = args.g;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tile = blockIdx.x;
+  const int n_tile = blockIdx.y;
+  const int cbt = g.cb0 + g.cb1;
+  const int num_k = g.taps * cbt;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&args.map_a0);
+    tma_prefetch_desc(&args.map_b);
+    if (g.cb1 > 0) tma_prefetch_desc(&args.map_a1);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      const int box_rows = g.tw * g.th;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kt = 0; kt < num_k; ++kt) {
+        const int tap = kt / cbt;
+        const int cb = kt - tap * cbt;
+        int dy = 0, dx = 0, py = 0, px = 0;
+        if (g.taps == 9) {
+          const int ky = tap / 3, kx = tap - ky * 3;
+          if (g.stride == 1) {
+            dy = ky - 1;
+            dx = kx - 1;
+          } else {  // input row = 2*oy + ky - 1 = 2*(oy + dy) + py
+            dy = (ky == 0) ? -1 : 0;
+            py = (ky == 0) ? 1 : ky - 1;
+            dx = (kx == 0) ? -1 : 0;
+            px = (kx == 0) ? 1 : kx - 1;
+          }
+        }
+        mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+        uint8_t* sa = smem + stage * L::STAGE_BYTES;
+        uint8_t* sb = sa + L::A_BYTES;
+        mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+        const bool src1 = cb >= g.cb0;
+        const CUtensorMap* ma = src1 ? &args.map_a1 : &args.map_a0;
+        const int csrc = src1 ? g.c1 : g.c0;
+        const int ccoord = (src1 ? cb - g.cb0 : cb) * BK + px * csrc;
+        for (int j = 0; j < g.nbox; ++j) {
+          const int s_idx = m_tile * g.nbox + j;
+          const int bx = s_idx % g.bx_count;
+          const int t2 = s_idx / g.bx_count;
+          const int by = t2 % g.by_count;
+          const int n = t2 / g.by_count;  // n >= n_img -> fully out of bounds -> zero fill
+          tma_load_5d(sa + j * box_rows * 128, ma, &full_bar[stage], ccoord, bx * g.tw + dx, py, by * g.th + dy, n);
+        }
+        tma_load_2d(sb, &args.map_b, &full_bar[stage], kt * BK, n_tile * BN);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kt = 0; kt < num_k; ++kt) {
+        mbar_wait(&full_bar[stage], phase, 2);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+        const uint32_t sb = sa + L::A_BYTES;
+        const uint64_t da = umma_desc_sw128(sa);
+        const uint64_t db = umma_desc_sw128(sb);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          // advance 32 bytes (16 bf16) along K inside the 128-byte swizzle atom: +2 in the >>4 address field
+          umma_bf16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kt > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs above have read it
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;       // row within the tile
+    // output row (pixel) of this thread
+    const int box_rows = g.tw * g.th;
+    const int j = r / box_rows;
+    const int pidx = r - j * box_rows;
+    const int s_idx = m_tile * g.nbox + j;
+    const int bx = s_idx % g.bx_count;
+    const int t2 = s_idx / g.bx_count;
+    const int by = t2 % g.by_count;
+    const int n = t2 / g.by_count;
+    const int y = by * g.th + pidx / g.tw;
+    const int x = bx * g.tw + pidx % g.tw;
+    bool valid = (n < g.n_img) && (y < g.h_out) && (x < g.w_out);
+    const int64_t row = ((int64_t)n * g.h_out + y) * g.w_out + x;
+    if (g.m_valid > 0 && row >= g.m_valid) valid = false;
+
+    mbar_wait(tmem_full_bar, 0, 3);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+
+    if (g.epilogue == CPD_EPI_GEGLU) {
+      // tile columns [0, BN/2) = value, [BN/2, BN) = gate  ->  BN/2 output columns
+      constexpr int HALF = BN / 2;
+      const int ncol0 = n_tile * HALF;
+#pragma unroll 1
+      for (int c = 0; c < HALF; c += 16) {
+        uint32_t va[16], vg[16];
+        tmem_ld16(taddr + c, va);
+        tmem_ld16(taddr + HALF + c, vg);
+        tmem_ld_wait();
+        if (valid && ncol0 + c < g.n_store) {
+          uint32_t packed[8];
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) {
+            float a0 = __uint_as_float(va[e]), a1 = __uint_as_float(va[e + 1]);
+            float g0 = __uint_as_float(vg[e]), g1 = __uint_as_float(vg[e + 1]);
+            if (args.bias) {
+              a0 += __ldg(args.bias + n_tile * BN + c + e);
+              a1 += __ldg(args.bias + n_tile * BN + c + e + 1);
+              g0 += __ldg(args.bias + n_tile * BN + HALF + c + e);
+              g1 += __ldg(args.bias + n_tile * BN + HALF + c + e + 1);
+            }
+            // the reference rounds the projection to the model dtype before x * gelu(gate) (attention.py:98-100)
+            a0 = __bfloat162float(__float2bfloat16_rn(a0));
+            a1 = __bfloat162float(__float2bfloat16_rn(a1));
+            g0 = __bfloat162float(__float2bfloat16_rn(g0));
+            g1 = __bfloat162float(__float2bfloat16_rn(g1));
+            g0 = __bfloat162float(__float2bfloat16_rn(gelu_erf_f(g0)));
+            g1 = __bfloat162float(__float2bfloat16_rn(gelu_erf_f(g1)));
+            packed[e / 2] = pack_bf16x2(a0 * g0, a1 * g1);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(args.d + row * g.ldd + ncol0 + c);
+          dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+        }
+      }
+    } else {
+      const int ncol0 = n_tile * BN;
+      const float* rv = (args.rowvec && valid) ? args.rowvec + (int64_t)n * g.rowvec_stride : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int h8 = 0; h8 < 4; ++h8) {  // 4 groups of 8 columns = one 16-byte store each
+            const int col = ncol0 + c + h8 * 8;
+            if (col < g.n_store) {
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[h8 * 8 + e]);
+              if (args.bias) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(args.bias + col));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(args.bias + col + 4));
+                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+              }
+              if (rv) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(rv + col));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(rv + col + 4));
+                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+              }
+              if (args.residual) {
+                const uint4 rr = __ldg(reinterpret_cast<const uint4*>(args.residual + row * g.ld_res + col));
+                const float2 r0 = unpack_bf16x2(rr.x), r1 = unpack_bf16x2(rr.y), r2 = unpack_bf16x2(rr.z),
+                             r3 = unpack_bf16x2(rr.w);
+                f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y;
+                f[4] += r2.x; f[5] += r2.y; f[6] += r3.x; f[7] += r3.y;
+              }
+              *reinterpret_cast<uint4*>(args.d + row * g.ldd + col) =
+                  make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                             pack_bf16x2(f[6], f[7]));
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+template <int BN, int STAGES>
+cpd_status launch(const GemmArgs& args, int m_tiles, int n_tiles, cudaStream_t s) {
+  using L = SmemLayout<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    CPD_CUDA_CHECK(cudaFuncSetAttribute(gemm_conv_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  gemm_conv_kernel<BN, STAGES><<<dim3(m_tiles, n_tiles), NUM_THREADS, L::TOTAL, s>>>(args);
+  CPD_CUDA_CHECK(cudaGetLastError());
+  return CPD_OK;
+}
+
+// choose a box (tw x th) of output pixels: tw | w, th | h, tw*th <= 128 and a multiple of 8, as large as possible
+bool choose_box(int h, int w, int* tw, int* th) {
+  int best = 0;
+  for (int a = 1; a <= 128 && a <= w; ++a) {
+    if (w % a) continue;
+    for (int b = 1; a * b <= 128 && b <= h; ++b) {
+      if (h % b) continue;
+      const int px = a * b;
+      if (128 % px) continue;
+      if (px % 8) continue;
+      if (px > best || (px == best && a > *tw)) {
+        best = px;
+        *tw = a;
+        *th = b;
+      }
+    }
+  }
+  return best > 0;
+}
+
+}  // namespace
+
+extern "C" cpd_status cpd_gemm_conv(const cpd_gemm_params* p, void* stream) {
+  CPD_REQUIRE(p != nullptr, "cpd_gemm_conv: null params");
+  CPD_REQUIRE(p->a0 && p->wt && p->d, "cpd_gemm_conv: a0, wt and d must be non-null");
+  CPD_REQUIRE(p->c0 > 0 && p->c0 % 64 == 0 && p->c1 >= 0 && p->c1 % 64 == 0,
+              "cpd_gemm_conv: channel counts must be multiples of 64 (c0=%d c1=%d)", p->c0, p->c1);
+  CPD_REQUIRE(p->c1 == 0 || p->a1, "cpd_gemm_conv: c1 > 0 needs a1");
+  CPD_REQUIRE(p->ksize == 1 || p->ksize == 3, "cpd_gemm_conv: ksize must be 1 or 3 (got %d)", p->ksize);
+  CPD_REQUIRE(p->stride == 1 || (p->stride == 2 && p->ksize == 3 && p->h_in % 2 == 0 && p->w_in % 2 == 0),
+              "cpd_gemm_conv: stride must be 1, or 2 with a 3x3 kernel and even h/w");
+  CPD_REQUIRE(p->n_img > 0 && p->h_in > 0 && p->w_in > 0, "cpd_gemm_conv: empty input (%d x %d x %d)", p->n_img, p->h_in, p->w_in);
+  CPD_REQUIRE(p->n_out > 0 && p->n_out % 8 == 0, "cpd_gemm_conv: n_out=%d must be a positive multiple of 8", p->n_out);
+  CPD_REQUIRE(p->ldd % 8 == 0 && (p->residual == nullptr || p->ld_res % 8 == 0), "cpd_gemm_conv: ldd/ld_res must be multiples of 8");
+  CPD_REQUIRE(((uintptr_t)p->d & 15) == 0, "cpd_gemm_conv: d must be 16-byte aligned");
+  CPD_REQUIRE(p->stride == 1 || p->c1 == 0, "cpd_gemm_conv: stride 2 supports a single source");
+
+  GemmArgs args;
+  ConvGeom& g = args.g;
+  const int C = p->c0 + p->c1;
+  g.taps = p->ksize * p->ksize;
+  g.cb0 = p->c0 / 64;
+  g.cb1 = p->c1 / 64;
+  g.c0 = p->c0;
+  g.c1 = p->c1;
+  g.stride = p->stride;
+  g.n_img = p->n_img;
+  g.h_out = p->h_in / p->stride;
+  g.w_out = p->w_in / p->stride;
+  g.m_valid = p->m_valid;
+  g.n_out = p->n_out;
+  g.epilogue = p->epilogue;
+  g.rowvec_stride = p->rowvec_stride;
+  g.ld_res = p->ld_res;
+  g.ldd = p->ldd;
+
+  int variant = p->variant;
+  if (variant == 0) variant = (p->n_out % 256 == 0 || p->n_out >= 1024) ? 2 : 1;
+  if (p->epilogue == CPD_EPI_GEGLU) variant = 1;
+  const int BN = variant == 2 ? 256 : 128;
+  if (p->epilogue == CPD_EPI_GEGLU) {
+    CPD_REQUIRE(p->n_out % 128 == 0, "cpd_gemm_conv: GEGLU needs n_out %% 128 == 0 (got %d)", p->n_out);
+    g.n_store = p->n_out / 2;
+  } else {
+    g.n_store = p->n_out;
+  }
+
+  const bool plain = (p->h_in == 1 && p->n_img == 1 && p->ksize == 1);
+  if (plain) {
+    g.tw = 128;
+    g.th = 1;
+    g.nbox = 1;
+    g.bx_count = (g.w_out + 127) / 128;
+    g.by_count = 1;
+  } else {
+    int tw = 0, th = 0;
+    CPD_REQUIRE(choose_box(g.h_out, g.w_out, &tw, &th), "cpd_gemm_conv: no 8..128-pixel box divides the %d x %d output", g.h_out, g.w_out);
+    g.tw = tw;
+    g.th = th;
+    g.nbox = 128 / (tw * th);
+    g.bx_count = g.w_out / tw;
+    g.by_count = g.h_out / th;
+  }
+  const int64_t total_boxes = (int64_t)g.n_img * g.bx_count * g.by_count;
+  const int m_tiles = (int)((total_boxes + g.nbox - 1) / g.nbox);
+  const int n_tiles = (p->n_out + BN - 1) / BN;
+
+  // tensor maps.  A: (c, x, parity, y, n)
+  auto make_a = [&](CUtensorMap* m, const void* base, int csrc) -> int {
+    uint64_t dims[5], str[4];
+    uint32_t box[5] = {64, (uint32_t)g.tw, 1, (uint32_t)g.th, 1};
+    if (p->stride == 1) {
+      dims[0] = csrc; dims[1] = p->w_in; dims[2] = 1; dims[3] = p->h_in; dims[4] = p->n_img;
+      str[0] = (uint64_t)csrc * 2;
+      str[1] = (uint64_t)p->w_in * csrc * 2;  // parity dim (size 1)
+      str[2] = (uint64_t)p->w_in * csrc * 2;
+      str[3] = (uint64_t)p->h_in * p->w_in * csrc * 2;
+    } else {
+      dims[0] = 2 * (uint64_t)csrc; dims[1] = p->w_in / 2; dims[2] = 2; dims[3] = p->h_in / 2; dims[4] = p->n_img;
+      str[0] = (uint64_t)csrc * 2 * 2;
+      str[1] = (uint64_t)p->w_in * csrc * 2;
+      str[2] = (uint64_t)p->w_in * csrc * 2 * 2;
+      str[3] = (uint64_t)p->h_in * p->w_in * csrc * 2;
+    }
+    return cpd_make_tmap_bf16(m, base, 5, dims, str, box);
+  };
+  int rc = make_a(&args.map_a0, p->a0, p->c0);
+  if (rc) return rc;
+  if (p->c1 > 0) {
+    rc = make_a(&args.map_a1, p->a1, p->c1);
+    if (rc) return rc;
+  } else {
+    args.map_a1 = args.map_a0;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)g.taps * C, (uint64_t)p->n_out};
+    uint64_t str[1] = {(uint64_t)g.taps * C * 2};
+    uint32_t box[2] = {64, (uint32_t)BN};
+    rc = cpd_make_tmap_bf16(&args.map_b, p->wt, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  args.bias = p->bias;
+  args.rowvec = p->rowvec;
+  args.residual = reinterpret_cast<const bf16*>(p->residual);
+  args.d = reinterpret_cast<bf16*>(p->d);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (variant == 2) return launch<256, 4>(args, m_tiles, n_tiles, s);
+  return launch<128, 3>(args, m_tiles, n_tiles, s);
+}

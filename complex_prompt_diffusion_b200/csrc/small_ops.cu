@@ -1,0 +1,259 @@
+// Small CUDA-core kernels around the UNet GEMMs: timestep embedding, small-M linear (time-embedding MLP and
+// the per-ResBlock emb projections), the 4->C input conv, the C->4 output conv and nearest 2x upsampling.
+// None of them is GEMM-shaped enough for tensor cores (K = 36, N = 4 or M <= 32); all are memory bound.
+#include "../../include/cpd_b200.h"
+#include "common.cuh"
+
+namespace {
+
+// models/util.py:65-85: emb = cat[cos(t * f), sin(t * f)], f_k = exp(-ln(10000) * k / half), fp32.
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, int rows, int dim, int round_t, bf16* __restrict__ out) {
+  const int half = dim / 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * half) return;
+  const int r = idx / half, k = idx - r * half;
+  float tv = t[r];
+  if (round_t) tv = __bfloat162float(__float2bfloat16_rn(tv));  // denoiser.py:393 casts t to the model dtype (P3)
+  const float f = expf(-logf(10000.0f) * (float)k / (float)half);
+  const float a = tv * f;
+  out[(int64_t)r * dim + k] = __float2bfloat16_rn(cosf(a));
+  out[(int64_t)r * dim + half + k] = __float2bfloat16_rn(sinf(a));
+}
+
+// out[m][n] = sum_k act(x[m][k]) * w[n][k] + b[n].  One warp per output column n, all m rows at once.
+template <int MT>
+__global__ void __launch_bounds__(256) small_linear_kernel(const bf16* __restrict__ x, int m, int k, const bf16* __restrict__ w,
+                                                           const float* __restrict__ b, int n, int silu_in,
+                                                           float* __restrict__ out_f32, bf16* __restrict__ out_bf16, int ld_out) {
+  extern __shared__ uint8_t sh_raw[];
+  bf16* xs = reinterpret_cast<bf16*>(sh_raw);  // [m][k] (activated)
+  for (int i = threadIdx.x; i < m * k; i += blockDim.x) {
+    float v = __bfloat162float(x[i]);
+    if (silu_in) v = __bfloat162float(__float2bfloat16_rn(silu_f(v)));
+    xs[i] = __float2bfloat16_rn(v);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (col >= n) return;
+  float acc[MT];
+#pragma unroll
+  for (int i = 0; i < MT; ++i) acc[i] = 0.f;
+  for (int kk = lane * 8; kk < k; kk += 256) {
+    const uint4 wv = __ldg(reinterpret_cast<const uint4*>(w + (int64_t)col * k + kk));
+    const uint32_t wu[4] = {wv.x, wv.y, wv.z, wv.w};
+    float wf[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float2 f = unpack_bf16x2(wu[e]); wf[2 * e] = f.x; wf[2 * e + 1] = f.y; }
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+      if (i < m) {
+        const uint4 xv = *reinterpret_cast<const uint4*>(xs + i * k + kk);
+        const uint32_t xu[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack_bf16x2(xu[e]);
+          acc[i] += f.x * wf[2 * e] + f.y * wf[2 * e + 1];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MT; ++i) {
+    float v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0 && i < m) {
+      v += b ? b[col] : 0.f;
+      v = __bfloat162float(__float2bfloat16_rn(v));  // the reference's Linear output is in the model dtype
+      if (out_f32) out_f32[(int64_t)i * ld_out + col] = v;
+      if (out_bf16) out_bf16[(int64_t)i * ld_out + col] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+// Input conv: x fp32 NCHW -> bf16 (cast) -> 3x3 pad 1 -> NHWC bf16.  One thread = one pixel x 8 output channels.
+__global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, int n, int cin, int h, int w,
+                                                      const bf16* __restrict__ wt, const float* __restrict__ bias, int cout,
+                                                      float scale, int rpi, bf16* __restrict__ out) {
+  const int cvecs = cout / 8;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)n * rpi * h * w * cvecs;
+  if (idx >= total) return;
+  const int cv = (int)(idx % cvecs);
+  const int64_t pix = idx / cvecs;
+  const int xx = (int)(pix % w);
+  const int yy = (int)((pix / w) % h);
+  const int nn = (int)(pix / ((int64_t)w * h)) / rpi;  // output row -> source image
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = bias ? bias[cv * 8 + e] : 0.f;
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = yy + ky - 1;
+    if (iy < 0 || iy >= h) continue;
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = xx + kx - 1;
+      if (ix < 0 || ix >= w) continue;
+      for (int c = 0; c < cin; ++c) {
+        const float xv = __bfloat162float(__float2bfloat16_rn(__fmul_rn(x[(((int64_t)nn * cin + c) * h + iy) * w + ix], scale)));
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          acc[e] += xv * __bfloat162float(wt[((int64_t)(cv * 8 + e) * 9 + ky * 3 + kx) * cin + c]);
+      }
+    }
+  }
+  *reinterpret_cast<uint4*>(out + pix * cout + cv * 8) =
+      make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+}
+
+// Output conv: NHWC bf16 (cin) -> 3x3 pad 1 -> NCHW (cout <= 8).  One warp per output pixel.
+template <int COUT>
+__global__ void __launch_bounds__(256) conv_out_kernel(const bf16* __restrict__ a, int n, int h, int w, int cin,
+                                                       const bf16* __restrict__ wt, const float* __restrict__ bias,
+                                                       void* __restrict__ out, int out_dtype) {
+  extern __shared__ uint8_t sh_raw[];
+  bf16* ws = reinterpret_cast<bf16*>(sh_raw);  // [COUT][9][cin]
+  for (int i = threadIdx.x * 8; i < COUT * 9 * cin; i += blockDim.x * 8)
+    *reinterpret_cast<uint4*>(ws + i) = __ldg(reinterpret_cast<const uint4*>(wt + i));
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t pix = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (pix >= (int64_t)n * h * w) return;
+  const int xx = (int)(pix % w);
+  const int yy = (int)((pix / w) % h);
+  const int nn = (int)(pix / ((int64_t)w * h));
+  float acc[COUT];
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
+  const int nvec = cin / 8;
+  for (int tap = 0; tap < 9; ++tap) {
+    const int iy = yy + tap / 3 - 1, ix = xx + tap % 3 - 1;
+    if (iy < 0 || iy >= h || ix < 0 || ix >= w) continue;
+    const bf16* src = a + (((int64_t)nn * h + iy) * w + ix) * cin;
+    for (int v = lane; v < nvec; v += 32) {
+      const uint4 av = __ldg(reinterpret_cast<const uint4*>(src + v * 8));
+      const uint32_t au[4] = {av.x, av.y, av.z, av.w};
+      float af[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const float2 f = unpack_bf16x2(au[e]); af[2 * e] = f.x; af[2 * e + 1] = f.y; }
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) {
+        const uint4 wv = *reinterpret_cast<const uint4*>(ws + ((int64_t)o * 9 + tap) * cin + v * 8);
+        const uint32_t wu[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack_bf16x2(wu[e]);
+          acc[o] += af[2 * e] * f.x + af[2 * e + 1] * f.y;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) {
+    float v = acc[o];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    if (lane == 0) {
+      v += bias ? bias[o] : 0.f;
+      const int64_t oi = (((int64_t)nn * COUT + o) * h + yy) * w + xx;
+      if (out_dtype == CPD_BF16) reinterpret_cast<bf16*>(out)[oi] = __float2bfloat16_rn(v);
+      else reinterpret_cast<float*>(out)[oi] = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) upsample2x_kernel(const bf16* __restrict__ a, int n, int h, int w, int c, bf16* __restrict__ out) {
+  const int cvecs = c / 8;
+  const int64_t total = (int64_t)n * (2 * h) * (2 * w) * cvecs;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % cvecs);
+    const int64_t pix = idx / cvecs;
+    const int ox = (int)(pix % (2 * w));
+    const int oy = (int)((pix / (2 * w)) % (2 * h));
+    const int nn = (int)(pix / ((int64_t)4 * w * h));
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(a + (((int64_t)nn * h + oy / 2) * w + ox / 2) * c + cv * 8));
+    *reinterpret_cast<uint4*>(out + pix * c + cv * 8) = v;
+  }
+}
+
+}  // namespace
+
+extern "C" cpd_status cpd_timestep_embedding(const float* t, int rows, int dim, int round_t_bf16, void* out, void* stream) {
+  CPD_REQUIRE(t && out && rows > 0 && dim > 0 && dim % 2 == 0, "cpd_timestep_embedding: bad arguments (rows=%d dim=%d)", rows, dim);
+  const int total = rows * (dim / 2);
+  timestep_embedding_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(t, rows, dim, round_t_bf16, (bf16*)out);
+  CPD_CUDA_CHECK(cudaGetLastError());
+  return CPD_OK;
+}
+
+extern "C" cpd_status cpd_small_linear(const void* x, int m, int k, const void* w, const float* b, int n, int silu_in,
+                                       float* out_f32, void* out_bf16, int ld_out, void* stream) {
+  CPD_REQUIRE(x && w && (out_f32 || out_bf16), "cpd_small_linear: null pointer");
+  CPD_REQUIRE(m >= 1 && m <= 32, "cpd_small_linear: m=%d must be in [1,32]", m);
+  CPD_REQUIRE(k > 0 && k % 8 == 0 && (size_t)m * k * 2 <= 160 * 1024, "cpd_small_linear: k=%d unsupported for m=%d", k, m);
+  CPD_REQUIRE(n > 0 && ld_out >= n, "cpd_small_linear: n=%d ld_out=%d", n, ld_out);
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t shm = (size_t)m * k * 2;
+  const int blocks = (n + 7) / 8;
+#define LAUNCH_SL(MT)                                                                                                         \
+  do {                                                                                                                        \
+    static bool cfg = false;                                                                                                  \
+    if (!cfg) {                                                                                                               \
+      CPD_CUDA_CHECK(cudaFuncSetAttribute(small_linear_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); \
+      cfg = true;                                                                                                             \
+    }                                                                                                                         \
+    small_linear_kernel<MT><<<blocks, 256, shm, s>>>((const bf16*)x, m, k, (const bf16*)w, b, n, silu_in, out_f32,           \
+                                                      (bf16*)out_bf16, ld_out);                                              \
+  } while (0)
+  if (m <= 4) LAUNCH_SL(4);
+  else if (m <= 16) LAUNCH_SL(16);
+  else LAUNCH_SL(32);
+#undef LAUNCH_SL
+  CPD_CUDA_CHECK(cudaGetLastError());
+  return CPD_OK;
+}
+
+extern "C" cpd_status cpd_conv_in(const float* x, int n, int cin, int h, int w, const void* wt, const float* bias, int cout,
+                                  float scale, int rows_per_image, void* out, void* stream) {
+  CPD_REQUIRE(x && wt && out, "cpd_conv_in: null pointer");
+  CPD_REQUIRE(n > 0 && cin > 0 && cin <= 8 && h > 0 && w > 0 && cout % 8 == 0, "cpd_conv_in: bad shape n=%d cin=%d h=%d w=%d cout=%d", n, cin, h, w, cout);
+  CPD_REQUIRE(rows_per_image >= 1, "cpd_conv_in: rows_per_image=%d", rows_per_image);
+  const int64_t total = (int64_t)n * rows_per_image * h * w * (cout / 8);
+  conv_in_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, n, cin, h, w, (const bf16*)wt, bias, cout,
+                                                                                   scale, rows_per_image, (bf16*)out);
+  CPD_CUDA_CHECK(cudaGetLastError());
+  return CPD_OK;
+}
+
+extern "C" cpd_status cpd_conv_out(const void* a, int n, int h, int w, int cin, const void* wt, const float* bias, int cout,
+                                   void* out, int out_dtype, void* stream) {
+  CPD_REQUIRE(a && wt && out, "cpd_conv_out: null pointer");
+  CPD_REQUIRE(cout == 4 || cout == 8, "cpd_conv_out: cout=%d unsupported (4 or 8)", cout);
+  CPD_REQUIRE(cin % 8 == 0 && (size_t)cout * 9 * cin * 2 <= 200 * 1024, "cpd_conv_out: cin=%d unsupported", cin);
+  CPD_REQUIRE(out_dtype == CPD_BF16 || out_dtype == CPD_F32, "cpd_conv_out: out_dtype=%d", out_dtype);
+  const int64_t pixels = (int64_t)n * h * w;
+  const size_t shm = (size_t)cout * 9 * cin * 2;
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)((pixels + 7) / 8);
+  if (cout == 4) {
+    static bool cfg = false;
+    if (!cfg) { CPD_CUDA_CHECK(cudaFuncSetAttribute(conv_out_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfg = true; }
+    conv_out_kernel<4><<<blocks, 256, shm, s>>>((const bf16*)a, n, h, w, cin, (const bf16*)wt, bias, out, out_dtype);
+  } else {
+    static bool cfg = false;
+    if (!cfg) { CPD_CUDA_CHECK(cudaFuncSetAttribute(conv_out_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfg = true; }
+    conv_out_kernel<8><<<blocks, 256, shm, s>>>((const bf16*)a, n, h, w, cin, (const bf16*)wt, bias, out, out_dtype);
+  }
+  CPD_CUDA_CHECK(cudaGetLastError());
+  return CPD_OK;
+}
+
+extern "C" cpd_status cpd_upsample2x(const void* a, int n, int h, int w, int c, void* out, void* stream) {
+  CPD_REQUIRE(a && out && n > 0 && h > 0 && w > 0 && c % 8 == 0, "cpd_upsample2x: bad arguments");
+  const int64_t total = (int64_t)n * 4 * h * w * (c / 8);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  upsample2x_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)a, n, h, w, c, (bf16*)out);
+  CPD_CUDA_CHECK(cudaGetLastError());
+  return CPD_OK;
+}

@@ -1,0 +1,433 @@
+"""UNetModel: the Stable-Diffusion UNet forward on B200, same call signature as the reference
+`cpd/models/unet.py:415-831` (`forward(x, timesteps, context, y=None, return_attn=..., ...)`) and the same
+`state_dict` parameter names, but executed as a static plan of hand-written sm_100a kernels
+(libcpd_b200.so) over NHWC bf16 activations:
+
+  3x3 / 1x1 convs and every Linear  -> cpd_gemm_conv   (tcgen05 implicit GEMM, TMA-fed, fused bias /
+                                       time-embedding / residual / GEGLU epilogues)
+  self- and cross-attention          -> cpd_attention   (fused flash-style kernel, tcgen05 + TMEM)
+  GroupNorm(+SiLU), LayerNorm        -> cpd_groupnorm / cpd_layernorm
+  timestep embedding + emb MLPs      -> cpd_timestep_embedding / cpd_small_linear (all 22 ResBlock emb
+                                       projections batched in one launch)
+  4->C input conv, C->4 output conv  -> cpd_conv_in / cpd_conv_out
+
+The skip concat (unet.py:814) is never materialised: GroupNorm and the 1x1 skip conv read both sources.
+Text-context K/V projections are step-invariant and cached per prompt (`set_context`).
+Weights are bf16 (the model dtype of BASELINE.json's bf16 configs); GroupNorm statistics are fp32
+(models/util.py:103-105), accumulation is fp32 in TMEM.
+"""
+import torch
+
+from .. import ops
+from .._lib import CPD_EPI_GEGLU, CPD_EPI_NONE
+
+
+def _enumerate_blocks(cfg):
+    """Block structure built by the reference constructor (unet.py:545-727)."""
+    mc = cfg["model_channels"]
+    inputs = [[("conv_in", cfg["in_channels"], mc)]]
+    chans = [mc]
+    ch, ds = mc, 1
+    mult_list = list(cfg["channel_mult"])
+    for level, mult in enumerate(mult_list):
+        for _ in range(cfg["num_res_blocks"]):
+            layers = [("res", ch, mult * mc)]
+            ch = mult * mc
+            if ds in cfg["attention_resolutions"]:
+                layers.append(("attn", ch))
+            inputs.append(layers)
+            chans.append(ch)
+        if level != len(mult_list) - 1:
+            inputs.append([("down", ch)])
+            chans.append(ch)
+            ds *= 2
+    middle = [("res", ch, ch), ("attn", ch), ("res", ch, ch)]
+    outputs = []
+    for level, mult in list(enumerate(mult_list))[::-1]:
+        for i in range(cfg["num_res_blocks"] + 1):
+            ich = chans.pop()
+            layers = [("res", ch + ich, mc * mult, ch, ich)]
+            ch = mc * mult
+            if ds in cfg["attention_resolutions"]:
+                layers.append(("attn", ch))
+            if level and i == cfg["num_res_blocks"]:
+                layers.append(("up", ch))
+                ds //= 2
+            outputs.append(layers)
+    return inputs, middle, outputs
+
+
+def _round16(d):
+    return (d + 15) // 16 * 16
+
+
+class UNetModel:
+    DEFAULTS = dict(image_size=32, in_channels=4, model_channels=320, out_channels=4, num_res_blocks=2,
+                    attention_resolutions=(4, 2, 1), channel_mult=(1, 2, 4, 4), num_heads=8, num_head_channels=-1,
+                    transformer_depth=1, context_dim=768, use_linear_in_transformer=False, use_spatial_transformer=True,
+                    legacy=False)
+
+    def __init__(self, state_dict=None, device="cuda", **config):
+        cfg = dict(self.DEFAULTS)
+        cfg.update({k: v for k, v in config.items() if k in self.DEFAULTS})
+        if not cfg["use_spatial_transformer"] or cfg["legacy"]:
+            raise NotImplementedError("only the SpatialTransformer (legacy=False) UNet of the SD configs is supported")
+        if cfg["transformer_depth"] != 1:
+            raise NotImplementedError("transformer_depth != 1")
+        if config.get("num_classes") is not None:
+            raise NotImplementedError("class-conditional UNets are not on the hot path")
+        self.cfg = cfg
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("UNetModel runs on CUDA only: there is no CPU fallback for the hot path")
+        self.dtype = torch.bfloat16
+        self.model_channels = cfg["model_channels"]
+        self.inputs, self.middle, self.outputs = _enumerate_blocks(cfg)
+        self.w = {}
+        self._ws = {}
+        self._ctx = None
+        self._ctx_key = None
+        self._probe = torch.zeros(1, dtype=self.dtype, device=self.device)
+        if state_dict is not None:
+            self.load_state_dict(state_dict)
+
+    # ---- nn.Module-like surface used by the Denoiser ------------------------------------------------
+    def parameters(self):
+        yield self._probe
+        for v in self.w.values():
+            if isinstance(v, torch.Tensor):
+                yield v
+
+    def heads(self, ch):
+        if self.cfg["num_head_channels"] == -1:
+            return self.cfg["num_heads"], ch // self.cfg["num_heads"]
+        return ch // self.cfg["num_head_channels"], self.cfg["num_head_channels"]
+
+    # ---- weight packing (once) ---------------------------------------------------------------------
+    def load_state_dict(self, sd, strict=True):
+        dev = self.device
+        W = {}
+
+        def bf(t):
+            return t.detach().to(torch.bfloat16)
+
+        def f32(name):  # 1-D parameters are used in fp32 after rounding to the model dtype
+            return bf(sd[name]).float().contiguous().to(dev)
+
+        def conv3(name):  # [Cout, Cin, 3, 3] -> [Cout, 3, 3, Cin]
+            return bf(sd[name]).permute(0, 2, 3, 1).contiguous().to(dev)
+
+        def mat(name):  # [out, in] or [out, in, 1, 1]
+            t = bf(sd[name])
+            return t.reshape(t.shape[0], t.shape[1]).contiguous().to(dev)
+
+        def pad_rows(t, heads, d, dpad):  # [heads*d, K] -> [heads*dpad, K] (zero rows)
+            if d == dpad:
+                return t
+            out = torch.zeros(heads, dpad, t.shape[1], dtype=t.dtype)
+            out[:, :d] = t.reshape(heads, d, t.shape[1])
+            return out.reshape(heads * dpad, t.shape[1])
+
+        def pad_cols(t, heads, d, dpad):  # [N, heads*d] -> [N, heads*dpad]
+            if d == dpad:
+                return t
+            out = torch.zeros(t.shape[0], heads, dpad, dtype=t.dtype)
+            out[:, :, :d] = t.reshape(t.shape[0], heads, d)
+            return out.reshape(t.shape[0], heads * dpad)
+
+        ted = self.model_channels * 4
+        W["te0.w"], W["te0.b"] = mat("time_embed.0.weight"), f32("time_embed.0.bias")
+        W["te2.w"], W["te2.b"] = mat("time_embed.2.weight"), f32("time_embed.2.bias")
+        emb_w, emb_b, emb_off = [], [], {}
+        off = 0
+
+        def res(p, cin, cout):
+            nonlocal off
+            W[p + "gn1.g"], W[p + "gn1.b"] = f32(p + "in_layers.0.weight"), f32(p + "in_layers.0.bias")
+            W[p + "conv1.w"], W[p + "conv1.b"] = conv3(p + "in_layers.2.weight"), f32(p + "in_layers.2.bias")
+            emb_w.append(bf(sd[p + "emb_layers.1.weight"]))
+            emb_b.append(bf(sd[p + "emb_layers.1.bias"]).float())
+            emb_off[p] = off
+            off += cout
+            W[p + "gn2.g"], W[p + "gn2.b"] = f32(p + "out_layers.0.weight"), f32(p + "out_layers.0.bias")
+            W[p + "conv2.w"], W[p + "conv2.b"] = conv3(p + "out_layers.3.weight"), f32(p + "out_layers.3.bias")
+            if cin != cout:
+                W[p + "skip.w"], W[p + "skip.b"] = mat(p + "skip_connection.weight"), f32(p + "skip_connection.bias")
+
+        def attn(p, ch):
+            nh, dh = self.heads(ch)
+            dpad = _round16(dh)
+            W[p + "norm.g"], W[p + "norm.b"] = f32(p + "norm.weight"), f32(p + "norm.bias")
+            W[p + "proj_in.w"], W[p + "proj_in.b"] = mat(p + "proj_in.weight"), f32(p + "proj_in.bias")
+            W[p + "proj_out.w"], W[p + "proj_out.b"] = mat(p + "proj_out.weight"), f32(p + "proj_out.bias")
+            b = p + "transformer_blocks.0."
+            for n in ("norm1", "norm2", "norm3"):
+                W[b + n + ".g"], W[b + n + ".b"] = f32(b + n + ".weight"), f32(b + n + ".bias")
+            q1 = pad_rows(bf(sd[b + "attn1.to_q.weight"]), nh, dh, dpad)
+            k1 = pad_rows(bf(sd[b + "attn1.to_k.weight"]), nh, dh, dpad)
+            W[b + "attn1.qk.w"] = torch.cat([q1, k1]).contiguous().to(dev)  # fused Q|K projection
+            W[b + "attn1.v.w"] = pad_rows(bf(sd[b + "attn1.to_v.weight"]), nh, dh, dpad).contiguous().to(dev)
+            W[b + "attn1.out.w"] = pad_cols(bf(sd[b + "attn1.to_out.0.weight"]), nh, dh, dpad).contiguous().to(dev)
+            W[b + "attn1.out.b"] = f32(b + "attn1.to_out.0.bias")
+            W[b + "attn2.q.w"] = pad_rows(bf(sd[b + "attn2.to_q.weight"]), nh, dh, dpad).contiguous().to(dev)
+            W[b + "attn2.k.w"] = pad_rows(bf(sd[b + "attn2.to_k.weight"]), nh, dh, dpad).contiguous().to(dev)
+            W[b + "attn2.v.w"] = pad_rows(bf(sd[b + "attn2.to_v.weight"]), nh, dh, dpad).contiguous().to(dev)
+            W[b + "attn2.out.w"] = pad_cols(bf(sd[b + "attn2.to_out.0.weight"]), nh, dh, dpad).contiguous().to(dev)
+            W[b + "attn2.out.b"] = f32(b + "attn2.to_out.0.bias")
+            # GEGLU: interleave [64 value rows | 64 gate rows] per 128-column tile (cpd_gemm_conv CPD_EPI_GEGLU)
+            w1, b1 = bf(sd[b + "ff.net.0.proj.weight"]), bf(sd[b + "ff.net.0.proj.bias"]).float()
+            inner4 = w1.shape[0] // 2
+            assert inner4 % 64 == 0
+            wv, wg = w1[:inner4].reshape(inner4 // 64, 64, -1), w1[inner4:].reshape(inner4 // 64, 64, -1)
+            W[b + "ff1.w"] = torch.cat([wv, wg], dim=1).reshape(2 * inner4, -1).contiguous().to(dev)
+            bv, bg = b1[:inner4].reshape(inner4 // 64, 64), b1[inner4:].reshape(inner4 // 64, 64)
+            W[b + "ff1.b"] = torch.cat([bv, bg], dim=1).reshape(2 * inner4).contiguous().to(dev)
+            W[b + "ff2.w"], W[b + "ff2.b"] = mat(b + "ff.net.2.weight"), f32(b + "ff.net.2.bias")
+
+        def block(prefix, layers):
+            for j, l in enumerate(layers):
+                p = f"{prefix}{j}."
+                if l[0] == "conv_in":
+                    W[p + "w"], W[p + "b"] = conv3(p + "weight"), f32(p + "bias")
+                elif l[0] == "res":
+                    res(p, l[1], l[2])
+                elif l[0] == "attn":
+                    attn(p, l[1])
+                elif l[0] == "down":
+                    W[p + "w"], W[p + "b"] = conv3(p + "op.weight"), f32(p + "op.bias")
+                elif l[0] == "up":
+                    W[p + "w"], W[p + "b"] = conv3(p + "conv.weight"), f32(p + "conv.bias")
+
+        for i, layers in enumerate(self.inputs):
+            block(f"input_blocks.{i}.", layers)
+        block("middle_block.", self.middle)
+        for i, layers in enumerate(self.outputs):
+            block(f"output_blocks.{i}.", layers)
+        W["out.gn.g"], W["out.gn.b"] = f32("out.0.weight"), f32("out.0.bias")
+        W["out.w"], W["out.b"] = conv3("out.2.weight"), f32("out.2.bias")
+        W["emb_all.w"] = torch.cat(emb_w).contiguous().to(dev)
+        W["emb_all.b"] = torch.cat(emb_b).contiguous().to(dev)
+        self.emb_off, self.emb_total, self.ted = emb_off, off, ted
+        self.w = W
+        return self
+
+    # ---- workspace ---------------------------------------------------------------------------------
+    def _buf(self, name, numel, dtype=torch.bfloat16):
+        key = (name, numel, dtype)
+        t = self._ws.get(key)
+        if t is None:
+            t = torch.empty(numel, dtype=dtype, device=self.device)
+            self._ws[key] = t
+        return t
+
+    # ---- text context: step-invariant K / V^T of every cross-attention layer ---------------------------
+    def set_context(self, context):
+        """context: [Rc, tokens, D]; query row b uses context row (b % Rc)."""
+        key = (context.data_ptr(), tuple(context.shape), context._version)
+        if self._ctx_key == key:
+            return
+        ctx = context.to(self.device, torch.bfloat16)
+        rc, ntok, D = ctx.shape
+        nk_pad = (ntok + 15) // 16 * 16
+        ctx_pad = torch.zeros(rc, nk_pad, D, dtype=torch.bfloat16, device=self.device)
+        ctx_pad[:, :ntok] = ctx
+        kv = {}
+        for prefix, layers in self._all_blocks():
+            for j, l in enumerate(layers):
+                if l[0] != "attn":
+                    continue
+                b = f"{prefix}{j}.transformer_blocks.0."
+                wk, wv = self.w[b + "attn2.k.w"], self.w[b + "attn2.v.w"]
+                ip = wk.shape[0]
+                kc = torch.empty(rc * nk_pad, ip, dtype=torch.bfloat16, device=self.device)
+                vt = torch.empty(ip, rc * nk_pad, dtype=torch.bfloat16, device=self.device)
+                ops.gemm_conv(ctx_pad, wk, kc, n_img=1, h=1, w=rc * nk_pad, c0=D, n_out=ip)
+                ops.gemm_conv(wv, ctx_pad, vt, n_img=1, h=1, w=ip, c0=D, n_out=rc * nk_pad)
+                kv[b] = (kc, vt)
+        self._ctx = dict(rc=rc, ntok=ntok, nk_pad=nk_pad, kv=kv, keep=ctx_pad)
+        self._ctx_key = key
+
+    def _all_blocks(self):
+        for i, layers in enumerate(self.inputs):
+            yield f"input_blocks.{i}.", layers
+        yield "middle_block.", self.middle
+        for i, layers in enumerate(self.outputs):
+            yield f"output_blocks.{i}.", layers
+
+    # ---- layers --------------------------------------------------------------------------------------
+    def _res(self, p, x0, x1, c0, c1, cout, R, h, w, emb_all, emb_stride, stats):
+        W = self.w
+        hw = h * w
+        cin = c0 + c1
+        gn = self._buf("gn", R * hw * cin)
+        ops.groupnorm(x0, W[p + "gn1.g"], W[p + "gn1.b"], gn, stats, n_img=R, hw=hw, c0=c0, a1=x1, c1=c1, eps=1e-5, silu=True)
+        h1 = self._buf("h1", R * hw * cout)
+        ops.gemm_conv(gn, W[p + "conv1.w"], h1, n_img=R, h=h, w=w, c0=cin, n_out=cout, ksize=3, bias=W[p + "conv1.b"],
+                      rowvec=emb_all[self.emb_off[p]:], rowvec_stride=emb_stride)
+        gn2 = self._buf("gn", R * hw * cout)
+        ops.groupnorm(h1, W[p + "gn2.g"], W[p + "gn2.b"], gn2, stats, n_img=R, hw=hw, c0=cout, eps=1e-5, silu=True)
+        if cin != cout:
+            skip = self._buf("skip", R * hw * cout)
+            ops.gemm_conv(x0, W[p + "skip.w"], skip, n_img=R, h=h, w=w, c0=c0, a1=x1, c1=c1, n_out=cout, ksize=1,
+                          bias=W[p + "skip.b"])
+        else:
+            skip = x0
+        out = self._buf(p + "out", R * hw * cout)
+        ops.gemm_conv(gn2, W[p + "conv2.w"], out, n_img=R, h=h, w=w, c0=cout, n_out=cout, ksize=3, bias=W[p + "conv2.b"],
+                      residual=skip, ld_res=cout)
+        return out
+
+    def _attn(self, p, x, ch, R, h, w, stats):
+        W = self.w
+        hw = h * w
+        T = R * hw
+        nh, dh = self.heads(ch)
+        dpad = _round16(dh)
+        ip = nh * dpad
+        scale = dh ** -0.5
+        b = p + "transformer_blocks.0."
+        gn = self._buf("gn", T * ch)
+        ops.groupnorm(x, W[p + "norm.g"], W[p + "norm.b"], gn, stats, n_img=R, hw=hw, c0=ch, eps=1e-6, silu=False)
+        hcur = self._buf("tr.h", T * ch)
+        ops.gemm_conv(gn, W[p + "proj_in.w"], hcur, n_img=1, h=1, w=T, c0=ch, n_out=ch, bias=W[p + "proj_in.b"])
+        ln = self._buf("tr.ln", T * ch)
+        # --- self-attention
+        ops.layernorm(hcur, W[b + "norm1.g"], W[b + "norm1.b"], ln, rows=T, c=ch)
+        qk = self._buf("tr.qk", T * 2 * ip)
+        ops.gemm_conv(ln, W[b + "attn1.qk.w"], qk, n_img=1, h=1, w=T, c0=ch, n_out=2 * ip)
+        vt = self._buf("tr.vt", ip * T)
+        ops.gemm_conv(W[b + "attn1.v.w"], ln, vt, n_img=1, h=1, w=ip, c0=ch, n_out=T)
+        o = self._buf("tr.o", T * ip)
+        ops.attention(qk, qk[ip:], vt, o, ldq=2 * ip, ldk=2 * ip, ldvt=T, ldo=ip, batch=R, heads=nh, nq=hw, nk=hw, nk_pad=hw,
+                      dpad=dpad, scale=scale)
+        ops.gemm_conv(o, W[b + "attn1.out.w"], hcur, n_img=1, h=1, w=T, c0=ip, n_out=ch, bias=W[b + "attn1.out.b"],
+                      residual=hcur, ld_res=ch)
+        # --- cross-attention (K / V^T cached per prompt)
+        ctx = self._ctx
+        if ctx is None:
+            raise RuntimeError("UNetModel: no text context set (call set_context or pass `context`)")
+        kc, vtc = ctx["kv"][b]
+        ops.layernorm(hcur, W[b + "norm2.g"], W[b + "norm2.b"], ln, rows=T, c=ch)
+        q2 = self._buf("tr.q2", T * ip)
+        ops.gemm_conv(ln, W[b + "attn2.q.w"], q2, n_img=1, h=1, w=T, c0=ch, n_out=ip)
+        ops.attention(q2, kc, vtc, o, ldq=ip, ldk=ip, ldvt=ctx["rc"] * ctx["nk_pad"], ldo=ip, batch=R, heads=nh, nq=hw,
+                      nk=ctx["ntok"], nk_pad=ctx["nk_pad"], dpad=dpad, scale=scale, kv_batch=ctx["rc"])
+        ops.gemm_conv(o, W[b + "attn2.out.w"], hcur, n_img=1, h=1, w=T, c0=ip, n_out=ch, bias=W[b + "attn2.out.b"],
+                      residual=hcur, ld_res=ch)
+        # --- GEGLU feed-forward
+        ops.layernorm(hcur, W[b + "norm3.g"], W[b + "norm3.b"], ln, rows=T, c=ch)
+        ff = self._buf("tr.ff", T * 4 * ch)
+        ops.gemm_conv(ln, W[b + "ff1.w"], ff, n_img=1, h=1, w=T, c0=ch, n_out=8 * ch, bias=W[b + "ff1.b"], epilogue=CPD_EPI_GEGLU)
+        ops.gemm_conv(ff, W[b + "ff2.w"], hcur, n_img=1, h=1, w=T, c0=4 * ch, n_out=ch, bias=W[b + "ff2.b"], residual=hcur,
+                      ld_res=ch)
+        out = self._buf(p + "out", T * ch)
+        ops.gemm_conv(hcur, W[p + "proj_out.w"], out, n_img=1, h=1, w=T, c0=ch, n_out=ch, bias=W[p + "proj_out.b"],
+                      residual=x, ld_res=ch)
+        return out
+
+    def _run_block(self, prefix, layers, hcur, skip, R, h, w, emb_all, emb_stride, stats):
+        """Returns (tensor, channels, h, w).  `skip` = (tensor, channels) second source of the first ResBlock or None."""
+        W = self.w
+        ch = None
+        for j, l in enumerate(layers):
+            p = f"{prefix}{j}."
+            if l[0] == "res":
+                if skip is not None and j == 0:
+                    hcur = self._res(p, hcur, skip[0], l[3], l[4], l[2], R, h, w, emb_all, emb_stride, stats)
+                else:
+                    hcur = self._res(p, hcur, None, l[1], 0, l[2], R, h, w, emb_all, emb_stride, stats)
+                ch = l[2]
+            elif l[0] == "attn":
+                hcur = self._attn(p, hcur, l[1], R, h, w, stats)
+                ch = l[1]
+            elif l[0] == "down":
+                ch = l[1]
+                out = self._buf(p + "out", R * (h // 2) * (w // 2) * ch)
+                ops.gemm_conv(hcur, W[p + "w"], out, n_img=R, h=h, w=w, c0=ch, n_out=ch, ksize=3, stride=2, bias=W[p + "b"])
+                hcur, h, w = out, h // 2, w // 2
+            elif l[0] == "up":
+                ch = l[1]
+                up = self._buf("up", R * 4 * h * w * ch)
+                ops.upsample2x(hcur, up, n=R, h=h, w=w, c=ch)
+                h, w = 2 * h, 2 * w
+                out = self._buf(p + "out", R * h * w * ch)
+                ops.gemm_conv(up, W[p + "w"], out, n_img=R, h=h, w=w, c0=ch, n_out=ch, ksize=3, bias=W[p + "b"])
+                hcur = out
+        return hcur, ch, h, w
+
+    # ---- forward ---------------------------------------------------------------------------------------
+    def _embeddings(self, t_rows):
+        """t_rows: fp32 device tensor [m] (already rounded to the model dtype).  Returns fp32 [m, emb_total]."""
+        W = self.w
+        m = t_rows.numel()
+        mc, ted = self.model_channels, self.ted
+        temb = self._buf("temb", m * mc)
+        ops.timestep_embedding(t_rows, temb, dim=mc, round_t_bf16=False)
+        e1 = self._buf("e1", m * ted)
+        ops.small_linear(temb, W["te0.w"], W["te0.b"], m=m, k=mc, n=ted, out_bf16=e1)
+        emb = self._buf("emb", m * ted)
+        ops.small_linear(e1, W["te2.w"], W["te2.b"], m=m, k=ted, n=ted, silu_in=True, out_bf16=emb)
+        emb_all = self._buf("emb_all", m * self.emb_total, torch.float32)
+        ops.small_linear(emb, W["emb_all.w"], W["emb_all.b"], m=m, k=ted, n=self.emb_total, silu_in=True, out_f32=emb_all)
+        return emb_all
+
+    def _forward_impl(self, x, scale, rows_per_image, t_rows, shared_t, return_skips=False):
+        W = self.w
+        B, cin, h, w = x.shape
+        R = B * rows_per_image
+        stats = self._buf("gn.stats", R * 64, torch.float64)
+        emb_all = self._embeddings(t_rows)
+        emb_stride = 0 if shared_t else self.emb_total
+        mc = self.model_channels
+        h0 = self._buf("input_blocks.0.out", R * h * w * mc)
+        ops.conv_in(x, W["input_blocks.0.0.w"], W["input_blocks.0.0.b"], h0, n=B, cin=cin, h=h, w=w, cout=mc, scale=scale,
+                    rows_per_image=rows_per_image)
+        hs = [(h0, mc, h, w)]
+        hcur, ch = h0, mc
+        for i, layers in enumerate(self.inputs[1:], start=1):
+            hcur, ch, h, w = self._run_block(f"input_blocks.{i}.", layers, hcur, None, R, h, w, emb_all, emb_stride, stats)
+            hs.append((hcur, ch, h, w))
+        hcur, ch, h, w = self._run_block("middle_block.", self.middle, hcur, None, R, h, w, emb_all, emb_stride, stats)
+        skips = []
+        for i, layers in enumerate(self.outputs):
+            s, sc, sh, sw = hs.pop()
+            assert (sh, sw) == (h, w)
+            if return_skips:
+                skips.append(s.view(R, sh, sw, sc).permute(0, 3, 1, 2))
+            hcur, ch, h, w = self._run_block(f"output_blocks.{i}.", layers, hcur, (s, sc), R, h, w, emb_all, emb_stride, stats)
+        gn = self._buf("gn", R * h * w * ch)
+        ops.groupnorm(hcur, W["out.gn.g"], W["out.gn.b"], gn, stats, n_img=R, hw=h * w, c0=ch, eps=1e-5, silu=True)
+        cout = self.cfg["out_channels"]
+        out = self._buf("eps", R * cout * h * w).view(R, cout, h, w)
+        ops.conv_out(gn, W["out.w"], W["out.b"], out, n=R, h=h, w=w, cin=ch, cout=cout)
+        return (out, skips) if return_skips else out
+
+    @torch.no_grad()
+    def forward_rows(self, x, c_in, t, rows_per_image):
+        """Fast path used by the Denoiser: x [B,4,h,w] fp32 (unscaled), every image is evaluated on
+        `rows_per_image` conditioning rows sharing x * c_in and the timestep t (denoiser.py:383-393).
+        Returns eps rows [B*rows_per_image, 4, h, w] bf16, image-major."""
+        t_rows = torch.full((1,), float(t), dtype=torch.float32, device=self.device)
+        return self._forward_impl(x.contiguous(), float(c_in), rows_per_image, t_rows, shared_t=True)
+
+    @torch.no_grad()
+    def forward(self, x, timesteps=None, context=None, y=None, **kwargs):
+        """Reference call signature (unet.py:765): x [N,4,h,w], timesteps [N], context [N or Rc, tokens, D].
+        Returns out [N,4,h,w] (bf16) or (out, skips) when return_attn=True (the 12 skip tensors, unet.py:802-804)."""
+        if y is not None:
+            raise NotImplementedError("class-conditional UNets are not on the hot path")
+        for k in ("inject_feats", "inject_attns", "return_feat"):
+            if kwargs.get(k):
+                raise NotImplementedError(f"UNetModel kwarg {k!r} is outside the hot-path scope")
+        if context is not None:
+            self.set_context(context)
+        n = x.shape[0]
+        x = x.to(self.device, torch.float32).contiguous()
+        t_rows = torch.as_tensor(timesteps).to(self.device, torch.float32).reshape(-1).contiguous()
+        if t_rows.numel() != n:
+            raise ValueError("timesteps must have one entry per row of x")
+        if n > 32:
+            raise NotImplementedError("more than 32 rows with distinct timesteps: use forward_rows")
+        return self._forward_impl(x, 1.0, 1, t_rows, shared_t=False, return_skips=bool(kwargs.get("return_attn", False)))
+
+    __call__ = forward

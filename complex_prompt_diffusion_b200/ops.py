@@ -1,0 +1,175 @@
+"""Thin torch-tensor wrappers over the C ABI (include/cpd_b200.h).  Device memory and the current CUDA
+stream come from torch; all arithmetic happens in libcpd_b200.so.  No fallbacks."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (AttnParams, GemmParams, StepParams, check, load, ptr, stream_ptr, CPD_BF16, CPD_F32, DTYPE_CODE,
+                   CPD_EPI_NONE, CPD_EPI_GEGLU, CPD_MAX_SUBPROMPTS)
+
+
+def _req(t, dtype, name):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (the hot path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+
+
+def sampler_step(eps, x, *, n_sub, weights, mask_scalars, masks, guidance, sampler, pred_type, sigma_hat, v_c_eps=0.0,
+                 v_c_x_div=1.0, dt=0.0, sigma_up=0.0, dpm_ratio=0.0, dpm_expm1=0.0, dpm_c1=0.0, dpm_c2=0.0, dpm_first=1,
+                 write_old=0, old_denoised=None, noise=None, denoised_out=None, eps_out=None):
+    """eps: [n_images * (1 + n_sub), 4, h, w] (image-major rows); x: [n_images, 4, h, w] fp32, updated in place."""
+    _req(x, torch.float32, "x")
+    _req(old_denoised, torch.float32, "old_denoised")
+    _req(noise, torch.float32, "noise")
+    _req(denoised_out, torch.float32, "denoised_out")
+    _req(eps_out, torch.float32, "eps_out")
+    if not eps.is_cuda or not eps.is_contiguous() or eps.dtype not in DTYPE_CODE:
+        raise RuntimeError("eps must be a contiguous CUDA tensor of dtype fp32/fp16/bf16")
+    n_images = x.shape[0]
+    L = x[0].numel() if n_images else eps[0].numel()
+    R = 1 + n_sub
+    if eps.numel() != n_images * R * L:
+        raise RuntimeError(f"eps has {eps.numel()} elements, expected {n_images}*{R}*{L}")
+    if n_sub < 1 or n_sub > CPD_MAX_SUBPROMPTS:
+        raise RuntimeError(f"n_sub={n_sub} out of range")
+    p = StepParams()
+    p.eps = eps.data_ptr()
+    p.eps_dtype = DTYPE_CODE[eps.dtype]
+    p.eps_image_stride = R * L
+    p.eps_row_stride = L
+    p.x = x.data_ptr()
+    p.old_denoised = old_denoised.data_ptr() if old_denoised is not None else None
+    p.noise = noise.data_ptr() if noise is not None else None
+    p.denoised_out = denoised_out.data_ptr() if denoised_out is not None else None
+    p.eps_out = eps_out.data_ptr() if eps_out is not None else None
+    p.n_images, p.n_sub, p.hw = n_images, n_sub, L // 4
+    for k in range(n_sub):
+        p.weights[k] = float(weights[k])
+        p.mask_scalar[k] = float(mask_scalars[k])
+        m = masks[k] if masks is not None else None
+        if m is not None:
+            _req(m, torch.float32, f"masks[{k}]")
+            if m.numel() != L // 4:
+                raise RuntimeError(f"masks[{k}] must have {L // 4} elements")
+            p.masks[k] = m.data_ptr()
+        else:
+            p.masks[k] = None
+    p.guidance = float(guidance)
+    p.sampler, p.pred_type = int(sampler), int(pred_type)
+    p.sigma_hat, p.v_c_eps, p.v_c_x_div, p.dt, p.sigma_up = float(sigma_hat), float(v_c_eps), float(v_c_x_div), float(dt), float(sigma_up)
+    p.dpm_ratio, p.dpm_expm1, p.dpm_c1, p.dpm_c2 = float(dpm_ratio), float(dpm_expm1), float(dpm_c1), float(dpm_c2)
+    p.dpm_first, p.write_old = int(dpm_first), int(write_old)
+    check(load().cpd_sampler_step(C.byref(p), stream_ptr()), "cpd_sampler_step")
+    return x
+
+
+def gemm_conv(a0, wt, out, *, n_img, h, w, c0, n_out, a1=None, c1=0, ksize=1, stride=1, bias=None, rowvec=None,
+              rowvec_stride=0, residual=None, ld_res=0, ldd=None, epilogue=CPD_EPI_NONE, variant=0, m_valid=0):
+    _req(a0, torch.bfloat16, "a0")
+    _req(a1, torch.bfloat16, "a1")
+    _req(wt, torch.bfloat16, "wt")
+    _req(out, torch.bfloat16, "out")
+    _req(bias, torch.float32, "bias")
+    _req(rowvec, torch.float32, "rowvec")
+    if residual is not None and (not residual.is_cuda or residual.dtype != torch.bfloat16):
+        raise RuntimeError("residual must be a CUDA bf16 tensor")
+    p = GemmParams()
+    p.a0, p.a1, p.c0, p.c1 = a0.data_ptr(), (a1.data_ptr() if a1 is not None else None), c0, c1
+    p.n_img, p.h_in, p.w_in, p.ksize, p.stride = n_img, h, w, ksize, stride
+    p.wt, p.n_out = wt.data_ptr(), n_out
+    p.bias = bias.data_ptr() if bias is not None else None
+    p.rowvec = rowvec.data_ptr() if rowvec is not None else None
+    p.rowvec_stride = rowvec_stride
+    p.residual = residual.data_ptr() if residual is not None else None
+    p.ld_res = ld_res
+    p.d = out.data_ptr()
+    p.ldd = ldd if ldd is not None else (n_out // 2 if epilogue == CPD_EPI_GEGLU else n_out)
+    p.epilogue, p.variant, p.m_valid = epilogue, variant, m_valid
+    check(load().cpd_gemm_conv(C.byref(p), stream_ptr()), "cpd_gemm_conv")
+    return out
+
+
+def groupnorm(a0, gamma, beta, out, stats, *, n_img, hw, c0, a1=None, c1=0, eps=1e-5, silu=True):
+    _req(a0, torch.bfloat16, "a0")
+    _req(a1, torch.bfloat16, "a1")
+    _req(gamma, torch.float32, "gamma")
+    _req(beta, torch.float32, "beta")
+    _req(out, torch.bfloat16, "out")
+    _req(stats, torch.float64, "stats")
+    if stats.numel() < n_img * 64:
+        raise RuntimeError("stats scratch too small")
+    check(load().cpd_groupnorm(ptr(a0), ptr(a1), c0, c1, n_img, hw, ptr(gamma), ptr(beta), float(eps), int(silu), ptr(stats),
+                               ptr(out), stream_ptr()), "cpd_groupnorm")
+    return out
+
+
+def layernorm(x, gamma, beta, out, *, rows, c, eps=1e-5):
+    _req(x, torch.bfloat16, "x")
+    _req(gamma, torch.float32, "gamma")
+    _req(beta, torch.float32, "beta")
+    _req(out, torch.bfloat16, "out")
+    check(load().cpd_layernorm(ptr(x), rows, c, ptr(gamma), ptr(beta), float(eps), ptr(out), stream_ptr()), "cpd_layernorm")
+    return out
+
+
+def timestep_embedding(t, out, *, dim, round_t_bf16=True):
+    _req(t, torch.float32, "t")
+    _req(out, torch.bfloat16, "out")
+    check(load().cpd_timestep_embedding(ptr(t), t.numel(), dim, int(round_t_bf16), ptr(out), stream_ptr()), "cpd_timestep_embedding")
+    return out
+
+
+def small_linear(x, w, b, *, m, k, n, silu_in=False, out_f32=None, out_bf16=None, ld_out=None):
+    _req(x, torch.bfloat16, "x")
+    _req(w, torch.bfloat16, "w")
+    _req(b, torch.float32, "b")
+    _req(out_f32, torch.float32, "out_f32")
+    _req(out_bf16, torch.bfloat16, "out_bf16")
+    check(load().cpd_small_linear(ptr(x), m, k, ptr(w), ptr(b), n, int(silu_in), ptr(out_f32), ptr(out_bf16),
+                                  ld_out if ld_out is not None else n, stream_ptr()), "cpd_small_linear")
+
+
+def conv_in(x, wt, bias, out, *, n, cin, h, w, cout, scale=1.0, rows_per_image=1):
+    _req(x, torch.float32, "x")
+    _req(wt, torch.bfloat16, "wt")
+    _req(bias, torch.float32, "bias")
+    _req(out, torch.bfloat16, "out")
+    check(load().cpd_conv_in(ptr(x), n, cin, h, w, ptr(wt), ptr(bias), cout, float(scale), int(rows_per_image), ptr(out),
+                             stream_ptr()), "cpd_conv_in")
+    return out
+
+
+def conv_out(a, wt, bias, out, *, n, h, w, cin, cout):
+    _req(a, torch.bfloat16, "a")
+    _req(wt, torch.bfloat16, "wt")
+    _req(bias, torch.float32, "bias")
+    if out.dtype not in (torch.bfloat16, torch.float32) or not out.is_cuda:
+        raise RuntimeError("out must be a CUDA bf16/fp32 tensor")
+    check(load().cpd_conv_out(ptr(a), n, h, w, cin, ptr(wt), ptr(bias), cout, ptr(out), DTYPE_CODE[out.dtype], stream_ptr()),
+          "cpd_conv_out")
+    return out
+
+
+def upsample2x(a, out, *, n, h, w, c):
+    _req(a, torch.bfloat16, "a")
+    _req(out, torch.bfloat16, "out")
+    check(load().cpd_upsample2x(ptr(a), n, h, w, c, ptr(out), stream_ptr()), "cpd_upsample2x")
+    return out
+
+
+def attention(q, k, vt, o, *, ldq, ldk, ldvt, ldo, batch, heads, nq, nk, nk_pad, dpad, scale, kv_batch=0):
+    for t, nme in ((q, "q"), (k, "k"), (vt, "vt"), (o, "o")):
+        if not t.is_cuda or t.dtype != torch.bfloat16:
+            raise RuntimeError(f"{nme} must be a CUDA bf16 tensor")
+    p = AttnParams()
+    p.q, p.ldq, p.k, p.ldk, p.vt, p.ldvt, p.o, p.ldo = q.data_ptr(), ldq, k.data_ptr(), ldk, vt.data_ptr(), ldvt, o.data_ptr(), ldo
+    p.batch, p.heads, p.nq, p.nk, p.nk_pad, p.dpad, p.scale = batch, heads, nq, nk, nk_pad, dpad, float(scale)
+    p.kv_batch = kv_batch
+    check(load().cpd_attention(C.byref(p), stream_ptr()), "cpd_attention")
+    return o

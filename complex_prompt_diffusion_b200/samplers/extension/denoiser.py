@@ -1,0 +1,149 @@
+"""Denoiser: composable multi-prompt classifier-free guidance around the UNet.
+
+Mirror of the reference interface `cpd/samplers/extension/denoiser.py` (`Denoiser(unet, vae, tokenizer,
+clip_model, decode, quantize=False, **kw)`, `forward(x, sigma, **kw) -> denoised`, `.scheduler`), keeping the
+kwargs names of SURVEY.md Appendix B.  The arithmetic after the UNet call - the fp16 weighted delta
+(:450-460), e_t = e_u + s * sum (:510-515), eps/v -> denoised (:533-542) - and the sampler update that
+follows it run as ONE CUDA kernel (`cpd_sampler_step`); nothing is computed on the CPU and no device->host
+synchronisation happens inside a step (the reference has five).
+
+Differences that are deliberate repairs of reference defects: the image batch may be > 1 and
+means B independent batch-1 trajectories (D7); sigma is passed once (D3); no hard-coded `.cuda()` (D6).
+Branches that are outside the hot-path scope (attention guidance, CLIP guidance, score correctors, dynamic
+scale clipping, unconditional blur, feature/attention injection, depth masks, gamma > 0) raise
+NotImplementedError when requested instead of being silently ignored.
+"""
+import math
+
+import torch
+
+from ... import ops
+from ..._lib import CPD_DPMPP_2M, CPD_EULER, CPD_EULER_ANCESTRAL, CPD_PRED_EPSILON, CPD_PRED_VELOCITY
+from ...scheduler.discrete import SigmaScheduler
+
+CPD_DENOISE_ONLY = 3
+
+_UNSUPPORTED_TRUTHY = ("attn_guide", "return_attn", "clip_guidance", "score_corrector", "scaled_clip", "dynamic_scale_clip",
+                       "unconditional_guidance_blur", "inject_feats", "inject_attns", "depth_mask")
+
+
+class ConditioningPlan:
+    """The conditioning dict {"and": [(scale, emb, guide, mask)...], "not": [...]} (prompts.py:622-648) flattened
+    into what the kernels need: context rows [1 + N, 77, D] (row 0 = unconditional), per-sub-prompt weights
+    rounded to the model dtype (P4: scale is moved to the UNet dtype before the fp16 cast, denoiser.py:373-381)
+    and masks (scalar or [hw] fp32 device tensors holding model-dtype-rounded values)."""
+
+    def __init__(self, c, uc, dtype, device, hw_shape):
+        if not isinstance(c, dict) or "and" not in c:
+            raise ValueError("conditioning must be a dict with an 'and' list (CompositionalPrompt._build_embeddings)")
+        if uc is None:
+            raise ValueError("unconditional_conditioning is required")
+        entries = [(s, f, m) for (s, f, _g, m) in c["and"]] + [(-s, f, m) for (s, f, _g, m) in c.get("not", [])]
+        if not 1 <= len(entries) <= ops.CPD_MAX_SUBPROMPTS:
+            raise ValueError(f"between 1 and {ops.CPD_MAX_SUBPROMPTS} weighted sub-prompts are supported, got {len(entries)}")
+        self.n_sub = len(entries)
+        self.weights, self.mask_scalars, self.masks = [], [], []
+        factors = [torch.as_tensor(uc)]
+        h, w = hw_shape
+        for scale, factor, mask in entries:
+            factors.append(torch.as_tensor(factor))
+            self.weights.append(float(torch.tensor([float(scale)]).to(dtype).float()))
+            if isinstance(mask, (int, float)):
+                self.mask_scalars.append(float(torch.tensor([float(mask)]).to(dtype).float()))
+                self.masks.append(None)
+            else:
+                m = torch.as_tensor(mask)
+                if m.numel() == 1:
+                    self.mask_scalars.append(float(m.reshape(1).to(dtype).float()))
+                    self.masks.append(None)
+                else:
+                    if m.numel() != h * w:
+                        raise ValueError(f"mask must be [1,1,{h},{w}] (prompts.py:855), got {tuple(m.shape)}")
+                    self.mask_scalars.append(1.0)
+                    self.masks.append(m.reshape(h * w).to(dtype).float().contiguous().to(device))
+        for f in factors:
+            if f.ndim != 3 or f.shape[0] != 1:
+                raise ValueError(f"each embedding must be [1, tokens, dim], got {tuple(f.shape)}")
+        self.context = torch.cat([f.to(device) for f in factors]).contiguous()  # [1 + N, tokens, D]
+
+
+class Denoiser(torch.nn.Module):
+    def __init__(self, unet, vae=None, tokenizer=None, clip_model=None, decode=None, quantize=False, **kwargs):
+        super().__init__()
+        self.name = kwargs.get("name", "Denoiser")
+        p = next(iter(unet.parameters()))
+        self.dtype, self.device = p.dtype, p.device
+        if self.device.type != "cuda":
+            raise RuntimeError("Denoiser needs a UNet on a CUDA device: the hot path has no CPU fallback")
+        self.scheduler = SigmaScheduler(num_train_timesteps=1000, **kwargs)
+        self.quantize = quantize
+        self.sigma_data = 1.0
+        self.unet, self.vae, self.tokenizer, self.clip_model, self.decode = unet, vae, tokenizer, clip_model, decode
+        self._plan_key, self._plan = None, None
+
+    # ---- host-side (once per sample() call) -----------------------------------------------------------
+    def _check_kwargs(self, kwargs):
+        for key in _UNSUPPORTED_TRUTHY:
+            v = kwargs.get(key, None)
+            if v is not None and v is not False:
+                raise NotImplementedError(f"Denoiser kwarg {key!r} is outside the B200 hot-path scope (SURVEY.md 8-f)")
+        if kwargs.get("gamma", 0):
+            raise NotImplementedError("gamma > 0 is not supported (the reference branch is defective, SURVEY.md D8)")
+        if kwargs.get("pred_type", "epsilon") not in ("epsilon", "velocity"):
+            raise ValueError(f"unknown pred_type {kwargs.get('pred_type')!r}")
+
+    def plan_conditioning(self, c, uc, hw_shape):
+        if isinstance(c, list):
+            raise NotImplementedError("per-step conditioning lists are not supported")
+        key = (id(c), id(uc), tuple(hw_shape))
+        if self._plan_key != key:
+            self._plan = ConditioningPlan(c, uc, self.dtype, self.device, hw_shape)
+            self._plan_key = key
+            self.unet.set_context(self._plan.context)
+        return self._plan
+
+    @staticmethod
+    def guidance_scale(**kwargs):
+        """unconditional_guidance_scale with the optional log decay of denoiser.py:475-494."""
+        s = kwargs.get("unconditional_guidance_scale", 1.0)
+        t_idx, total = kwargs.get("t_idx", 0), kwargs.get("total_steps", 1000)
+        if kwargs.get("decaying_uc_scale", False):
+            start = kwargs.get("decaying_uc_scale_start", int(total * 0.2))
+            if start < t_idx:
+                start = min(t_idx, start)
+                s = max(kwargs.get("decaying_uc_scale_min", 2), s - s * (math.log(t_idx + 1 - start) / math.log(total)))
+        return float(s)
+
+    # ---- device-side --------------------------------------------------------------------------------
+    def unet_rows(self, x, sigma, plan):
+        """Run the UNet on the (1 + N) conditioning rows of every image: returns eps rows [B*(1+N), 4, h, w]
+        (image-major).  x: [B,4,h,w] fp32; sigma: 0-dim/1-element fp32 CPU tensor (same for all images)."""
+        sig = torch.as_tensor(sigma, dtype=torch.float32).reshape(-1)[:1].cpu()
+        c_in = 1 / (sig ** 2 + 1 ** 2) ** 0.5  # get_scalings, fp32 like denoiser.py:390
+        t = self.scheduler.sigma_to_t(sig).to(self.dtype).float()  # fp64 -> model dtype (P3, denoiser.py:393)
+        return self.unet.forward_rows(x, float(c_in), float(t), rows_per_image=1 + plan.n_sub)
+
+    def fused_step(self, x, sigma, plan, step, **kwargs):
+        """One UNet evaluation + ONE fused kernel: CFG combine, denoised, sampler update (x updated in place).
+        `step` is a dict of the fp32 scalars for cpd_sampler_step."""
+        eps = self.unet_rows(x, sigma, plan)
+        sig = float(torch.as_tensor(sigma, dtype=torch.float32).reshape(-1)[0])
+        sig_t = torch.tensor([sig], dtype=torch.float32)
+        pred = CPD_PRED_VELOCITY if kwargs.get("pred_type", "epsilon") == "velocity" else CPD_PRED_EPSILON
+        ops.sampler_step(eps, x, n_sub=plan.n_sub, weights=plan.weights, mask_scalars=plan.mask_scalars, masks=plan.masks,
+                         guidance=self.guidance_scale(**kwargs), pred_type=pred, sigma_hat=sig,
+                         v_c_eps=float(-sig_t / (sig_t ** 2 + 1) ** 0.5), v_c_x_div=float(sig_t ** 2 + 1), **step)
+        return x
+
+    @torch.no_grad()
+    def forward(self, x, sigma, **kwargs):
+        """Reference-compatible entry point: returns the denoised sample for x:[B,4,h,w] (fp32)."""
+        if x.ndim != 4 or x.shape[1] != 4:
+            raise ValueError(f"[denoiser] `x` has incorrect shape: {tuple(x.shape)}")
+        self._check_kwargs(kwargs)
+        x = x.to(self.device, torch.float32).contiguous()
+        plan = self.plan_conditioning(kwargs.get("conditioning"), kwargs.get("unconditional_conditioning"), x.shape[-2:])
+        denoised = torch.empty_like(x)
+        scratch = x.clone()
+        self.fused_step(scratch, sigma, plan, dict(sampler=CPD_DENOISE_ONLY, denoised_out=denoised), **kwargs)
+        return denoised

@@ -1,0 +1,72 @@
+"""KDiffusionSampler: schedule, initial noise scaling and dispatch to the per-sampler loop
+(interface of cpd/samplers/k_diffusion.py:22-97).
+
+All per-step scalars are computed once on the host with the same fp32 torch expressions the reference
+evaluates on 0-dim tensors, then each step is one UNet evaluation plus one fused CUDA kernel
+(`Denoiser.fused_step`).  B images are B independent trajectories sharing the schedule.
+"""
+import torch
+
+from .extension.denoiser import Denoiser
+
+
+class KDiffusionSampler:
+    def __init__(self, model, name="sample_heun"):
+        self.name = name
+        self.denoiser = Denoiser(model["unet"], model.get("vae"), model.get("tokenizer"), model.get("clip_new_model"),
+                                 model.get("decode"))
+
+    # ---- schedule helpers ----------------------------------------------------------------------------
+    def _sigmas(self, steps, kwargs):
+        sigmas = self.denoiser.scheduler.get_sigmas(kwargs.get("scheduler", "default"), steps, **kwargs)
+        # The "linear"/"default" schedule is fp64 in the reference; its Euler loops then promote x to fp64 and
+        # crash in the UNet (defect D9, see oracle/make_golden.py), DPM++ 2M keeps x fp32.  Here the loop always
+        # runs on fp32 scalars.
+        return sigmas
+
+    def sample(self, steps, batch_size, shape, **kwargs):
+        dev = self.denoiser.device
+        decode = kwargs.get("decode", False)
+        x_T = kwargs.get("x_T", None)
+        sigmas = self._sigmas(steps, kwargs)
+        if decode:  # img2img: truncated schedule, x_T is the encoded image (k_diffusion.py:64-70)
+            strength = kwargs.get("denoising_strength", 0.0)
+            t_enc = int((1 - min(strength, 0.999)) * steps)
+            sigmas = sigmas[steps - t_enc - 1:]
+            noise = torch.randn([batch_size] + list(shape))
+            x = x_T.to(dev, torch.float32) + (noise * sigmas[0]).to(dev, torch.float32)
+        else:
+            if x_T is None:
+                x_T = torch.randn([batch_size] + list(shape))
+            x = (x_T.to("cpu", torch.float32) * sigmas[0]).to(torch.float32).to(dev) if not x_T.is_cuda \
+                else (x_T.float() * sigmas[0].to(dev)).float()
+        kwargs["total_steps"] = len(sigmas)
+        return self._sampling(x.contiguous(), sigmas, model_args=kwargs, disable=kwargs.get("silent", False), **kwargs)
+
+    def sample_img2img(self, x, noise, steps, **kwargs):
+        dev = self.denoiser.device
+        strength = kwargs.get("denoising_strength", 0.0)
+        t_enc = int((1 - min(strength, 0.999)) * steps)
+        sigmas = self._sigmas(steps, kwargs)
+        xi = x.to(dev, torch.float32) + (noise.cpu().float() * sigmas[steps - t_enc - 1]).to(dev, torch.float32)
+        sched = sigmas[steps - t_enc - 1:]
+        kwargs["total_steps"] = len(sched)
+        return self._sampling(xi.contiguous(), sched, model_args=kwargs, disable=not kwargs.get("verbose", False), **kwargs)
+
+    # ---- shared loop plumbing -------------------------------------------------------------------------
+    def _begin(self, x, model_args, kwargs):
+        if kwargs.get("clip_sample", False):
+            raise NotImplementedError("clip_sample thresholding is a 'next' row (SURVEY.md 8-f), not built yet")
+        if kwargs.get("s_churn", 0.0):
+            raise NotImplementedError("s_churn > 0 is not supported (gamma = 0 path only)")
+        den = self.denoiser
+        den._check_kwargs(model_args)
+        plan = den.plan_conditioning(model_args.get("conditioning"), model_args.get("unconditional_conditioning"), x.shape[-2:])
+        return den, plan
+
+    def _callback(self, callback, x_before, i, sigma, denoised):
+        if callback is not None:
+            callback({"x": x_before, "i": i, "sigma": sigma, "sigma_hat": sigma, "eps": denoised})
+
+    def _sampling(self, x, sigmas, model_args=None, **kwargs):
+        raise NotImplementedError()

@@ -1,0 +1,188 @@
+/*
+ * cpd_b200.h - C ABI of libcpd_b200.so: the B200 (sm_100a) kernels behind the denoising-loop hot path
+ * of milesgray/complex_prompt_diffusion (reference paths below are relative to /root/reference).
+ *
+ * The reference is pure Python/PyTorch and has no FFI; the boundary these entry points replace is the
+ * set of torch calls made by
+ *   cpd/samplers/extension/denoiser.py:450-463,508-515,528-544   (CFG combine, eps/v -> denoised)
+ *   cpd/samplers/euler.py:47-54,83-92 and cpd/samplers/dpmpp.py:39-54 (sampler updates)
+ *   cpd/models/unet.py:765-831 + attention.py + models/util.py    (UNet forward)
+ * and the binding a reference maintainer adds is the ctypes stub shown in INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes only (no torch types); every pointer is a DEVICE pointer unless
+ * stated otherwise; `stream` is a cudaStream_t passed as void*; every function returns 0 on success or a
+ * non-zero cpd_status and never throws; cpd_last_error() describes the last failure of the calling thread.
+ * No function allocates device memory or synchronises the device.
+ */
+#ifndef CPD_B200_H
+#define CPD_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int cpd_status; /* 0 = ok, 1 = invalid argument, 2 = CUDA error, 3 = unsupported */
+
+const char* cpd_last_error(void);
+int cpd_abi_version(void);
+
+/* dtypes of eps buffers */
+enum { CPD_F32 = 0, CPD_F16 = 1, CPD_BF16 = 2 };
+/* sampler kinds (registry names "Euler", "Euler Ancestral", "DPM++ 2m") */
+enum { CPD_EULER = 0, CPD_EULER_ANCESTRAL = 1, CPD_DPMPP_2M = 2,
+       CPD_DENOISE_ONLY = 3 /* Denoiser.forward alone: x is not updated, denoised_out receives the sample */ };
+/* prediction type (denoiser.py:537-542) */
+enum { CPD_PRED_EPSILON = 0, CPD_PRED_VELOCITY = 1 };
+
+#define CPD_MAX_SUBPROMPTS 16
+
+/*
+ * Fused multi-prompt CFG combine + eps/v -> denoised + sampler update: ONE pass over the latents.
+ * Replaces denoiser.py:450-460 (fp16 weighted delta), :510-515 (e_t = e_u + s * sum), :533-542
+ * (denoised), and the update of euler.py:49-54 / euler.py:85-92 / dpmpp.py:42-54.
+ *
+ * eps holds the UNet outputs for `n_images` images x (1 + n_sub) rows x L elements
+ * (L = 4 * hw); row 0 of each image is the unconditional row.  Element (b, r, i) lives at
+ * eps + (b * eps_image_stride + r * eps_row_stride + i) elements.
+ * All scalars are the fp32 values the reference computes on 0-dim tensors (host-side, see
+ * complex_prompt_diffusion_b200/samplers/k_diffusion.py).
+ */
+typedef struct {
+  const void* eps;
+  int eps_dtype;            /* CPD_F32 / CPD_F16 / CPD_BF16 */
+  int64_t eps_image_stride; /* elements */
+  int64_t eps_row_stride;   /* elements */
+  float* x;                 /* [n_images][L] in/out, fp32 (k_diffusion.py:73-74 keeps x fp32) */
+  float* old_denoised;      /* [n_images][L] in/out, DPM++ 2M history; may be NULL otherwise */
+  const float* noise;       /* [n_images][L] ancestral noise (euler.py:92); NULL otherwise */
+  float* denoised_out;      /* optional [n_images][L] copy of the denoised sample (callback 'eps'), or NULL */
+  float* eps_out;           /* optional [n_images][L] combined e_t (fp32), or NULL */
+  int n_images;
+  int n_sub;                /* N weighted sub-prompts (conjunctions + negations), 1..CPD_MAX_SUBPROMPTS */
+  int hw;                   /* latent pixels per channel; L = 4 * hw */
+  float weights[CPD_MAX_SUBPROMPTS];     /* scale (negated for "not"), ALREADY rounded to the model dtype (P4) */
+  float mask_scalar[CPD_MAX_SUBPROMPTS]; /* scalar mask value (1 when the sub-prompt has no mask) */
+  const float* masks[CPD_MAX_SUBPROMPTS];/* optional spatial mask [hw] per sub-prompt (broadcast over the 4 channels, */
+                                         /* values already rounded to the model dtype) or NULL */
+  float guidance;           /* unconditional_guidance_scale after optional decay (denoiser.py:475-494) */
+  int sampler;              /* CPD_EULER / CPD_EULER_ANCESTRAL / CPD_DPMPP_2M */
+  int pred_type;            /* CPD_PRED_EPSILON / CPD_PRED_VELOCITY */
+  float sigma_hat;          /* sigma_i * (gamma + 1), gamma = 0 */
+  float v_c_eps;            /* velocity: -sigma / (sigma^2 + 1)^0.5 */
+  float v_c_x_div;          /* velocity: sigma^2 + 1 (x is DIVIDED by it) */
+  float dt;                 /* Euler: sigma_{i+1} - sigma_hat; ancestral: sigma_down - sigma_i */
+  float sigma_up;           /* ancestral noise scale */
+  float dpm_ratio;          /* 2M: sigma_fn(t_next) / sigma_fn(t) */
+  float dpm_expm1;          /* 2M: (-h).expm1() */
+  float dpm_c1, dpm_c2;     /* 2M: (1 + 1/(2r)), 1/(2r) */
+  int dpm_first;            /* 2M: 1 when old_denoised is None or sigma_{i+1} == 0 (dpmpp.py:44) */
+  int write_old;            /* 2M: store denoised into old_denoised */
+} cpd_step_params;
+
+cpd_status cpd_sampler_step(const cpd_step_params* p, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * UNet building blocks (all activations NHWC bf16 = row-major [pixels, channels]).  The Python host
+ * (complex_prompt_diffusion_b200/models/unet.py) sequences them exactly like unet.py:765-831.
+ * --------------------------------------------------------------------------------------------------------- */
+
+/* Epilogue flags for cpd_gemm_conv */
+enum { CPD_EPI_NONE = 0, CPD_EPI_GEGLU = 1 };
+
+/*
+ * Implicit-GEMM convolution / GEMM on tcgen05 (TMEM accumulators, TMA-fed):
+ *   D[m, n] = sum_{tap, c} A[pixel(m) shifted by tap, c] * Wt[n, tap * C + c]  (+ bias[n]) (+ rowvec[img(m), n])
+ *             (+ residual[m, n])
+ * A is one or two NHWC bf16 tensors concatenated along channels (the UNet skip concat, unet.py:814):
+ * channels [0, c0) come from a0, [c0, c0 + c1) from a1 (c1 may be 0).  c0, c1 multiples of 64.
+ * ksize = 1 (plain GEMM / 1x1 conv, unet.py:247, attention.py:183-190,508-524) or 3 (pad 1; stride 1 or 2,
+ * unet.py:105,153-160,210,236).  Output pixels = n_img * (h_in/stride) * (w_in/stride).
+ * For a plain GEMM use n_img = 1, h_in = 1, w_in = M.
+ * wt: [n_out][ksize*ksize][c0 + c1] bf16 (K-major).  bias: fp32 [n_out] or NULL.
+ * rowvec: fp32, element (img, n) at rowvec[img * rowvec_stride + n] (time-embedding add, unet.py:266-274) or NULL.
+ * residual: bf16 [pixels][ld_res] or NULL.  d: bf16 [pixels][ldd].
+ * CPD_EPI_GEGLU: wt rows are interleaved per 128-column tile as [64 value rows | 64 gate rows]; d gets
+ * n_out/2 columns: value * gelu(gate) (attention.py:92-100).
+ */
+typedef struct {
+  const void* a0; const void* a1;
+  int c0, c1;
+  int n_img, h_in, w_in;
+  int ksize, stride;
+  const void* wt;
+  int n_out;
+  const float* bias;
+  const float* rowvec; int rowvec_stride;
+  const void* residual; int ld_res;
+  void* d; int ldd;
+  int epilogue;
+  int variant; /* 0 = auto; 1 = 128x128 tile (3 stages), 2 = 128x256 tile (4 stages) */
+  int m_valid; /* plain GEMM only: number of valid rows (<= w_in); 0 = all */
+} cpd_gemm_params;
+
+cpd_status cpd_gemm_conv(const cpd_gemm_params* p, void* stream);
+
+/*
+ * GroupNorm(32 groups) [+ SiLU] over NHWC bf16, fp32 statistics (models/util.py:95-105, attention.py:89-90).
+ * Input channels may come from two tensors (skip concat).  stats: fp64 scratch [n_img][32][2], zeroed by
+ * the call.  out: bf16 [n_img*hw][c0 + c1].
+ */
+cpd_status cpd_groupnorm(const void* a0, const void* a1, int c0, int c1, int n_img, int hw, const float* gamma,
+                         const float* beta, float eps, int silu, double* stats, void* out, void* stream);
+
+/* LayerNorm over the last dim of [rows][c] bf16 (attention.py:476-478), eps 1e-5. */
+cpd_status cpd_layernorm(const void* x, int rows, int c, const float* gamma, const float* beta, float eps, void* out,
+                         void* stream);
+
+/* Sinusoidal timestep embedding (models/util.py:65-85): t [rows] fp32 -> out bf16 [rows][dim], cos first.
+ * t is first rounded to the model dtype (bf16) as denoiser.py:393 does. */
+cpd_status cpd_timestep_embedding(const float* t, int rows, int dim, int round_t_bf16, void* out, void* stream);
+
+/* Small-M linear: out[m][n] = sum_k act(x[m][k]) * w[n][k] + b[n]; x bf16 [m][k], w bf16 [n][k], m <= 32.
+ * silu_in applies SiLU to x (unet.py:223-229 emb_layers).  out_f32 != NULL -> fp32 [m][ld_out];
+ * out_bf16 != NULL -> bf16 [m][ld_out]. */
+cpd_status cpd_small_linear(const void* x, int m, int k, const void* w, const float* b, int n, int silu_in,
+                            float* out_f32, void* out_bf16, int ld_out, void* stream);
+
+/* Input conv 3x3 (unet.py:548) fused with the Denoiser's input scaling and row broadcast (denoiser.py:390-391):
+ * x fp32 NCHW [n][cin][h][w]; every image is multiplied by `scale` (c_in, fp32), cast to bf16 (unet.py:794) and
+ * convolved; the result is written `rows_per_image` times (one copy per conditioning row), image-major:
+ * out bf16 NHWC [n * rows_per_image][h][w][cout]; w bf16 [cout][3][3][cin]; cin <= 8. */
+cpd_status cpd_conv_in(const float* x, int n, int cin, int h, int w, const void* wt, const float* bias, int cout,
+                       float scale, int rows_per_image, void* out, void* stream);
+
+/* Output conv 3x3 (unet.py:729-733): a bf16 NHWC [n][h][w][cin] (already GroupNorm+SiLU) -> out NCHW
+ * [n][cout][h][w] in out_dtype (CPD_BF16 or CPD_F32); cout <= 8. */
+cpd_status cpd_conv_out(const void* a, int n, int h, int w, int cin, const void* wt, const float* bias, int cout,
+                        void* out, int out_dtype, void* stream);
+
+/* Nearest 2x upsample of NHWC bf16 (unet.py:116). */
+cpd_status cpd_upsample2x(const void* a, int n, int h, int w, int c, void* out, void* stream);
+
+/*
+ * Fused flash-style attention on tcgen05 (attention.py:283-296,327,337,340,345-348), one launch for all
+ * (batch, head) pairs:  O = softmax(Q K^T * scale) V.
+ * q : bf16, row (b * nq + i) at q + row * ldq, head h at columns [h*dpad, h*dpad + dpad)   (pad columns zero)
+ * k : bf16, row (b * nk_pad + j) at k + row * ldk, same column layout
+ * vt: bf16 V transposed: row (h * dpad + c) at vt + row * ldvt, column (b * nk_pad + j)
+ * o : bf16, row (b * nq + i) at o + row * ldo, head h at columns [h*dpad, ...)
+ * nk = valid keys per batch (<= nk_pad); dpad multiple of 16, <= 160.
+ */
+typedef struct {
+  const void* q; int ldq;
+  const void* k; int ldk;
+  const void* vt; int ldvt;
+  void* o; int ldo;
+  int batch, heads, nq, nk, nk_pad, dpad;
+  float scale; /* dim_head ** -0.5 */
+  int kv_batch; /* number of distinct K/V batches: query batch b reads K/V batch (b % kv_batch); 0 = batch */
+} cpd_attn_params;
+
+cpd_status cpd_attention(const cpd_attn_params* p, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPD_B200_H */

@@ -1,0 +1,124 @@
+"""CPU-side tests: host logic of the drop-in package and the C ABI surface (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    path = os.path.join(ROOT, "complex_prompt_diffusion_b200", "libcpd_b200.so")
+    if not os.path.exists(path):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "complex_prompt_diffusion_b200", "csrc"), "-j8"], check=True)
+    return path
+
+
+def test_c_abi_exports_every_declared_symbol(lib_path):
+    header = open(os.path.join(ROOT, "include", "cpd_b200.h")).read()
+    declared = set(re.findall(r"\b(cpd_[a-z0-9_]+)\s*\(", header))
+    assert {"cpd_sampler_step", "cpd_gemm_conv", "cpd_attention", "cpd_groupnorm", "cpd_last_error"} <= declared
+    lib = ctypes.CDLL(lib_path)
+    for sym in declared:
+        assert hasattr(lib, sym), f"{sym} declared in include/cpd_b200.h but not exported"
+    from complex_prompt_diffusion_b200 import _lib
+    assert set(_lib.EXPORTED_SYMBOLS) == declared
+    assert _lib.load().cpd_abi_version() == 1
+
+
+def test_argument_validation_without_gpu(lib_path):
+    """Invalid arguments are rejected with a status code and a message before any CUDA call."""
+    from complex_prompt_diffusion_b200 import _lib
+    lib = _lib.load()
+    p = _lib.StepParams()
+    assert lib.cpd_sampler_step(ctypes.byref(p), None) != 0
+    assert b"eps and x" in lib.cpd_last_error()
+    gp = _lib.GemmParams()
+    gp.a0 = gp.wt = gp.d = 16
+    gp.c0 = 100
+    assert lib.cpd_gemm_conv(ctypes.byref(gp), None) != 0
+    assert b"multiples of 64" in lib.cpd_last_error()
+
+
+def test_registry_and_wrapper_surface():
+    from complex_prompt_diffusion_b200 import samplers
+    assert {"Euler", "Euler Ancestral", "DPM++ 2m"} <= set(samplers.lookup)
+    with pytest.raises(KeyError):
+        samplers.make({"name": "nope", "args": {}})
+    with pytest.raises(ValueError):
+        samplers.create(3)
+
+
+def test_product_has_no_cpu_fallback():
+    from complex_prompt_diffusion_b200.samplers.extension.denoiser import Denoiser
+
+    class CpuUNet:
+        def parameters(self):
+            return iter([torch.zeros(1)])
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Denoiser(CpuUNet())
+    from complex_prompt_diffusion_b200.models.unet import UNetModel
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        UNetModel(device="cpu")
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "complex_prompt_diffusion_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f"{f} imports the oracle"
+
+
+def test_schedule_matches_oracle_and_kats(golden_dir):
+    import json
+    from complex_prompt_diffusion_b200.scheduler import SigmaScheduler
+    from oracle.schedule import OracleSchedule
+    kat = json.load(open(os.path.join(golden_dir, "schedule_kat.json")))
+    s, o = SigmaScheduler(), OracleSchedule()
+    assert torch.equal(s.sigmas, o.sigmas)
+    for key, gs in kat["get_sigmas"].items():
+        alg, n = key.split("_")
+        sig = s.get_sigmas(alg, int(n))
+        assert sig.view(torch.int32 if sig.dtype == torch.float32 else torch.int64).tolist() == gs["bits"]
+        low, high = s.sigma_to_idx(sig[:-1])
+        assert low.tolist() == kat["sigma_to_t"][key]["low_idx"] and high.tolist() == kat["sigma_to_t"][key]["high_idx"]
+        assert [float(v) for v in s.sigma_to_t(sig[:-1])] == kat["sigma_to_t"][key]["t"]
+    # binary search == top-k on random, boundary and out-of-range sigmas (integer contract, bit-exact)
+    g = torch.Generator().manual_seed(0)
+    sig = torch.cat([torch.rand(2000, generator=g) * 16, s.sigmas[:50].float(), s.sigmas[-50:].float(),
+                     ((s.sigmas[:-1] + s.sigmas[1:]) / 2)[::37].float(), torch.tensor([0.0, 1e-6, 14.26, 20.0, 100.0])])
+    t_o, low_o, high_o = o.sigma_to_t_idx(sig)
+    low, high = s.sigma_to_idx(sig)
+    assert torch.equal(low, low_o) and torch.equal(high, high_o)
+    assert torch.equal(s.sigma_to_t(sig), t_o)
+
+
+def test_step_scalars_match_oracle_expressions():
+    from complex_prompt_diffusion_b200.samplers.dpmpp import dpmpp_2m_scalars
+    from complex_prompt_diffusion_b200.samplers.euler import get_ancestral_step
+    from oracle import samplers as OS
+    from oracle.schedule import OracleSchedule
+    sig = OracleSchedule().get_sigmas("karras", 8)
+    for i in range(8):
+        a, b = get_ancestral_step(sig[i], sig[i + 1])
+        c, d = OS.get_ancestral_step(sig[i], sig[i + 1])
+        assert float(a) == float(c) and float(b) == float(d)
+        ratio, em, c1, c2, first = dpmpp_2m_scalars(sig, i, have_history=i > 0)
+        t, tn = sig[i].log().neg(), sig[i + 1].log().neg()
+        assert ratio == float(tn.neg().exp() / t.neg().exp()) and em == float((-(tn - t)).expm1())
+        assert first == int(i == 0 or i == 7)
+
+
+def test_guidance_decay_matches_oracle():
+    from complex_prompt_diffusion_b200.samplers.extension.denoiser import Denoiser
+    from oracle.denoiser import guidance_scale
+    for t_idx in (0, 3, 5, 19):
+        a = Denoiser.guidance_scale(unconditional_guidance_scale=7.5, t_idx=t_idx, total_steps=21, decaying_uc_scale=True)
+        assert a == float(guidance_scale(7.5, t_idx, 21, True))

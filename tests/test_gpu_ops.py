@@ -1,0 +1,236 @@
+"""GPU parity of every C-ABI kernel against a plain torch fp32 reference of the same op.
+Run on a B200 with:  python -m pytest tests -m gpu"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from complex_prompt_diffusion_b200 import ops as o
+    o.load()
+    return o
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-20)).item()
+
+
+def bf(t):
+    return t.to(torch.bfloat16)
+
+
+DEV = "cuda"
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K,variant", [(128, 128, 64, 1), (256, 256, 128, 2), (384, 320, 320, 1), (1000, 1280, 640, 2),
+                                           (77 * 4, 384, 768, 1), (4096, 640, 2560, 0), (128, 128, 64, 2)])
+def test_gemm_plain(ops, M, N, K, variant):
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a = bf(torch.randn(M, K, generator=g)).to(DEV)
+    w = bf(torch.randn(N, K, generator=g) / math.sqrt(K)).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    res = bf(torch.randn(M, N, generator=g)).to(DEV)
+    out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=DEV)
+    ops.gemm_conv(a, w, out, n_img=1, h=1, w=M, c0=K, n_out=N, bias=bias, residual=res, ld_res=N, variant=variant)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t() + bias + res.float()
+    r = rel(out, ref)
+    print(f"gemm {M}x{N}x{K} v{variant}: rel {r:.3e}")
+    assert torch.isfinite(out.float()).all()
+    assert r < 4e-3
+
+
+def test_gemm_no_epilogue_exactness(ops):
+    # small integers: products/sums exactly representable -> tcgen05 result must be EXACT
+    M, N, K = 256, 128, 192
+    g = torch.Generator().manual_seed(5)
+    a = torch.randint(-3, 4, (M, K), generator=g).float()
+    w = torch.randint(-3, 4, (N, K), generator=g).float()
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    ops.gemm_conv(bf(a).to(DEV), bf(w).to(DEV), out, n_img=1, h=1, w=M, c0=K, n_out=N, variant=1)
+    torch.cuda.synchronize()
+    ref = a @ w.t()
+    bad = (out.float().cpu() != bf(ref).float()).nonzero()
+    print("mismatches:", bad.shape[0], bad[:10].tolist())
+    assert bad.shape[0] == 0
+
+
+def test_gemm_geglu(ops):
+    M, C = 512, 320
+    g = torch.Generator().manual_seed(11)
+    a = bf(torch.randn(M, C, generator=g)).to(DEV)
+    w = bf(torch.randn(8 * C, C, generator=g) / math.sqrt(C))
+    b = bf(torch.randn(8 * C, generator=g) * 0.1).float()
+    inner4 = 4 * C
+    wp = torch.cat([w[:inner4].reshape(-1, 64, C), w[inner4:].reshape(-1, 64, C)], dim=1).reshape(8 * C, C).contiguous().to(DEV)
+    bp = torch.cat([b[:inner4].reshape(-1, 64), b[inner4:].reshape(-1, 64)], dim=1).reshape(8 * C).contiguous().to(DEV)
+    out = torch.empty(M, inner4, dtype=torch.bfloat16, device=DEV)
+    ops.gemm_conv(a, wp, out, n_img=1, h=1, w=M, c0=C, n_out=8 * C, bias=bp, epilogue=ops.CPD_EPI_GEGLU)
+    torch.cuda.synchronize()
+    y = a.float() @ w.float().to(DEV).t() + b.to(DEV)
+    ref = y[:, :inner4] * F.gelu(y[:, inner4:])
+    r = rel(out, ref)
+    print(f"geglu rel {r:.3e}")
+    assert r < 6e-3
+
+
+@pytest.mark.parametrize("n,h,w,c0,c1,cout,stride,variant", [
+    (2, 16, 16, 64, 0, 128, 1, 1), (1, 64, 64, 320, 0, 320, 1, 0), (3, 8, 8, 128, 64, 256, 1, 2), (2, 32, 32, 64, 0, 64, 2, 1),
+    (4, 8, 8, 1280, 1280, 1280, 1, 0), (2, 16, 16, 128, 0, 128, 2, 2), (1, 24, 24, 64, 0, 64, 1, 1), (2, 12, 12, 64, 64, 128, 1, 1)])
+def test_conv3x3(ops, n, h, w, c0, c1, cout, stride, variant):
+    g = torch.Generator().manual_seed(n * h + cout)
+    cin = c0 + c1
+    x = bf(torch.randn(n, cin, h, w, generator=g))
+    wt = bf(torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(9 * cin))
+    bias = torch.randn(cout, generator=g)
+    rowvec = torch.randn(n, cout, generator=g)
+    ho, wo = h // stride, w // stride
+    res = bf(torch.randn(n, cout, ho, wo, generator=g))
+    nhwc = x.permute(0, 2, 3, 1).contiguous()
+    a0 = nhwc[..., :c0].contiguous().to(DEV)
+    a1 = nhwc[..., c0:].contiguous().to(DEV) if c1 else None
+    wp = wt.permute(0, 2, 3, 1).contiguous().to(DEV)
+    out = torch.full((n, ho, wo, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
+    ops.gemm_conv(a0, wp, out, n_img=n, h=h, w=w, c0=c0, a1=a1, c1=c1, n_out=cout, ksize=3, stride=stride,
+                  bias=bias.to(DEV), rowvec=rowvec.to(DEV).contiguous(), rowvec_stride=cout,
+                  residual=res.permute(0, 2, 3, 1).contiguous().to(DEV), ld_res=cout, variant=variant)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().to(DEV), wt.float().to(DEV), bias.to(DEV), stride=stride, padding=1)
+    ref = ref + rowvec.to(DEV)[:, :, None, None] + res.float().to(DEV)
+    r = rel(out.permute(0, 3, 1, 2), ref)
+    print(f"conv3x3 n{n} {h}x{w} {c0}+{c1}->{cout} s{stride} v{variant}: rel {r:.3e}")
+    assert torch.isfinite(out.float()).all()
+    assert r < 4e-3
+
+
+def test_conv1x1_two_sources(ops):
+    n, h, w, c0, c1, cout = 2, 16, 16, 128, 64, 320
+    g = torch.Generator().manual_seed(3)
+    x = bf(torch.randn(n, h, w, c0 + c1, generator=g))
+    wt = bf(torch.randn(cout, c0 + c1, generator=g) / math.sqrt(c0 + c1)).to(DEV)
+    out = torch.empty(n, h, w, cout, dtype=torch.bfloat16, device=DEV)
+    ops.gemm_conv(x[..., :c0].contiguous().to(DEV), wt, out, n_img=n, h=h, w=w, c0=c0, a1=x[..., c0:].contiguous().to(DEV), c1=c1,
+                  n_out=cout, ksize=1)
+    torch.cuda.synchronize()
+    ref = x.float().to(DEV) @ wt.float().t()
+    assert rel(out, ref) < 4e-3
+
+
+# ------------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("B,H,Nq,Nk,d", [(2, 8, 256, 256, 40), (1, 4, 1024, 1024, 80), (2, 2, 64, 64, 160), (3, 8, 256, 77, 40),
+                                         (2, 5, 576, 576, 64), (1, 2, 64, 64, 32), (4, 8, 4096, 77, 40), (1, 8, 4096, 4096, 40)])
+def test_attention(ops, B, H, Nq, Nk, d):
+    g = torch.Generator().manual_seed(B * Nq + d)
+    dpad = (d + 15) // 16 * 16
+    nk_pad = Nk if Nk % 16 == 0 else (Nk + 15) // 16 * 16
+    q = bf(torch.randn(B, Nq, H, d, generator=g))
+    k = bf(torch.randn(B, Nk, H, d, generator=g))
+    v = bf(torch.randn(B, Nk, H, d, generator=g))
+    qp = torch.zeros(B, Nq, H, dpad, dtype=torch.bfloat16); qp[..., :d] = q
+    kp = torch.zeros(B, nk_pad, H, dpad, dtype=torch.bfloat16); kp[:, :Nk, :, :d] = k
+    vp = torch.zeros(B, nk_pad, H, dpad, dtype=torch.bfloat16); vp[:, :Nk, :, :d] = v
+    vt = vp.permute(2, 3, 0, 1).reshape(H * dpad, B * nk_pad).contiguous().to(DEV)
+    o = torch.full((B, Nq, H, dpad), float("nan"), dtype=torch.bfloat16, device=DEV)
+    ops.attention(qp.to(DEV), kp.to(DEV), vt, o, ldq=H * dpad, ldk=H * dpad, ldvt=B * nk_pad, ldo=H * dpad, batch=B, heads=H,
+                  nq=Nq, nk=Nk, nk_pad=nk_pad, dpad=dpad, scale=d ** -0.5)
+    torch.cuda.synchronize()
+    qf, kf, vf = (t.float().to(DEV).permute(0, 2, 1, 3) for t in (q, k, v))
+    ref = torch.softmax(qf @ kf.transpose(-1, -2) * d ** -0.5, dim=-1) @ vf  # [B,H,Nq,d]
+    got = o[..., :d].permute(0, 2, 1, 3)
+    r = rel(got, ref)
+    print(f"attention B{B} H{H} {Nq}x{Nk} d{d}: rel {r:.3e}")
+    assert torch.isfinite(o.float()).all()
+    assert r < 1e-2
+    if dpad != d:
+        assert (o[..., d:] == 0).all()
+
+
+# ------------------------------------------------------------------------------------------------ norms / small ops
+@pytest.mark.parametrize("n,hw,c0,c1,silu,eps", [(2, 4096, 320, 0, True, 1e-5), (3, 64, 1280, 1280, True, 1e-5), (1, 1024, 640, 320, False, 1e-6),
+                                                  (2, 256, 64, 0, True, 1e-5), (16, 4096, 320, 320, True, 1e-5)])
+def test_groupnorm(ops, n, hw, c0, c1, silu, eps):
+    g = torch.Generator().manual_seed(hw + c0)
+    C = c0 + c1
+    x = bf(torch.randn(n, hw, C, generator=g) * 2 + 0.5)
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    out = torch.empty(n, hw, C, dtype=torch.bfloat16, device=DEV)
+    stats = torch.empty(n * 64, dtype=torch.float64, device=DEV)
+    ops.groupnorm(x[..., :c0].contiguous().to(DEV), gamma.to(DEV), beta.to(DEV), out, stats, n_img=n, hw=hw, c0=c0,
+                  a1=x[..., c0:].contiguous().to(DEV) if c1 else None, c1=c1, eps=eps, silu=silu)
+    torch.cuda.synchronize()
+    ref = F.group_norm(x.float().to(DEV).permute(0, 2, 1), 32, gamma.to(DEV), beta.to(DEV), eps)
+    if silu:
+        ref = F.silu(ref)
+    r = rel(out.permute(0, 2, 1), ref)
+    print(f"groupnorm n{n} hw{hw} C{C}: rel {r:.3e}")
+    assert r < 4e-3
+
+
+@pytest.mark.parametrize("rows,c", [(4096, 320), (1000, 640), (64, 1280), (5, 64), (300, 2048)])
+def test_layernorm(ops, rows, c):
+    g = torch.Generator().manual_seed(rows + c)
+    x = bf(torch.randn(rows, c, generator=g) * 3 + 1).to(DEV)
+    gamma, beta = torch.randn(c, generator=g).to(DEV), torch.randn(c, generator=g).to(DEV)
+    out = torch.empty_like(x)
+    ops.layernorm(x, gamma, beta, out, rows=rows, c=c)
+    torch.cuda.synchronize()
+    ref = F.layer_norm(x.float(), (c,), gamma, beta, 1e-5)
+    assert rel(out, ref) < 4e-3
+
+
+def test_timestep_embedding_and_small_linear(ops):
+    t = torch.tensor([937.93, 11.278, 500.0], device=DEV)
+    out = torch.empty(3, 320, dtype=torch.bfloat16, device=DEV)
+    ops.timestep_embedding(t, out, dim=320, round_t_bf16=True)
+    tt = t.to(torch.bfloat16).float()
+    half = 160
+    freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32, device=DEV) / half)
+    args = tt[:, None] * freqs[None]
+    ref = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+    assert (out.float() - ref).abs().max().item() < 1e-2
+    g = torch.Generator().manual_seed(0)
+    for m, k, n, silu in [(3, 320, 1280, False), (16, 1280, 4000, True), (1, 1280, 1280, True), (20, 64, 256, True)]:
+        x = bf(torch.randn(m, k, generator=g)).to(DEV)
+        w = bf(torch.randn(n, k, generator=g) / math.sqrt(k)).to(DEV)
+        b = torch.randn(n, generator=g).to(DEV)
+        o32 = torch.empty(m, n, device=DEV)
+        o16 = torch.empty(m, n, dtype=torch.bfloat16, device=DEV)
+        ops.small_linear(x, w, b, m=m, k=k, n=n, silu_in=silu, out_f32=o32, out_bf16=o16)
+        xin = F.silu(x.float()) if silu else x.float()
+        ref = xin @ w.float().t() + b
+        assert rel(o32, ref) < 6e-3 and rel(o16, ref) < 6e-3
+
+
+def test_conv_in_out_upsample(ops):
+    g = torch.Generator().manual_seed(1)
+    n, h, w, cout = 2, 16, 16, 64
+    x = torch.randn(n, 4, h, w, generator=g)
+    wt = bf(torch.randn(cout, 4, 3, 3, generator=g) / 6)
+    bias = torch.randn(cout, generator=g)
+    out = torch.empty(n * 3, h, w, cout, dtype=torch.bfloat16, device=DEV)
+    ops.conv_in(x.to(DEV), wt.permute(0, 2, 3, 1).contiguous().to(DEV), bias.to(DEV), out, n=n, cin=4, h=h, w=w, cout=cout,
+                scale=0.37, rows_per_image=3)
+    ref = F.conv2d(bf(x * 0.37).float().to(DEV), wt.float().to(DEV), bias.to(DEV), padding=1).permute(0, 2, 3, 1)
+    for r in range(3):
+        assert rel(out.view(n, 3, h, w, cout)[:, r], ref) < 4e-3
+    cin = 320
+    a = bf(torch.randn(n, h, w, cin, generator=g)).to(DEV)
+    w2 = bf(torch.randn(4, cin, 3, 3, generator=g) / math.sqrt(9 * cin))
+    b2 = torch.randn(4, generator=g)
+    o2 = torch.empty(n, 4, h, w, dtype=torch.bfloat16, device=DEV)
+    ops.conv_out(a, w2.permute(0, 2, 3, 1).contiguous().to(DEV), b2.to(DEV), o2, n=n, h=h, w=w, cin=cin, cout=4)
+    ref2 = F.conv2d(a.float().permute(0, 3, 1, 2), w2.float().to(DEV), b2.to(DEV), padding=1)
+    assert rel(o2, ref2) < 4e-3
+    up = torch.empty(n, 2 * h, 2 * w, cin, dtype=torch.bfloat16, device=DEV)
+    ops.upsample2x(a, up, n=n, h=h, w=w, c=cin)
+    ref3 = F.interpolate(a.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(up.float(), ref3)

@@ -1,0 +1,274 @@
+"""GPU parity of the drop-in sampling path (registry -> wrapper -> sampler -> Denoiser -> UNet -> fused step
+kernel) against the CPU oracle and the golden fixtures of the shimmed reference.
+
+Tolerances (BASELINE.json north_star): integer timestep indices bit-exact; per-step eps rel-L2 <= 1e-2 in
+bf16 and <= 1e-4 in fp32 (given identical eps inputs the fp32 sampler path is in fact bit-exact); final
+latent rel-L2 <= 2e-2 in bf16."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def cpd():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import complex_prompt_diffusion_b200 as pkg
+    from complex_prompt_diffusion_b200 import _lib
+    _lib.load()
+    return pkg
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-20)).item()
+
+
+class ReplayUNet:
+    """Stands in for the UNet on both sides: returns pre-recorded / synthetic eps rows, so that the host logic
+    and the fused step kernel are compared with the oracle on IDENTICAL eps inputs."""
+
+    def __init__(self, outs, dtype, device, expect_x=None, expect_t=None):
+        self.outs = [o.to(dtype) for o in outs]
+        self.i = 0
+        self.device = torch.device(device)
+        self._p = torch.zeros(1, dtype=dtype, device=device)
+        self.expect_x, self.expect_t = expect_x, expect_t
+
+    def parameters(self):
+        return iter([self._p])
+
+    def set_context(self, ctx):
+        self.ctx = ctx
+
+    # product fast path
+    def forward_rows(self, x, c_in, t, rows_per_image):
+        if self.expect_x is not None:
+            x_in = (x * torch.tensor(c_in, dtype=torch.float32, device=x.device)).cpu()
+            for r in range(rows_per_image):
+                assert torch.equal(x_in[0], self.expect_x[self.i][r]), "x * c_in differs from the reference's UNet input"
+            assert float(self.expect_t[self.i][0]) == t, "timestep differs from the reference's"
+        o = self.outs[self.i].to(self.device).contiguous()
+        self.i += 1
+        return o
+
+    # oracle path
+    def __call__(self, x, t, ctx, **kw):
+        o = self.outs[self.i]
+        self.i += 1
+        return o, [o] * 12
+
+
+def load_case(golden_dir):
+    z = np.load(os.path.join(golden_dir, "ref_sampling.npz"))
+    embs = torch.from_numpy(z["embs"])
+    mask = torch.from_numpy(z["mask"])
+    sc = z["scales"]
+    c = {"and": [(float(sc[0]), embs[0:1], None, 1), (float(sc[1]), embs[1:2], None, mask)],
+         "not": [(float(sc[2]), embs[2:3], None, 1)]}
+    return z, c
+
+
+CASES = [("Euler", "karras", "epsilon"), ("DPM++ 2m", "karras", "epsilon"), ("Euler Ancestral", "karras", "epsilon"),
+         ("Euler", "exp", "velocity"), ("DPM++ 2m", "linear", "velocity")]
+
+
+@pytest.mark.parametrize("name,sched,pred", CASES)
+def test_fused_loop_bit_exact_vs_reference_golden_fp32(cpd, golden_dir, name, sched, pred):
+    """fp32 eps recorded from the reference UNet -> registry sampler + fused CUDA step == reference, bit for bit."""
+    from complex_prompt_diffusion_b200 import samplers
+    z, c = load_case(golden_dir)
+    key = f"{name}|{sched}|{pred}".replace(" ", "_")
+    unet = ReplayUNet(list(torch.from_numpy(z[key + "|unet_out"])), torch.float32, DEV,
+                      expect_x=torch.from_numpy(z[key + "|unet_x"]), expect_t=torch.from_numpy(z[key + "|unet_t"]))
+    wrapper = samplers.make({"name": name, "args": {}}, {"model": {"unet": unet}})
+    noises = list(torch.from_numpy(z[key + "|noise"])) if (key + "|noise") in z.files else []
+    dens = []
+    out = wrapper.sampler.sample(steps=int(z["steps"]), batch_size=1, shape=[4, int(z["hw"]), int(z["hw"])],
+                                 x_T=torch.from_numpy(z["x_T"]).clone(), conditioning=c,
+                                 unconditional_conditioning=torch.from_numpy(z["uc"]),
+                                 unconditional_guidance_scale=float(z["guidance"]), scheduler=sched, pred_type=pred,
+                                 rng_compat=False, noise_sampler=(lambda x: noises.pop(0)) if noises else None,
+                                 callback=lambda d: dens.append(d["eps"].clone().cpu()))
+    torch.cuda.synchronize()
+    assert torch.equal(torch.stack(dens), torch.from_numpy(z[key + "|denoised"])), "per-step denoised differs"
+    assert torch.equal(out.cpu(), torch.from_numpy(z[key + "|final"])), "final latent differs"
+
+
+@pytest.mark.parametrize("name", ["Euler", "Euler Ancestral", "DPM++ 2m"])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("pred", ["epsilon", "velocity"])
+def test_fused_loop_bit_exact_vs_oracle_half_eps(cpd, name, dtype, pred):
+    """Synthetic bf16 / fp16 eps rows, B = 3 images, N = 3 sub-prompts (one negation, one spatial mask, one
+    scalar mask != 1): product on GPU == oracle on CPU, bit for bit."""
+    from complex_prompt_diffusion_b200 import samplers
+    from oracle.denoiser import OracleDenoiser
+    from oracle import samplers as OS
+    g = torch.Generator().manual_seed(42)
+    B, hw, steps, D = 3, 16, 5, 64
+    uc = torch.randn(1, 77, D, generator=g)
+    embs = [torch.randn(1, 77, D, generator=g) for _ in range(3)]
+    mask = (torch.rand(1, 1, hw, hw, generator=g) > 0.5).to(torch.uint8)
+    c = {"and": [(1.0, embs[0], None, 1), (0.6, embs[1], None, mask)], "not": [(0.37, embs[2], None, 0.5)]}
+    x_T = torch.randn(B, 4, hw, hw, generator=g)
+    base = [torch.randn(B, 1, 4, hw, hw, generator=g) for _ in range(steps)]
+    outs = [(b + 0.3 * torch.randn(B, 4, 4, hw, hw, generator=g)).reshape(B * 4, 4, hw, hw) for b in base]
+    noises = [torch.randn(B, 4, hw, hw, generator=g) for _ in range(steps)]
+    kw = dict(conditioning=c, unconditional_conditioning=uc, unconditional_guidance_scale=7.5, scheduler="karras", pred_type=pred)
+    # oracle: one image at a time (the reference supports batch 1 only)
+    finals = []
+    for b in range(B):
+        unet = ReplayUNet([o.view(B, 4, 4, hw, hw)[b] for o in outs], dtype, "cpu")
+        nz = [n[b:b + 1] for n in noises]
+        finals.append(OS.sample(OracleDenoiser(unet, dtype=dtype), name, steps, x_T[b:b + 1].clone(),
+                                noise_sampler=lambda x: nz.pop(0), **dict(kw)))
+    ref = torch.cat(finals)
+    unet = ReplayUNet(outs, dtype, DEV)
+    wrapper = samplers.make({"name": name, "args": {}}, {"model": {"unet": unet}})
+    nz = list(noises)
+    out = wrapper.sampler.sample(steps=steps, batch_size=B, shape=[4, hw, hw], x_T=x_T.clone(), rng_compat=False,
+                                 noise_sampler=lambda x: nz.pop(0), **dict(kw))
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), ref)
+
+
+def test_denoiser_forward_matches_oracle(cpd):
+    from complex_prompt_diffusion_b200.samplers.extension.denoiser import Denoiser
+    from oracle.denoiser import OracleDenoiser
+    g = torch.Generator().manual_seed(7)
+    hw, D = 8, 64
+    uc = torch.randn(1, 77, D, generator=g)
+    emb = torch.randn(1, 77, D, generator=g)
+    c = {"and": [(1.0, emb, None, 1)], "not": []}
+    x = torch.randn(1, 4, hw, hw, generator=g) * 5
+    eps = torch.randn(2, 4, hw, hw, generator=g)
+    sigma = torch.tensor([3.7])
+    for pred in ("epsilon", "velocity"):
+        ref = OracleDenoiser(ReplayUNet([eps], torch.float32, "cpu"), dtype=torch.float32)(
+            x, sigma, conditioning=c, unconditional_conditioning=uc, unconditional_guidance_scale=5.0, pred_type=pred)
+        got = Denoiser(ReplayUNet([eps], torch.float32, DEV))(x.to(DEV), sigma, conditioning=c, unconditional_conditioning=uc,
+                                                              unconditional_guidance_scale=5.0, pred_type=pred)
+        assert torch.equal(got.cpu(), ref)
+
+
+def test_unsupported_kwargs_fail_loudly(cpd):
+    from complex_prompt_diffusion_b200.samplers.extension.denoiser import Denoiser
+    d = Denoiser(ReplayUNet([torch.zeros(2, 4, 8, 8)], torch.float32, DEV))
+    with pytest.raises(NotImplementedError):
+        d(torch.zeros(1, 4, 8, 8, device=DEV), torch.tensor([1.0]), conditioning={"and": [(1.0, torch.zeros(1, 77, 8), None, 1)]},
+          unconditional_conditioning=torch.zeros(1, 77, 8), attn_guide=True)
+
+
+# ------------------------------------------------------------------------------------------------ UNet
+def _unet_pair(cfg_name, dtype_oracle):
+    from complex_prompt_diffusion_b200.models.unet import UNetModel
+    from oracle.unet import UNetConfig, OracleUNet, make_weights
+    cfg = getattr(UNetConfig, cfg_name)()
+    sd = make_weights(cfg, seed=0)
+    oracle = OracleUNet(cfg, sd, dtype=dtype_oracle)
+    gpu = UNetModel(sd, device=DEV, model_channels=cfg.model_channels, channel_mult=tuple(cfg.channel_mult),
+                    attention_resolutions=tuple(cfg.attention_resolutions), num_res_blocks=cfg.num_res_blocks,
+                    num_heads=cfg.num_heads, num_head_channels=cfg.num_head_channels, context_dim=cfg.context_dim,
+                    use_linear_in_transformer=cfg.use_linear_in_transformer)
+    return cfg, oracle, gpu
+
+
+def _layer_report(oracle, gpu, R):
+    rows = []
+    for name, ref in oracle.taps.items():
+        for key, buf in gpu._ws.items():
+            if key[0] == name + ".out" and buf.numel() == ref.numel():
+                got = buf.view(R, ref.shape[2], ref.shape[3], ref.shape[1]).permute(0, 3, 1, 2)
+                rows.append((name, rel(got, ref)))
+    return rows
+
+
+@pytest.mark.parametrize("cfg_name,hw,R", [("tiny", 16, 3), ("tiny", 32, 2), ("sd15", 16, 2)])
+def test_unet_forward_vs_oracle(cpd, cfg_name, hw, R):
+    cfg, oracle, gpu = _unet_pair(cfg_name, torch.float32)
+    g = torch.Generator().manual_seed(hw + R)
+    x = torch.randn(R, 4, hw, hw, generator=g)
+    t = torch.tensor([937.93, 11.278, 500.5][:R])
+    ctx = torch.randn(R, 77, cfg.context_dim, generator=g)
+    # the oracle runs on bf16-rounded weights / inputs in fp32 arithmetic: isolates kernel error from
+    # the (shared) quantisation of the weights
+    oracle.sd = {k: v.to(torch.bfloat16).float() for k, v in oracle.sd.items()}
+    oracle.taps = {}
+    t_r = t.to(torch.bfloat16).float()
+    ref = oracle(x, t_r, ctx.to(torch.bfloat16).float())
+    out, skips = gpu(x.to(DEV), t_r.to(DEV), ctx.to(DEV), return_attn=True)
+    torch.cuda.synchronize()
+    report = _layer_report(oracle, gpu, R)
+    for name, r in report:
+        print(f"  {name:40s} rel {r:.3e}")
+    r = rel(out, ref)
+    print(f"unet {cfg_name} {hw}x{hw} R{R}: eps rel-L2 {r:.3e}")
+    assert len(skips) == 3 * len(cfg.channel_mult)
+    assert torch.isfinite(out.float()).all()
+    assert r < 1e-2
+
+
+def test_unet_forward_rows_equals_forward(cpd):
+    cfg, oracle, gpu = _unet_pair("tiny", torch.float32)
+    g = torch.Generator().manual_seed(0)
+    B, R, hw = 2, 3, 16
+    x = torch.randn(B, 4, hw, hw, generator=g).to(DEV)
+    ctx = torch.randn(R, 77, cfg.context_dim, generator=g).to(DEV)
+    gpu.set_context(ctx)
+    c_in, t = 0.25, 500.0
+    a = gpu.forward_rows(x, c_in, t, R).clone()
+    x_in = (x * c_in).repeat_interleave(R, dim=0)
+    b = gpu.forward(x_in, torch.full((B * R,), t), None).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("name,steps", [("DPM++ 2m", 6), ("Euler", 6), ("Euler Ancestral", 6)])
+def test_end_to_end_sampling_vs_oracle_bf16(cpd, name, steps):
+    """Whole drop-in path on the GPU (bf16 UNet kernels) vs the oracle run with bf16-rounded weights:
+    per-step eps rel-L2 <= 1e-2, final latent rel-L2 <= 2e-2."""
+    from complex_prompt_diffusion_b200 import samplers
+    from oracle.denoiser import OracleDenoiser
+    from oracle import samplers as OS
+    cfg, oracle, gpu = _unet_pair("tiny", torch.float32)
+    oracle.sd = {k: v.to(torch.bfloat16).float() for k, v in oracle.sd.items()}
+    g = torch.Generator().manual_seed(3)
+    hw, D = 16, cfg.context_dim
+    uc = torch.randn(1, 77, D, generator=g)
+    embs = [torch.randn(1, 77, D, generator=g) for _ in range(3)]
+    c = {"and": [(1.0, embs[0], None, 1), (0.6, embs[1], None, 1)], "not": [(0.4, embs[2], None, 1)]}
+    x_T = torch.randn(1, 4, hw, hw, generator=g)
+    noises = [torch.randn(1, 4, hw, hw, generator=g) for _ in range(steps)]
+    kw = dict(conditioning=c, unconditional_conditioning=uc, unconditional_guidance_scale=7.5, scheduler="karras")
+
+    class BF16InOut:  # oracle UNet with the product's dtype boundaries (bf16 context / t / output)
+        def parameters(self):
+            return iter([torch.zeros(1, dtype=torch.bfloat16)])
+
+        def __call__(self, x, t, ctx, **k):
+            o = oracle(x.to(torch.bfloat16).float(), t.float(), ctx.to(torch.bfloat16).float())
+            return o.to(torch.bfloat16), [o] * 12
+
+    od = OracleDenoiser(BF16InOut(), dtype=torch.bfloat16)
+    od.trace = []
+    nz = list(noises)
+    ref = OS.sample(od, name, steps, x_T.clone(), noise_sampler=lambda x: nz.pop(0), **dict(kw))
+    wrapper = samplers.make({"name": name, "args": {}}, {"model": {"unet": gpu}})
+    nz2 = list(noises)
+    dens = []
+    out = wrapper.sampler.sample(steps=steps, batch_size=1, shape=[4, hw, hw], x_T=x_T.clone(), rng_compat=False,
+                                 noise_sampler=lambda x: nz2.pop(0), callback=lambda d: dens.append(d["eps"].clone().cpu()),
+                                 **dict(kw))
+    torch.cuda.synchronize()
+    for i, d in enumerate(dens):
+        r = rel(d, od.trace[i]["denoised"])
+        print(f"  step {i}: denoised rel {r:.3e}")
+    r = rel(out, ref)
+    print(f"{name}: final latent rel-L2 {r:.3e}")
+    assert r < 2e-2

@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Benchmark of the denoising-loop hot path (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                      (CPU arm: the oracle port on the host cores)
+
+A "step" is ONE full generation of the workload batch through the drop-in path:
+  config 2 of BASELINE.json - SD-1.5 UNet (random-init seeded weights), 64x64 latent (512 px), DPM++ 2M,
+  Karras schedule, 20 sampler steps, composable prompt of 3 weighted sub-prompts + unconditional, batch 4, bf16
+  = 20 x 16 = 320 UNet row-evaluations (257 TFLOP algorithmic) per step and per GPU.
+`value` = images/s over all GPUs with inputs resident in HBM; `e2e` = the same through the public sampler API
+with HOST inputs (pinned x_T and embeddings copied H2D, final latents read D2H inside the timed region).
+Multi-GPU: images are sharded across ranks (weak scaling: 4 images per GPU), no data-path collective.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(workload="SD-1.5 512px (64x64 latent), DPM++ 2M Karras 20 steps, 3 weighted sub-prompts + uncond, batch 4",
+                model="sd15", latent=64, sampler="DPM++ 2m", scheduler="karras", sampler_steps=20, n_sub=3, batch=4,
+                guidance=7.5)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default=WORKLOAD["model"], choices=["sd15", "sd21", "tiny"])
+    ap.add_argument("--latent", type=int, default=WORKLOAD["latent"])
+    ap.add_argument("--batch", type=int, default=WORKLOAD["batch"])
+    ap.add_argument("--sampler-steps", type=int, default=WORKLOAD["sampler_steps"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p["bf16_tflops_sustained"], source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+def make_inputs(cfg, latent, batch, n_sub, seed=0):
+    """Synthetic prompts / latents of the named shape: emb_k ~ N(0,1) [1,77,D], x_T ~ N(0,1)."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    D = cfg.context_dim
+    uc = torch.randn(1, 77, D, generator=g)
+    embs = [torch.randn(1, 77, D, generator=g) for _ in range(n_sub)]
+    weights = [1.0, 0.6, 0.4, 0.3, 0.2][:n_sub]
+    c = {"and": [(weights[k], embs[k], None, 1) for k in range(n_sub - 1)] if n_sub > 1 else [(1.0, embs[0], None, 1)],
+         "not": [(weights[n_sub - 1], embs[n_sub - 1], None, 1)] if n_sub > 1 else []}
+    x_T = torch.randn(batch, 4, latent, latent, generator=g)
+    return uc, c, x_T
+
+
+def oracle_cfg(name):
+    from oracle.unet import UNetConfig
+    return getattr(UNetConfig, name)()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------------ CPU arm
+def cpu_sample(cfg_name, latent, n_sub, sampler_steps_sample, threads):
+    """Times the oracle port on the host cores on a BOUNDED sample: `sampler_steps_sample` sampler steps of ONE
+    image (each = 1 + n_sub UNet row-evaluations, fp32), returns seconds per (image x sampler-step)."""
+    from oracle.unet import OracleUNet, make_weights
+    from oracle.denoiser import OracleDenoiser
+    from oracle import samplers as OS
+    torch.set_num_threads(threads)
+    cfg = oracle_cfg(cfg_name)
+    unet = OracleUNet(cfg, make_weights(cfg, seed=0))
+    uc, c, x_T = make_inputs(cfg, latent, 1, n_sub)
+    den = OracleDenoiser(unet)
+    sig = den.scheduler.get_sigmas("karras", WORKLOAD["sampler_steps"])
+    x = x_T * sig[0]
+    kw = dict(conditioning=c, unconditional_conditioning=uc, unconditional_guidance_scale=WORKLOAD["guidance"], total_steps=len(sig))
+    t0 = time.perf_counter()
+    OS.sample_dpmpp_2m(den, x, sig[:sampler_steps_sample + 1], kw)
+    dt = time.perf_counter() - t0
+    return dt / sampler_steps_sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample_steps = 1
+    for _ in range(args.warmup if args.latent <= 16 else 0):
+        cpu_sample(args.model, args.latent, WORKLOAD["n_sub"], sample_steps, threads)
+    times = [cpu_sample(args.model, args.latent, WORKLOAD["n_sub"], sample_steps, threads) for _ in range(max(1, min(args.steps, 3)))]
+    per_img_step = sum(times) / len(times)
+    sec_per_batch = per_img_step * args.sampler_steps * args.batch
+    ips = args.batch / sec_per_batch
+    sample = (f"{sample_steps} sampler step(s) of 1 image = {1 + WORKLOAD['n_sub']} fp32 UNet row-evals of the same workload, "
+              f"x{len(times)}, extrapolated linearly to {args.sampler_steps} steps x {args.batch} images")
+    line = {"impl": "reference", "metric": "images_per_s", "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec_per_batch * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": dict(WORKLOAD, model=args.model, latent=args.latent, batch=args.batch,
+                                                                sampler_steps=args.sampler_steps),
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "unet_evals_per_s": ips * args.sampler_steps * (1 + WORKLOAD["n_sub"]), "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------ GPU arm
+def run_b200(args):
+    from complex_prompt_diffusion_b200 import ops, samplers
+    from complex_prompt_diffusion_b200.models.unet import UNetModel
+    from oracle.unet import make_weights, count_flops  # weights fixture + FLOP enumerator only (not the measured path)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = oracle_cfg(args.model)
+    sd = make_weights(cfg, seed=0)
+    unet = UNetModel(sd, device=dev, model_channels=cfg.model_channels, channel_mult=tuple(cfg.channel_mult),
+                     attention_resolutions=tuple(cfg.attention_resolutions), num_res_blocks=cfg.num_res_blocks,
+                     num_heads=cfg.num_heads, num_head_channels=cfg.num_head_channels, context_dim=cfg.context_dim,
+                     use_linear_in_transformer=cfg.use_linear_in_transformer)
+    del sd
+    n_sub, B, S = WORKLOAD["n_sub"], args.batch, args.sampler_steps
+    uc, c, x_T = make_inputs(cfg, args.latent, B, n_sub, seed=rank)
+    wrapper = samplers.make({"name": WORKLOAD["sampler"], "args": {}}, {"model": {"unet": unet}})
+    kw = dict(unconditional_guidance_scale=WORKLOAD["guidance"], scheduler=WORKLOAD["scheduler"], rng_compat=False)
+
+    # resident inputs
+    uc_d = uc.to(dev)
+    c_d = {k: [(s, e.to(dev), g_, m) for (s, e, g_, m) in v] for k, v in c.items()}
+    x_T_d = x_T.to(dev)
+    # host (pinned) inputs for the e2e leg
+    x_T_h = x_T.clone().pin_memory()
+    uc_h = uc.clone().pin_memory()
+    c_h = {k: [(s, e.clone().pin_memory(), g_, m) for (s, e, g_, m) in v] for k, v in c.items()}
+    out_h = torch.empty(B, 4, args.latent, args.latent).pin_memory()
+
+    def step_resident():
+        return wrapper.sampler.sample(steps=S, batch_size=B, shape=[4, args.latent, args.latent], x_T=x_T_d, conditioning=c_d,
+                                      unconditional_conditioning=uc_d, **dict(kw))
+
+    def step_e2e():
+        xd = x_T_h.to(dev, non_blocking=True)
+        ucd = uc_h.to(dev, non_blocking=True)
+        cd = {k: [(s, e.to(dev, non_blocking=True), g_, m) for (s, e, g_, m) in v] for k, v in c_h.items()}
+        out = wrapper.sampler.sample(steps=S, batch_size=B, shape=[4, args.latent, args.latent], x_T=xd, conditioning=cd,
+                                     unconditional_conditioning=ucd, **dict(kw))
+        out_h.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out_h
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    for _ in range(args.warmup):
+        step_resident()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ops.LAUNCHES = 0
+    ms = timed(step_resident, args.steps)
+    launches = ops.LAUNCHES
+    clk = clocks.stop() if rank == 0 else None
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    imgs = B * world * args.steps
+    ips = imgs / (ms / 1e3)
+    ips_e2e = imgs / (ms_e2e / 1e3)
+    R = 1 + n_sub
+    evals_per_step = S * R * B
+    flops_row = count_flops(cfg, args.latent, args.latent)["total"]
+    pk = peaks()
+
+    # dominant kernel (tcgen05 implicit-GEMM conv / GEMM): per-launch CUDA-event timing over one more step
+    roof, roof_sampler = None, None
+    if rank == 0:
+        ops.PROFILE = []
+        step_resident()
+        torch.cuda.synchronize()
+        prof, ops.PROFILE = ops.PROFILE, None
+        g_ms = sum(a.elapsed_time(b) for (k_, a, b, f) in prof if k_ == "gemm_conv")
+        g_fl = sum(f for (k_, a, b, f) in prof if k_ == "gemm_conv")
+        g_n = sum(1 for (k_, a, b, f) in prof if k_ == "gemm_conv")
+        at_ms = sum(a.elapsed_time(b) for (k_, a, b, f) in prof if k_ == "attention")
+        at_fl = sum(f for (k_, a, b, f) in prof if k_ == "attention")
+        achieved = g_fl / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
+        roof = {"bound": "tensor", "kernel": "gemm_conv_kernel (tcgen05 implicit-GEMM conv / GEMM)", "achieved": achieved,
+                "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"], "traffic": None,
+                "peak_source": pk["source"] + " (sustained bf16)", "launches_per_step": g_n,
+                "avg_launch_us": g_ms * 1e3 / max(g_n, 1), "share_of_step": g_ms / (ms / args.steps),
+                "attention_tflops": at_fl / (at_ms / 1e3) / 1e12 if at_ms > 0 else None,
+                "attention_share_of_step": at_ms / (ms / args.steps),
+                "unet_tflops_whole_step": evals_per_step * flops_row / (ms / args.steps / 1e3) / 1e12,
+                "unet_frac_of_peak_whole_step": evals_per_step * flops_row / (ms / args.steps / 1e3) / 1e12 / pk["tf_sustained"]}
+        roof_sampler = sampler_roofline(ops, dev, pk)
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        per = cpu_sample(args.model, args.latent, n_sub, 1, threads)
+        sec_batch = per * S * B
+        cpu = {"value": B / sec_batch, "unit": "images/s", "cores": threads, "kind": "port",
+               "sample": f"1 sampler step of 1 image ({R} fp32 UNet row-evals, oracle port) = {per:.2f} s, extrapolated linearly to "
+                         f"{S} steps x {B} images"}
+    if rank == 0:
+        line = {"metric": "images_per_s", "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic",
+                "config": dict(WORKLOAD, model=args.model, latent=args.latent, batch=B, sampler_steps=S, parallelism=f"images sharded x{world}",
+                               l2="working set (1.7 GB weights + activations) larger than L2; no flush needed"),
+                "unet_evals_per_s": evals_per_step * world * args.steps / (ms / 1e3),
+                "e2e": {"value": ips_e2e, "unit": "images/s",
+                        "h2d_bytes_per_step": int(x_T_h.numel() * 4 + uc_h.numel() * 4 + sum(e.numel() * 4 for v in c_h.values() for (_, e, _, _) in v)),
+                        "d2h_bytes_per_step": int(out_h.numel() * 4)},
+                "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_sampler_step": roof_sampler, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def sampler_roofline(ops, dev, pk):
+    """Fused sampler-step kernel at a saturating synthetic batch (>= 256 MB of traffic, larger than L2) and at the
+    named shape (latency)."""
+    from complex_prompt_diffusion_b200._lib import CPD_DPMPP_2M, CPD_PRED_EPSILON
+    res = {}
+    for tag, B in (("saturating", 704), ("named_shape", 4)):
+        hw, n_sub = 64 * 64, 3
+        eps = torch.randn(B * 4, 4, 64, 64, device=dev).to(torch.bfloat16)
+        x = torch.randn(B, 4, 64, 64, device=dev)
+        old = torch.randn(B, 4, 64, 64, device=dev)
+        args = dict(n_sub=n_sub, weights=[1.0, 0.6, -0.4], mask_scalars=[1.0] * 3, masks=[None] * 3, guidance=7.5, sampler=CPD_DPMPP_2M,
+                    pred_type=CPD_PRED_EPSILON, sigma_hat=2.0, dpm_ratio=0.8, dpm_expm1=-0.2, dpm_c1=1.5, dpm_c2=0.5, dpm_first=0,
+                    write_old=1, old_denoised=old)
+        for _ in range(3):
+            ops.sampler_step(eps, x, **args)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 20
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            ops.sampler_step(eps, x, **args)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / n
+        bytes_per = (4 * 2 + 4 + 4 + 4 + 4) * 4 * hw * B  # R*2 (eps bf16) + x r/w + old r/w  
+        res[tag] = {"images": B, "bytes": bytes_per, "us_per_launch": us, "achieved_gbs": bytes_per / us / 1e3,
+                    "frac_of_hbm_peak": bytes_per / us / 1e3 / pk["hbm"]}
+    res["bound"] = "hbm"
+    res["peak"] = pk["hbm"]
+    res["unit"] = "GB/s"
+    return res
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

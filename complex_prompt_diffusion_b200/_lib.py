@@ -42,6 +42,7 @@ class GemmParams(C.Structure):
         ("rowvec", C.c_void_p), ("rowvec_stride", C.c_int),
         ("residual", C.c_void_p), ("ld_res", C.c_int),
         ("d", C.c_void_p), ("ldd", C.c_int), ("epilogue", C.c_int), ("variant", C.c_int), ("m_valid", C.c_int),
+        ("a_fp16", C.c_int), ("b_fp16", C.c_int), ("out_fp16", C.c_int),
     ]
 
 
@@ -50,7 +51,7 @@ class AttnParams(C.Structure):
         ("q", C.c_void_p), ("ldq", C.c_int), ("k", C.c_void_p), ("ldk", C.c_int), ("vt", C.c_void_p), ("ldvt", C.c_int),
         ("o", C.c_void_p), ("ldo", C.c_int),
         ("batch", C.c_int), ("heads", C.c_int), ("nq", C.c_int), ("nk", C.c_int), ("nk_pad", C.c_int), ("dpad", C.c_int),
-        ("scale", C.c_float), ("kv_batch", C.c_int),
+        ("scale", C.c_float), ("kv_batch", C.c_int), ("act_fp16", C.c_int),
     ]
 
 
@@ -60,15 +61,16 @@ _SIGS = {
     "cpd_sampler_step": (C.c_int, [C.POINTER(StepParams), C.c_void_p]),
     "cpd_gemm_conv": (C.c_int, [C.POINTER(GemmParams), C.c_void_p]),
     "cpd_groupnorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
-                                C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "cpd_layernorm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
+                                C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cpd_layernorm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p,
+                                C.c_void_p]),
     "cpd_timestep_embedding": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "cpd_small_linear": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                    C.c_void_p, C.c_int, C.c_void_p]),
     "cpd_conv_in": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float,
-                              C.c_int, C.c_void_p, C.c_void_p]),
+                              C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "cpd_conv_out": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
-                               C.c_int, C.c_void_p]),
+                               C.c_int, C.c_int, C.c_void_p]),
     "cpd_upsample2x": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "cpd_attention": (C.c_int, [C.POINTER(AttnParams), C.c_void_p]),
 }

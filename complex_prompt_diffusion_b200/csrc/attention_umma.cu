@@ -24,6 +24,7 @@ struct AttnArgs {
   int batch, heads, nq, nk, nk_pad, dpad, kv_batch;
   int datoms;      // ceil(dpad / 64)
   int kv_stages;   // 1 or 2
+  int fp16;        // q, k, vt, o element type: 1 = fp16, 0 = bf16
   float scale_log2;
 };
 
@@ -109,8 +110,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_kernel(const __grid_
   } else if (warp == 1) {
     if (lane == 0) {
       // ---- MMA issuer ----
-      const uint32_t idesc_s = umma_idesc_bf16(BQ, BKV);
-      const uint32_t idesc_o = umma_idesc_bf16(BQ, dpad);
+      const uint32_t idesc_s = umma_idesc_f16(BQ, BKV, a.fp16 != 0, a.fp16 != 0);
+      const uint32_t idesc_o = umma_idesc_f16(BQ, dpad, a.fp16 != 0, a.fp16 != 0);
       const int ksteps_s = dpad / 16;
       auto issue_s = [&](int j) {
         const int st = j % a.kv_stages;
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_kernel(const __grid_
         float p0 = (e < kv_valid) ? exp2f(__uint_as_float(v[e]) * a.scale_log2 - m_used) : 0.f;
         float p1 = (e + 1 < kv_valid) ? exp2f(__uint_as_float(v[e + 1]) * a.scale_log2 - m_used) : 0.f;
         psum += p0 + p1;
-        pk[e >> 1] = pack_bf16x2(p0, p1);
+        pk[e >> 1] = pack_act2(p0, p1, a.fp16 != 0);
       }
       l = l * alpha + psum;
       if (j > 0) {
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_kernel(const __grid_
         uint32_t o[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e)
-          o[e] = pack_bf16x2(__uint_as_float(t[2 * e]) * inv_l, __uint_as_float(t[2 * e + 1]) * inv_l);
+          o[e] = pack_act2(__uint_as_float(t[2 * e]) * inv_l, __uint_as_float(t[2 * e + 1]) * inv_l, a.fp16 != 0);
         uint4* dst = reinterpret_cast<uint4*>(a.o + ((int64_t)b * a.nq + qrow) * a.ldo + head * dpad + c);
         dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
         dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
@@ -257,6 +258,7 @@ extern "C" cpd_status cpd_attention(const cpd_attn_params* p, void* stream) {
   a.kv_batch = p->kv_batch > 0 ? p->kv_batch : p->batch;
   a.datoms = (p->dpad + 63) / 64;
   a.kv_stages = (p->dpad <= 80) ? 2 : 1;
+  a.fp16 = p->act_fp16;
   a.scale_log2 = p->scale * 1.4426950408889634f;
   int rc;
   {

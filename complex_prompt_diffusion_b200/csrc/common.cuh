@@ -165,10 +165,13 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
-// Instruction descriptor for kind::f16, A=B=bf16 (K-major), D=fp32, M x N tile.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// Instruction descriptor for kind::f16 (K-major A and B, D = fp32, M x N tile).  The A and B element formats
+// are independent fields (0 = fp16, 1 = bf16): activations may be fp16 while weights are bf16.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, bool a_fp16, bool b_fp16) {
+  return (1u << 4) | ((a_fp16 ? 0u : 1u) << 7) | ((b_fp16 ? 0u : 1u) << 10) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
 }
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) { return umma_idesc_f16(M, N, false, false); }
 // Shared-memory matrix descriptor: K-major operand, 128B swizzle, rows of 128 bytes (64 bf16), 8-row
 // swizzle atoms 1024 B apart (SBO), version 1 (Blackwell).  `addr` = shared::cta byte address.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t addr) {
@@ -222,6 +225,20 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t u) {
+  __half2 v = *reinterpret_cast<__half2*>(&u);
+  return __half22float2(v);
+}
+// activation tensors are 16-bit, either bf16 or fp16 (runtime flag, warp-uniform)
+__device__ __forceinline__ uint32_t pack_act2(float lo, float hi, bool f16) { return f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); }
+__device__ __forceinline__ float2 unpack_act2(uint32_t u, bool f16) { return f16 ? unpack_f16x2(u) : unpack_bf16x2(u); }
+__device__ __forceinline__ float round_act(float v, bool f16) {
+  return f16 ? __half2float(__float2half_rn(v)) : __bfloat162float(__float2bfloat16_rn(v));
 }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }

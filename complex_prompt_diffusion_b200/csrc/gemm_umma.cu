@@ -34,6 +34,8 @@ struct ConvGeom {
   int n_store;     // columns of D (n_out, or n_out/2 for GEGLU)
   int epilogue;
   int rowvec_stride, ld_res, ldd;
+  int out_fp16;       // D / residual element type: 1 = fp16, 0 = bf16
+  uint32_t idesc;     // tcgen05 instruction descriptor (encodes the A / B element formats)
 };
 
 struct GemmArgs {
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_conv_kernel(const __grid_
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      const uint32_t idesc = g.idesc;
       int stage = 0;
       uint32_t phase = 0;
       for (int kt = 0; kt < num_k; ++kt) {
@@ -165,6 +167,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_conv_kernel(const __grid_
     }
   } else {
     // ================= epilogue (warps 2..5) =================
+    const bool of16 = g.out_fp16 != 0;
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;       // row within the tile
     // output row (pixel) of this thread
@@ -209,13 +212,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_conv_kernel(const __grid_
               g1 += __ldg(args.bias + n_tile * BN + HALF + c + e + 1);
             }
             // the reference rounds the projection to the model dtype before x * gelu(gate) (attention.py:98-100)
-            a0 = __bfloat162float(__float2bfloat16_rn(a0));
-            a1 = __bfloat162float(__float2bfloat16_rn(a1));
-            g0 = __bfloat162float(__float2bfloat16_rn(g0));
-            g1 = __bfloat162float(__float2bfloat16_rn(g1));
-            g0 = __bfloat162float(__float2bfloat16_rn(gelu_erf_f(g0)));
-            g1 = __bfloat162float(__float2bfloat16_rn(gelu_erf_f(g1)));
-            packed[e / 2] = pack_bf16x2(a0 * g0, a1 * g1);
+            a0 = round_act(a0, of16);
+            a1 = round_act(a1, of16);
+            g0 = round_act(gelu_erf_f(round_act(g0, of16)), of16);
+            g1 = round_act(gelu_erf_f(round_act(g1, of16)), of16);
+            packed[e / 2] = pack_act2(a0 * g0, a1 * g1, of16);
           }
           uint4* dst = reinterpret_cast<uint4*>(args.d + row * g.ldd + ncol0 + c);
           dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
@@ -252,14 +253,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_conv_kernel(const __grid_
               }
               if (args.residual) {
                 const uint4 rr = __ldg(reinterpret_cast<const uint4*>(args.residual + row * g.ld_res + col));
-                const float2 r0 = unpack_bf16x2(rr.x), r1 = unpack_bf16x2(rr.y), r2 = unpack_bf16x2(rr.z),
-                             r3 = unpack_bf16x2(rr.w);
+                const float2 r0 = unpack_act2(rr.x, of16), r1 = unpack_act2(rr.y, of16), r2 = unpack_act2(rr.z, of16),
+                             r3 = unpack_act2(rr.w, of16);
                 f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y;
                 f[4] += r2.x; f[5] += r2.y; f[6] += r3.x; f[7] += r3.y;
               }
               *reinterpret_cast<uint4*>(args.d + row * g.ldd + col) =
-                  make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                             pack_bf16x2(f[6], f[7]));
+                  make_uint4(pack_act2(f[0], f[1], of16), pack_act2(f[2], f[3], of16), pack_act2(f[4], f[5], of16),
+                             pack_act2(f[6], f[7], of16));
             }
           }
         }
@@ -342,11 +343,13 @@ extern "C" cpd_status cpd_gemm_conv(const cpd_gemm_params* p, void* stream) {
   g.rowvec_stride = p->rowvec_stride;
   g.ld_res = p->ld_res;
   g.ldd = p->ldd;
+  g.out_fp16 = p->out_fp16;
 
   int variant = p->variant;
   if (variant == 0) variant = (p->n_out % 256 == 0 || p->n_out >= 1024) ? 2 : 1;
   if (p->epilogue == CPD_EPI_GEGLU) variant = 1;
   const int BN = variant == 2 ? 256 : 128;
+  g.idesc = umma_idesc_f16(BM, BN, p->a_fp16 != 0, p->b_fp16 != 0);
   if (p->epilogue == CPD_EPI_GEGLU) {
     CPD_REQUIRE(p->n_out % 128 == 0, "cpd_gemm_conv: GEGLU needs n_out %% 128 == 0 (got %d)", p->n_out);
     g.n_store = p->n_out / 2;

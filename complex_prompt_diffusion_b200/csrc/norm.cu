@@ -10,7 +10,7 @@ constexpr int GROUPS = 32;
 // ---- GroupNorm pass 1: per-(image, group) sum / sum of squares -----------------------------------
 // grid = (chunks, n_img).  Thread t owns channel vector (t % vec_per_px) and pixel lane (t / vec_per_px).
 __global__ void __launch_bounds__(512) gn_stats_kernel(const bf16* __restrict__ a0, const bf16* __restrict__ a1, int c0,
-                                                       int c1, int hw, int px_per_block, double* __restrict__ stats) {
+                                                       int c1, int hw, int px_per_block, int f16, double* __restrict__ stats) {
   extern __shared__ float sh[];  // [2][C]
   const int C = c0 + c1;
   const int vec_per_px = C / 8;
@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const bf16* __restrict__ 
       const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float2 f = unpack_bf16x2(u[e]);
+        const float2 f = unpack_act2(u[e], f16 != 0);
         s[2 * e] += f.x; ss[2 * e] += f.x * f.x;
         s[2 * e + 1] += f.y; ss[2 * e + 1] += f.y * f.y;
       }
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const bf16* __restrict__ 
 __global__ void __launch_bounds__(512) gn_apply_kernel(const bf16* __restrict__ a0, const bf16* __restrict__ a1, int c0,
                                                        int c1, int hw, int px_per_block, const double* __restrict__ stats,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                       float eps, int silu, bf16* __restrict__ out) {
+                                                       float eps, int silu, int f16, bf16* __restrict__ out) {
   extern __shared__ float sh[];  // scale[C], shift[C]
   const int C = c0 + c1;
   const int vec_per_px = C / 8;
@@ -102,11 +102,11 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(const bf16* __restrict__ 
     uint32_t o[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float2 f = unpack_bf16x2(u[e]);
+      const float2 f = unpack_act2(u[e], f16 != 0);
       float y0 = f.x * sc[2 * e] + sf[2 * e];
       float y1 = f.y * sc[2 * e + 1] + sf[2 * e + 1];
       if (silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
-      o[e] = pack_bf16x2(y0, y1);
+      o[e] = pack_act2(y0, y1, f16 != 0);
     }
     *reinterpret_cast<uint4*>(out + ((int64_t)n * hw + p) * C + ch) = make_uint4(o[0], o[1], o[2], o[3]);
   }
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(const bf16* __restrict__ 
 template <int MAXV>  // max 16-byte vectors per lane
 __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, int rows, int c,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                        float eps, bf16* __restrict__ out) {
+                                                        float eps, int f16, bf16* __restrict__ out) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
       const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float2 f = unpack_bf16x2(w[e]);
+        const float2 f = unpack_act2(w[e], f16 != 0);
         v[i][2 * e] = f.x; v[i][2 * e + 1] = f.y;
         sum += f.x + f.y;
       }
@@ -165,8 +165,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
       uint32_t o[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e)
-        o[e] = pack_bf16x2((v[i][2 * e] - mean) * rstd * gg[2 * e] + bb[2 * e],
-                           (v[i][2 * e + 1] - mean) * rstd * gg[2 * e + 1] + bb[2 * e + 1]);
+        o[e] = pack_act2((v[i][2 * e] - mean) * rstd * gg[2 * e] + bb[2 * e],
+                         (v[i][2 * e + 1] - mean) * rstd * gg[2 * e + 1] + bb[2 * e + 1], f16 != 0);
       *reinterpret_cast<uint4*>(out + (int64_t)warp * c + vi * 8) = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
 }  // namespace
 
 extern "C" cpd_status cpd_groupnorm(const void* a0, const void* a1, int c0, int c1, int n_img, int hw, const float* gamma,
-                                    const float* beta, float eps, int silu, double* stats, void* out, void* stream) {
+                                    const float* beta, float eps, int silu, int act_fp16, double* stats, void* out, void* stream) {
   CPD_REQUIRE(a0 && gamma && beta && stats && out, "cpd_groupnorm: null pointer");
   const int C = c0 + c1;
   CPD_REQUIRE(c0 > 0 && c1 >= 0 && c0 % 8 == 0 && c1 % 8 == 0 && C % GROUPS == 0 && C <= 4096,
@@ -196,16 +196,16 @@ extern "C" cpd_status cpd_groupnorm(const void* a0, const void* a1, int c0, int 
   if (px_per_block < lanes) px_per_block = lanes;
   chunks = (hw + px_per_block - 1) / px_per_block;
   const size_t shm = sizeof(float) * 2 * C;
-  gn_stats_kernel<<<dim3(chunks, n_img), threads, shm, s>>>((const bf16*)a0, (const bf16*)a1, c0, c1, hw, px_per_block, stats);
+  gn_stats_kernel<<<dim3(chunks, n_img), threads, shm, s>>>((const bf16*)a0, (const bf16*)a1, c0, c1, hw, px_per_block, act_fp16, stats);
   CPD_CUDA_CHECK(cudaGetLastError());
   gn_apply_kernel<<<dim3(chunks, n_img), threads, shm, s>>>((const bf16*)a0, (const bf16*)a1, c0, c1, hw, px_per_block, stats,
-                                                           gamma, beta, eps, silu, (bf16*)out);
+                                                           gamma, beta, eps, silu, act_fp16, (bf16*)out);
   CPD_CUDA_CHECK(cudaGetLastError());
   return CPD_OK;
 }
 
 extern "C" cpd_status cpd_layernorm(const void* x, int rows, int c, const float* gamma, const float* beta, float eps,
-                                    void* out, void* stream) {
+                                    int act_fp16, void* out, void* stream) {
   CPD_REQUIRE(x && gamma && beta && out, "cpd_layernorm: null pointer");
   CPD_REQUIRE(c > 0 && c % 8 == 0 && c <= 2048, "cpd_layernorm: c=%d must be a multiple of 8 and <= 2048", c);
   CPD_REQUIRE(rows >= 0, "cpd_layernorm: rows=%d", rows);
@@ -213,9 +213,9 @@ extern "C" cpd_status cpd_layernorm(const void* x, int rows, int c, const float*
   cudaStream_t s = (cudaStream_t)stream;
   const int blocks = (rows + 7) / 8;
   const int nvec = c / 8;
-  if (nvec <= 64) layernorm_kernel<2><<<blocks, 256, 0, s>>>((const bf16*)x, rows, c, gamma, beta, eps, (bf16*)out);
-  else if (nvec <= 160) layernorm_kernel<5><<<blocks, 256, 0, s>>>((const bf16*)x, rows, c, gamma, beta, eps, (bf16*)out);
-  else layernorm_kernel<8><<<blocks, 256, 0, s>>>((const bf16*)x, rows, c, gamma, beta, eps, (bf16*)out);
+  if (nvec <= 64) layernorm_kernel<2><<<blocks, 256, 0, s>>>((const bf16*)x, rows, c, gamma, beta, eps, act_fp16, (bf16*)out);
+  else if (nvec <= 160) layernorm_kernel<5><<<blocks, 256, 0, s>>>((const bf16*)x, rows, c, gamma, beta, eps, act_fp16, (bf16*)out);
+  else layernorm_kernel<8><<<blocks, 256, 0, s>>>((const bf16*)x, rows, c, gamma, beta, eps, act_fp16, (bf16*)out);
   CPD_CUDA_CHECK(cudaGetLastError());
   return CPD_OK;
 }

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const bf16* __restric
 // Input conv: x fp32 NCHW -> bf16 (cast) -> 3x3 pad 1 -> NHWC bf16.  One thread = one pixel x 8 output channels.
 __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, int n, int cin, int h, int w,
                                                       const bf16* __restrict__ wt, const float* __restrict__ bias, int cout,
-                                                      float scale, int rpi, bf16* __restrict__ out) {
+                                                      float scale, int rpi, int f16, bf16* __restrict__ out) {
   const int cvecs = cout / 8;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t total = (int64_t)n * rpi * h * w * cvecs;
@@ -103,14 +103,15 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
     }
   }
   *reinterpret_cast<uint4*>(out + pix * cout + cv * 8) =
-      make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+      make_uint4(pack_act2(acc[0], acc[1], f16 != 0), pack_act2(acc[2], acc[3], f16 != 0), pack_act2(acc[4], acc[5], f16 != 0),
+                 pack_act2(acc[6], acc[7], f16 != 0));
 }
 
 // Output conv: NHWC bf16 (cin) -> 3x3 pad 1 -> NCHW (cout <= 8).  One warp per output pixel.
 template <int COUT>
 __global__ void __launch_bounds__(256) conv_out_kernel(const bf16* __restrict__ a, int n, int h, int w, int cin,
                                                        const bf16* __restrict__ wt, const float* __restrict__ bias,
-                                                       void* __restrict__ out, int out_dtype) {
+                                                       void* __restrict__ out, int out_dtype, int f16) {
   extern __shared__ uint8_t sh_raw[];
   bf16* ws = reinterpret_cast<bf16*>(sh_raw);  // [COUT][9][cin]
   for (int i = threadIdx.x * 8; i < COUT * 9 * cin; i += blockDim.x * 8)
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const bf16* __restrict__ 
       const uint32_t au[4] = {av.x, av.y, av.z, av.w};
       float af[8];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { const float2 f = unpack_bf16x2(au[e]); af[2 * e] = f.x; af[2 * e + 1] = f.y; }
+      for (int e = 0; e < 4; ++e) { const float2 f = unpack_act2(au[e], f16 != 0); af[2 * e] = f.x; af[2 * e + 1] = f.y; }
 #pragma unroll
       for (int o = 0; o < COUT; ++o) {
         const uint4 wv = *reinterpret_cast<const uint4*>(ws + ((int64_t)o * 9 + tap) * cin + v * 8);
@@ -214,19 +215,19 @@ extern "C" cpd_status cpd_small_linear(const void* x, int m, int k, const void* 
 }
 
 extern "C" cpd_status cpd_conv_in(const float* x, int n, int cin, int h, int w, const void* wt, const float* bias, int cout,
-                                  float scale, int rows_per_image, void* out, void* stream) {
+                                  float scale, int rows_per_image, int act_fp16, void* out, void* stream) {
   CPD_REQUIRE(x && wt && out, "cpd_conv_in: null pointer");
   CPD_REQUIRE(n > 0 && cin > 0 && cin <= 8 && h > 0 && w > 0 && cout % 8 == 0, "cpd_conv_in: bad shape n=%d cin=%d h=%d w=%d cout=%d", n, cin, h, w, cout);
   CPD_REQUIRE(rows_per_image >= 1, "cpd_conv_in: rows_per_image=%d", rows_per_image);
   const int64_t total = (int64_t)n * rows_per_image * h * w * (cout / 8);
   conv_in_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, n, cin, h, w, (const bf16*)wt, bias, cout,
-                                                                                   scale, rows_per_image, (bf16*)out);
+                                                                                   scale, rows_per_image, act_fp16, (bf16*)out);
   CPD_CUDA_CHECK(cudaGetLastError());
   return CPD_OK;
 }
 
 extern "C" cpd_status cpd_conv_out(const void* a, int n, int h, int w, int cin, const void* wt, const float* bias, int cout,
-                                   void* out, int out_dtype, void* stream) {
+                                   void* out, int out_dtype, int act_fp16, void* stream) {
   CPD_REQUIRE(a && wt && out, "cpd_conv_out: null pointer");
   CPD_REQUIRE(cout == 4 || cout == 8, "cpd_conv_out: cout=%d unsupported (4 or 8)", cout);
   CPD_REQUIRE(cin % 8 == 0 && (size_t)cout * 9 * cin * 2 <= 200 * 1024, "cpd_conv_out: cin=%d unsupported", cin);
@@ -238,11 +239,11 @@ extern "C" cpd_status cpd_conv_out(const void* a, int n, int h, int w, int cin, 
   if (cout == 4) {
     static bool cfg = false;
     if (!cfg) { CPD_CUDA_CHECK(cudaFuncSetAttribute(conv_out_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfg = true; }
-    conv_out_kernel<4><<<blocks, 256, shm, s>>>((const bf16*)a, n, h, w, cin, (const bf16*)wt, bias, out, out_dtype);
+    conv_out_kernel<4><<<blocks, 256, shm, s>>>((const bf16*)a, n, h, w, cin, (const bf16*)wt, bias, out, out_dtype, act_fp16);
   } else {
     static bool cfg = false;
     if (!cfg) { CPD_CUDA_CHECK(cudaFuncSetAttribute(conv_out_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfg = true; }
-    conv_out_kernel<8><<<blocks, 256, shm, s>>>((const bf16*)a, n, h, w, cin, (const bf16*)wt, bias, out, out_dtype);
+    conv_out_kernel<8><<<blocks, 256, shm, s>>>((const bf16*)a, n, h, w, cin, (const bf16*)wt, bias, out, out_dtype, act_fp16);
   }
   CPD_CUDA_CHECK(cudaGetLastError());
   return CPD_OK;

@@ -67,7 +67,7 @@ class UNetModel:
                     transformer_depth=1, context_dim=768, use_linear_in_transformer=False, use_spatial_transformer=True,
                     legacy=False)
 
-    def __init__(self, state_dict=None, device="cuda", **config):
+    def __init__(self, state_dict=None, device="cuda", act_dtype=torch.float16, eps_dtype=torch.float32, **config):
         cfg = dict(self.DEFAULTS)
         cfg.update({k: v for k, v in config.items() if k in self.DEFAULTS})
         if not cfg["use_spatial_transformer"] or cfg["legacy"]:
@@ -80,7 +80,13 @@ class UNetModel:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("UNetModel runs on CUDA only: there is no CPU fallback for the hot path")
-        self.dtype = torch.bfloat16
+        self.dtype = torch.bfloat16  # model (weight) dtype
+        if act_dtype not in (torch.float16, torch.bfloat16):
+            raise ValueError("act_dtype must be torch.float16 or torch.bfloat16")
+        # Inter-kernel activations are 16-bit.  fp16 (default) has 3 more mantissa bits than bf16; tcgen05
+        # kind::f16 multiplies fp16 activations with bf16 weights at the same rate ("precision").
+        self.act_dtype = act_dtype
+        self.eps_dtype = eps_dtype
         self.model_channels = cfg["model_channels"]
         self.inputs, self.middle, self.outputs = _enumerate_blocks(cfg)
         self.w = {}
@@ -212,7 +218,8 @@ class UNetModel:
         return self
 
     # ---- workspace ---------------------------------------------------------------------------------
-    def _buf(self, name, numel, dtype=torch.bfloat16):
+    def _buf(self, name, numel, dtype=None):
+        dtype = self.act_dtype if dtype is None else dtype
         key = (name, numel, dtype)
         t = self._ws.get(key)
         if t is None:
@@ -226,10 +233,11 @@ class UNetModel:
         key = (context.data_ptr(), tuple(context.shape), context._version)
         if self._ctx_key == key:
             return
-        ctx = context.to(self.device, torch.bfloat16)
+        # the reference casts the context to the model dtype first (denoiser.py:373-385), then it is an activation
+        ctx = context.to(self.device, torch.bfloat16).to(self.act_dtype)
         rc, ntok, D = ctx.shape
         nk_pad = (ntok + 15) // 16 * 16
-        ctx_pad = torch.zeros(rc, nk_pad, D, dtype=torch.bfloat16, device=self.device)
+        ctx_pad = torch.zeros(rc, nk_pad, D, dtype=self.act_dtype, device=self.device)
         ctx_pad[:, :ntok] = ctx
         kv = {}
         for prefix, layers in self._all_blocks():
@@ -239,8 +247,8 @@ class UNetModel:
                 b = f"{prefix}{j}.transformer_blocks.0."
                 wk, wv = self.w[b + "attn2.k.w"], self.w[b + "attn2.v.w"]
                 ip = wk.shape[0]
-                kc = torch.empty(rc * nk_pad, ip, dtype=torch.bfloat16, device=self.device)
-                vt = torch.empty(ip, rc * nk_pad, dtype=torch.bfloat16, device=self.device)
+                kc = torch.empty(rc * nk_pad, ip, dtype=self.act_dtype, device=self.device)
+                vt = torch.empty(ip, rc * nk_pad, dtype=self.act_dtype, device=self.device)
                 ops.gemm_conv(ctx_pad, wk, kc, n_img=1, h=1, w=rc * nk_pad, c0=D, n_out=ip)
                 ops.gemm_conv(wv, ctx_pad, vt, n_img=1, h=1, w=ip, c0=D, n_out=rc * nk_pad)
                 kv[b] = (kc, vt)
@@ -361,11 +369,11 @@ class UNetModel:
         W = self.w
         m = t_rows.numel()
         mc, ted = self.model_channels, self.ted
-        temb = self._buf("temb", m * mc)
+        temb = self._buf("temb", m * mc, torch.bfloat16)
         ops.timestep_embedding(t_rows, temb, dim=mc, round_t_bf16=False)
-        e1 = self._buf("e1", m * ted)
+        e1 = self._buf("e1", m * ted, torch.bfloat16)
         ops.small_linear(temb, W["te0.w"], W["te0.b"], m=m, k=mc, n=ted, out_bf16=e1)
-        emb = self._buf("emb", m * ted)
+        emb = self._buf("emb", m * ted, torch.bfloat16)
         ops.small_linear(e1, W["te2.w"], W["te2.b"], m=m, k=ted, n=ted, silu_in=True, out_bf16=emb)
         emb_all = self._buf("emb_all", m * self.emb_total, torch.float32)
         ops.small_linear(emb, W["emb_all.w"], W["emb_all.b"], m=m, k=ted, n=self.emb_total, silu_in=True, out_f32=emb_all)
@@ -398,7 +406,7 @@ class UNetModel:
         gn = self._buf("gn", R * h * w * ch)
         ops.groupnorm(hcur, W["out.gn.g"], W["out.gn.b"], gn, stats, n_img=R, hw=h * w, c0=ch, eps=1e-5, silu=True)
         cout = self.cfg["out_channels"]
-        out = self._buf("eps", R * cout * h * w).view(R, cout, h, w)
+        out = self._buf("eps", R * cout * h * w, self.eps_dtype).view(R, cout, h, w)
         ops.conv_out(gn, W["out.w"], W["out.b"], out, n=R, h=h, w=w, cin=ch, cout=cout)
         return (out, skips) if return_skips else out
 
@@ -406,7 +414,7 @@ class UNetModel:
     def forward_rows(self, x, c_in, t, rows_per_image):
         """Fast path used by the Denoiser: x [B,4,h,w] fp32 (unscaled), every image is evaluated on
         `rows_per_image` conditioning rows sharing x * c_in and the timestep t (denoiser.py:383-393).
-        Returns eps rows [B*rows_per_image, 4, h, w] bf16, image-major."""
+        Returns eps rows [B*rows_per_image, 4, h, w] (eps_dtype), image-major."""
         t_rows = torch.full((1,), float(t), dtype=torch.float32, device=self.device)
         return self._forward_impl(x.contiguous(), float(c_in), rows_per_image, t_rows, shared_t=True)
 

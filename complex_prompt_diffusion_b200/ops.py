@@ -1,12 +1,40 @@
 """Thin torch-tensor wrappers over the C ABI (include/cpd_b200.h).  Device memory and the current CUDA
-stream come from torch; all arithmetic happens in libcpd_b200.so.  No fallbacks."""
+stream come from torch; all arithmetic happens in libcpd_b200.so.  No fallbacks.
+
+Activation tensors are 16-bit: torch.float16 or torch.bfloat16 (the `act_fp16` flag of the C ABI is derived
+from the tensor dtype); weights are always bf16."""
 import ctypes as C
 
 import torch
 
-from . import _lib
-from ._lib import (AttnParams, GemmParams, StepParams, check, load, ptr, stream_ptr, CPD_BF16, CPD_F32, DTYPE_CODE,
+from ._lib import (AttnParams, GemmParams, StepParams, check, load, ptr, stream_ptr, CPD_BF16, CPD_F32, DTYPE_CODE,  # noqa: F401
                    CPD_EPI_NONE, CPD_EPI_GEGLU, CPD_MAX_SUBPROMPTS)
+
+LAUNCHES = 0    # kernels launched through this module (bench.py reports it as gpu_launches)
+PROFILE = None  # when a list: (kind, start_event, end_event, flops) per tensor-core launch (bench.py roofline leg)
+
+_ACT = (torch.float16, torch.bfloat16)
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+class _Prof:
+    def __init__(self, kind, flops):
+        self.kind, self.flops = kind, flops
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e1.record()
+            PROFILE.append((self.kind, self.e0, self.e1, self.flops))
 
 
 def _req(t, dtype, name):
@@ -18,6 +46,17 @@ def _req(t, dtype, name):
         raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
     if not t.is_contiguous():
         raise RuntimeError(f"{name} must be contiguous")
+
+
+def _act(t, name, like=None):
+    """Validate a 16-bit activation tensor; returns 1 for fp16, 0 for bf16."""
+    if t is None:
+        return None
+    if not t.is_cuda or t.dtype not in _ACT:
+        raise RuntimeError(f"{name} must be a CUDA fp16/bf16 tensor, got {t.dtype} on {t.device}")
+    if like is not None and t.dtype != like:
+        raise RuntimeError(f"{name} must be {like}, got {t.dtype}")
+    return int(t.dtype == torch.float16)
 
 
 def sampler_step(eps, x, *, n_sub, weights, mask_scalars, masks, guidance, sampler, pred_type, sigma_hat, v_c_eps=0.0,
@@ -66,19 +105,20 @@ def sampler_step(eps, x, *, n_sub, weights, mask_scalars, masks, guidance, sampl
     p.dpm_ratio, p.dpm_expm1, p.dpm_c1, p.dpm_c2 = float(dpm_ratio), float(dpm_expm1), float(dpm_c1), float(dpm_c2)
     p.dpm_first, p.write_old = int(dpm_first), int(write_old)
     check(load().cpd_sampler_step(C.byref(p), stream_ptr()), "cpd_sampler_step")
+    _count()
     return x
 
 
 def gemm_conv(a0, wt, out, *, n_img, h, w, c0, n_out, a1=None, c1=0, ksize=1, stride=1, bias=None, rowvec=None,
               rowvec_stride=0, residual=None, ld_res=0, ldd=None, epilogue=CPD_EPI_NONE, variant=0, m_valid=0):
-    _req(a0, torch.bfloat16, "a0")
-    _req(a1, torch.bfloat16, "a1")
-    _req(wt, torch.bfloat16, "wt")
-    _req(out, torch.bfloat16, "out")
+    """a0/a1 and wt are 16-bit (fp16 or bf16, independently); out/residual share one 16-bit dtype."""
+    a_f16 = _act(a0, "a0")
+    _act(a1, "a1", like=a0.dtype)
+    b_f16 = _act(wt, "wt")
+    o_f16 = _act(out, "out")
+    _act(residual, "residual", like=out.dtype)
     _req(bias, torch.float32, "bias")
     _req(rowvec, torch.float32, "rowvec")
-    if residual is not None and (not residual.is_cuda or residual.dtype != torch.bfloat16):
-        raise RuntimeError("residual must be a CUDA bf16 tensor")
     p = GemmParams()
     p.a0, p.a1, p.c0, p.c1 = a0.data_ptr(), (a1.data_ptr() if a1 is not None else None), c0, c1
     p.n_img, p.h_in, p.w_in, p.ksize, p.stride = n_img, h, w, ksize, stride
@@ -91,30 +131,36 @@ def gemm_conv(a0, wt, out, *, n_img, h, w, c0, n_out, a1=None, c1=0, ksize=1, st
     p.d = out.data_ptr()
     p.ldd = ldd if ldd is not None else (n_out // 2 if epilogue == CPD_EPI_GEGLU else n_out)
     p.epilogue, p.variant, p.m_valid = epilogue, variant, m_valid
-    check(load().cpd_gemm_conv(C.byref(p), stream_ptr()), "cpd_gemm_conv")
+    p.a_fp16, p.b_fp16, p.out_fp16 = a_f16, b_f16, o_f16
+    flops = 2.0 * n_img * (h // stride) * (w // stride) * n_out * ksize * ksize * (c0 + c1)
+    with _Prof("gemm_conv", flops):
+        check(load().cpd_gemm_conv(C.byref(p), stream_ptr()), "cpd_gemm_conv")
+    _count()
     return out
 
 
 def groupnorm(a0, gamma, beta, out, stats, *, n_img, hw, c0, a1=None, c1=0, eps=1e-5, silu=True):
-    _req(a0, torch.bfloat16, "a0")
-    _req(a1, torch.bfloat16, "a1")
+    f16 = _act(a0, "a0")
+    _act(a1, "a1", like=a0.dtype)
+    _act(out, "out", like=a0.dtype)
     _req(gamma, torch.float32, "gamma")
     _req(beta, torch.float32, "beta")
-    _req(out, torch.bfloat16, "out")
     _req(stats, torch.float64, "stats")
     if stats.numel() < n_img * 64:
         raise RuntimeError("stats scratch too small")
-    check(load().cpd_groupnorm(ptr(a0), ptr(a1), c0, c1, n_img, hw, ptr(gamma), ptr(beta), float(eps), int(silu), ptr(stats),
+    check(load().cpd_groupnorm(ptr(a0), ptr(a1), c0, c1, n_img, hw, ptr(gamma), ptr(beta), float(eps), int(silu), f16, ptr(stats),
                                ptr(out), stream_ptr()), "cpd_groupnorm")
+    _count(2)
     return out
 
 
 def layernorm(x, gamma, beta, out, *, rows, c, eps=1e-5):
-    _req(x, torch.bfloat16, "x")
+    f16 = _act(x, "x")
+    _act(out, "out", like=x.dtype)
     _req(gamma, torch.float32, "gamma")
     _req(beta, torch.float32, "beta")
-    _req(out, torch.bfloat16, "out")
-    check(load().cpd_layernorm(ptr(x), rows, c, ptr(gamma), ptr(beta), float(eps), ptr(out), stream_ptr()), "cpd_layernorm")
+    check(load().cpd_layernorm(ptr(x), rows, c, ptr(gamma), ptr(beta), float(eps), f16, ptr(out), stream_ptr()), "cpd_layernorm")
+    _count()
     return out
 
 
@@ -122,6 +168,7 @@ def timestep_embedding(t, out, *, dim, round_t_bf16=True):
     _req(t, torch.float32, "t")
     _req(out, torch.bfloat16, "out")
     check(load().cpd_timestep_embedding(ptr(t), t.numel(), dim, int(round_t_bf16), ptr(out), stream_ptr()), "cpd_timestep_embedding")
+    _count()
     return out
 
 
@@ -133,43 +180,49 @@ def small_linear(x, w, b, *, m, k, n, silu_in=False, out_f32=None, out_bf16=None
     _req(out_bf16, torch.bfloat16, "out_bf16")
     check(load().cpd_small_linear(ptr(x), m, k, ptr(w), ptr(b), n, int(silu_in), ptr(out_f32), ptr(out_bf16),
                                   ld_out if ld_out is not None else n, stream_ptr()), "cpd_small_linear")
+    _count()
 
 
 def conv_in(x, wt, bias, out, *, n, cin, h, w, cout, scale=1.0, rows_per_image=1):
     _req(x, torch.float32, "x")
     _req(wt, torch.bfloat16, "wt")
     _req(bias, torch.float32, "bias")
-    _req(out, torch.bfloat16, "out")
-    check(load().cpd_conv_in(ptr(x), n, cin, h, w, ptr(wt), ptr(bias), cout, float(scale), int(rows_per_image), ptr(out),
+    f16 = _act(out, "out")
+    check(load().cpd_conv_in(ptr(x), n, cin, h, w, ptr(wt), ptr(bias), cout, float(scale), int(rows_per_image), f16, ptr(out),
                              stream_ptr()), "cpd_conv_in")
+    _count()
     return out
 
 
 def conv_out(a, wt, bias, out, *, n, h, w, cin, cout):
-    _req(a, torch.bfloat16, "a")
+    f16 = _act(a, "a")
     _req(wt, torch.bfloat16, "wt")
     _req(bias, torch.float32, "bias")
     if out.dtype not in (torch.bfloat16, torch.float32) or not out.is_cuda:
         raise RuntimeError("out must be a CUDA bf16/fp32 tensor")
-    check(load().cpd_conv_out(ptr(a), n, h, w, cin, ptr(wt), ptr(bias), cout, ptr(out), DTYPE_CODE[out.dtype], stream_ptr()),
+    check(load().cpd_conv_out(ptr(a), n, h, w, cin, ptr(wt), ptr(bias), cout, ptr(out), DTYPE_CODE[out.dtype], f16, stream_ptr()),
           "cpd_conv_out")
+    _count()
     return out
 
 
 def upsample2x(a, out, *, n, h, w, c):
-    _req(a, torch.bfloat16, "a")
-    _req(out, torch.bfloat16, "out")
+    _act(a, "a")
+    _act(out, "out", like=a.dtype)
     check(load().cpd_upsample2x(ptr(a), n, h, w, c, ptr(out), stream_ptr()), "cpd_upsample2x")
+    _count()
     return out
 
 
 def attention(q, k, vt, o, *, ldq, ldk, ldvt, ldo, batch, heads, nq, nk, nk_pad, dpad, scale, kv_batch=0):
-    for t, nme in ((q, "q"), (k, "k"), (vt, "vt"), (o, "o")):
-        if not t.is_cuda or t.dtype != torch.bfloat16:
-            raise RuntimeError(f"{nme} must be a CUDA bf16 tensor")
+    f16 = _act(q, "q")
+    for t, nme in ((k, "k"), (vt, "vt"), (o, "o")):
+        _act(t, nme, like=q.dtype)
     p = AttnParams()
     p.q, p.ldq, p.k, p.ldk, p.vt, p.ldvt, p.o, p.ldo = q.data_ptr(), ldq, k.data_ptr(), ldk, vt.data_ptr(), ldvt, o.data_ptr(), ldo
     p.batch, p.heads, p.nq, p.nk, p.nk_pad, p.dpad, p.scale = batch, heads, nq, nk, nk_pad, dpad, float(scale)
-    p.kv_batch = kv_batch
-    check(load().cpd_attention(C.byref(p), stream_ptr()), "cpd_attention")
+    p.kv_batch, p.act_fp16 = kv_batch, f16
+    with _Prof("attention", 4.0 * batch * heads * nq * nk * dpad):
+        check(load().cpd_attention(C.byref(p), stream_ptr()), "cpd_attention")
+    _count()
     return o

@@ -120,6 +120,9 @@ typedef struct {
   int epilogue;
   int variant; /* 0 = auto; 1 = 128x128 tile (3 stages), 2 = 128x256 tile (4 stages) */
   int m_valid; /* plain GEMM only: number of valid rows (<= w_in); 0 = all */
+  int a_fp16;  /* element type of a0/a1: 1 = fp16, 0 = bf16 (16-bit either way; tcgen05 kind::f16 takes both) */
+  int b_fp16;  /* element type of wt */
+  int out_fp16;/* element type of d and residual */
 } cpd_gemm_params;
 
 cpd_status cpd_gemm_conv(const cpd_gemm_params* p, void* stream);
@@ -130,11 +133,12 @@ cpd_status cpd_gemm_conv(const cpd_gemm_params* p, void* stream);
  * the call.  out: bf16 [n_img*hw][c0 + c1].
  */
 cpd_status cpd_groupnorm(const void* a0, const void* a1, int c0, int c1, int n_img, int hw, const float* gamma,
-                         const float* beta, float eps, int silu, double* stats, void* out, void* stream);
+                         const float* beta, float eps, int silu, int act_fp16, double* stats, void* out, void* stream);
 
-/* LayerNorm over the last dim of [rows][c] bf16 (attention.py:476-478), eps 1e-5. */
-cpd_status cpd_layernorm(const void* x, int rows, int c, const float* gamma, const float* beta, float eps, void* out,
-                         void* stream);
+/* LayerNorm over the last dim of [rows][c] (attention.py:476-478), eps 1e-5.
+ * act_fp16 (here and below): activation tensors are 16-bit, 1 = fp16, 0 = bf16.  Weights are always bf16. */
+cpd_status cpd_layernorm(const void* x, int rows, int c, const float* gamma, const float* beta, float eps, int act_fp16,
+                         void* out, void* stream);
 
 /* Sinusoidal timestep embedding (models/util.py:65-85): t [rows] fp32 -> out bf16 [rows][dim], cos first.
  * t is first rounded to the model dtype (bf16) as denoiser.py:393 does. */
@@ -151,12 +155,12 @@ cpd_status cpd_small_linear(const void* x, int m, int k, const void* w, const fl
  * convolved; the result is written `rows_per_image` times (one copy per conditioning row), image-major:
  * out bf16 NHWC [n * rows_per_image][h][w][cout]; w bf16 [cout][3][3][cin]; cin <= 8. */
 cpd_status cpd_conv_in(const float* x, int n, int cin, int h, int w, const void* wt, const float* bias, int cout,
-                       float scale, int rows_per_image, void* out, void* stream);
+                       float scale, int rows_per_image, int act_fp16, void* out, void* stream);
 
 /* Output conv 3x3 (unet.py:729-733): a bf16 NHWC [n][h][w][cin] (already GroupNorm+SiLU) -> out NCHW
  * [n][cout][h][w] in out_dtype (CPD_BF16 or CPD_F32); cout <= 8. */
 cpd_status cpd_conv_out(const void* a, int n, int h, int w, int cin, const void* wt, const float* bias, int cout,
-                        void* out, int out_dtype, void* stream);
+                        void* out, int out_dtype, int act_fp16, void* stream);
 
 /* Nearest 2x upsample of NHWC bf16 (unet.py:116). */
 cpd_status cpd_upsample2x(const void* a, int n, int h, int w, int c, void* out, void* stream);
@@ -178,6 +182,7 @@ typedef struct {
   int batch, heads, nq, nk, nk_pad, dpad;
   float scale; /* dim_head ** -0.5 */
   int kv_batch; /* number of distinct K/V batches: query batch b reads K/V batch (b % kv_batch); 0 = batch */
+  int act_fp16; /* q, k, vt, o element type: 1 = fp16, 0 = bf16 */
 } cpd_attn_params;
 
 cpd_status cpd_attention(const cpd_attn_params* p, void* stream);

@@ -234,3 +234,62 @@ def test_conv_in_out_upsample(ops):
     ops.upsample2x(a, up, n=n, h=h, w=w, c=cin)
     ref3 = F.interpolate(a.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
     assert torch.equal(up.float(), ref3)
+
+
+# ------------------------------------------------------------------------------------------------ fp16 activations x bf16 weights
+@pytest.mark.parametrize("a_dt,b_dt,o_dt", [(torch.float16, torch.bfloat16, torch.float16), (torch.bfloat16, torch.float16, torch.float16),
+                                            (torch.float16, torch.float16, torch.bfloat16)])
+def test_gemm_mixed_operand_formats(ops, a_dt, b_dt, o_dt):
+    """tcgen05 kind::f16 takes the A and B element formats independently (fp16 activations x bf16 weights)."""
+    M, N, K = 512, 384, 320
+    g = torch.Generator().manual_seed(9)
+    a = torch.randn(M, K, generator=g).to(a_dt).to(DEV)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(b_dt).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    res = torch.randn(M, N, generator=g).to(o_dt).to(DEV)
+    out = torch.empty(M, N, dtype=o_dt, device=DEV)
+    ops.gemm_conv(a, w, out, n_img=1, h=1, w=M, c0=K, n_out=N, bias=bias, residual=res, ld_res=N)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t() + bias + res.float()
+    r = rel(out, ref)
+    print(f"gemm a={a_dt} b={b_dt} out={o_dt}: rel {r:.3e}")
+    assert r < (6e-4 if o_dt == torch.float16 else 4e-3)
+
+
+def test_conv_attention_norms_fp16_activations(ops):
+    g = torch.Generator().manual_seed(21)
+    n, h, w, cin, cout = 2, 16, 16, 128, 128
+    x = torch.randn(n, cin, h, w, generator=g).half()
+    wt = bf(torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(9 * cin))
+    out = torch.empty(n, h, w, cout, dtype=torch.float16, device=DEV)
+    ops.gemm_conv(x.permute(0, 2, 3, 1).contiguous().to(DEV), wt.permute(0, 2, 3, 1).contiguous().to(DEV), out, n_img=n, h=h, w=w,
+                  c0=cin, n_out=cout, ksize=3)
+    ref = F.conv2d(x.float().to(DEV), wt.float().to(DEV), padding=1)
+    assert rel(out.permute(0, 3, 1, 2), ref) < 6e-4
+    # attention
+    B, H, Nq, d = 2, 8, 256, 40
+    dpad = 48
+    q, k, v = (torch.randn(B, Nq, H, d, generator=g).half() for _ in range(3))
+    qp, kp, vp = (torch.zeros(B, Nq, H, dpad, dtype=torch.float16) for _ in range(3))
+    qp[..., :d], kp[..., :d], vp[..., :d] = q, k, v
+    vt = vp.permute(2, 3, 0, 1).reshape(H * dpad, B * Nq).contiguous().to(DEV)
+    o = torch.empty(B, Nq, H, dpad, dtype=torch.float16, device=DEV)
+    ops.attention(qp.to(DEV), kp.to(DEV), vt, o, ldq=H * dpad, ldk=H * dpad, ldvt=B * Nq, ldo=H * dpad, batch=B, heads=H, nq=Nq,
+                  nk=Nq, nk_pad=Nq, dpad=dpad, scale=d ** -0.5)
+    qf, kf, vf = (t.float().to(DEV).permute(0, 2, 1, 3) for t in (q, k, v))
+    ref = torch.softmax(qf @ kf.transpose(-1, -2) * d ** -0.5, dim=-1) @ vf
+    r = rel(o[..., :d].permute(0, 2, 1, 3), ref)
+    print(f"attention fp16: rel {r:.3e}")
+    assert r < 1.5e-3
+    # norms
+    C, hw = 320, 1024
+    xx = (torch.randn(n, hw, C, generator=g) * 2 + 0.5).half().to(DEV)
+    gamma, beta = torch.randn(C, generator=g).to(DEV), torch.randn(C, generator=g).to(DEV)
+    og = torch.empty_like(xx)
+    stats = torch.empty(n * 64, dtype=torch.float64, device=DEV)
+    ops.groupnorm(xx, gamma, beta, og, stats, n_img=n, hw=hw, c0=C, silu=True)
+    refg = F.silu(F.group_norm(xx.float().permute(0, 2, 1), 32, gamma, beta, 1e-5))
+    assert rel(og.permute(0, 2, 1), refg) < 6e-4
+    ol = torch.empty_like(xx)
+    ops.layernorm(xx.view(-1, C), gamma, beta, ol.view(-1, C), rows=n * hw, c=C)
+    assert rel(ol, F.layer_norm(xx.float(), (C,), gamma, beta, 1e-5)) < 6e-4

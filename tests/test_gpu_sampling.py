@@ -166,13 +166,13 @@ def test_unsupported_kwargs_fail_loudly(cpd):
 
 
 # ------------------------------------------------------------------------------------------------ UNet
-def _unet_pair(cfg_name, dtype_oracle):
+def _unet_pair(cfg_name, dtype_oracle, act_dtype=torch.float16):
     from complex_prompt_diffusion_b200.models.unet import UNetModel
     from oracle.unet import UNetConfig, OracleUNet, make_weights
     cfg = getattr(UNetConfig, cfg_name)()
     sd = make_weights(cfg, seed=0)
     oracle = OracleUNet(cfg, sd, dtype=dtype_oracle)
-    gpu = UNetModel(sd, device=DEV, model_channels=cfg.model_channels, channel_mult=tuple(cfg.channel_mult),
+    gpu = UNetModel(sd, device=DEV, act_dtype=act_dtype, model_channels=cfg.model_channels, channel_mult=tuple(cfg.channel_mult),
                     attention_resolutions=tuple(cfg.attention_resolutions), num_res_blocks=cfg.num_res_blocks,
                     num_heads=cfg.num_heads, num_head_channels=cfg.num_head_channels, context_dim=cfg.context_dim,
                     use_linear_in_transformer=cfg.use_linear_in_transformer)
@@ -189,9 +189,15 @@ def _layer_report(oracle, gpu, R):
     return rows
 
 
-@pytest.mark.parametrize("cfg_name,hw,R", [("tiny", 16, 3), ("tiny", 32, 2), ("sd15", 16, 2)])
-def test_unet_forward_vs_oracle(cpd, cfg_name, hw, R):
-    cfg, oracle, gpu = _unet_pair(cfg_name, torch.float32)
+# Tolerance on per-row eps (rel-L2 vs the fp32-arithmetic oracle on the same bf16 weights).  With fp16
+# activations (the product default) the north-star bound 1e-2 holds with margin.  With bf16 activations the
+# 8-bit mantissa of every MMA operand puts the noise floor of ANY implementation at ~1.0-1.5e-2 for this
+# depth (torch's own CPU bf16 run of the oracle deviates 1.25e-2 / 1.46e-2 on tiny / SD-1.5), so that mode is
+# only checked against 2e-2.
+@pytest.mark.parametrize("act_dtype,tol", [(torch.float16, 1e-2), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("cfg_name,hw,R", [("tiny", 16, 3), ("tiny", 32, 2), ("sd15", 16, 2), ("sd21", 32, 2)])
+def test_unet_forward_vs_oracle(cpd, cfg_name, hw, R, act_dtype, tol):
+    cfg, oracle, gpu = _unet_pair(cfg_name, torch.float32, act_dtype)
     g = torch.Generator().manual_seed(hw + R)
     x = torch.randn(R, 4, hw, hw, generator=g)
     t = torch.tensor([937.93, 11.278, 500.5][:R])
@@ -208,10 +214,10 @@ def test_unet_forward_vs_oracle(cpd, cfg_name, hw, R):
     for name, r in report:
         print(f"  {name:40s} rel {r:.3e}")
     r = rel(out, ref)
-    print(f"unet {cfg_name} {hw}x{hw} R{R}: eps rel-L2 {r:.3e}")
-    assert len(skips) == 3 * len(cfg.channel_mult)
+    print(f"unet {cfg_name} {hw}x{hw} R{R} act={act_dtype}: eps rel-L2 {r:.3e} (tol {tol})")
+    assert len(skips) == len(gpu.outputs) == (cfg.num_res_blocks + 1) * len(cfg.channel_mult)
     assert torch.isfinite(out.float()).all()
-    assert r < 1e-2
+    assert r < tol
 
 
 def test_unet_forward_rows_equals_forward(cpd):
@@ -253,7 +259,7 @@ def test_end_to_end_sampling_vs_oracle_bf16(cpd, name, steps):
 
         def __call__(self, x, t, ctx, **k):
             o = oracle(x.to(torch.bfloat16).float(), t.float(), ctx.to(torch.bfloat16).float())
-            return o.to(torch.bfloat16), [o] * 12
+            return o, [o] * 12  # eps stays fp32, like UNetModel(eps_dtype=torch.float32)
 
     od = OracleDenoiser(BF16InOut(), dtype=torch.bfloat16)
     od.trace = []

@@ -324,6 +324,8 @@ extern "C" cpd_status cpd_gemm_conv(const cpd_gemm_params* p, void* stream) {
   CPD_REQUIRE(p->ldd % 8 == 0 && (p->residual == nullptr || p->ld_res % 8 == 0), "cpd_gemm_conv: ldd/ld_res must be multiples of 8");
   CPD_REQUIRE(((uintptr_t)p->d & 15) == 0, "cpd_gemm_conv: d must be 16-byte aligned");
   CPD_REQUIRE(p->stride == 1 || p->c1 == 0, "cpd_gemm_conv: stride 2 supports a single source");
+  CPD_REQUIRE((p->a_fp16 != 0) == (p->b_fp16 != 0),
+              "cpd_gemm_conv: A and B must have the same 16-bit format (tcgen05 kind::f16 traps on mixed fp16 x bf16)");
 
   GemmArgs args;
   ConvGeom& g = args.g;

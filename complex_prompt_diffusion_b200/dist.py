@@ -1,0 +1,102 @@
+"""Multi-GPU partitioning of the denoising loop.  One process per GPU (torch.distributed).
+
+Two independent axes:
+  * images (trajectories) are independent -> shard the batch across ranks, NO collective on the data path;
+    the final latents are gathered once at the end (`gather_images`).
+  * when the batch is smaller than the number of GPUs, the (1 + N) conditioning rows of one image are
+    independent UNet evaluations that meet only in the CFG combine -> shard rows across the ranks of an image
+    group and all-gather the eps rows (32-128 KB per rank per step) into every rank of the group; each rank
+    then runs the tiny fused step redundantly so x stays replicated (no broadcast).
+The partitioning arithmetic is plain Python (tested on CPU with the gloo backend, world size 2); the
+all-gather runs on NCCL over NVLink when the tensors are CUDA tensors.
+"""
+from dataclasses import dataclass
+from typing import List
+
+import torch
+
+
+@dataclass
+class Partition:
+    world: int
+    rank: int
+    images: List[int]        # global image indices this rank works on
+    rows: List[int]          # conditioning rows (0 = unconditional) this rank evaluates for each of its images
+    group_ranks: List[int]   # ranks sharing the same images (row-sharding group); [rank] when images are sharded
+    rows_total: int
+
+    @property
+    def needs_allgather(self):
+        return len(self.group_ranks) > 1
+
+
+def partition(batch: int, rows_total: int, world: int, rank: int) -> Partition:
+    """batch >= world: contiguous image shards (sizes differ by at most 1), every rank evaluates all rows.
+    batch < world: ranks are split into `batch` groups (sizes differ by at most 1); the ranks of a group split the
+    rows of that image between them (ranks beyond rows_total in a group stay idle but still step x)."""
+    if world <= 0 or not 0 <= rank < world:
+        raise ValueError(f"bad rank {rank} / world {world}")
+    if batch <= 0 or rows_total <= 0:
+        return Partition(world, rank, [], [], [rank], rows_total)
+    if batch >= world:
+        base, extra = divmod(batch, world)
+        start = rank * base + min(rank, extra)
+        n = base + (1 if rank < extra else 0)
+        return Partition(world, rank, list(range(start, start + n)), list(range(rows_total)), [rank], rows_total)
+    base, extra = divmod(world, batch)
+    # group g owns ranks [g_start, g_start + size)
+    g, g_start = 0, 0
+    while True:
+        size = base + (1 if g < extra else 0)
+        if rank < g_start + size:
+            break
+        g_start += size
+        g += 1
+    members = list(range(g_start, g_start + size))
+    local = rank - g_start
+    active = min(size, rows_total)
+    if local < active:
+        rb, re_ = divmod(rows_total, active)
+        r0 = local * rb + min(local, re_)
+        rows = list(range(r0, r0 + rb + (1 if local < re_ else 0)))
+    else:
+        rows = []
+    return Partition(world, rank, [g], rows, members, rows_total)
+
+
+def allgather_eps_rows(local_rows: torch.Tensor, part: Partition, group=None) -> torch.Tensor:
+    """local_rows: [len(part.rows), L] eps rows this rank computed for its image.  Returns [rows_total, L] on every
+    rank of the group (row order 0..rows_total-1).  Uses all_gather on a padded buffer (row counts differ by <= 1)."""
+    import torch.distributed as dist
+    if not part.needs_allgather:
+        return local_rows
+    size = len(part.group_ranks)
+    active = min(size, part.rows_total)
+    max_rows = -(-part.rows_total // active)
+    if local_rows.ndim != 2:
+        raise ValueError("allgather_eps_rows expects [rows, L]; idle ranks pass an empty [0, L] tensor")
+    L = local_rows.shape[1]
+    buf = local_rows.new_zeros(max_rows, L)
+    buf[: local_rows.shape[0]] = local_rows
+    out = [torch.empty_like(buf) for _ in range(size)]
+    dist.all_gather(out, buf, group=group)
+    rows = []
+    for local in range(active):
+        rb, re_ = divmod(part.rows_total, active)
+        n = rb + (1 if local < re_ else 0)
+        rows.append(out[local][:n])
+    return torch.cat(rows)
+
+
+def gather_images(local_x: torch.Tensor, batch: int, world: int, group=None) -> torch.Tensor:
+    """All ranks receive the full [batch, ...] tensor of final latents (image-sharded case)."""
+    import torch.distributed as dist
+    if world == 1:
+        return local_x
+    counts = [len(partition(batch, 1, world, r).images) for r in range(world)]
+    mx = max(counts)
+    buf = local_x.new_zeros((mx,) + tuple(local_x.shape[1:]))
+    buf[: local_x.shape[0]] = local_x
+    out = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf, group=group)
+    return torch.cat([o[:c] for o, c in zip(out, counts)])

@@ -214,6 +214,13 @@ class UNetModel:
         W["emb_all.w"] = torch.cat(emb_w).contiguous().to(dev)
         W["emb_all.b"] = torch.cat(emb_b).contiguous().to(dev)
         self.emb_off, self.emb_total, self.ted = emb_off, off, ted
+        # tcgen05 kind::f16 needs A and B in the SAME 16-bit format (mixed fp16 x bf16 raises an illegal-instruction
+        # trap on sm_100a), so tensor-core weights are stored in the activation dtype.  bf16 -> fp16 is exact for
+        # every weight with |w| >= 2^-14 (fp16 has the wider mantissa); smaller ones move by < 3e-8 absolute.
+        cuda_core = {"te0.w", "te2.w", "emb_all.w", "input_blocks.0.0.w", "out.w"}
+        for key in list(W):
+            if key.endswith(".w") and key not in cuda_core:
+                W[key] = W[key].to(self.act_dtype)
         self.w = W
         return self
 

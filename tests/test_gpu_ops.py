@@ -237,10 +237,19 @@ def test_conv_in_out_upsample(ops):
 
 
 # ------------------------------------------------------------------------------------------------ fp16 activations x bf16 weights
-@pytest.mark.parametrize("a_dt,b_dt,o_dt", [(torch.float16, torch.bfloat16, torch.float16), (torch.bfloat16, torch.float16, torch.float16),
+def test_gemm_rejects_mixed_operand_formats(ops):
+    """tcgen05 kind::f16 traps (illegal instruction) when A is fp16 and B is bf16: the C ABI refuses it up front."""
+    a = torch.zeros(128, 64, dtype=torch.float16, device=DEV)
+    w = torch.zeros(128, 64, dtype=torch.bfloat16, device=DEV)
+    out = torch.zeros(128, 128, dtype=torch.float16, device=DEV)
+    with pytest.raises(RuntimeError, match="same 16-bit format"):
+        ops.gemm_conv(a, w, out, n_img=1, h=1, w=128, c0=64, n_out=128)
+
+
+@pytest.mark.parametrize("a_dt,b_dt,o_dt", [(torch.float16, torch.float16, torch.float16), (torch.bfloat16, torch.bfloat16, torch.float16),
                                             (torch.float16, torch.float16, torch.bfloat16)])
-def test_gemm_mixed_operand_formats(ops, a_dt, b_dt, o_dt):
-    """tcgen05 kind::f16 takes the A and B element formats independently (fp16 activations x bf16 weights)."""
+def test_gemm_operand_and_output_formats(ops, a_dt, b_dt, o_dt):
+    """fp16 or bf16 operands (same format for A and B), independent 16-bit output format."""
     M, N, K = 512, 384, 320
     g = torch.Generator().manual_seed(9)
     a = torch.randn(M, K, generator=g).to(a_dt).to(DEV)
@@ -260,7 +269,7 @@ def test_conv_attention_norms_fp16_activations(ops):
     g = torch.Generator().manual_seed(21)
     n, h, w, cin, cout = 2, 16, 16, 128, 128
     x = torch.randn(n, cin, h, w, generator=g).half()
-    wt = bf(torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(9 * cin))
+    wt = bf(torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(9 * cin)).half()  # bf16 values, stored as fp16 (exact)
     out = torch.empty(n, h, w, cout, dtype=torch.float16, device=DEV)
     ops.gemm_conv(x.permute(0, 2, 3, 1).contiguous().to(DEV), wt.permute(0, 2, 3, 1).contiguous().to(DEV), out, n_img=n, h=h, w=w,
                   c0=cin, n_out=cout, ksize=3)

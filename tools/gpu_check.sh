@@ -9,7 +9,7 @@ rc=0
 for g in "${groups[@]}"; do
   case $g in
     step) sel="tests/test_gpu_sampling.py -k 'fused_loop or denoiser_forward or unsupported'";;
-    gemm) sel="tests/test_gpu_ops.py -k 'gemm'";;
+    gemm) sel="tests/test_gpu_ops.py -k 'gemm or fp16_activations'";;
     conv) sel="tests/test_gpu_ops.py -k 'conv3x3 or conv1x1'";;
     attn) sel="tests/test_gpu_ops.py -k 'attention'";;
     misc) sel="tests/test_gpu_ops.py -k 'groupnorm or layernorm or timestep or conv_in_out'";;

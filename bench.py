@@ -258,11 +258,27 @@ def run_b200(args):
         g_n = sum(1 for (k_, a, b, f) in prof if k_ == "gemm_conv")
         at_ms = sum(a.elapsed_time(b) for (k_, a, b, f) in prof if k_ == "attention")
         at_fl = sum(f for (k_, a, b, f) in prof if k_ == "attention")
+        breakdown = {}
+        for (k_, a, b, f) in prof:
+            breakdown[k_] = breakdown.get(k_, 0.0) + a.elapsed_time(b)
+        # GEMM launches grouped by shape class: where the tensor time goes
+        by_shape = {}
+        for (k_, a, b, f) in prof:
+            if k_ == "gemm_conv":
+                key = f"{f / 1e9:.1f}GF"
+                d = by_shape.setdefault(key, [0, 0.0])
+                d[0] += 1
+                d[1] += a.elapsed_time(b)
+        top = sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:12]
+        sys.stderr.write("per-op-kind ms in one step: " + json.dumps({k: round(v, 2) for k, v in breakdown.items()}) + "\n")
+        sys.stderr.write("top GEMM shape classes (GFLOP per launch: [launches, ms, TFLOP/s]): " + json.dumps(
+            {k: [v[0], round(v[1], 2), round(float(k[:-2]) * v[0] / v[1], 1)] for k, v in top}) + "\n")
         achieved = g_fl / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "gemm_conv_kernel (tcgen05 implicit-GEMM conv / GEMM)", "achieved": achieved,
                 "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"], "traffic": None,
                 "peak_source": pk["source"] + " (sustained bf16)", "launches_per_step": g_n,
                 "avg_launch_us": g_ms * 1e3 / max(g_n, 1), "share_of_step": g_ms / (ms / args.steps),
+                "breakdown_ms_per_step": {k: round(v, 3) for k, v in breakdown.items()},
                 "attention_tflops": at_fl / (at_ms / 1e3) / 1e12 if at_ms > 0 else None,
                 "attention_share_of_step": at_ms / (ms / args.steps),
                 "unet_tflops_whole_step": evals_per_step * flops_row / (ms / args.steps / 1e3) / 1e12,

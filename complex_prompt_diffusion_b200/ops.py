@@ -104,7 +104,8 @@ def sampler_step(eps, x, *, n_sub, weights, mask_scalars, masks, guidance, sampl
     p.sigma_hat, p.v_c_eps, p.v_c_x_div, p.dt, p.sigma_up = float(sigma_hat), float(v_c_eps), float(v_c_x_div), float(dt), float(sigma_up)
     p.dpm_ratio, p.dpm_expm1, p.dpm_c1, p.dpm_c2 = float(dpm_ratio), float(dpm_expm1), float(dpm_c1), float(dpm_c2)
     p.dpm_first, p.write_old = int(dpm_first), int(write_old)
-    check(load().cpd_sampler_step(C.byref(p), stream_ptr()), "cpd_sampler_step")
+    with _Prof("sampler_step", 0.0):
+        check(load().cpd_sampler_step(C.byref(p), stream_ptr()), "cpd_sampler_step")
     _count()
     return x
 
@@ -148,8 +149,9 @@ def groupnorm(a0, gamma, beta, out, stats, *, n_img, hw, c0, a1=None, c1=0, eps=
     _req(stats, torch.float64, "stats")
     if stats.numel() < n_img * 64:
         raise RuntimeError("stats scratch too small")
-    check(load().cpd_groupnorm(ptr(a0), ptr(a1), c0, c1, n_img, hw, ptr(gamma), ptr(beta), float(eps), int(silu), f16, ptr(stats),
-                               ptr(out), stream_ptr()), "cpd_groupnorm")
+    with _Prof("groupnorm", 0.0):
+        check(load().cpd_groupnorm(ptr(a0), ptr(a1), c0, c1, n_img, hw, ptr(gamma), ptr(beta), float(eps), int(silu), f16, ptr(stats),
+                                   ptr(out), stream_ptr()), "cpd_groupnorm")
     _count(2)
     return out
 
@@ -159,7 +161,8 @@ def layernorm(x, gamma, beta, out, *, rows, c, eps=1e-5):
     _act(out, "out", like=x.dtype)
     _req(gamma, torch.float32, "gamma")
     _req(beta, torch.float32, "beta")
-    check(load().cpd_layernorm(ptr(x), rows, c, ptr(gamma), ptr(beta), float(eps), f16, ptr(out), stream_ptr()), "cpd_layernorm")
+    with _Prof("layernorm", 0.0):
+        check(load().cpd_layernorm(ptr(x), rows, c, ptr(gamma), ptr(beta), float(eps), f16, ptr(out), stream_ptr()), "cpd_layernorm")
     _count()
     return out
 
@@ -167,7 +170,8 @@ def layernorm(x, gamma, beta, out, *, rows, c, eps=1e-5):
 def timestep_embedding(t, out, *, dim, round_t_bf16=True):
     _req(t, torch.float32, "t")
     _req(out, torch.bfloat16, "out")
-    check(load().cpd_timestep_embedding(ptr(t), t.numel(), dim, int(round_t_bf16), ptr(out), stream_ptr()), "cpd_timestep_embedding")
+    with _Prof("small", 0.0):
+        check(load().cpd_timestep_embedding(ptr(t), t.numel(), dim, int(round_t_bf16), ptr(out), stream_ptr()), "cpd_timestep_embedding")
     _count()
     return out
 
@@ -178,8 +182,9 @@ def small_linear(x, w, b, *, m, k, n, silu_in=False, out_f32=None, out_bf16=None
     _req(b, torch.float32, "b")
     _req(out_f32, torch.float32, "out_f32")
     _req(out_bf16, torch.bfloat16, "out_bf16")
-    check(load().cpd_small_linear(ptr(x), m, k, ptr(w), ptr(b), n, int(silu_in), ptr(out_f32), ptr(out_bf16),
-                                  ld_out if ld_out is not None else n, stream_ptr()), "cpd_small_linear")
+    with _Prof("small", 0.0):
+        check(load().cpd_small_linear(ptr(x), m, k, ptr(w), ptr(b), n, int(silu_in), ptr(out_f32), ptr(out_bf16),
+                                      ld_out if ld_out is not None else n, stream_ptr()), "cpd_small_linear")
     _count()
 
 
@@ -188,8 +193,9 @@ def conv_in(x, wt, bias, out, *, n, cin, h, w, cout, scale=1.0, rows_per_image=1
     _req(wt, torch.bfloat16, "wt")
     _req(bias, torch.float32, "bias")
     f16 = _act(out, "out")
-    check(load().cpd_conv_in(ptr(x), n, cin, h, w, ptr(wt), ptr(bias), cout, float(scale), int(rows_per_image), f16, ptr(out),
-                             stream_ptr()), "cpd_conv_in")
+    with _Prof("conv_in", 0.0):
+        check(load().cpd_conv_in(ptr(x), n, cin, h, w, ptr(wt), ptr(bias), cout, float(scale), int(rows_per_image), f16, ptr(out),
+                                 stream_ptr()), "cpd_conv_in")
     _count()
     return out
 
@@ -200,8 +206,9 @@ def conv_out(a, wt, bias, out, *, n, h, w, cin, cout):
     _req(bias, torch.float32, "bias")
     if out.dtype not in (torch.bfloat16, torch.float32) or not out.is_cuda:
         raise RuntimeError("out must be a CUDA bf16/fp32 tensor")
-    check(load().cpd_conv_out(ptr(a), n, h, w, cin, ptr(wt), ptr(bias), cout, ptr(out), DTYPE_CODE[out.dtype], f16, stream_ptr()),
-          "cpd_conv_out")
+    with _Prof("conv_out", 0.0):
+        check(load().cpd_conv_out(ptr(a), n, h, w, cin, ptr(wt), ptr(bias), cout, ptr(out), DTYPE_CODE[out.dtype], f16, stream_ptr()),
+              "cpd_conv_out")
     _count()
     return out
 
@@ -209,7 +216,8 @@ def conv_out(a, wt, bias, out, *, n, h, w, cin, cout):
 def upsample2x(a, out, *, n, h, w, c):
     _act(a, "a")
     _act(out, "out", like=a.dtype)
-    check(load().cpd_upsample2x(ptr(a), n, h, w, c, ptr(out), stream_ptr()), "cpd_upsample2x")
+    with _Prof("upsample", 0.0):
+        check(load().cpd_upsample2x(ptr(a), n, h, w, c, ptr(out), stream_ptr()), "cpd_upsample2x")
     _count()
     return out
 

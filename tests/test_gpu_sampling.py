@@ -195,7 +195,7 @@ def _layer_report(oracle, gpu, R):
 # depth (torch's own CPU bf16 run of the oracle deviates 1.25e-2 / 1.46e-2 on tiny / SD-1.5), so that mode is
 # only checked against 2e-2.
 @pytest.mark.parametrize("act_dtype,tol", [(torch.float16, 1e-2), (torch.bfloat16, 2e-2)])
-@pytest.mark.parametrize("cfg_name,hw,R", [("tiny", 16, 3), ("tiny", 32, 2), ("sd15", 16, 2), ("sd21", 32, 2)])
+@pytest.mark.parametrize("cfg_name,hw,R", [("tiny", 16, 3), ("tiny", 32, 2), ("sd15", 32, 2), ("sd21", 32, 2)])
 def test_unet_forward_vs_oracle(cpd, cfg_name, hw, R, act_dtype, tol):
     cfg, oracle, gpu = _unet_pair(cfg_name, torch.float32, act_dtype)
     g = torch.Generator().manual_seed(hw + R)

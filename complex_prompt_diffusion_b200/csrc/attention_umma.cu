@@ -28,7 +28,7 @@ struct AttnArgs {
   float scale_log2;
 };
 
-__global__ void __launch_bounds__(NUM_THREADS, 1) attention_kernel(const __grid_constant__ AttnArgs a) {
+__global__ void __launch_bounds__(NUM_THREADS, 2) attention_kernel(const __grid_constant__ AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int datoms = a.datoms;
@@ -157,19 +157,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_kernel(const __grid_
       const int kv_valid = min(BKV, a.nk - j * BKV);
       mbar_wait(s_full, (uint32_t)(j & 1), 30);
       tc_fence_after();
-      uint32_t v[128];
+      // pass 1 over the S row (TMEM reads are cheap: the row is re-read in pass 2 instead of living in 128 registers)
+      const bool full = (kv_valid == BKV);
+      float mx = -INFINITY;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t t[32];
         tmem_ld32(tmem_S + lane_off + c * 32, t);
+        tmem_ld_wait();
+        if (full) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) v[c * 32 + e] = t[e];
+          for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(t[e]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (c * 32 + e < kv_valid) mx = fmaxf(mx, __uint_as_float(t[e]));
+        }
       }
-      tmem_ld_wait();
-      float mx = -INFINITY;
-#pragma unroll
-      for (int e = 0; e < 128; ++e)
-        if (e < kv_valid) mx = fmaxf(mx, __uint_as_float(v[e]));
       const float m_blk = mx * a.scale_log2;
       float alpha = 1.0f;
       bool need = false;
@@ -180,16 +184,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention_kernel(const __grid_
         m_used = m_blk;
         need = true;
       }
-      float psum = 0.f;
+      // pass 2: p = 2^(s * scale_log2 - m) with the MUFU ex2 fed by one FFMA; packed to 16-bit in registers
+      float psum0 = 0.f, psum1 = 0.f;
       uint32_t pk[64];
+      const float neg_m = -m_used;
+      const bool f16 = a.fp16 != 0;
 #pragma unroll
-      for (int e = 0; e < 128; e += 2) {
-        float p0 = (e < kv_valid) ? exp2f(__uint_as_float(v[e]) * a.scale_log2 - m_used) : 0.f;
-        float p1 = (e + 1 < kv_valid) ? exp2f(__uint_as_float(v[e + 1]) * a.scale_log2 - m_used) : 0.f;
-        psum += p0 + p1;
-        pk[e >> 1] = pack_act2(p0, p1, a.fp16 != 0);
+      for (int c = 0; c < 4; ++c) {
+        uint32_t t[32];
+        tmem_ld32(tmem_S + lane_off + c * 32, t);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          float p0 = fast_ex2(fmaf(__uint_as_float(t[e]), a.scale_log2, neg_m));
+          float p1 = fast_ex2(fmaf(__uint_as_float(t[e + 1]), a.scale_log2, neg_m));
+          if (!full) {
+            if (c * 32 + e >= kv_valid) p0 = 0.f;
+            if (c * 32 + e + 1 >= kv_valid) p1 = 0.f;
+          }
+          psum0 += p0;
+          psum1 += p1;
+          pk[c * 16 + (e >> 1)] = pack_act2(p0, p1, f16);
+        }
       }
-      l = l * alpha + psum;
+      l = l * alpha + (psum0 + psum1);
       if (j > 0) {
         // previous P V must be complete before P is overwritten / O is rescaled
         mbar_wait(o_done, (uint32_t)((j - 1) & 1), 31);

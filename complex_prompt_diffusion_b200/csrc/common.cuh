@@ -240,6 +240,11 @@ __device__ __forceinline__ float2 unpack_act2(uint32_t u, bool f16) { return f16
 __device__ __forceinline__ float round_act(float v, bool f16) {
   return f16 ? __half2float(__float2half_rn(v)) : __bfloat162float(__float2bfloat16_rn(v));
 }
+__device__ __forceinline__ float fast_ex2(float x) {  // MUFU.EX2, no range fix-ups (inputs are <= ~8 here)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 

@@ -1,0 +1,104 @@
+// Geometry shared by the implicit-GEMM conv / GEMM kernels (gemm_umma.cu: 1-CTA tiles, gemm_umma2.cu: persistent
+// 2-CTA tiles): how the 128 rows of a CTA tile map to boxes of output pixels, and the TMA tensor maps of the
+// NHWC activations (rank 5: c, x, parity, y, n) and of the K-major weights.
+#pragma once
+#include "../../include/cpd_b200.h"
+#include "common.cuh"
+
+namespace cpd_gemm {
+
+constexpr int BM = 128;     // output rows per CTA (one TMEM lane each)
+constexpr int BK = 64;      // K elements per pipeline stage (one 128-byte swizzle atom of 16-bit elements)
+constexpr int UMMA_K = 16;  // K per tcgen05.mma for 16-bit inputs
+
+struct ConvGeom {
+  int taps;        // 1 or 9
+  int cb0, cb1;    // 64-channel blocks from source 0 / 1
+  int c0;          // channels of source 0 (stride-2 parity offset)
+  int c1;
+  int stride;      // 1 or 2
+  int tw, th, nb;  // box = nb images x th x tw output pixels
+  int nbox;        // boxes per 128-row CTA tile
+  int bx_count, by_count;
+  int n_img, h_out, w_out;
+  int m_valid;     // plain GEMM: valid rows; 0 = all
+  int n_out;       // GEMM N
+  int n_store;     // columns of D (n_out, or n_out/2 for GEGLU)
+  int epilogue;
+  int rowvec_stride, ld_res, ldd;
+  int out_fp16;    // D / residual element type: 1 = fp16, 0 = bf16
+  uint32_t idesc;  // tcgen05 instruction descriptor (encodes the A / B element formats and the MMA shape)
+};
+
+// Row r (0..127) of CTA tile `m_tile` -> output pixel.  Returns false when the row is padding.
+struct RowCoord {
+  int n, y, x;
+  int64_t row;  // linear output row = (n * h_out + y) * w_out + x
+  bool valid;
+};
+__device__ __forceinline__ RowCoord row_coord(const ConvGeom& g, int m_tile, int r) {
+  const int box_rows = g.tw * g.th * g.nb;
+  const int j = r / box_rows;
+  const int pidx = r - j * box_rows;
+  const int s_idx = m_tile * g.nbox + j;
+  const int bx = s_idx % g.bx_count;
+  const int t2 = s_idx / g.bx_count;
+  const int by = t2 % g.by_count;
+  const int ng = t2 / g.by_count;
+  const int img_px = g.tw * g.th;
+  const int ib = pidx / img_px;
+  const int p2 = pidx - ib * img_px;
+  RowCoord rc;
+  rc.n = ng * g.nb + ib;
+  rc.y = by * g.th + p2 / g.tw;
+  rc.x = bx * g.tw + p2 % g.tw;
+  rc.valid = (rc.n < g.n_img) && (rc.y < g.h_out) && (rc.x < g.w_out);
+  rc.row = ((int64_t)rc.n * g.h_out + rc.y) * g.w_out + rc.x;
+  if (g.m_valid > 0 && rc.row >= g.m_valid) rc.valid = false;
+  return rc;
+}
+
+// Coordinates of the TMA box j of CTA tile m_tile for filter tap `tap` (0..8) / channel block cb.
+struct BoxCoord {
+  int c, x, p, y, n;
+  bool src1;
+};
+__device__ __forceinline__ BoxCoord box_coord(const ConvGeom& g, int m_tile, int j, int tap, int cb) {
+  int dy = 0, dx = 0, py = 0, px = 0;
+  if (g.taps == 9) {
+    const int ky = tap / 3, kx = tap - ky * 3;
+    if (g.stride == 1) {
+      dy = ky - 1;
+      dx = kx - 1;
+    } else {  // input row = 2*oy + ky - 1 = 2*(oy + dy) + py
+      dy = (ky == 0) ? -1 : 0;
+      py = (ky == 0) ? 1 : ky - 1;
+      dx = (kx == 0) ? -1 : 0;
+      px = (kx == 0) ? 1 : kx - 1;
+    }
+  }
+  BoxCoord b;
+  b.src1 = cb >= g.cb0;
+  const int csrc = b.src1 ? g.c1 : g.c0;
+  b.c = (b.src1 ? cb - g.cb0 : cb) * BK + px * csrc;
+  const int s_idx = m_tile * g.nbox + j;
+  const int bx = s_idx % g.bx_count;
+  const int t2 = s_idx / g.bx_count;
+  const int by = t2 % g.by_count;
+  const int ng = t2 / g.by_count;  // beyond n_img -> fully out of bounds -> zero fill
+  b.x = bx * g.tw + dx;
+  b.p = py;
+  b.y = by * g.th + dy;
+  b.n = ng * g.nb;
+  return b;
+}
+
+// Host: validates p, fills the geometry (everything but idesc / n_store / tile counts) and the A tensor maps.
+int fill_geometry(const cpd_gemm_params* p, ConvGeom* g, CUtensorMap* map_a0, CUtensorMap* map_a1, int* m_tiles_cta);
+// Host: weights tensor map, box = 64 x box_rows.
+int make_b_map(const cpd_gemm_params* p, int taps, int box_rows, CUtensorMap* map_b);
+
+}  // namespace cpd_gemm
+
+// 2-CTA persistent kernel entry (gemm_umma2.cu); returns CPD_ERR_UNSUPPORTED when the shape is outside its domain.
+cpd_status cpd_gemm_conv_2cta(const cpd_gemm_params* p, void* stream);

@@ -232,7 +232,8 @@ def test_unet_forward_rows_equals_forward(cpd):
     x_in = (x * c_in).repeat_interleave(R, dim=0)
     b = gpu.forward(x_in, torch.full((B * R,), t), None).clone()
     torch.cuda.synchronize()
-    assert torch.equal(a, b)
+    # same kernels, but the embedding MLP runs on 1 row vs B*R rows (different reduction split): not bit-equal
+    assert rel(a.float().cpu(), b.float().cpu()) < 5e-3
 
 
 @pytest.mark.parametrize("name,steps", [("DPM++ 2m", 6), ("Euler", 6), ("Euler Ancestral", 6)])

@@ -253,17 +253,17 @@ def run_b200(args):
         step_resident()
         torch.cuda.synchronize()
         prof, ops.PROFILE = ops.PROFILE, None
-        g_ms = sum(a.elapsed_time(b) for (k_, a, b, f) in prof if k_ == "gemm_conv")
-        g_fl = sum(f for (k_, a, b, f) in prof if k_ == "gemm_conv")
-        g_n = sum(1 for (k_, a, b, f) in prof if k_ == "gemm_conv")
-        at_ms = sum(a.elapsed_time(b) for (k_, a, b, f) in prof if k_ == "attention")
-        at_fl = sum(f for (k_, a, b, f) in prof if k_ == "attention")
+        g_ms = sum(a.elapsed_time(b) for (k_, a, b, f, _l) in prof if k_ == "gemm_conv")
+        g_fl = sum(f for (k_, a, b, f, _l) in prof if k_ == "gemm_conv")
+        g_n = sum(1 for (k_, a, b, f, _l) in prof if k_ == "gemm_conv")
+        at_ms = sum(a.elapsed_time(b) for (k_, a, b, f, _l) in prof if k_ == "attention")
+        at_fl = sum(f for (k_, a, b, f, _l) in prof if k_ == "attention")
         breakdown = {}
-        for (k_, a, b, f) in prof:
+        for (k_, a, b, f, _l) in prof:
             breakdown[k_] = breakdown.get(k_, 0.0) + a.elapsed_time(b)
         # GEMM launches grouped by shape class: where the tensor time goes
         by_shape = {}
-        for (k_, a, b, f) in prof:
+        for (k_, a, b, f, _l) in prof:
             if k_ == "gemm_conv":
                 key = f"{f / 1e9:.1f}GF"
                 d = by_shape.setdefault(key, [0, 0.0])

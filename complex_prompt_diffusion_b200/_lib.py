@@ -42,7 +42,7 @@ class GemmParams(C.Structure):
         ("rowvec", C.c_void_p), ("rowvec_stride", C.c_int),
         ("residual", C.c_void_p), ("ld_res", C.c_int),
         ("d", C.c_void_p), ("ldd", C.c_int), ("epilogue", C.c_int), ("variant", C.c_int), ("m_valid", C.c_int),
-        ("a_fp16", C.c_int), ("b_fp16", C.c_int), ("out_fp16", C.c_int),
+        ("a_fp16", C.c_int), ("b_fp16", C.c_int), ("out_fp16", C.c_int), ("geglu_block", C.c_int),
     ]
 
 

@@ -10,33 +10,12 @@
 //
 // Replaces the cuDNN/cuBLAS calls behind nn.Conv2d / nn.Linear in cpd/models/unet.py:105,153-160,210,236,247
 // and cpd/models/attention.py:92-118,183-190,508-524.
-#include "../../include/cpd_b200.h"
-#include "common.cuh"
+#include "gemm_geom.cuh"
 
 namespace {
+using namespace cpd_gemm;
 
-constexpr int BM = 128;      // output rows per CTA (UMMA M)
-constexpr int BK = 64;       // K elements per pipeline stage (one 128-byte swizzle atom of bf16)
-constexpr int UMMA_K = 16;   // K per tcgen05.mma for 16-bit inputs
 constexpr int NUM_THREADS = 192;
-
-struct ConvGeom {
-  int taps;        // 1 or 9
-  int cb0, cb1;    // 64-channel blocks from source 0 / 1
-  int c0;          // channels of source 0 (stride-2 parity offset)
-  int c1;
-  int stride;      // 1 or 2
-  int tw, th, nbox;   // box = th x tw output pixels, nbox boxes per 128-row tile
-  int bx_count, by_count;
-  int n_img, h_out, w_out;
-  int m_valid;     // plain GEMM: valid rows; 0 = all
-  int n_out;       // GEMM N
-  int n_store;     // columns of D (n_out, or n_out/2 for GEGLU)
-  int epilogue;
-  int rowvec_stride, ld_res, ldd;
-  int out_fp16;       // D / residual element type: 1 = fp16, 0 = bf16
-  uint32_t idesc;     // tcgen05 instruction descriptor (encodes the A / B element formats)
-};
 
 struct GemmArgs {
   CUtensorMap map_a0, map_a1, map_b;
@@ -97,40 +76,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_conv_kernel(const __grid_
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
-      const int box_rows = g.tw * g.th;
+      const int box_bytes = g.tw * g.th * g.nb * 128;
       int stage = 0;
       uint32_t phase = 0;
       for (int kt = 0; kt < num_k; ++kt) {
         const int tap = kt / cbt;
         const int cb = kt - tap * cbt;
-        int dy = 0, dx = 0, py = 0, px = 0;
-        if (g.taps == 9) {
-          const int ky = tap / 3, kx = tap - ky * 3;
-          if (g.stride == 1) {
-            dy = ky - 1;
-            dx = kx - 1;
-          } else {  // input row = 2*oy + ky - 1 = 2*(oy + dy) + py
-            dy = (ky == 0) ? -1 : 0;
-            py = (ky == 0) ? 1 : ky - 1;
-            dx = (kx == 0) ? -1 : 0;
-            px = (kx == 0) ? 1 : kx - 1;
-          }
-        }
         mbar_wait(&empty_bar[stage], phase ^ 1, 1);
         uint8_t* sa = smem + stage * L::STAGE_BYTES;
         uint8_t* sb = sa + L::A_BYTES;
         mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-        const bool src1 = cb >= g.cb0;
-        const CUtensorMap* ma = src1 ? &args.map_a1 : &args.map_a0;
-        const int csrc = src1 ? g.c1 : g.c0;
-        const int ccoord = (src1 ? cb - g.cb0 : cb) * BK + px * csrc;
         for (int j = 0; j < g.nbox; ++j) {
-          const int s_idx = m_tile * g.nbox + j;
-          const int bx = s_idx % g.bx_count;
-          const int t2 = s_idx / g.bx_count;
-          const int by = t2 % g.by_count;
-          const int n = t2 / g.by_count;  // n >= n_img -> fully out of bounds -> zero fill
-          tma_load_5d(sa + j * box_rows * 128, ma, &full_bar[stage], ccoord, bx * g.tw + dx, py, by * g.th + dy, n);
+          const BoxCoord bc = box_coord(g, m_tile, j, tap, cb);
+          tma_load_5d(sa + j * box_bytes, bc.src1 ? &args.map_a1 : &args.map_a0, &full_bar[stage], bc.c, bc.x, bc.p, bc.y, bc.n);
         }
         tma_load_2d(sb, &args.map_b, &full_bar[stage], kt * BK, n_tile * BN);
         if (++stage == STAGES) {
@@ -170,20 +128,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_conv_kernel(const __grid_
     const bool of16 = g.out_fp16 != 0;
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;       // row within the tile
-    // output row (pixel) of this thread
-    const int box_rows = g.tw * g.th;
-    const int j = r / box_rows;
-    const int pidx = r - j * box_rows;
-    const int s_idx = m_tile * g.nbox + j;
-    const int bx = s_idx % g.bx_count;
-    const int t2 = s_idx / g.bx_count;
-    const int by = t2 % g.by_count;
-    const int n = t2 / g.by_count;
-    const int y = by * g.th + pidx / g.tw;
-    const int x = bx * g.tw + pidx % g.tw;
-    bool valid = (n < g.n_img) && (y < g.h_out) && (x < g.w_out);
-    const int64_t row = ((int64_t)n * g.h_out + y) * g.w_out + x;
-    if (g.m_valid > 0 && row >= g.m_valid) valid = false;
+    const RowCoord rc = row_coord(g, m_tile, r);
+    const bool valid = rc.valid;
+    const int64_t row = rc.row;
+    const int n = rc.n;
 
     mbar_wait(tmem_full_bar, 0, 3);
     tc_fence_after();
@@ -288,29 +236,37 @@ cpd_status launch(const GemmArgs& args, int m_tiles, int n_tiles, cudaStream_t s
   return CPD_OK;
 }
 
-// choose a box (tw x th) of output pixels: tw | w, th | h, tw*th <= 128 and a multiple of 8, as large as possible
-bool choose_box(int h, int w, int* tw, int* th) {
+}  // namespace
+
+namespace cpd_gemm {
+
+// Box of output pixels covered by one TMA load: nb images x th rows x tw columns with tw | w, th | h, a multiple of
+// 8 rows (one swizzle atom) that divides 128, as large as possible.  nb > 1 only when the box spans whole images.
+static bool choose_box(int h, int w, int n_img, int* tw, int* th, int* nb) {
   int best = 0;
+  *tw = *th = *nb = 0;
   for (int a = 1; a <= 128 && a <= w; ++a) {
     if (w % a) continue;
     for (int b = 1; a * b <= 128 && b <= h; ++b) {
       if (h % b) continue;
-      const int px = a * b;
-      if (128 % px) continue;
-      if (px % 8) continue;
-      if (px > best || (px == best && a > *tw)) {
-        best = px;
-        *tw = a;
-        *th = b;
+      const int max_n = (a == w && b == h) ? 128 / (a * b) : 1;
+      for (int c = 1; c <= max_n; c *= 2) {
+        const int px = a * b * c;
+        if (128 % px || px % 8) continue;
+        if (c > 1 && c > 2 * n_img) continue;  // do not pad tiny batches with many empty images
+        if (px > best || (px == best && c < *nb) || (px == best && c == *nb && a > *tw)) {
+          best = px;
+          *tw = a;
+          *th = b;
+          *nb = c;
+        }
       }
     }
   }
   return best > 0;
 }
 
-}  // namespace
-
-extern "C" cpd_status cpd_gemm_conv(const cpd_gemm_params* p, void* stream) {
+int fill_geometry(const cpd_gemm_params* p, ConvGeom* gp, CUtensorMap* map_a0, CUtensorMap* map_a1, int* m_tiles_cta) {
   CPD_REQUIRE(p != nullptr, "cpd_gemm_conv: null params");
   CPD_REQUIRE(p->a0 && p->wt && p->d, "cpd_gemm_conv: a0, wt and d must be non-null");
   CPD_REQUIRE(p->c0 > 0 && p->c0 % 64 == 0 && p->c1 >= 0 && p->c1 % 64 == 0,
@@ -326,10 +282,7 @@ extern "C" cpd_status cpd_gemm_conv(const cpd_gemm_params* p, void* stream) {
   CPD_REQUIRE(p->stride == 1 || p->c1 == 0, "cpd_gemm_conv: stride 2 supports a single source");
   CPD_REQUIRE((p->a_fp16 != 0) == (p->b_fp16 != 0),
               "cpd_gemm_conv: A and B must have the same 16-bit format (tcgen05 kind::f16 traps on mixed fp16 x bf16)");
-
-  GemmArgs args;
-  ConvGeom& g = args.g;
-  const int C = p->c0 + p->c1;
+  ConvGeom& g = *gp;
   g.taps = p->ksize * p->ksize;
   g.cb0 = p->c0 / 64;
   g.cb1 = p->c1 / 64;
@@ -346,43 +299,33 @@ extern "C" cpd_status cpd_gemm_conv(const cpd_gemm_params* p, void* stream) {
   g.ld_res = p->ld_res;
   g.ldd = p->ldd;
   g.out_fp16 = p->out_fp16;
-
-  int variant = p->variant;
-  if (variant == 0) variant = (p->n_out % 256 == 0 || p->n_out >= 1024) ? 2 : 1;
-  if (p->epilogue == CPD_EPI_GEGLU) variant = 1;
-  const int BN = variant == 2 ? 256 : 128;
-  g.idesc = umma_idesc_f16(BM, BN, p->a_fp16 != 0, p->b_fp16 != 0);
-  if (p->epilogue == CPD_EPI_GEGLU) {
-    CPD_REQUIRE(p->n_out % 128 == 0, "cpd_gemm_conv: GEGLU needs n_out %% 128 == 0 (got %d)", p->n_out);
-    g.n_store = p->n_out / 2;
-  } else {
-    g.n_store = p->n_out;
-  }
-
   const bool plain = (p->h_in == 1 && p->n_img == 1 && p->ksize == 1);
   if (plain) {
     g.tw = 128;
     g.th = 1;
+    g.nb = 1;
     g.nbox = 1;
     g.bx_count = (g.w_out + 127) / 128;
     g.by_count = 1;
   } else {
-    int tw = 0, th = 0;
-    CPD_REQUIRE(choose_box(g.h_out, g.w_out, &tw, &th), "cpd_gemm_conv: no 8..128-pixel box divides the %d x %d output", g.h_out, g.w_out);
+    int tw = 0, th = 0, nb = 0;
+    CPD_REQUIRE(choose_box(g.h_out, g.w_out, g.n_img, &tw, &th, &nb), "cpd_gemm_conv: no 8..128-row box tiles the %d x %d output",
+                g.h_out, g.w_out);
     g.tw = tw;
     g.th = th;
-    g.nbox = 128 / (tw * th);
+    g.nb = nb;
+    g.nbox = 128 / (tw * th * nb);
     g.bx_count = g.w_out / tw;
     g.by_count = g.h_out / th;
   }
-  const int64_t total_boxes = (int64_t)g.n_img * g.bx_count * g.by_count;
-  const int m_tiles = (int)((total_boxes + g.nbox - 1) / g.nbox);
-  const int n_tiles = (p->n_out + BN - 1) / BN;
+  const int64_t n_groups = (g.n_img + g.nb - 1) / g.nb;
+  const int64_t total_boxes = n_groups * g.bx_count * g.by_count;
+  *m_tiles_cta = (int)((total_boxes + g.nbox - 1) / g.nbox);
 
-  // tensor maps.  A: (c, x, parity, y, n)
+  // A: (c, x, parity, y, n)
   auto make_a = [&](CUtensorMap* m, const void* base, int csrc) -> int {
     uint64_t dims[5], str[4];
-    uint32_t box[5] = {64, (uint32_t)g.tw, 1, (uint32_t)g.th, 1};
+    uint32_t box[5] = {64, (uint32_t)g.tw, 1, (uint32_t)g.th, (uint32_t)g.nb};
     if (p->stride == 1) {
       dims[0] = csrc; dims[1] = p->w_in; dims[2] = 1; dims[3] = p->h_in; dims[4] = p->n_img;
       str[0] = (uint64_t)csrc * 2;
@@ -398,21 +341,48 @@ extern "C" cpd_status cpd_gemm_conv(const cpd_gemm_params* p, void* stream) {
     }
     return cpd_make_tmap_bf16(m, base, 5, dims, str, box);
   };
-  int rc = make_a(&args.map_a0, p->a0, p->c0);
+  int rc = make_a(map_a0, p->a0, p->c0);
   if (rc) return rc;
   if (p->c1 > 0) {
-    rc = make_a(&args.map_a1, p->a1, p->c1);
+    rc = make_a(map_a1, p->a1, p->c1);
     if (rc) return rc;
   } else {
-    args.map_a1 = args.map_a0;
+    *map_a1 = *map_a0;
   }
-  {
-    uint64_t dims[2] = {(uint64_t)g.taps * C, (uint64_t)p->n_out};
-    uint64_t str[1] = {(uint64_t)g.taps * C * 2};
-    uint32_t box[2] = {64, (uint32_t)BN};
-    rc = cpd_make_tmap_bf16(&args.map_b, p->wt, 2, dims, str, box);
-    if (rc) return rc;
+  return CPD_OK;
+}
+
+int make_b_map(const cpd_gemm_params* p, int taps, int box_rows, CUtensorMap* map_b) {
+  const int C = p->c0 + p->c1;
+  uint64_t dims[2] = {(uint64_t)taps * C, (uint64_t)p->n_out};
+  uint64_t str[1] = {(uint64_t)taps * C * 2};
+  uint32_t box[2] = {64, (uint32_t)box_rows};
+  return cpd_make_tmap_bf16(map_b, p->wt, 2, dims, str, box);
+}
+
+}  // namespace cpd_gemm
+
+// 1-CTA tiles (variant 1: 128 x 128, variant 2: 128 x 256), one tile per CTA.  Kept as the simple baseline the
+// persistent CTA-pair kernel (gemm_umma2.cu) is checked against; variant 0 (auto) dispatches to the pair kernel.
+static cpd_status gemm_conv_1cta(const cpd_gemm_params* p, void* stream) {
+  GemmArgs args;
+  ConvGeom& g = args.g;
+  int m_tiles = 0;
+  int rc = fill_geometry(p, &g, &args.map_a0, &args.map_a1, &m_tiles);
+  if (rc) return rc;
+  const int variant = p->epilogue == CPD_EPI_GEGLU ? 1 : p->variant;
+  const int BN = variant == 2 ? 256 : 128;
+  g.idesc = umma_idesc_f16(BM, BN, p->a_fp16 != 0, p->b_fp16 != 0);
+  if (p->epilogue == CPD_EPI_GEGLU) {
+    CPD_REQUIRE(p->n_out % 128 == 0 && (p->geglu_block == 0 || p->geglu_block == 128),
+                "cpd_gemm_conv: the 1-CTA GEGLU epilogue needs n_out %% 128 == 0 and weights interleaved per 128 columns");
+    g.n_store = p->n_out / 2;
+  } else {
+    g.n_store = p->n_out;
   }
+  const int n_tiles = (p->n_out + BN - 1) / BN;
+  rc = make_b_map(p, g.taps, BN, &args.map_b);
+  if (rc) return rc;
   args.bias = p->bias;
   args.rowvec = p->rowvec;
   args.residual = reinterpret_cast<const bf16*>(p->residual);
@@ -420,4 +390,10 @@ extern "C" cpd_status cpd_gemm_conv(const cpd_gemm_params* p, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (variant == 2) return launch<256, 4>(args, m_tiles, n_tiles, s);
   return launch<128, 3>(args, m_tiles, n_tiles, s);
+}
+
+extern "C" cpd_status cpd_gemm_conv(const cpd_gemm_params* p, void* stream) {
+  CPD_REQUIRE(p != nullptr, "cpd_gemm_conv: null params");
+  if (p->variant == 1 || p->variant == 2) return gemm_conv_1cta(p, stream);
+  return cpd_gemm_conv_2cta(p, stream);
 }

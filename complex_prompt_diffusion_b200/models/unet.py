@@ -66,6 +66,7 @@ class UNetModel:
                     attention_resolutions=(4, 2, 1), channel_mult=(1, 2, 4, 4), num_heads=8, num_head_channels=-1,
                     transformer_depth=1, context_dim=768, use_linear_in_transformer=False, use_spatial_transformer=True,
                     legacy=False)
+    GEGLU_BLOCK = 256
 
     def __init__(self, state_dict=None, device="cuda", act_dtype=torch.float16, eps_dtype=torch.float32, **config):
         cfg = dict(self.DEFAULTS)
@@ -180,13 +181,15 @@ class UNetModel:
             W[b + "attn2.v.w"] = pad_rows(bf(sd[b + "attn2.to_v.weight"]), nh, dh, dpad).contiguous().to(dev)
             W[b + "attn2.out.w"] = pad_cols(bf(sd[b + "attn2.to_out.0.weight"]), nh, dh, dpad).contiguous().to(dev)
             W[b + "attn2.out.b"] = f32(b + "attn2.to_out.0.bias")
-            # GEGLU: interleave [64 value rows | 64 gate rows] per 128-column tile (cpd_gemm_conv CPD_EPI_GEGLU)
+            # GEGLU: interleave [128 value rows | 128 gate rows] per 256-column tile (cpd_gemm_conv CPD_EPI_GEGLU,
+            # geglu_block = 256 = the CTA-pair kernel's tile width)
             w1, b1 = bf(sd[b + "ff.net.0.proj.weight"]), bf(sd[b + "ff.net.0.proj.bias"]).float()
             inner4 = w1.shape[0] // 2
-            assert inner4 % 64 == 0
-            wv, wg = w1[:inner4].reshape(inner4 // 64, 64, -1), w1[inner4:].reshape(inner4 // 64, 64, -1)
+            hb = self.GEGLU_BLOCK // 2
+            assert inner4 % hb == 0
+            wv, wg = w1[:inner4].reshape(inner4 // hb, hb, -1), w1[inner4:].reshape(inner4 // hb, hb, -1)
             W[b + "ff1.w"] = torch.cat([wv, wg], dim=1).reshape(2 * inner4, -1).contiguous().to(dev)
-            bv, bg = b1[:inner4].reshape(inner4 // 64, 64), b1[inner4:].reshape(inner4 // 64, 64)
+            bv, bg = b1[:inner4].reshape(inner4 // hb, hb), b1[inner4:].reshape(inner4 // hb, hb)
             W[b + "ff1.b"] = torch.cat([bv, bg], dim=1).reshape(2 * inner4).contiguous().to(dev)
             W[b + "ff2.w"], W[b + "ff2.b"] = mat(b + "ff.net.2.weight"), f32(b + "ff.net.2.bias")
 
@@ -332,7 +335,8 @@ class UNetModel:
         # --- GEGLU feed-forward
         ops.layernorm(hcur, W[b + "norm3.g"], W[b + "norm3.b"], ln, rows=T, c=ch)
         ff = self._buf("tr.ff", T * 4 * ch)
-        ops.gemm_conv(ln, W[b + "ff1.w"], ff, n_img=1, h=1, w=T, c0=ch, n_out=8 * ch, bias=W[b + "ff1.b"], epilogue=CPD_EPI_GEGLU)
+        ops.gemm_conv(ln, W[b + "ff1.w"], ff, n_img=1, h=1, w=T, c0=ch, n_out=8 * ch, bias=W[b + "ff1.b"], epilogue=CPD_EPI_GEGLU,
+                      geglu_block=self.GEGLU_BLOCK)
         ops.gemm_conv(ff, W[b + "ff2.w"], hcur, n_img=1, h=1, w=T, c0=4 * ch, n_out=ch, bias=W[b + "ff2.b"], residual=hcur,
                       ld_res=ch)
         out = self._buf(p + "out", T * ch)

@@ -22,8 +22,8 @@ def _count(n=1):
 
 
 class _Prof:
-    def __init__(self, kind, flops):
-        self.kind, self.flops = kind, flops
+    def __init__(self, kind, flops, label=""):
+        self.kind, self.flops, self.label = kind, flops, label
 
     def __enter__(self):
         if PROFILE is not None:
@@ -34,7 +34,7 @@ class _Prof:
     def __exit__(self, *exc):
         if PROFILE is not None:
             self.e1.record()
-            PROFILE.append((self.kind, self.e0, self.e1, self.flops))
+            PROFILE.append((self.kind, self.e0, self.e1, self.flops, self.label))
 
 
 def _req(t, dtype, name):
@@ -111,7 +111,7 @@ def sampler_step(eps, x, *, n_sub, weights, mask_scalars, masks, guidance, sampl
 
 
 def gemm_conv(a0, wt, out, *, n_img, h, w, c0, n_out, a1=None, c1=0, ksize=1, stride=1, bias=None, rowvec=None,
-              rowvec_stride=0, residual=None, ld_res=0, ldd=None, epilogue=CPD_EPI_NONE, variant=0, m_valid=0):
+              rowvec_stride=0, residual=None, ld_res=0, ldd=None, epilogue=CPD_EPI_NONE, variant=0, m_valid=0, geglu_block=128):
     """a0/a1 and wt are 16-bit (fp16 or bf16, independently); out/residual share one 16-bit dtype."""
     a_f16 = _act(a0, "a0")
     _act(a1, "a1", like=a0.dtype)
@@ -133,8 +133,10 @@ def gemm_conv(a0, wt, out, *, n_img, h, w, c0, n_out, a1=None, c1=0, ksize=1, st
     p.ldd = ldd if ldd is not None else (n_out // 2 if epilogue == CPD_EPI_GEGLU else n_out)
     p.epilogue, p.variant, p.m_valid = epilogue, variant, m_valid
     p.a_fp16, p.b_fp16, p.out_fp16 = a_f16, b_f16, o_f16
+    p.geglu_block = geglu_block if epilogue == CPD_EPI_GEGLU else 0
     flops = 2.0 * n_img * (h // stride) * (w // stride) * n_out * ksize * ksize * (c0 + c1)
-    with _Prof("gemm_conv", flops):
+    label = f"M={n_img * (h // stride) * (w // stride)} N={n_out} K={ksize * ksize * (c0 + c1)}" + (" geglu" if epilogue else "")
+    with _Prof("gemm_conv", flops, label):
         check(load().cpd_gemm_conv(C.byref(p), stream_ptr()), "cpd_gemm_conv")
     _count()
     return out
@@ -149,7 +151,7 @@ def groupnorm(a0, gamma, beta, out, stats, *, n_img, hw, c0, a1=None, c1=0, eps=
     _req(stats, torch.float64, "stats")
     if stats.numel() < n_img * 64:
         raise RuntimeError("stats scratch too small")
-    with _Prof("groupnorm", 0.0):
+    with _Prof("groupnorm", 0.0, f"n={n_img} hw={hw} C={c0 + c1}"):
         check(load().cpd_groupnorm(ptr(a0), ptr(a1), c0, c1, n_img, hw, ptr(gamma), ptr(beta), float(eps), int(silu), f16, ptr(stats),
                                    ptr(out), stream_ptr()), "cpd_groupnorm")
     _count(2)
@@ -161,7 +163,7 @@ def layernorm(x, gamma, beta, out, *, rows, c, eps=1e-5):
     _act(out, "out", like=x.dtype)
     _req(gamma, torch.float32, "gamma")
     _req(beta, torch.float32, "beta")
-    with _Prof("layernorm", 0.0):
+    with _Prof("layernorm", 0.0, f"rows={rows} C={c}"):
         check(load().cpd_layernorm(ptr(x), rows, c, ptr(gamma), ptr(beta), float(eps), f16, ptr(out), stream_ptr()), "cpd_layernorm")
     _count()
     return out
@@ -230,7 +232,7 @@ def attention(q, k, vt, o, *, ldq, ldk, ldvt, ldo, batch, heads, nq, nk, nk_pad,
     p.q, p.ldq, p.k, p.ldk, p.vt, p.ldvt, p.o, p.ldo = q.data_ptr(), ldq, k.data_ptr(), ldk, vt.data_ptr(), ldvt, o.data_ptr(), ldo
     p.batch, p.heads, p.nq, p.nk, p.nk_pad, p.dpad, p.scale = batch, heads, nq, nk, nk_pad, dpad, float(scale)
     p.kv_batch, p.act_fp16 = kv_batch, f16
-    with _Prof("attention", 4.0 * batch * heads * nq * nk * dpad):
+    with _Prof("attention", 4.0 * batch * heads * nq * nk * dpad, f"B={batch} H={heads} nq={nq} nk={nk} d={dpad}"):
         check(load().cpd_attention(C.byref(p), stream_ptr()), "cpd_attention")
     _count()
     return o

@@ -103,8 +103,13 @@ enum { CPD_EPI_NONE = 0, CPD_EPI_GEGLU = 1 };
  * wt: [n_out][ksize*ksize][c0 + c1] bf16 (K-major).  bias: fp32 [n_out] or NULL.
  * rowvec: fp32, element (img, n) at rowvec[img * rowvec_stride + n] (time-embedding add, unet.py:266-274) or NULL.
  * residual: bf16 [pixels][ld_res] or NULL.  d: bf16 [pixels][ldd].
- * CPD_EPI_GEGLU: wt rows are interleaved per 128-column tile as [64 value rows | 64 gate rows]; d gets
- * n_out/2 columns: value * gelu(gate) (attention.py:92-100).
+ * CPD_EPI_GEGLU: wt rows are interleaved per `geglu_block`-column tile (128 or 256) as
+ * [geglu_block/2 value rows | geglu_block/2 gate rows]; d gets n_out/2 columns: value * gelu(gate)
+ * (attention.py:92-100).
+ *
+ * variant 0 (auto) runs the persistent CTA-pair kernel (tcgen05 cta_group::2, 256 x BN tiles, double-buffered TMEM
+ * accumulators, gemm_umma2.cu); variants 1 / 2 run the one-tile-per-CTA 128 x 128 / 128 x 256 kernel
+ * (gemm_umma.cu); variant >= 32 forces the pair kernel's tile width BN = variant (a multiple of 32, <= 256).
  */
 typedef struct {
   const void* a0; const void* a1;
@@ -118,11 +123,12 @@ typedef struct {
   const void* residual; int ld_res;
   void* d; int ldd;
   int epilogue;
-  int variant; /* 0 = auto; 1 = 128x128 tile (3 stages), 2 = 128x256 tile (4 stages) */
+  int variant; /* 0 = auto (CTA-pair kernel); 1 = 128x128 1-CTA tile, 2 = 128x256 1-CTA tile; >= 32: pair kernel, BN = variant */
   int m_valid; /* plain GEMM only: number of valid rows (<= w_in); 0 = all */
   int a_fp16;  /* element type of a0/a1: 1 = fp16, 0 = bf16 (16-bit either way; tcgen05 kind::f16 takes both) */
   int b_fp16;  /* element type of wt */
   int out_fp16;/* element type of d and residual */
+  int geglu_block; /* CPD_EPI_GEGLU: interleave block of wt rows (128 or 256; 0 = 128) */
 } cpd_gemm_params;
 
 cpd_status cpd_gemm_conv(const cpd_gemm_params* p, void* stream);

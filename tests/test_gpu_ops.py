@@ -32,7 +32,12 @@ DEV = "cuda"
 
 # ------------------------------------------------------------------------------------------------ GEMM
 @pytest.mark.parametrize("M,N,K,variant", [(128, 128, 64, 1), (256, 256, 128, 2), (384, 320, 320, 1), (1000, 1280, 640, 2),
-                                           (77 * 4, 384, 768, 1), (4096, 640, 2560, 0), (128, 128, 64, 2)])
+                                           (77 * 4, 384, 768, 1), (4096, 640, 2560, 0), (128, 128, 64, 2),
+                                           # persistent CTA-pair kernel: auto tile width, forced widths, ragged M / N,
+                                           # more tiles than SM pairs (several tiles per cluster, both TMEM stages)
+                                           (128, 128, 64, 0), (256, 256, 128, 0), (384, 320, 320, 0), (1000, 1280, 640, 0),
+                                           (77 * 4, 384, 768, 0), (65536, 320, 320, 0), (16384, 640, 640, 160), (4096, 1280, 1280, 256),
+                                           (8192, 768, 320, 64), (5000, 328, 192, 96), (20000, 640, 128, 224), (300, 2560, 320, 192)])
 def test_gemm_plain(ops, M, N, K, variant):
     g = torch.Generator(device="cpu").manual_seed(M + N + K)
     a = bf(torch.randn(M, K, generator=g)).to(DEV)
@@ -56,36 +61,47 @@ def test_gemm_no_epilogue_exactness(ops):
     a = torch.randint(-3, 4, (M, K), generator=g).float()
     w = torch.randint(-3, 4, (N, K), generator=g).float()
     out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
-    ops.gemm_conv(bf(a).to(DEV), bf(w).to(DEV), out, n_img=1, h=1, w=M, c0=K, n_out=N, variant=1)
-    torch.cuda.synchronize()
-    ref = a @ w.t()
-    bad = (out.float().cpu() != bf(ref).float()).nonzero()
-    print("mismatches:", bad.shape[0], bad[:10].tolist())
-    assert bad.shape[0] == 0
+    for variant in (1, 0, 64):
+        out.fill_(float("nan"))
+        ops.gemm_conv(bf(a).to(DEV), bf(w).to(DEV), out, n_img=1, h=1, w=M, c0=K, n_out=N, variant=variant)
+        torch.cuda.synchronize()
+        ref = a @ w.t()
+        bad = (out.float().cpu() != bf(ref).float()).nonzero()
+        print(f"variant {variant} mismatches:", bad.shape[0], bad[:10].tolist())
+        assert bad.shape[0] == 0
 
 
-def test_gemm_geglu(ops):
-    M, C = 512, 320
+@pytest.mark.parametrize("M,C,block,variant", [(512, 320, 128, 1), (512, 320, 128, 0), (512, 320, 256, 0), (40000, 320, 256, 0),
+                                               (4096, 640, 256, 0)])
+def test_gemm_geglu(ops, M, C, block, variant):
     g = torch.Generator().manual_seed(11)
     a = bf(torch.randn(M, C, generator=g)).to(DEV)
     w = bf(torch.randn(8 * C, C, generator=g) / math.sqrt(C))
     b = bf(torch.randn(8 * C, generator=g) * 0.1).float()
     inner4 = 4 * C
-    wp = torch.cat([w[:inner4].reshape(-1, 64, C), w[inner4:].reshape(-1, 64, C)], dim=1).reshape(8 * C, C).contiguous().to(DEV)
-    bp = torch.cat([b[:inner4].reshape(-1, 64), b[inner4:].reshape(-1, 64)], dim=1).reshape(8 * C).contiguous().to(DEV)
+    hb = block // 2
+    wp = torch.cat([w[:inner4].reshape(-1, hb, C), w[inner4:].reshape(-1, hb, C)], dim=1).reshape(8 * C, C).contiguous().to(DEV)
+    bp = torch.cat([b[:inner4].reshape(-1, hb), b[inner4:].reshape(-1, hb)], dim=1).reshape(8 * C).contiguous().to(DEV)
     out = torch.empty(M, inner4, dtype=torch.bfloat16, device=DEV)
-    ops.gemm_conv(a, wp, out, n_img=1, h=1, w=M, c0=C, n_out=8 * C, bias=bp, epilogue=ops.CPD_EPI_GEGLU)
+    ops.gemm_conv(a, wp, out, n_img=1, h=1, w=M, c0=C, n_out=8 * C, bias=bp, epilogue=ops.CPD_EPI_GEGLU, variant=variant,
+                  geglu_block=block)
     torch.cuda.synchronize()
     y = a.float() @ w.float().to(DEV).t() + b.to(DEV)
     ref = y[:, :inner4] * F.gelu(y[:, inner4:])
     r = rel(out, ref)
-    print(f"geglu rel {r:.3e}")
+    print(f"geglu M{M} C{C} block{block} v{variant} rel {r:.3e}")
     assert r < 6e-3
 
 
 @pytest.mark.parametrize("n,h,w,c0,c1,cout,stride,variant", [
     (2, 16, 16, 64, 0, 128, 1, 1), (1, 64, 64, 320, 0, 320, 1, 0), (3, 8, 8, 128, 64, 256, 1, 2), (2, 32, 32, 64, 0, 64, 2, 1),
-    (4, 8, 8, 1280, 1280, 1280, 1, 0), (2, 16, 16, 128, 0, 128, 2, 2), (1, 24, 24, 64, 0, 64, 1, 1), (2, 12, 12, 64, 64, 128, 1, 1)])
+    (4, 8, 8, 1280, 1280, 1280, 1, 0), (2, 16, 16, 128, 0, 128, 2, 2), (1, 24, 24, 64, 0, 64, 1, 1), (2, 12, 12, 64, 64, 128, 1, 1),
+    # CTA-pair kernel: every level of the SD UNet (64^2 .. 8^2), stride 2, skip concat, tiny 2x2 / 4x4 images (boxes
+    # spanning several images), odd image counts, forced tile widths
+    (2, 16, 16, 64, 0, 128, 1, 0), (3, 8, 8, 128, 64, 256, 1, 0), (2, 32, 32, 64, 0, 64, 2, 0), (2, 16, 16, 128, 0, 128, 2, 0),
+    (1, 24, 24, 64, 0, 64, 1, 0), (2, 12, 12, 64, 64, 128, 1, 0), (16, 64, 64, 320, 0, 320, 1, 0), (16, 32, 32, 640, 320, 640, 1, 160),
+    (16, 16, 16, 1280, 0, 1280, 1, 256), (16, 8, 8, 1280, 1280, 1280, 1, 128), (5, 2, 2, 128, 0, 128, 1, 0), (3, 4, 4, 64, 64, 192, 1, 0),
+    (6, 4, 4, 128, 0, 64, 2, 0), (16, 64, 64, 320, 0, 320, 2, 0), (7, 16, 16, 64, 0, 320, 1, 96)])
 def test_conv3x3(ops, n, h, w, c0, c1, cout, stride, variant):
     g = torch.Generator().manual_seed(n * h + cout)
     cin = c0 + c1

@@ -35,6 +35,11 @@ static PFN_encodeTiled get_encode() {
 
 int cpd_make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                        const uint64_t* strides_bytes, const uint32_t* box) {
+  return cpd_make_tmap16(map, base, rank, dims, strides_bytes, box, 128);
+}
+
+int cpd_make_tmap16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, int swizzle_bytes) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) {
     cpd_set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
@@ -60,7 +65,11 @@ int cpd_make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint6
       return CPD_ERR_INVALID;
     }
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, gbox,
-                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                        : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                               : (swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE)),
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     cpd_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu,.. box %u,%u,..)", (int)r, rank,

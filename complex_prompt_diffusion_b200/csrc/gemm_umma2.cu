@@ -4,8 +4,11 @@
 //     CTA stages its own 128 rows of A and HALF of the B tile (BN/2 weight rows), so the shared-memory operand
 //     traffic per MMA is half that of a 1-CTA 128 x BN tile (which is shared-memory-bound at BN = 128).
 //   * persistent: one cluster per SM pair loops over output tiles; the fp32 accumulator is double-buffered in
-//     TMEM (2 x 256 columns), so the epilogue of tile i (TMEM -> registers -> bias / time-embedding / residual /
-//     GEGLU -> 16-bit stores) overlaps the TMA + MMA main loop of tile i + 1.
+//     TMEM (2 x 256 columns), so the epilogue of tile i overlaps the TMA + MMA main loop of tile i + 1.
+//   * epilogue through shared memory: TMEM -> registers -> bias / time-embedding / residual / GEGLU -> 64B-swizzled
+//     staging tile -> TMA store (full-line coalesced, asynchronous, clipped at the tensor edge by the TMA unit).  The
+//     residual tile is PREFETCHED by TMA into the same staging buffer one chunk ahead, so no thread ever issues a
+//     row-strided global load or store.
 //   * warp roles: warp 0 = TMA producer (both CTAs), warp 1 = MMA issuer (leader CTA only), warp 2 = TMEM
 //     allocator, warps 4-11 = epilogue (two warps per TMEM lane quarter, each taking half of the columns).
 //   * BN is a RUNTIME multiple of 32 (<= 256) chosen per layer so that BN divides N (320 -> 160, 640 -> 160/128,
@@ -27,8 +30,14 @@ constexpr int MAX_STAGES = 8;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int NUM_SM_PAIRS = 74;
 
+constexpr int CHUNK_COLS = 32;                     // output columns per staging chunk (64-byte rows, SWIZZLE_64B)
+constexpr int CHUNK_BYTES = BM * CHUNK_COLS * 2;   // 8 KB
+constexpr int STAGING_BUFS = 3;                    // per epilogue group
+constexpr int STAGING_BYTES = 2 * STAGING_BUFS * CHUNK_BYTES;
+
 struct Gemm2Args {
   CUtensorMap map_a0, map_a1, map_b;
+  CUtensorMap map_d, map_res;  // (c, x, y, n) views of the output / residual, box = 32 columns x one pixel box
   ConvGeom g;
   const float* bias;
   const float* rowvec;
@@ -48,11 +57,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stages = args.stages;
   const int stage_bytes = args.stage_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+  uint8_t* staging = smem + stages * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tmem_full = empty_bar + MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_bar = tmem_empty + 2;  // [2 groups][STAGING_BUFS]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + 2 * STAGING_BUFS);
 
   const ConvGeom& g = args.g;
   const int warp = threadIdx.x >> 5;
@@ -69,8 +80,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
     tma_prefetch_desc(&args.map_a0);
     tma_prefetch_desc(&args.map_b);
     if (g.cb1 > 0) tma_prefetch_desc(&args.map_a1);
+    tma_prefetch_desc(&args.map_d);
+    if (args.residual) tma_prefetch_desc(&args.map_res);
   }
   if (warp == 1 && lane == 0) {
+    for (int s = 0; s < 2 * STAGING_BUFS; ++s) mbar_init(&res_bar[s], 1);
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 2);   // leader: its own arrive.expect_tx + the peer's remote arrive
       mbar_init(&empty_bar[s], 1);  // tcgen05.commit multicast to both CTAs
@@ -200,112 +214,166 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
     }
   } else if (warp >= FIRST_EPI_WARP) {
     // ================= epilogue (warps 4..11 of both CTAs) =================
+    // Two groups of 4 warps (one warp per TMEM lane quarter); group `grp` owns every other half of the tile's
+    // 32-column chunks.  Per chunk: [leader] make sure the staging buffer two chunks back has been read by its TMA
+    // store and prefetch the NEXT chunk's residual tile -> [all] wait for this chunk's residual -> TMEM load ->
+    // epilogue math -> swizzled st.shared -> group barrier -> [leader] TMA store.
     const bool of16 = g.out_fp16 != 0;
-    const int q = warp & 3;                           // TMEM lane quarter this warp may access
-    const int half = (warp - FIRST_EPI_WARP) >> 2;    // which half of the tile's columns
-    const int r = q * 32 + lane;                      // row within this CTA's 128-row tile
+    const int q = warp & 3;                         // TMEM lane quarter this warp may access
+    const int grp = (warp - FIRST_EPI_WARP) >> 2;   // epilogue group
+    const int r = q * 32 + lane;                    // row within this CTA's 128-row tile
+    const bool leader = (q == 0 && lane == 0);
     const int bn = args.bn;
+    const bool geglu = g.epilogue == CPD_EPI_GEGLU;
+    const int out_w = geglu ? (bn >> 1) : bn;       // output columns per tile
+    const int nch = out_w / CHUNK_COLS;
+    const int c_lo = grp == 0 ? 0 : (nch + 1) / 2, c_hi = grp == 0 ? (nch + 1) / 2 : nch;
+    const int box_rows = g.tw * g.th * g.nb;
+    uint8_t* my_staging = staging + grp * STAGING_BUFS * CHUNK_BYTES;
+    uint64_t* my_res_bar = res_bar + grp * STAGING_BUFS;
+    const bool has_res = args.residual != nullptr;
+    const uint32_t sw = (uint32_t)((r >> 1) & 3);   // SWIZZLE_64B: 16-byte chunk index ^= (row / 2) % 4
+    uint8_t* my_row = nullptr;                      // set per buffer
+
+    // residual tile of chunk (tile t, chunk ch) -> staging buffer `buf`
+    auto issue_residual = [&](int t, int ch, int buf) {
+      const int m2 = t / args.n_tiles;
+      const int n_tile = t - m2 * args.n_tiles;
+      const int col0 = n_tile * out_w + ch * CHUNK_COLS;
+      mbar_arrive_expect_tx(&my_res_bar[buf], CHUNK_BYTES);
+      for (int j = 0; j < g.nbox; ++j) {
+        const BoxCoord bc = box_coord(g, m2 * 2 + (int)rank, j, 4, 0);
+        tma_load_4d(my_staging + buf * CHUNK_BYTES + j * box_rows * (CHUNK_COLS * 2), &args.map_res, &my_res_bar[buf], col0, bc.x,
+                    bc.y, bc.n);
+      }
+    };
+
+    int kc = 0;  // chunks processed by this group so far (staging buffer = kc % 3, residual barrier parity = (kc / 3) & 1)
+    if (leader && has_res && cluster_id < total_tiles && c_lo < c_hi) issue_residual(cluster_id, c_lo, 0);
     int it = 0;
     for (int t = cluster_id; t < total_tiles; t += num_clusters, ++it) {
       const int m2 = t / args.n_tiles;
       const int n_tile = t - m2 * args.n_tiles;
-      const RowCoord rc = row_coord(g, m2 * 2 + (int)rank, r);
-      const bool valid = rc.valid;
-      const int64_t row = rc.row;
+      const int m_tile = m2 * 2 + (int)rank;
+      const RowCoord rc = row_coord(g, m_tile, r);
+      const int n_img_row = rc.n < g.n_img ? rc.n : g.n_img - 1;
+      const float* rv = args.rowvec ? args.rowvec + (int64_t)n_img_row * g.rowvec_stride : nullptr;
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
       mbar_wait(&tmem_full[acc], acc_phase, 3);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS);
 
-      if (g.epilogue == CPD_EPI_GEGLU) {
-        // tile columns [0, bn/2) = value, [bn/2, bn) = gate  ->  bn/2 output columns
-        const int hb = bn >> 1;
-        const int nv = hb >> 4;  // 16-column value chunks
-        const int c_lo = half == 0 ? 0 : (nv + 1) / 2, c_hi = half == 0 ? (nv + 1) / 2 : nv;
-        const int ncol0 = n_tile * hb;
-        const float* bias_v = args.bias ? args.bias + n_tile * bn : nullptr;
-#pragma unroll 1
-        for (int ch = c_lo; ch < c_hi; ++ch) {
-          const int c = ch * 16;
-          uint32_t va[16], vg[16];
-          tmem_ld16(taddr + c, va);
-          tmem_ld16(taddr + hb + c, vg);
-          tmem_ld_wait();
-          if (valid && ncol0 + c < g.n_store) {
-            uint32_t packed[8];
-#pragma unroll
-            for (int e = 0; e < 16; e += 2) {
-              float a0 = __uint_as_float(va[e]), a1 = __uint_as_float(va[e + 1]);
-              float g0 = __uint_as_float(vg[e]), g1 = __uint_as_float(vg[e + 1]);
-              if (bias_v) {
-                a0 += __ldg(bias_v + c + e);
-                a1 += __ldg(bias_v + c + e + 1);
-                g0 += __ldg(bias_v + hb + c + e);
-                g1 += __ldg(bias_v + hb + c + e + 1);
-              }
-              // the reference rounds the projection to the model dtype before x * gelu(gate) (attention.py:98-100)
-              a0 = round_act(a0, of16);
-              a1 = round_act(a1, of16);
-              g0 = round_act(gelu_erf_f(round_act(g0, of16)), of16);
-              g1 = round_act(gelu_erf_f(round_act(g1, of16)), of16);
-              packed[e / 2] = pack_act2(a0 * g0, a1 * g1, of16);
+      for (int ch = c_lo; ch < c_hi; ++ch, ++kc) {
+        const int buf = kc % STAGING_BUFS;
+        uint8_t* sbuf = my_staging + buf * CHUNK_BYTES;
+        my_row = sbuf + r * (CHUNK_COLS * 2);
+        if (leader) {
+          // the store issued two chunks ago has finished READING its buffer (= the buffer of chunk kc + 1)
+          bulk_wait_group_read<1>();
+          if (has_res) {
+            int nt = t, nc = ch + 1;
+            if (nc == c_hi) {
+              nt = t + num_clusters;
+              nc = c_lo;
             }
-            uint4* dst = reinterpret_cast<uint4*>(args.d + row * g.ldd + ncol0 + c);
-            dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-            dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+            if (nt < total_tiles) issue_residual(nt, nc, (kc + 1) % STAGING_BUFS);
           }
         }
-      } else {
-        const int nch = bn >> 5;  // 32-column chunks
-        const int c_lo = half == 0 ? 0 : (nch + 1) / 2, c_hi = half == 0 ? (nch + 1) / 2 : nch;
-        const int ncol0 = n_tile * bn;
-        const float* rv = (args.rowvec && valid) ? args.rowvec + (int64_t)rc.n * g.rowvec_stride : nullptr;
-#pragma unroll 1
-        for (int ch = c_lo; ch < c_hi; ++ch) {
-          uint32_t v[32];
-          tmem_ld32(taddr + ch * 32, v);
+        const int col0 = n_tile * out_w + ch * CHUNK_COLS;  // first output column of this chunk
+        float f[32];
+        if (geglu) {
+          // tile columns [0, bn/2) = value, [bn/2, bn) = gate
+          uint32_t va[32], vg[32];
+          tmem_ld32(taddr + ch * CHUNK_COLS, va);
+          tmem_ld32(taddr + (bn >> 1) + ch * CHUNK_COLS, vg);
           tmem_ld_wait();
-          if (valid) {
+          const float* bias_v = args.bias ? args.bias + n_tile * bn + ch * CHUNK_COLS : nullptr;
 #pragma unroll
-            for (int h8 = 0; h8 < 4; ++h8) {  // 4 groups of 8 columns = one 16-byte store each
-              const int col = ncol0 + ch * 32 + h8 * 8;
-              if (col < g.n_store) {
-                float f[8];
+          for (int e = 0; e < 32; ++e) {
+            float a0 = __uint_as_float(va[e]), g0 = __uint_as_float(vg[e]);
+            if (bias_v) {
+              a0 += __ldg(bias_v + e);
+              g0 += __ldg(bias_v + (bn >> 1) + e);
+            }
+            // the reference rounds the projection to the model dtype before x * gelu(gate) (attention.py:98-100)
+            a0 = round_act(a0, of16);
+            g0 = round_act(gelu_erf_f(round_act(g0, of16)), of16);
+            f[e] = a0 * g0;
+          }
+        } else {
+          uint32_t v[32];
+          tmem_ld32(taddr + ch * CHUNK_COLS, v);
+          tmem_ld_wait();
 #pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[h8 * 8 + e]);
-                if (args.bias) {
-                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(args.bias + col));
-                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(args.bias + col + 4));
-                  f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                  f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-                }
-                if (rv) {
-                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(rv + col));
-                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(rv + col + 4));
-                  f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                  f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-                }
-                if (args.residual) {
-                  const uint4 rr = *reinterpret_cast<const uint4*>(args.residual + row * g.ld_res + col);
-                  const float2 r0 = unpack_act2(rr.x, of16), r1 = unpack_act2(rr.y, of16), r2 = unpack_act2(rr.z, of16),
-                               r3 = unpack_act2(rr.w, of16);
-                  f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y;
-                  f[4] += r2.x; f[5] += r2.y; f[6] += r3.x; f[7] += r3.y;
-                }
-                *reinterpret_cast<uint4*>(args.d + row * g.ldd + col) =
-                    make_uint4(pack_act2(f[0], f[1], of16), pack_act2(f[2], f[3], of16), pack_act2(f[4], f[5], of16),
-                               pack_act2(f[6], f[7], of16));
+          for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
+          if (col0 + CHUNK_COLS <= g.n_store) {
+            if (args.bias) {
+#pragma unroll
+              for (int e = 0; e < 32; e += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.bias + col0 + e));
+                f[e] += b4.x; f[e + 1] += b4.y; f[e + 2] += b4.z; f[e + 3] += b4.w;
+              }
+            }
+            if (rv) {
+#pragma unroll
+              for (int e = 0; e < 32; e += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(rv + col0 + e));
+                f[e] += b4.x; f[e + 1] += b4.y; f[e + 2] += b4.z; f[e + 3] += b4.w;
+              }
+            }
+          } else {  // ragged last chunk (n_out is only a multiple of 8)
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              if (col0 + e < g.n_store) {
+                if (args.bias) f[e] += __ldg(args.bias + col0 + e);
+                if (rv) f[e] += __ldg(rv + col0 + e);
               }
             }
           }
+        }
+        if (has_res) {
+          mbar_wait(&my_res_bar[buf], (uint32_t)((kc / STAGING_BUFS) & 1), 5);
+#pragma unroll
+          for (int c16 = 0; c16 < 4; ++c16) {
+            const uint4 rr = *reinterpret_cast<const uint4*>(my_row + ((c16 ^ sw) << 4));
+            const float2 r0 = unpack_act2(rr.x, of16), r1 = unpack_act2(rr.y, of16), r2 = unpack_act2(rr.z, of16),
+                         r3 = unpack_act2(rr.w, of16);
+            f[c16 * 8 + 0] += r0.x; f[c16 * 8 + 1] += r0.y; f[c16 * 8 + 2] += r1.x; f[c16 * 8 + 3] += r1.y;
+            f[c16 * 8 + 4] += r2.x; f[c16 * 8 + 5] += r2.y; f[c16 * 8 + 6] += r3.x; f[c16 * 8 + 7] += r3.y;
+          }
+        }
+#pragma unroll
+        for (int c16 = 0; c16 < 4; ++c16) {
+          *reinterpret_cast<uint4*>(my_row + ((c16 ^ sw) << 4)) =
+              make_uint4(pack_act2(f[c16 * 8 + 0], f[c16 * 8 + 1], of16), pack_act2(f[c16 * 8 + 2], f[c16 * 8 + 3], of16),
+                         pack_act2(f[c16 * 8 + 4], f[c16 * 8 + 5], of16), pack_act2(f[c16 * 8 + 6], f[c16 * 8 + 7], of16));
+        }
+        fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+        if (ch + 1 == c_hi) {
+          // last TMEM read of this tile by this warp: hand the accumulator back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
+        }
+        named_bar_sync(1 + grp, 128);
+        if (leader) {
+          if (col0 < g.n_store) {
+            for (int j = 0; j < g.nbox; ++j) {
+              const BoxCoord bc = box_coord(g, m_tile, j, 4, 0);
+              tma_store_4d(&args.map_d, sbuf + j * box_rows * (CHUNK_COLS * 2), col0, bc.x, bc.y, bc.n);
+            }
+          }
+          bulk_commit_group();
         }
       }
-      // all TMEM reads of this warp are complete (tcgen05.wait::ld above): hand the accumulator back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
+      if (c_lo == c_hi) {  // this group has no chunk in the tile (single-chunk tiles): still release the accumulator
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
+      }
     }
+    if (leader) bulk_wait_group<0>();  // all stores complete before the CTA (and its shared memory) goes away
   }
 
   __syncwarp();
@@ -365,7 +433,7 @@ cpd_status cpd_gemm_conv_2cta(const cpd_gemm_params* p, void* stream) {
   args.n_tiles = (p->n_out + bn - 1) / bn;
   args.num_k = g.taps * (g.cb0 + g.cb1);
   args.stage_bytes = A_BYTES + (bn / 2) * 128;
-  int stages = (227 * 1024 - 1024 - 512) / args.stage_bytes;
+  int stages = (227 * 1024 - 1024 - 512 - STAGING_BYTES) / args.stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   args.stages = stages;
   g.idesc = umma_idesc_f16(256, bn, p->a_fp16 != 0, p->b_fp16 != 0);
@@ -375,8 +443,23 @@ cpd_status cpd_gemm_conv_2cta(const cpd_gemm_params* p, void* stream) {
   args.rowvec = p->rowvec;
   args.residual = reinterpret_cast<const bf16*>(p->residual);
   args.d = reinterpret_cast<bf16*>(p->d);
+  {  // output / residual views (c, x, y, n), 64-byte swizzle, box = 32 columns x one pixel box
+    const uint64_t rows_x = (uint64_t)((p->m_valid > 0 && g.h_out == 1 && g.n_img == 1) ? p->m_valid : g.w_out);
+    uint64_t dims[4] = {(uint64_t)g.n_store, rows_x, (uint64_t)g.h_out, (uint64_t)g.n_img};
+    uint32_t box[4] = {(uint32_t)CHUNK_COLS, (uint32_t)g.tw, (uint32_t)g.th, (uint32_t)g.nb};
+    uint64_t str[3] = {(uint64_t)p->ldd * 2, (uint64_t)g.w_out * p->ldd * 2, (uint64_t)g.h_out * g.w_out * p->ldd * 2};
+    rc = cpd_make_tmap16(&args.map_d, p->d, 4, dims, str, box, 64);
+    if (rc) return rc;
+    if (p->residual) {
+      uint64_t rstr[3] = {(uint64_t)p->ld_res * 2, (uint64_t)g.w_out * p->ld_res * 2, (uint64_t)g.h_out * g.w_out * p->ld_res * 2};
+      rc = cpd_make_tmap16(&args.map_res, p->residual, 4, dims, rstr, box, 64);
+      if (rc) return rc;
+    } else {
+      args.map_res = args.map_d;
+    }
+  }
 
-  const int smem_bytes = stages * args.stage_bytes + 512 + 1024;
+  const int smem_bytes = stages * args.stage_bytes + STAGING_BYTES + 512 + 1024;
   static bool configured = false;
   if (!configured) {
     CPD_CUDA_CHECK(cudaFuncSetAttribute(gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

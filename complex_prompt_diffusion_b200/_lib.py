@@ -51,7 +51,7 @@ class AttnParams(C.Structure):
         ("q", C.c_void_p), ("ldq", C.c_int), ("k", C.c_void_p), ("ldk", C.c_int), ("vt", C.c_void_p), ("ldvt", C.c_int),
         ("o", C.c_void_p), ("ldo", C.c_int),
         ("batch", C.c_int), ("heads", C.c_int), ("nq", C.c_int), ("nk", C.c_int), ("nk_pad", C.c_int), ("dpad", C.c_int),
-        ("scale", C.c_float), ("kv_batch", C.c_int), ("act_fp16", C.c_int),
+        ("scale", C.c_float), ("kv_batch", C.c_int), ("act_fp16", C.c_int), ("d_head", C.c_int),
     ]
 
 
@@ -68,7 +68,7 @@ _SIGS = {
     "cpd_small_linear": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                    C.c_void_p, C.c_int, C.c_void_p]),
     "cpd_conv_in": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float,
-                              C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+                              C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "cpd_conv_out": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                C.c_int, C.c_int, C.c_void_p]),
     "cpd_upsample2x": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

@@ -263,12 +263,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) attention_kernel(const __grid_
 
 }  // namespace
 
+cpd_status cpd_attention_2tile(const cpd_attn_params* p, void* stream);  // attention_umma2.cu
+
 extern "C" cpd_status cpd_attention(const cpd_attn_params* p, void* stream) {
   CPD_REQUIRE(p && p->q && p->k && p->vt && p->o, "cpd_attention: null pointer");
   CPD_REQUIRE(p->dpad >= 16 && p->dpad % 16 == 0 && p->dpad <= 160, "cpd_attention: dpad=%d must be a multiple of 16 in [16,160]", p->dpad);
   CPD_REQUIRE(p->batch > 0 && p->heads > 0 && p->nq > 0 && p->nk > 0 && p->nk_pad >= p->nk, "cpd_attention: bad sizes");
   CPD_REQUIRE(p->ldq % 8 == 0 && p->ldk % 8 == 0 && p->ldvt % 8 == 0 && p->ldo % 8 == 0, "cpd_attention: leading dims must be multiples of 8");
   CPD_REQUIRE(((uintptr_t)p->o & 15) == 0, "cpd_attention: o must be 16-byte aligned");
+  CPD_REQUIRE(p->d_head >= 0 && p->d_head <= p->dpad, "cpd_attention: d_head=%d must be in [0, dpad=%d]", p->d_head, p->dpad);
+  if (p->d_head > 0) {  // two query tiles per CTA, P in tensor memory; falls through when the shape is outside its domain
+    const cpd_status st2 = cpd_attention_2tile(p, stream);
+    if (st2 != CPD_ERR_UNSUPPORTED) return st2;
+  }
   AttnArgs a;
   a.o = (bf16*)p->o;
   a.ldo = p->ldo;

@@ -30,8 +30,25 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const bf16* __restrict__ 
     for (int e = 0; e < 8; ++e) s[e] = ss[e] = 0.f;
     const int p0 = blockIdx.x * px_per_block;
     const int p1 = min(p0 + px_per_block, hw);
-    for (int p = p0 + pl; p < p1; p += lanes) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + ((int64_t)n * hw + p) * cs + coff));
+    const bf16* base = src + (int64_t)n * hw * cs + coff;
+    int p = p0 + pl;
+    for (; p + 3 * lanes < p1; p += 4 * lanes) {  // 4 independent 16-byte loads in flight per thread
+      uint4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)(p + j * lanes) * cs));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t u[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack_act2(u[e], f16 != 0);
+          s[2 * e] += f.x; ss[2 * e] += f.x * f.x;
+          s[2 * e + 1] += f.y; ss[2 * e + 1] += f.y * f.y;
+        }
+      }
+    }
+    for (; p < p1; p += lanes) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)p * cs));
       const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -96,8 +113,9 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(const bf16* __restrict__ 
   for (int e = 0; e < 8; ++e) { sc[e] = sh[ch + e]; sf[e] = sh[C + ch + e]; }
   const int p0 = blockIdx.x * px_per_block;
   const int p1 = min(p0 + px_per_block, hw);
-  for (int p = p0 + pl; p < p1; p += lanes) {
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + ((int64_t)n * hw + p) * cs + coff));
+  const bf16* base = src + (int64_t)n * hw * cs + coff;
+  bf16* obase = out + (int64_t)n * hw * C + ch;
+  auto apply_one = [&](const uint4& v, int p) {
     const uint32_t u[4] = {v.x, v.y, v.z, v.w};
     uint32_t o[4];
 #pragma unroll
@@ -108,66 +126,85 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(const bf16* __restrict__ 
       if (silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
       o[e] = pack_act2(y0, y1, f16 != 0);
     }
-    *reinterpret_cast<uint4*>(out + ((int64_t)n * hw + p) * C + ch) = make_uint4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<uint4*>(obase + (int64_t)p * C) = make_uint4(o[0], o[1], o[2], o[3]);
+  };
+  int p = p0 + pl;
+  for (; p + 3 * lanes < p1; p += 4 * lanes) {  // 4 independent 16-byte loads in flight per thread
+    uint4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)(p + j * lanes) * cs));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) apply_one(v[j], p + j * lanes);
   }
+  for (; p < p1; p += lanes) apply_one(__ldg(reinterpret_cast<const uint4*>(base + (int64_t)p * cs)), p);
 }
 
-// ---- LayerNorm: one warp per row, row held in registers ------------------------------------------
-template <int MAXV>  // max 16-byte vectors per lane
+// ---- LayerNorm: one warp per R rows (all loads of the R rows issued before the first use), rows in registers -----
+template <int MAXV, int R>  // max 16-byte vectors per lane, rows per warp
 __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, int rows, int c,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, int f16, bf16* __restrict__ out) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= rows) return;
+  const int row0 = warp * R;
+  if (row0 >= rows) return;
   const int nvec = c / 8;
-  float v[MAXV][8];
-  float sum = 0.f;
+  uint4 raw[R][MAXV];
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (int64_t)warp * c + vi * 8));
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int vi = lane + i * 32;
+      raw[rr][i] = make_uint4(0, 0, 0, 0);
+      if (vi < nvec && row0 + rr < rows) raw[rr][i] = __ldg(reinterpret_cast<const uint4*>(x + (int64_t)(row0 + rr) * c + vi * 8));
+    }
+#pragma unroll
+  for (int rr = 0; rr < R; ++rr) {
+    if (row0 + rr >= rows) break;
+    float v[MAXV][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const uint32_t w[4] = {raw[rr][i].x, raw[rr][i].y, raw[rr][i].z, raw[rr][i].w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float2 f = unpack_act2(w[e], f16 != 0);
         v[i][2 * e] = f.x; v[i][2 * e + 1] = f.y;
-        sum += f.x + f.y;
+        sum += f.x + f.y;  // lanes beyond nvec hold zeros
       }
     }
-  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float mean = sum / (float)c;
-  float var = 0.f;
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)c;
+    float var = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
+    for (int i = 0; i < MAXV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { const float d = v[i][e] - mean; var += d * d; }
+        for (int e = 0; e < 8; ++e) { const float d = v[i][e] - mean; var += d * d; }
+      }
     }
-  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
-  const float rstd = rsqrtf(var / (float)c + eps);
+    for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float rstd = rsqrtf(var / (float)c + eps);
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8 + 4));
-      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      uint32_t o[4];
+    for (int i = 0; i < MAXV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8 + 4));
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        uint32_t o[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e)
-        o[e] = pack_act2((v[i][2 * e] - mean) * rstd * gg[2 * e] + bb[2 * e],
-                         (v[i][2 * e + 1] - mean) * rstd * gg[2 * e + 1] + bb[2 * e + 1], f16 != 0);
-      *reinterpret_cast<uint4*>(out + (int64_t)warp * c + vi * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        for (int e = 0; e < 4; ++e)
+          o[e] = pack_act2((v[i][2 * e] - mean) * rstd * gg[2 * e] + bb[2 * e],
+                           (v[i][2 * e + 1] - mean) * rstd * gg[2 * e + 1] + bb[2 * e + 1], f16 != 0);
+        *reinterpret_cast<uint4*>(out + (int64_t)(row0 + rr) * c + vi * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
     }
   }
 }
@@ -211,11 +248,11 @@ extern "C" cpd_status cpd_layernorm(const void* x, int rows, int c, const float*
   CPD_REQUIRE(rows >= 0, "cpd_layernorm: rows=%d", rows);
   if (rows == 0) return CPD_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  const int blocks = (rows + 7) / 8;
   const int nvec = c / 8;
-  if (nvec <= 64) layernorm_kernel<2><<<blocks, 256, 0, s>>>((const bf16*)x, rows, c, gamma, beta, eps, act_fp16, (bf16*)out);
-  else if (nvec <= 160) layernorm_kernel<5><<<blocks, 256, 0, s>>>((const bf16*)x, rows, c, gamma, beta, eps, act_fp16, (bf16*)out);
-  else layernorm_kernel<8><<<blocks, 256, 0, s>>>((const bf16*)x, rows, c, gamma, beta, eps, act_fp16, (bf16*)out);
+  auto blocks = [&](int r_per_warp) { return (rows + 8 * r_per_warp - 1) / (8 * r_per_warp); };
+  if (nvec <= 64) layernorm_kernel<2, 4><<<blocks(4), 256, 0, s>>>((const bf16*)x, rows, c, gamma, beta, eps, act_fp16, (bf16*)out);
+  else if (nvec <= 160) layernorm_kernel<5, 2><<<blocks(2), 256, 0, s>>>((const bf16*)x, rows, c, gamma, beta, eps, act_fp16, (bf16*)out);
+  else layernorm_kernel<8, 1><<<blocks(1), 256, 0, s>>>((const bf16*)x, rows, c, gamma, beta, eps, act_fp16, (bf16*)out);
   CPD_CUDA_CHECK(cudaGetLastError());
   return CPD_OK;
 }

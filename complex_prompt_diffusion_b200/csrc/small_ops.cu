@@ -72,39 +72,58 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const bf16* __restric
   }
 }
 
-// Input conv: x fp32 NCHW -> bf16 (cast) -> 3x3 pad 1 -> NHWC bf16.  One thread = one pixel x 8 output channels.
+// Input conv: x fp32 NCHW -> (x * scale) cast to the 16-bit model dtype -> 3x3 pad 1 -> NHWC 16-bit, written `rpi` times
+// (one copy per conditioning row of the image: denoiser.py:390-391 broadcasts x_in over the rows).  One thread = one pixel
+// of one SOURCE image x 8 output channels; weights are staged transposed in shared memory ([tap][cout] fp32) so a warp
+// reads consecutive 32-byte groups, the 4 x 9 input taps are warp-broadcast loads.  `scale_ptr` (device, optional)
+// overrides `scale` so that a captured CUDA graph can be replayed with a new c_in.
 __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, int n, int cin, int h, int w,
                                                       const bf16* __restrict__ wt, const float* __restrict__ bias, int cout,
-                                                      float scale, int rpi, int f16, bf16* __restrict__ out) {
+                                                      float scale, const float* __restrict__ scale_ptr, int rpi, int f16,
+                                                      bf16* __restrict__ out) {
+  extern __shared__ uint8_t sh_raw[];
+  float* ws = reinterpret_cast<float*>(sh_raw);  // [9 * cin][cout]
+  const int taps = 9 * cin;
+  for (int i = threadIdx.x; i < taps * cout; i += blockDim.x) {
+    const int co = i / taps, tp = i - co * taps;  // wt is [cout][9][cin]
+    ws[tp * cout + co] = __bfloat162float(wt[i]);
+  }
+  __syncthreads();
+  if (scale_ptr) scale = __ldg(scale_ptr);
   const int cvecs = cout / 8;
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)n * rpi * h * w * cvecs;
-  if (idx >= total) return;
-  const int cv = (int)(idx % cvecs);
-  const int64_t pix = idx / cvecs;
-  const int xx = (int)(pix % w);
-  const int yy = (int)((pix / w) % h);
-  const int nn = (int)(pix / ((int64_t)w * h)) / rpi;  // output row -> source image
-  float acc[8];
+  const int64_t total = (int64_t)n * h * w * cvecs;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % cvecs);
+    const int64_t pix = idx / cvecs;
+    const int xx = (int)(pix % w);
+    const int yy = (int)((pix / w) % h);
+    const int nn = (int)(pix / ((int64_t)w * h));
+    float acc[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) acc[e] = bias ? bias[cv * 8 + e] : 0.f;
-  for (int ky = 0; ky < 3; ++ky) {
-    const int iy = yy + ky - 1;
-    if (iy < 0 || iy >= h) continue;
-    for (int kx = 0; kx < 3; ++kx) {
-      const int ix = xx + kx - 1;
-      if (ix < 0 || ix >= w) continue;
-      for (int c = 0; c < cin; ++c) {
-        const float xv = __bfloat162float(__float2bfloat16_rn(__fmul_rn(x[(((int64_t)nn * cin + c) * h + iy) * w + ix], scale)));
-#pragma unroll
-        for (int e = 0; e < 8; ++e)
-          acc[e] += xv * __bfloat162float(wt[((int64_t)(cv * 8 + e) * 9 + ky * 3 + kx) * cin + c]);
+    for (int e = 0; e < 8; ++e) acc[e] = bias ? __ldg(bias + cv * 8 + e) : 0.f;
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = yy + ky - 1;
+      if (iy < 0 || iy >= h) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = xx + kx - 1;
+        if (ix < 0 || ix >= w) continue;
+        for (int c = 0; c < cin; ++c) {
+          const float xm = __fmul_rn(__ldg(x + (((int64_t)nn * cin + c) * h + iy) * w + ix), scale);
+          const float xv = round_act(xm, f16 != 0);
+          const float4 w0 = *reinterpret_cast<const float4*>(ws + ((ky * 3 + kx) * cin + c) * cout + cv * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(ws + ((ky * 3 + kx) * cin + c) * cout + cv * 8 + 4);
+          acc[0] += xv * w0.x; acc[1] += xv * w0.y; acc[2] += xv * w0.z; acc[3] += xv * w0.w;
+          acc[4] += xv * w1.x; acc[5] += xv * w1.y; acc[6] += xv * w1.z; acc[7] += xv * w1.w;
+        }
       }
     }
+    const uint4 o = make_uint4(pack_act2(acc[0], acc[1], f16 != 0), pack_act2(acc[2], acc[3], f16 != 0),
+                               pack_act2(acc[4], acc[5], f16 != 0), pack_act2(acc[6], acc[7], f16 != 0));
+    const int64_t hw = (int64_t)h * w;
+    const int64_t p_in = pix - (int64_t)nn * hw;
+    for (int rr = 0; rr < rpi; ++rr)
+      *reinterpret_cast<uint4*>(out + (((int64_t)nn * rpi + rr) * hw + p_in) * cout + cv * 8) = o;
   }
-  *reinterpret_cast<uint4*>(out + pix * cout + cv * 8) =
-      make_uint4(pack_act2(acc[0], acc[1], f16 != 0), pack_act2(acc[2], acc[3], f16 != 0), pack_act2(acc[4], acc[5], f16 != 0),
-                 pack_act2(acc[6], acc[7], f16 != 0));
 }
 
 // Output conv: NHWC bf16 (cin) -> 3x3 pad 1 -> NCHW (cout <= 8).  One warp per output pixel.
@@ -215,13 +234,17 @@ extern "C" cpd_status cpd_small_linear(const void* x, int m, int k, const void* 
 }
 
 extern "C" cpd_status cpd_conv_in(const float* x, int n, int cin, int h, int w, const void* wt, const float* bias, int cout,
-                                  float scale, int rows_per_image, int act_fp16, void* out, void* stream) {
+                                  float scale, const float* scale_ptr, int rows_per_image, int act_fp16, void* out, void* stream) {
   CPD_REQUIRE(x && wt && out, "cpd_conv_in: null pointer");
   CPD_REQUIRE(n > 0 && cin > 0 && cin <= 8 && h > 0 && w > 0 && cout % 8 == 0, "cpd_conv_in: bad shape n=%d cin=%d h=%d w=%d cout=%d", n, cin, h, w, cout);
   CPD_REQUIRE(rows_per_image >= 1, "cpd_conv_in: rows_per_image=%d", rows_per_image);
-  const int64_t total = (int64_t)n * rows_per_image * h * w * (cout / 8);
-  conv_in_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, n, cin, h, w, (const bf16*)wt, bias, cout,
-                                                                                   scale, rows_per_image, act_fp16, (bf16*)out);
+  const int64_t total = (int64_t)n * h * w * (cout / 8);
+  const size_t shm = (size_t)9 * cin * cout * sizeof(float);
+  CPD_REQUIRE(shm <= 48 * 1024, "cpd_conv_in: cin=%d x cout=%d weights do not fit 48 KB of shared memory", cin, cout);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  conv_in_kernel<<<(unsigned)blocks, 256, shm, (cudaStream_t)stream>>>(x, n, cin, h, w, (const bf16*)wt, bias, cout, scale, scale_ptr,
+                                                                      rows_per_image, act_fp16, (bf16*)out);
   CPD_CUDA_CHECK(cudaGetLastError());
   return CPD_OK;
 }

@@ -68,7 +68,8 @@ class UNetModel:
                     legacy=False)
     GEGLU_BLOCK = 256
 
-    def __init__(self, state_dict=None, device="cuda", act_dtype=torch.float16, eps_dtype=torch.float32, **config):
+    def __init__(self, state_dict=None, device="cuda", act_dtype=torch.float16, eps_dtype=torch.float32, use_cuda_graph=True,
+                 **config):
         cfg = dict(self.DEFAULTS)
         cfg.update({k: v for k, v in config.items() if k in self.DEFAULTS})
         if not cfg["use_spatial_transformer"] or cfg["legacy"]:
@@ -92,6 +93,8 @@ class UNetModel:
         self.inputs, self.middle, self.outputs = _enumerate_blocks(cfg)
         self.w = {}
         self._ws = {}
+        self._graphs = {}
+        self.use_cuda_graph = bool(use_cuda_graph)
         self._ctx = None
         self._ctx_key = None
         self._probe = torch.zeros(1, dtype=self.dtype, device=self.device)
@@ -247,7 +250,8 @@ class UNetModel:
         ctx = context.to(self.device, torch.bfloat16).to(self.act_dtype)
         rc, ntok, D = ctx.shape
         nk_pad = (ntok + 15) // 16 * 16
-        ctx_pad = torch.zeros(rc, nk_pad, D, dtype=self.act_dtype, device=self.device)
+        ctx_pad = self._buf("ctx_pad", rc * nk_pad * D).view(rc, nk_pad, D)
+        ctx_pad.zero_()
         ctx_pad[:, :ntok] = ctx
         kv = {}
         for prefix, layers in self._all_blocks():
@@ -257,8 +261,9 @@ class UNetModel:
                 b = f"{prefix}{j}.transformer_blocks.0."
                 wk, wv = self.w[b + "attn2.k.w"], self.w[b + "attn2.v.w"]
                 ip = wk.shape[0]
-                kc = torch.empty(rc * nk_pad, ip, dtype=self.act_dtype, device=self.device)
-                vt = torch.empty(ip, rc * nk_pad, dtype=self.act_dtype, device=self.device)
+                # persistent buffers (stable addresses: captured CUDA graphs stay valid across prompts)
+                kc = self._buf(b + "kc", rc * nk_pad * ip).view(rc * nk_pad, ip)
+                vt = self._buf(b + "vt", ip * rc * nk_pad).view(ip, rc * nk_pad)
                 ops.gemm_conv(ctx_pad, wk, kc, n_img=1, h=1, w=rc * nk_pad, c0=D, n_out=ip)
                 ops.gemm_conv(wv, ctx_pad, vt, n_img=1, h=1, w=ip, c0=D, n_out=rc * nk_pad)
                 kv[b] = (kc, vt)
@@ -317,7 +322,7 @@ class UNetModel:
         ops.gemm_conv(W[b + "attn1.v.w"], ln, vt, n_img=1, h=1, w=ip, c0=ch, n_out=T)
         o = self._buf("tr.o", T * ip)
         ops.attention(qk, qk[ip:], vt, o, ldq=2 * ip, ldk=2 * ip, ldvt=T, ldo=ip, batch=R, heads=nh, nq=hw, nk=hw, nk_pad=hw,
-                      dpad=dpad, scale=scale)
+                      dpad=dpad, scale=scale, d_head=dh)
         ops.gemm_conv(o, W[b + "attn1.out.w"], hcur, n_img=1, h=1, w=T, c0=ip, n_out=ch, bias=W[b + "attn1.out.b"],
                       residual=hcur, ld_res=ch)
         # --- cross-attention (K / V^T cached per prompt)
@@ -329,7 +334,7 @@ class UNetModel:
         q2 = self._buf("tr.q2", T * ip)
         ops.gemm_conv(ln, W[b + "attn2.q.w"], q2, n_img=1, h=1, w=T, c0=ch, n_out=ip)
         ops.attention(q2, kc, vtc, o, ldq=ip, ldk=ip, ldvt=ctx["rc"] * ctx["nk_pad"], ldo=ip, batch=R, heads=nh, nq=hw,
-                      nk=ctx["ntok"], nk_pad=ctx["nk_pad"], dpad=dpad, scale=scale, kv_batch=ctx["rc"])
+                      nk=ctx["ntok"], nk_pad=ctx["nk_pad"], dpad=dpad, scale=scale, kv_batch=ctx["rc"], d_head=dh)
         ops.gemm_conv(o, W[b + "attn2.out.w"], hcur, n_img=1, h=1, w=T, c0=ip, n_out=ch, bias=W[b + "attn2.out.b"],
                       residual=hcur, ld_res=ch)
         # --- GEGLU feed-forward
@@ -390,7 +395,7 @@ class UNetModel:
         ops.small_linear(emb, W["emb_all.w"], W["emb_all.b"], m=m, k=ted, n=self.emb_total, silu_in=True, out_f32=emb_all)
         return emb_all
 
-    def _forward_impl(self, x, scale, rows_per_image, t_rows, shared_t, return_skips=False):
+    def _forward_impl(self, x, scale, rows_per_image, t_rows, shared_t, return_skips=False, scale_dev=None):
         W = self.w
         B, cin, h, w = x.shape
         R = B * rows_per_image
@@ -400,7 +405,7 @@ class UNetModel:
         mc = self.model_channels
         h0 = self._buf("input_blocks.0.out", R * h * w * mc)
         ops.conv_in(x, W["input_blocks.0.0.w"], W["input_blocks.0.0.b"], h0, n=B, cin=cin, h=h, w=w, cout=mc, scale=scale,
-                    rows_per_image=rows_per_image)
+                    rows_per_image=rows_per_image, scale_dev=scale_dev)
         hs = [(h0, mc, h, w)]
         hcur, ch = h0, mc
         for i, layers in enumerate(self.inputs[1:], start=1):
@@ -426,8 +431,34 @@ class UNetModel:
         """Fast path used by the Denoiser: x [B,4,h,w] fp32 (unscaled), every image is evaluated on
         `rows_per_image` conditioning rows sharing x * c_in and the timestep t (denoiser.py:383-393).
         Returns eps rows [B*rows_per_image, 4, h, w] (eps_dtype), image-major."""
-        t_rows = torch.full((1,), float(t), dtype=torch.float32, device=self.device)
-        return self._forward_impl(x.contiguous(), float(c_in), rows_per_image, t_rows, shared_t=True)
+        if not self.use_cuda_graph or ops.PROFILE is not None:
+            t_rows = torch.full((1,), float(t), dtype=torch.float32, device=self.device)
+            return self._forward_impl(x.contiguous(), float(c_in), rows_per_image, t_rows, shared_t=True)
+        # One CUDA graph per (shape, rows, context layout): the ~850 kernel launches of an evaluation are replayed with a
+        # single cudaGraphLaunch; the per-step scalars (c_in, t) and x live in static device buffers.
+        ctx = self._ctx
+        key = (tuple(x.shape), rows_per_image, None if ctx is None else (ctx["rc"], ctx["ntok"]))
+        g = self._graphs.get(key)
+        if g is None:
+            st = dict(x=torch.empty(tuple(x.shape), dtype=torch.float32, device=self.device),
+                      sc=torch.empty(2, dtype=torch.float32, device=self.device))  # [c_in, t]
+            st["x"].copy_(x)
+            st["sc"].copy_(torch.tensor([float(c_in), float(t)], dtype=torch.float32))
+            # eager warm-up: allocates every workspace buffer and configures the kernels outside the capture
+            self._forward_impl(st["x"], 1.0, rows_per_image, st["sc"][1:2], shared_t=True, scale_dev=st["sc"][0:1])
+            torch.cuda.synchronize(self.device)
+            n0 = ops.LAUNCHES
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self._forward_impl(st["x"], 1.0, rows_per_image, st["sc"][1:2], shared_t=True, scale_dev=st["sc"][0:1])
+            st.update(graph=graph, out=out, launches=ops.LAUNCHES - n0)
+            g = self._graphs[key] = st
+        g["x"].copy_(x, non_blocking=True)
+        g["sc"][0:1].fill_(float(c_in))  # scalars travel by value in the fill kernels' parameters (no host buffer to race on)
+        g["sc"][1:2].fill_(float(t))
+        g["graph"].replay()
+        ops.LAUNCHES += g["launches"]
+        return g["out"]
 
     @torch.no_grad()
     def forward(self, x, timesteps=None, context=None, y=None, **kwargs):

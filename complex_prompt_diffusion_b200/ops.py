@@ -190,13 +190,14 @@ def small_linear(x, w, b, *, m, k, n, silu_in=False, out_f32=None, out_bf16=None
     _count()
 
 
-def conv_in(x, wt, bias, out, *, n, cin, h, w, cout, scale=1.0, rows_per_image=1):
+def conv_in(x, wt, bias, out, *, n, cin, h, w, cout, scale=1.0, rows_per_image=1, scale_dev=None):
     _req(x, torch.float32, "x")
+    _req(scale_dev, torch.float32, "scale_dev")
     _req(wt, torch.bfloat16, "wt")
     _req(bias, torch.float32, "bias")
     f16 = _act(out, "out")
     with _Prof("conv_in", 0.0):
-        check(load().cpd_conv_in(ptr(x), n, cin, h, w, ptr(wt), ptr(bias), cout, float(scale), int(rows_per_image), f16, ptr(out),
+        check(load().cpd_conv_in(ptr(x), n, cin, h, w, ptr(wt), ptr(bias), cout, float(scale), ptr(scale_dev), int(rows_per_image), f16, ptr(out),
                                  stream_ptr()), "cpd_conv_in")
     _count()
     return out
@@ -224,14 +225,14 @@ def upsample2x(a, out, *, n, h, w, c):
     return out
 
 
-def attention(q, k, vt, o, *, ldq, ldk, ldvt, ldo, batch, heads, nq, nk, nk_pad, dpad, scale, kv_batch=0):
+def attention(q, k, vt, o, *, ldq, ldk, ldvt, ldo, batch, heads, nq, nk, nk_pad, dpad, scale, kv_batch=0, d_head=0):
     f16 = _act(q, "q")
     for t, nme in ((k, "k"), (vt, "vt"), (o, "o")):
         _act(t, nme, like=q.dtype)
     p = AttnParams()
     p.q, p.ldq, p.k, p.ldk, p.vt, p.ldvt, p.o, p.ldo = q.data_ptr(), ldq, k.data_ptr(), ldk, vt.data_ptr(), ldvt, o.data_ptr(), ldo
     p.batch, p.heads, p.nq, p.nk, p.nk_pad, p.dpad, p.scale = batch, heads, nq, nk, nk_pad, dpad, float(scale)
-    p.kv_batch, p.act_fp16 = kv_batch, f16
+    p.kv_batch, p.act_fp16, p.d_head = kv_batch, f16, d_head
     with _Prof("attention", 4.0 * batch * heads * nq * nk * dpad, f"B={batch} H={heads} nq={nq} nk={nk} d={dpad}"):
         check(load().cpd_attention(C.byref(p), stream_ptr()), "cpd_attention")
     _count()

@@ -159,9 +159,10 @@ cpd_status cpd_small_linear(const void* x, int m, int k, const void* w, const fl
 /* Input conv 3x3 (unet.py:548) fused with the Denoiser's input scaling and row broadcast (denoiser.py:390-391):
  * x fp32 NCHW [n][cin][h][w]; every image is multiplied by `scale` (c_in, fp32), cast to bf16 (unet.py:794) and
  * convolved; the result is written `rows_per_image` times (one copy per conditioning row), image-major:
- * out bf16 NHWC [n * rows_per_image][h][w][cout]; w bf16 [cout][3][3][cin]; cin <= 8. */
+ * out bf16 NHWC [n * rows_per_image][h][w][cout]; w bf16 [cout][3][3][cin]; cin <= 8.
+ * scale_ptr: optional DEVICE pointer to the scale (overrides `scale`), so a captured CUDA graph replays with a new c_in. */
 cpd_status cpd_conv_in(const float* x, int n, int cin, int h, int w, const void* wt, const float* bias, int cout,
-                       float scale, int rows_per_image, int act_fp16, void* out, void* stream);
+                       float scale, const float* scale_ptr, int rows_per_image, int act_fp16, void* out, void* stream);
 
 /* Output conv 3x3 (unet.py:729-733): a bf16 NHWC [n][h][w][cin] (already GroupNorm+SiLU) -> out NCHW
  * [n][cout][h][w] in out_dtype (CPD_BF16 or CPD_F32); cout <= 8. */
@@ -189,6 +190,8 @@ typedef struct {
   float scale; /* dim_head ** -0.5 */
   int kv_batch; /* number of distinct K/V batches: query batch b reads K/V batch (b % kv_batch); 0 = batch */
   int act_fp16; /* q, k, vt, o element type: 1 = fp16, 0 = bf16 */
+  int d_head;   /* real head dim (<= dpad); > 0 enables the two-query-tile kernel (attention_umma2.cu) for nq > 128 and
+                   d_head <= 111, which loads only d_head rows of V^T per head; 0 = one-tile kernel */
 } cpd_attn_params;
 
 cpd_status cpd_attention(const cpd_attn_params* p, void* stream);

@@ -143,8 +143,12 @@ def test_conv1x1_two_sources(ops):
 
 # ------------------------------------------------------------------------------------------------ attention
 @pytest.mark.parametrize("B,H,Nq,Nk,d", [(2, 8, 256, 256, 40), (1, 4, 1024, 1024, 80), (2, 2, 64, 64, 160), (3, 8, 256, 77, 40),
-                                         (2, 5, 576, 576, 64), (1, 2, 64, 64, 32), (4, 8, 4096, 77, 40), (1, 8, 4096, 4096, 40)])
-def test_attention(ops, B, H, Nq, Nk, d):
+                                         (2, 5, 576, 576, 64), (1, 2, 64, 64, 32), (4, 8, 4096, 77, 40), (1, 8, 4096, 4096, 40),
+                                         (2, 3, 320, 200, 40), (1, 2, 256, 1000, 96)])
+@pytest.mark.parametrize("two_tile", [False, True])
+def test_attention(ops, B, H, Nq, Nk, d, two_tile):
+    """two_tile=True passes d_head, which selects the two-query-tile kernel with P in tensor memory (attention_umma2.cu)
+    whenever nq > 128 and d_head <= 111; other shapes fall through to the one-tile kernel."""
     g = torch.Generator().manual_seed(B * Nq + d)
     dpad = (d + 15) // 16 * 16
     nk_pad = Nk if Nk % 16 == 0 else (Nk + 15) // 16 * 16
@@ -157,13 +161,13 @@ def test_attention(ops, B, H, Nq, Nk, d):
     vt = vp.permute(2, 3, 0, 1).reshape(H * dpad, B * nk_pad).contiguous().to(DEV)
     o = torch.full((B, Nq, H, dpad), float("nan"), dtype=torch.bfloat16, device=DEV)
     ops.attention(qp.to(DEV), kp.to(DEV), vt, o, ldq=H * dpad, ldk=H * dpad, ldvt=B * nk_pad, ldo=H * dpad, batch=B, heads=H,
-                  nq=Nq, nk=Nk, nk_pad=nk_pad, dpad=dpad, scale=d ** -0.5)
+                  nq=Nq, nk=Nk, nk_pad=nk_pad, dpad=dpad, scale=d ** -0.5, d_head=d if two_tile else 0)
     torch.cuda.synchronize()
     qf, kf, vf = (t.float().to(DEV).permute(0, 2, 1, 3) for t in (q, k, v))
     ref = torch.softmax(qf @ kf.transpose(-1, -2) * d ** -0.5, dim=-1) @ vf  # [B,H,Nq,d]
     got = o[..., :d].permute(0, 2, 1, 3)
     r = rel(got, ref)
-    print(f"attention B{B} H{H} {Nq}x{Nk} d{d}: rel {r:.3e}")
+    print(f"attention B{B} H{H} {Nq}x{Nk} d{d} two_tile={two_tile}: rel {r:.3e}")
     assert torch.isfinite(o.float()).all()
     assert r < 1e-2
     if dpad != d:

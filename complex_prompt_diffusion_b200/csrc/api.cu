@@ -1,5 +1,6 @@
 // Error plumbing, ABI version and the host-side TMA tensor-map encoder.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/cpd_b200.h"
@@ -15,6 +16,15 @@ void cpd_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* cpd_last_error(void) { return g_err; }
+
+bool cpd_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("CPD_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
 extern "C" int cpd_abi_version(void) { return 1; }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

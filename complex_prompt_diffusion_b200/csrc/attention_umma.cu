@@ -79,10 +79,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) attention_kernel(const __grid_
     tmem_alloc(tmem_ptr_smem, tmem_cols);
     tmem_relinquish();
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
   const uint32_t tmem_S = tmem_base;
   const uint32_t tmem_O = tmem_base + 128;
 
@@ -313,7 +315,7 @@ extern "C" cpd_status cpd_attention(const cpd_attn_params* p, void* stream) {
     configured = 227 * 1024;
   }
   dim3 grid((p->nq + BQ - 1) / BQ, p->heads, p->batch);
-  attention_kernel<<<grid, NUM_THREADS, shm, (cudaStream_t)stream>>>(a);
+  CPD_CUDA_CHECK(cpd_launch(attention_kernel, dim3(grid), dim3(NUM_THREADS), shm, (cudaStream_t)stream, a));
   CPD_CUDA_CHECK(cudaGetLastError());
   return CPD_OK;
 }

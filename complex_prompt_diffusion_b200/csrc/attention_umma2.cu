@@ -129,10 +129,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention2_kernel(const __grid
     }
     fence_proxy_async_smem();
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -395,7 +397,7 @@ cpd_status cpd_attention_2tile(const cpd_attn_params* p, void* stream) {
     configured = true;
   }
   dim3 grid((p->nq + 2 * BQ - 1) / (2 * BQ), p->heads, p->batch);
-  attention2_kernel<<<grid, NUM_THREADS, shm, (cudaStream_t)stream>>>(a);
+  CPD_CUDA_CHECK(cpd_launch(attention2_kernel, dim3(grid), dim3(NUM_THREADS), shm, (cudaStream_t)stream, a));
   CPD_CUDA_CHECK(cudaGetLastError());
   return CPD_OK;
 }

@@ -38,6 +38,27 @@ void cpd_set_error(const char* fmt, ...);
     }                                             \
   } while (0)
 
+// Every kernel is launched with programmatic stream serialization (PDL): it may start while its predecessor in the
+// stream is still draining, runs its data-independent prologue (barrier init, TMEM allocation, tensor-map prefetch,
+// weight staging) and blocks in pdl_wait() until the predecessor has completed and flushed.  CPD_PDL=0 disables it.
+bool cpd_pdl_enabled();
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t cpd_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = cpd_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // Encode a tiled bf16 tensor map (rank <= 5) with 128B swizzle; dims/strides innermost first,
 // strides in BYTES for dims 1..rank-1.  Returns CPD_OK or an error code.
 int cpd_make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
@@ -50,6 +71,10 @@ int cpd_make_tmap16(CUtensorMap* map, const void* base, int rank, const uint64_t
 // device helpers
 // ----------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+// PDL: let the next kernel in the stream begin launching / wait for the previous kernel's completion + memory flush
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -345,7 +370,34 @@ __device__ __forceinline__ float fast_ex2(float x) {  // MUFU.EX2, no range fix-
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// Exact-erf GELU (attention.py:98-100 uses F.gelu, the erf form) with erf from Abramowitz & Stegun 7.1.26
+// (|error| <= 1.5e-7, far below 16-bit output rounding): 2 MUFU (rcp, ex2) + ~10 FMA-pipe instructions.
+__device__ __forceinline__ float gelu_fast_f(float x) {
+  const float z = x * 0.70710678118654752440f;
+  const float az = fabsf(z);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, az, 1.0f)));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float e = fast_ex2(az * az * -1.4426950408889634f);
+  const float erf_abs = fmaf(-p, e, 1.0f);
+  const float erf_z = copysignf(erf_abs, z);
+  const float hx = 0.5f * x;
+  return fmaf(hx, erf_z, hx);
+}
+// (a0 * b0, a1 * b1) of two packed 16-bit pairs, rounded once to the activation format (one HMUL2)
+__device__ __forceinline__ uint32_t mul_act2(uint32_t a, uint32_t b, bool f16) {
+  if (f16) {
+    __half2 r = __hmul2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+  __nv_bfloat162 r = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
 
 #endif  // __CUDACC__

@@ -68,10 +68,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_conv_kernel(const __grid_
     tmem_alloc(tmem_ptr_smem, BN);
     tmem_relinquish();
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -231,7 +233,7 @@ cpd_status launch(const GemmArgs& args, int m_tiles, int n_tiles, cudaStream_t s
     CPD_CUDA_CHECK(cudaFuncSetAttribute(gemm_conv_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
-  gemm_conv_kernel<BN, STAGES><<<dim3(m_tiles, n_tiles), NUM_THREADS, L::TOTAL, s>>>(args);
+  CPD_CUDA_CHECK(cpd_launch(gemm_conv_kernel<BN, STAGES>, dim3(dim3(m_tiles, n_tiles)), dim3(NUM_THREADS), L::TOTAL, s, args));
   CPD_CUDA_CHECK(cudaGetLastError());
   return CPD_OK;
 }

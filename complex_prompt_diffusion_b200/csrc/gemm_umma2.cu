@@ -75,6 +75,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
   const int num_k = args.num_k;
   const int cbt = g.cb0 + g.cb1;
 
+  pdl_launch_dependents();
   cluster_sync_all();  // both CTAs of the pair are resident before the pair-wide TMEM allocation
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&args.map_a0);
@@ -103,6 +104,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     // ================= TMA producer (both CTAs) =================
@@ -282,24 +284,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
         }
         const int col0 = n_tile * out_w + ch * CHUNK_COLS;  // first output column of this chunk
         float f[32];
+        uint32_t packed[16];  // GEGLU produces packed 16-bit pairs directly
         if (geglu) {
-          // tile columns [0, bn/2) = value, [bn/2, bn) = gate
+          // tile columns [0, bn/2) = value, [bn/2, bn) = gate.  The reference rounds the projection to the model dtype,
+          // applies gelu (rounded), then multiplies in the model dtype (attention.py:98-100): value and gelu(gate) are
+          // packed to 16 bit and multiplied with one HMUL2 per pair.
           uint32_t va[32], vg[32];
           tmem_ld32(taddr + ch * CHUNK_COLS, va);
           tmem_ld32(taddr + (bn >> 1) + ch * CHUNK_COLS, vg);
           tmem_ld_wait();
           const float* bias_v = args.bias ? args.bias + n_tile * bn + ch * CHUNK_COLS : nullptr;
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            float a0 = __uint_as_float(va[e]), g0 = __uint_as_float(vg[e]);
+          for (int e = 0; e < 32; e += 4) {
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bg = bv;
             if (bias_v) {
-              a0 += __ldg(bias_v + e);
-              g0 += __ldg(bias_v + (bn >> 1) + e);
+              bv = __ldg(reinterpret_cast<const float4*>(bias_v + e));
+              bg = __ldg(reinterpret_cast<const float4*>(bias_v + (bn >> 1) + e));
             }
-            // the reference rounds the projection to the model dtype before x * gelu(gate) (attention.py:98-100)
-            a0 = round_act(a0, of16);
-            g0 = round_act(gelu_erf_f(round_act(g0, of16)), of16);
-            f[e] = a0 * g0;
+            const uint32_t a01 = pack_act2(__uint_as_float(va[e]) + bv.x, __uint_as_float(va[e + 1]) + bv.y, of16);
+            const uint32_t a23 = pack_act2(__uint_as_float(va[e + 2]) + bv.z, __uint_as_float(va[e + 3]) + bv.w, of16);
+            const float2 g01 = unpack_act2(pack_act2(__uint_as_float(vg[e]) + bg.x, __uint_as_float(vg[e + 1]) + bg.y, of16), of16);
+            const float2 g23 = unpack_act2(pack_act2(__uint_as_float(vg[e + 2]) + bg.z, __uint_as_float(vg[e + 3]) + bg.w, of16), of16);
+            packed[e >> 1] = mul_act2(a01, pack_act2(gelu_fast_f(g01.x), gelu_fast_f(g01.y), of16), of16);
+            packed[(e >> 1) + 1] = mul_act2(a23, pack_act2(gelu_fast_f(g23.x), gelu_fast_f(g23.y), of16), of16);
           }
         } else {
           uint32_t v[32];
@@ -332,7 +339,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
             }
           }
         }
-        if (has_res) {
+        if (has_res && !geglu) {
           mbar_wait(&my_res_bar[buf], (uint32_t)((kc / STAGING_BUFS) & 1), 5);
 #pragma unroll
           for (int c16 = 0; c16 < 4; ++c16) {
@@ -343,12 +350,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
             f[c16 * 8 + 4] += r2.x; f[c16 * 8 + 5] += r2.y; f[c16 * 8 + 6] += r3.x; f[c16 * 8 + 7] += r3.y;
           }
         }
+        if (!geglu) {
 #pragma unroll
-        for (int c16 = 0; c16 < 4; ++c16) {
-          *reinterpret_cast<uint4*>(my_row + ((c16 ^ sw) << 4)) =
-              make_uint4(pack_act2(f[c16 * 8 + 0], f[c16 * 8 + 1], of16), pack_act2(f[c16 * 8 + 2], f[c16 * 8 + 3], of16),
-                         pack_act2(f[c16 * 8 + 4], f[c16 * 8 + 5], of16), pack_act2(f[c16 * 8 + 6], f[c16 * 8 + 7], of16));
+          for (int c16 = 0; c16 < 4; ++c16) {
+            packed[c16 * 4 + 0] = pack_act2(f[c16 * 8 + 0], f[c16 * 8 + 1], of16);
+            packed[c16 * 4 + 1] = pack_act2(f[c16 * 8 + 2], f[c16 * 8 + 3], of16);
+            packed[c16 * 4 + 2] = pack_act2(f[c16 * 8 + 4], f[c16 * 8 + 5], of16);
+            packed[c16 * 4 + 3] = pack_act2(f[c16 * 8 + 6], f[c16 * 8 + 7], of16);
+          }
         }
+#pragma unroll
+        for (int c16 = 0; c16 < 4; ++c16)
+          *reinterpret_cast<uint4*>(my_row + ((c16 ^ sw) << 4)) =
+              make_uint4(packed[c16 * 4], packed[c16 * 4 + 1], packed[c16 * 4 + 2], packed[c16 * 4 + 3]);
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
         if (ch + 1 == c_hi) {
           // last TMEM read of this tile by this warp: hand the accumulator back to the MMA warp
@@ -421,6 +435,7 @@ cpd_status cpd_gemm_conv_2cta(const cpd_gemm_params* p, void* stream) {
   args.m_tiles2 = (m_tiles_cta + 1) / 2;
   int bn = (p->variant >= 32) ? p->variant : pick_bn(args.m_tiles2, p->n_out, geglu);
   if (geglu) bn = p->geglu_block ? p->geglu_block : 128;  // fixed by the weight interleave
+  CPD_REQUIRE(!(geglu && p->residual), "cpd_gemm_conv: the GEGLU epilogue takes no residual");
   CPD_REQUIRE(bn % 32 == 0 && bn >= 32 && bn <= 256, "cpd_gemm_conv: tile width %d must be a multiple of 32 in [32, 256]", bn);
   if (geglu) {
     CPD_REQUIRE((bn == 128 || bn == 256) && p->n_out % bn == 0,
@@ -467,7 +482,7 @@ cpd_status cpd_gemm_conv_2cta(const cpd_gemm_params* p, void* stream) {
   }
   const long total_tiles = (long)args.m_tiles2 * args.n_tiles;
   const int clusters = (int)(total_tiles < NUM_SM_PAIRS ? total_tiles : NUM_SM_PAIRS);
-  gemm2_kernel<<<dim3(2 * clusters), NUM_THREADS2, smem_bytes, (cudaStream_t)stream>>>(args);
+  CPD_CUDA_CHECK(cpd_launch(gemm2_kernel, dim3(dim3(2 * clusters)), dim3(NUM_THREADS2), smem_bytes, (cudaStream_t)stream, args));
   CPD_CUDA_CHECK(cudaGetLastError());
   return CPD_OK;
 }

@@ -9,9 +9,11 @@ constexpr int GROUPS = 32;
 
 // ---- GroupNorm pass 1: per-(image, group) sum / sum of squares -----------------------------------
 // grid = (chunks, n_img).  Thread t owns channel vector (t % vec_per_px) and pixel lane (t / vec_per_px).
-__global__ void __launch_bounds__(512) gn_stats_kernel(const bf16* __restrict__ a0, const bf16* __restrict__ a1, int c0,
+__global__ void __launch_bounds__(512, 2) gn_stats_kernel(const bf16* __restrict__ a0, const bf16* __restrict__ a1, int c0,
                                                        int c1, int hw, int px_per_block, int f16, double* __restrict__ stats) {
   extern __shared__ float sh[];  // [2][C]
+  pdl_launch_dependents();
+  pdl_wait();
   const int C = c0 + c1;
   const int vec_per_px = C / 8;
   const int lanes = blockDim.x / vec_per_px;
@@ -32,12 +34,12 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const bf16* __restrict__ 
     const int p1 = min(p0 + px_per_block, hw);
     const bf16* base = src + (int64_t)n * hw * cs + coff;
     int p = p0 + pl;
-    for (; p + 3 * lanes < p1; p += 4 * lanes) {  // 4 independent 16-byte loads in flight per thread
-      uint4 v[4];
+    for (; p + 7 * lanes < p1; p += 8 * lanes) {  // 8 independent 16-byte loads in flight per thread
+      uint4 v[8];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)(p + j * lanes) * cs));
+      for (int j = 0; j < 8; ++j) v[j] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)(p + j * lanes) * cs));
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 8; ++j) {
         const uint32_t u[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -77,11 +79,13 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const bf16* __restrict__ 
 }
 
 // ---- GroupNorm pass 2: normalise, affine, optional SiLU, write bf16 ---------------------------------
-__global__ void __launch_bounds__(512) gn_apply_kernel(const bf16* __restrict__ a0, const bf16* __restrict__ a1, int c0,
+__global__ void __launch_bounds__(512, 2) gn_apply_kernel(const bf16* __restrict__ a0, const bf16* __restrict__ a1, int c0,
                                                        int c1, int hw, int px_per_block, const double* __restrict__ stats,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        float eps, int silu, int f16, bf16* __restrict__ out) {
   extern __shared__ float sh[];  // scale[C], shift[C]
+  pdl_launch_dependents();
+  pdl_wait();
   const int C = c0 + c1;
   const int vec_per_px = C / 8;
   const int lanes = blockDim.x / vec_per_px;
@@ -129,21 +133,23 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(const bf16* __restrict__ 
     *reinterpret_cast<uint4*>(obase + (int64_t)p * C) = make_uint4(o[0], o[1], o[2], o[3]);
   };
   int p = p0 + pl;
-  for (; p + 3 * lanes < p1; p += 4 * lanes) {  // 4 independent 16-byte loads in flight per thread
-    uint4 v[4];
+  for (; p + 7 * lanes < p1; p += 8 * lanes) {  // 8 independent 16-byte loads in flight per thread
+    uint4 v[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)(p + j * lanes) * cs));
+    for (int j = 0; j < 8; ++j) v[j] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)(p + j * lanes) * cs));
 #pragma unroll
-    for (int j = 0; j < 4; ++j) apply_one(v[j], p + j * lanes);
+    for (int j = 0; j < 8; ++j) apply_one(v[j], p + j * lanes);
   }
   for (; p < p1; p += lanes) apply_one(__ldg(reinterpret_cast<const uint4*>(base + (int64_t)p * cs)), p);
 }
 
 // ---- LayerNorm: one warp per R rows (all loads of the R rows issued before the first use), rows in registers -----
 template <int MAXV, int R>  // max 16-byte vectors per lane, rows per warp
-__global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, int rows, int c,
+__global__ void __launch_bounds__(256, 4) layernorm_kernel(const bf16* __restrict__ x, int rows, int c,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, int f16, bf16* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int row0 = warp * R;
@@ -222,21 +228,22 @@ extern "C" cpd_status cpd_groupnorm(const void* a0, const void* a1, int c0, int 
   cudaStream_t s = (cudaStream_t)stream;
   CPD_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * GROUPS * n_img, s));
   const int vec_per_px = C / 8;
-  int lanes = 512 / vec_per_px;
+  // <= 256 threads per block (4 blocks per SM at <= 64 registers), 8 x 16-byte loads in flight per thread
+  int lanes = 256 / vec_per_px;
   if (lanes < 1) lanes = 1;
   if (lanes > hw) lanes = hw;
   const int threads = ((lanes * vec_per_px + 31) / 32) * 32;
   CPD_REQUIRE(threads <= 512, "cpd_groupnorm: C=%d too large", C);
-  // enough blocks to fill the machine: target ~4 blocks per SM over all images
+  // one wave of ~4 blocks per SM over all images, but at least 8 pixels per pixel lane
   int chunks = (148 * 4 + n_img - 1) / n_img;
   int px_per_block = (hw + chunks - 1) / chunks;
-  if (px_per_block < lanes) px_per_block = lanes;
+  if (px_per_block < 8 * lanes) px_per_block = 8 * lanes;
   chunks = (hw + px_per_block - 1) / px_per_block;
   const size_t shm = sizeof(float) * 2 * C;
-  gn_stats_kernel<<<dim3(chunks, n_img), threads, shm, s>>>((const bf16*)a0, (const bf16*)a1, c0, c1, hw, px_per_block, act_fp16, stats);
+  CPD_CUDA_CHECK(cpd_launch(gn_stats_kernel, dim3(dim3(chunks, n_img)), dim3(threads), shm, s, (const bf16*)a0, (const bf16*)a1, c0, c1, hw, px_per_block, act_fp16, stats));
   CPD_CUDA_CHECK(cudaGetLastError());
-  gn_apply_kernel<<<dim3(chunks, n_img), threads, shm, s>>>((const bf16*)a0, (const bf16*)a1, c0, c1, hw, px_per_block, stats,
-                                                           gamma, beta, eps, silu, act_fp16, (bf16*)out);
+  CPD_CUDA_CHECK(cpd_launch(gn_apply_kernel, dim3(dim3(chunks, n_img)), dim3(threads), shm, s, (const bf16*)a0, (const bf16*)a1, c0, c1, hw, px_per_block, stats,
+                                                           gamma, beta, eps, silu, act_fp16, (bf16*)out));
   CPD_CUDA_CHECK(cudaGetLastError());
   return CPD_OK;
 }
@@ -250,9 +257,9 @@ extern "C" cpd_status cpd_layernorm(const void* x, int rows, int c, const float*
   cudaStream_t s = (cudaStream_t)stream;
   const int nvec = c / 8;
   auto blocks = [&](int r_per_warp) { return (rows + 8 * r_per_warp - 1) / (8 * r_per_warp); };
-  if (nvec <= 64) layernorm_kernel<2, 4><<<blocks(4), 256, 0, s>>>((const bf16*)x, rows, c, gamma, beta, eps, act_fp16, (bf16*)out);
-  else if (nvec <= 160) layernorm_kernel<5, 2><<<blocks(2), 256, 0, s>>>((const bf16*)x, rows, c, gamma, beta, eps, act_fp16, (bf16*)out);
-  else layernorm_kernel<8, 1><<<blocks(1), 256, 0, s>>>((const bf16*)x, rows, c, gamma, beta, eps, act_fp16, (bf16*)out);
+  if (nvec <= 64) CPD_CUDA_CHECK(cpd_launch(layernorm_kernel<2, 4>, dim3(blocks(4)), dim3(256), 0, s, (const bf16*)x, rows, c, gamma, beta, eps, act_fp16, (bf16*)out));
+  else if (nvec <= 160) CPD_CUDA_CHECK(cpd_launch(layernorm_kernel<5, 2>, dim3(blocks(2)), dim3(256), 0, s, (const bf16*)x, rows, c, gamma, beta, eps, act_fp16, (bf16*)out));
+  else CPD_CUDA_CHECK(cpd_launch(layernorm_kernel<8, 1>, dim3(blocks(1)), dim3(256), 0, s, (const bf16*)x, rows, c, gamma, beta, eps, act_fp16, (bf16*)out));
   CPD_CUDA_CHECK(cudaGetLastError());
   return CPD_OK;
 }

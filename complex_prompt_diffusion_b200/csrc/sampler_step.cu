@@ -39,6 +39,8 @@ __device__ __forceinline__ void load4(const void* base, int64_t idx, float (&out
 
 template <int DT>
 __global__ void __launch_bounds__(256) sampler_step_kernel(const __grid_constant__ StepArgs args) {
+  pdl_launch_dependents();
+  pdl_wait();
   const cpd_step_params& p = args.p;
   const int L = 4 * p.hw;
   const int vec_per_img = L / 4;
@@ -152,9 +154,9 @@ extern "C" cpd_status cpd_sampler_step(const cpd_step_params* p, void* stream) {
   if (blocks > max_blocks) blocks = max_blocks;
   cudaStream_t s = (cudaStream_t)stream;
   switch (p->eps_dtype) {
-    case CPD_F32: sampler_step_kernel<CPD_F32><<<blocks, 256, 0, s>>>(args); break;
-    case CPD_F16: sampler_step_kernel<CPD_F16><<<blocks, 256, 0, s>>>(args); break;
-    case CPD_BF16: sampler_step_kernel<CPD_BF16><<<blocks, 256, 0, s>>>(args); break;
+    case CPD_F32: CPD_CUDA_CHECK(cpd_launch(sampler_step_kernel<CPD_F32>, dim3(blocks), dim3(256), 0, s, args)); break;
+    case CPD_F16: CPD_CUDA_CHECK(cpd_launch(sampler_step_kernel<CPD_F16>, dim3(blocks), dim3(256), 0, s, args)); break;
+    case CPD_BF16: CPD_CUDA_CHECK(cpd_launch(sampler_step_kernel<CPD_BF16>, dim3(blocks), dim3(256), 0, s, args)); break;
     default: cpd_set_error("cpd_sampler_step: unknown eps_dtype %d", p->eps_dtype); return CPD_ERR_INVALID;
   }
   CPD_CUDA_CHECK(cudaGetLastError());

@@ -8,6 +8,8 @@ namespace {
 
 // models/util.py:65-85: emb = cat[cos(t * f), sin(t * f)], f_k = exp(-ln(10000) * k / half), fp32.
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, int rows, int dim, int round_t, bf16* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int half = dim / 2;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * half) return;
@@ -25,6 +27,8 @@ template <int MT>
 __global__ void __launch_bounds__(256) small_linear_kernel(const bf16* __restrict__ x, int m, int k, const bf16* __restrict__ w,
                                                            const float* __restrict__ b, int n, int silu_in,
                                                            float* __restrict__ out_f32, bf16* __restrict__ out_bf16, int ld_out) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ uint8_t sh_raw[];
   bf16* xs = reinterpret_cast<bf16*>(sh_raw);  // [m][k] (activated)
   for (int i = threadIdx.x; i < m * k; i += blockDim.x) {
@@ -81,6 +85,8 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
                                                       const bf16* __restrict__ wt, const float* __restrict__ bias, int cout,
                                                       float scale, const float* __restrict__ scale_ptr, int rpi, int f16,
                                                       bf16* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ uint8_t sh_raw[];
   float* ws = reinterpret_cast<float*>(sh_raw);  // [9 * cin][cout]
   const int taps = 9 * cin;
@@ -131,6 +137,8 @@ template <int COUT>
 __global__ void __launch_bounds__(256) conv_out_kernel(const bf16* __restrict__ a, int n, int h, int w, int cin,
                                                        const bf16* __restrict__ wt, const float* __restrict__ bias,
                                                        void* __restrict__ out, int out_dtype, int f16) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ uint8_t sh_raw[];
   bf16* ws = reinterpret_cast<bf16*>(sh_raw);  // [COUT][9][cin]
   for (int i = threadIdx.x * 8; i < COUT * 9 * cin; i += blockDim.x * 8)
@@ -183,6 +191,8 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const bf16* __restrict__ 
 }
 
 __global__ void __launch_bounds__(256) upsample2x_kernel(const bf16* __restrict__ a, int n, int h, int w, int c, bf16* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cvecs = c / 8;
   const int64_t total = (int64_t)n * (2 * h) * (2 * w) * cvecs;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -201,7 +211,7 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const bf16* __restrict_
 extern "C" cpd_status cpd_timestep_embedding(const float* t, int rows, int dim, int round_t_bf16, void* out, void* stream) {
   CPD_REQUIRE(t && out && rows > 0 && dim > 0 && dim % 2 == 0, "cpd_timestep_embedding: bad arguments (rows=%d dim=%d)", rows, dim);
   const int total = rows * (dim / 2);
-  timestep_embedding_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(t, rows, dim, round_t_bf16, (bf16*)out);
+  CPD_CUDA_CHECK(cpd_launch(timestep_embedding_kernel, dim3((total + 255) / 256), dim3(256), 0, (cudaStream_t)stream, t, rows, dim, round_t_bf16, (bf16*)out));
   CPD_CUDA_CHECK(cudaGetLastError());
   return CPD_OK;
 }
@@ -222,8 +232,8 @@ extern "C" cpd_status cpd_small_linear(const void* x, int m, int k, const void* 
       CPD_CUDA_CHECK(cudaFuncSetAttribute(small_linear_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); \
       cfg = true;                                                                                                             \
     }                                                                                                                         \
-    small_linear_kernel<MT><<<blocks, 256, shm, s>>>((const bf16*)x, m, k, (const bf16*)w, b, n, silu_in, out_f32,           \
-                                                      (bf16*)out_bf16, ld_out);                                              \
+    CPD_CUDA_CHECK(cpd_launch(small_linear_kernel<MT>, dim3(blocks), dim3(256), shm, s, (const bf16*)x, m, k, (const bf16*)w, b, n, silu_in, out_f32,           \
+                                                      (bf16*)out_bf16, ld_out));                                              \
   } while (0)
   if (m <= 4) LAUNCH_SL(4);
   else if (m <= 16) LAUNCH_SL(16);
@@ -243,8 +253,8 @@ extern "C" cpd_status cpd_conv_in(const float* x, int n, int cin, int h, int w, 
   CPD_REQUIRE(shm <= 48 * 1024, "cpd_conv_in: cin=%d x cout=%d weights do not fit 48 KB of shared memory", cin, cout);
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  conv_in_kernel<<<(unsigned)blocks, 256, shm, (cudaStream_t)stream>>>(x, n, cin, h, w, (const bf16*)wt, bias, cout, scale, scale_ptr,
-                                                                      rows_per_image, act_fp16, (bf16*)out);
+  CPD_CUDA_CHECK(cpd_launch(conv_in_kernel, dim3((unsigned)blocks), dim3(256), shm, (cudaStream_t)stream, x, n, cin, h, w, (const bf16*)wt, bias, cout, scale, scale_ptr,
+                                                                      rows_per_image, act_fp16, (bf16*)out));
   CPD_CUDA_CHECK(cudaGetLastError());
   return CPD_OK;
 }
@@ -262,11 +272,11 @@ extern "C" cpd_status cpd_conv_out(const void* a, int n, int h, int w, int cin, 
   if (cout == 4) {
     static bool cfg = false;
     if (!cfg) { CPD_CUDA_CHECK(cudaFuncSetAttribute(conv_out_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfg = true; }
-    conv_out_kernel<4><<<blocks, 256, shm, s>>>((const bf16*)a, n, h, w, cin, (const bf16*)wt, bias, out, out_dtype, act_fp16);
+    CPD_CUDA_CHECK(cpd_launch(conv_out_kernel<4>, dim3(blocks), dim3(256), shm, s, (const bf16*)a, n, h, w, cin, (const bf16*)wt, bias, out, out_dtype, act_fp16));
   } else {
     static bool cfg = false;
     if (!cfg) { CPD_CUDA_CHECK(cudaFuncSetAttribute(conv_out_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfg = true; }
-    conv_out_kernel<8><<<blocks, 256, shm, s>>>((const bf16*)a, n, h, w, cin, (const bf16*)wt, bias, out, out_dtype, act_fp16);
+    CPD_CUDA_CHECK(cpd_launch(conv_out_kernel<8>, dim3(blocks), dim3(256), shm, s, (const bf16*)a, n, h, w, cin, (const bf16*)wt, bias, out, out_dtype, act_fp16));
   }
   CPD_CUDA_CHECK(cudaGetLastError());
   return CPD_OK;
@@ -277,7 +287,7 @@ extern "C" cpd_status cpd_upsample2x(const void* a, int n, int h, int w, int c, 
   const int64_t total = (int64_t)n * 4 * h * w * (c / 8);
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  upsample2x_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)a, n, h, w, c, (bf16*)out);
+  CPD_CUDA_CHECK(cpd_launch(upsample2x_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (const bf16*)a, n, h, w, c, (bf16*)out));
   CPD_CUDA_CHECK(cudaGetLastError());
   return CPD_OK;
 }

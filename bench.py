@@ -25,6 +25,11 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one gemm2_kernel launch (conv3x3 16x64x64 320->320, ncu --set full,
+# profiles/r01_ncu_full_summaries.txt): 43.8 MB + 2.7 MB; algorithmic bytes of that launch = 42 MB in + 42 MB out + 1.8 MB weights
+# (the output stays in the 126 MB L2 for the next kernel, so the write-back is not seen inside the launch).
+NCU_TRAFFIC = {"bytes_per_launch": 46.6e6, "launch": "conv3x3 M=65536 N=320 K=2880", "source": "profiles/r01_ncu_full_summaries.txt"}
+
 WORKLOAD = dict(workload="SD-1.5 512px (64x64 latent), DPM++ 2M Karras 20 steps, 3 weighted sub-prompts + uncond, batch 4",
                 model="sd15", latent=64, sampler="DPM++ 2m", scheduler="karras", sampler_steps=20, n_sub=3, batch=4,
                 guidance=7.5)
@@ -275,7 +280,8 @@ def run_b200(args):
             {k: [v[0], round(v[1], 2), round(float(k[:-2]) * v[0] / v[1], 1)] for k, v in top}) + "\n")
         achieved = g_fl / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "gemm_conv_kernel (tcgen05 implicit-GEMM conv / GEMM)", "achieved": achieved,
-                "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"], "traffic": None,
+                "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
+                "traffic": NCU_TRAFFIC,
                 "peak_source": pk["source"] + " (sustained bf16)", "launches_per_step": g_n,
                 "avg_launch_us": g_ms * 1e3 / max(g_n, 1), "share_of_step": g_ms / (ms / args.steps),
                 "breakdown_ms_per_step": {k: round(v, 3) for k, v in breakdown.items()},
@@ -295,10 +301,14 @@ def run_b200(args):
                          f"{S} steps x {B} images"}
     if rank == 0:
         line = {"metric": "images_per_s", "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16",
                 "data": "synthetic",
                 "config": dict(WORKLOAD, model=args.model, latent=args.latent, batch=B, sampler_steps=S, parallelism=f"images sharded x{world}",
-                               l2="working set (1.7 GB weights + activations) larger than L2; no flush needed"),
+                               l2="working set (1.7 GB weights + activations) larger than L2; no flush needed",
+                               precision="bf16 model weights converted once to fp16 tensor-core operands, fp16 activations, fp32 "
+                                         "accumulation and norm statistics (same tensor rate as bf16, 3 more mantissa bits: "
+                                         "needed for the <=1e-2 per-step eps tolerance)",
+                               executor="one CUDA graph per UNet evaluation (~850 kernels, PDL edges), replayed per sampler step"),
                 "unet_evals_per_s": evals_per_step * world * args.steps / (ms / 1e3),
                 "e2e": {"value": ips_e2e, "unit": "images/s",
                         "h2d_bytes_per_step": int(x_T_h.numel() * 4 + uc_h.numel() * 4 + sum(e.numel() * 4 for v in c_h.values() for (_, e, _, _) in v)),

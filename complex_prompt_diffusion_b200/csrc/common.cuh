@@ -277,6 +277,16 @@ __device__ __forceinline__ void tma_load_5d_pair(void* dst, const CUtensorMap* m
       "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+// Same, written to this CTA and every CTA of `cta_mask` at the same shared-memory offset (each copy is credited to the
+// leader barrier of the receiving CTA's pair).
+__device__ __forceinline__ void tma_load_5d_pair_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                                    int c4, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, "
+      "%4, %5, %6, %7}], [%2], %8;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "h"(cta_mask)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
                "r"(ncols)

@@ -95,6 +95,9 @@ __device__ __forceinline__ BoxCoord box_coord(const ConvGeom& g, int m_tile, int
 
 // Host: validates p, fills the geometry (everything but idesc / n_store / tile counts) and the A tensor maps.
 int fill_geometry(const cpd_gemm_params* p, ConvGeom* g, CUtensorMap* map_a0, CUtensorMap* map_a1, int* m_tiles_cta);
+// Host: half-box A maps for the multicast kernel (CPD_ERR_UNSUPPORTED when the box cannot be halved).
+int make_a_half_maps(const cpd_gemm_params* p, const ConvGeom& g, CUtensorMap* map_a0h, CUtensorMap* map_a1h, int* half_x,
+                     int* half_y, int* half_n);
 // Host: weights tensor map, box = 64 x box_rows.
 int make_b_map(const cpd_gemm_params* p, int taps, int box_rows, CUtensorMap* map_b);
 

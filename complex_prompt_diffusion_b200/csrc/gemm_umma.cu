@@ -268,6 +268,26 @@ static bool choose_box(int h, int w, int n_img, int* tw, int* th, int* nb) {
   return best > 0;
 }
 
+// NHWC activation view (c, x, parity, y, n) with a box of nb images x th rows x tw columns x 64 channels
+static int make_a_map(const cpd_gemm_params* p, int tw, int th, int nb, const void* base, int csrc, CUtensorMap* m) {
+  uint64_t dims[5], str[4];
+  uint32_t box[5] = {64, (uint32_t)tw, 1, (uint32_t)th, (uint32_t)nb};
+  if (p->stride == 1) {
+    dims[0] = csrc; dims[1] = p->w_in; dims[2] = 1; dims[3] = p->h_in; dims[4] = p->n_img;
+    str[0] = (uint64_t)csrc * 2;
+    str[1] = (uint64_t)p->w_in * csrc * 2;  // parity dim (size 1)
+    str[2] = (uint64_t)p->w_in * csrc * 2;
+    str[3] = (uint64_t)p->h_in * p->w_in * csrc * 2;
+  } else {
+    dims[0] = 2 * (uint64_t)csrc; dims[1] = p->w_in / 2; dims[2] = 2; dims[3] = p->h_in / 2; dims[4] = p->n_img;
+    str[0] = (uint64_t)csrc * 2 * 2;
+    str[1] = (uint64_t)p->w_in * csrc * 2;
+    str[2] = (uint64_t)p->w_in * csrc * 2 * 2;
+    str[3] = (uint64_t)p->h_in * p->w_in * csrc * 2;
+  }
+  return cpd_make_tmap_bf16(m, base, 5, dims, str, box);
+}
+
 int fill_geometry(const cpd_gemm_params* p, ConvGeom* gp, CUtensorMap* map_a0, CUtensorMap* map_a1, int* m_tiles_cta) {
   CPD_REQUIRE(p != nullptr, "cpd_gemm_conv: null params");
   CPD_REQUIRE(p->a0 && p->wt && p->d, "cpd_gemm_conv: a0, wt and d must be non-null");
@@ -324,32 +344,44 @@ int fill_geometry(const cpd_gemm_params* p, ConvGeom* gp, CUtensorMap* map_a0, C
   const int64_t total_boxes = n_groups * g.bx_count * g.by_count;
   *m_tiles_cta = (int)((total_boxes + g.nbox - 1) / g.nbox);
 
-  // A: (c, x, parity, y, n)
-  auto make_a = [&](CUtensorMap* m, const void* base, int csrc) -> int {
-    uint64_t dims[5], str[4];
-    uint32_t box[5] = {64, (uint32_t)g.tw, 1, (uint32_t)g.th, (uint32_t)g.nb};
-    if (p->stride == 1) {
-      dims[0] = csrc; dims[1] = p->w_in; dims[2] = 1; dims[3] = p->h_in; dims[4] = p->n_img;
-      str[0] = (uint64_t)csrc * 2;
-      str[1] = (uint64_t)p->w_in * csrc * 2;  // parity dim (size 1)
-      str[2] = (uint64_t)p->w_in * csrc * 2;
-      str[3] = (uint64_t)p->h_in * p->w_in * csrc * 2;
-    } else {
-      dims[0] = 2 * (uint64_t)csrc; dims[1] = p->w_in / 2; dims[2] = 2; dims[3] = p->h_in / 2; dims[4] = p->n_img;
-      str[0] = (uint64_t)csrc * 2 * 2;
-      str[1] = (uint64_t)p->w_in * csrc * 2;
-      str[2] = (uint64_t)p->w_in * csrc * 2 * 2;
-      str[3] = (uint64_t)p->h_in * p->w_in * csrc * 2;
-    }
-    return cpd_make_tmap_bf16(m, base, 5, dims, str, box);
-  };
-  int rc = make_a(map_a0, p->a0, p->c0);
+  int rc = make_a_map(p, g.tw, g.th, g.nb, p->a0, p->c0, map_a0);
   if (rc) return rc;
   if (p->c1 > 0) {
-    rc = make_a(map_a1, p->a1, p->c1);
+    rc = make_a_map(p, g.tw, g.th, g.nb, p->a1, p->c1, map_a1);
     if (rc) return rc;
   } else {
     *map_a1 = *map_a0;
+  }
+  return CPD_OK;
+}
+
+// Half-box views for the multicast kernel: the box is split in two along its outermost dimension of extent > 1
+// (images, then rows, then columns), so the first half of the box is the first 64 rows of the shared-memory tile.
+int make_a_half_maps(const cpd_gemm_params* p, const ConvGeom& g, CUtensorMap* map_a0h, CUtensorMap* map_a1h, int* half_x,
+                     int* half_y, int* half_n) {
+  if (g.nbox != 1) return CPD_ERR_UNSUPPORTED;
+  int tw = g.tw, th = g.th, nb = g.nb;
+  *half_x = *half_y = *half_n = 0;
+  if (nb > 1 && nb % 2 == 0) {
+    nb /= 2;
+    *half_n = nb;
+  } else if (nb == 1 && th > 1 && th % 2 == 0) {
+    th /= 2;
+    *half_y = th;
+  } else if (nb == 1 && th == 1 && tw % 2 == 0) {
+    tw /= 2;
+    *half_x = tw;
+  } else {
+    return CPD_ERR_UNSUPPORTED;
+  }
+  if ((tw * th * nb) % 8 != 0) return CPD_ERR_UNSUPPORTED;
+  int rc = make_a_map(p, tw, th, nb, p->a0, p->c0, map_a0h);
+  if (rc) return rc;
+  if (p->c1 > 0) {
+    rc = make_a_map(p, tw, th, nb, p->a1, p->c1, map_a1h);
+    if (rc) return rc;
+  } else {
+    *map_a1h = *map_a0h;
   }
   return CPD_OK;
 }

@@ -38,51 +38,68 @@ __device__ __forceinline__ void load4(const void* base, int64_t idx, float (&out
 }
 
 template <int DT>
-__global__ void __launch_bounds__(256) sampler_step_kernel(const __grid_constant__ StepArgs args) {
+__global__ void __launch_bounds__(256, 4) sampler_step_kernel(const __grid_constant__ StepArgs args) {
   pdl_launch_dependents();
   pdl_wait();
   const cpd_step_params& p = args.p;
   const int L = 4 * p.hw;
   const int vec_per_img = L / 4;
   const int64_t total = (int64_t)p.n_images * vec_per_img;
-  // per-sub-prompt fp16 products for scalar masks: half(m) * half(w) (rounded to fp16)
-  float mw_scalar[CPD_MAX_SUBPROMPTS];
-  float w_h[CPD_MAX_SUBPROMPTS];
-#pragma unroll
-  for (int k = 0; k < CPD_MAX_SUBPROMPTS; ++k) {
-    w_h[k] = h_round(p.weights[k]);
-    mw_scalar[k] = h_round(__fmul_rn(h_round(p.mask_scalar[k]), w_h[k]));
-  }
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (int64_t)gridDim.x * blockDim.x) {
     const int b = (int)(v / vec_per_img);
     const int i = (int)(v - (int64_t)b * vec_per_img) * 4;  // element offset inside the image
     const int pix = i % p.hw;
     const int64_t ebase = (int64_t)b * p.eps_image_stride + i;
-    float eu[4], hu[4], sum[4];
+    // Issue every independent load of this vector before the first use (memory-level parallelism: the kernel is a pure
+    // HBM stream): x, the 2M history / ancestral noise, the unconditional row and the sub-prompt rows four at a time.
+    const float4 xv = *reinterpret_cast<const float4*>(p.x + (int64_t)b * L + i);
+    float4 aux = make_float4(0.f, 0.f, 0.f, 0.f);  // old_denoised (2M) or noise (ancestral)
+    if (p.sampler == CPD_DPMPP_2M) {
+      if (!p.dpm_first) aux = *reinterpret_cast<const float4*>(p.old_denoised + (int64_t)b * L + i);
+    } else if (p.sampler == CPD_EULER_ANCESTRAL) {
+      aux = __ldg(reinterpret_cast<const float4*>(p.noise + (int64_t)b * L + i));
+    }
+    float eu[4], hu[4], sum[4] = {0.f, 0.f, 0.f, 0.f};
     load4<DT>(p.eps, ebase, eu);
+    for (int k0 = 0; k0 < p.n_sub; k0 += 4) {
+      float ek4[4][4];
+      float4 m4[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) hu[j] = h_round(eu[j]);
-    for (int k = 0; k < p.n_sub; ++k) {
-      float ek[4];
-      load4<DT>(p.eps, ebase + (int64_t)(k + 1) * p.eps_row_stride, ek);
-      float mw[4];
-      if (p.masks[k] != nullptr) {
-        float4 m = __ldg(reinterpret_cast<const float4*>(p.masks[k] + pix));
-        mw[0] = h_round(__fmul_rn(h_round(m.x), w_h[k]));
-        mw[1] = h_round(__fmul_rn(h_round(m.y), w_h[k]));
-        mw[2] = h_round(__fmul_rn(h_round(m.z), w_h[k]));
-        mw[3] = h_round(__fmul_rn(h_round(m.w), w_h[k]));
-      } else {
-        mw[0] = mw[1] = mw[2] = mw[3] = mw_scalar[k];
+      for (int kk = 0; kk < 4; ++kk) {
+        const int k = k0 + kk;
+        if (k < p.n_sub) {
+          load4<DT>(p.eps, ebase + (int64_t)(k + 1) * p.eps_row_stride, ek4[kk]);
+          if (p.masks[k] != nullptr) m4[kk] = __ldg(reinterpret_cast<const float4*>(p.masks[k] + pix));
+        }
+      }
+      if (k0 == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hu[j] = h_round(eu[j]);
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float d = h_round(__fsub_rn(h_round(ek[j]), hu[j]));
-        float term = h_round(__fmul_rn(mw[j], d));
-        sum[j] = (k == 0) ? term : h_round(__fadd_rn(sum[j], term));
+      for (int kk = 0; kk < 4; ++kk) {
+        const int k = k0 + kk;
+        if (k < p.n_sub) {
+          // half(m) * half(w), rounded to fp16 (denoiser.py:451-452); weights live in the kernel-parameter constant bank
+          const float w_hk = h_round(p.weights[k]);
+          float mw[4];
+          if (p.masks[k] != nullptr) {
+            mw[0] = h_round(__fmul_rn(h_round(m4[kk].x), w_hk));
+            mw[1] = h_round(__fmul_rn(h_round(m4[kk].y), w_hk));
+            mw[2] = h_round(__fmul_rn(h_round(m4[kk].z), w_hk));
+            mw[3] = h_round(__fmul_rn(h_round(m4[kk].w), w_hk));
+          } else {
+            mw[0] = mw[1] = mw[2] = mw[3] = h_round(__fmul_rn(h_round(p.mask_scalar[k]), w_hk));
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float d = h_round(__fsub_rn(h_round(ek4[kk][j]), hu[j]));
+            float term = h_round(__fmul_rn(mw[j], d));
+            sum[j] = (k == 0) ? term : h_round(__fadd_rn(sum[j], term));
+          }
+        }
       }
     }
-    float4 xv = *reinterpret_cast<const float4*>(p.x + (int64_t)b * L + i);
     float x[4] = {xv.x, xv.y, xv.z, xv.w};
     float et[4], den[4], xn[4];
 #pragma unroll
@@ -94,11 +111,7 @@ __global__ void __launch_bounds__(256) sampler_step_kernel(const __grid_constant
       else den[j] = __fadd_rn(__fmul_rn(et[j], p.v_c_eps), __fdiv_rn(x[j], p.v_c_x_div));
     }
     if (p.sampler == CPD_DPMPP_2M) {
-      float od[4] = {0.f, 0.f, 0.f, 0.f};
-      if (!p.dpm_first) {
-        float4 o = *reinterpret_cast<const float4*>(p.old_denoised + (int64_t)b * L + i);
-        od[0] = o.x; od[1] = o.y; od[2] = o.z; od[3] = o.w;
-      }
+      const float od[4] = {aux.x, aux.y, aux.z, aux.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float dd = den[j];
@@ -108,11 +121,7 @@ __global__ void __launch_bounds__(256) sampler_step_kernel(const __grid_constant
       if (p.write_old)
         *reinterpret_cast<float4*>(p.old_denoised + (int64_t)b * L + i) = make_float4(den[0], den[1], den[2], den[3]);
     } else {
-      float nz[4] = {0.f, 0.f, 0.f, 0.f};
-      if (p.sampler == CPD_EULER_ANCESTRAL) {
-        float4 n = __ldg(reinterpret_cast<const float4*>(p.noise + (int64_t)b * L + i));
-        nz[0] = n.x; nz[1] = n.y; nz[2] = n.z; nz[3] = n.w;
-      }
+      const float nz[4] = {aux.x, aux.y, aux.z, aux.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float d = __fdiv_rn(__fsub_rn(x[j], den[j]), p.sigma_hat);
@@ -149,7 +158,7 @@ extern "C" cpd_status cpd_sampler_step(const cpd_step_params* p, void* stream) {
   StepArgs args;
   args.p = *p;
   const int64_t total = (int64_t)p->n_images * p->hw;
-  int blocks = (int)((total + 255) / 256);
+  int blocks = (int)((total + 255) / 256);  // total = number of 4-element vectors
   const int max_blocks = 148 * 8;
   if (blocks > max_blocks) blocks = max_blocks;
   cudaStream_t s = (cudaStream_t)stream;

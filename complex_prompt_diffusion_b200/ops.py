@@ -110,6 +110,40 @@ def sampler_step(eps, x, *, n_sub, weights, mask_scalars, masks, guidance, sampl
     return x
 
 
+AUTOTUNE = True      # time the tile-shape variants of cpd_gemm_conv once per layer shape (first eager call) and keep the best
+_TUNED = {}          # shape key -> variant code
+_TUNE_CANDIDATES = (160, 128, 96, 192, 224, 256, 64, 2160, 2128, 2256, 2096, 2192)
+
+
+def _tune_gemm(key, p, out, residual):
+    """Try every tile-shape variant on this exact problem (output redirected to a scratch tensor so that in-place residual
+    launches stay idempotent), CUDA-event timed; returns the fastest variant code."""
+    lib = load()
+    scratch = torch.empty_like(out)
+    real_d = p.d
+    p.d = scratch.data_ptr()
+    cands = (p.geglu_block,) if p.epilogue == CPD_EPI_GEGLU else _TUNE_CANDIDATES
+    best, best_t = 0, float("inf")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for v in cands:
+        if v % 1000 >= p.n_out + 32 and v % 1000 > 64:  # tile much wider than N: all padding
+            continue
+        p.variant = v
+        if lib.cpd_gemm_conv(C.byref(p), stream_ptr()) != 0:
+            continue  # variant not applicable to this shape
+        e0.record()
+        for _ in range(3):
+            lib.cpd_gemm_conv(C.byref(p), stream_ptr())
+        e1.record()
+        e1.synchronize()
+        t = e0.elapsed_time(e1)
+        if t < best_t:
+            best, best_t = v, t
+    p.d = real_d
+    _TUNED[key] = best
+    return best
+
+
 def gemm_conv(a0, wt, out, *, n_img, h, w, c0, n_out, a1=None, c1=0, ksize=1, stride=1, bias=None, rowvec=None,
               rowvec_stride=0, residual=None, ld_res=0, ldd=None, epilogue=CPD_EPI_NONE, variant=0, m_valid=0, geglu_block=128):
     """a0/a1 and wt are 16-bit (fp16 or bf16, independently); out/residual share one 16-bit dtype."""
@@ -134,6 +168,12 @@ def gemm_conv(a0, wt, out, *, n_img, h, w, c0, n_out, a1=None, c1=0, ksize=1, st
     p.epilogue, p.variant, p.m_valid = epilogue, variant, m_valid
     p.a_fp16, p.b_fp16, p.out_fp16 = a_f16, b_f16, o_f16
     p.geglu_block = geglu_block if epilogue == CPD_EPI_GEGLU else 0
+    if variant == 0 and AUTOTUNE:
+        key = (n_img, h, w, c0, c1, n_out, ksize, stride, epilogue, p.geglu_block, residual is not None, rowvec is not None, a_f16, m_valid)
+        variant = _TUNED.get(key)
+        if variant is None:
+            variant = 0 if torch.cuda.is_current_stream_capturing() else _tune_gemm(key, p, out, residual)
+        p.variant = variant
     flops = 2.0 * n_img * (h // stride) * (w // stride) * n_out * ksize * ksize * (c0 + c1)
     label = f"M={n_img * (h // stride) * (w // stride)} N={n_out} K={ksize * ksize * (c0 + c1)}" + (" geglu" if epilogue else "")
     with _Prof("gemm_conv", flops, label):

@@ -15,6 +15,8 @@ Multi-GPU: images are sharded across ranks (weak scaling: 4 images per GPU), no 
 import argparse
 import json
 import os
+
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the single JSON line (NCCL logs its version / INFO there)
 import subprocess
 import sys
 import threading

@@ -81,8 +81,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention2_kernel(const __grid
   uint64_t* v_empty = v_full + MAX_STAGES;
   uint64_t* s_full = v_empty + MAX_STAGES;   // [2]
   uint64_t* p_full = s_full + 2;             // [2]
-  uint64_t* o_done = p_full + 2;             // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_done + 2);
+  uint64_t* pv_done = p_full + 2;            // [2]  P V_t(j) complete: P_t may be overwritten, O_t may be rescaled / read
+  uint64_t* s_free = pv_done + 2;            // [2]  S_t(j) has been read into registers (separate-P mode)
+  uint64_t* stagger = s_free + 2;            // [1]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(stagger + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * (2 * BQ);
@@ -106,8 +108,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention2_kernel(const __grid
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
       mbar_init(&p_full[t], 128);
-      mbar_init(&o_done[t], 1);
+      mbar_init(&pv_done[t], 1);
+      mbar_init(&s_free[t], 128);
     }
+    mbar_init(stagger, 128);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -135,6 +139,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention2_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_wait();
+  // TMEM columns.  Separate-P mode (dv <= 64, i.e. SD-1.x d = 40): per tile [S 128 | P 64 | O 64]; S(j+1) is issued as
+  // soon as the softmax threads have READ S(j), so the Q K^T round trip never stalls the exp stream.  Aliased mode
+  // (larger head dims): P overwrites S in place, O lives in the upper half; S(j+1) follows P V(j) on the in-order pipe.
+  const bool sep = a.dv <= 64;
+  const uint32_t colS0 = 0, colS1 = sep ? 256u : 128u;
+  const uint32_t offP = sep ? 128u : 0u;                 // P_t relative to S_t
+  const uint32_t colO0 = sep ? 192u : 256u, colO1 = sep ? 448u : 384u;
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -171,9 +182,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention2_kernel(const __grid
     auto issue_s = [&](int t, int st) {  // S_t = Q_t K(st)^T
       if (elect_one()) {
         const uint32_t qa = q_addr + t * q_tile_bytes, ka = k_addr + st * k_stage_bytes;
+        const uint32_t dS = tmem_base + (t ? colS1 : colS0);
         for (int kk = 0; kk < ksteps_s; ++kk) {
           const uint32_t off = (uint32_t)((kk >> 2) * ATOM_BYTES + (kk & 3) * 32);
-          umma_bf16(tmem_base + t * 128, umma_desc_sw128(qa + off), umma_desc_sw128(ka + off), idesc_s, kk > 0 ? 1u : 0u);
+          umma_bf16(dS, umma_desc_sw128(qa + off), umma_desc_sw128(ka + off), idesc_s, kk > 0 ? 1u : 0u);
         }
         umma_commit(&s_full[t]);
       }
@@ -182,7 +194,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention2_kernel(const __grid
     mbar_wait(q_full, 0, 21);
     mbar_wait(&k_full[0], 0, 20);
     tc_fence_after();
+    // Stagger the two tiles by about half a block: tile 1 starts when tile 0 has finished the row-max phase of its first
+    // block, so one tile's MUFU-free phases line up with the other tile's exp phase.
     issue_s(0, 0);
+    mbar_wait(stagger, 0, 24);
     issue_s(1, 0);
     if (elect_one()) umma_commit(&k_empty[0]);
     __syncwarp();
@@ -195,25 +210,40 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention2_kernel(const __grid
         st_n = 0;
         ph_n ^= 1;
       }
+      const bool more = j + 1 < nblk;
+      if (sep && more) {
+        // S_t(j+1) as soon as S_t(j) sits in the softmax threads' registers
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&s_free[t], (uint32_t)(j & 1), 25);
+          if (t == 0) mbar_wait(&k_full[st_n], ph_n, 20);
+          tc_fence_after();
+          issue_s(t, st_n);
+        }
+        if (elect_one()) umma_commit(&k_empty[st_n]);
+        __syncwarp();
+      }
       mbar_wait(&v_full[st], ph, 23);
       const int kv_valid = min(BKV, a.nk - j * BKV);
       const int ksteps_o = (kv_valid + 15) / 16;
       for (int t = 0; t < 2; ++t) {
-        mbar_wait(&p_full[t], (uint32_t)(j & 1), 22);  // P_t(j) is in TMEM (over S_t), S_t(j) fully consumed
+        mbar_wait(&p_full[t], (uint32_t)(j & 1), 22);  // P_t(j) is in TMEM
         tc_fence_after();
         if (elect_one()) {
           const uint32_t va = v_addr + st * v_stage_bytes;
+          const uint32_t dO = tmem_base + (t ? colO1 : colO0);
+          const uint32_t aP = tmem_base + (t ? colS1 : colS0) + offP;
           for (int kk = 0; kk < ksteps_o; ++kk) {
             const uint32_t offv = (uint32_t)((kk >> 2) * vt_atom_bytes + (kk & 3) * 32);
             // A = P_t: 16-bit elements packed two per TMEM column -> 8 columns per K = 16 step
-            umma_f16_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + kk * 8, umma_desc_sw128(va + offv), idesc_o,
-                        (j > 0 || kk > 0) ? 1u : 0u);
+            umma_f16_ts(dO, aP + kk * 8, umma_desc_sw128(va + offv), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
           }
-          if (j == nblk - 1) umma_commit(&o_done[t]);
+          // separate-P mode: every block (the softmax waits for it before overwriting P_t / rescaling O_t); aliased mode:
+          // only the last block (s_full of the next block already implies it on the in-order pipe)
+          if (sep || !more) umma_commit(&pv_done[t]);
           if (t == 1) umma_commit(&v_empty[st]);
         }
         __syncwarp();
-        if (j + 1 < nblk) {
+        if (!sep && more) {
           if (t == 0) {
             mbar_wait(&k_full[st_n], ph_n, 20);
             tc_fence_after();
@@ -234,12 +264,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention2_kernel(const __grid
     const int qd = warp & 3;        // TMEM lane quarter of this warp
     const int r = qd * 32 + lane;
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-    const uint32_t tS = tmem_base + t * 128 + lane_off;
-    const uint32_t tO = tmem_base + 256 + t * 128 + lane_off;
+    const uint32_t tS = tmem_base + (t ? colS1 : colS0) + lane_off;
+    const uint32_t tP = tS + offP;
+    const uint32_t tO = tmem_base + (t ? colO1 : colO0) + lane_off;
     float m_used = -INFINITY;
     for (int j = 0; j < nblk; ++j) {
       const int kv_valid = min(BKV, a.nk - j * BKV);
-      mbar_wait(&s_full[t], (uint32_t)(j & 1), 30);  // also: P V_t(j-1) has completed (in-order pipe, earlier commit scope)
+      mbar_wait(&s_full[t], (uint32_t)(j & 1), 30);
       tc_fence_after();
       uint32_t s[128];
       tmem_ld32(tS + 0, reinterpret_cast<uint32_t(&)[32]>(s[0]));
@@ -247,6 +278,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention2_kernel(const __grid
       tmem_ld32(tS + 64, reinterpret_cast<uint32_t(&)[32]>(s[64]));
       tmem_ld32(tS + 96, reinterpret_cast<uint32_t(&)[32]>(s[96]));
       tmem_ld_wait();
+      if (sep) {  // the S row now lives in registers: the tensor pipe may overwrite S_t with the next block
+        tc_fence_before();
+        mbar_arrive(&s_free[t]);
+      }
       const bool full = (kv_valid == BKV);
       float mx0 = -INFINITY, mx1 = -INFINITY;
       if (full) {
@@ -260,6 +295,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention2_kernel(const __grid
         for (int e = 0; e < 128; ++e)
           if (e < kv_valid) mx0 = fmaxf(mx0, __uint_as_float(s[e]));
       }
+      if (t == 0 && j == 0) mbar_arrive(stagger);
       const float m_blk = fmaxf(mx0, mx1) * a.scale_log2;
       float alpha = 1.0f;
       bool need = false;
@@ -270,7 +306,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention2_kernel(const __grid
         m_used = m_blk;
         need = true;
       }
-      if (__any_sync(0xffffffffu, need)) {  // rare: rescale this warp's 32 rows of O (P V_t(j-1) is complete)
+      if (sep && j > 0) {  // P V_t(j-1) complete: O_t may be rescaled and P_t overwritten (normally long done: no stall)
+        mbar_wait(&pv_done[t], (uint32_t)((j - 1) & 1), 31);
+        tc_fence_after();
+      }
+      if (__any_sync(0xffffffffu, need)) {  // rare: rescale this warp's 32 rows of O
         for (int c = 0; c < a.dv; c += 16) {
           uint32_t o16[16];
           tmem_ld16(tO + c, o16);
@@ -299,14 +339,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention2_kernel(const __grid
           s[e >> 1] = pack_act2(p0, p1, f16);
         }
       }
-      tmem_st32(tS + 0, &s[0]);
-      tmem_st32(tS + 32, &s[32]);
+      tmem_st32(tP + 0, &s[0]);
+      tmem_st32(tP + 32, &s[32]);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[t]);
     }
     // ---- epilogue: O / l -> global (l = O[:, d], accumulated by the ones row of V^T) ----
-    mbar_wait(&o_done[t], 0, 32);
+    mbar_wait(&pv_done[t], sep ? (uint32_t)((nblk - 1) & 1) : 0u, 32);
     tc_fence_after();
     const int qrow = q0 + t * BQ + r;
     float inv_l;

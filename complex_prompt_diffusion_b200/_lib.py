@@ -43,6 +43,7 @@ class GemmParams(C.Structure):
         ("residual", C.c_void_p), ("ld_res", C.c_int),
         ("d", C.c_void_p), ("ldd", C.c_int), ("epilogue", C.c_int), ("variant", C.c_int), ("m_valid", C.c_int),
         ("a_fp16", C.c_int), ("b_fp16", C.c_int), ("out_fp16", C.c_int), ("geglu_block", C.c_int),
+        ("splitk_ws", C.c_void_p), ("splitk_ws_floats", C.c_int64),
     ]
 
 

@@ -61,6 +61,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
       : "memory");
 }
 
+template <bool SEP>  // SEP: P in its own TMEM columns (dv <= 64); otherwise P overwrites S in place
 __global__ void __launch_bounds__(NUM_THREADS, 1) attention2_kernel(const __grid_constant__ Attn2Args a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention2_kernel(const __grid
   // TMEM columns.  Separate-P mode (dv <= 64, i.e. SD-1.x d = 40): per tile [S 128 | P 64 | O 64]; S(j+1) is issued as
   // soon as the softmax threads have READ S(j), so the Q K^T round trip never stalls the exp stream.  Aliased mode
   // (larger head dims): P overwrites S in place, O lives in the upper half; S(j+1) follows P V(j) on the in-order pipe.
-  const bool sep = a.dv <= 64;
+  constexpr bool sep = SEP;
   const uint32_t colS0 = 0, colS1 = sep ? 256u : 128u;
   const uint32_t offP = sep ? 128u : 0u;                 // P_t relative to S_t
   const uint32_t colO0 = sep ? 192u : 256u, colO1 = sep ? 448u : 384u;
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention2_kernel(const __grid
     // Stagger the two tiles by about half a block: tile 1 starts when tile 0 has finished the row-max phase of its first
     // block, so one tile's MUFU-free phases line up with the other tile's exp phase.
     issue_s(0, 0);
-    mbar_wait(stagger, 0, 24);
+    if (nblk > 1) mbar_wait(stagger, 0, 24);  // a single block (cross-attention) has nothing to interleave with
     issue_s(1, 0);
     if (elect_one()) umma_commit(&k_empty[0]);
     __syncwarp();
@@ -433,11 +434,15 @@ cpd_status cpd_attention_2tile(const cpd_attn_params* p, void* stream) {
   const size_t shm = (size_t)q_bytes + (size_t)stages * per_stage + 512 + 1024;
   static bool configured = false;
   if (!configured) {
-    CPD_CUDA_CHECK(cudaFuncSetAttribute(attention2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+    CPD_CUDA_CHECK(cudaFuncSetAttribute(attention2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+    CPD_CUDA_CHECK(cudaFuncSetAttribute(attention2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
     configured = true;
   }
   dim3 grid((p->nq + 2 * BQ - 1) / (2 * BQ), p->heads, p->batch);
-  CPD_CUDA_CHECK(cpd_launch(attention2_kernel, dim3(grid), dim3(NUM_THREADS), shm, (cudaStream_t)stream, a));
+  if (dv <= 64)
+    CPD_CUDA_CHECK(cpd_launch(attention2_kernel<true>, dim3(grid), dim3(NUM_THREADS), shm, (cudaStream_t)stream, a));
+  else
+    CPD_CUDA_CHECK(cpd_launch(attention2_kernel<false>, dim3(grid), dim3(NUM_THREADS), shm, (cudaStream_t)stream, a));
   CPD_CUDA_CHECK(cudaGetLastError());
   return CPD_OK;
 }

@@ -55,6 +55,9 @@ struct Gemm2Args {
   int m_tiles2;     // 256-row tiles
   int n_tiles;
   int num_k;        // taps * 64-channel blocks
+  int splits;       // split-K: each output tile is computed by `splits` work units over disjoint K ranges; the fp32
+                    // partial sums are added into `ws` (red.global.add) and a second kernel applies the epilogue
+  float* ws;        // [rows][n_store] fp32, all zero on entry (the finalize kernel re-zeroes it)
 };
 
 // MC = 1: cluster = one CTA pair.  MC = 2: cluster = two CTA pairs working on the same 256 rows and adjacent column
@@ -85,10 +88,17 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
   const int cluster_id = blockIdx.x / (2 * MC);
   const int num_clusters = gridDim.x / (2 * MC);
   const int n_tiles_c = args.n_tiles / MC;         // column tiles per cluster step (host guarantees divisibility)
-  const int total_tiles = args.m_tiles2 * n_tiles_c;
-  auto tile_mn = [&](int t, int& m2, int& n_tile) {
+  const int splits = args.splits;
+  const int total_tiles = args.m_tiles2 * n_tiles_c * splits;  // work units: (row block, column tile(s), K range)
+  auto tile_mn = [&](int u, int& m2, int& n_tile) {
+    const int t = u / splits;
     m2 = t / n_tiles_c;
     n_tile = (t - m2 * n_tiles_c) * MC + pair;
+  };
+  auto k_range = [&](int u, int& k0, int& k1) {
+    const int sp = u % splits;
+    k0 = (int)((long)sp * args.num_k / splits);
+    k1 = (int)((long)(sp + 1) * args.num_k / splits);
   };
   const int num_k = args.num_k;
   const int cbt = g.cb0 + g.cb1;
@@ -144,12 +154,23 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
         const int b_row = n_tile * tile_w + (int)rank * bn_half;
         // box 0 of this tile at tap (0, 0) (the only box when nbox == 1, the common case)
         const BoxCoord b0 = box_coord(g, m_tile, 0, 4, 0);  // tap 4 = centre: no shift
-        int tap = 0, cb = 0;
+        int k0, k1;
+        k_range(t, k0, k1);
+        int tap = k0 / cbt, cb = k0 - tap * cbt;
         int dy = 0, dx = 0, py = 0, px = 0;
         if (g.taps == 9) {
-          if (g.stride == 1) { dy = -1; dx = -1; } else { dy = -1; py = 1; dx = -1; px = 1; }
+          const int ky = tap / 3, kx = tap - ky * 3;
+          if (g.stride == 1) {
+            dy = ky - 1;
+            dx = kx - 1;
+          } else {
+            dy = (ky == 0) ? -1 : 0;
+            py = (ky == 0) ? 1 : ky - 1;
+            dx = (kx == 0) ? -1 : 0;
+            px = (kx == 0) ? 1 : kx - 1;
+          }
         }
-        for (int kt = 0; kt < num_k; ++kt) {
+        for (int kt = k0; kt < k1; ++kt) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 1);
           uint8_t* sa = smem + stage * stage_bytes;
           const bool src1 = cb >= g.cb0;
@@ -217,7 +238,9 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
         uint32_t accum = 0;
-        for (int kt = 0; kt < num_k; ++kt) {
+        int k0, k1;
+        k_range(t, k0, k1);
+        for (int kt = k0; kt < k1; ++kt) {
           mbar_wait(&full_bar[stage], phase, 2);
           tc_fence_after();
           const uint64_t db = da + b_off;
@@ -269,7 +292,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
     const int box_rows = g.tw * g.th * g.nb;
     uint8_t* my_staging = staging + grp * STAGING_BUFS * CHUNK_BYTES;
     uint64_t* my_res_bar = res_bar + grp * STAGING_BUFS;
-    const bool has_res = args.residual != nullptr;
+    const bool has_res = args.residual != nullptr && splits == 1;
     const uint32_t sw = (uint32_t)((r >> 1) & 3);   // SWIZZLE_64B: 16-byte chunk index ^= (row / 2) % 4
     uint8_t* my_row = nullptr;                      // set per buffer
 
@@ -302,6 +325,30 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS);
 
+      if (splits > 1) {
+        // split-K: add this unit's fp32 partial tile into the workspace; bias / residual / conversion happen in the
+        // finalize kernel once every K range has been added
+        for (int ch = c_lo; ch < c_hi; ++ch) {
+          uint32_t v[32];
+          tmem_ld32(taddr + ch * CHUNK_COLS, v);
+          tmem_ld_wait();
+          const int col0 = n_tile * out_w + ch * CHUNK_COLS;
+          if (rc.valid) {
+            float* wrow = args.ws + rc.row * g.n_store + col0;
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+              if (col0 + e < g.n_store)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wrow + e), "f"(__uint_as_float(v[e])),
+                             "f"(__uint_as_float(v[e + 1])), "f"(__uint_as_float(v[e + 2])), "f"(__uint_as_float(v[e + 3]))
+                             : "memory");
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], leader_crank);
+        continue;
+      }
       for (int ch = c_lo; ch < c_hi; ++ch, ++kc) {
         const int buf = kc % STAGING_BUFS;
         uint8_t* sbuf = my_staging + buf * CHUNK_BYTES;
@@ -435,6 +482,45 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
   }
 }
 
+// Split-K epilogue: d = convert(ws + bias + rowvec + residual), and ws is zeroed again for the next split-K launch.
+__global__ void __launch_bounds__(256) splitk_finalize_kernel(float* __restrict__ ws, int64_t rows, int n_store, int rows_per_img,
+                                                              const float* __restrict__ bias, const float* __restrict__ rowvec,
+                                                              int rowvec_stride, const bf16* residual, int ld_res, bf16* d, int ldd,
+                                                              int of16) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int vec_per_row = n_store / 8;
+  const int64_t total = rows * vec_per_row;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / vec_per_row;
+    const int col = (int)(i - row * vec_per_row) * 8;
+    float4* wp = reinterpret_cast<float4*>(ws + row * n_store + col);
+    const float4 a0 = wp[0], a1 = wp[1];
+    wp[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    wp[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float f[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    if (bias) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] += __ldg(bias + col + e);
+    }
+    if (rowvec) {
+      const float* rv = rowvec + (row / rows_per_img) * rowvec_stride + col;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] += __ldg(rv + e);
+    }
+    if (residual) {
+      const uint4 rr = *reinterpret_cast<const uint4*>(residual + row * ld_res + col);
+      const float2 r0 = unpack_act2(rr.x, of16 != 0), r1 = unpack_act2(rr.y, of16 != 0), r2 = unpack_act2(rr.z, of16 != 0),
+                   r3 = unpack_act2(rr.w, of16 != 0);
+      f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y;
+      f[4] += r2.x; f[5] += r2.y; f[6] += r3.x; f[7] += r3.y;
+    }
+    *reinterpret_cast<uint4*>(d + row * ldd + col) =
+        make_uint4(pack_act2(f[0], f[1], of16 != 0), pack_act2(f[2], f[3], of16 != 0), pack_act2(f[4], f[5], of16 != 0),
+                   pack_act2(f[6], f[7], of16 != 0));
+  }
+}
+
 // Default tile shape from a cost model (the Python host additionally auto-tunes the variant per layer shape on first
 // use, ops.gemm_conv).  Measured on B200 (profiles/r01_*): the main loop is bound by the bytes DELIVERED into
 // each SM (~45 B/cycle/SM whatever the source - TMA multicast across two pairs did not help, B300_MICROARCH: "at
@@ -490,7 +576,7 @@ cpd_status launch2(const Gemm2Args& args, int smem_bytes, cudaStream_t stream) {
     CPD_CUDA_CHECK(cudaFuncSetAttribute(gemm2_kernel<MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  const long steps = (long)args.m_tiles2 * (args.n_tiles / MC);
+  const long steps = (long)args.m_tiles2 * (args.n_tiles / MC) * args.splits;
   const int max_clusters = MC == 2 ? 33 : NUM_SM_PAIRS;
   const int clusters = (int)(steps < max_clusters ? steps : max_clusters);
   CPD_CUDA_CHECK(cpd_launch(gemm2_kernel<MC>, dim3(2 * MC * clusters), dim3(NUM_THREADS2), smem_bytes, stream, args));
@@ -510,18 +596,26 @@ cpd_status cpd_gemm_conv_2cta(const cpd_gemm_params* p, void* stream) {
   args.num_k = g.taps * (g.cb0 + g.cb1);
   // variant: 0 = auto; 32..256 = pair kernel, one sub-tile of BN = variant; 2000 + BN = two sub-tiles of BN (256 x 2BN tile);
   // 1000 + BN = two-pair multicast cluster with BN (1000 = auto BN)
+  // + 10000 * S: split-K over S disjoint K ranges (needs p->splitk_ws)
   int force_bn = 0, force_mc = 0, force_nsub = 0;
-  if (p->variant >= 2000) {
+  int variant = p->variant;
+  int splits = 1;
+  if (variant >= 10000) {
+    splits = variant / 10000;
+    variant %= 10000;
+    if (variant < 32) variant = 160;  // default tile for split launches
+  }
+  if (variant >= 2000) {
     force_mc = 1;
     force_nsub = 2;
-    force_bn = p->variant - 2000;
-  } else if (p->variant >= 1000) {
+    force_bn = variant - 2000;
+  } else if (variant >= 1000) {
     force_mc = 2;
-    force_bn = p->variant - 1000;
-  } else if (p->variant >= 32) {
+    force_bn = variant - 1000;
+  } else if (variant >= 32) {
     force_mc = 1;
     force_nsub = 1;
-    force_bn = p->variant;
+    force_bn = variant;
   }
   static int mc_env = -1;
   if (mc_env < 0) {
@@ -578,6 +672,17 @@ cpd_status cpd_gemm_conv_2cta(const cpd_gemm_params* p, void* stream) {
   args.rowvec = p->rowvec;
   args.residual = reinterpret_cast<const bf16*>(p->residual);
   args.d = reinterpret_cast<bf16*>(p->d);
+  const int64_t out_rows = (p->m_valid > 0 && g.h_out == 1 && g.n_img == 1) ? p->m_valid : (int64_t)g.n_img * g.h_out * g.w_out;
+  if (splits > 1) {
+    CPD_REQUIRE(!geglu && mc == 1, "cpd_gemm_conv: split-K supports neither the GEGLU epilogue nor the multicast cluster");
+    CPD_REQUIRE(p->splitk_ws != nullptr && p->splitk_ws_floats >= out_rows * g.n_store,
+                "cpd_gemm_conv: split-K needs a zeroed fp32 workspace of %lld floats (got %lld)", (long long)(out_rows * g.n_store),
+                (long long)p->splitk_ws_floats);
+    CPD_REQUIRE(g.n_store % 8 == 0 && splits <= args.num_k, "cpd_gemm_conv: bad split-K configuration (splits=%d, k-iterations=%d)",
+                splits, args.num_k);
+  }
+  args.splits = splits;
+  args.ws = p->splitk_ws;
   {  // output / residual views (c, x, y, n), 64-byte swizzle, box = 32 columns x one pixel box
     const uint64_t rows_x = (uint64_t)((p->m_valid > 0 && g.h_out == 1 && g.n_img == 1) ? p->m_valid : g.w_out);
     uint64_t dims[4] = {(uint64_t)g.n_store, rows_x, (uint64_t)g.h_out, (uint64_t)g.n_img};
@@ -596,5 +701,13 @@ cpd_status cpd_gemm_conv_2cta(const cpd_gemm_params* p, void* stream) {
 
   const int smem_bytes = stages * args.stage_bytes + STAGING_BYTES + 512 + 1024;
   if (mc == 2) return launch2<2>(args, smem_bytes, (cudaStream_t)stream);
-  return launch2<1>(args, smem_bytes, (cudaStream_t)stream);
+  const cpd_status st = launch2<1>(args, smem_bytes, (cudaStream_t)stream);
+  if (st != CPD_OK || splits == 1) return st;
+  const int64_t vecs = out_rows * (g.n_store / 8);
+  int blocks = (int)((vecs + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  CPD_CUDA_CHECK(cpd_launch(splitk_finalize_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, p->splitk_ws, out_rows, g.n_store,
+                            g.h_out * g.w_out, p->bias, p->rowvec, p->rowvec_stride, reinterpret_cast<const bf16*>(p->residual),
+                            p->ld_res, reinterpret_cast<bf16*>(p->d), p->ldd, p->out_fp16));
+  return CPD_OK;
 }

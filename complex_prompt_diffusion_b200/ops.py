@@ -113,6 +113,16 @@ def sampler_step(eps, x, *, n_sub, weights, mask_scalars, masks, guidance, sampl
 AUTOTUNE = True      # time the tile-shape variants of cpd_gemm_conv once per layer shape (first eager call) and keep the best
 _TUNED = {}          # shape key -> variant code
 _TUNE_CANDIDATES = (160, 128, 96, 192, 224, 256, 64, 2160, 2128, 2256, 2096, 2192)
+_TUNE_SPLITK = (20160, 30160, 40160, 22160, 32160, 42160, 20128, 40128)  # small-M layers: split-K x tile shape
+_SPLITK_WS = {}      # device index -> zeroed fp32 workspace (re-zeroed by every split-K launch)
+_SPLITK_FLOATS = 16 * 1024 * 1024
+
+
+def _splitk_ws(device):
+    ws = _SPLITK_WS.get(device.index)
+    if ws is None:
+        ws = _SPLITK_WS[device.index] = torch.zeros(_SPLITK_FLOATS, dtype=torch.float32, device=device)
+    return ws
 
 
 def _tune_gemm(key, p, out, residual):
@@ -123,6 +133,10 @@ def _tune_gemm(key, p, out, residual):
     real_d = p.d
     p.d = scratch.data_ptr()
     cands = (p.geglu_block,) if p.epilogue == CPD_EPI_GEGLU else _TUNE_CANDIDATES
+    rows = p.n_img * (p.h_in // p.stride) * (p.w_in // p.stride)
+    k_iters = p.ksize * p.ksize * (p.c0 + p.c1) // 64
+    if p.epilogue != CPD_EPI_GEGLU and -(-rows // 256) * -(-p.n_out // 160) <= 40 and k_iters >= 32:
+        cands = cands + _TUNE_SPLITK  # too few tiles for 74 SM pairs: also try split-K
     best, best_t = 0, float("inf")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for v in cands:
@@ -167,6 +181,8 @@ def gemm_conv(a0, wt, out, *, n_img, h, w, c0, n_out, a1=None, c1=0, ksize=1, st
     p.ldd = ldd if ldd is not None else (n_out // 2 if epilogue == CPD_EPI_GEGLU else n_out)
     p.epilogue, p.variant, p.m_valid = epilogue, variant, m_valid
     p.a_fp16, p.b_fp16, p.out_fp16 = a_f16, b_f16, o_f16
+    ws = _splitk_ws(out.device)
+    p.splitk_ws, p.splitk_ws_floats = ws.data_ptr(), ws.numel()
     p.geglu_block = geglu_block if epilogue == CPD_EPI_GEGLU else 0
     if variant == 0 and AUTOTUNE:
         key = (n_img, h, w, c0, c1, n_out, ksize, stride, epilogue, p.geglu_block, residual is not None, rowvec is not None, a_f16, m_valid)

@@ -109,7 +109,9 @@ enum { CPD_EPI_NONE = 0, CPD_EPI_GEGLU = 1 };
  *
  * variant 0 (auto) runs the persistent CTA-pair kernel (tcgen05 cta_group::2, 256 x BN tiles, double-buffered TMEM
  * accumulators, gemm_umma2.cu); variants 1 / 2 run the one-tile-per-CTA 128 x 128 / 128 x 256 kernel
- * (gemm_umma.cu); variant >= 32 forces the pair kernel's tile width BN = variant (a multiple of 32, <= 256).
+ * (gemm_umma.cu); variant 32..256 forces the pair kernel's tile width BN = variant (a multiple of 32); 2000 + BN: 256 x 2BN tiles
+ * (two sub-tiles, one TMEM accumulator stage); 1000 + BN: two-pair cluster with TMA-multicast A; + 10000 * S: split-K over S
+ * K ranges (small-M layers that cannot fill 74 SM pairs), partial sums reduced through splitk_ws by a second kernel.
  */
 typedef struct {
   const void* a0; const void* a1;
@@ -129,6 +131,8 @@ typedef struct {
   int b_fp16;  /* element type of wt */
   int out_fp16;/* element type of d and residual */
   int geglu_block; /* CPD_EPI_GEGLU: interleave block of wt rows (128 or 256; 0 = 128) */
+  float* splitk_ws;         /* optional fp32 workspace for split-K launches (variant >= 10000): >= pixels * n_out floats, */
+  int64_t splitk_ws_floats; /* ALL ZERO on entry; it is zero again when the call's kernels have run */
 } cpd_gemm_params;
 
 cpd_status cpd_gemm_conv(const cpd_gemm_params* p, void* stream);

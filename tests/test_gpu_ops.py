@@ -43,7 +43,9 @@ DEV = "cuda"
                                            (40000, 2560, 320, 1256), (128, 128, 64, 1064), (70000, 320, 2880, 1000),
                                            # wide tiles: two sub-tiles per tile, single TMEM accumulator stage (variant 2000 + BN)
                                            (65536, 320, 320, 2160), (16384, 640, 640, 2160), (4096, 1280, 1280, 2160), (30000, 512, 192, 2256),
-                                           (1000, 328, 128, 2096), (50000, 1280, 256, 2192)])
+                                           (1000, 328, 128, 2096), (50000, 1280, 256, 2192),
+                                           # split-K (+ 10000 * S): partial sums reduced through the fp32 workspace
+                                           (1024, 1280, 1280, 20160), (1000, 328, 640, 30128), (4096, 1280, 5120, 42160), (256, 128, 2048, 40064)])
 def test_gemm_plain(ops, M, N, K, variant):
     g = torch.Generator(device="cpu").manual_seed(M + N + K)
     a = bf(torch.randn(M, K, generator=g)).to(DEV)
@@ -114,7 +116,9 @@ def test_gemm_geglu(ops, M, C, block, variant):
     (5, 16, 16, 128, 0, 512, 1, 1000),
     # wide 256 x 320 tiles (two sub-tiles, one accumulator stage)
     (16, 64, 64, 320, 0, 320, 1, 2160), (16, 32, 32, 640, 320, 640, 1, 2160), (16, 16, 16, 1280, 0, 1280, 1, 2160),
-    (16, 8, 8, 1280, 1280, 1280, 1, 2160), (16, 64, 64, 320, 0, 320, 2, 2160), (3, 32, 32, 64, 64, 256, 1, 2128)])
+    (16, 8, 8, 1280, 1280, 1280, 1, 2160), (16, 64, 64, 320, 0, 320, 2, 2160), (3, 32, 32, 64, 64, 256, 1, 2128),
+    # split-K on the small-M levels (8x8 / 4x4 images)
+    (16, 8, 8, 1280, 0, 1280, 1, 20160), (16, 8, 8, 1280, 1280, 1280, 1, 42160), (5, 4, 4, 128, 64, 192, 1, 30096), (16, 16, 16, 640, 0, 1280, 2, 20160)])
 def test_conv3x3(ops, n, h, w, c0, c1, cout, stride, variant):
     g = torch.Generator().manual_seed(n * h + cout)
     cin = c0 + c1

@@ -18,6 +18,8 @@ def main():
     ap.add_argument("--images", type=int, default=4)
     ap.add_argument("--rows", type=int, default=4)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--ncu-replay", action="store_true",
+                    help="run under `ncu --profile-from-start off`: profile exactly ONE CUDA-graph replay of the evaluation")
     a = ap.parse_args()
     from complex_prompt_diffusion_b200 import ops
     from complex_prompt_diffusion_b200.models.unet import UNetModel
@@ -40,6 +42,13 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     print(f"whole forward ({a.images * a.rows} rows): {e0.elapsed_time(e1) / a.reps:.3f} ms")
+    if a.ncu_replay:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        unet.forward_rows(x, 0.5, 500.0, a.rows)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     agg = collections.OrderedDict()
     for _ in range(a.reps):
         ops.PROFILE = []

@@ -55,9 +55,11 @@ struct Gemm2Args {
   int m_tiles2;     // 256-row tiles
   int n_tiles;
   int num_k;        // taps * 64-channel blocks
-  int splits;       // split-K: each output tile is computed by `splits` work units over disjoint K ranges; the fp32
-                    // partial sums are added into `ws` (red.global.add) and a second kernel applies the epilogue
-  float* ws;        // [rows][n_store] fp32, all zero on entry (the finalize kernel re-zeroes it)
+  int splits;       // split-K: each output tile is computed by `splits` work units over disjoint K ranges; unit s stores
+                    // its fp32 partial tile into slice s of `ws` and a second kernel sums the slices in a fixed order
+                    // (no atomics: bit-reproducible) and applies the epilogue
+  float* ws;        // [splits][rows][n_store] fp32
+  int64_t ws_slice; // rows * n_store
 };
 
 // MC = 1: cluster = one CTA pair.  MC = 2: cluster = two CTA pairs working on the same 256 rows and adjacent column
@@ -334,13 +336,12 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
           tmem_ld_wait();
           const int col0 = n_tile * out_w + ch * CHUNK_COLS;
           if (rc.valid) {
-            float* wrow = args.ws + rc.row * g.n_store + col0;
+            float* wrow = args.ws + (int64_t)(t % splits) * args.ws_slice + rc.row * g.n_store + col0;
 #pragma unroll
             for (int e = 0; e < 32; e += 4) {
               if (col0 + e < g.n_store)
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(wrow + e), "f"(__uint_as_float(v[e])),
-                             "f"(__uint_as_float(v[e + 1])), "f"(__uint_as_float(v[e + 2])), "f"(__uint_as_float(v[e + 3]))
-                             : "memory");
+                *reinterpret_cast<float4*>(wrow + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                                                   __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
             }
           }
         }
@@ -482,8 +483,9 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
   }
 }
 
-// Split-K epilogue: d = convert(ws + bias + rowvec + residual), and ws is zeroed again for the next split-K launch.
-__global__ void __launch_bounds__(256) splitk_finalize_kernel(float* __restrict__ ws, int64_t rows, int n_store, int rows_per_img,
+// Split-K epilogue: d = convert(sum_s ws[s] + bias + rowvec + residual), slices summed in a fixed order.
+__global__ void __launch_bounds__(256) splitk_finalize_kernel(const float* __restrict__ ws, int splits, int64_t ws_slice, int64_t rows,
+                                                              int n_store, int rows_per_img,
                                                               const float* __restrict__ bias, const float* __restrict__ rowvec,
                                                               int rowvec_stride, const bf16* residual, int ld_res, bf16* d, int ldd,
                                                               int of16) {
@@ -494,11 +496,13 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(float* __restrict_
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = i / vec_per_row;
     const int col = (int)(i - row * vec_per_row) * 8;
-    float4* wp = reinterpret_cast<float4*>(ws + row * n_store + col);
-    const float4 a0 = wp[0], a1 = wp[1];
-    wp[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-    wp[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-    float f[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int sp = 0; sp < splits; ++sp) {
+      const float4* wp = reinterpret_cast<const float4*>(ws + sp * ws_slice + row * n_store + col);
+      const float4 a0 = wp[0], a1 = wp[1];
+      f[0] += a0.x; f[1] += a0.y; f[2] += a0.z; f[3] += a0.w;
+      f[4] += a1.x; f[5] += a1.y; f[6] += a1.z; f[7] += a1.w;
+    }
     if (bias) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) f[e] += __ldg(bias + col + e);
@@ -675,14 +679,15 @@ cpd_status cpd_gemm_conv_2cta(const cpd_gemm_params* p, void* stream) {
   const int64_t out_rows = (p->m_valid > 0 && g.h_out == 1 && g.n_img == 1) ? p->m_valid : (int64_t)g.n_img * g.h_out * g.w_out;
   if (splits > 1) {
     CPD_REQUIRE(!geglu && mc == 1, "cpd_gemm_conv: split-K supports neither the GEGLU epilogue nor the multicast cluster");
-    CPD_REQUIRE(p->splitk_ws != nullptr && p->splitk_ws_floats >= out_rows * g.n_store,
-                "cpd_gemm_conv: split-K needs a zeroed fp32 workspace of %lld floats (got %lld)", (long long)(out_rows * g.n_store),
+    CPD_REQUIRE(p->splitk_ws != nullptr && p->splitk_ws_floats >= (int64_t)splits * out_rows * g.n_store,
+                "cpd_gemm_conv: split-K needs an fp32 workspace of %lld floats (got %lld)", (long long)(splits * out_rows * g.n_store),
                 (long long)p->splitk_ws_floats);
     CPD_REQUIRE(g.n_store % 8 == 0 && splits <= args.num_k, "cpd_gemm_conv: bad split-K configuration (splits=%d, k-iterations=%d)",
                 splits, args.num_k);
   }
   args.splits = splits;
   args.ws = p->splitk_ws;
+  args.ws_slice = out_rows * g.n_store;
   {  // output / residual views (c, x, y, n), 64-byte swizzle, box = 32 columns x one pixel box
     const uint64_t rows_x = (uint64_t)((p->m_valid > 0 && g.h_out == 1 && g.n_img == 1) ? p->m_valid : g.w_out);
     uint64_t dims[4] = {(uint64_t)g.n_store, rows_x, (uint64_t)g.h_out, (uint64_t)g.n_img};
@@ -706,7 +711,7 @@ cpd_status cpd_gemm_conv_2cta(const cpd_gemm_params* p, void* stream) {
   const int64_t vecs = out_rows * (g.n_store / 8);
   int blocks = (int)((vecs + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  CPD_CUDA_CHECK(cpd_launch(splitk_finalize_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, p->splitk_ws, out_rows, g.n_store,
+  CPD_CUDA_CHECK(cpd_launch(splitk_finalize_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (const float*)p->splitk_ws, splits, args.ws_slice, out_rows, g.n_store,
                             g.h_out * g.w_out, p->bias, p->rowvec, p->rowvec_stride, reinterpret_cast<const bf16*>(p->residual),
                             p->ld_res, reinterpret_cast<bf16*>(p->d), p->ldd, p->out_fp16));
   return CPD_OK;

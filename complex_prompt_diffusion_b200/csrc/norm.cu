@@ -7,19 +7,19 @@ namespace {
 
 constexpr int GROUPS = 32;
 
-// ---- GroupNorm pass 1: per-(image, group) sum / sum of squares -----------------------------------
-// grid = (chunks, n_img).  Thread t owns channel vector (t % vec_per_px) and pixel lane (t / vec_per_px).
+// ---- GroupNorm pass 1: per-(image, pixel chunk, group) sum / sum of squares ----------------------------------------
+// grid = (chunks, n_img).  Thread t owns channel vector (t % vec_per_px) and pixel lane (t / vec_per_px).  No atomics
+// anywhere: per-thread partials go to shared memory, are summed over the pixel lanes in a fixed order, reduced per group in
+// fp64 and written to partial[n][chunk][group][2]; pass 2 sums the chunks in a fixed order.  Results are bit-reproducible.
 __global__ void __launch_bounds__(512, 2) gn_stats_kernel(const bf16* __restrict__ a0, const bf16* __restrict__ a1, int c0,
-                                                       int c1, int hw, int px_per_block, int f16, double* __restrict__ stats) {
-  extern __shared__ float sh[];  // [2][C]
+                                                          int c1, int hw, int px_per_block, int f16, double* __restrict__ partial) {
+  extern __shared__ float sh[];  // [lanes][2][C]
   pdl_launch_dependents();
   pdl_wait();
   const int C = c0 + c1;
   const int vec_per_px = C / 8;
   const int lanes = blockDim.x / vec_per_px;
   const int n = blockIdx.y;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
   const int cv = threadIdx.x % vec_per_px;
   const int pl = threadIdx.x / vec_per_px;
   if (pl < lanes) {
@@ -59,10 +59,11 @@ __global__ void __launch_bounds__(512, 2) gn_stats_kernel(const bf16* __restrict
         s[2 * e + 1] += f.y; ss[2 * e + 1] += f.y * f.y;
       }
     }
+    float* mine = sh + (size_t)pl * 2 * C;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      atomicAdd(&sh[ch + e], s[e]);
-      atomicAdd(&sh[C + ch + e], ss[e]);
+      mine[ch + e] = s[e];
+      mine[C + ch + e] = ss[e];
     }
   }
   __syncthreads();
@@ -70,17 +71,20 @@ __global__ void __launch_bounds__(512, 2) gn_stats_kernel(const bf16* __restrict
   if (threadIdx.x < GROUPS) {
     double S = 0.0, SS = 0.0;
     for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) {
-      S += (double)sh[c];
-      SS += (double)sh[C + c];
+      for (int l = 0; l < lanes; ++l) {  // fixed order: lane 0, 1, ...
+        S += (double)sh[(size_t)l * 2 * C + c];
+        SS += (double)sh[(size_t)l * 2 * C + C + c];
+      }
     }
-    atomicAdd(&stats[((int64_t)n * GROUPS + threadIdx.x) * 2 + 0], S);
-    atomicAdd(&stats[((int64_t)n * GROUPS + threadIdx.x) * 2 + 1], SS);
+    double* out = partial + (((int64_t)n * gridDim.x + blockIdx.x) * GROUPS + threadIdx.x) * 2;
+    out[0] = S;
+    out[1] = SS;
   }
 }
 
 // ---- GroupNorm pass 2: normalise, affine, optional SiLU, write bf16 ---------------------------------
 __global__ void __launch_bounds__(512, 2) gn_apply_kernel(const bf16* __restrict__ a0, const bf16* __restrict__ a1, int c0,
-                                                       int c1, int hw, int px_per_block, const double* __restrict__ stats,
+                                                       int c1, int hw, int px_per_block, const double* __restrict__ partial,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        float eps, int silu, int f16, bf16* __restrict__ out) {
   extern __shared__ float sh[];  // scale[C], shift[C]
@@ -94,8 +98,12 @@ __global__ void __launch_bounds__(512, 2) gn_apply_kernel(const bf16* __restrict
   const double cnt = (double)hw * cpg;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / cpg;
-    const double S = stats[((int64_t)n * GROUPS + g) * 2 + 0];
-    const double SS = stats[((int64_t)n * GROUPS + g) * 2 + 1];
+    double S = 0.0, SS = 0.0;
+    for (int k = 0; k < (int)gridDim.x; ++k) {  // chunk partials of pass 1, fixed order
+      const double* pp = partial + (((int64_t)n * gridDim.x + k) * GROUPS + g) * 2;
+      S += pp[0];
+      SS += pp[1];
+    }
     const double mean = S / cnt;
     double var = SS / cnt - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -226,7 +234,6 @@ extern "C" cpd_status cpd_groupnorm(const void* a0, const void* a1, int c0, int 
   CPD_REQUIRE(c1 == 0 || a1, "cpd_groupnorm: c1 > 0 needs a1");
   CPD_REQUIRE(n_img > 0 && hw > 0, "cpd_groupnorm: empty input");
   cudaStream_t s = (cudaStream_t)stream;
-  CPD_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * GROUPS * n_img, s));
   const int vec_per_px = C / 8;
   // <= 256 threads per block (4 blocks per SM at <= 64 registers), 8 x 16-byte loads in flight per thread
   int lanes = 256 / vec_per_px;
@@ -239,8 +246,19 @@ extern "C" cpd_status cpd_groupnorm(const void* a0, const void* a1, int c0, int 
   int px_per_block = (hw + chunks - 1) / chunks;
   if (px_per_block < 8 * lanes) px_per_block = 8 * lanes;
   chunks = (hw + px_per_block - 1) / px_per_block;
+  if (chunks > CPD_GN_MAX_CHUNKS) {  // the scratch holds CPD_GN_MAX_CHUNKS partials per image
+    px_per_block = (hw + CPD_GN_MAX_CHUNKS - 1) / CPD_GN_MAX_CHUNKS;
+    chunks = (hw + px_per_block - 1) / px_per_block;
+  }
   const size_t shm = sizeof(float) * 2 * C;
-  CPD_CUDA_CHECK(cpd_launch(gn_stats_kernel, dim3(dim3(chunks, n_img)), dim3(threads), shm, s, (const bf16*)a0, (const bf16*)a1, c0, c1, hw, px_per_block, act_fp16, stats));
+  const size_t shm_stats = sizeof(float) * 2 * C * lanes;
+  CPD_REQUIRE(shm_stats <= 160 * 1024, "cpd_groupnorm: C=%d needs %zu bytes of shared memory", C, shm_stats);
+  static bool cfg = false;
+  if (!cfg) {
+    CPD_CUDA_CHECK(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    cfg = true;
+  }
+  CPD_CUDA_CHECK(cpd_launch(gn_stats_kernel, dim3(dim3(chunks, n_img)), dim3(threads), shm_stats, s, (const bf16*)a0, (const bf16*)a1, c0, c1, hw, px_per_block, act_fp16, stats));
   CPD_CUDA_CHECK(cudaGetLastError());
   CPD_CUDA_CHECK(cpd_launch(gn_apply_kernel, dim3(dim3(chunks, n_img)), dim3(threads), shm, s, (const bf16*)a0, (const bf16*)a1, c0, c1, hw, px_per_block, stats,
                                                            gamma, beta, eps, silu, act_fp16, (bf16*)out));

@@ -59,8 +59,14 @@ __global__ void __launch_bounds__(256, 4) sampler_step_kernel(const __grid_const
     } else if (p.sampler == CPD_EULER_ANCESTRAL) {
       aux = __ldg(reinterpret_cast<const float4*>(p.noise + (int64_t)b * L + i));
     }
-    float eu[4], hu[4], sum[4] = {0.f, 0.f, 0.f, 0.f};
+    // The fp16 delta (denoiser.py:450-460) runs on packed half2: for fp16 operands HSUB2 / HMUL2 / HADD2 (one rounding) give
+    // bit-identical results to "compute in fp32, round to fp16" (products of two halves are exact in fp32; sums are exact
+    // unless the smaller operand is below a quarter ulp of the larger, where both roundings return the larger).  The _rn
+    // intrinsics keep ptxas from contracting mul + add into a single-rounding HFMA2.
+    float eu[4];
     load4<DT>(p.eps, ebase, eu);
+    const __half2 hu01 = __floats2half2_rn(eu[0], eu[1]), hu23 = __floats2half2_rn(eu[2], eu[3]);
+    __half2 sum01 = __floats2half2_rn(0.f, 0.f), sum23 = sum01;
     for (int k0 = 0; k0 < p.n_sub; k0 += 4) {
       float ek4[4][4];
       float4 m4[4];
@@ -72,34 +78,34 @@ __global__ void __launch_bounds__(256, 4) sampler_step_kernel(const __grid_const
           if (p.masks[k] != nullptr) m4[kk] = __ldg(reinterpret_cast<const float4*>(p.masks[k] + pix));
         }
       }
-      if (k0 == 0) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) hu[j] = h_round(eu[j]);
-      }
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         const int k = k0 + kk;
         if (k < p.n_sub) {
           // half(m) * half(w), rounded to fp16 (denoiser.py:451-452); weights live in the kernel-parameter constant bank
-          const float w_hk = h_round(p.weights[k]);
-          float mw[4];
+          const __half w_hk = __float2half_rn(p.weights[k]);
+          __half2 mw01, mw23;
           if (p.masks[k] != nullptr) {
-            mw[0] = h_round(__fmul_rn(h_round(m4[kk].x), w_hk));
-            mw[1] = h_round(__fmul_rn(h_round(m4[kk].y), w_hk));
-            mw[2] = h_round(__fmul_rn(h_round(m4[kk].z), w_hk));
-            mw[3] = h_round(__fmul_rn(h_round(m4[kk].w), w_hk));
+            const __half2 wk2 = __half2half2(w_hk);
+            mw01 = __hmul2_rn(__floats2half2_rn(m4[kk].x, m4[kk].y), wk2);
+            mw23 = __hmul2_rn(__floats2half2_rn(m4[kk].z, m4[kk].w), wk2);
           } else {
-            mw[0] = mw[1] = mw[2] = mw[3] = h_round(__fmul_rn(h_round(p.mask_scalar[k]), w_hk));
+            mw01 = mw23 = __half2half2(__hmul_rn(__float2half_rn(p.mask_scalar[k]), w_hk));
           }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float d = h_round(__fsub_rn(h_round(ek4[kk][j]), hu[j]));
-            float term = h_round(__fmul_rn(mw[j], d));
-            sum[j] = (k == 0) ? term : h_round(__fadd_rn(sum[j], term));
+          const __half2 t01 = __hmul2_rn(mw01, __hsub2_rn(__floats2half2_rn(ek4[kk][0], ek4[kk][1]), hu01));
+          const __half2 t23 = __hmul2_rn(mw23, __hsub2_rn(__floats2half2_rn(ek4[kk][2], ek4[kk][3]), hu23));
+          if (k == 0) {
+            sum01 = t01;
+            sum23 = t23;
+          } else {
+            sum01 = __hadd2_rn(sum01, t01);
+            sum23 = __hadd2_rn(sum23, t23);
           }
         }
       }
     }
+    const float2 s01 = __half22float2(sum01), s23 = __half22float2(sum23);
+    const float sum[4] = {s01.x, s01.y, s23.x, s23.y};
     float x[4] = {xv.x, xv.y, xv.z, xv.w};
     float et[4], den[4], xn[4];
 #pragma unroll

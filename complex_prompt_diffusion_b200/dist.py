@@ -100,3 +100,41 @@ def gather_images(local_x: torch.Tensor, batch: int, world: int, group=None) -> 
     out = [torch.empty_like(buf) for _ in range(world)]
     dist.all_gather(out, buf, group=group)
     return torch.cat([o[:c] for o, c in zip(out, counts)])
+
+
+def sample_sharded(wrapper, *, steps, batch, shape, x_T, conditioning, unconditional_conditioning, world=None, rank=None, **kw):
+    """Run `wrapper.sampler.sample` for a global batch of `batch` images on all ranks of the default process group.
+    batch >= world: images are sharded (no data-path collective); batch < world: the ranks of an image's group split
+    its (1 + N) conditioning rows and all-gather eps every step.  x_T is the GLOBAL [batch, C, h, w] start noise (same
+    on every rank).  Returns the full [batch, C, h, w] result on every rank."""
+    import torch.distributed as dist
+    world = dist.get_world_size() if world is None else world
+    rank = dist.get_rank() if rank is None else rank
+    rows_total = 1 + len(conditioning["and"]) + len(conditioning.get("not", []))
+    part = partition(batch, rows_total, world, rank)
+    sampler = wrapper.sampler
+    groups = None
+    if batch < world:
+        # one NCCL sub-group per image (every rank must create every group, in the same order)
+        groups, seen = {}, set()
+        for r in range(world):
+            members = tuple(partition(batch, rows_total, world, r).group_ranks)
+            if members not in seen:
+                seen.add(members)
+                groups[members] = dist.new_group(list(members)) if len(members) > 1 else None
+        sampler.denoiser.set_row_partition(part, groups[tuple(part.group_ranks)])
+    else:
+        sampler.denoiser.set_row_partition(None)
+    mine = x_T[part.images]
+    out = sampler.sample(steps=steps, batch_size=len(part.images), shape=shape, x_T=mine, conditioning=conditioning,
+                         unconditional_conditioning=unconditional_conditioning, **kw)
+    if batch >= world:
+        return gather_images(out, batch, world)
+    # row-sharded: every rank of a group holds the same image; gather one copy per image
+    outs = [torch.empty_like(out) for _ in range(world)]
+    dist.all_gather(outs, out.contiguous())
+    firsts = {}
+    for r in range(world):
+        img = partition(batch, rows_total, world, r).images[0]
+        firsts.setdefault(img, outs[r])
+    return torch.cat([firsts[i] for i in range(batch)])

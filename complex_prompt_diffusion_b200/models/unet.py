@@ -399,7 +399,7 @@ class UNetModel:
         W = self.w
         B, cin, h, w = x.shape
         R = B * rows_per_image
-        stats = self._buf("gn.stats", R * 64, torch.float64)
+        stats = self._buf("gn.stats", R * 64 * ops.GN_MAX_CHUNKS, torch.float64)
         emb_all = self._embeddings(t_rows)
         emb_stride = 0 if shared_t else self.emb_total
         mc = self.model_channels

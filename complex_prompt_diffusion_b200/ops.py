@@ -4,6 +4,7 @@ stream come from torch; all arithmetic happens in libcpd_b200.so.  No fallbacks.
 Activation tensors are 16-bit: torch.float16 or torch.bfloat16 (the `act_fp16` flag of the C ABI is derived
 from the tensor dtype); weights are always bf16."""
 import ctypes as C
+import os
 
 import torch
 
@@ -110,18 +111,18 @@ def sampler_step(eps, x, *, n_sub, weights, mask_scalars, masks, guidance, sampl
     return x
 
 
-AUTOTUNE = True      # time the tile-shape variants of cpd_gemm_conv once per layer shape (first eager call) and keep the best
+AUTOTUNE = os.environ.get("CPD_GEMM_AUTOTUNE", "1") != "0"  # time the tile-shape variants of cpd_gemm_conv once per layer shape (first eager call) and keep the best
 _TUNED = {}          # shape key -> variant code
 _TUNE_CANDIDATES = (160, 128, 96, 192, 224, 256, 64, 2160, 2128, 2256, 2096, 2192)
 _TUNE_SPLITK = (20160, 30160, 40160, 22160, 32160, 42160, 20128, 40128)  # small-M layers: split-K x tile shape
-_SPLITK_WS = {}      # device index -> zeroed fp32 workspace (re-zeroed by every split-K launch)
-_SPLITK_FLOATS = 16 * 1024 * 1024
+_SPLITK_WS = {}      # device index -> fp32 scratch for the split-K partial tiles
+_SPLITK_FLOATS = 32 * 1024 * 1024
 
 
 def _splitk_ws(device):
     ws = _SPLITK_WS.get(device.index)
     if ws is None:
-        ws = _SPLITK_WS[device.index] = torch.zeros(_SPLITK_FLOATS, dtype=torch.float32, device=device)
+        ws = _SPLITK_WS[device.index] = torch.empty(_SPLITK_FLOATS, dtype=torch.float32, device=device)
     return ws
 
 
@@ -205,13 +206,16 @@ def groupnorm(a0, gamma, beta, out, stats, *, n_img, hw, c0, a1=None, c1=0, eps=
     _req(gamma, torch.float32, "gamma")
     _req(beta, torch.float32, "beta")
     _req(stats, torch.float64, "stats")
-    if stats.numel() < n_img * 64:
-        raise RuntimeError("stats scratch too small")
+    if stats.numel() < n_img * 64 * GN_MAX_CHUNKS:
+        raise RuntimeError(f"stats scratch too small: need n_img * 64 * {GN_MAX_CHUNKS} doubles")
     with _Prof("groupnorm", 0.0, f"n={n_img} hw={hw} C={c0 + c1}"):
         check(load().cpd_groupnorm(ptr(a0), ptr(a1), c0, c1, n_img, hw, ptr(gamma), ptr(beta), float(eps), int(silu), f16, ptr(stats),
                                    ptr(out), stream_ptr()), "cpd_groupnorm")
     _count(2)
     return out
+
+
+GN_MAX_CHUNKS = 64  # CPD_GN_MAX_CHUNKS of include/cpd_b200.h
 
 
 def layernorm(x, gamma, beta, out, *, rows, c, eps=1e-5):

@@ -80,6 +80,17 @@ class Denoiser(torch.nn.Module):
         self.sigma_data = 1.0
         self.unet, self.vae, self.tokenizer, self.clip_model, self.decode = unet, vae, tokenizer, clip_model, decode
         self._plan_key, self._plan = None, None
+        self._part, self._group = None, None
+
+    def set_row_partition(self, part, group=None):
+        """Multi-GPU row sharding (used when the image batch is smaller than the GPU count): this rank
+        evaluates only `part.rows` of the (1 + N) conditioning rows of its image; the eps rows are all-gathered over
+        NCCL inside `part.group_ranks` every step and every rank of the group runs the (tiny) fused step redundantly, so
+        x stays replicated without a broadcast.  `part` comes from `dist.partition`; None switches it off."""
+        if part is not None and not part.needs_allgather:
+            part = None
+        self._part, self._group = part, group
+        self._plan_key = None
 
     # ---- host-side (once per sample() call) -----------------------------------------------------------
     def _check_kwargs(self, kwargs):
@@ -99,7 +110,10 @@ class Denoiser(torch.nn.Module):
         if self._plan_key != key:
             self._plan = ConditioningPlan(c, uc, self.dtype, self.device, hw_shape)
             self._plan_key = key
-            self.unet.set_context(self._plan.context)
+            if self._part is None:
+                self.unet.set_context(self._plan.context)
+            elif self._part.rows:
+                self.unet.set_context(self._plan.context[self._part.rows].contiguous())
         return self._plan
 
     @staticmethod
@@ -121,7 +135,19 @@ class Denoiser(torch.nn.Module):
         sig = torch.as_tensor(sigma, dtype=torch.float32).reshape(-1)[:1].cpu()
         c_in = 1 / (sig ** 2 + 1 ** 2) ** 0.5  # get_scalings, fp32 like denoiser.py:390
         t = self.scheduler.sigma_to_t(sig).to(self.dtype).float()  # fp64 -> model dtype (P3, denoiser.py:393)
-        return self.unet.forward_rows(x, float(c_in), float(t), rows_per_image=1 + plan.n_sub)
+        if self._part is None:
+            return self.unet.forward_rows(x, float(c_in), float(t), rows_per_image=1 + plan.n_sub)
+        # row-sharded: my rows of my (single) image, then the NCCL all-gather of eps inside the image's rank group
+        from ... import dist as D
+        if x.shape[0] != 1:
+            raise ValueError("row sharding works on one image per rank group (shard the batch across groups first)")
+        L = x[0].numel()
+        if self._part.rows:
+            local = self.unet.forward_rows(x, float(c_in), float(t), rows_per_image=len(self._part.rows)).reshape(len(self._part.rows), L)
+        else:
+            local = torch.empty(0, L, dtype=self.unet.eps_dtype, device=self.device)
+        full = D.allgather_eps_rows(local, self._part, group=self._group)
+        return full.reshape(1 + plan.n_sub, *x.shape[1:]).contiguous()
 
     def fused_step(self, x, sigma, plan, step, **kwargs):
         """One UNet evaluation + ONE fused kernel: CFG combine, denoised, sampler update (x updated in place).

@@ -131,17 +131,18 @@ typedef struct {
   int b_fp16;  /* element type of wt */
   int out_fp16;/* element type of d and residual */
   int geglu_block; /* CPD_EPI_GEGLU: interleave block of wt rows (128 or 256; 0 = 128) */
-  float* splitk_ws;         /* optional fp32 workspace for split-K launches (variant >= 10000): >= pixels * n_out floats, */
-  int64_t splitk_ws_floats; /* ALL ZERO on entry; it is zero again when the call's kernels have run */
+  float* splitk_ws;         /* optional fp32 scratch for split-K launches (variant >= 10000): >= S * pixels * n_out floats */
+  int64_t splitk_ws_floats; /* (one slice per K range, summed in a fixed order by the finalize kernel: no atomics) */
 } cpd_gemm_params;
 
 cpd_status cpd_gemm_conv(const cpd_gemm_params* p, void* stream);
 
 /*
  * GroupNorm(32 groups) [+ SiLU] over NHWC bf16, fp32 statistics (models/util.py:95-105, attention.py:89-90).
- * Input channels may come from two tensors (skip concat).  stats: fp64 scratch [n_img][32][2], zeroed by
- * the call.  out: bf16 [n_img*hw][c0 + c1].
+ * Input channels may come from two tensors (skip concat).  stats: fp64 scratch of n_img * CPD_GN_MAX_CHUNKS * 64
+ * doubles (per-chunk partial sums, reduced in a fixed order: no atomics, bit-reproducible).  out: bf16 [n_img*hw][c0 + c1].
  */
+#define CPD_GN_MAX_CHUNKS 64
 cpd_status cpd_groupnorm(const void* a0, const void* a1, int c0, int c1, int n_img, int hw, const float* gamma,
                          const float* beta, float eps, int silu, int act_fp16, double* stats, void* out, void* stream);
 

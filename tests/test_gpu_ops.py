@@ -200,7 +200,7 @@ def test_groupnorm(ops, n, hw, c0, c1, silu, eps):
     x = bf(torch.randn(n, hw, C, generator=g) * 2 + 0.5)
     gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
     out = torch.empty(n, hw, C, dtype=torch.bfloat16, device=DEV)
-    stats = torch.empty(n * 64, dtype=torch.float64, device=DEV)
+    stats = torch.empty(n * 64 * ops.GN_MAX_CHUNKS, dtype=torch.float64, device=DEV)
     ops.groupnorm(x[..., :c0].contiguous().to(DEV), gamma.to(DEV), beta.to(DEV), out, stats, n_img=n, hw=hw, c0=c0,
                   a1=x[..., c0:].contiguous().to(DEV) if c1 else None, c1=c1, eps=eps, silu=silu)
     torch.cuda.synchronize()
@@ -332,7 +332,7 @@ def test_conv_attention_norms_fp16_activations(ops):
     xx = (torch.randn(n, hw, C, generator=g) * 2 + 0.5).half().to(DEV)
     gamma, beta = torch.randn(C, generator=g).to(DEV), torch.randn(C, generator=g).to(DEV)
     og = torch.empty_like(xx)
-    stats = torch.empty(n * 64, dtype=torch.float64, device=DEV)
+    stats = torch.empty(n * 64 * ops.GN_MAX_CHUNKS, dtype=torch.float64, device=DEV)
     ops.groupnorm(xx, gamma, beta, og, stats, n_img=n, hw=hw, c0=C, silu=True)
     refg = F.silu(F.group_norm(xx.float().permute(0, 2, 1), 32, gamma, beta, 1e-5))
     assert rel(og.permute(0, 2, 1), refg) < 6e-4

@@ -13,6 +13,8 @@
 // is rescaled with O.  Lazy rescaling (threshold 2^8) keeps O corrections rare.
 //
 // Replaces the sliced einsum / softmax / einsum of cpd/models/attention.py:283-348 for head dims <= 112.
+#include <stdlib.h>
+
 #include "../../include/cpd_b200.h"
 #include "common.cuh"
 
@@ -439,7 +441,14 @@ cpd_status cpd_attention_2tile(const cpd_attn_params* p, void* stream) {
     configured = true;
   }
   dim3 grid((p->nq + 2 * BQ - 1) / (2 * BQ), p->heads, p->batch);
-  if (dv <= 64)
+  // The separate-P layout (S(j+1) issued as soon as S(j) is in registers) measured SLOWER than aliasing P over S
+  // (893 vs 829 us on 16 x 8 x 4096^2, d = 40, same box): it stays opt-in (CPD_ATTN_SEP=1) for experiments.
+  static int sep_env = -1;
+  if (sep_env < 0) {
+    const char* e = getenv("CPD_ATTN_SEP");
+    sep_env = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (dv <= 64 && sep_env)
     CPD_CUDA_CHECK(cpd_launch(attention2_kernel<true>, dim3(grid), dim3(NUM_THREADS), shm, (cudaStream_t)stream, a));
   else
     CPD_CUDA_CHECK(cpd_launch(attention2_kernel<false>, dim3(grid), dim3(NUM_THREADS), shm, (cudaStream_t)stream, a));

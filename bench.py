@@ -234,6 +234,15 @@ def run_b200(args):
 
     for _ in range(args.warmup):
         step_resident()
+    if os.environ.get("CPD_BENCH_NCU"):
+        # `ncu --profile-from-start off ... python bench.py ...`: profile exactly one step (use --sampler-steps 2 to keep
+        # the launch list short), then exit: numbers printed under a profiler are never bench values.
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()

@@ -113,7 +113,7 @@ def sampler_step(eps, x, *, n_sub, weights, mask_scalars, masks, guidance, sampl
 
 AUTOTUNE = os.environ.get("CPD_GEMM_AUTOTUNE", "1") != "0"  # time the tile-shape variants of cpd_gemm_conv once per layer shape (first eager call) and keep the best
 _TUNED = {}          # shape key -> variant code
-_TUNE_CANDIDATES = (160, 128, 96, 192, 224, 256, 64, 2160, 2128, 2256, 2096, 2192)
+_TUNE_CANDIDATES = (160, 128, 96, 192, 224, 256, 64, 2160, 2128, 2256, 2096, 2192, 1, 2)  # 1, 2: one-tile-per-CTA kernel
 _TUNE_SPLITK = (20160, 30160, 40160, 22160, 32160, 42160, 20128, 40128)  # small-M layers: split-K x tile shape
 _SPLITK_WS = {}      # device index -> fp32 scratch for the split-K partial tiles
 _SPLITK_FLOATS = 32 * 1024 * 1024
@@ -156,6 +156,9 @@ def _tune_gemm(key, p, out, residual):
             best, best_t = v, t
     p.d = real_d
     _TUNED[key] = best
+    if os.environ.get("CPD_GEMM_DEBUG"):
+        print(f"tuned gemm rows={rows} N={p.n_out} K={p.ksize * p.ksize * (p.c0 + p.c1)} epi={p.epilogue} res={residual is not None}: "
+              f"variant {best} ({best_t / 3 * 1e3:.1f} us)", flush=True)
     return best
 
 

@@ -37,6 +37,23 @@ constexpr int CHUNK_BYTES = BM * CHUNK_COLS * 2;   // 8 KB
 constexpr int STAGING_BUFS = 3;                    // per epilogue group
 constexpr int STAGING_BYTES = 2 * STAGING_BUFS * CHUNK_BYTES;
 
+#ifdef CPD_TIMELINE
+// Debug build (make TIMELINE=1): CTA 0 stamps %globaltimer at the phases of its first tile (tools/gemm_timeline.py)
+__device__ unsigned long long cpd_dbg_ts[16];
+#define CPD_STAMP(i)                                                                  \
+  do {                                                                                \
+    if (blockIdx.x == 0) {                                                            \
+      unsigned long long _t;                                                          \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));                          \
+      cpd_dbg_ts[i] = _t;                                                             \
+    }                                                                                 \
+  } while (0)
+#else
+#define CPD_STAMP(i) \
+  do {               \
+  } while (0)
+#endif
+
 struct Gemm2Args {
   CUtensorMap map_a0, map_a1, map_b;
   CUtensorMap map_d, map_res;  // (c, x, y, n) views of the output / residual, box = 32 columns x one pixel box
@@ -106,8 +123,10 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
   const int cbt = g.cb0 + g.cb1;
   const bool two_acc = args.bn * args.nsub <= ACC_COLS;  // room for two accumulator stages in the 512 TMEM columns
 
+  if (threadIdx.x == 0) CPD_STAMP(0);
   pdl_launch_dependents();
   cluster_sync_all();  // both CTAs of the pair are resident before the pair-wide TMEM allocation
+  if (threadIdx.x == 0) CPD_STAMP(1);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&args.map_a0);
     tma_prefetch_desc(&args.map_b);
@@ -136,6 +155,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
+  if (threadIdx.x == 0) CPD_STAMP(2);
 
   if (warp == 0) {
     // ================= TMA producer (both CTAs) =================
@@ -200,6 +220,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
               tma_load_2d_pair(sa + A_BYTES + sub * (bn_half * 128), &args.map_b, &full_bar[stage], kt * BK, b_row + sub * args.bn);
           }
           __syncwarp();
+          if (kt == k0 && t == cluster_id && lane == 0) CPD_STAMP(3);
           if (++stage == stages) {
             stage = 0;
             phase ^= 1;
@@ -245,6 +266,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
         for (int kt = k0; kt < k1; ++kt) {
           mbar_wait(&full_bar[stage], phase, 2);
           tc_fence_after();
+          if (kt == k0 && t == cluster_id && lane == 0) CPD_STAMP(4);
           const uint64_t db = da + b_off;
           if (elect_one()) {
             // +2 in the address field = 32 bytes = 16 elements along K inside the 128-byte swizzle atom
@@ -273,6 +295,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
         }
         if (elect_one()) umma_commit_pair(&tmem_full[acc], (uint16_t)(3u << (2 * pair)));  // accumulator complete, both CTAs of the pair
         __syncwarp();
+        if (t == cluster_id && lane == 0) CPD_STAMP(5);
       }
     }
   } else if (warp >= FIRST_EPI_WARP) {
@@ -321,10 +344,21 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
       const RowCoord rc = row_coord(g, m_tile, r);
       const int n_img_row = rc.n < g.n_img ? rc.n : g.n_img - 1;
       const float* rv = args.rowvec ? args.rowvec + (int64_t)n_img_row * g.rowvec_stride : nullptr;
+      {  // pull this tile's bias / time-embedding lines into L1 while the main loop runs (first-touch latency ~1 us)
+        const int bias_w = geglu ? bn : out_w;        // floats of bias per tile
+        const int lines = (bias_w + 31) >> 5;         // 128-byte lines
+        const int col_first = n_tile * bias_w;
+        if (r < lines && col_first + r * 32 < g.n_out) {
+          if (args.bias) asm volatile("prefetch.global.L1 [%0];" ::"l"(args.bias + col_first + r * 32));
+        }
+        if (rv && (lane < lines) && col_first + lane * 32 < g.n_out)
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(rv + col_first + lane * 32));
+      }
       const int acc = two_acc ? (it & 1) : 0;
       const uint32_t acc_phase = (uint32_t)((two_acc ? (it >> 1) : it) & 1);
       mbar_wait(&tmem_full[acc], acc_phase, 3);
       tc_fence_after();
+      if (t == cluster_id && leader && grp == 0) CPD_STAMP(6);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS);
 
       if (splits > 1) {
@@ -463,6 +497,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
             }
           }
           bulk_commit_group();
+          if (t == cluster_id && grp == 0 && ch == c_lo) CPD_STAMP(7);
         }
       }
       if (c_lo == c_hi) {  // this group has no chunk in the tile (single-chunk tiles): still release the accumulator
@@ -471,15 +506,20 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
         if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], leader_crank);
       }
     }
-    if (leader) bulk_wait_group<0>();  // all stores complete before the CTA (and its shared memory) goes away
+    // the staging buffers must outlive the TMA engine's READS of them; the global writes themselves are complete (and
+    // visible to the next kernel) at grid completion like any other store
+    if (leader) bulk_wait_group_read<0>();
+    if (leader && grp == 0) CPD_STAMP(8);
   }
 
   __syncwarp();
   tc_fence_before();
   cluster_sync_all();
+  if (threadIdx.x == 0) CPD_STAMP(9);
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc_pair(tmem_base, 512);
+    if (lane == 0) CPD_STAMP(10);
   }
 }
 
@@ -588,6 +628,12 @@ cpd_status launch2(const Gemm2Args& args, int smem_bytes, cudaStream_t stream) {
 }
 
 }  // namespace
+
+#ifdef CPD_TIMELINE
+extern "C" int cpd_debug_gemm_timeline(unsigned long long* host16) {
+  return (int)cudaMemcpyFromSymbol(host16, cpd_dbg_ts, sizeof(unsigned long long) * 16);
+}
+#endif
 
 cpd_status cpd_gemm_conv_2cta(const cpd_gemm_params* p, void* stream) {
   Gemm2Args args;

@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""Phase timeline of one gemm2_kernel launch (needs a TIMELINE=1 build: make -C complex_prompt_diffusion_b200/csrc clean all TIMELINE=1)."""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+NAMES = ["entry", "cluster sync 1", "setup done (alloc, barriers, sync 2)", "first TMA issued", "first stage landed", "last MMA committed",
+         "epilogue: accumulator ready", "first TMA store issued", "stores read", "cluster sync 3", "dealloc"]
+
+
+def main():
+    from complex_prompt_diffusion_b200 import ops
+    ops.AUTOTUNE = False
+    lib = ops.load()
+    for (M, N, K, v) in [(256, 160, 64, 160), (256, 160, 640, 160), (16384, 640, 640, 160)]:
+        a = torch.randn(M, K, device="cuda").half()
+        w = torch.randn(N, K, device="cuda").half()
+        o = torch.empty(M, N, device="cuda", dtype=torch.float16)
+        bias = torch.randn(N, device="cuda")
+        for _ in range(5):
+            ops.gemm_conv(a, w, o, n_img=1, h=1, w=M, c0=K, n_out=N, bias=bias, variant=v)
+        torch.cuda.synchronize()
+        ts = (C.c_ulonglong * 16)()
+        lib.cpd_debug_gemm_timeline(ts)
+        print(f"M={M} N={N} K={K}:")
+        for i, nm in enumerate(NAMES):
+            print(f"   {nm:40s} +{(ts[i] - ts[0]) / 1e3:7.2f} us")
+
+
+if __name__ == "__main__":
+    main()

@@ -6,6 +6,8 @@
 //
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 = softmax / correction /
 // epilogue (128 threads <-> 128 query rows).
+#include <stdlib.h>
+
 #include "../../include/cpd_b200.h"
 #include "common.cuh"
 
@@ -265,7 +267,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) attention_kernel(const __grid_
 
 }  // namespace
 
-cpd_status cpd_attention_2tile(const cpd_attn_params* p, void* stream);  // attention_umma2.cu
+cpd_status cpd_attention_2tile(const cpd_attn_params* p, void* stream);       // attention_umma2.cu
+cpd_status cpd_attention_persistent(const cpd_attn_params* p, void* stream);  // attention_umma3.cu
 
 extern "C" cpd_status cpd_attention(const cpd_attn_params* p, void* stream) {
   CPD_REQUIRE(p && p->q && p->k && p->vt && p->o, "cpd_attention: null pointer");
@@ -275,6 +278,15 @@ extern "C" cpd_status cpd_attention(const cpd_attn_params* p, void* stream) {
   CPD_REQUIRE(((uintptr_t)p->o & 15) == 0, "cpd_attention: o must be 16-byte aligned");
   CPD_REQUIRE(p->d_head >= 0 && p->d_head <= p->dpad, "cpd_attention: d_head=%d must be in [0, dpad=%d]", p->d_head, p->dpad);
   if (p->d_head > 0) {  // two query tiles per CTA, P in tensor memory; falls through when the shape is outside its domain
+    static int persist = -1;  // CPD_ATTN_PERSIST=0: one CTA per work item (attention_umma2.cu) instead of the persistent kernel
+    if (persist < 0) {
+      const char* e = getenv("CPD_ATTN_PERSIST");
+      persist = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (persist) {
+      const cpd_status st3 = cpd_attention_persistent(p, stream);
+      if (st3 != CPD_ERR_UNSUPPORTED) return st3;
+    }
     const cpd_status st2 = cpd_attention_2tile(p, stream);
     if (st2 != CPD_ERR_UNSUPPORTED) return st2;
   }

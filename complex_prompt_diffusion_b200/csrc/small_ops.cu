@@ -252,7 +252,7 @@ extern "C" cpd_status cpd_conv_in(const float* x, int n, int cin, int h, int w, 
   const size_t shm = (size_t)9 * cin * cout * sizeof(float);
   CPD_REQUIRE(shm <= 48 * 1024, "cpd_conv_in: cin=%d x cout=%d weights do not fit 48 KB of shared memory", cin, cout);
   int64_t blocks = (total + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > 148 * 2) blocks = 148 * 2;  // each block stages the 9 x cin x cout weights once: few, long-lived blocks
   CPD_CUDA_CHECK(cpd_launch(conv_in_kernel, dim3((unsigned)blocks), dim3(256), shm, (cudaStream_t)stream, x, n, cin, h, w, (const bf16*)wt, bias, cout, scale, scale_ptr,
                                                                       rows_per_image, act_fp16, (bf16*)out));
   CPD_CUDA_CHECK(cudaGetLastError());

@@ -6,14 +6,35 @@
 namespace {
 
 constexpr int GROUPS = 32;
+// SiLU with one MUFU op: x * sigmoid(x) = h + h * tanh(h), h = x / 2 (tanh.approx.f32: |error| ~ 2^-11, the size of the
+// 16-bit output rounding; exp + rcp would keep the MUFU pipe busy twice as long and bound the apply pass).
+__device__ __forceinline__ float silu_tanh_f(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+constexpr int RING = 8;  // per-thread cp.async ring depth of the GroupNorm kernels (16-byte slots)
+
+// Per-thread asynchronous 16-byte copies global -> shared (LDGSTS): RING loads in flight per thread at no register cost.  A
+// thread only ever reads the slots it filled itself, so no barrier is involved - cp.async.wait_group orders the read.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ---- GroupNorm pass 1: per-(image, pixel chunk, group) sum / sum of squares ----------------------------------------
 // grid = (chunks, n_img).  Thread t owns channel vector (t % vec_per_px) and pixel lane (t / vec_per_px).  No atomics
 // anywhere: per-thread partials go to shared memory, are summed over the pixel lanes in a fixed order, reduced per group in
 // fp64 and written to partial[n][chunk][group][2]; pass 2 sums the chunks in a fixed order.  Results are bit-reproducible.
+template <bool F16>
 __global__ void __launch_bounds__(512, 2) gn_stats_kernel(const bf16* __restrict__ a0, const bf16* __restrict__ a1, int c0,
-                                                          int c1, int hw, int px_per_block, int f16, double* __restrict__ partial) {
-  extern __shared__ float sh[];  // [lanes][2][C]
+                                                          int c1, int hw, int px_per_block, double* __restrict__ partial) {
+  extern __shared__ __align__(16) float sh_raw[];  // ring[RING][blockDim.x] of uint4, then partial sums [lanes][2][C]
+  uint4* ring = reinterpret_cast<uint4*>(sh_raw) + threadIdx.x;
+  float* sh = sh_raw + (size_t)RING * blockDim.x * 4;
   pdl_launch_dependents();
   pdl_wait();
   const int C = c0 + c1;
@@ -32,31 +53,31 @@ __global__ void __launch_bounds__(512, 2) gn_stats_kernel(const bf16* __restrict
     for (int e = 0; e < 8; ++e) s[e] = ss[e] = 0.f;
     const int p0 = blockIdx.x * px_per_block;
     const int p1 = min(p0 + px_per_block, hw);
-    const bf16* base = src + (int64_t)n * hw * cs + coff;
-    int p = p0 + pl;
-    for (; p + 7 * lanes < p1; p += 8 * lanes) {  // 8 independent 16-byte loads in flight per thread
-      uint4 v[8];
+    const bf16* base = src + ((int64_t)n * hw + p0 + pl) * cs + coff;
+    const int64_t step = (int64_t)lanes * cs;
+    const int np = (p1 - p0 - pl + lanes - 1) / lanes;  // pixels of this thread
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)(p + j * lanes) * cs));
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint32_t u[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = unpack_act2(u[e], f16 != 0);
-          s[2 * e] += f.x; ss[2 * e] += f.x * f.x;
-          s[2 * e + 1] += f.y; ss[2 * e + 1] += f.y * f.y;
-        }
-      }
+    for (int j = 0; j < RING; ++j) {
+      if (j < np) cp_async16(ring + j * blockDim.x, base + j * step);
+      cp_async_commit();
     }
-    for (; p < p1; p += lanes) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)p * cs));
-      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+    for (int j0 = 0; j0 < np; j0 += RING) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = unpack_act2(u[e], f16 != 0);
-        s[2 * e] += f.x; ss[2 * e] += f.x * f.x;
-        s[2 * e + 1] += f.y; ss[2 * e + 1] += f.y * f.y;
+      for (int jj = 0; jj < RING; ++jj) {
+        const int j = j0 + jj;
+        cp_async_wait<RING - 1>();
+        if (j < np) {
+          const uint4 v = ring[jj * blockDim.x];
+          if (j + RING < np) cp_async16(ring + jj * blockDim.x, base + (j + RING) * step);
+          const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = unpack_act2(u[e], F16);
+            s[2 * e] += f.x; ss[2 * e] += f.x * f.x;
+            s[2 * e + 1] += f.y; ss[2 * e + 1] += f.y * f.y;
+          }
+        }
+        cp_async_commit();
       }
     }
     float* mine = sh + (size_t)pl * 2 * C;
@@ -67,88 +88,119 @@ __global__ void __launch_bounds__(512, 2) gn_stats_kernel(const bf16* __restrict
     }
   }
   __syncthreads();
-  const int cpg = C / GROUPS;
-  if (threadIdx.x < GROUPS) {
-    double S = 0.0, SS = 0.0;
-    for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) {
-      for (int l = 0; l < lanes; ++l) {  // fixed order: lane 0, 1, ...
-        S += (double)sh[(size_t)l * 2 * C + c];
-        SS += (double)sh[(size_t)l * 2 * C + C + c];
-      }
-    }
-    double* out = partial + (((int64_t)n * gridDim.x + blockIdx.x) * GROUPS + threadIdx.x) * 2;
-    out[0] = S;
-    out[1] = SS;
+  // Block reduction in a fixed order: (1) fp32 sum over the pixel lanes per (statistic, channel), (2) fp64 sum over the
+  // channels of a group by one thread per (group, statistic).
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float acc = sh[i];
+    for (int l = 1; l < lanes; ++l) acc += sh[(size_t)l * 2 * C + i];
+    sh[i] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * GROUPS) {
+    const int cpg = C / GROUPS;
+    const int g = threadIdx.x >> 1, st = threadIdx.x & 1;
+    const float* v = sh + st * C + g * cpg;
+    double acc = 0.0;
+    for (int c = 0; c < cpg; ++c) acc += (double)v[c];
+    partial[(((int64_t)n * gridDim.x + blockIdx.x) * GROUPS + g) * 2 + st] = acc;
   }
 }
 
 // ---- GroupNorm pass 2: normalise, affine, optional SiLU, write bf16 ---------------------------------
+template <bool F16>
 __global__ void __launch_bounds__(512, 2) gn_apply_kernel(const bf16* __restrict__ a0, const bf16* __restrict__ a1, int c0,
                                                        int c1, int hw, int px_per_block, const double* __restrict__ partial,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                       float eps, int silu, int f16, bf16* __restrict__ out) {
-  extern __shared__ float sh[];  // scale[C], shift[C]
+                                                       float eps, int silu, bf16* __restrict__ out) {
+  extern __shared__ __align__(16) float sh_raw[];  // ring[RING][blockDim.x] of uint4, scale[C], shift[C], group stats
+  uint4* ring = reinterpret_cast<uint4*>(sh_raw) + threadIdx.x;
+  float* sh = sh_raw + (size_t)RING * blockDim.x * 4;
   pdl_launch_dependents();
   pdl_wait();
   const int C = c0 + c1;
   const int vec_per_px = C / 8;
   const int lanes = blockDim.x / vec_per_px;
   const int n = blockIdx.y;
-  const int cpg = C / GROUPS;
-  const double cnt = (double)hw * cpg;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
-    double S = 0.0, SS = 0.0;
-    for (int k = 0; k < (int)gridDim.x; ++k) {  // chunk partials of pass 1, fixed order
-      const double* pp = partial + (((int64_t)n * gridDim.x + k) * GROUPS + g) * 2;
-      S += pp[0];
-      SS += pp[1];
-    }
-    const double mean = S / cnt;
-    double var = SS / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    const float sc = rstd * gamma[c];
-    sh[c] = sc;
-    sh[C + c] = beta[c] - (float)mean * sc;
-  }
-  __syncthreads();
+  // The data loads do not depend on the statistics: fill the ring first, reduce the chunk partials while they fly.
   const int cv = threadIdx.x % vec_per_px;
   const int pl = threadIdx.x / vec_per_px;
-  if (pl >= lanes) return;
   const int ch = cv * 8;
   const bf16* src;
   int cs, coff;
   if (ch < c0) { src = a0; cs = c0; coff = ch; } else { src = a1; cs = c1; coff = ch - c0; }
+  const int p0 = blockIdx.x * px_per_block;
+  const int p1 = min(p0 + px_per_block, hw);
+  const bf16* base = src + ((int64_t)n * hw + p0 + pl) * cs + coff;
+  const int64_t step = (int64_t)lanes * cs;
+  const int np = pl < lanes ? (p1 - p0 - pl + lanes - 1) / lanes : 0;  // pixels of this thread
+#pragma unroll
+  for (int j = 0; j < RING; ++j) {
+    if (j < np) cp_async16(ring + j * blockDim.x, base + j * step);
+    cp_async_commit();
+  }
+  const int cpg = C / GROUPS;
+  const double cnt = (double)hw * cpg;
+  {  // chunk partials of pass 1: one warp per group at a time, lanes over chunks, fixed butterfly (bit-reproducible)
+    float* gstat = sh + 2 * C;  // [GROUPS][2]: mean, rstd
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int g = warp; g < GROUPS; g += nwarps) {
+      double S = 0.0, SS = 0.0;
+      for (int k = lane; k < (int)gridDim.x; k += 32) {
+        const double2 pp = *reinterpret_cast<const double2*>(partial + (((int64_t)n * gridDim.x + k) * GROUPS + g) * 2);
+        S += pp.x;
+        SS += pp.y;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        S += __shfl_xor_sync(0xffffffffu, S, o);
+        SS += __shfl_xor_sync(0xffffffffu, SS, o);
+      }
+      if (lane == 0) {
+        const double mean = S / cnt;
+        double var = SS / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        gstat[2 * g] = (float)mean;
+        gstat[2 * g + 1] = (float)(1.0 / sqrt(var + (double)eps));
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const int g = (int)__fdividef((float)c + 0.5f, (float)cpg);  // exact for c < 2^20
+      const float sc = gstat[2 * g + 1] * gamma[c];
+      sh[c] = sc;
+      sh[C + c] = beta[c] - gstat[2 * g] * sc;
+    }
+  }
+  __syncthreads();
+  if (pl >= lanes) return;
   float sc[8], sf[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) { sc[e] = sh[ch + e]; sf[e] = sh[C + ch + e]; }
-  const int p0 = blockIdx.x * px_per_block;
-  const int p1 = min(p0 + px_per_block, hw);
-  const bf16* base = src + (int64_t)n * hw * cs + coff;
-  bf16* obase = out + (int64_t)n * hw * C + ch;
-  auto apply_one = [&](const uint4& v, int p) {
-    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
-    uint32_t o[4];
+  bf16* obase = out + ((int64_t)n * hw + p0 + pl) * C + ch;
+  const int64_t ostep = (int64_t)lanes * C;
+  for (int j0 = 0; j0 < np; j0 += RING) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 f = unpack_act2(u[e], f16 != 0);
-      float y0 = f.x * sc[2 * e] + sf[2 * e];
-      float y1 = f.y * sc[2 * e + 1] + sf[2 * e + 1];
-      if (silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
-      o[e] = pack_act2(y0, y1, f16 != 0);
+    for (int jj = 0; jj < RING; ++jj) {
+      const int j = j0 + jj;
+      cp_async_wait<RING - 1>();
+      if (j < np) {
+        const uint4 v = ring[jj * blockDim.x];
+        if (j + RING < np) cp_async16(ring + jj * blockDim.x, base + (j + RING) * step);
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack_act2(u[e], F16);
+          float y0 = f.x * sc[2 * e] + sf[2 * e];
+          float y1 = f.y * sc[2 * e + 1] + sf[2 * e + 1];
+          if (silu) { y0 = silu_tanh_f(y0); y1 = silu_tanh_f(y1); }
+          o[e] = pack_act2(y0, y1, F16);
+        }
+        *reinterpret_cast<uint4*>(obase + j * ostep) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+      cp_async_commit();
     }
-    *reinterpret_cast<uint4*>(obase + (int64_t)p * C) = make_uint4(o[0], o[1], o[2], o[3]);
-  };
-  int p = p0 + pl;
-  for (; p + 7 * lanes < p1; p += 8 * lanes) {  // 8 independent 16-byte loads in flight per thread
-    uint4 v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)(p + j * lanes) * cs));
-#pragma unroll
-    for (int j = 0; j < 8; ++j) apply_one(v[j], p + j * lanes);
   }
-  for (; p < p1; p += lanes) apply_one(__ldg(reinterpret_cast<const uint4*>(base + (int64_t)p * cs)), p);
 }
 
 // ---- LayerNorm: one warp per R rows (all loads of the R rows issued before the first use), rows in registers -----
@@ -223,6 +275,89 @@ __global__ void __launch_bounds__(256, 4) layernorm_kernel(const bf16* __restric
   }
 }
 
+// ---- LayerNorm, sub-warp layout: LPR lanes share one row, VPL 16-byte vectors per lane (c = 8 * LPR * VPL), 32 / LPR rows
+// per warp and pass, R passes whose loads are all issued before the first use (R * VPL * 16 bytes in flight per lane, every
+// lane busy - the one-warp-per-row layout leaves 3/4 of the lanes idle on the second vector at c = 320).
+template <int LPR, int VPL, int R>
+__global__ void __launch_bounds__(256, 3) layernorm_sub_kernel(const bf16* __restrict__ x, int rows, int c,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               float eps, int f16, bf16* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  constexpr int RPW = 32 / LPR;  // rows per warp and pass
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR;
+  const int row0 = warp * (RPW * R) + lane / LPR;
+  if (warp * (RPW * R) >= rows) return;
+  uint4 raw[R][VPL];
+#pragma unroll
+  for (int rr = 0; rr < R; ++rr) {
+    const int row = row0 + rr * RPW;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      raw[rr][i] = make_uint4(0, 0, 0, 0);
+      if (row < rows) raw[rr][i] = __ldg(reinterpret_cast<const uint4*>(x + (int64_t)row * c + (sub + i * LPR) * 8));
+    }
+  }
+  float mean[R], rstd[R];
+  const float inv_c = 1.0f / (float)c;
+#pragma unroll
+  for (int rr = 0; rr < R; ++rr) {
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const uint32_t w[4] = {raw[rr][i].x, raw[rr][i].y, raw[rr][i].z, raw[rr][i].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_act2(w[e], f16 != 0);
+        sum += f.x + f.y;
+      }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    mean[rr] = sum * inv_c;
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const uint32_t w[4] = {raw[rr][i].x, raw[rr][i].y, raw[rr][i].z, raw[rr][i].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_act2(w[e], f16 != 0);
+        const float d0 = f.x - mean[rr], d1 = f.y - mean[rr];
+        var += d0 * d0 + d1 * d1;
+      }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    rstd[rr] = rsqrtf(var * inv_c + eps);
+  }
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int col = (sub + i * LPR) * 8;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + col));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + col + 4));
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) {
+      const int row = row0 + rr * RPW;
+      if (row >= rows) continue;
+      const uint32_t w[4] = {raw[rr][i].x, raw[rr][i].y, raw[rr][i].z, raw[rr][i].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_act2(w[e], f16 != 0);
+        o[e] = pack_act2((f.x - mean[rr]) * rstd[rr] * gg[2 * e] + bb[2 * e], (f.y - mean[rr]) * rstd[rr] * gg[2 * e + 1] + bb[2 * e + 1],
+                         f16 != 0);
+      }
+      *reinterpret_cast<uint4*>(out + (int64_t)row * c + col) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" cpd_status cpd_groupnorm(const void* a0, const void* a1, int c0, int c1, int n_img, int hw, const float* gamma,
@@ -250,18 +385,28 @@ extern "C" cpd_status cpd_groupnorm(const void* a0, const void* a1, int c0, int 
     px_per_block = (hw + CPD_GN_MAX_CHUNKS - 1) / CPD_GN_MAX_CHUNKS;
     chunks = (hw + px_per_block - 1) / px_per_block;
   }
-  const size_t shm = sizeof(float) * 2 * C;
-  const size_t shm_stats = sizeof(float) * 2 * C * lanes;
-  CPD_REQUIRE(shm_stats <= 160 * 1024, "cpd_groupnorm: C=%d needs %zu bytes of shared memory", C, shm_stats);
+  const size_t ring_bytes = (size_t)RING * threads * 16;
+  const size_t shm = ring_bytes + sizeof(float) * (2 * C + 2 * GROUPS);
+  const size_t shm_stats = ring_bytes + sizeof(float) * 2 * C * lanes;
+  CPD_REQUIRE(shm_stats <= 160 * 1024 && shm <= 160 * 1024, "cpd_groupnorm: C=%d needs %zu bytes of shared memory", C, shm_stats);
   static bool cfg = false;
   if (!cfg) {
-    CPD_CUDA_CHECK(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CPD_CUDA_CHECK(cudaFuncSetAttribute(gn_stats_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CPD_CUDA_CHECK(cudaFuncSetAttribute(gn_stats_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CPD_CUDA_CHECK(cudaFuncSetAttribute(gn_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CPD_CUDA_CHECK(cudaFuncSetAttribute(gn_apply_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     cfg = true;
   }
-  CPD_CUDA_CHECK(cpd_launch(gn_stats_kernel, dim3(dim3(chunks, n_img)), dim3(threads), shm_stats, s, (const bf16*)a0, (const bf16*)a1, c0, c1, hw, px_per_block, act_fp16, stats));
-  CPD_CUDA_CHECK(cudaGetLastError());
-  CPD_CUDA_CHECK(cpd_launch(gn_apply_kernel, dim3(dim3(chunks, n_img)), dim3(threads), shm, s, (const bf16*)a0, (const bf16*)a1, c0, c1, hw, px_per_block, stats,
-                                                           gamma, beta, eps, silu, act_fp16, (bf16*)out));
+  const dim3 grid(chunks, n_img);
+  if (act_fp16) {
+    CPD_CUDA_CHECK(cpd_launch(gn_stats_kernel<true>, grid, dim3(threads), shm_stats, s, (const bf16*)a0, (const bf16*)a1, c0, c1, hw, px_per_block, stats));
+    CPD_CUDA_CHECK(cpd_launch(gn_apply_kernel<true>, grid, dim3(threads), shm, s, (const bf16*)a0, (const bf16*)a1, c0, c1, hw, px_per_block,
+                              (const double*)stats, gamma, beta, eps, silu, (bf16*)out));
+  } else {
+    CPD_CUDA_CHECK(cpd_launch(gn_stats_kernel<false>, grid, dim3(threads), shm_stats, s, (const bf16*)a0, (const bf16*)a1, c0, c1, hw, px_per_block, stats));
+    CPD_CUDA_CHECK(cpd_launch(gn_apply_kernel<false>, grid, dim3(threads), shm, s, (const bf16*)a0, (const bf16*)a1, c0, c1, hw, px_per_block,
+                              (const double*)stats, gamma, beta, eps, silu, (bf16*)out));
+  }
   CPD_CUDA_CHECK(cudaGetLastError());
   return CPD_OK;
 }
@@ -275,9 +420,16 @@ extern "C" cpd_status cpd_layernorm(const void* x, int rows, int c, const float*
   cudaStream_t s = (cudaStream_t)stream;
   const int nvec = c / 8;
   auto blocks = [&](int r_per_warp) { return (rows + 8 * r_per_warp - 1) / (8 * r_per_warp); };
-  if (nvec <= 64) CPD_CUDA_CHECK(cpd_launch(layernorm_kernel<2, 4>, dim3(blocks(4)), dim3(256), 0, s, (const bf16*)x, rows, c, gamma, beta, eps, act_fp16, (bf16*)out));
+#define CPD_LN_SUB(LPR, VPL, R)                                                                                                  \
+  CPD_CUDA_CHECK(cpd_launch(layernorm_sub_kernel<LPR, VPL, R>, dim3(blocks((32 / LPR) * R)), dim3(256), 0, s, (const bf16*)x, rows, c, \
+                            gamma, beta, eps, act_fp16, (bf16*)out))
+  if (nvec == 40) CPD_LN_SUB(8, 5, 2);        // c = 320
+  else if (nvec == 80) CPD_LN_SUB(16, 5, 2);  // c = 640
+  else if (nvec == 160) CPD_LN_SUB(32, 5, 2);  // c = 1280
+  else if (nvec <= 64) CPD_CUDA_CHECK(cpd_launch(layernorm_kernel<2, 4>, dim3(blocks(4)), dim3(256), 0, s, (const bf16*)x, rows, c, gamma, beta, eps, act_fp16, (bf16*)out));
   else if (nvec <= 160) CPD_CUDA_CHECK(cpd_launch(layernorm_kernel<5, 2>, dim3(blocks(2)), dim3(256), 0, s, (const bf16*)x, rows, c, gamma, beta, eps, act_fp16, (bf16*)out));
   else CPD_CUDA_CHECK(cpd_launch(layernorm_kernel<8, 1>, dim3(blocks(1)), dim3(256), 0, s, (const bf16*)x, rows, c, gamma, beta, eps, act_fp16, (bf16*)out));
+#undef CPD_LN_SUB
   CPD_CUDA_CHECK(cudaGetLastError());
   return CPD_OK;
 }

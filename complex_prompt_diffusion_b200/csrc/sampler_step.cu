@@ -19,63 +19,101 @@ struct StepArgs {
 
 __device__ __forceinline__ float h_round(float v) { return __half2float(__float2half_rn(v)); }
 
-template <int DT>
-__device__ __forceinline__ void load4(const void* base, int64_t idx, float (&out)[4]) {
-  if (DT == CPD_F32) {
-    float4 v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx));
-    out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
-  } else if (DT == CPD_F16) {
-    uint2 v = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(base) + idx));
-    float2 a = __half22float2(*reinterpret_cast<__half2*>(&v.x));
-    float2 b = __half22float2(*reinterpret_cast<__half2*>(&v.y));
-    out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
-  } else {
-    uint2 v = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(base) + idx));
-    float2 a = unpack_bf16x2(v.x);
-    float2 b = unpack_bf16x2(v.y);
-    out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
+// VEC consecutive elements of one eps row, kept as raw 32-bit words (fp32: one element per word, 16-bit: two per word) so a
+// row costs VEC or VEC/2 registers until it is used: one 16-byte load for fp32 x 4 and for 16-bit x 8.
+template <int DT, int VEC>
+struct EpsRow {
+  static constexpr int W = (DT == CPD_F32) ? VEC : VEC / 2;
+  uint32_t w[W];
+  __device__ __forceinline__ void load(const void* base, int64_t idx) {
+    if (DT == CPD_F32) {
+#pragma unroll
+      for (int q = 0; q < VEC / 4; ++q) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(base) + idx) + q);
+        w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+      }
+    } else if (VEC == 8) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(base) + idx));
+      w[0] = v.x; w[1] = v.y; w[W - 2] = v.z; w[W - 1] = v.w;
+    } else {
+      const uint2 v = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(base) + idx));
+      w[0] = v.x; w[1] = v.y;
+    }
+  }
+  __device__ __forceinline__ __half2 half2_at(int q) const {  // elements 2q, 2q+1 rounded to fp16
+    if (DT == CPD_F32) return __floats2half2_rn(__uint_as_float(w[2 * q]), __uint_as_float(w[2 * q + 1]));
+    if (DT == CPD_F16) { uint32_t u = w[q]; return *reinterpret_cast<__half2*>(&u); }
+    const float2 f = unpack_bf16x2(w[q]);
+    return __floats2half2_rn(f.x, f.y);
+  }
+  __device__ __forceinline__ float at(int j) const {
+    if (DT == CPD_F32) return __uint_as_float(w[j]);
+    if (DT == CPD_F16) { uint32_t u = w[j >> 1]; const __half2 h = *reinterpret_cast<__half2*>(&u); return (j & 1) ? __high2float(h) : __low2float(h); }
+    const float2 f = unpack_bf16x2(w[j >> 1]);
+    return (j & 1) ? f.y : f.x;
+  }
+};
+
+template <int VEC>
+__device__ __forceinline__ void load_f32(const float* p, float (&out)[VEC]) {
+  if (VEC < 4) return;
+#pragma unroll
+  for (int q = 0; q < VEC / 4; ++q) {
+    const float4 v = *(reinterpret_cast<const float4*>(p) + q);
+    out[4 * q] = v.x; out[4 * q + 1] = v.y; out[4 * q + 2] = v.z; out[4 * q + 3] = v.w;
   }
 }
+template <int VEC>
+__device__ __forceinline__ void store_f32(float* p, const float (&v)[VEC]) {
+#pragma unroll
+  for (int q = 0; q < VEC / 4; ++q) *(reinterpret_cast<float4*>(p) + q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
 
-template <int DT>
-__global__ void __launch_bounds__(256, 4) sampler_step_kernel(const __grid_constant__ StepArgs args) {
+// One thread owns VEC consecutive latent elements of one image (VEC = 4 for fp32 eps, 8 for 16-bit eps when hw % 8 == 0, so
+// every eps row is fetched with 16-byte loads).
+template <int DT, int VEC>
+__global__ void __launch_bounds__(256, VEC == 8 ? 3 : 4) sampler_step_kernel(const __grid_constant__ StepArgs args) {
   pdl_launch_dependents();
   pdl_wait();
   const cpd_step_params& p = args.p;
   const int L = 4 * p.hw;
-  const int vec_per_img = L / 4;
+  const int vec_per_img = L / VEC;
   const int64_t total = (int64_t)p.n_images * vec_per_img;
+  constexpr int H2 = VEC / 2;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (int64_t)gridDim.x * blockDim.x) {
     const int b = (int)(v / vec_per_img);
-    const int i = (int)(v - (int64_t)b * vec_per_img) * 4;  // element offset inside the image
+    const int i = (int)(v - (int64_t)b * vec_per_img) * VEC;  // element offset inside the image
     const int pix = i % p.hw;
     const int64_t ebase = (int64_t)b * p.eps_image_stride + i;
     // Issue every independent load of this vector before the first use (memory-level parallelism: the kernel is a pure
     // HBM stream): x, the 2M history / ancestral noise, the unconditional row and the sub-prompt rows four at a time.
-    const float4 xv = *reinterpret_cast<const float4*>(p.x + (int64_t)b * L + i);
-    float4 aux = make_float4(0.f, 0.f, 0.f, 0.f);  // old_denoised (2M) or noise (ancestral)
+    float x[VEC], aux[VEC];  // aux: old_denoised (2M) or noise (ancestral)
+    load_f32<VEC>(p.x + (int64_t)b * L + i, x);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) aux[j] = 0.f;
     if (p.sampler == CPD_DPMPP_2M) {
-      if (!p.dpm_first) aux = *reinterpret_cast<const float4*>(p.old_denoised + (int64_t)b * L + i);
+      if (!p.dpm_first) load_f32<VEC>(p.old_denoised + (int64_t)b * L + i, aux);
     } else if (p.sampler == CPD_EULER_ANCESTRAL) {
-      aux = __ldg(reinterpret_cast<const float4*>(p.noise + (int64_t)b * L + i));
+      load_f32<VEC>(p.noise + (int64_t)b * L + i, aux);
     }
     // The fp16 delta (denoiser.py:450-460) runs on packed half2: for fp16 operands HSUB2 / HMUL2 / HADD2 (one rounding) give
     // bit-identical results to "compute in fp32, round to fp16" (products of two halves are exact in fp32; sums are exact
     // unless the smaller operand is below a quarter ulp of the larger, where both roundings return the larger).  The _rn
     // intrinsics keep ptxas from contracting mul + add into a single-rounding HFMA2.
-    float eu[4];
-    load4<DT>(p.eps, ebase, eu);
-    const __half2 hu01 = __floats2half2_rn(eu[0], eu[1]), hu23 = __floats2half2_rn(eu[2], eu[3]);
-    __half2 sum01 = __floats2half2_rn(0.f, 0.f), sum23 = sum01;
+    EpsRow<DT, VEC> eu;
+    eu.load(p.eps, ebase);
+    __half2 sum[H2];
+#pragma unroll
+    for (int q = 0; q < H2; ++q) sum[q] = __floats2half2_rn(0.f, 0.f);
     for (int k0 = 0; k0 < p.n_sub; k0 += 4) {
-      float ek4[4][4];
-      float4 m4[4];
+      EpsRow<DT, VEC> ek4[4];
+      float m4[4][VEC == 4 ? 4 : 1];  // spatial masks: prefetched with the rows (VEC 4) or read at use (VEC 8: registers)
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
         const int k = k0 + kk;
         if (k < p.n_sub) {
-          load4<DT>(p.eps, ebase + (int64_t)(k + 1) * p.eps_row_stride, ek4[kk]);
-          if (p.masks[k] != nullptr) m4[kk] = __ldg(reinterpret_cast<const float4*>(p.masks[k] + pix));
+          ek4[kk].load(p.eps, ebase + (int64_t)(k + 1) * p.eps_row_stride);
+          if (VEC == 4 && p.masks[k] != nullptr) load_f32<VEC == 4 ? 4 : 1>(p.masks[k] + pix, m4[kk]);
         }
       }
 #pragma unroll
@@ -84,63 +122,51 @@ __global__ void __launch_bounds__(256, 4) sampler_step_kernel(const __grid_const
         if (k < p.n_sub) {
           // half(m) * half(w), rounded to fp16 (denoiser.py:451-452); weights live in the kernel-parameter constant bank
           const __half w_hk = __float2half_rn(p.weights[k]);
-          __half2 mw01, mw23;
-          if (p.masks[k] != nullptr) {
-            const __half2 wk2 = __half2half2(w_hk);
-            mw01 = __hmul2_rn(__floats2half2_rn(m4[kk].x, m4[kk].y), wk2);
-            mw23 = __hmul2_rn(__floats2half2_rn(m4[kk].z, m4[kk].w), wk2);
-          } else {
-            mw01 = mw23 = __half2half2(__hmul_rn(__float2half_rn(p.mask_scalar[k]), w_hk));
-          }
-          const __half2 t01 = __hmul2_rn(mw01, __hsub2_rn(__floats2half2_rn(ek4[kk][0], ek4[kk][1]), hu01));
-          const __half2 t23 = __hmul2_rn(mw23, __hsub2_rn(__floats2half2_rn(ek4[kk][2], ek4[kk][3]), hu23));
-          if (k == 0) {
-            sum01 = t01;
-            sum23 = t23;
-          } else {
-            sum01 = __hadd2_rn(sum01, t01);
-            sum23 = __hadd2_rn(sum23, t23);
+          const __half2 wk2 = __half2half2(w_hk);
+          const __half2 mw_s = __half2half2(__hmul_rn(__float2half_rn(p.mask_scalar[k]), w_hk));
+#pragma unroll
+          for (int q = 0; q < H2; ++q) {
+            __half2 mw = mw_s;
+            if (p.masks[k] != nullptr) {
+              const float2 mm = (VEC == 4) ? make_float2(m4[kk][(2 * q) % 4], m4[kk][(2 * q + 1) % 4])
+                                           : __ldg(reinterpret_cast<const float2*>(p.masks[k] + pix + 2 * q));
+              mw = __hmul2_rn(__floats2half2_rn(mm.x, mm.y), wk2);
+            }
+            const __half2 t = __hmul2_rn(mw, __hsub2_rn(ek4[kk].half2_at(q), eu.half2_at(q)));
+            sum[q] = (k == 0) ? t : __hadd2_rn(sum[q], t);
           }
         }
       }
     }
-    const float2 s01 = __half22float2(sum01), s23 = __half22float2(sum23);
-    const float sum[4] = {s01.x, s01.y, s23.x, s23.y};
-    float x[4] = {xv.x, xv.y, xv.z, xv.w};
-    float et[4], den[4], xn[4];
+    float et[VEC], den[VEC], xn[VEC];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float scaled = h_round(__fmul_rn(sum[j], p.guidance));
-      if (DT == CPD_F16) et[j] = h_round(__fadd_rn(eu[j], scaled));
-      else et[j] = __fadd_rn(eu[j], scaled);
+    for (int j = 0; j < VEC; ++j) {
+      const float sj = (j & 1) ? __high2float(sum[j >> 1]) : __low2float(sum[j >> 1]);
+      float scaled = h_round(__fmul_rn(sj, p.guidance));
+      if (DT == CPD_F16) et[j] = h_round(__fadd_rn(eu.at(j), scaled));
+      else et[j] = __fadd_rn(eu.at(j), scaled);
       if (p.pred_type == CPD_PRED_EPSILON) den[j] = __fsub_rn(x[j], __fmul_rn(p.sigma_hat, et[j]));
       else den[j] = __fadd_rn(__fmul_rn(et[j], p.v_c_eps), __fdiv_rn(x[j], p.v_c_x_div));
     }
     if (p.sampler == CPD_DPMPP_2M) {
-      const float od[4] = {aux.x, aux.y, aux.z, aux.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < VEC; ++j) {
         float dd = den[j];
-        if (!p.dpm_first) dd = __fsub_rn(__fmul_rn(p.dpm_c1, den[j]), __fmul_rn(p.dpm_c2, od[j]));
+        if (!p.dpm_first) dd = __fsub_rn(__fmul_rn(p.dpm_c1, den[j]), __fmul_rn(p.dpm_c2, aux[j]));
         xn[j] = __fsub_rn(__fmul_rn(p.dpm_ratio, x[j]), __fmul_rn(p.dpm_expm1, dd));
       }
-      if (p.write_old)
-        *reinterpret_cast<float4*>(p.old_denoised + (int64_t)b * L + i) = make_float4(den[0], den[1], den[2], den[3]);
+      if (p.write_old) store_f32<VEC>(p.old_denoised + (int64_t)b * L + i, den);
     } else {
-      const float nz[4] = {aux.x, aux.y, aux.z, aux.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < VEC; ++j) {
         float d = __fdiv_rn(__fsub_rn(x[j], den[j]), p.sigma_hat);
         xn[j] = __fadd_rn(x[j], __fmul_rn(d, p.dt));
-        if (p.sampler == CPD_EULER_ANCESTRAL) xn[j] = __fadd_rn(xn[j], __fmul_rn(nz[j], p.sigma_up));
+        if (p.sampler == CPD_EULER_ANCESTRAL) xn[j] = __fadd_rn(xn[j], __fmul_rn(aux[j], p.sigma_up));
       }
     }
-    if (p.sampler != CPD_DENOISE_ONLY)
-      *reinterpret_cast<float4*>(p.x + (int64_t)b * L + i) = make_float4(xn[0], xn[1], xn[2], xn[3]);
-    if (p.denoised_out)
-      *reinterpret_cast<float4*>(p.denoised_out + (int64_t)b * L + i) = make_float4(den[0], den[1], den[2], den[3]);
-    if (p.eps_out)
-      *reinterpret_cast<float4*>(p.eps_out + (int64_t)b * L + i) = make_float4(et[0], et[1], et[2], et[3]);
+    if (p.sampler != CPD_DENOISE_ONLY) store_f32<VEC>(p.x + (int64_t)b * L + i, xn);
+    if (p.denoised_out) store_f32<VEC>(p.denoised_out + (int64_t)b * L + i, den);
+    if (p.eps_out) store_f32<VEC>(p.eps_out + (int64_t)b * L + i, et);
   }
 }
 
@@ -163,15 +189,23 @@ extern "C" cpd_status cpd_sampler_step(const cpd_step_params* p, void* stream) {
   if (p->n_images == 0) return CPD_OK;  // empty batch: nothing to do
   StepArgs args;
   args.p = *p;
-  const int64_t total = (int64_t)p->n_images * p->hw;
-  int blocks = (int)((total + 255) / 256);  // total = number of 4-element vectors
+  const bool wide = p->eps_dtype != CPD_F32 && p->hw % 8 == 0 && p->eps_row_stride % 8 == 0 && p->eps_image_stride % 8 == 0 &&
+                    ((uintptr_t)p->eps & 15) == 0;
+  const int64_t total = (int64_t)p->n_images * p->hw * 4 / (wide ? 8 : 4);  // number of per-thread vectors
+  int blocks = (int)((total + 255) / 256);
   const int max_blocks = 148 * 8;
   if (blocks > max_blocks) blocks = max_blocks;
   cudaStream_t s = (cudaStream_t)stream;
   switch (p->eps_dtype) {
-    case CPD_F32: CPD_CUDA_CHECK(cpd_launch(sampler_step_kernel<CPD_F32>, dim3(blocks), dim3(256), 0, s, args)); break;
-    case CPD_F16: CPD_CUDA_CHECK(cpd_launch(sampler_step_kernel<CPD_F16>, dim3(blocks), dim3(256), 0, s, args)); break;
-    case CPD_BF16: CPD_CUDA_CHECK(cpd_launch(sampler_step_kernel<CPD_BF16>, dim3(blocks), dim3(256), 0, s, args)); break;
+    case CPD_F32: CPD_CUDA_CHECK(cpd_launch(sampler_step_kernel<CPD_F32, 4>, dim3(blocks), dim3(256), 0, s, args)); break;
+    case CPD_F16:
+      if (wide) CPD_CUDA_CHECK(cpd_launch(sampler_step_kernel<CPD_F16, 8>, dim3(blocks), dim3(256), 0, s, args));
+      else CPD_CUDA_CHECK(cpd_launch(sampler_step_kernel<CPD_F16, 4>, dim3(blocks), dim3(256), 0, s, args));
+      break;
+    case CPD_BF16:
+      if (wide) CPD_CUDA_CHECK(cpd_launch(sampler_step_kernel<CPD_BF16, 8>, dim3(blocks), dim3(256), 0, s, args));
+      else CPD_CUDA_CHECK(cpd_launch(sampler_step_kernel<CPD_BF16, 4>, dim3(blocks), dim3(256), 0, s, args));
+      break;
     default: cpd_set_error("cpd_sampler_step: unknown eps_dtype %d", p->eps_dtype); return CPD_ERR_INVALID;
   }
   CPD_CUDA_CHECK(cudaGetLastError());

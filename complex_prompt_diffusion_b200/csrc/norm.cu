@@ -1,5 +1,7 @@
 // GroupNorm(32)(+SiLU) and LayerNorm over NHWC bf16 activations: HBM-bound, 16-byte vectorised,
 // fp32 statistics (models/util.py:95-105; attention.py:89-90,476-478 of the reference).
+#include <stdlib.h>
+
 #include "../../include/cpd_b200.h"
 #include "common.cuh"
 
@@ -203,6 +205,112 @@ __global__ void __launch_bounds__(512, 2) gn_apply_kernel(const bf16* __restrict
   }
 }
 
+// ---- GroupNorm, single pass for slabs that fit the register file: one block owns every pixel of (image, slab of whole
+// groups whose channel count is a multiple of 8).  The slab is read once into registers (<= V 16-byte vectors per thread),
+// reduced (fp32 per thread -> fp32 over pixel lanes -> fp64 over the channels of a group, fixed order), normalised from the
+// registers and written: one read + one write of the tensor, one launch.
+template <bool F16, int V>
+__global__ void __launch_bounds__(640, 1) gn_fused_kernel(const bf16* __restrict__ a0, const bf16* __restrict__ a1, int c0,
+                                                          int c1, int hw, int slab_c, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float eps, int silu,
+                                                          bf16* __restrict__ out) {
+  extern __shared__ __align__(16) float sh[];  // [lanes][2][slab_c] partial sums, then scale[slab_c], shift[slab_c]
+  pdl_launch_dependents();
+  pdl_wait();
+  const int C = c0 + c1;
+  const int cpg = C / GROUPS;
+  const int vps = slab_c / 8;  // vectors per pixel of the slab
+  const int lanes = blockDim.x / vps;
+  const int n = blockIdx.y;
+  const int ch0 = blockIdx.x * slab_c;  // first channel of the slab (slabs never straddle a0 | a1)
+  const int cv = threadIdx.x % vps;
+  const int pl = threadIdx.x / vps;
+  const int ch = ch0 + cv * 8;
+  const bf16* src;
+  int cs, coff;
+  if (ch < c0) { src = a0; cs = c0; coff = ch; } else { src = a1; cs = c1; coff = ch - c0; }
+  const bf16* base = src + ((int64_t)n * hw + pl) * cs + coff;
+  const int64_t step = (int64_t)lanes * cs;
+  uint4 raw[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    raw[j] = make_uint4(0, 0, 0, 0);  // zeros add nothing to the sums
+    if (pl + j * lanes < hw) raw[j] = __ldg(reinterpret_cast<const uint4*>(base + j * step));
+  }
+  float s[8], ss[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s[e] = ss[e] = 0.f;
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const uint32_t u[4] = {raw[j].x, raw[j].y, raw[j].z, raw[j].w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = unpack_act2(u[e], F16);
+      s[2 * e] += f.x; ss[2 * e] += f.x * f.x;
+      s[2 * e + 1] += f.y; ss[2 * e + 1] += f.y * f.y;
+    }
+  }
+  {
+    float* mine = sh + (size_t)pl * 2 * slab_c + cv * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      mine[e] = s[e];
+      mine[slab_c + e] = ss[e];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * slab_c; i += blockDim.x) {
+    float acc = sh[i];
+    for (int l = 1; l < lanes; ++l) acc += sh[(size_t)l * 2 * slab_c + i];
+    sh[i] = acc;
+  }
+  __syncthreads();
+  float* gstat = sh + 2 * slab_c;  // [groups of the slab][2] (lane 1's region: free after the lane reduction... kept separate)
+  const int gslab = slab_c / cpg;
+  if (threadIdx.x < gslab) {
+    const int g = threadIdx.x;
+    double S = 0.0, SS = 0.0;
+    for (int c = 0; c < cpg; ++c) {
+      S += (double)sh[g * cpg + c];
+      SS += (double)sh[slab_c + g * cpg + c];
+    }
+    const double cnt = (double)hw * cpg;
+    const double mean = S / cnt;
+    double var = SS / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    gstat[2 * g] = (float)mean;
+    gstat[2 * g + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  float sc[8], sf[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int cl = cv * 8 + e;  // channel inside the slab
+    const int g = (int)__fdividef((float)cl + 0.5f, (float)cpg);
+    const float k = gstat[2 * g + 1] * __ldg(gamma + ch0 + cl);
+    sc[e] = k;
+    sf[e] = __ldg(beta + ch0 + cl) - gstat[2 * g] * k;
+  }
+  bf16* obase = out + ((int64_t)n * hw + pl) * C + ch;
+  const int64_t ostep = (int64_t)lanes * C;
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    if (pl + j * lanes < hw) {
+      const uint32_t u[4] = {raw[j].x, raw[j].y, raw[j].z, raw[j].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_act2(u[e], F16);
+        float y0 = f.x * sc[2 * e] + sf[2 * e];
+        float y1 = f.y * sc[2 * e + 1] + sf[2 * e + 1];
+        if (silu) { y0 = silu_tanh_f(y0); y1 = silu_tanh_f(y1); }
+        o[e] = pack_act2(y0, y1, F16);
+      }
+      *reinterpret_cast<uint4*>(obase + j * ostep) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
 // ---- LayerNorm: one warp per R rows (all loads of the R rows issued before the first use), rows in registers -----
 template <int MAXV, int R>  // max 16-byte vectors per lane, rows per warp
 __global__ void __launch_bounds__(256, 4) layernorm_kernel(const bf16* __restrict__ x, int rows, int c,
@@ -369,6 +477,54 @@ extern "C" cpd_status cpd_groupnorm(const void* a0, const void* a1, int c0, int 
   CPD_REQUIRE(c1 == 0 || a1, "cpd_groupnorm: c1 > 0 needs a1");
   CPD_REQUIRE(n_img > 0 && hw > 0, "cpd_groupnorm: empty input");
   cudaStream_t s = (cudaStream_t)stream;
+  {  // single-pass kernel when (image, slab of whole groups) fits the register file of one block
+    const int cpg = C / GROUPS;
+    int slab_c = cpg;
+    while (slab_c % 8) slab_c += cpg;  // smallest multiple of cpg that is a multiple of 8
+    const int vps = slab_c / 8;
+    const bool whole = C % slab_c == 0 && c0 % slab_c == 0;
+    static int fused_on = -1;  // CPD_GN_FUSED=0 keeps the two-kernel path (A/B measurements)
+    if (fused_on < 0) {
+      const char* e = getenv("CPD_GN_FUSED");
+      fused_on = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (fused_on && whole && vps <= 20) {
+      int V = 0, lanes = 0;
+      for (int v : {8, 4, 2, 10}) {  // most loads in flight per thread with 128..640 threads per block
+        const int l = (hw + v - 1) / v;
+        if (l * vps <= 640 && (l * vps >= 128 || v == 2)) { V = v; lanes = l; break; }
+      }
+      if (V) {
+        const int threads = lanes * vps;
+        const size_t shm = sizeof(float) * ((size_t)2 * slab_c * lanes + 2 * slab_c + 2 * GROUPS);
+        if (shm <= 200 * 1024) {
+          static bool cfg_f = false;
+          const dim3 grid(C / slab_c, n_img);
+#define CPD_GN_FUSED_LAUNCH(F, VV)                                                                                        \
+  do {                                                                                                                    \
+    static bool attr = false;                                                                                             \
+    if (!attr) {                                                                                                          \
+      CPD_CUDA_CHECK(cudaFuncSetAttribute(gn_fused_kernel<F, VV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+      attr = true;                                                                                                        \
+    }                                                                                                                     \
+    CPD_CUDA_CHECK(cpd_launch(gn_fused_kernel<F, VV>, grid, dim3(threads), shm, s, (const bf16*)a0, (const bf16*)a1, c0, c1, hw, \
+                              slab_c, gamma, beta, eps, silu, (bf16*)out));                                               \
+  } while (0)
+          (void)cfg_f;
+          if (act_fp16) {
+            if (V == 2) CPD_GN_FUSED_LAUNCH(true, 2); else if (V == 4) CPD_GN_FUSED_LAUNCH(true, 4);
+            else if (V == 8) CPD_GN_FUSED_LAUNCH(true, 8); else CPD_GN_FUSED_LAUNCH(true, 10);
+          } else {
+            if (V == 2) CPD_GN_FUSED_LAUNCH(false, 2); else if (V == 4) CPD_GN_FUSED_LAUNCH(false, 4);
+            else if (V == 8) CPD_GN_FUSED_LAUNCH(false, 8); else CPD_GN_FUSED_LAUNCH(false, 10);
+          }
+#undef CPD_GN_FUSED_LAUNCH
+          CPD_CUDA_CHECK(cudaGetLastError());
+          return CPD_OK;
+        }
+      }
+    }
+  }
   const int vec_per_px = C / 8;
   // <= 256 threads per block (4 blocks per SM at <= 64 registers), 8 x 16-byte loads in flight per thread
   int lanes = 256 / vec_per_px;

@@ -38,6 +38,7 @@ struct Attn2Args {
   int datoms;   // ceil(dqk / 64)
   int stages;
   int fp16;
+  int xu_gate;  // separate-P mode: alternate the two tiles' exp phases (CPD_ATTN_GATE=0 turns it off)
   float scale_log2;
 };
 
@@ -63,6 +64,21 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
       : "memory");
 }
 
+#ifdef CPD_TIMELINE
+// Debug build (make TIMELINE=1): CTA 0, lane 0 of the first softmax warp of each tile stamps clock64 at the phases of key
+// blocks 8..15 (tools/attn_timeline.py): [tile][block - 8][phase]
+__device__ long long cpd_dbg_attn[2][8][8];
+#define ATT_STAMP(ph)                                                                                              \
+  do {                                                                                                             \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && qd == 2 && lane == 0 && j >= 8 && j < 16)         \
+      cpd_dbg_attn[t][j - 8][ph] = clock64();                                                                      \
+  } while (0)
+#else
+#define ATT_STAMP(ph) \
+  do {                \
+  } while (0)
+#endif
+
 template <bool SEP>  // SEP: P in its own TMEM columns (dv <= 64); otherwise P overwrites S in place
 __global__ void __launch_bounds__(NUM_THREADS, 1) attention2_kernel(const __grid_constant__ Attn2Args a) {
   extern __shared__ uint8_t smem_raw[];
@@ -87,7 +103,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention2_kernel(const __grid
   uint64_t* pv_done = p_full + 2;            // [2]  P V_t(j) complete: P_t may be overwritten, O_t may be rescaled / read
   uint64_t* s_free = pv_done + 2;            // [2]  S_t(j) has been read into registers (separate-P mode)
   uint64_t* stagger = s_free + 2;            // [1]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(stagger + 1);
+  uint64_t* xu_done = stagger + 1;           // [2][4] exp phase of (tile, lane quarter) finished: the MUFU pipe is free for the other tile
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(xu_done + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * (2 * BQ);
@@ -115,6 +132,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention2_kernel(const __grid
       mbar_init(&s_free[t], 128);
     }
     mbar_init(stagger, 128);
+    for (int i = 0; i < 8; ++i) mbar_init(&xu_done[i], 1);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -273,14 +291,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention2_kernel(const __grid
     float m_used = -INFINITY;
     for (int j = 0; j < nblk; ++j) {
       const int kv_valid = min(BKV, a.nk - j * BKV);
+      ATT_STAMP(0);
       mbar_wait(&s_full[t], (uint32_t)(j & 1), 30);
       tc_fence_after();
+      ATT_STAMP(1);
       uint32_t s[128];
       tmem_ld32(tS + 0, reinterpret_cast<uint32_t(&)[32]>(s[0]));
       tmem_ld32(tS + 32, reinterpret_cast<uint32_t(&)[32]>(s[32]));
       tmem_ld32(tS + 64, reinterpret_cast<uint32_t(&)[32]>(s[64]));
       tmem_ld32(tS + 96, reinterpret_cast<uint32_t(&)[32]>(s[96]));
       tmem_ld_wait();
+      ATT_STAMP(2);
       if (sep) {  // the S row now lives in registers: the tensor pipe may overwrite S_t with the next block
         tc_fence_before();
         mbar_arrive(&s_free[t]);
@@ -298,6 +319,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention2_kernel(const __grid
         for (int e = 0; e < 128; ++e)
           if (e < kv_valid) mx0 = fmaxf(mx0, __uint_as_float(s[e]));
       }
+      ATT_STAMP(3);
       if (t == 0 && j == 0) mbar_arrive(stagger);
       const float m_blk = fmaxf(mx0, mx1) * a.scale_log2;
       float alpha = 1.0f;
@@ -309,11 +331,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention2_kernel(const __grid
         m_used = m_blk;
         need = true;
       }
-      if (sep && j > 0) {  // P V_t(j-1) complete: O_t may be rescaled and P_t overwritten (normally long done: no stall)
-        mbar_wait(&pv_done[t], (uint32_t)((j - 1) & 1), 31);
-        tc_fence_after();
-      }
+      // Separate-P mode: P V_t(j-1) must be complete before O_t is rescaled (rare) and before P_t is overwritten - the
+      // latter only after the exp phase, so the P V round trip hides behind it.
+      bool pv_waited = !sep || j == 0;
       if (__any_sync(0xffffffffu, need)) {  // rare: rescale this warp's 32 rows of O
+        if (!pv_waited) {
+          mbar_wait(&pv_done[t], (uint32_t)((j - 1) & 1), 31);
+          tc_fence_after();
+          pv_waited = true;
+        }
         for (int c = 0; c < a.dv; c += 16) {
           uint32_t o16[16];
           tmem_ld16(tO + c, o16);
@@ -323,16 +349,41 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention2_kernel(const __grid
           tmem_st16(tO + c, o16);
         }
       }
+      // Separate-P mode: nothing couples the two tiles any more, and they drift into lockstep (both in the exp phase,
+      // each at half MUFU rate, then both in the MUFU-free phases).  The two warps that share an SM sub-partition
+      // (tile 0 / tile 1, same lane quarter) therefore alternate their exp phases: T0(j), T1(j), T0(j+1), ...
+      if (sep && a.xu_gate) {
+        if (t == 0) {
+          if (j > 0) mbar_wait(&xu_done[4 + qd], (uint32_t)((j - 1) & 1), 33);
+        } else {
+          mbar_wait(&xu_done[qd], (uint32_t)(j & 1), 34);
+        }
+      }
+      ATT_STAMP(4);
       // p = 2^(s * scale_log2 - m): one FFMA feeding MUFU.EX2; packed pairs overwrite s[] in place (s[e/2] <- e, e+1)
       const float neg_m = -m_used;
       if (full) {
 #pragma unroll
-        for (int e = 0; e < 128; e += 2) {
+        for (int e = 0; e < 64; e += 2) {
+          const float p0 = fast_ex2(fmaf(__uint_as_float(s[e]), a.scale_log2, neg_m));
+          const float p1 = fast_ex2(fmaf(__uint_as_float(s[e + 1]), a.scale_log2, neg_m));
+          s[e >> 1] = pack_act2(p0, p1, f16);
+        }
+        if (sep && a.xu_gate == 2) {  // half-way: the other tile may start its exp phase (half-period offset, overlap allowed)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&xu_done[t * 4 + qd]);
+        }
+#pragma unroll
+        for (int e = 64; e < 128; e += 2) {
           const float p0 = fast_ex2(fmaf(__uint_as_float(s[e]), a.scale_log2, neg_m));
           const float p1 = fast_ex2(fmaf(__uint_as_float(s[e + 1]), a.scale_log2, neg_m));
           s[e >> 1] = pack_act2(p0, p1, f16);
         }
       } else {
+        if (sep && a.xu_gate == 2) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&xu_done[t * 4 + qd]);
+        }
 #pragma unroll
         for (int e = 0; e < 128; e += 2) {
           float p0 = fast_ex2(fmaf(__uint_as_float(s[e]), a.scale_log2, neg_m));
@@ -342,11 +393,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention2_kernel(const __grid
           s[e >> 1] = pack_act2(p0, p1, f16);
         }
       }
+      ATT_STAMP(5);
+      if (sep && a.xu_gate == 1) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xu_done[t * 4 + qd]);
+      }
+      if (!pv_waited) {
+        mbar_wait(&pv_done[t], (uint32_t)((j - 1) & 1), 31);
+        tc_fence_after();
+      }
       tmem_st32(tP + 0, &s[0]);
       tmem_st32(tP + 32, &s[32]);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[t]);
+      ATT_STAMP(6);
     }
     // ---- epilogue: O / l -> global (l = O[:, d], accumulated by the ones row of V^T) ----
     mbar_wait(&pv_done[t], sep ? (uint32_t)((nblk - 1) & 1) : 0u, 32);
@@ -390,6 +451,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention2_kernel(const __grid
 }
 
 }  // namespace
+
+#ifdef CPD_TIMELINE
+extern "C" int cpd_debug_attn_timeline(long long* host128) {
+  return (int)cudaMemcpyFromSymbol(host128, cpd_dbg_attn, sizeof(long long) * 128);
+}
+#endif
 
 // Returns CPD_ERR_UNSUPPORTED when the shape is outside this kernel's domain (the caller falls back to the one-tile kernel).
 cpd_status cpd_attention_2tile(const cpd_attn_params* p, void* stream) {
@@ -448,6 +515,12 @@ cpd_status cpd_attention_2tile(const cpd_attn_params* p, void* stream) {
     const char* e = getenv("CPD_ATTN_SEP");
     sep_env = (e && e[0] == '1') ? 1 : 0;
   }
+  static int gate_env = -1;
+  if (gate_env < 0) {
+    const char* e = getenv("CPD_ATTN_GATE");
+    gate_env = e ? (e[0] - '0') : 2;  // 0 none, 1 strict alternation, 2 half-period offset
+  }
+  a.xu_gate = gate_env;
   if (dv <= 64 && sep_env)
     CPD_CUDA_CHECK(cpd_launch(attention2_kernel<true>, dim3(grid), dim3(NUM_THREADS), shm, (cudaStream_t)stream, a));
   else

@@ -23,7 +23,7 @@ namespace {
 constexpr int BQ = 128;
 constexpr int BKV = 128;
 constexpr int ATOM_BYTES = 128 * 128;  // 128 rows x 64 16-bit elements
-constexpr int NUM_THREADS = 320;       // warp 0 TMA, warp 1 MMA, warps 2-5 softmax tile 0, warps 6-9 softmax tile 1
+constexpr int NUM_THREADS = 352;       // warp 0 TMA, warp 1 MMA, warps 2-5 softmax tile 0, warps 6-9 softmax tile 1, warp 10 second MMA issuer (separate-P mode)
 constexpr int MAX_STAGES = 4;
 constexpr float RESCALE_TAU = 8.0f;    // lazy O rescale threshold (log2 domain)
 
@@ -121,9 +121,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention2_kernel(const __grid
     mbar_init(q_full, 1);
     for (int s = 0; s < stages; ++s) {
       mbar_init(&k_full[s], 1);
-      mbar_init(&k_empty[s], 1);
+      mbar_init(&k_empty[s], SEP ? 2 : 1);  // separate-P mode: one tcgen05.commit per tile issuer
       mbar_init(&v_full[s], 1);
-      mbar_init(&v_empty[s], 1);
+      mbar_init(&v_empty[s], SEP ? 2 : 1);
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
@@ -193,6 +193,70 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention2_kernel(const __grid
           ph ^= 1;
         }
       }
+    }
+  } else if (SEP && (warp == 1 || warp == 10)) {
+    // ================= separate-P mode: one MMA issuer warp PER TILE =================
+    // A single issuer serialises ~1500 cycles of barrier / fence / elect / commit latencies per (tile, key block) - as long as
+    // a whole softmax block - and becomes the bottleneck once S(j+1) is taken off the critical path.  Each tile's issuer runs
+    //   S_t(0);  for j: [S_t(j+1) once the softmax has read S_t(j)]  [P V_t(j) once P_t(j) is stored]
+    // and both commit to the K / V stage-release barriers (count 2).
+    const int t = warp == 1 ? 0 : 1;
+    const uint32_t idesc_s = umma_idesc_f16(BQ, BKV, f16, f16);
+    const uint32_t idesc_o = umma_idesc_f16(BQ, a.dv, f16, f16);
+    const int ksteps_s = a.dqk / 16;
+    const uint32_t qa = smem_u32(sQ) + t * q_tile_bytes, k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+    const uint32_t dS = tmem_base + (t ? colS1 : colS0);
+    const uint32_t dO = tmem_base + (t ? colO1 : colO0);
+    const uint32_t aP = dS + offP;
+    auto issue_s = [&](int st) {
+      if (elect_one()) {
+        const uint32_t ka = k_addr + st * k_stage_bytes;
+        for (int kk = 0; kk < ksteps_s; ++kk) {
+          const uint32_t off = (uint32_t)((kk >> 2) * ATOM_BYTES + (kk & 3) * 32);
+          umma_bf16(dS, umma_desc_sw128(qa + off), umma_desc_sw128(ka + off), idesc_s, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[t]);
+        umma_commit(&k_empty[st]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0, 21);
+    mbar_wait(&k_full[0], 0, 20);
+    if (t == 1 && nblk > 1) mbar_wait(stagger, 0, 24);
+    tc_fence_after();
+    issue_s(0);
+    int st = 0;
+    uint32_t ph = 0;
+    for (int j = 0; j < nblk; ++j) {
+      int st_n = st + 1;
+      uint32_t ph_n = ph;
+      if (st_n == stages) {
+        st_n = 0;
+        ph_n ^= 1;
+      }
+      if (j + 1 < nblk) {
+        mbar_wait(&s_free[t], (uint32_t)(j & 1), 25);
+        mbar_wait(&k_full[st_n], ph_n, 20);
+        tc_fence_after();
+        issue_s(st_n);
+      }
+      mbar_wait(&v_full[st], ph, 23);
+      mbar_wait(&p_full[t], (uint32_t)(j & 1), 22);
+      tc_fence_after();
+      if (elect_one()) {
+        const int kv_valid = min(BKV, a.nk - j * BKV);
+        const int ksteps_o = (kv_valid + 15) / 16;
+        const uint32_t va = v_addr + st * v_stage_bytes;
+        for (int kk = 0; kk < ksteps_o; ++kk) {
+          const uint32_t offv = (uint32_t)((kk >> 2) * vt_atom_bytes + (kk & 3) * 32);
+          umma_f16_ts(dO, aP + kk * 8, umma_desc_sw128(va + offv), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(&pv_done[t]);
+        umma_commit(&v_empty[st]);
+      }
+      __syncwarp();
+      st = st_n;
+      ph = ph_n;
     }
   } else if (warp == 1) {
     // ================= MMA issuer (whole warp runs the loop; one elected lane issues) =================
@@ -279,7 +343,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention2_kernel(const __grid
       st = st_n;
       ph = ph_n;
     }
-  } else {
+  } else if (warp < 10) {
     // ================= softmax warpgroups: thread <-> query row =================
     const int t = (warp - 2) >> 2;  // tile
     const int qd = warp & 3;        // TMEM lane quarter of this warp
@@ -508,8 +572,11 @@ cpd_status cpd_attention_2tile(const cpd_attn_params* p, void* stream) {
     configured = true;
   }
   dim3 grid((p->nq + 2 * BQ - 1) / (2 * BQ), p->heads, p->batch);
-  // The separate-P layout (S(j+1) issued as soon as S(j) is in registers) measured SLOWER than aliasing P over S
-  // (893 vs 829 us on 16 x 8 x 4096^2, d = 40, same box): it stays opt-in (CPD_ATTN_SEP=1) for experiments.
+  // The separate-P layout (S(j+1) issued as soon as S(j) is in registers; one MMA issuer warp per tile; optional exp-phase
+  // gate between the tiles) removes the wait for S but measures no faster than aliasing P over S (839-870 vs 829-838 us on
+  // 16 x 8 x 4096^2, d = 40): a lone warp in its exp phase issues a MUFU.EX2 only every ~11-13 cycles (8 would saturate the
+  // pipe), so with two softmax warps per SM sub-partition the MUFU pipe stays ~60 % busy either way
+  // (profiles/r01_attn_timelines.txt).  Opt-in (CPD_ATTN_SEP=1) for experiments.
   static int sep_env = -1;
   if (sep_env < 0) {
     const char* e = getenv("CPD_ATTN_SEP");

@@ -16,9 +16,8 @@
 namespace {
 
 constexpr int BQ = 128;
-constexpr int BKV = 128;
 constexpr int ATOM_BYTES = 128 * 128;  // 128 rows x 64 16-bit elements
-constexpr int NUM_THREADS = 320;       // warp 0 TMA, warp 1 MMA, warps 2-5 softmax tile 0, warps 6-9 softmax tile 1
+// threads: warp 0 TMA, warp 1 MMA, then one softmax warpgroup (4 warps) per query tile: 64 + NT * 128
 constexpr int MAX_STAGES = 4;
 constexpr float RESCALE_TAU = 8.0f;    // lazy O rescale threshold (log2 domain)
 
@@ -34,7 +33,7 @@ struct Attn3Args {
   int stages;
   int qbufs;    // Q buffers (2 = the next item's Q is loaded while this item runs; 1 when shared memory is short)
   int fp16;
-  int nqp;      // 256-row query pairs per (batch, head)
+  int nqp;      // work items (NT x 128 query rows) per (batch, head)
   int items;    // batch * heads * nqp
   float scale_log2;
 };
@@ -61,16 +60,49 @@ __device__ __forceinline__ void tmem_st32_3(uint32_t taddr, const uint32_t* r) {
       : "memory");
 }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1) attention3_kernel(const __grid_constant__ Attn3Args a) {
+#ifdef CPD_TIMELINE
+// Debug build (make TIMELINE=1): CTA 0 stamps clock64 at the phases of key blocks 8..15 of its first item
+// (tools/attn_timeline.py --persistent): softmax [tile][block - 8][phase], MMA issuer [block - 8][tile][PV issued, S issued]
+__device__ long long cpd_dbg_attn3[4][8][8];
+__device__ long long cpd_dbg_mma3[8][4][4];
+#define ATT3_STAMP(ph)                                                                       \
+  do {                                                                                       \
+    if (blockIdx.x == 0 && it == 0 && qd == 2 && lane == 0 && j >= 8 && j < 16)              \
+      cpd_dbg_attn3[t][j - 8][ph] = clock64();                                               \
+  } while (0)
+#define MMA3_STAMP(ph)                                                                       \
+  do {                                                                                       \
+    if (blockIdx.x == 0 && it == 0 && lane == 0 && j >= 8 && j < 16)                         \
+      cpd_dbg_mma3[j - 8][t][ph] = clock64();                                                \
+  } while (0)
+#else
+#define ATT3_STAMP(ph) \
+  do {                 \
+  } while (0)
+#define MMA3_STAMP(ph) \
+  do {                 \
+  } while (0)
+#endif
+
+// NT query tiles of 128 rows per work item, key blocks of BKV keys.  <2, 128>: the general shape.  <4, 64>: four softmax
+// warpgroups (4 warps per SM sub-partition) for head dims <= 63 - a lone warp in its exp phase reaches only ~75 % of the
+// MUFU rate (every MUFU.EX2 carries an 8-cycle issue stall, the FFMA / F2FP around it add to it), two or more interleave
+// to ~93 %; with four tiles in flight the tensor-pipe round trip of one tile also hides behind the other three.
+template <int NT, int BKV>
+__global__ void __launch_bounds__(64 + NT * 128, 1) attention3_kernel(const __grid_constant__ Attn3Args a) {
+  constexpr int NUM_THREADS = 64 + NT * 128;
+  constexpr int K_ATOM = BKV * 128;  // BKV rows x 64 16-bit elements
+  constexpr int VATOMS = BKV / 64;   // 64-key atoms of a V^T stage
+  constexpr int OCOLS = 256 / NT;    // TMEM columns reserved per O_t
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int datoms = a.datoms;
   const int stages = a.stages;
   const int q_tile_bytes = datoms * ATOM_BYTES;
-  const int q_buf_bytes = 2 * q_tile_bytes;  // both tiles of an item
-  const int k_stage_bytes = datoms * ATOM_BYTES;
+  const int q_buf_bytes = NT * q_tile_bytes;  // all tiles of an item
+  const int k_stage_bytes = datoms * K_ATOM;
   const int vt_atom_bytes = a.dv * 128;
-  const int v_stage_bytes = 2 * vt_atom_bytes;
+  const int v_stage_bytes = VATOMS * vt_atom_bytes;
   uint8_t* sQ = smem;  // [2 buffers][2 tiles]
   uint8_t* sK = sQ + a.qbufs * q_buf_bytes;
   uint8_t* sV = sK + stages * k_stage_bytes;
@@ -81,11 +113,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention3_kernel(const __grid
   uint64_t* k_empty = k_full + MAX_STAGES;
   uint64_t* v_full = k_empty + MAX_STAGES;
   uint64_t* v_empty = v_full + MAX_STAGES;
-  uint64_t* s_full = v_empty + MAX_STAGES;    // [2]  S_t of the current block is in TMEM
-  uint64_t* p_full = s_full + 2;              // [2]  P_t of the current block is in TMEM (128 arrivals)
-  uint64_t* pv_last = p_full + 2;             // [2]  the last P V_t of the item has completed: O_t is final
-  uint64_t* o_free = pv_last + 2;             // [2]  O_t has been read by its softmax warpgroup (128 arrivals)
-  uint64_t* stagger = o_free + 2;             // [1]
+  uint64_t* s_full = v_empty + MAX_STAGES;    // [NT]  S_t of the current block is in TMEM
+  uint64_t* p_full = s_full + NT;             // [NT]  P_t of the current block is in TMEM (128 arrivals)
+  uint64_t* pv_last = p_full + NT;            // [NT]  the last P V_t of the item has completed: O_t is final
+  uint64_t* o_free = pv_last + NT;            // [NT]  O_t has been read by its softmax warpgroup (128 arrivals)
+  uint64_t* stagger = o_free + NT;            // [1]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(stagger + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -101,10 +133,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention3_kernel(const __grid
     for (int s = 0; s < 2; ++s) {
       mbar_init(&q_full[s], 1);
       mbar_init(&q_empty[s], 1);
-      mbar_init(&s_full[s], 1);
-      mbar_init(&p_full[s], 128);
-      mbar_init(&pv_last[s], 1);
-      mbar_init(&o_free[s], 128);
+    }
+    for (int t = 0; t < NT; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&p_full[t], 128);
+      mbar_init(&pv_last[t], 1);
+      mbar_init(&o_free[t], 128);
     }
     for (int s = 0; s < stages; ++s) {
       mbar_init(&k_full[s], 1);
@@ -122,7 +156,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention3_kernel(const __grid
   {  // rows d .. dv-1 of every V^T stage atom: ones row (-> O[:, d] = sum of P), then zero rows (never touched by TMA)
     const uint32_t one2 = f16 ? 0x3C003C00u : 0x3F803F80u;
     const int pad_rows = a.dv - a.d;
-    const int chunks = stages * 2 * pad_rows * 8;
+    const int chunks = stages * VATOMS * pad_rows * 8;
     for (int i = threadIdx.x; i < chunks; i += NUM_THREADS) {
       const int c16 = i & 7;
       const int rr = (i >> 3) % pad_rows;
@@ -137,7 +171,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention3_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_wait();
-  // TMEM columns: S_t / P_t (aliased) at t * 128, O_t at 256 + t * 128
+  // TMEM columns: S_t / P_t (aliased) at t * BKV, O_t at 256 + t * OCOLS
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -154,19 +188,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention3_kernel(const __grid
         const int qb = a.qbufs == 2 ? (it & 1) : 0;
         mbar_wait(&q_empty[qb], (uint32_t)(((a.qbufs == 2 ? (it >> 1) : it) & 1) ^ 1), 12);
         mbar_arrive_expect_tx(&q_full[qb], q_buf_bytes);
-        for (int t = 0; t < 2; ++t)
+        for (int t = 0; t < NT; ++t)
           for (int dd = 0; dd < datoms; ++dd)
             tma_load_2d(sQ + qb * q_buf_bytes + t * q_tile_bytes + dd * ATOM_BYTES, &a.map_q, &q_full[qb], head * a.dqk + dd * 64,
-                        b * a.nq + qp * (2 * BQ) + t * BQ);
+                        b * a.nq + qp * (NT * BQ) + t * BQ);
         for (int j = 0; j < nblk; ++j) {
           mbar_wait(&k_empty[st], ph ^ 1, 10);
           mbar_arrive_expect_tx(&k_full[st], k_stage_bytes);
           for (int dd = 0; dd < datoms; ++dd)
-            tma_load_2d(sK + st * k_stage_bytes + dd * ATOM_BYTES, &a.map_k, &k_full[st], head * a.dqk + dd * 64,
+            tma_load_2d(sK + st * k_stage_bytes + dd * K_ATOM, &a.map_k, &k_full[st], head * a.dqk + dd * 64,
                         bkv * a.nk_pad + j * BKV);
           mbar_wait(&v_empty[st], ph ^ 1, 11);
-          mbar_arrive_expect_tx(&v_full[st], 2 * a.d * 128);
-          for (int t = 0; t < 2; ++t)
+          mbar_arrive_expect_tx(&v_full[st], VATOMS * a.d * 128);
+          for (int t = 0; t < VATOMS; ++t)
             tma_load_2d(sV + st * v_stage_bytes + t * vt_atom_bytes, &a.map_vt, &v_full[st], bkv * a.nk_pad + j * BKV + t * 64,
                         head * a.dqk);
           if (++st == stages) {
@@ -186,8 +220,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention3_kernel(const __grid
       if (elect_one()) {
         const uint32_t qa = q_addr + qb * q_buf_bytes + t * q_tile_bytes, ka = k_addr + st * k_stage_bytes;
         for (int kk = 0; kk < ksteps_s; ++kk) {
-          const uint32_t off = (uint32_t)((kk >> 2) * ATOM_BYTES + (kk & 3) * 32);
-          umma_bf16(tmem_base + t * 128, umma_desc_sw128(qa + off), umma_desc_sw128(ka + off), idesc_s, kk > 0 ? 1u : 0u);
+          const uint32_t offq = (uint32_t)((kk >> 2) * ATOM_BYTES + (kk & 3) * 32);
+          const uint32_t offk = (uint32_t)((kk >> 2) * K_ATOM + (kk & 3) * 32);
+          umma_bf16(tmem_base + t * BKV, umma_desc_sw128(qa + offq), umma_desc_sw128(ka + offk), idesc_s, kk > 0 ? 1u : 0u);
         }
         umma_commit(&s_full[t]);
       }
@@ -207,8 +242,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention3_kernel(const __grid
       mbar_wait(&k_full[0], 0, 20);
       tc_fence_after();
       issue_s(0, 0, 0);
-      if (nblk > 1) mbar_wait(stagger, 0, 24);  // stagger tile 1 behind tile 0's row-max phase (self-attention)
-      issue_s(1, 0, 0);
+      if (NT == 2 && nblk > 1) mbar_wait(stagger, 0, 24);  // stagger tile 1 behind tile 0's row-max phase (self-attention)
+      for (int t = 1; t < NT; ++t) issue_s(t, 0, 0);
       if (elect_one()) {
         umma_commit(&k_empty[0]);
         if (nblk == 1) umma_commit(&q_empty[0]);
@@ -230,19 +265,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention3_kernel(const __grid
         mbar_wait(&v_full[st], ph, 23);
         const int kv_valid = min(BKV, a.nk - j * BKV);
         const int ksteps_o = (kv_valid + 15) / 16;
-        for (int t = 0; t < 2; ++t) {
+        for (int t = 0; t < NT; ++t) {
+          MMA3_STAMP(0);
           mbar_wait(&p_full[t], blk & 1u, 22);  // P_t(j) is in TMEM
+          MMA3_STAMP(1);
           if (j == 0 && it > 0) mbar_wait(&o_free[t], (uint32_t)((it - 1) & 1), 26);  // previous item's O_t has been read
           tc_fence_after();
           if (elect_one()) {
             const uint32_t va = v_addr + st * v_stage_bytes;
             for (int kk = 0; kk < ksteps_o; ++kk) {
               const uint32_t offv = (uint32_t)((kk >> 2) * vt_atom_bytes + (kk & 3) * 32);
-              umma_f16_ts3(tmem_base + 256 + t * 128, tmem_base + t * 128 + kk * 8, umma_desc_sw128(va + offv), idesc_o,
+              umma_f16_ts3(tmem_base + 256 + t * OCOLS, tmem_base + t * BKV + kk * 8, umma_desc_sw128(va + offv), idesc_o,
                            (j > 0 || kk > 0) ? 1u : 0u);
             }
             if (last_j) umma_commit(&pv_last[t]);
-            if (t == 1) umma_commit(&v_empty[st]);
+            if (t == NT - 1) umma_commit(&v_empty[st]);
           }
           __syncwarp();
           if (has_next) {
@@ -251,8 +288,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention3_kernel(const __grid
               mbar_wait(&k_full[st_n], ph_n, 20);
               tc_fence_after();
             }
+            MMA3_STAMP(2);
             issue_s(t, q_buf(it_n), st_n);
-            if (t == 1) {
+            MMA3_STAMP(3);
+            if (t == NT - 1) {
               if (elect_one()) {
                 umma_commit(&k_empty[st_n]);
                 if (j_n + 1 == nblk) umma_commit(&q_empty[q_buf(it_n)]);  // the last Q K^T of that item has been issued
@@ -271,8 +310,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention3_kernel(const __grid
     const int qd = warp & 3;        // TMEM lane quarter of this warp
     const int r = qd * 32 + lane;
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-    const uint32_t tS = tmem_base + t * 128 + lane_off;
-    const uint32_t tO = tmem_base + 256 + t * 128 + lane_off;
+    const uint32_t tS = tmem_base + t * BKV + lane_off;
+    const uint32_t tO = tmem_base + 256 + t * OCOLS + lane_off;
     uint32_t blk = 0;
     int it = 0;
     for (int w = first; w < a.items; w += step, ++it) {
@@ -283,25 +322,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention3_kernel(const __grid
       float m_used = -INFINITY;
       for (int j = 0; j < nblk; ++j, ++blk) {
         const int kv_valid = min(BKV, a.nk - j * BKV);
+        ATT3_STAMP(0);
         mbar_wait(&s_full[t], blk & 1u, 30);  // also: P V_t of the previous block has completed (in-order pipe)
         tc_fence_after();
-        uint32_t s[128];
+        ATT3_STAMP(1);
+        uint32_t s[BKV];
         const bool full = (kv_valid == BKV);
-        tmem_ld32(tS + 0, reinterpret_cast<uint32_t(&)[32]>(s[0]));
-        if (kv_valid > 32) tmem_ld32(tS + 32, reinterpret_cast<uint32_t(&)[32]>(s[32]));
-        if (kv_valid > 64) tmem_ld32(tS + 64, reinterpret_cast<uint32_t(&)[32]>(s[64]));
-        if (kv_valid > 96) tmem_ld32(tS + 96, reinterpret_cast<uint32_t(&)[32]>(s[96]));
+#pragma unroll
+        for (int c32 = 0; c32 < BKV / 32; ++c32)
+          if (c32 == 0 || kv_valid > c32 * 32) tmem_ld32(tS + c32 * 32, reinterpret_cast<uint32_t(&)[32]>(s[c32 * 32]));
         tmem_ld_wait();
+        ATT3_STAMP(2);
         float mx0 = -INFINITY, mx1 = -INFINITY;
         if (full) {
 #pragma unroll
-          for (int e = 0; e < 128; e += 2) {
+          for (int e = 0; e < BKV; e += 2) {
             mx0 = fmaxf(mx0, __uint_as_float(s[e]));
             mx1 = fmaxf(mx1, __uint_as_float(s[e + 1]));
           }
         } else {
 #pragma unroll
-          for (int e = 0; e < 128; ++e)
+          for (int e = 0; e < BKV; ++e)
             if (e < kv_valid) mx0 = fmaxf(mx0, __uint_as_float(s[e]));
         }
         if (t == 0 && blk == 0) mbar_arrive(stagger);
@@ -325,18 +366,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention3_kernel(const __grid
             tmem_st16(tO + c, o16);
           }
         }
+        ATT3_STAMP(3);
         // p = 2^(s * scale_log2 - m): one FFMA feeding MUFU.EX2; packed pairs overwrite s[] in place (s[e/2] <- e, e+1)
         const float neg_m = -m_used;
         if (full) {
 #pragma unroll
-          for (int e = 0; e < 128; e += 2) {
+          for (int e = 0; e < BKV; e += 2) {
             const float p0 = fast_ex2(fmaf(__uint_as_float(s[e]), a.scale_log2, neg_m));
             const float p1 = fast_ex2(fmaf(__uint_as_float(s[e + 1]), a.scale_log2, neg_m));
             s[e >> 1] = pack_act2(p0, p1, f16);
           }
         } else {
 #pragma unroll
-          for (int c32 = 0; c32 < 4; ++c32) {
+          for (int c32 = 0; c32 < BKV / 32; ++c32) {
             if (c32 * 32 < kv_valid) {  // warp-uniform: whole 32-column groups beyond the valid keys cost nothing
 #pragma unroll
               for (int e = c32 * 32; e < c32 * 32 + 32; e += 2) {
@@ -352,16 +394,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention3_kernel(const __grid
             }
           }
         }
-        tmem_st32_3(tS + 0, &s[0]);
-        tmem_st32_3(tS + 32, &s[32]);
+        ATT3_STAMP(4);
+#pragma unroll
+        for (int c32 = 0; c32 < BKV / 64; ++c32) tmem_st32_3(tS + c32 * 32, &s[c32 * 32]);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_full[t]);
+        ATT3_STAMP(5);
       }
       // ---- item epilogue: O / l -> global (l = O[:, d], accumulated by the ones row of V^T) ----
       mbar_wait(&pv_last[t], (uint32_t)(it & 1), 32);
       tc_fence_after();
-      const int qrow = qp * (2 * BQ) + t * BQ + r;
+      const int qrow = qp * (NT * BQ) + t * BQ + r;
       float inv_l;
       {
         uint32_t o16[16];
@@ -406,12 +450,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention3_kernel(const __grid
 
 }  // namespace
 
-// Returns CPD_ERR_UNSUPPORTED when the shape is outside this kernel's domain (the caller falls back).
-cpd_status cpd_attention_persistent(const cpd_attn_params* p, void* stream) {
+#ifdef CPD_TIMELINE
+extern "C" int cpd_debug_attn3_timeline(long long* soft256, long long* mma128) {
+  int rc = (int)cudaMemcpyFromSymbol(soft256, cpd_dbg_attn3, sizeof(long long) * 256);
+  if (rc) return rc;
+  return (int)cudaMemcpyFromSymbol(mma128, cpd_dbg_mma3, sizeof(long long) * 128);
+}
+#endif
+
+template <int NT, int BKV>
+static cpd_status launch_attention3(const cpd_attn_params* p, int dv, void* stream) {
   const int d = p->d_head;
-  if (d <= 0 || d > p->dpad || p->nq <= BQ) return CPD_ERR_UNSUPPORTED;
-  const int dv = (d + 1 + 15) / 16 * 16;
-  if (dv > 128) return CPD_ERR_UNSUPPORTED;
   Attn3Args a;
   a.o = (bf16*)p->o;
   a.ldo = p->ldo;
@@ -423,15 +472,15 @@ cpd_status cpd_attention_persistent(const cpd_attn_params* p, void* stream) {
   a.datoms = (p->dpad + 63) / 64;
   a.fp16 = p->act_fp16;
   a.scale_log2 = p->scale * 1.4426950408889634f;
-  a.nqp = (p->nq + 2 * BQ - 1) / (2 * BQ);
+  a.nqp = (p->nq + NT * BQ - 1) / (NT * BQ);
   a.items = p->batch * p->heads * a.nqp;
-  const int per_stage = a.datoms * ATOM_BYTES + 2 * dv * 128;
+  const int per_stage = a.datoms * BKV * 128 + (BKV / 64) * dv * 128;
   a.qbufs = 2;
-  int q_bytes = a.qbufs * 2 * a.datoms * ATOM_BYTES;  // (double-buffered) tile pair
+  int q_bytes = a.qbufs * NT * a.datoms * ATOM_BYTES;  // (double-buffered) tiles of an item
   int stages = (227 * 1024 - 1024 - 512 - q_bytes) / per_stage;
   if (stages < 2) {  // large head dims: one Q buffer
     a.qbufs = 1;
-    q_bytes = 2 * a.datoms * ATOM_BYTES;
+    q_bytes = NT * a.datoms * ATOM_BYTES;
     stages = (227 * 1024 - 1024 - 512 - q_bytes) / per_stage;
   }
   if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -459,10 +508,28 @@ cpd_status cpd_attention_persistent(const cpd_attn_params* p, void* stream) {
   const size_t shm = (size_t)q_bytes + (size_t)stages * per_stage + 512 + 1024;
   static bool configured = false;
   if (!configured) {
-    CPD_CUDA_CHECK(cudaFuncSetAttribute(attention3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+    CPD_CUDA_CHECK(cudaFuncSetAttribute(attention3_kernel<NT, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
     configured = true;
   }
   const int ctas = a.items < 148 ? a.items : 148;
-  CPD_CUDA_CHECK(cpd_launch(attention3_kernel, dim3(ctas), dim3(NUM_THREADS), shm, (cudaStream_t)stream, a));
+  CPD_CUDA_CHECK(cpd_launch(attention3_kernel<NT, BKV>, dim3(ctas), dim3(64 + NT * 128), shm, (cudaStream_t)stream, a));
   return CPD_OK;
+}
+
+// Returns CPD_ERR_UNSUPPORTED when the shape is outside this kernel's domain (the caller falls back).
+cpd_status cpd_attention_persistent(const cpd_attn_params* p, void* stream) {
+  const int d = p->d_head;
+  if (d <= 0 || d > p->dpad || p->nq <= BQ) return CPD_ERR_UNSUPPORTED;
+  const int dv = (d + 1 + 15) / 16 * 16;
+  if (dv > 128) return CPD_ERR_UNSUPPORTED;
+  // Four 128-row tiles x 64-key blocks (O_t in 64 TMEM columns: dv <= 64) is built and tested but measured SLOWER
+  // (1254 vs 838 us on 16 x 8 x 4096^2, d = 40): the single MMA issuer warp spends ~1500 cycles of barrier / fence / commit
+  // latency per (tile, key block) and cannot feed four tiles (profiles/r01_attn_timelines.txt).  Opt-in: CPD_ATTN_4TILE=1.
+  static int four = -1;
+  if (four < 0) {
+    const char* e = getenv("CPD_ATTN_4TILE");
+    four = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (four && dv <= 64 && p->nk > 128 && p->nq >= 4 * BQ) return launch_attention3<4, 64>(p, dv, stream);
+  return launch_attention3<2, 128>(p, dv, stream);
 }

@@ -25,6 +25,29 @@ def main():
         ops.attention(q, k, vt, o, ldq=ip, ldk=ip, ldvt=B * nk_pad, ldo=ip, batch=B, heads=H, nq=Nq, nk=Nk, nk_pad=nk_pad, dpad=dpad,
                       scale=d ** -0.5, d_head=d)
     torch.cuda.synchronize()
+    if "--persistent" in sys.argv:
+        soft, mma = (C.c_longlong * 256)(), (C.c_longlong * 128)()
+        lib.cpd_debug_attn3_timeline(soft, mma)
+        t0 = soft[0]
+        ev = []
+        names = ["top", "S ready", "S in regs", "max done", "exp done", "P arrive"]
+        for t in range(4):
+            for j in range(8):
+                for ph in range(6):
+                    v = soft[(t * 8 + j) * 8 + ph]
+                    if v:
+                        ev.append((v - t0, f"tile {t} blk {8 + j}: {names[ph]}"))
+        mn = ["wait P", "P seen", "S issue", "S issued"]
+        for j in range(8):
+            for t in range(4):
+                for ph in range(4):
+                    v = mma[(j * 4 + t) * 4 + ph]
+                    if v:
+                        ev.append((v - t0, f"    MMA blk {8 + j} tile {t}: {mn[ph]}"))
+        for v, n in sorted(ev):
+            if 0 <= v < 14000:
+                print(f"{v:7d}  {n}")
+        return
     ts = (C.c_longlong * 128)()
     lib.cpd_debug_attn_timeline(ts)
     t0 = ts[0]

@@ -279,3 +279,122 @@ def test_end_to_end_sampling_vs_oracle_bf16(cpd, name, steps):
     r = rel(out, ref)
     print(f"{name}: final latent rel-L2 {r:.3e}")
     assert r < 2e-2
+
+
+# ------------------------------------------------------------------------------- BASELINE.json configs
+def _oracle_side(oracle, dtype=torch.bfloat16):
+    class BF16InOut:  # oracle UNet with the product's dtype boundaries (bf16 context / t, fp32 eps out)
+        def parameters(self):
+            return iter([torch.zeros(1, dtype=dtype)])
+
+        def __call__(self, x, t, ctx, **k):
+            o = oracle(x.to(dtype).float(), t.float(), ctx.to(dtype).float())
+            return o, [o] * 12
+    return BF16InOut()
+
+
+def test_config1_sd15_256px_euler10_cfg_single_prompt(cpd):
+    """BASELINE.json configs[0]: SD-1.5 UNet random-init, 32x32 latent, Euler 10 steps (Karras), CFG 7.5, one prompt +
+    unconditional, batch 1 - the oracle runs it in fp32 arithmetic on the CPU (bf16-rounded weights, the model dtype of
+    the product); the GPU path must stay within the north-star tolerances at every step."""
+    from complex_prompt_diffusion_b200 import samplers
+    from oracle.denoiser import OracleDenoiser
+    from oracle import samplers as OS
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    cfg, oracle, gpu = _unet_pair("sd15", torch.float32)
+    oracle.sd = {k: v.to(torch.bfloat16).float() for k, v in oracle.sd.items()}
+    g = torch.Generator().manual_seed(11)
+    hw, steps = 32, 10
+    uc = torch.randn(1, 77, cfg.context_dim, generator=g)
+    c = {"and": [(1.0, torch.randn(1, 77, cfg.context_dim, generator=g), None, 1)], "not": []}
+    x_T = torch.randn(1, 4, hw, hw, generator=g)
+    kw = dict(conditioning=c, unconditional_conditioning=uc, unconditional_guidance_scale=7.5, scheduler="karras")
+    od = OracleDenoiser(_oracle_side(oracle), dtype=torch.bfloat16)
+    od.trace = []
+    ref = OS.sample(od, "Euler", steps, x_T.clone(), **dict(kw))
+    wrapper = samplers.make({"name": "Euler", "args": {}}, {"model": {"unet": gpu}})
+    dens = []
+    out = wrapper.sampler.sample(steps=steps, batch_size=1, shape=[4, hw, hw], x_T=x_T.clone(), rng_compat=False,
+                                 callback=lambda d: dens.append(d["eps"].clone().cpu()), **dict(kw))
+    torch.cuda.synchronize()
+    assert len(dens) == steps == len(od.trace)
+    for i, d in enumerate(dens):
+        r = rel(d, od.trace[i]["denoised"])
+        print(f"  step {i}: denoised rel {r:.3e}")
+        assert r < 2e-2
+    r = rel(out, ref)
+    print(f"config 1: final latent rel-L2 {r:.3e}")
+    assert r < 2e-2
+
+
+def test_config3_sd21_vprediction_euler_ancestral_seeded_noise(cpd):
+    """BASELINE.json configs[2] at a CPU-checkable size: SD-2.1 UNet (head dim 64, linear projections, 1024-d context),
+    v-prediction, Euler-ancestral with cpd/noise.py seeded noise ('iter' mode: first draw uses seed + 1), one image per
+    GPU (the batch-8 config shards one image per GPU with no collective)."""
+    from complex_prompt_diffusion_b200 import samplers
+    from complex_prompt_diffusion_b200.noise import NoiseGenerator
+    from oracle.denoiser import OracleDenoiser
+    from oracle import samplers as OS
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    cfg, oracle, gpu = _unet_pair("sd21", torch.float32)
+    oracle.sd = {k: v.to(torch.bfloat16).float() for k, v in oracle.sd.items()}
+    g = torch.Generator().manual_seed(21)
+    hw, steps, seed = 32, 4, 1234
+    uc = torch.randn(1, 77, cfg.context_dim, generator=g)
+    c = {"and": [(1.0, torch.randn(1, 77, cfg.context_dim, generator=g), None, 1)], "not": []}
+    shape = (1, 4, hw, hw)
+    x_T = OS.OracleNoiseGenerator(shape, "cpu", seed=seed).sample()
+    assert torch.equal(x_T, NoiseGenerator(shape, "cpu", seed=seed).sample())  # both draw with seed + 1
+    kw = dict(conditioning=c, unconditional_conditioning=uc, unconditional_guidance_scale=7.5, scheduler="karras",
+              pred_type="velocity")
+    od = OracleDenoiser(_oracle_side(oracle), dtype=torch.bfloat16)
+    od.trace = []
+    ong = OS.OracleNoiseGenerator(shape, "cpu", seed=seed + 100)
+    ref = OS.sample(od, "Euler Ancestral", steps, x_T.clone(), noise_sampler=lambda x: ong.sample(), **dict(kw))
+    wrapper = samplers.make({"name": "Euler Ancestral", "args": {}}, {"model": {"unet": gpu}})
+    ng = NoiseGenerator(shape, DEV, seed=seed + 100)
+    out = wrapper.sampler.sample(steps=steps, batch_size=1, shape=[4, hw, hw], x_T=x_T.clone(), rng_compat=False,
+                                 noise_sampler=ng.sampler(), **dict(kw))
+    torch.cuda.synchronize()
+    r = rel(out, ref)
+    print(f"config 3 (sd21 v-pred Euler-a, {hw}x{hw}): final latent rel-L2 {r:.3e}")
+    assert torch.isfinite(out).all()
+    assert r < 2e-2
+
+
+def test_config2_full_size_properties(cpd):
+    """BASELINE.json configs[1] at FULL size (SD-1.5, 64x64 latent, DPM++ 2M Karras 20 steps, 3 weighted sub-prompts +
+    uncond, batch 4) - too large for the CPU oracle, so checked through size-independent properties: (1) the run is
+    bit-reproducible; (2) images of a batch are independent trajectories: image b of the batch-4 run equals a batch-1
+    run of the same x_T[b] (different GEMM tile variants may be tuned per shape -> 16-bit-level tolerance, not bits);
+    (3) with every sub-prompt equal to the unconditional embedding the guidance term vanishes, so the result must not
+    depend on the guidance scale."""
+    from complex_prompt_diffusion_b200 import samplers
+    cfg, _, gpu = _unet_pair("sd15", torch.float32)
+    g = torch.Generator().manual_seed(5)
+    hw, steps, B = 64, 20, 4
+    D = cfg.context_dim
+    uc = torch.randn(1, 77, D, generator=g).to(DEV)
+    embs = [torch.randn(1, 77, D, generator=g).to(DEV) for _ in range(3)]
+    c = {"and": [(1.0, embs[0], None, 1), (0.6, embs[1], None, 1)], "not": [(0.4, embs[2], None, 1)]}
+    x_T = torch.randn(B, 4, hw, hw, generator=g).to(DEV)
+    wrapper = samplers.make({"name": "DPM++ 2m", "args": {}}, {"model": {"unet": gpu}})
+
+    def run(x, cond, s=7.5):
+        out = wrapper.sampler.sample(steps=steps, batch_size=x.shape[0], shape=[4, hw, hw], x_T=x.clone(), rng_compat=False,
+                                     conditioning=cond, unconditional_conditioning=uc, unconditional_guidance_scale=s,
+                                     scheduler="karras")
+        torch.cuda.synchronize()
+        return out.clone()
+
+    a = run(x_T, c)
+    assert torch.isfinite(a).all() and a.shape == (B, 4, hw, hw)
+    assert torch.equal(a, run(x_T, c)), "the sampling loop is not bit-reproducible"
+    for b in (0, B - 1):
+        r = rel(run(x_T[b:b + 1], c), a[b:b + 1])
+        print(f"config 2: image {b} alone vs in the batch: rel {r:.3e}")
+        assert r < 1e-2
+    same = {"and": [(1.0, uc, None, 1), (0.6, uc, None, 1)], "not": [(0.4, uc, None, 1)]}
+    r = rel(run(x_T[:1], same, s=7.5), run(x_T[:1], same, s=1.0))
+    print(f"config 2: guidance-scale invariance with cond == uncond: rel {r:.3e}")
+    assert r < 1e-5

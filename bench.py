@@ -43,7 +43,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--model", default=WORKLOAD["model"], choices=["sd15", "sd21", "tiny"])
+    ap.add_argument("--model", default=WORKLOAD["model"], choices=["sd15", "sd21", "sdxl", "tiny", "tiny_xl"])
+    ap.add_argument("--sampler", default=WORKLOAD["sampler"], choices=["Euler", "Euler Ancestral", "DPM++ 2m"])
+    ap.add_argument("--n-sub", type=int, default=WORKLOAD["n_sub"], help="weighted sub-prompts per image (UNet rows = 1 + n_sub)")
+    ap.add_argument("--pred-type", default="epsilon", choices=["epsilon", "velocity"])
     ap.add_argument("--latent", type=int, default=WORKLOAD["latent"])
     ap.add_argument("--batch", type=int, default=WORKLOAD["batch"])
     ap.add_argument("--sampler-steps", type=int, default=WORKLOAD["sampler_steps"])
@@ -61,7 +64,8 @@ def peaks():
 
 
 def make_inputs(cfg, latent, batch, n_sub, seed=0):
-    """Synthetic prompts / latents of the named shape: emb_k ~ N(0,1) [1,77,D], x_T ~ N(0,1)."""
+    """Synthetic prompts / latents of the named shape: emb_k ~ N(0,1) [1,77,D], x_T ~ N(0,1).
+    UNets with vector conditioning (SDXL) also get y ~ N(0,1) [1 + n_sub, adm] through make_y."""
     g = torch.Generator().manual_seed(1000 + seed)
     D = cfg.context_dim
     uc = torch.randn(1, 77, D, generator=g)
@@ -71,6 +75,23 @@ def make_inputs(cfg, latent, batch, n_sub, seed=0):
          "not": [(weights[n_sub - 1], embs[n_sub - 1], None, 1)] if n_sub > 1 else []}
     x_T = torch.randn(batch, 4, latent, latent, generator=g)
     return uc, c, x_T
+
+
+def make_y(cfg, n_sub, seed=0):
+    if not cfg.adm_in_channels:
+        return None
+    return torch.randn(1 + n_sub, cfg.adm_in_channels, generator=torch.Generator().manual_seed(2000 + seed))
+
+
+def workload_of(args):
+    """The default is BASELINE.json configs[1]; other flags describe what was actually run."""
+    w = dict(WORKLOAD, model=args.model, latent=args.latent, batch=args.batch, sampler_steps=args.sampler_steps, sampler=args.sampler,
+             n_sub=args.n_sub, pred_type=args.pred_type)
+    if (args.model, args.latent, args.batch, args.sampler_steps, args.sampler, args.n_sub) != (
+            WORKLOAD["model"], WORKLOAD["latent"], WORKLOAD["batch"], WORKLOAD["sampler_steps"], WORKLOAD["sampler"], WORKLOAD["n_sub"]):
+        w["workload"] = (f"{args.model} {args.latent * 8}px ({args.latent}x{args.latent} latent), {args.sampler} Karras {args.sampler_steps} steps, "
+                         f"{args.n_sub} weighted sub-prompt(s) + uncond, batch {args.batch} per GPU, {args.pred_type}-prediction")
+    return w
 
 
 def oracle_cfg(name):
@@ -116,7 +137,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------ CPU arm
-def cpu_sample(cfg_name, latent, n_sub, sampler_steps_sample, threads):
+def cpu_sample(cfg_name, latent, n_sub, sampler_steps_sample, threads, sampler="DPM++ 2m", pred_type="epsilon", total_steps=None):
     """Times the oracle port on the host cores on a BOUNDED sample: `sampler_steps_sample` sampler steps of ONE
     image (each = 1 + n_sub UNet row-evaluations, fp32), returns seconds per (image x sampler-step)."""
     from oracle.unet import OracleUNet, make_weights
@@ -127,11 +148,18 @@ def cpu_sample(cfg_name, latent, n_sub, sampler_steps_sample, threads):
     unet = OracleUNet(cfg, make_weights(cfg, seed=0))
     uc, c, x_T = make_inputs(cfg, latent, 1, n_sub)
     den = OracleDenoiser(unet)
-    sig = den.scheduler.get_sigmas("karras", WORKLOAD["sampler_steps"])
+    sig = den.scheduler.get_sigmas("karras", total_steps or WORKLOAD["sampler_steps"])
     x = x_T * sig[0]
-    kw = dict(conditioning=c, unconditional_conditioning=uc, unconditional_guidance_scale=WORKLOAD["guidance"], total_steps=len(sig))
+    kw = dict(conditioning=c, unconditional_conditioning=uc, unconditional_guidance_scale=WORKLOAD["guidance"], total_steps=len(sig),
+              pred_type=pred_type)
+    y = make_y(cfg, n_sub)
+    if y is not None:
+        kw["y"] = y
     t0 = time.perf_counter()
-    OS.sample_dpmpp_2m(den, x, sig[:sampler_steps_sample + 1], kw)
+    if sampler == "DPM++ 2m":
+        OS.sample_dpmpp_2m(den, x, sig[:sampler_steps_sample + 1], kw)
+    else:
+        OS.SAMPLERS[sampler](den, x, sig[:sampler_steps_sample + 1], kw, lambda t: torch.randn_like(t))
     dt = time.perf_counter() - t0
     return dt / sampler_steps_sample
 
@@ -143,20 +171,20 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     sample_steps = 1
     for _ in range(args.warmup if args.latent <= 16 else 0):
-        cpu_sample(args.model, args.latent, WORKLOAD["n_sub"], sample_steps, threads)
-    times = [cpu_sample(args.model, args.latent, WORKLOAD["n_sub"], sample_steps, threads) for _ in range(max(1, min(args.steps, 3)))]
+        cpu_sample(args.model, args.latent, args.n_sub, sample_steps, threads, args.sampler, args.pred_type, args.sampler_steps)
+    times = [cpu_sample(args.model, args.latent, args.n_sub, sample_steps, threads, args.sampler, args.pred_type, args.sampler_steps)
+             for _ in range(max(1, min(args.steps, 3)))]
     per_img_step = sum(times) / len(times)
     sec_per_batch = per_img_step * args.sampler_steps * args.batch
     ips = args.batch / sec_per_batch
-    sample = (f"{sample_steps} sampler step(s) of 1 image = {1 + WORKLOAD['n_sub']} fp32 UNet row-evals of the same workload, "
+    sample = (f"{sample_steps} sampler step(s) of 1 image = {1 + args.n_sub} fp32 UNet row-evals of the same workload, "
               f"x{len(times)}, extrapolated linearly to {args.sampler_steps} steps x {args.batch} images")
     line = {"impl": "reference", "metric": "images_per_s", "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec_per_batch * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": dict(WORKLOAD, model=args.model, latent=args.latent, batch=args.batch,
-                                                                sampler_steps=args.sampler_steps),
+            "dtype": "f32", "data": "synthetic", "config": workload_of(args),
             "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "unet_evals_per_s": ips * args.sampler_steps * (1 + WORKLOAD["n_sub"]), "gpu_launches": 0}
+            "unet_evals_per_s": ips * args.sampler_steps * (1 + args.n_sub), "gpu_launches": 0}
     print(json.dumps(line))
 
 
@@ -179,12 +207,16 @@ def run_b200(args):
     unet = UNetModel(sd, device=dev, model_channels=cfg.model_channels, channel_mult=tuple(cfg.channel_mult),
                      attention_resolutions=tuple(cfg.attention_resolutions), num_res_blocks=cfg.num_res_blocks,
                      num_heads=cfg.num_heads, num_head_channels=cfg.num_head_channels, context_dim=cfg.context_dim,
-                     use_linear_in_transformer=cfg.use_linear_in_transformer)
+                     use_linear_in_transformer=cfg.use_linear_in_transformer, transformer_depth=cfg.transformer_depth,
+                     adm_in_channels=cfg.adm_in_channels, num_classes="sequential" if cfg.adm_in_channels else None)
     del sd
-    n_sub, B, S = WORKLOAD["n_sub"], args.batch, args.sampler_steps
+    n_sub, B, S = args.n_sub, args.batch, args.sampler_steps
     uc, c, x_T = make_inputs(cfg, args.latent, B, n_sub, seed=rank)
-    wrapper = samplers.make({"name": WORKLOAD["sampler"], "args": {}}, {"model": {"unet": unet}})
-    kw = dict(unconditional_guidance_scale=WORKLOAD["guidance"], scheduler=WORKLOAD["scheduler"], rng_compat=False)
+    wrapper = samplers.make({"name": args.sampler, "args": {}}, {"model": {"unet": unet}})
+    kw = dict(unconditional_guidance_scale=WORKLOAD["guidance"], scheduler=WORKLOAD["scheduler"], rng_compat=False, pred_type=args.pred_type)
+    y = make_y(cfg, n_sub, seed=rank)
+    if y is not None:
+        kw["y"] = y.to(dev)
 
     # resident inputs
     uc_d = uc.to(dev)
@@ -305,7 +337,7 @@ def run_b200(args):
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        per = cpu_sample(args.model, args.latent, n_sub, 1, threads)
+        per = cpu_sample(args.model, args.latent, n_sub, 1, threads, args.sampler, args.pred_type, S)
         sec_batch = per * S * B
         cpu = {"value": B / sec_batch, "unit": "images/s", "cores": threads, "kind": "port",
                "sample": f"1 sampler step of 1 image ({R} fp32 UNet row-evals, oracle port) = {per:.2f} s, extrapolated linearly to "
@@ -314,7 +346,7 @@ def run_b200(args):
         line = {"metric": "images_per_s", "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16",
                 "data": "synthetic",
-                "config": dict(WORKLOAD, model=args.model, latent=args.latent, batch=B, sampler_steps=S, parallelism=f"images sharded x{world}",
+                "config": dict(workload_of(args), parallelism=f"images sharded x{world}",
                                l2="working set (1.7 GB weights + activations) larger than L2; no flush needed",
                                precision="bf16 model weights converted once to fp16 tensor-core operands, fp16 activations, fp32 "
                                          "accumulation and norm statistics (same tensor rate as bf16, 3 more mantissa bits: "

@@ -29,19 +29,24 @@ def _enumerate_blocks(cfg):
     chans = [mc]
     ch, ds = mc, 1
     mult_list = list(cfg["channel_mult"])
+    td = cfg["transformer_depth"]
+
+    def depth(level):  # int, or one depth per level (SDXL extension; the middle block uses the last level's)
+        return td if isinstance(td, int) else list(td)[min(level, len(td) - 1)]
+
     for level, mult in enumerate(mult_list):
         for _ in range(cfg["num_res_blocks"]):
             layers = [("res", ch, mult * mc)]
             ch = mult * mc
             if ds in cfg["attention_resolutions"]:
-                layers.append(("attn", ch))
+                layers.append(("attn", ch, depth(level)))
             inputs.append(layers)
             chans.append(ch)
         if level != len(mult_list) - 1:
             inputs.append([("down", ch)])
             chans.append(ch)
             ds *= 2
-    middle = [("res", ch, ch), ("attn", ch), ("res", ch, ch)]
+    middle = [("res", ch, ch), ("attn", ch, depth(len(mult_list) - 1)), ("res", ch, ch)]
     outputs = []
     for level, mult in list(enumerate(mult_list))[::-1]:
         for i in range(cfg["num_res_blocks"] + 1):
@@ -49,7 +54,7 @@ def _enumerate_blocks(cfg):
             layers = [("res", ch + ich, mc * mult, ch, ich)]
             ch = mc * mult
             if ds in cfg["attention_resolutions"]:
-                layers.append(("attn", ch))
+                layers.append(("attn", ch, depth(level)))
             if level and i == cfg["num_res_blocks"]:
                 layers.append(("up", ch))
                 ds //= 2
@@ -65,7 +70,7 @@ class UNetModel:
     DEFAULTS = dict(image_size=32, in_channels=4, model_channels=320, out_channels=4, num_res_blocks=2,
                     attention_resolutions=(4, 2, 1), channel_mult=(1, 2, 4, 4), num_heads=8, num_head_channels=-1,
                     transformer_depth=1, context_dim=768, use_linear_in_transformer=False, use_spatial_transformer=True,
-                    legacy=False)
+                    legacy=False, adm_in_channels=0)
     GEGLU_BLOCK = 256
 
     def __init__(self, state_dict=None, device="cuda", act_dtype=torch.float16, eps_dtype=torch.float32, use_cuda_graph=True,
@@ -74,10 +79,10 @@ class UNetModel:
         cfg.update({k: v for k, v in config.items() if k in self.DEFAULTS})
         if not cfg["use_spatial_transformer"] or cfg["legacy"]:
             raise NotImplementedError("only the SpatialTransformer (legacy=False) UNet of the SD configs is supported")
-        if cfg["transformer_depth"] != 1:
-            raise NotImplementedError("transformer_depth != 1")
-        if config.get("num_classes") is not None:
-            raise NotImplementedError("class-conditional UNets are not on the hot path")
+        if config.get("num_classes") not in (None, "sequential"):
+            raise NotImplementedError("class-conditional UNets are not on the hot path (only the SDXL vector conditioning is)")
+        if (config.get("num_classes") == "sequential") != bool(cfg["adm_in_channels"]):
+            raise ValueError("vector conditioning needs num_classes='sequential' together with adm_in_channels > 0")
         self.cfg = cfg
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -97,6 +102,8 @@ class UNetModel:
         self.use_cuda_graph = bool(use_cuda_graph)
         self._ctx = None
         self._ctx_key = None
+        self._y = None  # vector conditioning rows (SDXL), bf16 [rows, adm_in_channels], stable address
+        self._y_key = None
         self._probe = torch.zeros(1, dtype=self.dtype, device=self.device)
         if state_dict is not None:
             self.load_state_dict(state_dict)
@@ -148,6 +155,13 @@ class UNetModel:
         ted = self.model_channels * 4
         W["te0.w"], W["te0.b"] = mat("time_embed.0.weight"), f32("time_embed.0.bias")
         W["te2.w"], W["te2.b"] = mat("time_embed.2.weight"), f32("time_embed.2.bias")
+        self.adm = int(self.cfg["adm_in_channels"])
+        if self.adm:
+            # emb = time_embed(t_emb) + label_emb(y) (SDXL extension) is ONE small linear over [SiLU(e1) | SiLU(l1)]:
+            # the second layers are concatenated along K and their biases summed
+            W["lab0.w"], W["lab0.b"] = mat("label_emb.0.0.weight"), f32("label_emb.0.0.bias")
+            W["te2lab2.w"] = torch.cat([bf(sd["time_embed.2.weight"]), bf(sd["label_emb.0.2.weight"])], dim=1).contiguous().to(dev)
+            W["te2lab2.b"] = (bf(sd["time_embed.2.bias"]).float() + bf(sd["label_emb.0.2.bias"]).float()).contiguous().to(dev)
         emb_w, emb_b, emb_off = [], [], {}
         off = 0
 
@@ -164,13 +178,16 @@ class UNetModel:
             if cin != cout:
                 W[p + "skip.w"], W[p + "skip.b"] = mat(p + "skip_connection.weight"), f32(p + "skip_connection.bias")
 
-        def attn(p, ch):
-            nh, dh = self.heads(ch)
-            dpad = _round16(dh)
+        def attn(p, ch, depth):
             W[p + "norm.g"], W[p + "norm.b"] = f32(p + "norm.weight"), f32(p + "norm.bias")
             W[p + "proj_in.w"], W[p + "proj_in.b"] = mat(p + "proj_in.weight"), f32(p + "proj_in.bias")
             W[p + "proj_out.w"], W[p + "proj_out.b"] = mat(p + "proj_out.weight"), f32(p + "proj_out.bias")
-            b = p + "transformer_blocks.0."
+            for d in range(depth):
+                tblock(p + f"transformer_blocks.{d}.", ch)
+
+        def tblock(b, ch):
+            nh, dh = self.heads(ch)
+            dpad = _round16(dh)
             for n in ("norm1", "norm2", "norm3"):
                 W[b + n + ".g"], W[b + n + ".b"] = f32(b + n + ".weight"), f32(b + n + ".bias")
             q1 = pad_rows(bf(sd[b + "attn1.to_q.weight"]), nh, dh, dpad)
@@ -204,7 +221,7 @@ class UNetModel:
                 elif l[0] == "res":
                     res(p, l[1], l[2])
                 elif l[0] == "attn":
-                    attn(p, l[1])
+                    attn(p, l[1], l[2])
                 elif l[0] == "down":
                     W[p + "w"], W[p + "b"] = conv3(p + "op.weight"), f32(p + "op.bias")
                 elif l[0] == "up":
@@ -223,7 +240,7 @@ class UNetModel:
         # tcgen05 kind::f16 needs A and B in the SAME 16-bit format (mixed fp16 x bf16 raises an illegal-instruction
         # trap on sm_100a), so tensor-core weights are stored in the activation dtype.  bf16 -> fp16 is exact for
         # every weight with |w| >= 2^-14 (fp16 has the wider mantissa); smaller ones move by < 3e-8 absolute.
-        cuda_core = {"te0.w", "te2.w", "emb_all.w", "input_blocks.0.0.w", "out.w"}
+        cuda_core = {"te0.w", "te2.w", "emb_all.w", "input_blocks.0.0.w", "out.w", "lab0.w", "te2lab2.w"}
         for key in list(W):
             if key.endswith(".w") and key not in cuda_core:
                 W[key] = W[key].to(self.act_dtype)
@@ -258,17 +275,36 @@ class UNetModel:
             for j, l in enumerate(layers):
                 if l[0] != "attn":
                     continue
-                b = f"{prefix}{j}.transformer_blocks.0."
-                wk, wv = self.w[b + "attn2.k.w"], self.w[b + "attn2.v.w"]
-                ip = wk.shape[0]
-                # persistent buffers (stable addresses: captured CUDA graphs stay valid across prompts)
-                kc = self._buf(b + "kc", rc * nk_pad * ip).view(rc * nk_pad, ip)
-                vt = self._buf(b + "vt", ip * rc * nk_pad).view(ip, rc * nk_pad)
-                ops.gemm_conv(ctx_pad, wk, kc, n_img=1, h=1, w=rc * nk_pad, c0=D, n_out=ip)
-                ops.gemm_conv(wv, ctx_pad, vt, n_img=1, h=1, w=ip, c0=D, n_out=rc * nk_pad)
-                kv[b] = (kc, vt)
+                for d in range(l[2]):
+                    b = f"{prefix}{j}.transformer_blocks.{d}."
+                    wk, wv = self.w[b + "attn2.k.w"], self.w[b + "attn2.v.w"]
+                    ip = wk.shape[0]
+                    # persistent buffers (stable addresses: captured CUDA graphs stay valid across prompts)
+                    kc = self._buf(b + "kc", rc * nk_pad * ip).view(rc * nk_pad, ip)
+                    vt = self._buf(b + "vt", ip * rc * nk_pad).view(ip, rc * nk_pad)
+                    ops.gemm_conv(ctx_pad, wk, kc, n_img=1, h=1, w=rc * nk_pad, c0=D, n_out=ip)
+                    ops.gemm_conv(wv, ctx_pad, vt, n_img=1, h=1, w=ip, c0=D, n_out=rc * nk_pad)
+                    kv[b] = (kc, vt)
         self._ctx = dict(rc=rc, ntok=ntok, nk_pad=nk_pad, kv=kv, keep=ctx_pad)
         self._ctx_key = key
+
+    def set_vector(self, y):
+        """Vector conditioning of the SDXL extension: y [Ry, adm_in_channels]; UNet row b uses y row (b % Ry).  Kept in a
+        persistent bf16 buffer (the model dtype), so captured graphs stay valid when the prompt changes."""
+        if not self.adm:
+            if y is not None:
+                raise ValueError("this UNet has no vector conditioning (adm_in_channels = 0)")
+            return
+        if y is None:
+            raise ValueError(f"this UNet needs vector conditioning y [rows, {self.adm}]")
+        key = (y.data_ptr(), tuple(y.shape), y._version)
+        if self._y_key == key:
+            return
+        if y.ndim != 2 or y.shape[1] != self.adm:
+            raise ValueError(f"y must be [rows, {self.adm}], got {tuple(y.shape)}")
+        buf = self._buf("y", y.shape[0] * self.adm, torch.bfloat16).view(y.shape[0], self.adm)
+        buf.copy_(y.to(self.device, torch.bfloat16))
+        self._y, self._y_key = buf, key
 
     def _all_blocks(self):
         for i, layers in enumerate(self.inputs):
@@ -300,7 +336,7 @@ class UNetModel:
                       residual=skip, ld_res=cout)
         return out
 
-    def _attn(self, p, x, ch, R, h, w, stats):
+    def _attn(self, p, x, ch, R, h, w, stats, depth=1):
         W = self.w
         hw = h * w
         T = R * hw
@@ -308,42 +344,43 @@ class UNetModel:
         dpad = _round16(dh)
         ip = nh * dpad
         scale = dh ** -0.5
-        b = p + "transformer_blocks.0."
         gn = self._buf("gn", T * ch)
         ops.groupnorm(x, W[p + "norm.g"], W[p + "norm.b"], gn, stats, n_img=R, hw=hw, c0=ch, eps=1e-6, silu=False)
         hcur = self._buf("tr.h", T * ch)
         ops.gemm_conv(gn, W[p + "proj_in.w"], hcur, n_img=1, h=1, w=T, c0=ch, n_out=ch, bias=W[p + "proj_in.b"])
         ln = self._buf("tr.ln", T * ch)
-        # --- self-attention
-        ops.layernorm(hcur, W[b + "norm1.g"], W[b + "norm1.b"], ln, rows=T, c=ch)
-        qk = self._buf("tr.qk", T * 2 * ip)
-        ops.gemm_conv(ln, W[b + "attn1.qk.w"], qk, n_img=1, h=1, w=T, c0=ch, n_out=2 * ip)
-        vt = self._buf("tr.vt", ip * T)
-        ops.gemm_conv(W[b + "attn1.v.w"], ln, vt, n_img=1, h=1, w=ip, c0=ch, n_out=T)
-        o = self._buf("tr.o", T * ip)
-        ops.attention(qk, qk[ip:], vt, o, ldq=2 * ip, ldk=2 * ip, ldvt=T, ldo=ip, batch=R, heads=nh, nq=hw, nk=hw, nk_pad=hw,
-                      dpad=dpad, scale=scale, d_head=dh)
-        ops.gemm_conv(o, W[b + "attn1.out.w"], hcur, n_img=1, h=1, w=T, c0=ip, n_out=ch, bias=W[b + "attn1.out.b"],
-                      residual=hcur, ld_res=ch)
-        # --- cross-attention (K / V^T cached per prompt)
-        ctx = self._ctx
-        if ctx is None:
-            raise RuntimeError("UNetModel: no text context set (call set_context or pass `context`)")
-        kc, vtc = ctx["kv"][b]
-        ops.layernorm(hcur, W[b + "norm2.g"], W[b + "norm2.b"], ln, rows=T, c=ch)
-        q2 = self._buf("tr.q2", T * ip)
-        ops.gemm_conv(ln, W[b + "attn2.q.w"], q2, n_img=1, h=1, w=T, c0=ch, n_out=ip)
-        ops.attention(q2, kc, vtc, o, ldq=ip, ldk=ip, ldvt=ctx["rc"] * ctx["nk_pad"], ldo=ip, batch=R, heads=nh, nq=hw,
-                      nk=ctx["ntok"], nk_pad=ctx["nk_pad"], dpad=dpad, scale=scale, kv_batch=ctx["rc"], d_head=dh)
-        ops.gemm_conv(o, W[b + "attn2.out.w"], hcur, n_img=1, h=1, w=T, c0=ip, n_out=ch, bias=W[b + "attn2.out.b"],
-                      residual=hcur, ld_res=ch)
-        # --- GEGLU feed-forward
-        ops.layernorm(hcur, W[b + "norm3.g"], W[b + "norm3.b"], ln, rows=T, c=ch)
-        ff = self._buf("tr.ff", T * 4 * ch)
-        ops.gemm_conv(ln, W[b + "ff1.w"], ff, n_img=1, h=1, w=T, c0=ch, n_out=8 * ch, bias=W[b + "ff1.b"], epilogue=CPD_EPI_GEGLU,
-                      geglu_block=self.GEGLU_BLOCK)
-        ops.gemm_conv(ff, W[b + "ff2.w"], hcur, n_img=1, h=1, w=T, c0=4 * ch, n_out=ch, bias=W[b + "ff2.b"], residual=hcur,
-                      ld_res=ch)
+        for d in range(depth):
+            b = p + f"transformer_blocks.{d}."
+            # --- self-attention
+            ops.layernorm(hcur, W[b + "norm1.g"], W[b + "norm1.b"], ln, rows=T, c=ch)
+            qk = self._buf("tr.qk", T * 2 * ip)
+            ops.gemm_conv(ln, W[b + "attn1.qk.w"], qk, n_img=1, h=1, w=T, c0=ch, n_out=2 * ip)
+            vt = self._buf("tr.vt", ip * T)
+            ops.gemm_conv(W[b + "attn1.v.w"], ln, vt, n_img=1, h=1, w=ip, c0=ch, n_out=T)
+            o = self._buf("tr.o", T * ip)
+            ops.attention(qk, qk[ip:], vt, o, ldq=2 * ip, ldk=2 * ip, ldvt=T, ldo=ip, batch=R, heads=nh, nq=hw, nk=hw, nk_pad=hw,
+                          dpad=dpad, scale=scale, d_head=dh)
+            ops.gemm_conv(o, W[b + "attn1.out.w"], hcur, n_img=1, h=1, w=T, c0=ip, n_out=ch, bias=W[b + "attn1.out.b"],
+                          residual=hcur, ld_res=ch)
+            # --- cross-attention (K / V^T cached per prompt)
+            ctx = self._ctx
+            if ctx is None:
+                raise RuntimeError("UNetModel: no text context set (call set_context or pass `context`)")
+            kc, vtc = ctx["kv"][b]
+            ops.layernorm(hcur, W[b + "norm2.g"], W[b + "norm2.b"], ln, rows=T, c=ch)
+            q2 = self._buf("tr.q2", T * ip)
+            ops.gemm_conv(ln, W[b + "attn2.q.w"], q2, n_img=1, h=1, w=T, c0=ch, n_out=ip)
+            ops.attention(q2, kc, vtc, o, ldq=ip, ldk=ip, ldvt=ctx["rc"] * ctx["nk_pad"], ldo=ip, batch=R, heads=nh, nq=hw,
+                          nk=ctx["ntok"], nk_pad=ctx["nk_pad"], dpad=dpad, scale=scale, kv_batch=ctx["rc"], d_head=dh)
+            ops.gemm_conv(o, W[b + "attn2.out.w"], hcur, n_img=1, h=1, w=T, c0=ip, n_out=ch, bias=W[b + "attn2.out.b"],
+                          residual=hcur, ld_res=ch)
+            # --- GEGLU feed-forward
+            ops.layernorm(hcur, W[b + "norm3.g"], W[b + "norm3.b"], ln, rows=T, c=ch)
+            ff = self._buf("tr.ff", T * 4 * ch)
+            ops.gemm_conv(ln, W[b + "ff1.w"], ff, n_img=1, h=1, w=T, c0=ch, n_out=8 * ch, bias=W[b + "ff1.b"], epilogue=CPD_EPI_GEGLU,
+                          geglu_block=self.GEGLU_BLOCK)
+            ops.gemm_conv(ff, W[b + "ff2.w"], hcur, n_img=1, h=1, w=T, c0=4 * ch, n_out=ch, bias=W[b + "ff2.b"], residual=hcur,
+                          ld_res=ch)
         out = self._buf(p + "out", T * ch)
         ops.gemm_conv(hcur, W[p + "proj_out.w"], out, n_img=1, h=1, w=T, c0=ch, n_out=ch, bias=W[p + "proj_out.b"],
                       residual=x, ld_res=ch)
@@ -362,7 +399,7 @@ class UNetModel:
                     hcur = self._res(p, hcur, None, l[1], 0, l[2], R, h, w, emb_all, emb_stride, stats)
                 ch = l[2]
             elif l[0] == "attn":
-                hcur = self._attn(p, hcur, l[1], R, h, w, stats)
+                hcur = self._attn(p, hcur, l[1], R, h, w, stats, l[2])
                 ch = l[1]
             elif l[0] == "down":
                 ch = l[1]
@@ -380,17 +417,24 @@ class UNetModel:
         return hcur, ch, h, w
 
     # ---- forward ---------------------------------------------------------------------------------------
-    def _embeddings(self, t_rows):
-        """t_rows: fp32 device tensor [m] (already rounded to the model dtype).  Returns fp32 [m, emb_total]."""
+    def _embeddings(self, t_rows, y_rows=None):
+        """t_rows: fp32 device tensor [m] (already rounded to the model dtype); y_rows: bf16 [m, adm] or None.
+        Returns fp32 [m, emb_total]."""
         W = self.w
         m = t_rows.numel()
         mc, ted = self.model_channels, self.ted
         temb = self._buf("temb", m * mc, torch.bfloat16)
         ops.timestep_embedding(t_rows, temb, dim=mc, round_t_bf16=False)
-        e1 = self._buf("e1", m * ted, torch.bfloat16)
-        ops.small_linear(temb, W["te0.w"], W["te0.b"], m=m, k=mc, n=ted, out_bf16=e1)
         emb = self._buf("emb", m * ted, torch.bfloat16)
-        ops.small_linear(e1, W["te2.w"], W["te2.b"], m=m, k=ted, n=ted, silu_in=True, out_bf16=emb)
+        if self.adm:
+            e1l1 = self._buf("e1l1", m * 2 * ted, torch.bfloat16)  # [m][SiLU inputs of time_embed.2 | label_emb.0.2]
+            ops.small_linear(temb, W["te0.w"], W["te0.b"], m=m, k=mc, n=ted, out_bf16=e1l1, ld_out=2 * ted)
+            ops.small_linear(y_rows, W["lab0.w"], W["lab0.b"], m=m, k=self.adm, n=ted, out_bf16=e1l1[ted:], ld_out=2 * ted)
+            ops.small_linear(e1l1, W["te2lab2.w"], W["te2lab2.b"], m=m, k=2 * ted, n=ted, silu_in=True, out_bf16=emb)
+        else:
+            e1 = self._buf("e1", m * ted, torch.bfloat16)
+            ops.small_linear(temb, W["te0.w"], W["te0.b"], m=m, k=mc, n=ted, out_bf16=e1)
+            ops.small_linear(e1, W["te2.w"], W["te2.b"], m=m, k=ted, n=ted, silu_in=True, out_bf16=emb)
         emb_all = self._buf("emb_all", m * self.emb_total, torch.float32)
         ops.small_linear(emb, W["emb_all.w"], W["emb_all.b"], m=m, k=ted, n=self.emb_total, silu_in=True, out_f32=emb_all)
         return emb_all
@@ -400,7 +444,24 @@ class UNetModel:
         B, cin, h, w = x.shape
         R = B * rows_per_image
         stats = self._buf("gn.stats", R * 64 * ops.GN_MAX_CHUNKS, torch.float64)
-        emb_all = self._embeddings(t_rows)
+        if self.adm:
+            # vector conditioning differs per conditioning row: one embedding row per UNet row (t repeated when shared)
+            if self._y is None:
+                raise RuntimeError("UNetModel: no vector conditioning set (call set_vector or pass `y`)")
+            if R > 16:
+                raise NotImplementedError("more than 16 UNet rows per evaluation with vector conditioning (shard the batch)")
+            y_rows = self._buf("y_rows", R * self.adm, torch.bfloat16).view(R, self.adm)
+            ry = self._y.shape[0]
+            if R % ry:
+                raise ValueError(f"{R} UNet rows are not a multiple of the {ry} vector-conditioning rows")
+            y_rows.copy_(self._y.repeat(R // ry, 1))
+            if shared_t:
+                t_all = self._buf("t_rows", R, torch.float32)
+                t_all.copy_(t_rows.reshape(1).expand(R))
+                t_rows, shared_t = t_all, False
+            emb_all = self._embeddings(t_rows, y_rows)
+        else:
+            emb_all = self._embeddings(t_rows)
         emb_stride = 0 if shared_t else self.emb_total
         mc = self.model_channels
         h0 = self._buf("input_blocks.0.out", R * h * w * mc)
@@ -437,7 +498,8 @@ class UNetModel:
         # One CUDA graph per (shape, rows, context layout): the ~850 kernel launches of an evaluation are replayed with a
         # single cudaGraphLaunch; the per-step scalars (c_in, t) and x live in static device buffers.
         ctx = self._ctx
-        key = (tuple(x.shape), rows_per_image, None if ctx is None else (ctx["rc"], ctx["ntok"]))
+        key = (tuple(x.shape), rows_per_image, None if ctx is None else (ctx["rc"], ctx["ntok"]),
+               None if self._y is None else tuple(self._y.shape))
         g = self._graphs.get(key)
         if g is None:
             st = dict(x=torch.empty(tuple(x.shape), dtype=torch.float32, device=self.device),
@@ -464,8 +526,8 @@ class UNetModel:
     def forward(self, x, timesteps=None, context=None, y=None, **kwargs):
         """Reference call signature (unet.py:765): x [N,4,h,w], timesteps [N], context [N or Rc, tokens, D].
         Returns out [N,4,h,w] (bf16) or (out, skips) when return_attn=True (the 12 skip tensors, unet.py:802-804)."""
-        if y is not None:
-            raise NotImplementedError("class-conditional UNets are not on the hot path")
+        if y is not None or self.adm:
+            self.set_vector(y)
         for k in ("inject_feats", "inject_attns", "return_feat"):
             if kwargs.get(k):
                 raise NotImplementedError(f"UNetModel kwarg {k!r} is outside the hot-path scope")

@@ -103,17 +103,32 @@ class Denoiser(torch.nn.Module):
         if kwargs.get("pred_type", "epsilon") not in ("epsilon", "velocity"):
             raise ValueError(f"unknown pred_type {kwargs.get('pred_type')!r}")
 
-    def plan_conditioning(self, c, uc, hw_shape):
+    def plan_conditioning(self, c, uc, hw_shape, y=None):
+        """`y` (extension for UNets with vector conditioning, i.e. SDXL - not expressible by the reference): tensor
+        [1 + N, adm] with one row per UNet row (row 0 = unconditional) or [1, adm] shared by all rows."""
         if isinstance(c, list):
             raise NotImplementedError("per-step conditioning lists are not supported")
-        key = (id(c), id(uc), tuple(hw_shape))
+        key = (id(c), id(uc), tuple(hw_shape), id(y))
         if self._plan_key != key:
             self._plan = ConditioningPlan(c, uc, self.dtype, self.device, hw_shape)
             self._plan_key = key
-            if self._part is None:
+            rows = None if self._part is None else self._part.rows
+            if rows is None:
                 self.unet.set_context(self._plan.context)
-            elif self._part.rows:
-                self.unet.set_context(self._plan.context[self._part.rows].contiguous())
+            elif rows:
+                self.unet.set_context(self._plan.context[rows].contiguous())
+            if y is not None or getattr(self.unet, "adm", 0):
+                if y is None:
+                    raise ValueError("this UNet needs vector conditioning: pass y=[1 + N, adm] (row 0 = unconditional)")
+                y = torch.as_tensor(y)
+                if y.shape[0] == 1:
+                    y = y.expand(1 + self._plan.n_sub, -1)
+                if y.shape[0] != 1 + self._plan.n_sub:
+                    raise ValueError(f"y must have 1 or {1 + self._plan.n_sub} rows, got {y.shape[0]}")
+                if rows is None:
+                    self.unet.set_vector(y.contiguous())
+                elif rows:
+                    self.unet.set_vector(y[rows].contiguous())
         return self._plan
 
     @staticmethod
@@ -168,7 +183,8 @@ class Denoiser(torch.nn.Module):
             raise ValueError(f"[denoiser] `x` has incorrect shape: {tuple(x.shape)}")
         self._check_kwargs(kwargs)
         x = x.to(self.device, torch.float32).contiguous()
-        plan = self.plan_conditioning(kwargs.get("conditioning"), kwargs.get("unconditional_conditioning"), x.shape[-2:])
+        plan = self.plan_conditioning(kwargs.get("conditioning"), kwargs.get("unconditional_conditioning"), x.shape[-2:],
+                                      y=kwargs.get("y"))
         denoised = torch.empty_like(x)
         scratch = x.clone()
         self.fused_step(scratch, sigma, plan, dict(sampler=CPD_DENOISE_ONLY, denoised_out=denoised), **kwargs)

@@ -61,7 +61,8 @@ class KDiffusionSampler:
             raise NotImplementedError("s_churn > 0 is not supported (gamma = 0 path only)")
         den = self.denoiser
         den._check_kwargs(model_args)
-        plan = den.plan_conditioning(model_args.get("conditioning"), model_args.get("unconditional_conditioning"), x.shape[-2:])
+        plan = den.plan_conditioning(model_args.get("conditioning"), model_args.get("unconditional_conditioning"), x.shape[-2:],
+                                     y=model_args.get("y"))
         return den, plan
 
     def _callback(self, callback, x_before, i, sigma, denoised):

@@ -30,9 +30,10 @@ class UNetConfig:
     channel_mult: List[int] = field(default_factory=lambda: [1, 2, 4, 4])
     num_heads: int = 8
     num_head_channels: int = -1
-    transformer_depth: int = 1
+    transformer_depth: object = 1  # int, or one depth per level (SDXL: [1, 2, 10]); the middle block uses the last
     context_dim: int = 768
     use_linear_in_transformer: bool = False
+    adm_in_channels: int = 0  # > 0: vector conditioning y -> label_emb MLP added to the time embedding (SDXL: 2816)
 
     @staticmethod
     def sd15():
@@ -41,6 +42,27 @@ class UNetConfig:
     @staticmethod
     def sd21():
         return UNetConfig(num_heads=-1, num_head_channels=64, context_dim=1024, use_linear_in_transformer=True)
+
+    @staticmethod
+    def sdxl():
+        """SDXL-base UNet (BASELINE.json configs[3]).  NOT expressible by the reference constructor (scalar
+        transformer_depth unet.py:467,593; num_classes only int / "continuous" :536-543; no yaml): an extension of the same
+        block grammar - channel_mult [1, 2, 4], attention at ds 2 and 4 with 2 and 10 transformer blocks (10 in the middle),
+        64-wide heads, linear projections, 2048-d context (two text encoders concatenated on the feature axis) and a
+        2816-d vector conditioning through label_emb = Linear -> SiLU -> Linear added to the time embedding."""
+        return UNetConfig(channel_mult=[1, 2, 4], attention_resolutions=[4, 2], num_heads=-1, num_head_channels=64,
+                          transformer_depth=[1, 2, 10], context_dim=2048, use_linear_in_transformer=True, adm_in_channels=2816)
+
+    @staticmethod
+    def tiny_xl(context_dim=128):
+        """Small config with the SDXL topology (per-level depths, label_emb) for fast tests."""
+        return UNetConfig(model_channels=64, channel_mult=[1, 2, 4], attention_resolutions=[4, 2], num_heads=-1,
+                          num_head_channels=32, transformer_depth=[1, 1, 2], context_dim=context_dim, num_res_blocks=1,
+                          use_linear_in_transformer=True, adm_in_channels=80)
+
+    def depth(self, level):
+        td = self.transformer_depth
+        return td if isinstance(td, int) else td[min(level, len(td) - 1)]
 
     @staticmethod
     def tiny(context_dim=64):
@@ -59,7 +81,7 @@ def enumerate_blocks(cfg: UNetConfig):
     """Block structure exactly as built by UNetModel.__init__ (unet.py:545-727).
 
     Returns (input_blocks, middle, output_blocks); each block is a list of layer tuples:
-      ("conv_in", cin, cout) | ("res", cin, cout) | ("attn", ch) | ("down", ch) | ("up", ch)
+      ("conv_in", cin, cout) | ("res", cin, cout) | ("attn", ch, depth) | ("down", ch) | ("up", ch)
     """
     mc = cfg.model_channels
     inputs = [[("conv_in", cfg.in_channels, mc)]]
@@ -70,14 +92,14 @@ def enumerate_blocks(cfg: UNetConfig):
             layers = [("res", ch, mult * mc)]
             ch = mult * mc
             if ds in cfg.attention_resolutions:
-                layers.append(("attn", ch))
+                layers.append(("attn", ch, cfg.depth(level)))
             inputs.append(layers)
             chans.append(ch)
         if level != len(cfg.channel_mult) - 1:
             inputs.append([("down", ch)])
             chans.append(ch)
             ds *= 2
-    middle = [("res", ch, ch), ("attn", ch), ("res", ch, ch)]
+    middle = [("res", ch, ch), ("attn", ch, cfg.depth(len(cfg.channel_mult) - 1)), ("res", ch, ch)]
     outputs = []
     for level, mult in list(enumerate(cfg.channel_mult))[::-1]:
         for i in range(cfg.num_res_blocks + 1):
@@ -85,7 +107,7 @@ def enumerate_blocks(cfg: UNetConfig):
             layers = [("res", ch + ich, mc * mult)]
             ch = mc * mult
             if ds in cfg.attention_resolutions:
-                layers.append(("attn", ch))
+                layers.append(("attn", ch, cfg.depth(level)))
             if level and i == cfg.num_res_blocks:
                 layers.append(("up", ch))
                 ds //= 2
@@ -101,6 +123,11 @@ def param_shapes(cfg: UNetConfig):
     shapes["time_embed.0.bias"] = (ted,)
     shapes["time_embed.2.weight"] = (ted, ted)
     shapes["time_embed.2.bias"] = (ted,)
+    if cfg.adm_in_channels:
+        shapes["label_emb.0.0.weight"] = (ted, cfg.adm_in_channels)
+        shapes["label_emb.0.0.bias"] = (ted,)
+        shapes["label_emb.0.2.weight"] = (ted, ted)
+        shapes["label_emb.0.2.bias"] = (ted,)
 
     def res(p, cin, cout):
         shapes[p + "in_layers.0.weight"] = (cin,)
@@ -117,7 +144,7 @@ def param_shapes(cfg: UNetConfig):
             shapes[p + "skip_connection.weight"] = (cout, cin, 1, 1)
             shapes[p + "skip_connection.bias"] = (cout,)
 
-    def attn(p, ch):
+    def attn(p, ch, depth):
         nh, dh = cfg.heads(ch)
         inner = nh * dh
         shapes[p + "norm.weight"] = (ch,)
@@ -130,7 +157,7 @@ def param_shapes(cfg: UNetConfig):
             shapes[p + "proj_out.weight"] = (ch, inner, 1, 1)
         shapes[p + "proj_in.bias"] = (inner,)
         shapes[p + "proj_out.bias"] = (ch,)
-        for d in range(cfg.transformer_depth):
+        for d in range(depth):
             b = p + f"transformer_blocks.{d}."
             for a, cdim in (("attn1", inner), ("attn2", cfg.context_dim)):
                 shapes[b + a + ".to_q.weight"] = (inner, inner)
@@ -155,7 +182,7 @@ def param_shapes(cfg: UNetConfig):
             elif l[0] == "res":
                 res(p, l[1], l[2])
             elif l[0] == "attn":
-                attn(p, l[1])
+                attn(p, l[1], l[2])
             elif l[0] == "down":
                 shapes[p + "op.weight"] = (l[1], l[1], 3, 3)
                 shapes[p + "op.bias"] = (l[1],)
@@ -259,7 +286,7 @@ class OracleUNet:
         r2 = r1.reshape(b, nh, n, dh).permute(0, 2, 1, 3).reshape(b, n, inner).to(x.dtype)
         return F.linear(r2, sd[p + "to_out.0.weight"], sd[p + "to_out.0.bias"])
 
-    def _attn(self, p, x, context):
+    def _attn(self, p, x, context, depth=1):
         """SpatialTransformer.forward, attention.py:526-537 (+ BasicTransformerBlock :485-490, GEGLU :92-100)."""
         sd, cfg = self.sd, self.cfg
         b, c, hh, ww = x.shape
@@ -272,7 +299,7 @@ class OracleUNet:
         else:
             x = F.conv2d(x, sd[p + "proj_in.weight"], sd[p + "proj_in.bias"])
             x = x.permute(0, 2, 3, 1).reshape(b, hh * ww, -1)
-        for d in range(cfg.transformer_depth):
+        for d in range(depth):
             bp = p + f"transformer_blocks.{d}."
             dim = x.shape[-1]
             x = self._cross_attention(bp + "attn1.", F.layer_norm(x, (dim,), sd[bp + "norm1.weight"], sd[bp + "norm1.bias"], 1e-5), None, nh) + x
@@ -302,7 +329,7 @@ class OracleUNet:
             elif l[0] == "res":
                 h = self._res(p, h, emb)
             elif l[0] == "attn":
-                h = self._attn(p, h, context)
+                h = self._attn(p, h, context, l[2])
             elif l[0] == "down":
                 h = F.conv2d(h, sd[p + "op.weight"], sd[p + "op.bias"], stride=2, padding=1)  # unet.py:151-160
             elif l[0] == "up":
@@ -313,12 +340,16 @@ class OracleUNet:
 
     # --- forward -------------------------------------------------------------------------------
     @torch.no_grad()
-    def __call__(self, x, timesteps, context, return_attn=False, **_):
+    def __call__(self, x, timesteps, context, return_attn=False, y=None, **_):
         """UNetModel.forward, unet.py:765-831.  x:[R,4,h,w], timesteps:[R], context:[R,77,D]."""
         sd, cfg = self.sd, self.cfg
         t_emb = timestep_embedding(timesteps, cfg.model_channels).to(self.dtype)
         emb = F.linear(F.silu(F.linear(t_emb, sd["time_embed.0.weight"], sd["time_embed.0.bias"])),
                        sd["time_embed.2.weight"], sd["time_embed.2.bias"])
+        if cfg.adm_in_channels:  # vector conditioning (SDXL extension): emb = emb + label_emb(y)
+            assert y is not None and y.shape == (x.shape[0], cfg.adm_in_channels), "this UNet needs y [rows, adm_in_channels]"
+            emb = emb + F.linear(F.silu(F.linear(y.to(self.dtype), sd["label_emb.0.0.weight"], sd["label_emb.0.0.bias"])),
+                                 sd["label_emb.0.2.weight"], sd["label_emb.0.2.bias"])
         context = context.to(self.dtype)
         hs = []
         h = x.type(self.dtype)
@@ -352,6 +383,8 @@ def count_flops(cfg: UNetConfig, h, w, ctx_len=77):
     ted = cfg.model_channels * 4
     conv = lin = att = 0
     lin += 2 * cfg.model_channels * ted + 2 * ted * ted
+    if cfg.adm_in_channels:
+        lin += 2 * cfg.adm_in_channels * ted + 2 * ted * ted
     hw = [h, w]
 
     def layer(l):
@@ -373,7 +406,7 @@ def count_flops(cfg: UNetConfig, h, w, ctx_len=77):
                 lin += pr
             else:
                 conv += pr
-            for _ in range(cfg.transformer_depth):
+            for _ in range(l[2]):
                 lin += 2 * px * inner * inner * 4  # attn1 q,k,v,out
                 lin += 2 * px * inner * inner * 2 + 2 * ctx_len * cfg.context_dim * inner * 2  # attn2
                 lin += 2 * px * inner * inner * 8 + 2 * px * inner * 4 * inner  # ff

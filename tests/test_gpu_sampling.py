@@ -175,7 +175,8 @@ def _unet_pair(cfg_name, dtype_oracle, act_dtype=torch.float16):
     gpu = UNetModel(sd, device=DEV, act_dtype=act_dtype, model_channels=cfg.model_channels, channel_mult=tuple(cfg.channel_mult),
                     attention_resolutions=tuple(cfg.attention_resolutions), num_res_blocks=cfg.num_res_blocks,
                     num_heads=cfg.num_heads, num_head_channels=cfg.num_head_channels, context_dim=cfg.context_dim,
-                    use_linear_in_transformer=cfg.use_linear_in_transformer)
+                    use_linear_in_transformer=cfg.use_linear_in_transformer, transformer_depth=cfg.transformer_depth,
+                    adm_in_channels=cfg.adm_in_channels, num_classes="sequential" if cfg.adm_in_channels else None)
     return cfg, oracle, gpu
 
 
@@ -195,7 +196,7 @@ def _layer_report(oracle, gpu, R):
 # depth (torch's own CPU bf16 run of the oracle deviates 1.25e-2 / 1.46e-2 on tiny / SD-1.5), so that mode is
 # only checked against 2e-2.
 @pytest.mark.parametrize("act_dtype,tol", [(torch.float16, 1e-2), (torch.bfloat16, 2e-2)])
-@pytest.mark.parametrize("cfg_name,hw,R", [("tiny", 16, 3), ("tiny", 32, 2), ("sd15", 32, 2), ("sd21", 32, 2)])
+@pytest.mark.parametrize("cfg_name,hw,R", [("tiny", 16, 3), ("tiny", 32, 2), ("sd15", 32, 2), ("sd21", 32, 2), ("tiny_xl", 32, 3)])
 def test_unet_forward_vs_oracle(cpd, cfg_name, hw, R, act_dtype, tol):
     cfg, oracle, gpu = _unet_pair(cfg_name, torch.float32, act_dtype)
     g = torch.Generator().manual_seed(hw + R)
@@ -207,8 +208,10 @@ def test_unet_forward_vs_oracle(cpd, cfg_name, hw, R, act_dtype, tol):
     oracle.sd = {k: v.to(torch.bfloat16).float() for k, v in oracle.sd.items()}
     oracle.taps = {}
     t_r = t.to(torch.bfloat16).float()
-    ref = oracle(x, t_r, ctx.to(torch.bfloat16).float())
-    out, skips = gpu(x.to(DEV), t_r.to(DEV), ctx.to(DEV), return_attn=True)
+    y = torch.randn(R, cfg.adm_in_channels, generator=g) if cfg.adm_in_channels else None  # SDXL-style vector conditioning
+    ykw = {} if y is None else {"y": y.to(torch.bfloat16).float()}
+    ref = oracle(x, t_r, ctx.to(torch.bfloat16).float(), **ykw)
+    out, skips = gpu(x.to(DEV), t_r.to(DEV), ctx.to(DEV), return_attn=True, **({} if y is None else {"y": y.to(DEV)}))
     torch.cuda.synchronize()
     report = _layer_report(oracle, gpu, R)
     for name, r in report:
@@ -398,3 +401,48 @@ def test_config2_full_size_properties(cpd):
     r = rel(run(x_T[:1], same, s=7.5), run(x_T[:1], same, s=1.0))
     print(f"config 2: guidance-scale invariance with cond == uncond: rel {r:.3e}")
     assert r < 1e-5
+
+
+def test_config4_sdxl_topology_dual_encoder_vector_conditioning(cpd):
+    """BASELINE.json configs[3] at a CPU-checkable size.  SDXL is not expressible by the reference, so both
+    the oracle and the product extend the same block grammar: per-level transformer depths, no attention at the first
+    level, 64-wide heads (here 32), linear projections, a context that is two encoders concatenated on the feature axis
+    and a vector conditioning y through label_emb.  Checked: the sampling path (DPM++ 2M, cond + uncond rows with
+    DIFFERENT y rows, batch 2 on the GPU = two independent trajectories) against one oracle run per image."""
+    from complex_prompt_diffusion_b200 import samplers
+    from oracle.denoiser import OracleDenoiser
+    from oracle import samplers as OS
+    cfg, oracle, gpu = _unet_pair("tiny_xl", torch.float32)
+    oracle.sd = {k: v.to(torch.bfloat16).float() for k, v in oracle.sd.items()}
+    g = torch.Generator().manual_seed(44)
+    hw, steps, B = 32, 5, 2
+    D = cfg.context_dim
+    enc_a, enc_b = torch.randn(2, 1, 77, D // 3, generator=g), torch.randn(2, 1, 77, D - D // 3, generator=g)
+    uc = torch.cat([enc_a[0], enc_b[0]], dim=-1)  # dual-encoder conditioning: concat on the feature axis
+    c = {"and": [(1.0, torch.cat([enc_a[1], enc_b[1]], dim=-1), None, 1)], "not": []}
+    y = torch.randn(2, cfg.adm_in_channels, generator=g)  # row 0: unconditional, row 1: the prompt
+    x_T = torch.randn(B, 4, hw, hw, generator=g)
+    kw = dict(conditioning=c, unconditional_conditioning=uc, unconditional_guidance_scale=5.0, scheduler="karras", y=y)
+
+    class Side:  # oracle UNet with the product's dtype boundaries
+        def parameters(self):
+            return iter([torch.zeros(1, dtype=torch.bfloat16)])
+
+        def __call__(self, x, t, ctx, y=None, **k):
+            o = oracle(x.to(torch.bfloat16).float(), t.float(), ctx.to(torch.bfloat16).float(), y=y.to(torch.bfloat16).float())
+            return o, [o] * 12
+
+    wrapper = samplers.make({"name": "DPM++ 2m", "args": {}}, {"model": {"unet": gpu}})
+    out = wrapper.sampler.sample(steps=steps, batch_size=B, shape=[4, hw, hw], x_T=x_T.clone(), rng_compat=False, **dict(kw))
+    torch.cuda.synchronize()
+    for b in range(B):
+        od = OracleDenoiser(Side(), dtype=torch.bfloat16)
+        ref = OS.sample(od, "DPM++ 2m", steps, x_T[b:b + 1].clone(), **dict(kw))
+        r = rel(out[b:b + 1], ref)
+        print(f"config 4 (SDXL topology): image {b} final latent rel-L2 {r:.3e}")
+        assert r < 2e-2
+    with pytest.raises(ValueError):  # a UNet with vector conditioning must be given y
+        bad = dict(kw)
+        bad.pop("y")
+        wrapper.sampler.sample(steps=2, batch_size=1, shape=[4, hw, hw], x_T=x_T[:1].clone(), rng_compat=False,
+                               conditioning={"and": list(c["and"]), "not": []}, unconditional_conditioning=uc.clone())

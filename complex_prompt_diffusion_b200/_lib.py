@@ -11,7 +11,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcpd_b200.so")
 
 CPD_F32, CPD_F16, CPD_BF16 = 0, 1, 2
-CPD_EULER, CPD_EULER_ANCESTRAL, CPD_DPMPP_2M = 0, 1, 2
+CPD_EULER, CPD_EULER_ANCESTRAL, CPD_DPMPP_2M, CPD_DENOISE_ONLY, CPD_HEUN2, CPD_LMS = 0, 1, 2, 3, 4, 5
+CPD_THRESH_DYNAMIC, CPD_THRESH_STATIC = 0, 1
 CPD_PRED_EPSILON, CPD_PRED_VELOCITY = 0, 1
 CPD_EPI_NONE, CPD_EPI_GEGLU = 0, 1
 CPD_MAX_SUBPROMPTS = 16
@@ -31,6 +32,9 @@ class StepParams(C.Structure):
         ("sigma_hat", C.c_float), ("v_c_eps", C.c_float), ("v_c_x_div", C.c_float), ("dt", C.c_float),
         ("sigma_up", C.c_float), ("dpm_ratio", C.c_float), ("dpm_expm1", C.c_float), ("dpm_c1", C.c_float),
         ("dpm_c2", C.c_float), ("dpm_first", C.c_int), ("write_old", C.c_int),
+        ("x_base", C.c_void_p), ("x_out", C.c_void_p), ("d_out", C.c_void_p), ("d_prev", C.c_void_p * 3),
+        ("lms_coeff", C.c_float * 4), ("lms_order", C.c_int), ("noise_mul", C.c_float),
+        ("clip_scaled", C.c_void_p), ("scaled_out", C.c_void_p),
     ]
 
 
@@ -60,6 +64,7 @@ _SIGS = {
     "cpd_last_error": (C.c_char_p, []),
     "cpd_abi_version": (C.c_int, []),
     "cpd_sampler_step": (C.c_int, [C.POINTER(StepParams), C.c_void_p]),
+    "cpd_threshold": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]),
     "cpd_gemm_conv": (C.c_int, [C.POINTER(GemmParams), C.c_void_p]),
     "cpd_groupnorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                 C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -87,14 +87,17 @@ __global__ void __launch_bounds__(256, VEC == 8 ? 3 : 4) sampler_step_kernel(con
     const int64_t ebase = (int64_t)b * p.eps_image_stride + i;
     // Issue every independent load of this vector before the first use (memory-level parallelism: the kernel is a pure
     // HBM stream): x, the 2M history / ancestral noise, the unconditional row and the sub-prompt rows four at a time.
-    float x[VEC], aux[VEC];  // aux: old_denoised (2M) or noise (ancestral)
+    float x[VEC], aux[VEC];  // x: the UNet input; aux: old_denoised (2M), noise (ancestral / 2S-a) or d of stage 1 (Heun)
     load_f32<VEC>(p.x + (int64_t)b * L + i, x);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) aux[j] = 0.f;
     if (p.sampler == CPD_DPMPP_2M) {
       if (!p.dpm_first) load_f32<VEC>(p.old_denoised + (int64_t)b * L + i, aux);
+      else if (p.noise) load_f32<VEC>(p.noise + (int64_t)b * L + i, aux);  // DPM++ 2S ancestral: noise after the update
     } else if (p.sampler == CPD_EULER_ANCESTRAL) {
       load_f32<VEC>(p.noise + (int64_t)b * L + i, aux);
+    } else if (p.sampler == CPD_HEUN2) {
+      load_f32<VEC>(p.d_prev[0] + (int64_t)b * L + i, aux);
     }
     // The fp16 delta (denoiser.py:450-460) runs on packed half2: for fp16 operands HSUB2 / HMUL2 / HADD2 (one rounding) give
     // bit-identical results to "compute in fp32, round to fp16" (products of two halves are exact in fp32; sums are exact
@@ -139,32 +142,65 @@ __global__ void __launch_bounds__(256, VEC == 8 ? 3 : 4) sampler_step_kernel(con
       }
     }
     float et[VEC], den[VEC], xn[VEC];
+    const float clip = p.clip_scaled ? __ldg(p.clip_scaled + b) : 0.f;
+    const float nmul = p.noise_mul == 0.f ? 1.f : p.noise_mul;
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       const float sj = (j & 1) ? __high2float(sum[j >> 1]) : __low2float(sum[j >> 1]);
       float scaled = h_round(__fmul_rn(sj, p.guidance));
+      if (p.scaled_out) p.scaled_out[(int64_t)b * L + i + j] = scaled;
+      if (p.clip_scaled) scaled = h_round(fminf(fmaxf(scaled, -clip), clip));  // x.float() -> clamp_ -> .half()
       if (DT == CPD_F16) et[j] = h_round(__fadd_rn(eu.at(j), scaled));
       else et[j] = __fadd_rn(eu.at(j), scaled);
       if (p.pred_type == CPD_PRED_EPSILON) den[j] = __fsub_rn(x[j], __fmul_rn(p.sigma_hat, et[j]));
       else den[j] = __fadd_rn(__fmul_rn(et[j], p.v_c_eps), __fdiv_rn(x[j], p.v_c_x_div));
+    }
+    // xb: the sample the update starts from (the UNet input unless this is the second stage of a two-stage sampler)
+    float xb[VEC];
+    if (p.x_base) {
+      load_f32<VEC>(p.x_base + (int64_t)b * L + i, xb);
+    } else {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) xb[j] = x[j];
     }
     if (p.sampler == CPD_DPMPP_2M) {
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
         float dd = den[j];
         if (!p.dpm_first) dd = __fsub_rn(__fmul_rn(p.dpm_c1, den[j]), __fmul_rn(p.dpm_c2, aux[j]));
-        xn[j] = __fsub_rn(__fmul_rn(p.dpm_ratio, x[j]), __fmul_rn(p.dpm_expm1, dd));
+        xn[j] = __fsub_rn(__fmul_rn(p.dpm_ratio, xb[j]), __fmul_rn(p.dpm_expm1, dd));
+        if (p.dpm_first && p.noise) xn[j] = __fadd_rn(xn[j], __fmul_rn(__fmul_rn(aux[j], nmul), p.sigma_up));  // dpmpp.py:111
       }
       if (p.write_old) store_f32<VEC>(p.old_denoised + (int64_t)b * L + i, den);
     } else {
+      float d[VEC];
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        float d = __fdiv_rn(__fsub_rn(x[j], den[j]), p.sigma_hat);
-        xn[j] = __fadd_rn(x[j], __fmul_rn(d, p.dt));
-        if (p.sampler == CPD_EULER_ANCESTRAL) xn[j] = __fadd_rn(xn[j], __fmul_rn(aux[j], p.sigma_up));
+      for (int j = 0; j < VEC; ++j) d[j] = __fdiv_rn(__fsub_rn(x[j], den[j]), p.sigma_hat);  // to_ode
+      if (p.d_out) store_f32<VEC>(p.d_out + (int64_t)b * L + i, d);
+      if (p.sampler == CPD_HEUN2) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) xn[j] = __fadd_rn(xb[j], __fmul_rn(__fdiv_rn(__fadd_rn(aux[j], d[j]), 2.0f), p.dt));
+      } else if (p.sampler == CPD_LMS) {
+        float acc[VEC];  // sum(coeff * d ...) of lms.py:52: 0 + c0 * d_i, then + c1 * d_{i-1}, ... left to right
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] = __fmul_rn(p.lms_coeff[0], d[j]);
+        for (int k = 1; k < p.lms_order; ++k) {
+          float dk[VEC];
+          load_f32<VEC>(p.d_prev[k - 1] + (int64_t)b * L + i, dk);
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) acc[j] = __fadd_rn(acc[j], __fmul_rn(p.lms_coeff[k], dk[j]));
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) xn[j] = __fadd_rn(xb[j], acc[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          xn[j] = __fadd_rn(xb[j], __fmul_rn(d[j], p.dt));
+          if (p.sampler == CPD_EULER_ANCESTRAL) xn[j] = __fadd_rn(xn[j], __fmul_rn(__fmul_rn(aux[j], nmul), p.sigma_up));
+        }
       }
     }
-    if (p.sampler != CPD_DENOISE_ONLY) store_f32<VEC>(p.x + (int64_t)b * L + i, xn);
+    if (p.sampler != CPD_DENOISE_ONLY) store_f32<VEC>((p.x_out ? p.x_out : p.x) + (int64_t)b * L + i, xn);
     if (p.denoised_out) store_f32<VEC>(p.denoised_out + (int64_t)b * L + i, den);
     if (p.eps_out) store_f32<VEC>(p.eps_out + (int64_t)b * L + i, et);
   }
@@ -180,7 +216,11 @@ extern "C" cpd_status cpd_sampler_step(const cpd_step_params* p, void* stream) {
   CPD_REQUIRE(p->hw > 0 && p->hw % 4 == 0, "cpd_sampler_step: hw=%d must be a positive multiple of 4", p->hw);
   CPD_REQUIRE(p->n_images >= 0, "cpd_sampler_step: n_images=%d", p->n_images);
   CPD_REQUIRE(p->eps_row_stride % 4 == 0 && p->eps_image_stride % 4 == 0, "cpd_sampler_step: eps strides must be multiples of 4");
-  CPD_REQUIRE(p->sampler >= CPD_EULER && p->sampler <= CPD_DENOISE_ONLY, "cpd_sampler_step: unknown sampler %d", p->sampler);
+  CPD_REQUIRE(p->sampler >= CPD_EULER && p->sampler <= CPD_LMS, "cpd_sampler_step: unknown sampler %d", p->sampler);
+  CPD_REQUIRE(p->sampler != CPD_HEUN2 || p->d_prev[0], "cpd_sampler_step: the second Heun stage needs d_prev[0]");
+  CPD_REQUIRE(p->sampler != CPD_LMS || (p->lms_order >= 1 && p->lms_order <= 4), "cpd_sampler_step: lms_order=%d", p->lms_order);
+  if (p->sampler == CPD_LMS)
+    for (int k = 1; k < p->lms_order; ++k) CPD_REQUIRE(p->d_prev[k - 1], "cpd_sampler_step: LMS order %d needs d_prev[%d]", p->lms_order, k - 1);
   CPD_REQUIRE(p->pred_type == CPD_PRED_EPSILON || p->pred_type == CPD_PRED_VELOCITY, "cpd_sampler_step: unknown pred_type %d",
               p->pred_type);
   CPD_REQUIRE(p->sampler != CPD_EULER_ANCESTRAL || p->noise, "cpd_sampler_step: ancestral sampler needs noise");

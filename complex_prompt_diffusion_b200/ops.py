@@ -62,9 +62,13 @@ def _act(t, name, like=None):
 
 def sampler_step(eps, x, *, n_sub, weights, mask_scalars, masks, guidance, sampler, pred_type, sigma_hat, v_c_eps=0.0,
                  v_c_x_div=1.0, dt=0.0, sigma_up=0.0, dpm_ratio=0.0, dpm_expm1=0.0, dpm_c1=0.0, dpm_c2=0.0, dpm_first=1,
-                 write_old=0, old_denoised=None, noise=None, denoised_out=None, eps_out=None):
-    """eps: [n_images * (1 + n_sub), 4, h, w] (image-major rows); x: [n_images, 4, h, w] fp32, updated in place."""
+                 write_old=0, old_denoised=None, noise=None, denoised_out=None, eps_out=None, x_base=None, x_out=None, d_out=None,
+                 d_prev=(), lms_coeff=(), noise_mul=1.0, clip_scaled=None, scaled_out=None):
+    """eps: [n_images * (1 + n_sub), 4, h, w] (image-major rows); x: [n_images, 4, h, w] fp32, the UNet input; the updated
+    sample goes to x_out (default: x, in place) and starts from x_base (default: x)."""
     _req(x, torch.float32, "x")
+    for name, t in (("x_base", x_base), ("x_out", x_out), ("d_out", d_out), ("clip_scaled", clip_scaled), ("scaled_out", scaled_out)):
+        _req(t, torch.float32, name)
     _req(old_denoised, torch.float32, "old_denoised")
     _req(noise, torch.float32, "noise")
     _req(denoised_out, torch.float32, "denoised_out")
@@ -105,10 +109,41 @@ def sampler_step(eps, x, *, n_sub, weights, mask_scalars, masks, guidance, sampl
     p.sigma_hat, p.v_c_eps, p.v_c_x_div, p.dt, p.sigma_up = float(sigma_hat), float(v_c_eps), float(v_c_x_div), float(dt), float(sigma_up)
     p.dpm_ratio, p.dpm_expm1, p.dpm_c1, p.dpm_c2 = float(dpm_ratio), float(dpm_expm1), float(dpm_c1), float(dpm_c2)
     p.dpm_first, p.write_old = int(dpm_first), int(write_old)
+    p.x_base = x_base.data_ptr() if x_base is not None else None
+    p.x_out = x_out.data_ptr() if x_out is not None else None
+    p.d_out = d_out.data_ptr() if d_out is not None else None
+    for k in range(3):
+        if k < len(d_prev) and d_prev[k] is not None:
+            _req(d_prev[k], torch.float32, f"d_prev[{k}]")
+            p.d_prev[k] = d_prev[k].data_ptr()
+        else:
+            p.d_prev[k] = None
+    for k in range(4):
+        p.lms_coeff[k] = float(lms_coeff[k]) if k < len(lms_coeff) else 0.0
+    p.lms_order = len(lms_coeff)
+    p.noise_mul = float(noise_mul)
+    p.clip_scaled = clip_scaled.data_ptr() if clip_scaled is not None else None
+    p.scaled_out = scaled_out.data_ptr() if scaled_out is not None else None
     with _Prof("sampler_step", 0.0):
         check(load().cpd_sampler_step(C.byref(p), stream_ptr()), "cpd_sampler_step")
     _count()
     return x
+
+
+def threshold(x, bound, *, alg, threshold, clamp_inplace=True):
+    """Thresholding extension on the device (cpd_threshold): bound[b] = max(percentile_q(|x_b|), 1) or the static bound;
+    optionally x <- half(clamp(x, -bound[b], bound[b])) in place.  x: [n_images, ...] fp32, bound: [n_images] fp32."""
+    _req(x, torch.float32, "x")
+    _req(bound, torch.float32, "bound")
+    n = x.shape[0]
+    if bound.numel() < n:
+        raise RuntimeError("bound must hold one fp32 value per image")
+    L = x[0].numel() if n else 4
+    with _Prof("threshold", 0.0):
+        check(load().cpd_threshold(ptr(x), n, L, int(alg), float(threshold), int(bool(clamp_inplace)), ptr(bound), stream_ptr()),
+              "cpd_threshold")
+    _count(2 if clamp_inplace else 1)
+    return bound
 
 
 AUTOTUNE = os.environ.get("CPD_GEMM_AUTOTUNE", "1") != "0"  # time the tile-shape variants of cpd_gemm_conv once per layer shape (first eager call) and keep the best

@@ -42,6 +42,7 @@ class DPMPlusPlus2mDiffusionSampler(KDiffusionSampler):
             den.fused_step(x, sigmas[i], plan, dict(sampler=CPD_DPMPP_2M, dpm_ratio=ratio, dpm_expm1=em, dpm_c1=c1, dpm_c2=c2,
                                                     dpm_first=first, write_old=1, old_denoised=old, denoised_out=den_out),
                            **model_args)
+            self._clip_sample(x, kwargs)
             self._callback(callback, x_before, i, sigmas[i], den_out)
         return x
 

@@ -39,6 +39,7 @@ class EulerDiffusionSampler(KDiffusionSampler):
             dt = sigmas[i + 1] - sigma_hat
             x_before = x.clone() if callback is not None else None
             den.fused_step(x, sigma_hat, plan, dict(sampler=CPD_EULER, dt=float(dt), denoised_out=den_out), **model_args)
+            self._clip_sample(x, kwargs)
             self._callback(callback, x_before, i, sigmas[i], den_out)
         return x
 
@@ -65,6 +66,7 @@ class EulerAncestralDiffusionSampler(KDiffusionSampler):
             x_before = x.clone() if callback is not None else None
             den.fused_step(x, sigmas[i], plan, dict(sampler=CPD_EULER_ANCESTRAL, dt=float(dt), sigma_up=float(sigma_up),
                                                     noise=noise, denoised_out=den_out), **model_args)
+            self._clip_sample(x, kwargs)
             self._callback(callback, x_before, i, sigmas[i], den_out)
         return x
 

@@ -18,13 +18,22 @@ import math
 import torch
 
 from ... import ops
-from ..._lib import CPD_DPMPP_2M, CPD_EULER, CPD_EULER_ANCESTRAL, CPD_PRED_EPSILON, CPD_PRED_VELOCITY
+from ..._lib import (CPD_DENOISE_ONLY, CPD_DPMPP_2M, CPD_EULER, CPD_EULER_ANCESTRAL, CPD_PRED_EPSILON, CPD_PRED_VELOCITY,
+                     CPD_THRESH_DYNAMIC, CPD_THRESH_STATIC)
 from ...scheduler.discrete import SigmaScheduler
 
-CPD_DENOISE_ONLY = 3
+_UNSUPPORTED_TRUTHY = ("attn_guide", "return_attn", "clip_guidance", "score_corrector", "unconditional_guidance_blur",
+                       "inject_feats", "inject_attns", "depth_mask")
 
-_UNSUPPORTED_TRUTHY = ("attn_guide", "return_attn", "clip_guidance", "score_corrector", "scaled_clip", "dynamic_scale_clip",
-                       "unconditional_guidance_blur", "inject_feats", "inject_attns", "depth_mask")
+# thresholding extensions that run on the device (samplers/extension/threshold.py:47-88); the other registered variants
+# (dynanormic / scaled / mean-centred ...) still raise
+THRESHOLD_ALGS = {"dynamic_thresholding": CPD_THRESH_DYNAMIC, "static_thresholding": CPD_THRESH_STATIC}
+
+
+def threshold_alg(name):
+    if name not in THRESHOLD_ALGS:
+        raise NotImplementedError(f"thresholding algorithm {name!r} is not built on the device (have: {sorted(THRESHOLD_ALGS)})")
+    return THRESHOLD_ALGS[name]
 
 
 class ConditioningPlan:
@@ -171,9 +180,21 @@ class Denoiser(torch.nn.Module):
         sig = float(torch.as_tensor(sigma, dtype=torch.float32).reshape(-1)[0])
         sig_t = torch.tensor([sig], dtype=torch.float32)
         pred = CPD_PRED_VELOCITY if kwargs.get("pred_type", "epsilon") == "velocity" else CPD_PRED_EPSILON
-        ops.sampler_step(eps, x, n_sub=plan.n_sub, weights=plan.weights, mask_scalars=plan.mask_scalars, masks=plan.masks,
-                         guidance=self.guidance_scale(**kwargs), pred_type=pred, sigma_hat=sig,
-                         v_c_eps=float(-sig_t / (sig_t ** 2 + 1) ** 0.5), v_c_x_div=float(sig_t ** 2 + 1), **step)
+        common = dict(n_sub=plan.n_sub, weights=plan.weights, mask_scalars=plan.mask_scalars, masks=plan.masks,
+                      guidance=self.guidance_scale(**kwargs), pred_type=pred, sigma_hat=sig,
+                      v_c_eps=float(-sig_t / (sig_t ** 2 + 1) ** 0.5), v_c_x_div=float(sig_t ** 2 + 1))
+        clip = None
+        if kwargs.get("scaled_clip", kwargs.get("dynamic_scale_clip", False)):
+            # Dynamic scale clip (denoiser.py:499-512): the scaled guidance term s * sum_e_t is thresholded before it is
+            # added to e_u.  The reference runs np.percentile on a CPU copy every step; here a combine-only pass writes
+            # the term, cpd_threshold finds the per-image bound on the device and the fused step clamps with it.
+            alg = threshold_alg(kwargs.get("scaled_clip_alg", "dynamic_thresholding"))
+            thr = kwargs.get("scaled_clip_threshold", kwargs.get("dynamic_scale_clip_threshold", 99.5))
+            scaled = torch.empty_like(x)
+            clip = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+            ops.sampler_step(eps, x, sampler=CPD_DENOISE_ONLY, scaled_out=scaled, **common)
+            ops.threshold(scaled, clip, alg=alg, threshold=float(thr), clamp_inplace=False)
+        ops.sampler_step(eps, x, clip_scaled=clip, **common, **step)
         return x
 
     @torch.no_grad()

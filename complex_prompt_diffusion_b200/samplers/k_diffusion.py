@@ -55,8 +55,6 @@ class KDiffusionSampler:
 
     # ---- shared loop plumbing -------------------------------------------------------------------------
     def _begin(self, x, model_args, kwargs):
-        if kwargs.get("clip_sample", False):
-            raise NotImplementedError("clip_sample thresholding is a 'next' row (SURVEY.md 8-f), not built yet")
         if kwargs.get("s_churn", 0.0):
             raise NotImplementedError("s_churn > 0 is not supported (gamma = 0 path only)")
         den = self.denoiser
@@ -64,6 +62,18 @@ class KDiffusionSampler:
         plan = den.plan_conditioning(model_args.get("conditioning"), model_args.get("unconditional_conditioning"), x.shape[-2:],
                                      y=model_args.get("y"))
         return den, plan
+
+    def _clip_sample(self, x, kwargs):
+        """Sample thresholding after the update (euler.py:55-56, dpmpp.py:51-52): x <- half(clamp(x, -s, s)) with
+        s = max(percentile(|x|), 1) per image, all on the device (the reference goes through np.percentile on the CPU)."""
+        if not kwargs.get("clip_sample", False):
+            return
+        from .. import ops
+        from .extension.denoiser import threshold_alg
+        alg = threshold_alg(kwargs.get("clip_sample_alg", "dynamic_thresholding"))
+        if getattr(self, "_clip_bound", None) is None or self._clip_bound.numel() < x.shape[0] or self._clip_bound.device != x.device:
+            self._clip_bound = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+        ops.threshold(x, self._clip_bound, alg=alg, threshold=float(kwargs.get("clip_sample_thresh", 90)), clamp_inplace=True)
 
     def _callback(self, callback, x_before, i, sigma, denoised):
         if callback is not None:

@@ -32,7 +32,9 @@ int cpd_abi_version(void);
 enum { CPD_F32 = 0, CPD_F16 = 1, CPD_BF16 = 2 };
 /* sampler kinds (registry names "Euler", "Euler Ancestral", "DPM++ 2m") */
 enum { CPD_EULER = 0, CPD_EULER_ANCESTRAL = 1, CPD_DPMPP_2M = 2,
-       CPD_DENOISE_ONLY = 3 /* Denoiser.forward alone: x is not updated, denoised_out receives the sample */ };
+       CPD_DENOISE_ONLY = 3, /* Denoiser.forward alone: x is not updated, denoised_out receives the sample */
+       CPD_HEUN2 = 4,        /* second stage of Heun (huen.py:52-57): x_base + ((d_prev[0] + d_2) / 2) * dt */
+       CPD_LMS = 5 };        /* linear multistep (lms.py:40-52): x + sum_j lms_coeff[j] * d_{i-j} */
 /* prediction type (denoiser.py:537-542) */
 enum { CPD_PRED_EPSILON = 0, CPD_PRED_VELOCITY = 1 };
 
@@ -79,9 +81,42 @@ typedef struct {
   float dpm_c1, dpm_c2;     /* 2M: (1 + 1/(2r)), 1/(2r) */
   int dpm_first;            /* 2M: 1 when old_denoised is None or sigma_{i+1} == 0 (dpmpp.py:44) */
   int write_old;            /* 2M: store denoised into old_denoised */
+  /* Two-stage and multistep samplers (Heun huen.py:24-58, DPM2 / DPM2-a dpm2.py:24-108, DPM++ 2S-a dpmpp.py:70-113, LMS
+   * lms.py:28-52) reuse the modes above with the UNet input, the tensor the update starts from and the destination
+   * taken apart: stage 1 = CPD_EULER (or CPD_DPMPP_2M with dpm_first) writing x_2 to x_out; stage 2 evaluates x = x_2
+   * and updates x_base. */
+  const float* x_base;      /* sample the update starts from; NULL = x (the UNet input) */
+  float* x_out;             /* destination of the updated sample; NULL = x (in place) */
+  float* d_out;             /* optional [n_images][L]: d = (x - denoised) / sigma_hat of this evaluation (to_ode) */
+  const float* d_prev[3];   /* CPD_HEUN2: d of stage 1 in d_prev[0]; CPD_LMS: d_{i-1}, d_{i-2}, d_{i-3} */
+  float lms_coeff[4];       /* CPD_LMS: coefficients of d_i, d_{i-1}, d_{i-2}, d_{i-3} (linear_multistep_coeff) */
+  int lms_order;            /* CPD_LMS: min(i + 1, order), 1..4 */
+  float noise_mul;          /* noise is multiplied by this (s_noise / temperature) before sigma_up; 0 is read as 1 */
+  /* Thresholding extensions (samplers/extension/threshold.py:65-88 "dynamic_thresholding", 47-63 "static_thresholding"),
+   * with the clamp bound s = max(percentile(|.|), 1) computed ON THE DEVICE by cpd_abs_percentile_max1: */
+  const float* clip_scaled; /* optional DEVICE array [n_images] (from cpd_threshold): the scaled guidance term s * sum_e_t of
+                               image b is clamped to [-c[b], c[b]] and rounded to fp16 before it is added to e_u
+                               (denoiser.py:510-515, scaled_clip) */
+  float* scaled_out;        /* optional [n_images][L] fp32 copy of half(s * sum_e_t) BEFORE clamping (input of the
+                               percentile pass); with sampler = CPD_DENOISE_ONLY nothing else needs to be written */
 } cpd_step_params;
 
 cpd_status cpd_sampler_step(const cpd_step_params* p, void* stream);
+
+/*
+ * Thresholding extensions on the device (samplers/extension/threshold.py; hooks denoiser.py:510-512, euler.py:55-56,
+ * dpmpp.py:51-52,92-93).  The reference copies the tensor to the CPU for np.percentile every step.
+ *   alg = CPD_THRESH_DYNAMIC ("dynamic_thresholding", threshold.py:65-88): for each of the n_images rows of
+ *     x [n_images][L] (fp32) the `threshold`-th percentile (0..100, numpy's default linear interpolation between order
+ *     statistics, evaluated in fp32 like np.percentile on a float32 array) of |x| is found by an exact 4-pass radix select;
+ *     bound[b] = max(percentile_b, 1.0).  Images are independent trajectories here, so the bound is per
+ *     image; with n_images = 1 this is exactly np.max(np.append(s, 1.0)).
+ *   alg = CPD_THRESH_STATIC ("static_thresholding", threshold.py:47-63): bound[b] = threshold.
+ * bound: [n_images] fp32 device array (always written).  If clamp_inplace != 0, x is then clamped to
+ * [-bound[b], bound[b]] and rounded through fp16 (the reference returns x.half()).
+ */
+enum { CPD_THRESH_DYNAMIC = 0, CPD_THRESH_STATIC = 1 };
+cpd_status cpd_threshold(float* x, int n_images, int L, int alg, float threshold, int clamp_inplace, float* bound, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * UNet building blocks (all activations NHWC bf16 = row-major [pixels, channels]).  The Python host

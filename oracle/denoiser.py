@@ -96,6 +96,10 @@ class OracleDenoiser:
                                   kwargs.get("decaying_uc_scale_start", None))
         sum_e_t, e_t_uncond = self.process_conditioning(x, c, **kwargs)
         scaled_e_t = uc_scale * sum_e_t  # denoiser.py:514 (fp16 tensor * python float stays fp16)
+        if kwargs.get("scaled_clip", kwargs.get("dynamic_scale_clip", False)):  # :499-512: dynamic scale clip
+            from .samplers import threshold_apply
+            thr = kwargs.get("scaled_clip_threshold", kwargs.get("dynamic_scale_clip_threshold", 99.5))
+            scaled_e_t = threshold_apply(scaled_e_t, kwargs.get("scaled_clip_alg", "dynamic_thresholding"), thr).half()
         return e_t_uncond + scaled_e_t  # :515
 
     def __call__(self, x, sigma, **kwargs):

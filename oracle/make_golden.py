@@ -114,9 +114,35 @@ def reference_sampling(ref_shim):
     uc, embs, mask, c, x_T = make_case_inputs(cfg, hw)
     out = {"x_T": x_T.numpy(), "uc": uc.numpy(), "embs": torch.cat(embs).numpy(), "mask": mask.numpy(),
            "scales": np.array([1.0, 0.6, 0.4]), "steps": np.array(steps), "hw": np.array(hw), "guidance": np.array(7.5)}
-    for name, sched, pred in (("Euler", "karras", "epsilon"), ("DPM++ 2m", "karras", "epsilon"),
-                              ("Euler Ancestral", "karras", "epsilon"), ("Euler", "exp", "velocity"),
-                              ("DPM++ 2m", "linear", "velocity")):
+    return _run_cases(ref_shim, unet, out, c, uc, x_T, hw, steps,
+                      (("Euler", "karras", "epsilon", {}), ("DPM++ 2m", "karras", "epsilon", {}),
+                       ("Euler Ancestral", "karras", "epsilon", {}), ("Euler", "exp", "velocity", {}),
+                       ("DPM++ 2m", "linear", "velocity", {})))
+
+
+MORE_CASES = (("Huen", "karras", "epsilon", {}), ("DPM2", "karras", "epsilon", {}), ("DPM2 Ancestral", "karras", "epsilon", {}),
+              ("DPM++ 2s Ancestral", "karras", "epsilon", {}), ("LMS", "karras", "epsilon", {}), ("Huen", "exp", "velocity", {}),
+              ("Euler", "karras", "epsilon", {"scaled_clip": True, "scaled_clip_threshold": 97.0}),
+              ("DPM++ 2m", "karras", "epsilon", {"scaled_clip": True, "scaled_clip_alg": "static_thresholding",
+                                                 "scaled_clip_threshold": 0.5}))
+
+
+def reference_sampling_more(ref_shim):
+    """tests/golden/ref_sampling2.npz: the remaining k-diffusion samplers (two-stage / multistep) and the dynamic /
+    static scale clip of the Denoiser, same inputs as ref_sampling.npz."""
+    from oracle.unet import UNetConfig, make_weights
+
+    cfg = UNetConfig.tiny()
+    hw, steps = 8, 6
+    unet = ref_shim.build_reference_unet(cfg)
+    unet.load_state_dict(make_weights(cfg, seed=0), strict=True)
+    unet.eval()
+    uc, embs, mask, c, x_T = make_case_inputs(cfg, hw)
+    return _run_cases(ref_shim, unet, {}, c, uc, x_T, hw, steps, MORE_CASES)
+
+
+def _run_cases(ref_shim, unet, out, c, uc, x_T, hw, steps, cases):
+    for name, sched, pred, extra in cases:
         # NB ("Euler", "linear") cannot be generated: get_sigmas_linear returns fp64 sigmas, to_ode's
         # append_dims (euler.py:103-111) turns the 0-dim sigma into a 4-D fp64 tensor, x is promoted to fp64
         # and the second UNet call raises "Input type (double) and bias type (float)" (defect D9).
@@ -143,11 +169,11 @@ def reference_sampling(ref_shim):
             res = wrapper.sampler.sample(steps=steps, batch_size=1, shape=[4, hw, hw], x_T=x_T.clone(), conditioning=c,
                                          unconditional_conditioning=uc, unconditional_guidance_scale=7.5,
                                          scheduler=sched, device="cpu", silent=True, pred_type=pred,
-                                         callback=lambda d: dens.append(d["eps"].clone()))
+                                         callback=lambda d: dens.append(d["eps"].clone()), **extra)
         finally:
             torch.randn_like = real_randn_like
             unet.forward = orig_forward
-        key = f"{name}|{sched}|{pred}".replace(" ", "_")
+        key = f"{name}|{sched}|{pred}".replace(" ", "_") + ("|" + "|".join(f"{k}={v}" for k, v in extra.items()) if extra else "")
         out[key + "|final"] = res.numpy()
         out[key + "|denoised"] = torch.stack(dens).numpy()
         out[key + "|unet_x"] = torch.stack(u_x).numpy()
@@ -167,9 +193,12 @@ def main():
     import cpd.scheduler.k as K
 
     os.makedirs(GOLD, exist_ok=True)
-    with open(os.path.join(GOLD, "schedule_kat.json"), "w") as f:
-        json.dump(schedule_kats(K), f, indent=1)
-    np.savez_compressed(os.path.join(GOLD, "ref_sampling.npz"), **reference_sampling(ref_shim))
+    if "--more-only" not in sys.argv:
+        with open(os.path.join(GOLD, "schedule_kat.json"), "w") as f:
+            json.dump(schedule_kats(K), f, indent=1)
+    if "--more-only" not in sys.argv:
+        np.savez_compressed(os.path.join(GOLD, "ref_sampling.npz"), **reference_sampling(ref_shim))
+    np.savez_compressed(os.path.join(GOLD, "ref_sampling2.npz"), **reference_sampling_more(ref_shim))
     print("golden fixtures written to", GOLD)
 
 

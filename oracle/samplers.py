@@ -1,13 +1,39 @@
-"""Oracle (test infrastructure): Euler / Euler-ancestral / DPM++ 2M loops and KDiffusionSampler.sample.
+"""Oracle (test infrastructure): the k-diffusion sampler loops and KDiffusionSampler.sample.
 
-Follows cpd/samplers/k_diffusion.py:56-82, cpd/samplers/euler.py:24-57,71-105 and
-cpd/samplers/dpmpp.py:23-56 (paths relative to /root/reference).  Noise is INJECTED
-(``noise_sampler`` replaces ``torch.randn_like``) so the CUDA path and the oracle consume identical
-tensors (RNG row).
+Follows cpd/samplers/k_diffusion.py:56-82, cpd/samplers/euler.py:24-57,71-105, cpd/samplers/dpmpp.py:23-56
+(DPM++ 2M) and :70-113 (DPM++ 2S ancestral), cpd/samplers/huen.py:24-58, cpd/samplers/dpm2.py:24-108 and
+cpd/samplers/lms.py:28-64 (paths relative to /root/reference).  Noise is INJECTED (``noise_sampler`` replaces
+``torch.randn_like``) so the CUDA path and the oracle consume identical tensors (RNG row).
+
+Sample thresholding (``clip_sample``, euler.py:55-56,93-94, dpmpp.py:51-52; threshold.py:47-88): repair D10 - the
+reference's thresholding returns ``x.half()``, which silently turns x, ``s_in = x.new_ones(...)`` and therefore the sigma
+handed to the Denoiser into fp16 for every later step.  Restated as what the extension computes (clamp to +-s, values
+rounded through fp16) with x kept fp32.
 """
+import numpy as np
 import torch
 
 from .denoiser import append_dims
+
+
+def threshold_apply(x, alg, threshold):
+    """threshold.py:47-63 (static) / :65-88 (dynamic): returns fp32 values rounded through fp16 (D10)."""
+    x = x.float().clone()
+    if alg == "static_thresholding":
+        s = threshold
+    elif alg == "dynamic_thresholding":
+        s = np.percentile(np.abs(x.cpu()), threshold, axis=tuple(range(1, x.ndim)))  # threshold.py:74-78
+        s = np.max(np.append(s, 1.0))  # :80
+    else:
+        raise NotImplementedError(alg)
+    torch.clamp_(x, -1 * s, s)
+    return x.half().float()
+
+
+def _clip(x, model_args):
+    if model_args.get("clip_sample", False):
+        return threshold_apply(x, model_args.get("clip_sample_alg", "dynamic_thresholding"), model_args.get("clip_sample_thresh", 90))
+    return x
 
 
 def to_ode(x, sigma, denoised):
@@ -37,6 +63,7 @@ def sample_euler(denoiser, x, sigmas, model_args, noise_sampler=None, callback=N
             callback({"x": x, "i": i, "sigma": sigmas[i], "sigma_hat": sigma_hat, "eps": den})
         dt = sigmas[i + 1] - sigma_hat
         x = x + d * dt
+        x = _clip(x, model_args)
     return x
 
 
@@ -54,6 +81,7 @@ def sample_euler_ancestral(denoiser, x, sigmas, model_args, noise_sampler, callb
         dt = sigma_down - sigmas[i]
         x = x + d * dt
         x = x + noise_sampler(x) * sigma_up
+        x = _clip(x, model_args)
     return x
 
 
@@ -78,11 +106,157 @@ def sample_dpmpp_2m(denoiser, x, sigmas, model_args, callback=None):
             r = h_last / h
             den_d = (1 + 1 / (2 * r)) * den - (1 / (2 * r)) * old_den
             x = (sigma_fn(t_next) / sigma_fn(t)) * x - (-h).expm1() * den_d
+        x = _clip(x, model_args)
         old_den = den
     return x
 
 
-SAMPLERS = {"Euler": sample_euler, "Euler Ancestral": sample_euler_ancestral, "DPM++ 2m": sample_dpmpp_2m}
+@torch.no_grad()
+def sample_heun(denoiser, x, sigmas, model_args, noise_sampler=None, callback=None):
+    """huen.py:24-58 ("Huen"), gamma = 0.  One randn_like per step is drawn and discarded (:40)."""
+    s_in = x.new_ones([x.shape[0]])
+    for i in range(len(sigmas) - 1):
+        model_args["t_idx"] = i
+        if noise_sampler is not None:
+            noise_sampler(x)
+        sigma_hat = sigmas[i] * 1.0
+        den = denoiser(x, sigma_hat * s_in, **model_args)
+        d = to_ode(x, sigma_hat, den)
+        if callback is not None:
+            callback({"x": x, "i": i, "sigma": sigmas[i], "sigma_hat": sigma_hat, "eps": den})
+        dt = sigmas[i + 1] - sigma_hat
+        if sigmas[i + 1] == 0:
+            x = x + d * dt
+        else:
+            x_2 = x + d * dt
+            den_2 = denoiser(x_2, sigmas[i + 1] * s_in, **model_args)
+            d_2 = to_ode(x_2, sigmas[i + 1], den_2)
+            d_prime = (d + d_2) / 2
+            x = x + d_prime * dt
+    return x
+
+
+@torch.no_grad()
+def sample_dpm2(denoiser, x, sigmas, model_args, noise_sampler=None, callback=None):
+    """dpm2.py:24-56: cube-root midpoint, second evaluation on EVERY step (no sigma_next == 0 special case)."""
+    s_in = x.new_ones([x.shape[0]])
+    for i in range(len(sigmas) - 1):
+        model_args["t_idx"] = i
+        if noise_sampler is not None:
+            noise_sampler(x)
+        sigma_hat = sigmas[i] * 1.0
+        den = denoiser(x, sigma_hat * s_in, **model_args)
+        d = to_ode(x, sigma_hat, den)
+        if callback is not None:
+            callback({"x": x, "i": i, "sigma": sigmas[i], "sigma_hat": sigma_hat, "eps": den})
+        sigma_mid = ((sigma_hat ** (1 / 3) + sigmas[i + 1] ** (1 / 3)) / 2) ** 3
+        dt_1 = sigma_mid - sigma_hat
+        dt_2 = sigmas[i + 1] - sigma_hat
+        x_2 = x + d * dt_1
+        den_2 = denoiser(x_2, sigma_mid * s_in, **model_args)
+        d_2 = to_ode(x_2, sigma_mid, den_2)
+        x = x + d_2 * dt_2
+    return x
+
+
+@torch.no_grad()
+def sample_dpm2_ancestral(denoiser, x, sigmas, model_args, noise_sampler, callback=None):
+    """dpm2.py:74-108 (t_idx is NOT updated in this loop, like the reference)."""
+    s_in = x.new_ones([x.shape[0]])
+    for i in range(len(sigmas) - 1):
+        den = denoiser(x, sigmas[i] * s_in, **model_args)
+        sigma_down, sigma_up = get_ancestral_step(sigmas[i], sigmas[i + 1])
+        if callback is not None:
+            callback({"x": x, "i": i, "sigma": sigmas[i], "sigma_hat": sigmas[i], "eps": den})
+        d = to_ode(x, sigmas[i], den)
+        sigma_mid = ((sigmas[i] ** (1 / 3) + sigma_down ** (1 / 3)) / 2) ** 3
+        dt_1 = sigma_mid - sigmas[i]
+        dt_2 = sigma_down - sigmas[i]
+        x_2 = x + d * dt_1
+        den_2 = denoiser(x_2, sigma_mid * s_in, **model_args)
+        d_2 = to_ode(x_2, sigma_mid, den_2)
+        x = x + d_2 * dt_2
+        x = x + noise_sampler(x) * sigma_up
+    return x
+
+
+def get_ancestral_step_eta(sigma_from, sigma_to, eta=1.0):
+    """dpmpp.py:115-122."""
+    if not eta:
+        return sigma_to, 0.0
+    sigma_up = min(sigma_to, eta * (sigma_to ** 2 * (sigma_from ** 2 - sigma_to ** 2) / sigma_from ** 2) ** 0.5)
+    sigma_down = (sigma_to ** 2 - sigma_up ** 2) ** 0.5
+    return sigma_down, sigma_up
+
+
+@torch.no_grad()
+def sample_dpmpp_2s_ancestral(denoiser, x, sigmas, model_args, noise_sampler, callback=None):
+    """dpmpp.py:70-113 (eta = 1, temperature = 1 defaults; t_idx is not updated in this loop)."""
+    eta, tmp = model_args.get("eta", 1.0), model_args.get("temperature", 1.0)
+    s_in = x.new_ones([x.shape[0]])
+    sigma_fn = lambda t: t.neg().exp()
+    t_fn = lambda sigma: sigma.log().neg()
+    for i in range(len(sigmas) - 1):
+        den = denoiser(x, sigmas[i] * s_in, **model_args)
+        sigma_down, sigma_up = get_ancestral_step_eta(sigmas[i], sigmas[i + 1], eta=eta)
+        if callback is not None:
+            callback({"x": x, "i": i, "sigma": sigmas[i], "sigma_hat": sigmas[i], "eps": den})
+        if sigma_down == 0:
+            d = to_ode(x, sigmas[i], den)
+            dt = sigma_down - sigmas[i]
+            x = x + d * dt
+        else:
+            t, t_next = t_fn(sigmas[i]), t_fn(sigma_down)
+            r = 1 / 2
+            h = t_next - t
+            s = t + r * h
+            x_2 = (sigma_fn(s) / sigma_fn(t)) * x - (-h * r).expm1() * den
+            den_2 = denoiser(x_2, sigma_fn(s) * s_in, **model_args)
+            x = (sigma_fn(t_next) / sigma_fn(t)) * x - (-h).expm1() * den_2
+        x = x + noise_sampler(x) * tmp * sigma_up
+    return x
+
+
+def linear_multistep_coeff(order, t, i, j):
+    """lms.py:54-64 (scipy.integrate.quad, epsrel 1e-4)."""
+    from scipy import integrate
+    if order - 1 > i:
+        raise ValueError(f"Order {order} too high for step {i}")
+
+    def fn(tau):
+        prod = 1.0
+        for k in range(order):
+            if j == k:
+                continue
+            prod *= (tau - t[i - k]) / (t[i - j] - t[i - k])
+        return prod
+    return integrate.quad(fn, t[i], t[i + 1], epsrel=1e-4)[0]
+
+
+@torch.no_grad()
+def sample_lms(denoiser, x, sigmas, model_args, noise_sampler=None, callback=None):
+    """lms.py:28-52, order 4."""
+    order = model_args.get("order", 4)
+    s_in = x.new_ones([x.shape[0]])
+    ds = []
+    for i in range(len(sigmas) - 1):
+        model_args["t_idx"] = i
+        den = denoiser(x, sigmas[i] * s_in, **model_args)
+        d = to_ode(x, sigmas[i], den)
+        ds.append(d)
+        if len(ds) > order:
+            ds.pop(0)
+        if callback is not None:
+            callback({"x": x, "i": i, "sigma": sigmas[i], "sigma_hat": sigmas[i], "eps": den})
+        cur_order = min(i + 1, order)
+        coeffs = [linear_multistep_coeff(cur_order, sigmas.cpu(), i, j) for j in range(cur_order)]
+        x = x + sum(coeff * d for coeff, d in zip(coeffs, reversed(ds)))
+    return x
+
+
+SAMPLERS = {"Euler": sample_euler, "Euler Ancestral": sample_euler_ancestral, "DPM++ 2m": sample_dpmpp_2m,
+            "Huen": sample_heun, "DPM2": sample_dpm2, "DPM2 Ancestral": sample_dpm2_ancestral,
+            "DPM++ 2s Ancestral": sample_dpmpp_2s_ancestral, "LMS": sample_lms}
 
 
 @torch.no_grad()

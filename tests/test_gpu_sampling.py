@@ -446,3 +446,97 @@ def test_config4_sdxl_topology_dual_encoder_vector_conditioning(cpd):
         bad.pop("y")
         wrapper.sampler.sample(steps=2, batch_size=1, shape=[4, hw, hw], x_T=x_T[:1].clone(), rng_compat=False,
                                conditioning={"and": list(c["and"]), "not": []}, unconditional_conditioning=uc.clone())
+
+
+# ----------------------------------------------- remaining samplers, thresholding on device
+MORE_CASES = [("Huen", "karras", "epsilon", {}), ("DPM2", "karras", "epsilon", {}), ("DPM2 Ancestral", "karras", "epsilon", {}),
+              ("DPM++ 2s Ancestral", "karras", "epsilon", {}), ("LMS", "karras", "epsilon", {}), ("Huen", "exp", "velocity", {}),
+              ("Euler", "karras", "epsilon", {"scaled_clip": True, "scaled_clip_threshold": 97.0}),
+              ("DPM++ 2m", "karras", "epsilon", {"scaled_clip": True, "scaled_clip_alg": "static_thresholding",
+                                                 "scaled_clip_threshold": 0.5})]
+
+
+@pytest.mark.parametrize("name,sched,pred,extra", MORE_CASES)
+def test_more_samplers_bit_exact_vs_reference_golden_fp32(cpd, golden_dir, name, sched, pred, extra):
+    """The two-stage / multistep samplers and the Denoiser's scale clip, fed the UNet outputs the shimmed reference
+    recorded (tests/golden/ref_sampling2.npz): every UNet input (x * c_in, t), every denoised tensor and the final latent
+    equal the reference's bit for bit."""
+    from complex_prompt_diffusion_b200 import samplers
+    z, c = load_case(golden_dir)
+    z2 = np.load(os.path.join(golden_dir, "ref_sampling2.npz"))
+    key = f"{name}|{sched}|{pred}".replace(" ", "_") + ("|" + "|".join(f"{k}={v}" for k, v in extra.items()) if extra else "")
+    unet = ReplayUNet(list(torch.from_numpy(z2[key + "|unet_out"])), torch.float32, DEV,
+                      expect_x=torch.from_numpy(z2[key + "|unet_x"]), expect_t=torch.from_numpy(z2[key + "|unet_t"]))
+    wrapper = samplers.make({"name": name, "args": {}}, {"model": {"unet": unet}})
+    noises = list(torch.from_numpy(z2[key + "|noise"])) if (key + "|noise") in z2.files else []
+    dens = []
+    c_dev = {k: [(s, e, g_, m) for (s, e, g_, m) in v] for k, v in c.items()}
+    out = wrapper.sampler.sample(steps=int(z["steps"]), batch_size=1, shape=[4, int(z["hw"]), int(z["hw"])],
+                                 x_T=torch.from_numpy(z["x_T"]).clone(), conditioning=c_dev,
+                                 unconditional_conditioning=torch.from_numpy(z["uc"]),
+                                 unconditional_guidance_scale=float(z["guidance"]), scheduler=sched, pred_type=pred,
+                                 rng_compat=False, noise_sampler=(lambda x: noises.pop(0)) if noises else None,
+                                 callback=lambda d: dens.append(d["eps"].clone().cpu()), **extra)
+    torch.cuda.synchronize()
+    assert unet.i == len(unet.outs), "different number of UNet evaluations than the reference"
+    assert torch.equal(torch.stack(dens), torch.from_numpy(z2[key + "|denoised"])), "per-step denoised differs"
+    assert torch.equal(out.cpu(), torch.from_numpy(z2[key + "|final"])), "final latent differs"
+
+
+@pytest.mark.parametrize("n,L,q", [(1, 4 * 64 * 64, 99.5), (3, 4 * 32 * 32, 90.0), (2, 4 * 128 * 128, 97.3), (5, 64, 50.0),
+                                   (1, 4 * 96 * 96, 100.0), (2, 1024, 0.0)])
+def test_threshold_percentile_matches_numpy(cpd, n, L, q):
+    """cpd_threshold: per-image percentile of |x| (exact radix select + numpy's linear interpolation) and the clamp +
+    fp16 rounding of threshold.py:65-88, bit for bit against np.percentile on the same data."""
+    from complex_prompt_diffusion_b200 import ops
+    from complex_prompt_diffusion_b200._lib import CPD_THRESH_DYNAMIC, CPD_THRESH_STATIC
+    g = torch.Generator().manual_seed(n * 1000 + L)
+    x = torch.randn(n, L, generator=g) * torch.tensor([0.3, 1.0, 2.5, 0.05, 4.0][:n]).reshape(n, 1)
+    x[0, :7] = x[0, 7]  # duplicates
+    xd = x.to(DEV).clone()
+    bound = torch.empty(n, dtype=torch.float32, device=DEV)
+    ops.threshold(xd, bound, alg=CPD_THRESH_DYNAMIC, threshold=q, clamp_inplace=True)
+    torch.cuda.synchronize()
+    for b in range(n):
+        s = np.percentile(np.abs(x[b:b + 1].numpy()), q, axis=(1,))
+        s = np.max(np.append(s, 1.0))
+        assert float(bound[b]) == float(np.float32(s)), (b, float(bound[b]), s)
+        ref = torch.clamp(x[b].clone(), -1 * s, s).half().float()
+        assert torch.equal(xd[b].cpu(), ref)
+    ops.threshold(xd, bound, alg=CPD_THRESH_STATIC, threshold=0.25, clamp_inplace=True)
+    torch.cuda.synchronize()
+    assert float(xd.abs().max()) <= 0.25 and torch.all(bound.cpu() == 0.25)
+
+
+@pytest.mark.parametrize("name", ["Euler", "Euler Ancestral", "DPM++ 2m"])
+def test_clip_sample_on_device_vs_oracle(cpd, name):
+    """Sample thresholding after every update (clip_sample, euler.py:55-56,93-94, dpmpp.py:51-52) with the percentile
+    found on the device: bit-exact against the oracle (repair D10: x stays fp32 with fp16-rounded values), B = 2."""
+    from complex_prompt_diffusion_b200 import samplers
+    from oracle.denoiser import OracleDenoiser
+    from oracle import samplers as OS
+    g = torch.Generator().manual_seed(8)
+    B, hw, steps, D = 2, 16, 5, 64
+    uc = torch.randn(1, 77, D, generator=g)
+    embs = [torch.randn(1, 77, D, generator=g) for _ in range(2)]
+    c = {"and": [(1.0, embs[0], None, 1)], "not": [(0.5, embs[1], None, 1)]}
+    x_T = torch.randn(B, 4, hw, hw, generator=g)
+    outs = [(torch.randn(B, 1, 4, hw, hw, generator=g) + 0.3 * torch.randn(B, 3, 4, hw, hw, generator=g)).reshape(B * 3, 4, hw, hw)
+            for _ in range(steps)]
+    noises = [torch.randn(B, 4, hw, hw, generator=g) for _ in range(steps)]
+    kw = dict(conditioning=c, unconditional_conditioning=uc, unconditional_guidance_scale=7.5, scheduler="karras",
+              clip_sample=True, clip_sample_thresh=85.0, scaled_clip=True, scaled_clip_threshold=99.0)
+    finals = []
+    for b in range(B):
+        unet = ReplayUNet([o.view(B, 3, 4, hw, hw)[b] for o in outs], torch.float32, "cpu")
+        nz = [n[b:b + 1] for n in noises]
+        finals.append(OS.sample(OracleDenoiser(unet, dtype=torch.float32), name, steps, x_T[b:b + 1].clone(),
+                                noise_sampler=lambda x: nz.pop(0), **dict(kw)))
+    ref = torch.cat(finals)
+    unet = ReplayUNet(outs, torch.float32, DEV)
+    wrapper = samplers.make({"name": name, "args": {}}, {"model": {"unet": unet}})
+    nz2 = list(noises)
+    out = wrapper.sampler.sample(steps=steps, batch_size=B, shape=[4, hw, hw], x_T=x_T.clone(), rng_compat=False,
+                                 noise_sampler=lambda x: nz2.pop(0), **dict(kw))
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), ref)

@@ -172,3 +172,34 @@ def test_fp16_delta_differs_from_exact_combine():
     exact = e_u + 7.5 * sum(wk * (ek - e_u) for wk, ek in zip(w, e_k))
     rel = ((got - exact).norm() / exact.norm()).item()
     assert 1e-4 < rel < 1e-2
+
+
+# ---- remaining k-diffusion samplers + Denoiser scale clip (tests/golden/ref_sampling2.npz, oracle/make_golden.py) ----
+MORE_CASES = [("Huen", "karras", "epsilon", {}), ("DPM2", "karras", "epsilon", {}), ("DPM2 Ancestral", "karras", "epsilon", {}),
+              ("DPM++ 2s Ancestral", "karras", "epsilon", {}), ("LMS", "karras", "epsilon", {}), ("Huen", "exp", "velocity", {}),
+              ("Euler", "karras", "epsilon", {"scaled_clip": True, "scaled_clip_threshold": 97.0}),
+              ("DPM++ 2m", "karras", "epsilon", {"scaled_clip": True, "scaled_clip_alg": "static_thresholding",
+                                                 "scaled_clip_threshold": 0.5})]
+
+
+def more_key(name, sched, pred, extra):
+    return f"{name}|{sched}|{pred}".replace(" ", "_") + ("|" + "|".join(f"{k}={v}" for k, v in extra.items()) if extra else "")
+
+
+@pytest.mark.parametrize("name,sched,pred,extra", MORE_CASES)
+def test_oracle_more_samplers_bit_exact_on_replayed_unet(golden_dir, name, sched, pred, extra):
+    z, c = _load_case(golden_dir)
+    z2 = np.load(os.path.join(golden_dir, "ref_sampling2.npz"))
+    key = more_key(name, sched, pred, extra)
+    unet = _ReplayUNet(torch.from_numpy(z2[key + "|unet_out"]), torch.from_numpy(z2[key + "|unet_x"]), torch.from_numpy(z2[key + "|unet_t"]))
+    den = OracleDenoiser(unet, dtype=torch.float32)
+    noises = list(torch.from_numpy(z2[key + "|noise"])) if (key + "|noise") in z2.files else []
+    dens = []
+    out = OS.sample(den, name, int(z["steps"]), torch.from_numpy(z["x_T"]).clone(),
+                    noise_sampler=(lambda x: noises.pop(0)) if noises else None,
+                    callback=lambda d: dens.append(d["eps"].clone()),
+                    conditioning=c, unconditional_conditioning=torch.from_numpy(z["uc"]),
+                    unconditional_guidance_scale=float(z["guidance"]), scheduler=sched, pred_type=pred, **extra)
+    assert unet.i == len(unet.outs), "the restatement made a different number of UNet evaluations than the reference"
+    assert torch.equal(torch.stack(dens), torch.from_numpy(z2[key + "|denoised"]))
+    assert torch.equal(out, torch.from_numpy(z2[key + "|final"]))

@@ -269,7 +269,15 @@ def sample(denoiser, name, steps, x_T, noise_sampler=None, callback=None, **kwar
     """
     scheduler = kwargs.get("scheduler", "default")
     sigmas = denoiser.scheduler.get_sigmas(scheduler, steps, **kwargs)
-    x = x_T * sigmas[0]  # k_diffusion.py:74
+    if kwargs.get("decode", False):  # img2img branch, k_diffusion.py:64-70 (the frame-to-frame step of cpd/animation.py:171-176)
+        denoising_strength = kwargs.get("denoising_strength", 0.0)
+        t_enc = int((1 - min(denoising_strength, 0.999)) * steps)
+        sigmas = sigmas[steps - t_enc - 1:]
+        noise = torch.randn(list(x_T.shape))
+        noise = noise * sigmas[0]
+        x = x_T + noise
+    else:
+        x = x_T * sigmas[0]  # k_diffusion.py:74
     kwargs["total_steps"] = len(sigmas)  # :76
     fn = SAMPLERS[name]
     if name == "DPM++ 2m":

@@ -81,3 +81,18 @@ def test_allgather_paths_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert all(ok1 and ok2 for _, ok1, ok2 in res), res
+
+
+@pytest.mark.parametrize("n_frames,seg,world", [(64, 8, 1), (64, 8, 2), (64, 8, 4), (64, 8, 8), (10, 4, 3), (5, 8, 2), (0, 4, 2)])
+def test_animation_segments_cover_every_frame_once(n_frames, seg, world):
+    """BASELINE.json configs[4]: frames shard across ranks as whole independent segments."""
+    from complex_prompt_diffusion_b200.animation import segments, segments_for_rank
+    seen = []
+    for r in range(world):
+        for (a, b) in segments_for_rank(n_frames, seg, world, r):
+            assert 0 <= a < b <= n_frames and b - a <= seg
+            seen += list(range(a, b))
+    assert sorted(seen) == list(range(n_frames))
+    assert sum(b - a for a, b in segments(n_frames, seg)) == n_frames
+    if n_frames == 64 and seg == 8:
+        assert all(len(segments_for_rank(n_frames, seg, world, r)) == 8 // world for r in range(world))

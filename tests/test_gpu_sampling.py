@@ -540,3 +540,49 @@ def test_clip_sample_on_device_vs_oracle(cpd, name):
                                  noise_sampler=lambda x: nz2.pop(0), **dict(kw))
     torch.cuda.synchronize()
     assert torch.equal(out.cpu(), ref)
+
+
+def test_config5_frame_sequence_chain_vs_oracle(cpd):
+    """BASELINE.json configs[4] at a CPU-checkable size: a frame sequence in independent segments; inside a segment frame i
+    is an img2img sample (decode=True, denoising_strength, truncated schedule k_diffusion.py:64-70) started from frame i-1,
+    with per-frame prompts.  The GPU drop-in path renders rank 0's and rank 1's segments of a 2-rank deal; the oracle
+    renders the same chains on the CPU."""
+    from complex_prompt_diffusion_b200 import samplers
+    from complex_prompt_diffusion_b200.animation import render_sequence, segments
+    from oracle.denoiser import OracleDenoiser
+    from oracle import samplers as OS
+    cfg, oracle, gpu = _unet_pair("tiny", torch.float32)
+    oracle.sd = {k: v.to(torch.bfloat16).float() for k, v in oracle.sd.items()}
+    g = torch.Generator().manual_seed(9)
+    hw, steps, n_frames, seg, strength = 16, 6, 6, 3, 0.45
+    D = cfg.context_dim
+    uc = torch.randn(1, 77, D, generator=g)
+    a, b = torch.randn(1, 77, D, generator=g), torch.randn(1, 77, D, generator=g)
+    frames = []
+    for i in range(n_frames):  # prompt lerp a -> b over the sequence (animation.py:139-141)
+        w = i / (n_frames - 1)
+        frames.append({"conditioning": {"and": [(1.0, torch.lerp(a, b, w), None, 1)], "not": []},
+                       "unconditional_conditioning": uc, "seed": 100 + i})
+    wrapper = samplers.make({"name": "Euler", "args": {}}, {"model": {"unet": gpu}})
+    common = dict(unconditional_guidance_scale=5.0, scheduler="karras", rng_compat=False)
+    got = {}
+    for rank in range(2):
+        got.update(render_sequence(wrapper, frames, steps=steps, shape=[4, hw, hw], segment_len=seg, strength=strength, world=2,
+                                   rank=rank, **common))
+    torch.cuda.synchronize()
+    assert sorted(got) == list(range(n_frames))
+    od = OracleDenoiser(_oracle_side(oracle), dtype=torch.bfloat16)
+    for (s0, s1) in segments(n_frames, seg):
+        prev = None
+        for i in range(s0, s1):
+            kw = dict(conditioning=frames[i]["conditioning"], unconditional_conditioning=uc, unconditional_guidance_scale=5.0,
+                      scheduler="karras")
+            torch.manual_seed(frames[i]["seed"])
+            if prev is None:
+                ref = OS.sample(od, "Euler", steps, torch.randn(1, 4, hw, hw), **kw)
+            else:
+                ref = OS.sample(od, "Euler", steps, prev, decode=True, denoising_strength=strength, **kw)
+            prev = ref.clone()
+            r = rel(got[i], ref)
+            print(f"config 5: frame {i} latent rel-L2 {r:.3e}")
+            assert r < 2e-2

@@ -48,9 +48,18 @@ __device__ unsigned long long cpd_dbg_ts[16];
       cpd_dbg_ts[i] = _t;                                                             \
     }                                                                                 \
   } while (0)
+// epilogue chunk phases of the first two tiles (group 0 leader of CTA 0): [tile][chunk][phase], clock64
+__device__ long long cpd_dbg_epi[2][8][8];
+#define EPI_STAMP(ph)                                                                          \
+  do {                                                                                         \
+    if (blockIdx.x == 0 && grp == 0 && leader && it < 2 && (ch - c_lo) < 8) cpd_dbg_epi[it][ch - c_lo][ph] = clock64(); \
+  } while (0)
 #else
 #define CPD_STAMP(i) \
   do {               \
+  } while (0)
+#define EPI_STAMP(ph) \
+  do {                \
   } while (0)
 #endif
 
@@ -94,8 +103,10 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tmem_full = empty_bar + MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* res_bar = tmem_empty + 2;  // [2 groups][STAGING_BUFS]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + 2 * STAGING_BUFS);
+  uint64_t* res_bar = tmem_empty + 2;  // [2 groups][STAGING_BUFS]  residual tile landed in the staging buffer (TMA tx)
+  uint64_t* chunk_ready = res_bar + 2 * STAGING_BUFS;  // [2][STAGING_BUFS]  128 epilogue threads have written the chunk
+  uint64_t* buf_free = chunk_ready + 2 * STAGING_BUFS;  // [2][STAGING_BUFS]  the TMA store has finished reading the buffer
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(buf_free + 2 * STAGING_BUFS);
 
   const ConvGeom& g = args.g;
   const int warp = threadIdx.x >> 5;
@@ -135,7 +146,11 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
     if (args.residual) tma_prefetch_desc(&args.map_res);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < 2 * STAGING_BUFS; ++s) mbar_init(&res_bar[s], 1);
+    for (int s = 0; s < 2 * STAGING_BUFS; ++s) {
+      mbar_init(&res_bar[s], 1);
+      mbar_init(&chunk_ready[s], 128);
+      mbar_init(&buf_free[s], 1);
+    }
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 2);   // leader: its own arrive.expect_tx + the peer's remote arrive
       mbar_init(&empty_bar[s], MC);  // one tcgen05.commit (multicast to the whole cluster) per pair that reads it
@@ -301,9 +316,9 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
   } else if (warp >= FIRST_EPI_WARP) {
     // ================= epilogue (warps 4..11 of both CTAs) =================
     // Two groups of 4 warps (one warp per TMEM lane quarter); group `grp` owns every other half of the tile's
-    // 32-column chunks.  Per chunk: [leader] make sure the staging buffer two chunks back has been read by its TMA
-    // store and prefetch the NEXT chunk's residual tile -> [all] wait for this chunk's residual -> TMEM load ->
-    // epilogue math -> swizzled st.shared -> group barrier -> [leader] TMA store.
+    // 32-column chunks.  Per chunk: TMEM load -> epilogue math -> wait until the staging buffer is free (or, with a
+    // residual, until its tile has landed there) -> swizzled st.shared -> arrive on chunk_ready.  The store warp (warp 3)
+    // issues the TMA store, recycles the buffers and prefetches the residual tiles.
     const bool of16 = g.out_fp16 != 0;
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
     const int grp = (warp - FIRST_EPI_WARP) >> 2;   // epilogue group
@@ -321,21 +336,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
     const uint32_t sw = (uint32_t)((r >> 1) & 3);   // SWIZZLE_64B: 16-byte chunk index ^= (row / 2) % 4
     uint8_t* my_row = nullptr;                      // set per buffer
 
-    // residual tile of chunk (tile t, chunk ch) -> staging buffer `buf`
-    auto issue_residual = [&](int t, int ch, int buf) {
-      int m2, n_tile;
-      tile_mn(t, m2, n_tile);
-      const int col0 = n_tile * out_w + ch * CHUNK_COLS;
-      mbar_arrive_expect_tx(&my_res_bar[buf], CHUNK_BYTES);
-      for (int j = 0; j < g.nbox; ++j) {
-        const BoxCoord bc = box_coord(g, m2 * 2 + (int)rank, j, 4, 0);
-        tma_load_4d(my_staging + buf * CHUNK_BYTES + j * box_rows * (CHUNK_COLS * 2), &args.map_res, &my_res_bar[buf], col0, bc.x,
-                    bc.y, bc.n);
-      }
-    };
-
     int kc = 0;  // chunks processed by this group so far (staging buffer = kc % 3, residual barrier parity = (kc / 3) & 1)
-    if (leader && has_res && cluster_id < total_tiles && c_lo < c_hi) issue_residual(cluster_id, c_lo, 0);
     int it = 0;
     for (int t = cluster_id; t < total_tiles; t += num_clusters, ++it) {
       int m2, n_tile;
@@ -388,18 +389,8 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
         const int buf = kc % STAGING_BUFS;
         uint8_t* sbuf = my_staging + buf * CHUNK_BYTES;
         my_row = sbuf + r * (CHUNK_COLS * 2);
-        if (leader) {
-          // the store issued two chunks ago has finished READING its buffer (= the buffer of chunk kc + 1)
-          bulk_wait_group_read<1>();
-          if (has_res) {
-            int nt = t, nc = ch + 1;
-            if (nc == c_hi) {
-              nt = t + num_clusters;
-              nc = c_lo;
-            }
-            if (nt < total_tiles) issue_residual(nt, nc, (kc + 1) % STAGING_BUFS);
-          }
-        }
+        EPI_STAMP(0);
+        EPI_STAMP(1);
         const int col0 = n_tile * out_w + ch * CHUNK_COLS;  // first output column of this chunk
         float f[32];
         uint32_t packed[16];  // GEGLU produces packed 16-bit pairs directly
@@ -430,6 +421,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
           uint32_t v[32];
           tmem_ld32(taddr + ch * CHUNK_COLS, v);
           tmem_ld_wait();
+          EPI_STAMP(2);
 #pragma unroll
           for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
           if (col0 + CHUNK_COLS <= g.n_store) {
@@ -457,6 +449,10 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
             }
           }
         }
+        EPI_STAMP(3);
+        // the staging buffer is ours once its previous TMA store has been read out: with a residual the landed residual
+        // tile implies it (the store warp loads it only into a freed buffer), otherwise the store warp says so
+        if (!has_res) mbar_wait(&buf_free[grp * STAGING_BUFS + buf], (uint32_t)(((kc / STAGING_BUFS) & 1) ^ 1), 6);
         if (has_res && !geglu) {
           mbar_wait(&my_res_bar[buf], (uint32_t)((kc / STAGING_BUFS) & 1), 5);
 #pragma unroll
@@ -481,24 +477,19 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
         for (int c16 = 0; c16 < 4; ++c16)
           *reinterpret_cast<uint4*>(my_row + ((c16 ^ sw) << 4)) =
               make_uint4(packed[c16 * 4], packed[c16 * 4 + 1], packed[c16 * 4 + 2], packed[c16 * 4 + 3]);
+        EPI_STAMP(4);
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+        EPI_STAMP(5);
         if (ch + 1 == c_hi) {
           // last TMEM read of this tile by this warp: hand the accumulator back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], leader_crank);
         }
-        named_bar_sync(1 + grp, 128);
-        if (leader) {
-          if (col0 < g.n_store) {
-            for (int j = 0; j < g.nbox; ++j) {
-              const BoxCoord bc = box_coord(g, m_tile, j, 4, 0);
-              tma_store_4d(&args.map_d, sbuf + j * box_rows * (CHUNK_COLS * 2), col0, bc.x, bc.y, bc.n);
-            }
-          }
-          bulk_commit_group();
-          if (t == cluster_id && grp == 0 && ch == c_lo) CPD_STAMP(7);
-        }
+        mbar_arrive(&chunk_ready[grp * STAGING_BUFS + buf]);  // the store warp issues the TMA store: nobody waits here
+        EPI_STAMP(6);
+        if (t == cluster_id && grp == 0 && ch == c_lo && leader) CPD_STAMP(7);
+        EPI_STAMP(7);
       }
       if (c_lo == c_hi) {  // this group has no chunk in the tile (single-chunk tiles): still release the accumulator
         tc_fence_before();
@@ -506,10 +497,89 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
         if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], leader_crank);
       }
     }
-    // the staging buffers must outlive the TMA engine's READS of them; the global writes themselves are complete (and
-    // visible to the next kernel) at grid completion like any other store
-    if (leader) bulk_wait_group_read<0>();
     if (leader && grp == 0) CPD_STAMP(8);
+  } else if (warp == 3 && lane < 2 && splits == 1) {
+    // ================= store warp: lane g serves epilogue group g =================
+    // The TMA store of a finished chunk (~650 cycles to issue), the wait for older stores to release their staging
+    // buffers and the residual prefetch used to sit in the epilogue leader's path behind a 128-thread barrier, i.e. on
+    // the critical path of every chunk (2200 cycles per 128 x 32 chunk, more than the main loop of any layer with
+    // K <= 1280).  Here the 128 epilogue threads only arrive on chunk_ready and go on; this thread issues the store,
+    // frees the buffer of the previous chunk once it has been read (buf_free, or by loading the next residual tile into
+    // it) and keeps STAGING_BUFS residual tiles in flight.
+    const int grp = lane;
+    const bool geglu = g.epilogue == CPD_EPI_GEGLU;
+    const int bn = args.bn;
+    const int out_w = geglu ? (bn >> 1) : bn * args.nsub;
+    const int nch = out_w / CHUNK_COLS;
+    const int c_lo = grp == 0 ? 0 : (nch + 1) / 2, c_hi = grp == 0 ? (nch + 1) / 2 : nch;
+    const int box_rows = g.tw * g.th * g.nb;
+    uint8_t* my_staging = staging + grp * STAGING_BUFS * CHUNK_BYTES;
+    uint64_t* my_res_bar = res_bar + grp * STAGING_BUFS;
+    uint64_t* my_ready = chunk_ready + grp * STAGING_BUFS;
+    uint64_t* my_free = buf_free + grp * STAGING_BUFS;
+    const bool has_res = args.residual != nullptr;
+    if (c_lo < c_hi) {
+      auto issue_residual = [&](int t, int ch, int buf) {
+        int m2, n_tile;
+        tile_mn(t, m2, n_tile);
+        const int col0 = n_tile * out_w + ch * CHUNK_COLS;
+        mbar_arrive_expect_tx(&my_res_bar[buf], CHUNK_BYTES);
+        for (int j = 0; j < g.nbox; ++j) {
+          const BoxCoord bc = box_coord(g, m2 * 2 + (int)rank, j, 4, 0);
+          tma_load_4d(my_staging + buf * CHUNK_BYTES + j * box_rows * (CHUNK_COLS * 2), &args.map_res, &my_res_bar[buf], col0, bc.x,
+                      bc.y, bc.n);
+        }
+      };
+      int t_r = cluster_id, ch_r = c_lo, kc_r = 0;  // residual prefetch cursor
+      auto advance_r = [&]() {
+        ++kc_r;
+        if (++ch_r == c_hi) {
+          ch_r = c_lo;
+          t_r += num_clusters;
+        }
+      };
+      if (has_res)
+        for (int i = 0; i < STAGING_BUFS && t_r < total_tiles; ++i) {
+          issue_residual(t_r, ch_r, kc_r % STAGING_BUFS);
+          advance_r();
+        }
+      int kc = 0;
+      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+        int m2, n_tile;
+        tile_mn(t, m2, n_tile);
+        const int m_tile = m2 * 2 + (int)rank;
+        const BoxCoord bc0 = box_coord(g, m_tile, 0, 4, 0);  // once per tile: the chunks differ only in their column
+        for (int ch = c_lo; ch < c_hi; ++ch, ++kc) {
+          const int buf = kc % STAGING_BUFS;
+          const uint8_t* sbuf = my_staging + buf * CHUNK_BYTES;
+          const int col0 = n_tile * out_w + ch * CHUNK_COLS;
+          mbar_wait(&my_ready[buf], (uint32_t)((kc / STAGING_BUFS) & 1), 7);
+          if (col0 < g.n_store) {
+            tma_store_4d(&args.map_d, sbuf, col0, bc0.x, bc0.y, bc0.n);
+            for (int j = 1; j < g.nbox; ++j) {
+              const BoxCoord bc = box_coord(g, m_tile, j, 4, 0);
+              tma_store_4d(&args.map_d, sbuf + j * box_rows * (CHUNK_COLS * 2), col0, bc.x, bc.y, bc.n);
+            }
+          }
+          bulk_commit_group();
+          if (kc >= 1) {
+            bulk_wait_group_read<1>();  // every store but the one just issued has been read: chunk kc - 1's buffer is free
+            const int prev = (kc - 1) % STAGING_BUFS;
+            if (has_res) {
+              if (t_r < total_tiles) {
+                issue_residual(t_r, ch_r, prev);  // kc_r == kc + 2: this IS the buffer that chunk will use
+                advance_r();
+              }
+            } else {
+              mbar_arrive(&my_free[prev]);
+            }
+          }
+        }
+      }
+      // the staging buffers must outlive the TMA engine's READS of them; the global writes themselves are complete (and
+      // visible to the next kernel) at grid completion like any other store
+      bulk_wait_group_read<0>();
+    }
   }
 
   __syncwarp();
@@ -632,6 +702,9 @@ cpd_status launch2(const Gemm2Args& args, int smem_bytes, cudaStream_t stream) {
 #ifdef CPD_TIMELINE
 extern "C" int cpd_debug_gemm_timeline(unsigned long long* host16) {
   return (int)cudaMemcpyFromSymbol(host16, cpd_dbg_ts, sizeof(unsigned long long) * 16);
+}
+extern "C" int cpd_debug_gemm_epilogue(long long* host128) {
+  return (int)cudaMemcpyFromSymbol(host128, cpd_dbg_epi, sizeof(long long) * 128);
 }
 #endif
 

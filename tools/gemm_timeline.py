@@ -28,6 +28,17 @@ def main():
         print(f"M={M} N={N} K={K}:")
         for i, nm in enumerate(NAMES):
             print(f"   {nm:40s} +{(ts[i] - ts[0]) / 1e3:7.2f} us")
+        ep = (C.c_longlong * 128)()
+        lib.cpd_debug_gemm_epilogue(ep)
+        names = ["chunk top", "buffer free", "tmem ld done", "bias added", "st.shared done", "proxy fence", "group barrier", "store issued"]
+        for tile in range(2):
+            for ch in range(8):
+                row = [ep[(tile * 8 + ch) * 8 + ph] for ph in range(8)]
+                if row[0] == 0:
+                    continue
+                t0 = ep[(tile * 8) * 8]
+                print(f"   epilogue tile {tile} chunk {ch}: " + "  ".join(f"{n}=+{v - t0}" for n, v in zip(names, row)))
+        C.memset(C.addressof(ep), 0, C.sizeof(ep))
 
 
 if __name__ == "__main__":

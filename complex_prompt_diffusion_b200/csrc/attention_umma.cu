@@ -269,6 +269,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) attention_kernel(const __grid_
 
 cpd_status cpd_attention_2tile(const cpd_attn_params* p, void* stream);       // attention_umma2.cu
 cpd_status cpd_attention_persistent(const cpd_attn_params* p, void* stream);  // attention_umma3.cu
+cpd_status cpd_attention_split(const cpd_attn_params* p, void* stream);       // attention_umma4.cu
 
 extern "C" cpd_status cpd_attention(const cpd_attn_params* p, void* stream) {
   CPD_REQUIRE(p && p->q && p->k && p->vt && p->o, "cpd_attention: null pointer");
@@ -282,6 +283,15 @@ extern "C" cpd_status cpd_attention(const cpd_attn_params* p, void* stream) {
     if (persist < 0) {
       const char* e = getenv("CPD_ATTN_PERSIST");
       persist = (e && e[0] == '0') ? 0 : 1;
+    }
+    static int split = -1;  // CPD_ATTN_SPLIT=0: never the split-row kernel (attention_umma4.cu)
+    if (split < 0) {
+      const char* e = getenv("CPD_ATTN_SPLIT");
+      split = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (split) {
+      const cpd_status st4 = cpd_attention_split(p, stream);
+      if (st4 != CPD_ERR_UNSUPPORTED) return st4;
     }
     if (persist) {
       const cpd_status st3 = cpd_attention_persistent(p, stream);

@@ -161,7 +161,9 @@ def test_conv1x1_two_sources(ops):
 # ------------------------------------------------------------------------------------------------ attention
 @pytest.mark.parametrize("B,H,Nq,Nk,d", [(2, 8, 256, 256, 40), (1, 4, 1024, 1024, 80), (2, 2, 64, 64, 160), (3, 8, 256, 77, 40),
                                          (2, 5, 576, 576, 64), (1, 2, 64, 64, 32), (4, 8, 4096, 77, 40), (1, 8, 4096, 4096, 40),
-                                         (2, 3, 320, 200, 40), (1, 2, 256, 1000, 96)])
+                                         (2, 3, 320, 200, 40), (1, 2, 256, 1000, 96),
+                                         # split-row kernel (attention_umma4.cu: d <= 63, more than two key blocks), ragged shapes
+                                         (2, 3, 300, 700, 40), (1, 2, 1000, 330, 48), (1, 1, 129, 257, 16), (2, 2, 512, 384, 63)])
 @pytest.mark.parametrize("two_tile", [False, True])
 def test_attention(ops, B, H, Nq, Nk, d, two_tile):
     """two_tile=True passes d_head, which selects the two-query-tile kernel with P in tensor memory (attention_umma2.cu)

@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention4_kernel(const __grid
     const uint32_t tO = tmem_base + (t ? colO1 : colO0) + lane_off;
     const int bar_id = 1 + t * 4 + qd;    // the SPLIT warps that hold the same 32 rows (same SM sub-partition)
     const int col0 = hf * CW;             // first key column (inside the block) of this thread
+    const uint32_t xch_addr = smem_u32(xch);
     float m_used = -INFINITY;
     for (int j = 0; j < nblk; ++j) {
       const int kv_valid = min(BKV, a.nk - j * BKV);
@@ -287,11 +288,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention4_kernel(const __grid
       // block maximum of the whole row: exchange the half maxima (double-buffered by block parity: a thread can be at
       // most one barrier ahead of its partner)
       float mx = fmaxf(mx0, mx1);
-      {
-        float* slot = xch + ((((j & 1) * 2 + t) * SPLIT) * 128);
-        slot[hf * 128 + r] = mx;
+      {  // explicit shared-space accesses (the carved-up dynamic buffer is a generic pointer to the compiler)
+        const uint32_t slot = xch_addr + (uint32_t)(((((j & 1) * 2 + t) * SPLIT) * 128 + r) * 4);
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(slot + hf * 512), "f"(mx) : "memory");
         named_bar_sync(bar_id, 32 * SPLIT);
-        mx = fmaxf(mx, slot[(hf ^ 1) * 128 + r]);
+        float other;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(slot + (hf ^ 1) * 512) : "memory");
+        mx = fmaxf(mx, other);
       }
       const float m_blk = mx * a.scale_log2;
       float alpha = 1.0f;

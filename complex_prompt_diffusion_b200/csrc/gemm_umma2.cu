@@ -10,7 +10,7 @@
 //     residual tile is PREFETCHED by TMA into the same staging buffer one chunk ahead, so no thread ever issues a
 //     row-strided global load or store.
 //   * warp roles: warp 0 = TMA producer (both CTAs), warp 1 = MMA issuer (leader CTA only), warp 2 = TMEM
-//     allocator, warps 4-11 = epilogue (two warps per TMEM lane quarter, each taking half of the columns).
+//     allocator, warps 4-11 = epilogue (EPI_GROUPS groups of four warps, one warp per TMEM lane quarter, each group taking a contiguous share of the columns); warp 3 = TMA-store issuer.
 //   * BN is a RUNTIME multiple of 32 (<= 256) chosen per layer so that BN divides N (320 -> 160, 640 -> 160/128,
 //     1280 -> 256/160) and the tile count fills whole waves of 74 SM pairs.
 //
@@ -24,7 +24,8 @@
 namespace {
 using namespace cpd_gemm;
 
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 8;   // 12 (three groups, 128-register cap, two staging buffers each) measured SLOWER: 240 vs 229.5 ms of GEMM time per generation
+constexpr int EPI_GROUPS = EPI_WARPS / 4;            // one warp per TMEM lane quarter in each group
 constexpr int FIRST_EPI_WARP = 4;
 constexpr int NUM_THREADS2 = 32 * (FIRST_EPI_WARP + EPI_WARPS);
 constexpr int ACC_COLS = 256;   // TMEM columns per accumulator stage
@@ -35,7 +36,7 @@ constexpr int NUM_SM_PAIRS = 74;
 constexpr int CHUNK_COLS = 32;                     // output columns per staging chunk (64-byte rows, SWIZZLE_64B)
 constexpr int CHUNK_BYTES = BM * CHUNK_COLS * 2;   // 8 KB
 constexpr int STAGING_BUFS = 3;                    // per epilogue group
-constexpr int STAGING_BYTES = 2 * STAGING_BUFS * CHUNK_BYTES;
+constexpr int STAGING_BYTES = EPI_GROUPS * STAGING_BUFS * CHUNK_BYTES;
 
 #ifdef CPD_TIMELINE
 // Debug build (make TIMELINE=1): CTA 0 stamps %globaltimer at the phases of its first tile (tools/gemm_timeline.py)
@@ -103,10 +104,10 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tmem_full = empty_bar + MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* res_bar = tmem_empty + 2;  // [2 groups][STAGING_BUFS]  residual tile landed in the staging buffer (TMA tx)
-  uint64_t* chunk_ready = res_bar + 2 * STAGING_BUFS;  // [2][STAGING_BUFS]  128 epilogue threads have written the chunk
-  uint64_t* buf_free = chunk_ready + 2 * STAGING_BUFS;  // [2][STAGING_BUFS]  the TMA store has finished reading the buffer
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(buf_free + 2 * STAGING_BUFS);
+  uint64_t* res_bar = tmem_empty + 2;  // [EPI_GROUPS][STAGING_BUFS]  residual tile landed in the staging buffer (TMA tx)
+  uint64_t* chunk_ready = res_bar + EPI_GROUPS * STAGING_BUFS;  // [groups][bufs]  128 epilogue threads have written the chunk
+  uint64_t* buf_free = chunk_ready + EPI_GROUPS * STAGING_BUFS;  // [groups][bufs]  the TMA store has finished reading the buffer
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(buf_free + EPI_GROUPS * STAGING_BUFS);
 
   const ConvGeom& g = args.g;
   const int warp = threadIdx.x >> 5;
@@ -146,7 +147,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
     if (args.residual) tma_prefetch_desc(&args.map_res);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < 2 * STAGING_BUFS; ++s) {
+    for (int s = 0; s < EPI_GROUPS * STAGING_BUFS; ++s) {
       mbar_init(&res_bar[s], 1);
       mbar_init(&chunk_ready[s], 128);
       mbar_init(&buf_free[s], 1);
@@ -315,7 +316,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
     }
   } else if (warp >= FIRST_EPI_WARP) {
     // ================= epilogue (warps 4..11 of both CTAs) =================
-    // Two groups of 4 warps (one warp per TMEM lane quarter); group `grp` owns every other half of the tile's
+    // EPI_GROUPS groups of 4 warps (one warp per TMEM lane quarter); group `grp` owns a contiguous share of the tile's
     // 32-column chunks.  Per chunk: TMEM load -> epilogue math -> wait until the staging buffer is free (or, with a
     // residual, until its tile has landed there) -> swizzled st.shared -> arrive on chunk_ready.  The store warp (warp 3)
     // issues the TMA store, recycles the buffers and prefetches the residual tiles.
@@ -328,7 +329,8 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
     const bool geglu = g.epilogue == CPD_EPI_GEGLU;
     const int out_w = geglu ? (bn >> 1) : bn * args.nsub;  // output columns per tile
     const int nch = out_w / CHUNK_COLS;
-    const int c_lo = grp == 0 ? 0 : (nch + 1) / 2, c_hi = grp == 0 ? (nch + 1) / 2 : nch;
+    const int c_lo = grp * (nch / EPI_GROUPS) + min(grp, nch % EPI_GROUPS);  // contiguous, sizes differ by at most one
+    const int c_hi = c_lo + nch / EPI_GROUPS + (grp < nch % EPI_GROUPS ? 1 : 0);
     const int box_rows = g.tw * g.th * g.nb;
     uint8_t* my_staging = staging + grp * STAGING_BUFS * CHUNK_BYTES;
     uint64_t* my_res_bar = res_bar + grp * STAGING_BUFS;
@@ -498,7 +500,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
       }
     }
     if (leader && grp == 0) CPD_STAMP(8);
-  } else if (warp == 3 && lane < 2 && splits == 1) {
+  } else if (warp == 3 && lane < EPI_GROUPS && splits == 1) {
     // ================= store warp: lane g serves epilogue group g =================
     // The TMA store of a finished chunk (~650 cycles to issue), the wait for older stores to release their staging
     // buffers and the residual prefetch used to sit in the epilogue leader's path behind a 128-thread barrier, i.e. on
@@ -511,7 +513,8 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
     const int bn = args.bn;
     const int out_w = geglu ? (bn >> 1) : bn * args.nsub;
     const int nch = out_w / CHUNK_COLS;
-    const int c_lo = grp == 0 ? 0 : (nch + 1) / 2, c_hi = grp == 0 ? (nch + 1) / 2 : nch;
+    const int c_lo = grp * (nch / EPI_GROUPS) + min(grp, nch % EPI_GROUPS);  // contiguous, sizes differ by at most one
+    const int c_hi = c_lo + nch / EPI_GROUPS + (grp < nch % EPI_GROUPS ? 1 : 0);
     const int box_rows = g.tw * g.th * g.nb;
     uint8_t* my_staging = staging + grp * STAGING_BUFS * CHUNK_BYTES;
     uint64_t* my_res_bar = res_bar + grp * STAGING_BUFS;
@@ -567,7 +570,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
             const int prev = (kc - 1) % STAGING_BUFS;
             if (has_res) {
               if (t_r < total_tiles) {
-                issue_residual(t_r, ch_r, prev);  // kc_r == kc + 2: this IS the buffer that chunk will use
+                issue_residual(t_r, ch_r, prev);  // kc_r == kc + STAGING_BUFS - 1: this IS the buffer that chunk will use
                 advance_r();
               }
             } else {

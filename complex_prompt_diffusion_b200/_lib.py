@@ -8,7 +8,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcpd_b200.so")
+LIB_PATH = os.environ.get("CPD_B200_LIB", os.path.join(_HERE, "libcpd_b200.so"))  # the override is for A/B measurements of two builds
 
 CPD_F32, CPD_F16, CPD_BF16 = 0, 1, 2
 CPD_EULER, CPD_EULER_ANCESTRAL, CPD_DPMPP_2M, CPD_DENOISE_ONLY, CPD_HEUN2, CPD_LMS = 0, 1, 2, 3, 4, 5

@@ -37,6 +37,8 @@ constexpr int CHUNK_COLS = 32;                     // output columns per staging
 constexpr int CHUNK_BYTES = BM * CHUNK_COLS * 2;   // 8 KB
 constexpr int STAGING_BUFS = 3;                    // per epilogue group
 constexpr int STAGING_BYTES = EPI_GROUPS * STAGING_BUFS * CHUNK_BYTES;
+constexpr int BIAS_FLOATS = 512;                   // widest tile: 2 sub-tiles x 256 columns
+constexpr int BIAS_BYTES = EPI_GROUPS * 2 * BIAS_FLOATS * 4;  // per group, double-buffered by tile parity
 
 #ifdef CPD_TIMELINE
 // Debug build (make TIMELINE=1): CTA 0 stamps %globaltimer at the phases of its first tile (tools/gemm_timeline.py)
@@ -100,7 +102,8 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
   const int stages = args.stages;
   const int stage_bytes = args.stage_bytes;
   uint8_t* staging = smem + stages * stage_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES);
+  float* bias_s = reinterpret_cast<float*>(staging + STAGING_BYTES);  // [EPI_GROUPS][2][BIAS_FLOATS]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES + BIAS_BYTES);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tmem_full = empty_bar + MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -347,15 +350,28 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
       const RowCoord rc = row_coord(g, m_tile, r);
       const int n_img_row = rc.n < g.n_img ? rc.n : g.n_img - 1;
       const float* rv = args.rowvec ? args.rowvec + (int64_t)n_img_row * g.rowvec_stride : nullptr;
-      {  // pull this tile's bias / time-embedding lines into L1 while the main loop runs (first-touch latency ~1 us)
-        const int bias_w = geglu ? bn : out_w;        // floats of bias per tile
-        const int lines = (bias_w + 31) >> 5;         // 128-byte lines
+      // This tile's bias goes to shared memory while the main loop runs (one L2 round trip per tile instead of one per
+      // 32-column chunk: prefetch.global.L1 did not keep the per-chunk __ldg from missing).  Double-buffered by tile parity:
+      // with one group barrier per tile a warp is at most one tile ahead of the slowest reader.
+      const int bias_w = geglu ? bn : out_w;  // floats of bias per tile
+      float* my_bias = bias_s + (grp * 2 + (it & 1)) * BIAS_FLOATS;
+      if (args.bias) {
         const int col_first = n_tile * bias_w;
-        if (r < lines && col_first + r * 32 < g.n_out) {
-          if (args.bias) asm volatile("prefetch.global.L1 [%0];" ::"l"(args.bias + col_first + r * 32));
+        const int idx = r * 4;
+        if (idx < bias_w) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (col_first + idx + 3 < g.n_out) {
+            v = __ldg(reinterpret_cast<const float4*>(args.bias + col_first + idx));
+          } else {
+            if (col_first + idx < g.n_out) v.x = __ldg(args.bias + col_first + idx);
+            if (col_first + idx + 1 < g.n_out) v.y = __ldg(args.bias + col_first + idx + 1);
+            if (col_first + idx + 2 < g.n_out) v.z = __ldg(args.bias + col_first + idx + 2);
+          }
+          *reinterpret_cast<float4*>(my_bias + idx) = v;
         }
-        if (rv && (lane < lines) && col_first + lane * 32 < g.n_out)
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(rv + col_first + lane * 32));
+        if (rv && (lane < ((bias_w + 31) >> 5)) && col_first + lane * 32 < g.n_out)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(rv + col_first + lane * 32));
+        named_bar_sync(1 + grp, 128);
       }
       const int acc = two_acc ? (it & 1) : 0;
       const uint32_t acc_phase = (uint32_t)((two_acc ? (it >> 1) : it) & 1);
@@ -404,13 +420,13 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
           tmem_ld32(taddr + ch * CHUNK_COLS, va);
           tmem_ld32(taddr + (bn >> 1) + ch * CHUNK_COLS, vg);
           tmem_ld_wait();
-          const float* bias_v = args.bias ? args.bias + n_tile * bn + ch * CHUNK_COLS : nullptr;
+          const float* bias_v = args.bias ? my_bias + ch * CHUNK_COLS : nullptr;  // shared memory (broadcast reads)
 #pragma unroll
           for (int e = 0; e < 32; e += 4) {
             float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bg = bv;
             if (bias_v) {
-              bv = __ldg(reinterpret_cast<const float4*>(bias_v + e));
-              bg = __ldg(reinterpret_cast<const float4*>(bias_v + (bn >> 1) + e));
+              bv = *reinterpret_cast<const float4*>(bias_v + e);
+              bg = *reinterpret_cast<const float4*>(bias_v + (bn >> 1) + e);
             }
             const uint32_t a01 = pack_act2(__uint_as_float(va[e]) + bv.x, __uint_as_float(va[e + 1]) + bv.y, of16);
             const uint32_t a23 = pack_act2(__uint_as_float(va[e + 2]) + bv.z, __uint_as_float(va[e + 3]) + bv.w, of16);
@@ -430,7 +446,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
             if (args.bias) {
 #pragma unroll
               for (int e = 0; e < 32; e += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(args.bias + col0 + e));
+                const float4 b4 = *reinterpret_cast<const float4*>(my_bias + ch * CHUNK_COLS + e);
                 f[e] += b4.x; f[e + 1] += b4.y; f[e + 2] += b4.z; f[e + 3] += b4.w;
               }
             }
@@ -445,7 +461,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
               if (col0 + e < g.n_store) {
-                if (args.bias) f[e] += __ldg(args.bias + col0 + e);
+                if (args.bias) f[e] += my_bias[ch * CHUNK_COLS + e];
                 if (rv) f[e] += __ldg(rv + col0 + e);
               }
             }
@@ -780,7 +796,7 @@ cpd_status cpd_gemm_conv_2cta(const cpd_gemm_params* p, void* stream) {
   args.n_tiles = (p->n_out + tile_w - 1) / tile_w;
   CPD_REQUIRE(mc == 1 || args.n_tiles % 2 == 0, "cpd_gemm_conv: the multicast cluster needs an even number of column tiles (BN=%d)", bn);
   args.stage_bytes = A_BYTES + tc.nsub * (bn / 2) * 128;
-  int stages = (227 * 1024 - 1024 - 512 - STAGING_BYTES) / args.stage_bytes;
+  int stages = (227 * 1024 - 1024 - 512 - STAGING_BYTES - BIAS_BYTES) / args.stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   {
     static int cap = -1;  // CPD_GEMM_STAGES: pipeline-depth experiments
@@ -826,7 +842,7 @@ cpd_status cpd_gemm_conv_2cta(const cpd_gemm_params* p, void* stream) {
     }
   }
 
-  const int smem_bytes = stages * args.stage_bytes + STAGING_BYTES + 512 + 1024;
+  const int smem_bytes = stages * args.stage_bytes + STAGING_BYTES + BIAS_BYTES + 512 + 1024;
   if (mc == 2) return launch2<2>(args, smem_bytes, (cudaStream_t)stream);
   const cpd_status st = launch2<1>(args, smem_bytes, (cudaStream_t)stream);
   if (st != CPD_OK || splits == 1) return st;

@@ -28,9 +28,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one gemm2_kernel launch (conv3x3 16x64x64 320->320, ncu --set full,
-# profiles/r01_ncu_full_summaries.txt): 43.8 MB + 2.7 MB; algorithmic bytes of that launch = 42 MB in + 42 MB out + 1.8 MB weights
-# (the output stays in the 126 MB L2 for the next kernel, so the write-back is not seen inside the launch).
-NCU_TRAFFIC = {"bytes_per_launch": 46.6e6, "launch": "conv3x3 M=65536 N=320 K=2880", "source": "profiles/r01_ncu_full_summaries.txt"}
+# profiles/r01_ncu_full_v2.txt): 43.9 MB + 8.1 MB; algorithmic bytes of that launch = 42 MB in + 42 MB out + 1.8 MB weights
+# (most of the output is still in the 126 MB L2 when the launch ends, so its write-back is not seen inside the launch).
+NCU_TRAFFIC = {"bytes_per_launch": 51.95e6, "launch": "conv3x3 M=65536 N=320 K=2880", "source": "profiles/r01_ncu_full_v2.txt"}
 
 WORKLOAD = dict(workload="SD-1.5 512px (64x64 latent), DPM++ 2M Karras 20 steps, 3 weighted sub-prompts + uncond, batch 4",
                 model="sd15", latent=64, sampler="DPM++ 2m", scheduler="karras", sampler_steps=20, n_sub=3, batch=4,
@@ -208,7 +208,8 @@ def run_b200(args):
                      attention_resolutions=tuple(cfg.attention_resolutions), num_res_blocks=cfg.num_res_blocks,
                      num_heads=cfg.num_heads, num_head_channels=cfg.num_head_channels, context_dim=cfg.context_dim,
                      use_linear_in_transformer=cfg.use_linear_in_transformer, transformer_depth=cfg.transformer_depth,
-                     adm_in_channels=cfg.adm_in_channels, num_classes="sequential" if cfg.adm_in_channels else None)
+                     adm_in_channels=cfg.adm_in_channels, num_classes="sequential" if cfg.adm_in_channels else None,
+                     use_cuda_graph=not args.no_graph)
     del sd
     n_sub, B, S = args.n_sub, args.batch, args.sampler_steps
     uc, c, x_T = make_inputs(cfg, args.latent, B, n_sub, seed=rank)

@@ -1,0 +1,25 @@
+#!/bin/bash
+# Round profiles: (1) ncu launch list of one bench step (gpu__time_duration only), (2) ncu --set full of the dominant kernels
+# on their hot shapes through the micro-benchmark tools, summarised to text on the box (the .ncu-rep files are too large to keep).
+# Usage (under gpurun): bash tools/capture_profiles.sh <tag>     -> gpurun_out/<tag>_launches.csv, gpurun_out/<tag>_ncu_full.txt
+tag=${1:-r01}
+mkdir -p gpurun_out /tmp/prof
+CPD_BENCH_NCU=1 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+  --log-file gpurun_out/${tag}_launches.csv python bench.py --sampler-steps 2 --steps 1 --warmup 1 --no-cpu-baseline --no-graph > /tmp/prof/launch.log 2>&1
+python tools/summarize_launches.py gpurun_out/${tag}_launches.csv > gpurun_out/${tag}_launches_summary.txt 2>&1
+out=gpurun_out/${tag}_ncu_full.txt
+: > $out
+cap() {  # name, kernel regex, skip, count, command...
+  local name=$1 rx=$2 skip=$3 cnt=$4; shift 4
+  ncu --set full --clock-control none -k regex:"$rx" -s $skip -c $cnt -f -o /tmp/prof/$name "$@" > /tmp/prof/$name.log 2>&1
+  echo "## $name: $*" >> $out
+  python tools/ncu_summary.py /tmp/prof/$name.ncu-rep >> $out 2>&1
+}
+cap gemm_conv3_64_320 gemm2_kernel 3 1 python tools/bench_gemm.py --only 0 --reps 2
+cap gemm_lin_16384_640_640 gemm2_kernel 3 1 python tools/bench_gemm.py --only 5 --reps 2
+cap attention_self_4096_d40 attention4_kernel 3 1 python tools/bench_attn.py --only 0 --reps 2
+cap attention_cross_4096x77_d40 attention3_kernel 3 1 python tools/bench_attn.py --only 3 --reps 2
+cap groupnorm "gn_" 6 4 python tools/bench_norm.py --only gn --reps 2
+cap layernorm layernorm_sub 3 1 python tools/bench_norm.py --only ln --reps 2
+cap sampler_step sampler_step_kernel 3 2 python tools/bench_step.py
+ls -la gpurun_out/${tag}_* | cat

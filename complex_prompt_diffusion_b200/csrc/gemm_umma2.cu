@@ -124,15 +124,21 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
   const int n_tiles_c = args.n_tiles / MC;         // column tiles per cluster step (host guarantees divisibility)
   const int splits = args.splits;
   const int total_tiles = args.m_tiles2 * n_tiles_c * splits;  // work units: (row block, column tile(s), K range)
+  // (integer divisions cost ~50 cycles each, 64-bit ones several hundred: the common splits == 1 / single-column-tile cases skip them)
   auto tile_mn = [&](int u, int& m2, int& n_tile) {
-    const int t = u / splits;
-    m2 = t / n_tiles_c;
+    const int t = splits == 1 ? u : u / splits;
+    m2 = n_tiles_c == 1 ? t : t / n_tiles_c;
     n_tile = (t - m2 * n_tiles_c) * MC + pair;
   };
   auto k_range = [&](int u, int& k0, int& k1) {
-    const int sp = u % splits;
-    k0 = (int)((long)sp * args.num_k / splits);
-    k1 = (int)((long)(sp + 1) * args.num_k / splits);
+    if (splits == 1) {
+      k0 = 0;
+      k1 = args.num_k;
+      return;
+    }
+    const unsigned sp = (unsigned)(u % splits);  // sp * num_k < 2^31: num_k <= a few thousand 64-channel blocks
+    k0 = (int)(sp * (unsigned)args.num_k / (unsigned)splits);
+    k1 = (int)((sp + 1u) * (unsigned)args.num_k / (unsigned)splits);
   };
   const int num_k = args.num_k;
   const int cbt = g.cb0 + g.cb1;

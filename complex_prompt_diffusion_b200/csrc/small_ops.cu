@@ -145,22 +145,29 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const bf16* __restrict__ 
     *reinterpret_cast<uint4*>(ws + i) = __ldg(reinterpret_cast<const uint4*>(wt + i));
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t pix = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
-  if (pix >= (int64_t)n * h * w) return;
+  const int nvec = cin / 8;
+  const int64_t total = (int64_t)n * h * w;
+  // persistent blocks: the COUT x 9 x cin weights are staged once per block, then every warp walks over output pixels
+  for (int64_t pix = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; pix < total; pix += (int64_t)gridDim.x * (blockDim.x >> 5)) {
   const int xx = (int)(pix % w);
   const int yy = (int)((pix / w) % h);
   const int nn = (int)(pix / ((int64_t)w * h));
   float acc[COUT];
 #pragma unroll
   for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
-  const int nvec = cin / 8;
-  for (int tap = 0; tap < 9; ++tap) {
-    const int iy = yy + tap / 3 - 1, ix = xx + tap % 3 - 1;
-    if (iy < 0 || iy >= h || ix < 0 || ix >= w) continue;
-    const bf16* src = a + (((int64_t)nn * h + iy) * w + ix) * cin;
-    for (int v = lane; v < nvec; v += 32) {
-      const uint4 av = __ldg(reinterpret_cast<const uint4*>(src + v * 8));
-      const uint32_t au[4] = {av.x, av.y, av.z, av.w};
+  for (int v = lane; v < nvec; v += 32) {
+    // all nine taps of this channel vector are loaded before the first use (nine 16-byte loads in flight per lane)
+    uint4 av9[9];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int iy = yy + tap / 3 - 1, ix = xx + tap % 3 - 1;
+      av9[tap] = make_uint4(0u, 0u, 0u, 0u);  // zero padding
+      if (iy >= 0 && iy < h && ix >= 0 && ix < w)
+        av9[tap] = __ldg(reinterpret_cast<const uint4*>(a + (((int64_t)nn * h + iy) * w + ix) * cin + v * 8));
+    }
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const uint32_t au[4] = {av9[tap].x, av9[tap].y, av9[tap].z, av9[tap].w};
       float af[8];
 #pragma unroll
       for (int e = 0; e < 4; ++e) { const float2 f = unpack_act2(au[e], f16 != 0); af[2 * e] = f.x; af[2 * e + 1] = f.y; }
@@ -187,6 +194,7 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const bf16* __restrict__ 
       if (out_dtype == CPD_BF16) reinterpret_cast<bf16*>(out)[oi] = __float2bfloat16_rn(v);
       else reinterpret_cast<float*>(out)[oi] = v;
     }
+  }
   }
 }
 
@@ -268,7 +276,8 @@ extern "C" cpd_status cpd_conv_out(const void* a, int n, int h, int w, int cin, 
   const int64_t pixels = (int64_t)n * h * w;
   const size_t shm = (size_t)cout * 9 * cin * 2;
   cudaStream_t s = (cudaStream_t)stream;
-  const unsigned blocks = (unsigned)((pixels + 7) / 8);
+  unsigned blocks = (unsigned)((pixels + 7) / 8);
+  if (blocks > 148 * 8) blocks = 148 * 8;  // persistent: weights staged once per block, full occupancy (64 warps per SM)
   if (cout == 4) {
     static bool cfg = false;
     if (!cfg) { CPD_CUDA_CHECK(cudaFuncSetAttribute(conv_out_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfg = true; }

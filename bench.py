@@ -398,6 +398,10 @@ def sampler_roofline(ops, dev, pk):
 
 
 if __name__ == "__main__":
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner under NCCL_DEBUG) are sent to stderr
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(_real_stdout, "w")
     a = parse()
     if a.impl == "reference":
         run_reference(a)

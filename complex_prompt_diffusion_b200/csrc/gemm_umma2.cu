@@ -194,6 +194,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
       int stage = 0;
       uint32_t phase = 0;
       const uint16_t mc_mask = (uint16_t)(0x5u << rank);  // same-rank CTAs of both pairs
+      if (lane == 0) CPD_STAMP(13);
       for (int t = cluster_id; t < total_tiles; t += num_clusters) {
         int m2, n_tile;
         tile_mn(t, m2, n_tile);
@@ -217,8 +218,10 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
             px = (kx == 0) ? 1 : kx - 1;
           }
         }
+        if (t == cluster_id && lane == 0) CPD_STAMP(11);
         for (int kt = k0; kt < k1; ++kt) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+          if (kt == k0 && t == cluster_id && lane == 0) CPD_STAMP(12);
           uint8_t* sa = smem + stage * stage_bytes;
           const bool src1 = cb >= g.cb0;
           const CUtensorMap* ma = src1 ? &args.map_a1 : &args.map_a0;

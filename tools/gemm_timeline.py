@@ -28,6 +28,8 @@ def main():
         print(f"M={M} N={N} K={K}:")
         for i, nm in enumerate(NAMES):
             print(f"   {nm:40s} +{(ts[i] - ts[0]) / 1e3:7.2f} us")
+        for i, nm in ((13, "producer: loop entered"), (11, "producer: first tile coordinates done"), (12, "producer: first empty-slot wait passed")):
+            print(f"   {nm:40s} +{(ts[i] - ts[0]) / 1e3:7.2f} us")
         ep = (C.c_longlong * 128)()
         lib.cpd_debug_gemm_epilogue(ep)
         names = ["chunk top", "buffer free", "tmem ld done", "bias added", "st.shared done", "proxy fence", "group barrier", "store issued"]

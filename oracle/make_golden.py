@@ -185,6 +185,19 @@ def _run_cases(ref_shim, unet, out, c, uc, x_T, hw, steps, cases):
     return out
 
 
+def reference_vae(ref_shim):
+    """tests/golden/ref_vae.npz: the shimmed reference first-stage decoder (tiny config, seeded weights) on a seeded latent."""
+    from oracle.vae import VAEConfig, make_weights
+
+    cfg = VAEConfig.tiny()
+    sd = make_weights(cfg, seed=0)
+    decode = ref_shim.build_reference_vae_decode(cfg, sd)
+    z = torch.randn(2, 4, 16, 16, generator=torch.Generator().manual_seed(5))
+    img = decode(z)
+    print("vae decode", tuple(img.shape), "std", float(img.std()))
+    return {"z": z.numpy(), "image": img.numpy()}
+
+
 def main():
     sys.path.insert(0, os.path.dirname(HERE))
     from oracle import ref_shim
@@ -193,12 +206,14 @@ def main():
     import cpd.scheduler.k as K
 
     os.makedirs(GOLD, exist_ok=True)
-    if "--more-only" not in sys.argv:
+    if "--more-only" not in sys.argv and "--vae-only" not in sys.argv:
         with open(os.path.join(GOLD, "schedule_kat.json"), "w") as f:
             json.dump(schedule_kats(K), f, indent=1)
-    if "--more-only" not in sys.argv:
+    if "--more-only" not in sys.argv and "--vae-only" not in sys.argv:
         np.savez_compressed(os.path.join(GOLD, "ref_sampling.npz"), **reference_sampling(ref_shim))
-    np.savez_compressed(os.path.join(GOLD, "ref_sampling2.npz"), **reference_sampling_more(ref_shim))
+    if "--vae-only" not in sys.argv:
+        np.savez_compressed(os.path.join(GOLD, "ref_sampling2.npz"), **reference_sampling_more(ref_shim))
+    np.savez_compressed(os.path.join(GOLD, "ref_vae.npz"), **reference_vae(ref_shim))
     print("golden fixtures written to", GOLD)
 
 

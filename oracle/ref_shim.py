@@ -51,6 +51,10 @@ def install():
     torch.cuda.memory_stats = lambda *a, **k: {"active_bytes.all.current": 0, "reserved_bytes.all.current": 1 << 50}
     torch.cuda.mem_get_info = lambda *a, **k: (1 << 50, 1 << 50)
     torch.cuda.current_device = lambda: 0
+    # cpd/models/autoencoder.py:9 imports taming's VectorQuantizer (absent here; only VQModel uses it, not the KL decoder)
+    for name in ("taming", "taming.modules", "taming.modules.vqvae"):
+        _stub(name)
+    _stub("taming.modules.vqvae.quantize", VectorQuantizer2=object)
     import cpd.samplers  # noqa: F401  (first, to dodge the scheduler<->samplers import cycle)
     # D4: unet.py:592-596,649-653,703-707 pass use_linear=/use_checkpoint= which
     # SpatialTransformer.__init__ (attention.py:500-502) does not accept -> drop them.
@@ -74,3 +78,22 @@ def build_reference_unet(cfg):
                         num_heads=cfg.num_heads, num_head_channels=cfg.num_head_channels,
                         use_spatial_transformer=True, transformer_depth=cfg.transformer_depth,
                         context_dim=cfg.context_dim, use_checkpoint=False, legacy=False)
+
+
+def build_reference_vae_decode(cfg, sd):
+    """AutoencoderKL.decode (cpd/models/autoencoder.py:825-828) from its two parts - post_quant_conv (:800) and Decoder (:380) -
+    without the loss / encoder the full class would instantiate.  Returns a callable z -> image."""
+    import torch
+    import cpd.models.autoencoder as AE
+
+    dec = AE.Decoder(ch=cfg.ch, out_ch=cfg.out_ch, ch_mult=tuple(cfg.ch_mult), num_res_blocks=cfg.num_res_blocks,
+                     attn_resolutions=[], in_channels=3, resolution=256, z_channels=cfg.z_channels)
+    pqc = torch.nn.Conv2d(cfg.embed_dim, cfg.z_channels, 1)
+    dec.load_state_dict({k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")}, strict=True)
+    pqc.load_state_dict({"weight": sd["post_quant_conv.weight"], "bias": sd["post_quant_conv.bias"]})
+    dec.eval()
+
+    @torch.no_grad()
+    def decode(z):
+        return dec(pqc(z))
+    return decode

@@ -203,3 +203,15 @@ def test_oracle_more_samplers_bit_exact_on_replayed_unet(golden_dir, name, sched
     assert unet.i == len(unet.outs), "the restatement made a different number of UNet evaluations than the reference"
     assert torch.equal(torch.stack(dens), torch.from_numpy(z2[key + "|denoised"]))
     assert torch.equal(out, torch.from_numpy(z2[key + "|final"]))
+
+
+def test_oracle_vae_decoder_matches_reference(golden_dir):
+    """the first-stage decoder restatement (oracle/vae.py) against the shimmed reference Decoder +
+    post_quant_conv on the same seeded weights and latent (tests/golden/ref_vae.npz)."""
+    from oracle.vae import VAEConfig, OracleVAEDecoder, make_weights as vae_weights
+    z = np.load(os.path.join(golden_dir, "ref_vae.npz"))
+    cfg = VAEConfig.tiny()
+    out = OracleVAEDecoder(cfg, vae_weights(cfg, seed=0))(torch.from_numpy(z["z"]))
+    ref = torch.from_numpy(z["image"])
+    rel = ((out - ref).norm() / ref.norm()).item()
+    assert out.shape == ref.shape and rel < 1e-5, rel

@@ -79,6 +79,9 @@ _SIGS = {
                                C.c_int, C.c_int, C.c_void_p]),
     "cpd_upsample2x": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "cpd_attention": (C.c_int, [C.POINTER(AttnParams), C.c_void_p]),
+    "cpd_softmax_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_float, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
+    "cpd_pointwise_small": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
+                                      C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)

@@ -214,6 +214,96 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const bf16* __restrict_
   }
 }
 
+
+// Row softmax over a 16-bit matrix (VAE mid-block attention, autoencoder.py:252-255): out[r][c] = softmax_c(scale * x[r][c]),
+// fp32 arithmetic, one block per row, the row cached in registers (cols <= 256 threads x 8 vectors x 8 elements).
+template <int MAXV>
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const bf16* __restrict__ x, int cols, int64_t ld, float scale_log2,
+                                                           int f16, bf16* __restrict__ out, int64_t ldo) {
+  __shared__ float red[8];
+  pdl_launch_dependents();
+  pdl_wait();
+  const bf16* xr = x + (int64_t)blockIdx.x * ld;
+  bf16* orow = out + (int64_t)blockIdx.x * ldo;
+  const int nvec = cols / 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint4 raw[MAXV];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = threadIdx.x + i * 256;
+    raw[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (v < nvec) {
+      raw[i] = __ldg(reinterpret_cast<const uint4*>(xr + v * 8));
+      const uint32_t u[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_act2(u[e], f16 != 0);
+        mx = fmaxf(mx, fmaxf(f.x, f.y));
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  // scale > 0: max(scale * x) = scale * max(x); p = 2^((x - max) * scale * log2 e)
+  float sum = 0.f;
+  float p[MAXV][8];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = threadIdx.x + i * 256;
+    const uint32_t u[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = unpack_act2(u[e], f16 != 0);
+      p[i][2 * e] = v < nvec ? exp2f((f.x - mx) * scale_log2) : 0.f;
+      p[i][2 * e + 1] = v < nvec ? exp2f((f.y - mx) * scale_log2) : 0.f;
+      sum += p[i][2 * e] + p[i][2 * e + 1];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum += red[i];  // fixed order: bit-reproducible
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = threadIdx.x + i * 256;
+    if (v < nvec)
+      *reinterpret_cast<uint4*>(orow + v * 8) =
+          make_uint4(pack_act2(p[i][0] * inv, p[i][1] * inv, f16 != 0), pack_act2(p[i][2] * inv, p[i][3] * inv, f16 != 0),
+                     pack_act2(p[i][4] * inv, p[i][5] * inv, f16 != 0), pack_act2(p[i][6] * inv, p[i][7] * inv, f16 != 0));
+  }
+}
+
+// 1x1 conv over an fp32 NCHW tensor with a handful of channels (post_quant_conv, autoencoder.py:800,826):
+// out[n][o][p] = b[o] + sum_c w[o][c] * (x[n][c][p] * scale); cin, cout <= 8.
+__global__ void __launch_bounds__(256) pointwise_small_kernel(const float* __restrict__ x, int n, int cin, int cout, int64_t hw,
+                                                              const float* __restrict__ w, const float* __restrict__ b, float scale,
+                                                              float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t total = (int64_t)n * hw;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t nn = idx / hw, p = idx - nn * hw;
+    float xv[8];
+    for (int c = 0; c < cin; ++c) xv[c] = __fmul_rn(x[(nn * cin + c) * hw + p], scale);
+    for (int o = 0; o < cout; ++o) {
+      float acc = b ? b[o] : 0.f;
+      for (int c = 0; c < cin; ++c) acc = fmaf(w[o * cin + c], xv[c], acc);
+      out[(nn * cout + o) * hw + p] = acc;
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" cpd_status cpd_timestep_embedding(const float* t, int rows, int dim, int round_t_bf16, void* out, void* stream) {
@@ -258,7 +348,14 @@ extern "C" cpd_status cpd_conv_in(const float* x, int n, int cin, int h, int w, 
   CPD_REQUIRE(rows_per_image >= 1, "cpd_conv_in: rows_per_image=%d", rows_per_image);
   const int64_t total = (int64_t)n * h * w * (cout / 8);
   const size_t shm = (size_t)9 * cin * cout * sizeof(float);
-  CPD_REQUIRE(shm <= 48 * 1024, "cpd_conv_in: cin=%d x cout=%d weights do not fit 48 KB of shared memory", cin, cout);
+  CPD_REQUIRE(shm <= 100 * 1024, "cpd_conv_in: cin=%d x cout=%d weights do not fit 100 KB of shared memory", cin, cout);
+  {
+    static bool cfg = false;
+    if (!cfg) {
+      CPD_CUDA_CHECK(cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      cfg = true;
+    }
+  }
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 2) blocks = 148 * 2;  // each block stages the 9 x cin x cout weights once: few, long-lived blocks
   CPD_CUDA_CHECK(cpd_launch(conv_in_kernel, dim3((unsigned)blocks), dim3(256), shm, (cudaStream_t)stream, x, n, cin, h, w, (const bf16*)wt, bias, cout, scale, scale_ptr,
@@ -297,6 +394,35 @@ extern "C" cpd_status cpd_upsample2x(const void* a, int n, int h, int w, int c, 
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   CPD_CUDA_CHECK(cpd_launch(upsample2x_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (const bf16*)a, n, h, w, c, (bf16*)out));
+  CPD_CUDA_CHECK(cudaGetLastError());
+  return CPD_OK;
+}
+
+extern "C" cpd_status cpd_softmax_rows(const void* x, int rows, int cols, int64_t ld, float scale, int act_fp16, void* out, int64_t ldo,
+                                       void* stream) {
+  CPD_REQUIRE(x && out, "cpd_softmax_rows: null pointer");
+  CPD_REQUIRE(rows >= 0 && cols > 0 && cols % 8 == 0 && cols <= 256 * 8 * 8, "cpd_softmax_rows: cols=%d must be a multiple of 8, <= 16384", cols);
+  CPD_REQUIRE(ld % 8 == 0 && ldo % 8 == 0 && ld >= cols && ldo >= cols, "cpd_softmax_rows: bad leading dimensions");
+  CPD_REQUIRE(scale > 0.f, "cpd_softmax_rows: scale must be positive");
+  if (rows == 0) return CPD_OK;
+  const float sl2 = scale * 1.4426950408889634f;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cols <= 256 * 8 * 2)
+    CPD_CUDA_CHECK(cpd_launch(softmax_rows_kernel<2>, dim3(rows), dim3(256), 0, s, (const bf16*)x, cols, ld, sl2, act_fp16, (bf16*)out, ldo));
+  else
+    CPD_CUDA_CHECK(cpd_launch(softmax_rows_kernel<8>, dim3(rows), dim3(256), 0, s, (const bf16*)x, cols, ld, sl2, act_fp16, (bf16*)out, ldo));
+  CPD_CUDA_CHECK(cudaGetLastError());
+  return CPD_OK;
+}
+
+extern "C" cpd_status cpd_pointwise_small(const float* x, int n, int cin, int cout, int64_t hw, const float* w, const float* b, float scale,
+                                          float* out, void* stream) {
+  CPD_REQUIRE(x && w && out, "cpd_pointwise_small: null pointer");
+  CPD_REQUIRE(n >= 0 && cin >= 1 && cin <= 8 && cout >= 1 && cout <= 8 && hw > 0, "cpd_pointwise_small: n=%d cin=%d cout=%d", n, cin, cout);
+  if (n == 0) return CPD_OK;
+  int64_t blocks = ((int64_t)n * hw + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  CPD_CUDA_CHECK(cpd_launch(pointwise_small_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, x, n, cin, cout, hw, w, b, scale, out));
   CPD_CUDA_CHECK(cudaGetLastError());
   return CPD_OK;
 }

@@ -335,3 +335,25 @@ def attention(q, k, vt, o, *, ldq, ldk, ldvt, ldo, batch, heads, nq, nk, nk_pad,
         check(load().cpd_attention(C.byref(p), stream_ptr()), "cpd_attention")
     _count()
     return o
+
+
+def softmax_rows(x, out, *, rows, cols, scale, ld=None, ldo=None):
+    """out[r][c] = softmax_c(scale * x[r][c]) over a 16-bit row-major matrix (VAE AttnBlock weights); out may alias x."""
+    f16 = _act(x, "x")
+    _act(out, "out", like=x.dtype)
+    with _Prof("softmax_rows", 0.0, f"rows={rows} cols={cols}"):
+        check(load().cpd_softmax_rows(ptr(x), rows, cols, int(ld if ld is not None else cols), float(scale), f16, ptr(out),
+                                      int(ldo if ldo is not None else cols), stream_ptr()), "cpd_softmax_rows")
+    _count()
+    return out
+
+
+def pointwise_small(x, w, b, out, *, n, cin, cout, hw, scale=1.0):
+    """1x1 conv of an fp32 NCHW tensor with <= 8 channels (post_quant_conv), input multiplied by `scale` first."""
+    for name, t in (("x", x), ("w", w), ("b", b), ("out", out)):
+        _req(t, torch.float32, name)
+    with _Prof("small", 0.0):
+        check(load().cpd_pointwise_small(ptr(x), n, cin, cout, int(hw), ptr(w), ptr(b), float(scale), ptr(out), stream_ptr()),
+              "cpd_pointwise_small")
+    _count()
+    return out

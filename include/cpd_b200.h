@@ -236,6 +236,20 @@ typedef struct {
 
 cpd_status cpd_attention(const cpd_attn_params* p, void* stream);
 
+/* ---- first-stage decoder (VAE decode, cpd/models/autoencoder.py:380-509,825-828: SURVEY.md 8-f row 3) ------------------
+ * The decoder reuses cpd_gemm_conv / cpd_groupnorm / cpd_upsample2x / cpd_conv_in / cpd_conv_out; two small ops are its own: */
+
+/* Row softmax of a 16-bit row-major matrix: out[r][c] = softmax_c(scale * x[r][c]) (fp32 arithmetic), the attention weights
+ * of AttnBlock (autoencoder.py:250-255; one head of width C, so Q K^T and P V are plain cpd_gemm_conv GEMMs).
+ * cols: multiple of 8, <= 16384; ld / ldo in elements; scale > 0; out may alias x. */
+cpd_status cpd_softmax_rows(const void* x, int rows, int cols, int64_t ld, float scale, int act_fp16, void* out, int64_t ldo,
+                            void* stream);
+
+/* 1x1 convolution of an fp32 NCHW tensor with <= 8 channels (post_quant_conv, autoencoder.py:800,826), with the
+ * 1 / scale_factor of decode_first_stage folded in: out[n][o][p] = b[o] + sum_c w[o][c] * (x[n][c][p] * scale). */
+cpd_status cpd_pointwise_small(const float* x, int n, int cin, int cout, int64_t hw, const float* w, const float* b, float scale,
+                               float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

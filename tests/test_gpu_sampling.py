@@ -586,3 +586,59 @@ def test_config5_frame_sequence_chain_vs_oracle(cpd):
             r = rel(got[i], ref)
             print(f"config 5: frame {i} latent rel-L2 {r:.3e}")
             assert r < 2e-2
+
+
+# ----------------------------------------------------------------- first-stage decoder (VAE decode)
+def _vae_pair(cfg_name, act_dtype=torch.float16):
+    from complex_prompt_diffusion_b200.models.vae import VAEDecoder
+    from oracle.vae import VAEConfig, OracleVAEDecoder, make_weights
+    cfg = getattr(VAEConfig, cfg_name)()
+    sd = make_weights(cfg, seed=0)
+    oracle = OracleVAEDecoder(cfg, {k: v.to(torch.bfloat16).float() for k, v in sd.items()})  # bf16-rounded weights, fp32 arithmetic
+    gpu = VAEDecoder(sd, device=DEV, act_dtype=act_dtype, ch=cfg.ch, out_ch=cfg.out_ch, ch_mult=tuple(cfg.ch_mult),
+                     num_res_blocks=cfg.num_res_blocks, z_channels=cfg.z_channels, embed_dim=cfg.embed_dim)
+    return cfg, oracle, gpu
+
+
+@pytest.mark.parametrize("B,hw", [(2, 16), (1, 32)])
+def test_vae_decode_vs_oracle(cpd, B, hw):
+    """AutoencoderKL.decode (autoencoder.py:825-828) on the GPU vs the oracle restatement (itself pinned against the shimmed
+    reference Decoder, tests/golden/ref_vae.npz): tiny config, bf16-rounded weights on both sides."""
+    cfg, oracle, gpu = _vae_pair("tiny")
+    z = torch.randn(B, 4, hw, hw, generator=torch.Generator().manual_seed(hw))
+    oracle.taps = {}
+    ref = oracle(z)
+    out = gpu.decode(z.to(DEV))
+    torch.cuda.synchronize()
+    r = rel(out, ref)
+    print(f"vae decode tiny B{B} {hw}x{hw} -> {tuple(out.shape)}: rel-L2 {r:.3e}")
+    assert out.shape == ref.shape and torch.isfinite(out).all()
+    assert r < 1e-2
+    # the 1 / scale_factor of decode_first_stage folded into the first kernel
+    out2 = gpu.decode((z * 0.18215).to(DEV), unscale=True)
+    torch.cuda.synchronize()
+    assert rel(out2, ref) < 1e-2
+
+
+def test_vae_decode_golden_reference_image(cpd, golden_dir):
+    """The same decoder against the image the shimmed REFERENCE produced (fp32 weights there, bf16-rounded here)."""
+    cfg, _, gpu = _vae_pair("tiny")
+    g = np.load(os.path.join(golden_dir, "ref_vae.npz"))
+    out = gpu.decode(torch.from_numpy(g["z"]).to(DEV))
+    torch.cuda.synchronize()
+    r = rel(out, torch.from_numpy(g["image"]))
+    print(f"vae decode vs reference golden: rel-L2 {r:.3e}")
+    assert r < 1.5e-2
+
+
+def test_softmax_rows(cpd):
+    from complex_prompt_diffusion_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    for rows, cols in ((64, 256), (33, 4096), (5, 8192)):
+        x = (torch.randn(rows, cols, generator=g) * 30).to(torch.float16).to(DEV)
+        out = torch.empty_like(x)
+        ops.softmax_rows(x, out, rows=rows, cols=cols, scale=cols ** -0.5)
+        torch.cuda.synchronize()
+        ref = torch.softmax(x.float() * cols ** -0.5, dim=-1)
+        assert rel(out, ref) < 2e-3
+        assert torch.allclose(out.float().sum(-1), torch.ones(rows, device=DEV), atol=5e-3)

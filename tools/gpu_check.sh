@@ -14,7 +14,7 @@ for g in "${groups[@]}"; do
     attn) sel="tests/test_gpu_ops.py -k 'attention'";;
     misc) sel="tests/test_gpu_ops.py -k 'groupnorm or layernorm or timestep or conv_in_out'";;
     unet) sel="tests/test_gpu_sampling.py -k 'unet_forward'";;
-    e2e)  sel="tests/test_gpu_sampling.py -k 'end_to_end or config'";;
+    e2e)  sel="tests/test_gpu_sampling.py -k 'end_to_end or config or vae or softmax_rows'";;
     *) sel="$g";;
   esac
   echo "=== group $g"

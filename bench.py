@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--sampler-steps", type=int, default=WORKLOAD["sampler_steps"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-decode", action="store_true", help="skip the extra latents -> images (VAE decode) measurement")
     return ap.parse_args()
 
 
@@ -265,6 +266,26 @@ def run_b200(args):
             ms = float(t)
         return ms
 
+    # Optional tail of the pipeline: latents -> images through the first-stage decoder, reported as an
+    # extra key; the headline metric stays the denoising loop BASELINE.json names.
+    vae = None
+    if not args.no_decode and not os.environ.get("CPD_BENCH_NCU"):
+        from complex_prompt_diffusion_b200.models.vae import VAEDecoder
+        from oracle.vae import VAEConfig, make_weights as vae_weights  # weight fixture only
+        vcfg = VAEConfig.sd()
+        vae = VAEDecoder(vae_weights(vcfg, seed=0), device=dev, ch=vcfg.ch, ch_mult=tuple(vcfg.ch_mult), num_res_blocks=vcfg.num_res_blocks)
+        img_h = torch.empty(B, 3, args.latent * 8, args.latent * 8).pin_memory()
+
+    def step_e2e_images():
+        xd = x_T_h.to(dev, non_blocking=True)
+        ucd = uc_h.to(dev, non_blocking=True)
+        cd = {k: [(s, e.to(dev, non_blocking=True), g_, m) for (s, e, g_, m) in v] for k, v in c_h.items()}
+        lat = wrapper.sampler.sample(steps=S, batch_size=B, shape=[4, args.latent, args.latent], x_T=xd, conditioning=cd,
+                                     unconditional_conditioning=ucd, **dict(kw))
+        img_h.copy_(vae.decode(lat, unscale=True), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return img_h
+
     for _ in range(args.warmup):
         step_resident()
     if os.environ.get("CPD_BENCH_NCU"):
@@ -286,6 +307,11 @@ def run_b200(args):
     for _ in range(min(args.warmup, 2)):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    ms_img = None
+    if vae is not None:
+        for _ in range(2):
+            step_e2e_images()
+        ms_img = timed(step_e2e_images, args.steps)
 
     imgs = B * world * args.steps
     ips = imgs / (ms / 1e3)
@@ -358,6 +384,10 @@ def run_b200(args):
                         "h2d_bytes_per_step": int(x_T_h.numel() * 4 + uc_h.numel() * 4 + sum(e.numel() * 4 for v in c_h.values() for (_, e, _, _) in v)),
                         "d2h_bytes_per_step": int(out_h.numel() * 4)},
                 "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_sampler_step": roof_sampler, "cpu_baseline": cpu}
+        if ms_img is not None:
+            line["e2e_decoded_images"] = {"value": imgs / (ms_img / 1e3), "unit": "images/s",
+                                          "what": "e2e plus the first-stage decoder (latents -> 512 px images, fp32 images read back D2H)",
+                                          "d2h_bytes_per_step": int(img_h.numel() * 4)}
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist

@@ -351,7 +351,7 @@ def run_b200(args):
         achieved = g_fl / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "gemm_conv_kernel (tcgen05 implicit-GEMM conv / GEMM)", "achieved": achieved,
                 "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
-                "traffic": NCU_TRAFFIC,
+                "traffic": NCU_TRAFFIC["bytes_per_launch"], "traffic_detail": NCU_TRAFFIC,
                 "peak_source": pk["source"] + " (sustained bf16)", "launches_per_step": g_n,
                 "avg_launch_us": g_ms * 1e3 / max(g_n, 1), "share_of_step": g_ms / (ms / args.steps),
                 "breakdown_ms_per_step": {k: round(v, 3) for k, v in breakdown.items()},

@@ -140,7 +140,6 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
     k0 = (int)(sp * (unsigned)args.num_k / (unsigned)splits);
     k1 = (int)((sp + 1u) * (unsigned)args.num_k / (unsigned)splits);
   };
-  const int num_k = args.num_k;
   const int cbt = g.cb0 + g.cb1;
   const bool two_acc = args.bn * args.nsub <= ACC_COLS;  // room for two accumulator stages in the 512 TMEM columns
 
@@ -343,7 +342,6 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
     const int nch = out_w / CHUNK_COLS;
     const int c_lo = grp * (nch / EPI_GROUPS) + min(grp, nch % EPI_GROUPS);  // contiguous, sizes differ by at most one
     const int c_hi = c_lo + nch / EPI_GROUPS + (grp < nch % EPI_GROUPS ? 1 : 0);
-    const int box_rows = g.tw * g.th * g.nb;
     uint8_t* my_staging = staging + grp * STAGING_BUFS * CHUNK_BYTES;
     uint64_t* my_res_bar = res_bar + grp * STAGING_BUFS;
     const bool has_res = args.residual != nullptr && splits == 1;

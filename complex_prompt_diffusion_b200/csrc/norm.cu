@@ -622,7 +622,6 @@ extern "C" cpd_status cpd_groupnorm(const void* a0, const void* a1, int c0, int 
         const int threads = lanes * vps;
         const size_t shm = sizeof(float) * ((size_t)2 * slab_c * lanes + 2 * slab_c + 2 * GROUPS);
         if (shm <= 200 * 1024) {
-          static bool cfg_f = false;
           const dim3 grid(C / slab_c, n_img);
 #define CPD_GN_FUSED_LAUNCH(F, VV)                                                                                        \
   do {                                                                                                                    \
@@ -634,7 +633,6 @@ extern "C" cpd_status cpd_groupnorm(const void* a0, const void* a1, int c0, int 
     CPD_CUDA_CHECK(cpd_launch(gn_fused_kernel<F, VV>, grid, dim3(threads), shm, s, (const bf16*)a0, (const bf16*)a1, c0, c1, hw, \
                               slab_c, gamma, beta, eps, silu, (bf16*)out));                                               \
   } while (0)
-          (void)cfg_f;
           if (act_fp16) {
             if (V == 2) CPD_GN_FUSED_LAUNCH(true, 2); else if (V == 4) CPD_GN_FUSED_LAUNCH(true, 4);
             else if (V == 8) CPD_GN_FUSED_LAUNCH(true, 8); else CPD_GN_FUSED_LAUNCH(true, 10);

@@ -56,9 +56,8 @@ struct EpsRow {
 
 template <int VEC>
 __device__ __forceinline__ void load_f32(const float* p, float (&out)[VEC]) {
-  if (VEC < 4) return;
 #pragma unroll
-  for (int q = 0; q < VEC / 4; ++q) {
+  for (int q = 0; q < (VEC >= 4 ? VEC / 4 : 0); ++q) {
     const float4 v = *(reinterpret_cast<const float4*>(p) + q);
     out[4 * q] = v.x; out[4 * q + 1] = v.y; out[4 * q + 2] = v.z; out[4 * q + 3] = v.w;
   }

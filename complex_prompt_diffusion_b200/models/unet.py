@@ -260,8 +260,11 @@ class UNetModel:
     # ---- text context: step-invariant K / V^T of every cross-attention layer ---------------------------
     def set_context(self, context):
         """context: [Rc, tokens, D]; query row b uses context row (b % Rc)."""
-        key = (context.data_ptr(), tuple(context.shape), context._version)
-        if self._ctx_key == key:
+        # The cache is keyed on the tensor OBJECT (kept alive here, so its storage cannot be recycled for another prompt)
+        # and its version counter - never on data_ptr(): the caching allocator hands the address of a freed context to
+        # the next one of the same shape.
+        key = (context, context._version)
+        if self._ctx_key is not None and self._ctx_key[0] is context and self._ctx_key[1] == context._version:
             return
         # the reference casts the context to the model dtype first (denoiser.py:373-385), then it is an activation
         ctx = context.to(self.device, torch.bfloat16).to(self.act_dtype)
@@ -297,8 +300,8 @@ class UNetModel:
             return
         if y is None:
             raise ValueError(f"this UNet needs vector conditioning y [rows, {self.adm}]")
-        key = (y.data_ptr(), tuple(y.shape), y._version)
-        if self._y_key == key:
+        key = (y, y._version)  # object identity + version (see set_context)
+        if self._y_key is not None and self._y_key[0] is y and self._y_key[1] == y._version:
             return
         if y.ndim != 2 or y.shape[1] != self.adm:
             raise ValueError(f"y must be [rows, {self.adm}], got {tuple(y.shape)}")

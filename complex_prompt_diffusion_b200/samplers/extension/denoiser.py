@@ -112,13 +112,32 @@ class Denoiser(torch.nn.Module):
         if kwargs.get("pred_type", "epsilon") not in ("epsilon", "velocity"):
             raise ValueError(f"unknown pred_type {kwargs.get('pred_type')!r}")
 
-    def plan_conditioning(self, c, uc, hw_shape, y=None):
+    @staticmethod
+    def _versions(c, uc, y):
+        """Version counters of every tensor the plan is built from (in-place edits of an embedding invalidate the plan)."""
+        out = []
+        entries = list(c.get("and", [])) + list(c.get("not", []))
+        items = [uc, y]
+        for (scale, emb, _guide, mask) in entries:
+            items += [scale, emb, mask]
+        for t in items:
+            out.append(t._version if isinstance(t, torch.Tensor) else (float(t) if isinstance(t, (int, float)) else None))
+        return out
+
+    def plan_conditioning(self, c, uc, hw_shape, y=None, force=False):
         """`y` (extension for UNets with vector conditioning, i.e. SDXL - not expressible by the reference): tensor
-        [1 + N, adm] with one row per UNet row (row 0 = unconditional) or [1, adm] shared by all rows."""
+        [1 + N, adm] with one row per UNet row (row 0 = unconditional) or [1, adm] shared by all rows.
+        The plan is rebuilt at the start of every sample() call (`force`) and, between direct Denoiser calls, whenever the
+        conditioning OBJECTS or their tensor versions change.  The objects are kept alive by the cache: `id()` / `data_ptr()`
+        of a freed object are recycled by Python / the caching allocator and must never key a cache."""
         if isinstance(c, list):
             raise NotImplementedError("per-step conditioning lists are not supported")
-        key = (id(c), id(uc), tuple(hw_shape), id(y))
-        if self._plan_key != key:
+        if not isinstance(c, dict) or "and" not in c:
+            raise ValueError("conditioning must be a dict with an 'and' list (CompositionalPrompt._build_embeddings)")
+        key = (c, uc, y, tuple(hw_shape), self._versions(c, uc, y))
+        k0 = self._plan_key
+        same = (not force and k0 is not None and k0[0] is c and k0[1] is uc and k0[2] is y and k0[3] == key[3] and k0[4] == key[4])
+        if not same:
             self._plan = ConditioningPlan(c, uc, self.dtype, self.device, hw_shape)
             self._plan_key = key
             rows = None if self._part is None else self._part.rows

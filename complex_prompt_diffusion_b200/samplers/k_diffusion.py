@@ -60,7 +60,7 @@ class KDiffusionSampler:
         den = self.denoiser
         den._check_kwargs(model_args)
         plan = den.plan_conditioning(model_args.get("conditioning"), model_args.get("unconditional_conditioning"), x.shape[-2:],
-                                     y=model_args.get("y"))
+                                     y=model_args.get("y"), force=True)  # once per sample() call: never a stale prompt
         return den, plan
 
     def _clip_sample(self, x, kwargs):

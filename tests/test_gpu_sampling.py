@@ -642,3 +642,68 @@ def test_softmax_rows(cpd):
         ref = torch.softmax(x.float() * cols ** -0.5, dim=-1)
         assert rel(out, ref) < 2e-3
         assert torch.allclose(out.float().sum(-1), torch.ones(rows, device=DEV), atol=5e-3)
+
+
+def test_unet_forward_non_square_latent(cpd):
+    """Non-square latents (the reference builds shape=[C, H//8, W//8], prompts.py:375): 16 x 32 and 32 x 16 through the conv
+    tiling, the attention token order and the up / down sampling."""
+    cfg, oracle, gpu = _unet_pair("tiny", torch.float32)
+    oracle.sd = {k: v.to(torch.bfloat16).float() for k, v in oracle.sd.items()}
+    g = torch.Generator().manual_seed(77)
+    for (h, w) in ((16, 32), (32, 16)):
+        x = torch.randn(2, 4, h, w, generator=g)
+        t = torch.tensor([700.0, 30.5]).to(torch.bfloat16).float()
+        ctx = torch.randn(2, 77, cfg.context_dim, generator=g)
+        ref = oracle(x, t, ctx.to(torch.bfloat16).float())
+        out = gpu(x.to(DEV), t.to(DEV), ctx.to(DEV))
+        torch.cuda.synchronize()
+        r = rel(out, ref)
+        print(f"unet tiny {h}x{w}: eps rel-L2 {r:.3e}")
+        assert out.shape == ref.shape and r < 1e-2
+
+
+def test_prompt_caches_never_serve_a_stale_prompt(cpd):
+    """Regression: the text-context K/V cache and the conditioning plan were keyed on data_ptr() / id(), which the caching
+    allocator / Python recycle once a tensor or dict is freed - a NEW prompt of the same shape could silently reuse the old
+    prompt's K/V.  Caches are keyed on object identity (kept alive) + version counters and rebuilt per sample() call."""
+    from complex_prompt_diffusion_b200 import samplers
+    cfg, oracle, gpu = _unet_pair("tiny", torch.float32)
+    oracle.sd = {k: v.to(torch.bfloat16).float() for k, v in oracle.sd.items()}
+    g = torch.Generator().manual_seed(123)
+    x = torch.randn(2, 4, 16, 16, generator=g)
+    t = torch.tensor([600.0, 50.0]).to(torch.bfloat16).float()
+    for i in range(4):  # each context is freed before the next one of the same shape is allocated (same address)
+        ctx = torch.randn(2, 77, cfg.context_dim, generator=g)
+        ctx_dev = ctx.to(DEV)
+        out = gpu(x.to(DEV), t.to(DEV), ctx_dev).clone()
+        torch.cuda.synchronize()
+        r = rel(out, oracle(x, t, ctx.to(torch.bfloat16).float()))
+        assert r < 1e-2, (i, r)
+        del ctx_dev, out
+    # in-place edit of the same tensor object must also be seen
+    ctx_dev = torch.randn(2, 77, cfg.context_dim, generator=g).to(DEV)
+    a = gpu(x.to(DEV), t.to(DEV), ctx_dev).clone()
+    ctx_dev.mul_(-1.0)
+    b = gpu(x.to(DEV), t.to(DEV), ctx_dev).clone()
+    torch.cuda.synchronize()
+    assert rel(b, oracle(x, t, ctx_dev.cpu().to(torch.bfloat16).float())) < 1e-2 and rel(a, b) > 1e-2
+    # sampler level: a new conditioning dict per call (old ones garbage collected)
+    wrapper = samplers.make({"name": "Euler", "args": {}}, {"model": {"unet": gpu}})
+    x_T = torch.randn(1, 4, 16, 16, generator=g)
+    outs = []
+    for i in range(3):
+        emb = torch.randn(1, 77, cfg.context_dim, generator=torch.Generator().manual_seed(900 + i))
+        uc = torch.randn(1, 77, cfg.context_dim, generator=torch.Generator().manual_seed(800))
+        c = {"and": [(1.0, emb, None, 1)], "not": []}
+        outs.append(wrapper.sampler.sample(steps=3, batch_size=1, shape=[4, 16, 16], x_T=x_T.clone(), rng_compat=False, conditioning=c,
+                                           unconditional_conditioning=uc, unconditional_guidance_scale=5.0, scheduler="karras").clone())
+        del c, emb, uc
+    torch.cuda.synchronize()
+    assert rel(outs[0], outs[1]) > 1e-3 and rel(outs[1], outs[2]) > 1e-3  # three different prompts, three different results
+    emb = torch.randn(1, 77, cfg.context_dim, generator=torch.Generator().manual_seed(901))
+    uc = torch.randn(1, 77, cfg.context_dim, generator=torch.Generator().manual_seed(800))
+    again = wrapper.sampler.sample(steps=3, batch_size=1, shape=[4, 16, 16], x_T=x_T.clone(), rng_compat=False,
+                                   conditioning={"and": [(1.0, emb, None, 1)], "not": []}, unconditional_conditioning=uc,
+                                   unconditional_guidance_scale=5.0, scheduler="karras")
+    torch.cuda.synchronize()
+    assert torch.equal(again, outs[1])

@@ -442,7 +442,17 @@ class UNetModel:
         ops.small_linear(emb, W["emb_all.w"], W["emb_all.b"], m=m, k=ted, n=self.emb_total, silu_in=True, out_f32=emb_all)
         return emb_all
 
-    def _forward_impl(self, x, scale, rows_per_image, t_rows, shared_t, return_skips=False, scale_dev=None):
+    def _nhwc(self, t, name, R, c, h, w):
+        """A caller-provided NCHW tensor [R, c, h, w] -> NHWC activation buffer (feature / skip injection, unet.py:806-813)."""
+        t = torch.as_tensor(t)
+        if tuple(t.shape) != (R, c, h, w):
+            raise ValueError(f"injected tensor has shape {tuple(t.shape)}, expected {(R, c, h, w)}")
+        buf = self._buf(name, R * h * w * c)
+        buf.view(R, h, w, c).copy_(t.to(self.device).permute(0, 2, 3, 1))
+        return buf
+
+    def _forward_impl(self, x, scale, rows_per_image, t_rows, shared_t, return_skips=False, scale_dev=None, inject=None,
+                      return_feats=False):
         W = self.w
         B, cin, h, w = x.shape
         R = B * rows_per_image
@@ -476,28 +486,38 @@ class UNetModel:
             hcur, ch, h, w = self._run_block(f"input_blocks.{i}.", layers, hcur, None, R, h, w, emb_all, emb_stride, stats)
             hs.append((hcur, ch, h, w))
         hcur, ch, h, w = self._run_block("middle_block.", self.middle, hcur, None, R, h, w, emb_all, emb_stride, stats)
-        skips = []
+        skips, feats = [], []
+        inject = inject or {}
         for i, layers in enumerate(self.outputs):
             s, sc, sh, sw = hs.pop()
             assert (sh, sw) == (h, w)
             if return_skips:
                 skips.append(s.view(R, sh, sw, sc).permute(0, 3, 1, 2))
+            if inject.get("attns") is not None and inject.get("attns_stop", 10) > i:  # unet.py:806-809: replace the skip tensor
+                s = self._nhwc(inject["attns"][i], f"inject.skip.{i}", R, sc, sh, sw)
+            if inject.get("feats") is not None and inject.get("feats_stop", 10) > i:  # unet.py:810-813: replace h
+                hcur = self._nhwc(inject["feats"][i], f"inject.h.{i}", R, ch, h, w)
             hcur, ch, h, w = self._run_block(f"output_blocks.{i}.", layers, hcur, (s, sc), R, h, w, emb_all, emb_stride, stats)
+            if return_feats:  # unet.py:816-817
+                feats.append(hcur.view(R, h, w, ch).permute(0, 3, 1, 2).float().clone())
         gn = self._buf("gn", R * h * w * ch)
         ops.groupnorm(hcur, W["out.gn.g"], W["out.gn.b"], gn, stats, n_img=R, hw=h * w, c0=ch, eps=1e-5, silu=True)
         cout = self.cfg["out_channels"]
         out = self._buf("eps", R * cout * h * w, self.eps_dtype).view(R, cout, h, w)
         ops.conv_out(gn, W["out.w"], W["out.b"], out, n=R, h=h, w=w, cin=ch, cout=cout)
+        if return_feats:
+            return (out, skips, feats) if return_skips else (out, feats)
         return (out, skips) if return_skips else out
 
     @torch.no_grad()
-    def forward_rows(self, x, c_in, t, rows_per_image):
+    def forward_rows(self, x, c_in, t, rows_per_image, inject=None):
         """Fast path used by the Denoiser: x [B,4,h,w] fp32 (unscaled), every image is evaluated on
         `rows_per_image` conditioning rows sharing x * c_in and the timestep t (denoiser.py:383-393).
         Returns eps rows [B*rows_per_image, 4, h, w] (eps_dtype), image-major."""
-        if not self.use_cuda_graph or ops.PROFILE is not None:
+        if not self.use_cuda_graph or ops.PROFILE is not None or inject:
+            # eager: profiling, or feature / skip injection (caller tensors change per call: not part of the captured graph)
             t_rows = torch.full((1,), float(t), dtype=torch.float32, device=self.device)
-            return self._forward_impl(x.contiguous(), float(c_in), rows_per_image, t_rows, shared_t=True)
+            return self._forward_impl(x.contiguous(), float(c_in), rows_per_image, t_rows, shared_t=True, inject=inject)
         # One CUDA graph per (shape, rows, context layout): the ~850 kernel launches of an evaluation are replayed with a
         # single cudaGraphLaunch; the per-step scalars (c_in, t) and x live in static device buffers.
         ctx = self._ctx
@@ -531,9 +551,10 @@ class UNetModel:
         Returns out [N,4,h,w] (bf16) or (out, skips) when return_attn=True (the 12 skip tensors, unet.py:802-804)."""
         if y is not None or self.adm:
             self.set_vector(y)
-        for k in ("inject_feats", "inject_attns", "return_feat"):
-            if kwargs.get(k):
-                raise NotImplementedError(f"UNetModel kwarg {k!r} is outside the hot-path scope")
+        inject = None
+        if kwargs.get("inject_feats") is not None or kwargs.get("inject_attns") is not None:
+            inject = dict(feats=kwargs.get("inject_feats"), feats_stop=kwargs.get("inject_feats_stop", 10),
+                          attns=kwargs.get("inject_attns"), attns_stop=kwargs.get("inject_attns_stop", 10))
         if context is not None:
             self.set_context(context)
         n = x.shape[0]
@@ -543,6 +564,7 @@ class UNetModel:
             raise ValueError("timesteps must have one entry per row of x")
         if n > 32:
             raise NotImplementedError("more than 32 rows with distinct timesteps: use forward_rows")
-        return self._forward_impl(x, 1.0, 1, t_rows, shared_t=False, return_skips=bool(kwargs.get("return_attn", False)))
+        return self._forward_impl(x, 1.0, 1, t_rows, shared_t=False, return_skips=bool(kwargs.get("return_attn", False)),
+                                  inject=inject, return_feats=bool(kwargs.get("return_feat", False)))
 
     __call__ = forward

@@ -22,8 +22,7 @@ from ..._lib import (CPD_DENOISE_ONLY, CPD_DPMPP_2M, CPD_EULER, CPD_EULER_ANCEST
                      CPD_THRESH_DYNAMIC, CPD_THRESH_STATIC)
 from ...scheduler.discrete import SigmaScheduler
 
-_UNSUPPORTED_TRUTHY = ("attn_guide", "return_attn", "clip_guidance", "score_corrector", "unconditional_guidance_blur",
-                       "inject_feats", "inject_attns", "depth_mask")
+_UNSUPPORTED_TRUTHY = ("attn_guide", "return_attn", "clip_guidance", "score_corrector", "unconditional_guidance_blur", "depth_mask")
 
 # thresholding extensions that run on the device (samplers/extension/threshold.py:47-88); the other registered variants
 # (dynanormic / scaled / mean-centred ...) still raise
@@ -172,14 +171,27 @@ class Denoiser(torch.nn.Module):
         return float(s)
 
     # ---- device-side --------------------------------------------------------------------------------
-    def unet_rows(self, x, sigma, plan):
+    @staticmethod
+    def _inject(kwargs):
+        """Feature / skip injection kwargs of denoiser.py:353-356, handed to the UNet like :397-402 (lists of tensors with
+        one [R, c, h, w] entry per output block, applied to blocks below the *_stop index)."""
+        if kwargs.get("inject_feats") is None and kwargs.get("inject_attns") is None:
+            return None
+        return dict(feats=kwargs.get("inject_feats"), feats_stop=kwargs.get("inject_feats_stop", 10),
+                    attns=kwargs.get("inject_attns"), attns_stop=kwargs.get("inject_attns_stop", 10))
+
+    def unet_rows(self, x, sigma, plan, inject=None):
         """Run the UNet on the (1 + N) conditioning rows of every image: returns eps rows [B*(1+N), 4, h, w]
         (image-major).  x: [B,4,h,w] fp32; sigma: 0-dim/1-element fp32 CPU tensor (same for all images)."""
         sig = torch.as_tensor(sigma, dtype=torch.float32).reshape(-1)[:1].cpu()
         c_in = 1 / (sig ** 2 + 1 ** 2) ** 0.5  # get_scalings, fp32 like denoiser.py:390
         t = self.scheduler.sigma_to_t(sig).to(self.dtype).float()  # fp64 -> model dtype (P3, denoiser.py:393)
         if self._part is None:
+            if inject:
+                return self.unet.forward_rows(x, float(c_in), float(t), rows_per_image=1 + plan.n_sub, inject=inject)
             return self.unet.forward_rows(x, float(c_in), float(t), rows_per_image=1 + plan.n_sub)
+        if inject:
+            raise NotImplementedError("feature injection together with row sharding")
         # row-sharded: my rows of my (single) image, then the NCCL all-gather of eps inside the image's rank group
         from ... import dist as D
         if x.shape[0] != 1:
@@ -195,7 +207,7 @@ class Denoiser(torch.nn.Module):
     def fused_step(self, x, sigma, plan, step, **kwargs):
         """One UNet evaluation + ONE fused kernel: CFG combine, denoised, sampler update (x updated in place).
         `step` is a dict of the fp32 scalars for cpd_sampler_step."""
-        eps = self.unet_rows(x, sigma, plan)
+        eps = self.unet_rows(x, sigma, plan, inject=self._inject(kwargs))
         sig = float(torch.as_tensor(sigma, dtype=torch.float32).reshape(-1)[0])
         sig_t = torch.tensor([sig], dtype=torch.float32)
         pred = CPD_PRED_VELOCITY if kwargs.get("pred_type", "epsilon") == "velocity" else CPD_PRED_EPSILON

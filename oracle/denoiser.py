@@ -71,12 +71,16 @@ class OracleDenoiser:
         x_in = x * sc_in  # :391  ([1,4,h,w] * [bs,1,1,1])
         t_full, low_idx, high_idx = self.scheduler.sigma_to_t_idx(t_in)
         t_in = t_full.to(self.dtype)  # :393 (P3: cast to the UNet parameter dtype)
+        inj = dict(inject_feats=kwargs.get("inject_feats", None), inject_feats_stop=kwargs.get("inject_feats_stop", 10),
+                   inject_attns=kwargs.get("inject_attns", None), inject_attns_stop=kwargs.get("inject_attns_stop", 10))  # :353-356
+        if inj["inject_feats"] is None and inj["inject_attns"] is None:
+            inj = {}
         if kwargs.get("y") is not None:  # SDXL extension: vector conditioning rows [1 + N, adm] (row 0 = unconditional) or [1, adm]
             y = torch.as_tensor(kwargs["y"])
             y = y.expand(bs, -1) if y.shape[0] == 1 else y
-            out, _skips = self.unet(x_in, t_in, f_uc, return_attn=True, y=_safe_to(y, self.dtype))
+            out, _skips = self.unet(x_in, t_in, f_uc, return_attn=True, y=_safe_to(y, self.dtype), **inj)
         else:
-            out, _skips = self.unet(x_in, t_in, f_uc, return_attn=True)  # :397-402
+            out, _skips = self.unet(x_in, t_in, f_uc, return_attn=True, **inj)  # :397-402
         e_t_out = list(out.chunk(bs))  # :439
         e_t_uncond = e_t_out.pop(0)  # :440
         sum_e_t = combine_fp16(e_t_out, e_t_uncond, e_scales, e_masks)  # :450-460

@@ -340,7 +340,8 @@ class OracleUNet:
 
     # --- forward -------------------------------------------------------------------------------
     @torch.no_grad()
-    def __call__(self, x, timesteps, context, return_attn=False, y=None, **_):
+    def __call__(self, x, timesteps, context, return_attn=False, y=None, return_feat=False, inject_feats=None, inject_feats_stop=10,
+                 inject_attns=None, inject_attns_stop=10, **_):
         """UNetModel.forward, unet.py:765-831.  x:[R,4,h,w], timesteps:[R], context:[R,77,D]."""
         sd, cfg = self.sd, self.cfg
         t_emb = timestep_embedding(timesteps, cfg.model_channels).to(self.dtype)
@@ -357,20 +358,27 @@ class OracleUNet:
             h = self._block(f"input_blocks.{i}.", layers, h, emb, context)
             hs.append(h)
         h = self._block("middle_block.", self.middle, h, emb, context)
-        skips = []
+        skips, feats = [], []
         for i, layers in enumerate(self.outputs):
             skip = hs.pop()
             skips.append(skip)
+            if inject_attns is not None and inject_attns_stop > i:  # unet.py:806-809: replace the skip tensor
+                assert inject_attns[i].shape == skip.shape
+                skip = inject_attns[i].to(self.dtype)
+            if inject_feats is not None and inject_feats_stop > i:  # unet.py:810-813: replace the running feature map
+                assert inject_feats[i].shape == h.shape
+                h = inject_feats[i].to(self.dtype)
             h = torch.cat([h, skip], dim=1)
             h = self._block(f"output_blocks.{i}.", layers, h, emb, context)
+            feats.append(h)  # unet.py:816-817 (return_feat)
         # unet.py:818 casts h back to x.dtype before self.out; under the product's autocast the final
         # conv then runs (and returns) in the model dtype.
         h = F.silu(group_norm32(h, sd["out.0.weight"], sd["out.0.bias"], 1e-5))
         out = F.conv2d(h, sd["out.2.weight"], sd["out.2.bias"], padding=1)
         self._tap("out", out)
-        if return_attn:
-            return out, skips
-        return out
+        if return_attn:  # unet.py:822-831
+            return (out, skips, feats) if return_feat else (out, skips)
+        return (out, feats) if return_feat else out
 
     def parameters(self):
         return iter(self.sd.values())

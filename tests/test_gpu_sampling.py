@@ -707,3 +707,61 @@ def test_prompt_caches_never_serve_a_stale_prompt(cpd):
                                    unconditional_guidance_scale=5.0, scheduler="karras")
     torch.cuda.synchronize()
     assert torch.equal(again, outs[1])
+
+
+def test_feature_and_skip_injection(cpd):
+    """SURVEY.md 8-f row 4 (the part inside the UNet call): `inject_feats` / `inject_attns` with their `*_stop` indices
+    (unet.py:776-779,806-813; denoiser.py:353-356,397-402) and `return_attn` / `return_feat` (unet.py:802-804,816-831).
+    The structure of a run with prompt A (its skip tensors and the inputs of its output blocks) is injected into a run with
+    prompt B, on the oracle and on the GPU, through UNetModel.forward and through the Denoiser / sampler."""
+    from complex_prompt_diffusion_b200 import samplers
+    from oracle.denoiser import OracleDenoiser
+    from oracle import samplers as OS
+    cfg, oracle, gpu = _unet_pair("tiny", torch.float32)
+    oracle.sd = {k: v.to(torch.bfloat16).float() for k, v in oracle.sd.items()}
+    g = torch.Generator().manual_seed(31)
+    R, hw = 2, 16
+    x = torch.randn(R, 4, hw, hw, generator=g)
+    t = torch.tensor([640.0, 640.0]).to(torch.bfloat16).float()
+    ctx_a = torch.randn(R, 77, cfg.context_dim, generator=g).to(torch.bfloat16).float()
+    ctx_b = torch.randn(R, 77, cfg.context_dim, generator=g).to(torch.bfloat16).float()
+    _, skips_a, feats_a = oracle(x, t, ctx_a, return_attn=True, return_feat=True)
+    out_g, skips_g, feats_g = gpu(x.to(DEV), t.to(DEV), ctx_a.to(DEV), return_attn=True, return_feat=True)
+    torch.cuda.synchronize()
+    assert len(skips_g) == len(skips_a) and len(feats_g) == len(feats_a)
+    for a, b in zip(feats_a, feats_g):
+        assert rel(b, a) < 1e-2
+    inj_h = [skips_a[0]] + feats_a[:-1]  # input of output block i: the middle-block output has the shape of the first skip
+    inj_h = [torch.randn(v.shape, generator=g) * v.std() for v in inj_h]
+    kw = dict(inject_feats=inj_h, inject_feats_stop=2, inject_attns=skips_a, inject_attns_stop=3)
+    ref = oracle(x, t, ctx_b, **kw)
+    plain = oracle(x, t, ctx_b)
+    out = gpu(x.to(DEV), t.to(DEV), ctx_b.to(DEV), **{k: ([v.to(DEV) for v in val] if isinstance(val, list) else val) for k, val in kw.items()})
+    torch.cuda.synchronize()
+    r = rel(out, ref)
+    print(f"injection through UNetModel.forward: rel {r:.3e} (vs the un-injected run: {rel(plain, ref):.3e})")
+    assert r < 1e-2 and rel(plain, ref) > 5e-2
+    # through the sampler / Denoiser: the same injection lists at every step, rows = uncond + 1 prompt
+    uc = torch.randn(1, 77, cfg.context_dim, generator=g)
+    c = {"and": [(1.0, torch.randn(1, 77, cfg.context_dim, generator=g), None, 1)], "not": []}
+    x_T = torch.randn(1, 4, hw, hw, generator=g)
+    skw = dict(conditioning=c, unconditional_conditioning=uc, unconditional_guidance_scale=4.0, scheduler="karras", **kw)
+    refs = OS.sample(OracleDenoiser(_oracle_side_kw(oracle), dtype=torch.bfloat16), "Euler", 3, x_T.clone(), **dict(skw))
+    wrapper = samplers.make({"name": "Euler", "args": {}}, {"model": {"unet": gpu}})
+    outs = wrapper.sampler.sample(steps=3, batch_size=1, shape=[4, hw, hw], x_T=x_T.clone(), rng_compat=False, **dict(skw))
+    torch.cuda.synchronize()
+    r = rel(outs, refs)
+    print(f"injection through the sampler: final latent rel {r:.3e}")
+    assert r < 2e-2
+
+
+def _oracle_side_kw(oracle, dtype=torch.bfloat16):
+    class Side:  # oracle UNet with the product's dtype boundaries, forwarding the injection kwargs
+        def parameters(self):
+            return iter([torch.zeros(1, dtype=dtype)])
+
+        def __call__(self, x, t, ctx, **k):
+            k.pop("return_attn", None)
+            o = oracle(x.to(dtype).float(), t.float(), ctx.to(dtype).float(), **k)
+            return o, [o] * 12
+    return Side()

@@ -14,7 +14,8 @@
 //   * ONE MMA issuer warp PER TILE: a single issuer serialises ~1500 cycles of barrier / fence / commit latency per
 //     (tile, key block) and cannot keep up once the softmax no longer waits for it.
 //
-// Replaces the sliced einsum / softmax / einsum of cpd/models/attention.py:283-348 for head dims <= 63.
+// Replaces the sliced einsum / softmax / einsum of cpd/models/attention.py:283-348 for head dims <= 63 (default) and, opt-in
+// with P aliased over S, for head dims <= 111.
 #include <stdlib.h>
 
 #include "../../include/cpd_b200.h"
@@ -68,6 +69,10 @@ __device__ __forceinline__ void tmem_st32_4(uint32_t taddr, const uint32_t* r) {
       : "memory");
 }
 
+// SEP = true : P in its own TMEM columns (per tile S 128 | P 64 | O 64: head dims <= 63), S(j+1) runs ahead of the softmax.
+// SEP = false: P overwrites S in place (per tile S/P 128, O 128 in the upper half: head dims <= 111); S(j+1) follows P V(j)
+//              on the in-order tensor pipe - the split rows and the per-tile issuers still apply.
+template <bool SEP>
 __global__ void __launch_bounds__(NUM_THREADS, 1) attention4_kernel(const __grid_constant__ Attn4Args a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -150,7 +155,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention4_kernel(const __grid
   // TMEM columns.  Separate-P mode (dv <= 64, i.e. SD-1.x d = 40): per tile [S 128 | P 64 | O 64]; S(j+1) is issued as
   // soon as the softmax threads have READ S(j), so the Q K^T round trip never stalls the exp stream.  Aliased mode
   // (larger head dims): P overwrites S in place, O lives in the upper half; S(j+1) follows P V(j) on the in-order pipe.
-  constexpr bool sep = true;
+  constexpr bool sep = SEP;
   const uint32_t colS0 = 0, colS1 = sep ? 256u : 128u;
   const uint32_t offP = sep ? 128u : 0u;                 // P_t relative to S_t
   const uint32_t colO0 = sep ? 192u : 256u, colO1 = sep ? 448u : 384u;
@@ -221,7 +226,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention4_kernel(const __grid
         st_n = 0;
         ph_n ^= 1;
       }
-      if (j + 1 < nblk) {
+      if (sep && j + 1 < nblk) {  // S_t(j+1) as soon as both halves of S_t(j) sit in registers
         mbar_wait(&s_free[t], (uint32_t)(j & 1), 25);
         mbar_wait(&k_full[st_n], ph_n, 20);
         tc_fence_after();
@@ -242,6 +247,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention4_kernel(const __grid
         umma_commit(&v_empty[st]);
       }
       __syncwarp();
+      if (!sep && j + 1 < nblk) {  // aliased: S_t(j+1) overwrites P_t(j), so it follows P V_t(j) on the in-order tensor pipe
+        mbar_wait(&k_full[st_n], ph_n, 20);
+        tc_fence_after();
+        issue_s(st_n);
+      }
       st = st_n;
       ph = ph_n;
     }
@@ -268,9 +278,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention4_kernel(const __grid
       tmem_ld32(tS + col0, reinterpret_cast<uint32_t(&)[32]>(s[0]));
       tmem_ld32(tS + col0 + 32, reinterpret_cast<uint32_t(&)[32]>(s[32]));
       tmem_ld_wait();
-      // this half of the S row now lives in registers: once both halves do, the tensor pipe may write S_t(j+1)
-      tc_fence_before();
-      mbar_arrive(&s_free[t]);
+      if (sep) {  // this half of the S row now lives in registers: once both halves do, the tensor pipe may write S_t(j+1)
+        tc_fence_before();
+        mbar_arrive(&s_free[t]);
+      }
       const bool full = (kv_valid == BKV);
       float mx0 = -INFINITY, mx1 = -INFINITY;
       if (full) {
@@ -308,7 +319,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention4_kernel(const __grid
       }
       // P V_t(j-1) must be complete before O_t is rescaled (rare) and before P_t is overwritten - the latter only after the
       // exp phase, so the P V round trip hides behind it.
-      bool pv_waited = j == 0;
+      bool pv_waited = !sep || j == 0;  // aliased mode: s_full(j) already implies that P V_t(j-1) has completed
       if (__any_sync(0xffffffffu, need)) {  // rare: rescale this warp's 32 rows of O (every other 16-column group per half)
         if (!pv_waited) {
           mbar_wait(&pv_done[t], (uint32_t)((j - 1) & 1), 31);
@@ -400,8 +411,18 @@ cpd_status cpd_attention_split(const cpd_attn_params* p, void* stream) {
   const int d = p->d_head;
   if (d <= 0 || d > p->dpad || p->nq <= BQ) return CPD_ERR_UNSUPPORTED;
   const int dv = (d + 1 + 15) / 16 * 16;
-  if (dv > 64) return CPD_ERR_UNSUPPORTED;          // O_t and P_t have 64 TMEM columns each
+  if (dv > 128) return CPD_ERR_UNSUPPORTED;          // O_t has at most 128 TMEM columns
+  const bool sep = dv <= 64;                         // room for P next to S and O: S(j+1) runs ahead
   if (p->nk <= 2 * BKV) return CPD_ERR_UNSUPPORTED;  // few key blocks (cross-attention): the persistent kernel is the better fit
+  // The aliased variant (head dims 64..111) is correct but measured SLOWER than the two-tile kernels (1024^2 d80: 93.0 vs
+  // 84.6 us, 9216^2 d64: 1449 vs 1359 us): with P over S the Q K^T round trip is back on every tile's critical path and the
+  // extra warps only add barrier traffic.  Opt-in: CPD_ATTN_SPLIT_ALIASED=1.
+  static int alias_ok = -1;
+  if (alias_ok < 0) {
+    const char* e = getenv("CPD_ATTN_SPLIT_ALIASED");
+    alias_ok = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (!sep && !alias_ok) return CPD_ERR_UNSUPPORTED;
   Attn4Args a;
   a.o = (bf16*)p->o;
   a.ldo = p->ldo;
@@ -442,11 +463,13 @@ cpd_status cpd_attention_split(const cpd_attn_params* p, void* stream) {
   const size_t shm = (size_t)q_bytes + (size_t)stages * per_stage + 512 + XCH_BYTES + 1024;
   static bool configured = false;
   if (!configured) {
-    CPD_CUDA_CHECK(cudaFuncSetAttribute(attention4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+    CPD_CUDA_CHECK(cudaFuncSetAttribute(attention4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+    CPD_CUDA_CHECK(cudaFuncSetAttribute(attention4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
     configured = true;
   }
   dim3 grid((p->nq + 2 * BQ - 1) / (2 * BQ), p->heads, p->batch);
-  CPD_CUDA_CHECK(cpd_launch(attention4_kernel, dim3(grid), dim3(NUM_THREADS), shm, (cudaStream_t)stream, a));
+  if (sep) CPD_CUDA_CHECK(cpd_launch(attention4_kernel<true>, dim3(grid), dim3(NUM_THREADS), shm, (cudaStream_t)stream, a));
+  else CPD_CUDA_CHECK(cpd_launch(attention4_kernel<false>, dim3(grid), dim3(NUM_THREADS), shm, (cudaStream_t)stream, a));
   CPD_CUDA_CHECK(cudaGetLastError());
   return CPD_OK;
 }

@@ -68,7 +68,7 @@ def make_inputs(cfg, latent, batch, n_sub, seed=0):
     """Synthetic prompts / latents of the named shape: emb_k ~ N(0,1) [1,77,D], x_T ~ N(0,1).
     UNets with vector conditioning (SDXL) also get y ~ N(0,1) [1 + n_sub, adm] through make_y."""
     g = torch.Generator().manual_seed(1000 + seed)
-    D = cfg.context_dim
+    D = cfg["context_dim"] if isinstance(cfg, dict) else cfg.context_dim
     uc = torch.randn(1, 77, D, generator=g)
     embs = [torch.randn(1, 77, D, generator=g) for _ in range(n_sub)]
     weights = [1.0, 0.6, 0.4, 0.3, 0.2][:n_sub]
@@ -79,9 +79,10 @@ def make_inputs(cfg, latent, batch, n_sub, seed=0):
 
 
 def make_y(cfg, n_sub, seed=0):
-    if not cfg.adm_in_channels:
+    adm = cfg["adm_in_channels"] if isinstance(cfg, dict) else cfg.adm_in_channels
+    if not adm:
         return None
-    return torch.randn(1 + n_sub, cfg.adm_in_channels, generator=torch.Generator().manual_seed(2000 + seed))
+    return torch.randn(1 + n_sub, adm, generator=torch.Generator().manual_seed(2000 + seed))
 
 
 def workload_of(args):
@@ -192,8 +193,8 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------------ GPU arm
 def run_b200(args):
     from complex_prompt_diffusion_b200 import ops, samplers
+    from complex_prompt_diffusion_b200.models import fixtures
     from complex_prompt_diffusion_b200.models.unet import UNetModel
-    from oracle.unet import make_weights, count_flops  # weights fixture + FLOP enumerator only (not the measured path)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -203,14 +204,9 @@ def run_b200(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    cfg = oracle_cfg(args.model)
-    sd = make_weights(cfg, seed=0)
-    unet = UNetModel(sd, device=dev, model_channels=cfg.model_channels, channel_mult=tuple(cfg.channel_mult),
-                     attention_resolutions=tuple(cfg.attention_resolutions), num_res_blocks=cfg.num_res_blocks,
-                     num_heads=cfg.num_heads, num_head_channels=cfg.num_head_channels, context_dim=cfg.context_dim,
-                     use_linear_in_transformer=cfg.use_linear_in_transformer, transformer_depth=cfg.transformer_depth,
-                     adm_in_channels=cfg.adm_in_channels, num_classes="sequential" if cfg.adm_in_channels else None,
-                     use_cuda_graph=not args.no_graph)
+    cfg = fixtures.UNET_PRESETS[args.model]  # random-init weights of the named architecture (no network for checkpoints)
+    sd = fixtures.random_state_dict(fixtures.unet_param_shapes(cfg), seed=0)
+    unet = UNetModel(sd, device=dev, use_cuda_graph=not args.no_graph, **fixtures.unet_kwargs(args.model))
     del sd
     n_sub, B, S = args.n_sub, args.batch, args.sampler_steps
     uc, c, x_T = make_inputs(cfg, args.latent, B, n_sub, seed=rank)
@@ -271,9 +267,8 @@ def run_b200(args):
     vae = None
     if not args.no_decode and not os.environ.get("CPD_BENCH_NCU"):
         from complex_prompt_diffusion_b200.models.vae import VAEDecoder
-        from oracle.vae import VAEConfig, make_weights as vae_weights  # weight fixture only
-        vcfg = VAEConfig.sd()
-        vae = VAEDecoder(vae_weights(vcfg, seed=0), device=dev, ch=vcfg.ch, ch_mult=tuple(vcfg.ch_mult), num_res_blocks=vcfg.num_res_blocks)
+        vcfg = fixtures.VAE_PRESETS["sd"]
+        vae = VAEDecoder(fixtures.random_state_dict(fixtures.vae_param_shapes(vcfg), seed=0), device=dev, **vcfg)
         img_h = torch.empty(B, 3, args.latent * 8, args.latent * 8).pin_memory()
 
     def step_e2e_images():
@@ -318,7 +313,7 @@ def run_b200(args):
     ips_e2e = imgs / (ms_e2e / 1e3)
     R = 1 + n_sub
     evals_per_step = S * R * B
-    flops_row = count_flops(cfg, args.latent, args.latent)["total"]
+    flops_row = fixtures.unet_flops(cfg, args.latent, args.latent)
     pk = peaks()
 
     # dominant kernel (tcgen05 implicit-GEMM conv / GEMM): per-launch CUDA-event timing over one more step

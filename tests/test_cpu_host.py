@@ -74,6 +74,30 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f"{f} imports the oracle"
+    # developer tools measure the product, never the oracle
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith(".py"):
+            src = open(os.path.join(ROOT, "tools", f)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f"tools/{f} imports the oracle"
+    # bench.py: only the CPU legs (cpu_sample / oracle_cfg, i.e. cpu_baseline and --impl reference) may touch oracle/
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    gpu_arm = src[src.index("def run_b200"):src.index("def sampler_roofline")]
+    assert not re.search(r"^\s*(from|import)\s+oracle", gpu_arm, re.M), "the GPU arm of bench.py imports the oracle"
+
+
+def test_fixtures_agree_with_the_oracle_enumerators():
+    """The product-side presets / parameter shapes / FLOP enumerators (used by bench.py's GPU arm) describe the same
+    architectures as the oracle's."""
+    from complex_prompt_diffusion_b200.models import fixtures as F
+    from oracle.unet import UNetConfig, param_shapes, count_flops
+    from oracle.vae import VAEConfig, param_shapes as vae_shapes, count_flops as vae_fl
+    for n in ("sd15", "sd21", "sdxl", "tiny", "tiny_xl"):
+        assert F.unet_param_shapes(F.UNET_PRESETS[n]) == param_shapes(getattr(UNetConfig, n)())
+        assert F.unet_flops(F.UNET_PRESETS[n], 64, 64) == count_flops(getattr(UNetConfig, n)(), 64, 64)["total"]
+    for n in ("sd", "tiny"):
+        assert F.vae_param_shapes(F.VAE_PRESETS[n]) == vae_shapes(getattr(VAEConfig, n)())
+        assert F.vae_flops(F.VAE_PRESETS[n], 64, 64) == vae_fl(getattr(VAEConfig, n)(), 64, 64)
+    assert abs(F.unet_flops(F.UNET_PRESETS["sd15"], 64, 64) / 1e12 - 0.8033) < 1e-3  # SURVEY.md 8-d
 
 
 def test_schedule_matches_oracle_and_kats(golden_dir):

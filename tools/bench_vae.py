@@ -17,9 +17,9 @@ def main():
     a = ap.parse_args()
     from complex_prompt_diffusion_b200 import ops
     from complex_prompt_diffusion_b200.models.vae import VAEDecoder
-    from oracle.vae import VAEConfig, make_weights, count_flops  # weight fixture + FLOP enumerator only
-    cfg = VAEConfig.sd()
-    dec = VAEDecoder(make_weights(cfg, seed=0), device="cuda", ch=cfg.ch, ch_mult=tuple(cfg.ch_mult), num_res_blocks=cfg.num_res_blocks)
+    from complex_prompt_diffusion_b200.models import fixtures
+    cfg = fixtures.VAE_PRESETS["sd"]
+    dec = VAEDecoder(fixtures.random_state_dict(fixtures.vae_param_shapes(cfg), seed=0), device="cuda", **cfg)
     z = torch.randn(a.batch, 4, a.latent, a.latent, device="cuda")
     for _ in range(2):
         out = dec.decode(z)
@@ -31,7 +31,7 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.reps
-    fl = count_flops(cfg, a.latent, a.latent) * a.batch
+    fl = fixtures.vae_flops(cfg, a.latent, a.latent) * a.batch
     print(f"vae decode B={a.batch} {a.latent}x{a.latent} -> {tuple(out.shape)}: {ms:.2f} ms  {fl / ms / 1e9:.1f} TFLOP/s  "
           f"{a.batch / ms * 1e3:.1f} images/s  finite={bool(torch.isfinite(out).all())}")
     ops.PROFILE = []

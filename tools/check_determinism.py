@@ -14,16 +14,13 @@ def rel(a, b):
 
 def main():
     from complex_prompt_diffusion_b200.models.unet import UNetModel
-    from oracle.unet import UNetConfig, make_weights
+    from complex_prompt_diffusion_b200.models import fixtures
     for name, hw in (("tiny", 32), ("sd15", 32)):
-        cfg = getattr(UNetConfig, name)()
-        unet = UNetModel(make_weights(cfg, seed=0), device="cuda", model_channels=cfg.model_channels, channel_mult=tuple(cfg.channel_mult),
-                         attention_resolutions=tuple(cfg.attention_resolutions), num_res_blocks=cfg.num_res_blocks, num_heads=cfg.num_heads,
-                         num_head_channels=cfg.num_head_channels, context_dim=cfg.context_dim,
-                         use_linear_in_transformer=cfg.use_linear_in_transformer)
+        cfg = fixtures.UNET_PRESETS[name]
+        unet = UNetModel(fixtures.random_state_dict(fixtures.unet_param_shapes(cfg), seed=0), device="cuda", **fixtures.unet_kwargs(name))
         g = torch.Generator().manual_seed(1)
         x = torch.randn(2, 4, hw, hw, generator=g).cuda()
-        ctx = torch.randn(4, 77, cfg.context_dim, generator=g).cuda()
+        ctx = torch.randn(4, 77, cfg["context_dim"], generator=g).cuda()
         unet.set_context(ctx)
         a = unet.forward_rows(x, 0.5, 500.0, 4).clone()
         b = unet.forward_rows(x, 0.5, 500.0, 4).clone()

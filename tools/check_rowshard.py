@@ -13,18 +13,16 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 def main():
     from complex_prompt_diffusion_b200 import samplers, dist as D
     from complex_prompt_diffusion_b200.models.unet import UNetModel
-    from oracle.unet import UNetConfig, make_weights
+    from complex_prompt_diffusion_b200.models import fixtures
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    cfg = UNetConfig.tiny()
-    unet = UNetModel(make_weights(cfg, seed=0), device=dev, model_channels=cfg.model_channels, channel_mult=tuple(cfg.channel_mult),
-                     attention_resolutions=tuple(cfg.attention_resolutions), num_res_blocks=cfg.num_res_blocks, num_heads=cfg.num_heads,
-                     context_dim=cfg.context_dim)
+    cfg = fixtures.UNET_PRESETS["tiny"]
+    unet = UNetModel(fixtures.random_state_dict(fixtures.unet_param_shapes(cfg), seed=0), device=dev, **fixtures.unet_kwargs("tiny"))
     g = torch.Generator().manual_seed(0)
-    uc = torch.randn(1, 77, cfg.context_dim, generator=g)
-    embs = [torch.randn(1, 77, cfg.context_dim, generator=g) for _ in range(3)]
+    uc = torch.randn(1, 77, cfg["context_dim"], generator=g)
+    embs = [torch.randn(1, 77, cfg["context_dim"], generator=g) for _ in range(3)]
     c = {"and": [(1.0, embs[0], None, 1), (0.6, embs[1], None, 1)], "not": [(0.4, embs[2], None, 1)]}
     x_T = torch.randn(2, 4, 32, 32, generator=g)
     wrapper = samplers.make({"name": "DPM++ 2m", "args": {}}, {"model": {"unet": unet}})

@@ -11,15 +11,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def main():
     from complex_prompt_diffusion_b200.models.unet import UNetModel
-    from oracle.unet import UNetConfig, make_weights, count_flops
+    from complex_prompt_diffusion_b200.models import fixtures
     for name, hw, imgs, rows in (("sd21", 96, 1, 2), ("sd15", 128, 1, 2), ("sd15", 32, 1, 2), ("sd15", 64, 1, 4), ("sd21", 64, 2, 2)):
-        cfg = getattr(UNetConfig, name)()
-        unet = UNetModel(make_weights(cfg, seed=0), device="cuda", model_channels=cfg.model_channels, channel_mult=tuple(cfg.channel_mult),
-                         attention_resolutions=tuple(cfg.attention_resolutions), num_res_blocks=cfg.num_res_blocks, num_heads=cfg.num_heads,
-                         num_head_channels=cfg.num_head_channels, context_dim=cfg.context_dim,
-                         use_linear_in_transformer=cfg.use_linear_in_transformer)
+        cfg = fixtures.UNET_PRESETS[name]
+        unet = UNetModel(fixtures.random_state_dict(fixtures.unet_param_shapes(cfg), seed=0), device="cuda", **fixtures.unet_kwargs(name))
         x = torch.randn(imgs, 4, hw, hw, device="cuda")
-        unet.set_context(torch.randn(rows, 77, cfg.context_dim, device="cuda"))
+        unet.set_context(torch.randn(rows, 77, cfg["context_dim"], device="cuda"))
         for _ in range(2):
             out = unet.forward_rows(x, 0.5, 500.0, rows)
         torch.cuda.synchronize()
@@ -28,7 +25,7 @@ def main():
             out = unet.forward_rows(x, 0.5, 500.0, rows)
         torch.cuda.synchronize()
         ms = (time.perf_counter() - t0) / 3 * 1e3
-        fl = count_flops(cfg, hw, hw)["total"] * imgs * rows
+        fl = fixtures.unet_flops(cfg, hw, hw) * imgs * rows
         print(f"{name} {hw}x{hw} {imgs} image(s) x {rows} rows: finite={bool(torch.isfinite(out).all())} {ms:.2f} ms/eval "
               f"{fl / ms / 1e9:.0f} TFLOP/s")
         del unet

@@ -11,16 +11,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 def main():
     from complex_prompt_diffusion_b200 import ops
     from complex_prompt_diffusion_b200.models.unet import UNetModel
-    from oracle.unet import UNetConfig, make_weights
+    from complex_prompt_diffusion_b200.models import fixtures
     name = sys.argv[1] if len(sys.argv) > 1 else "tiny"
-    cfg = getattr(UNetConfig, name)()
-    unet = UNetModel(make_weights(cfg, seed=0), device="cuda", use_cuda_graph=False, model_channels=cfg.model_channels,
-                     channel_mult=tuple(cfg.channel_mult), attention_resolutions=tuple(cfg.attention_resolutions),
-                     num_res_blocks=cfg.num_res_blocks, num_heads=cfg.num_heads, num_head_channels=cfg.num_head_channels,
-                     context_dim=cfg.context_dim, use_linear_in_transformer=cfg.use_linear_in_transformer)
+    cfg = fixtures.UNET_PRESETS[name]
+    unet = UNetModel(fixtures.random_state_dict(fixtures.unet_param_shapes(cfg), seed=0), device="cuda", use_cuda_graph=False, **fixtures.unet_kwargs(name))
     g = torch.Generator().manual_seed(1)
     x = torch.randn(2, 4, 32, 32, generator=g).cuda()
-    ctx = torch.randn(4, 77, cfg.context_dim, generator=g).cuda()
+    ctx = torch.randn(4, 77, cfg["context_dim"], generator=g).cuda()
     unet.set_context(ctx)
     log, state = [], {"pass": 0, "i": 0, "bad": 0}
 

@@ -23,14 +23,11 @@ def main():
     a = ap.parse_args()
     from complex_prompt_diffusion_b200 import ops
     from complex_prompt_diffusion_b200.models.unet import UNetModel
-    from oracle.unet import UNetConfig, make_weights
-    cfg = getattr(UNetConfig, a.model)()
-    unet = UNetModel(make_weights(cfg, seed=0), device="cuda", model_channels=cfg.model_channels, channel_mult=tuple(cfg.channel_mult),
-                     attention_resolutions=tuple(cfg.attention_resolutions), num_res_blocks=cfg.num_res_blocks, num_heads=cfg.num_heads,
-                     num_head_channels=cfg.num_head_channels, context_dim=cfg.context_dim,
-                     use_linear_in_transformer=cfg.use_linear_in_transformer)
+    from complex_prompt_diffusion_b200.models import fixtures
+    cfg = fixtures.UNET_PRESETS[a.model]
+    unet = UNetModel(fixtures.random_state_dict(fixtures.unet_param_shapes(cfg), seed=0), device="cuda", **fixtures.unet_kwargs(a.model))
     x = torch.randn(a.images, 4, a.latent, a.latent, device="cuda")
-    ctx = torch.randn(a.rows, 77, cfg.context_dim, device="cuda")
+    ctx = torch.randn(a.rows, 77, cfg["context_dim"], device="cuda")
     unet.set_context(ctx)
     for _ in range(2):
         unet.forward_rows(x, 0.5, 500.0, a.rows)

@@ -64,6 +64,7 @@ _SIGS = {
     "cpd_last_error": (C.c_char_p, []),
     "cpd_abi_version": (C.c_int, []),
     "cpd_sampler_step": (C.c_int, [C.POINTER(StepParams), C.c_void_p]),
+    "cpd_add_noise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int64, C.c_void_p]),
     "cpd_threshold": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]),
     "cpd_gemm_conv": (C.c_int, [C.POINTER(GemmParams), C.c_void_p]),
     "cpd_groupnorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,

@@ -205,7 +205,33 @@ __global__ void __launch_bounds__(256, VEC == 8 ? 3 : 4) sampler_step_kernel(con
   }
 }
 
+__global__ void __launch_bounds__(256) add_noise_kernel(float* __restrict__ x, const float* __restrict__ noise, float noise_mul, float scale,
+                                                        int64_t n4) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 xv = reinterpret_cast<float4*>(x)[i];
+    const float4 nv = __ldg(reinterpret_cast<const float4*>(noise) + i);
+    xv.x = __fadd_rn(xv.x, __fmul_rn(__fmul_rn(nv.x, noise_mul), scale));
+    xv.y = __fadd_rn(xv.y, __fmul_rn(__fmul_rn(nv.y, noise_mul), scale));
+    xv.z = __fadd_rn(xv.z, __fmul_rn(__fmul_rn(nv.z, noise_mul), scale));
+    xv.w = __fadd_rn(xv.w, __fmul_rn(__fmul_rn(nv.w, noise_mul), scale));
+    reinterpret_cast<float4*>(x)[i] = xv;
+  }
+}
+
 }  // namespace
+
+extern "C" cpd_status cpd_add_noise(float* x, const float* noise, float noise_mul, float scale, int64_t n, void* stream) {
+  CPD_REQUIRE(x && noise, "cpd_add_noise: null pointer");
+  CPD_REQUIRE(n >= 0 && n % 4 == 0, "cpd_add_noise: n=%lld must be a non-negative multiple of 4", (long long)n);
+  if (n == 0) return CPD_OK;
+  int64_t blocks = (n / 4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  CPD_CUDA_CHECK(cpd_launch(add_noise_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, x, noise, noise_mul, scale, n / 4));
+  CPD_CUDA_CHECK(cudaGetLastError());
+  return CPD_OK;
+}
 
 extern "C" cpd_status cpd_sampler_step(const cpd_step_params* p, void* stream) {
   CPD_REQUIRE(p != nullptr, "cpd_sampler_step: null params");

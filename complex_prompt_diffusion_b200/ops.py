@@ -130,6 +130,18 @@ def sampler_step(eps, x, *, n_sub, weights, mask_scalars, masks, guidance, sampl
     return x
 
 
+def add_noise(x, noise, *, noise_mul, scale):
+    """x += (noise * noise_mul) * scale in place (stochastic churn before the denoiser call), separately rounded fp32 ops."""
+    _req(x, torch.float32, "x")
+    _req(noise, torch.float32, "noise")
+    if noise.numel() != x.numel():
+        raise RuntimeError("noise must have the shape of x")
+    with _Prof("small", 0.0):
+        check(load().cpd_add_noise(ptr(x), ptr(noise), float(noise_mul), float(scale), int(x.numel()), stream_ptr()), "cpd_add_noise")
+    _count()
+    return x
+
+
 def threshold(x, bound, *, alg, threshold, clamp_inplace=True):
     """Thresholding extension on the device (cpd_threshold): bound[b] = max(percentile_q(|x_b|), 1) or the static bound;
     optionally x <- half(clamp(x, -bound[b], bound[b])) in place.  x: [n_images, ...] fp32, bound: [n_images] fp32."""

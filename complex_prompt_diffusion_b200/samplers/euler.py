@@ -29,18 +29,15 @@ class EulerDiffusionSampler(KDiffusionSampler):
         model_args = {} if model_args is None else model_args
         callback = kwargs.get("callback", None)
         den, plan = self._begin(x, model_args, kwargs)
-        rng_compat = kwargs.get("rng_compat", True)
         den_out = torch.empty_like(x) if callback is not None else None
         for i in range(len(sigmas) - 1):
             model_args["t_idx"] = i
-            if rng_compat:
-                torch.randn_like(x)  # euler.py:43 draws one (unused, gamma = 0) noise tensor per step
-            sigma_hat = sigmas[i] * 1.0
+            sigma_hat = self._churn(x, sigmas, i, kwargs)  # euler.py:42-46
             dt = sigmas[i + 1] - sigma_hat
             x_before = x.clone() if callback is not None else None
             den.fused_step(x, sigma_hat, plan, dict(sampler=CPD_EULER, dt=float(dt), denoised_out=den_out), **model_args)
             self._clip_sample(x, kwargs)
-            self._callback(callback, x_before, i, sigmas[i], den_out)
+            self._callback(callback, x_before, i, sigmas[i], den_out, sigma_hat)
         return x
 
 

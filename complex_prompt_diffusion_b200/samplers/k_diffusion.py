@@ -55,13 +55,30 @@ class KDiffusionSampler:
 
     # ---- shared loop plumbing -------------------------------------------------------------------------
     def _begin(self, x, model_args, kwargs):
-        if kwargs.get("s_churn", 0.0):
-            raise NotImplementedError("s_churn > 0 is not supported (gamma = 0 path only)")
         den = self.denoiser
         den._check_kwargs(model_args)
         plan = den.plan_conditioning(model_args.get("conditioning"), model_args.get("unconditional_conditioning"), x.shape[-2:],
                                      y=model_args.get("y"), force=True)  # once per sample() call: never a stale prompt
         return den, plan
+
+    def _churn(self, x, sigmas, i, kwargs):
+        """Stochastic churn of Karras et al. Algorithm 2 (euler.py:40-46, huen.py:38-43, dpm2.py:38-43): one noise tensor is
+        drawn per step (also when gamma = 0: the reference consumes the RNG either way; `rng_compat=False` skips the unused
+        draw), sigma_hat = sigma * (gamma + 1) and, when gamma > 0, x += (noise * s_noise) * sqrt(sigma_hat^2 - sigma^2) on the
+        device.  Returns sigma_hat (0-dim fp32 tensor)."""
+        from .. import ops
+        s_churn, s_tmin = kwargs.get("s_churn", 0.0), kwargs.get("s_tmin", 0.0)
+        s_tmax, s_noise = kwargs.get("s_tmax", float("inf")), kwargs.get("s_noise", 1.0)
+        gamma = min(s_churn / (len(sigmas) - 1), 2 ** 0.5 - 1) if s_tmin <= sigmas[i] <= s_tmax else 0.0
+        noise_sampler = kwargs.get("noise_sampler", None)
+        noise = None
+        if gamma > 0 or kwargs.get("rng_compat", True):
+            noise = noise_sampler(x) if noise_sampler is not None else torch.randn_like(x)
+        sigma_hat = sigmas[i] * (gamma + 1)
+        if gamma > 0:
+            scale = (sigma_hat ** 2 - sigmas[i] ** 2) ** 0.5
+            ops.add_noise(x, noise.to(x.device, torch.float32).contiguous(), noise_mul=float(s_noise), scale=float(scale))
+        return sigma_hat
 
     def _clip_sample(self, x, kwargs):
         """Sample thresholding after the update (euler.py:55-56, dpmpp.py:51-52): x <- half(clamp(x, -s, s)) with
@@ -75,9 +92,9 @@ class KDiffusionSampler:
             self._clip_bound = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
         ops.threshold(x, self._clip_bound, alg=alg, threshold=float(kwargs.get("clip_sample_thresh", 90)), clamp_inplace=True)
 
-    def _callback(self, callback, x_before, i, sigma, denoised):
+    def _callback(self, callback, x_before, i, sigma, denoised, sigma_hat=None):
         if callback is not None:
-            callback({"x": x_before, "i": i, "sigma": sigma, "sigma_hat": sigma, "eps": denoised})
+            callback({"x": x_before, "i": i, "sigma": sigma, "sigma_hat": sigma if sigma_hat is None else sigma_hat, "eps": denoised})
 
     def _sampling(self, x, sigmas, model_args=None, **kwargs):
         raise NotImplementedError()

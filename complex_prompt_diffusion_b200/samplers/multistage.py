@@ -32,24 +32,21 @@ class HeunDiffusionSampler(KDiffusionSampler):
         model_args = {} if model_args is None else model_args
         callback = kwargs.get("callback", None)
         den, plan = self._begin(x, model_args, kwargs)
-        rng_compat = kwargs.get("rng_compat", True)
         den_out = torch.empty_like(x) if callback is not None else None
         x2, d1 = torch.empty_like(x), torch.empty_like(x)
         for i in range(len(sigmas) - 1):
             model_args["t_idx"] = i
-            if rng_compat:
-                torch.randn_like(x)  # huen.py:40 draws one (unused, gamma = 0) noise tensor per step
-            sigma_hat = sigmas[i] * 1.0
+            sigma_hat = self._churn(x, sigmas, i, kwargs)  # huen.py:39-43
             dt = sigmas[i + 1] - sigma_hat
             if sigmas[i + 1] == 0:  # Euler step (huen.py:48-50)
                 x_before = x.clone() if callback is not None else None
                 den.fused_step(x, sigma_hat, plan, dict(sampler=CPD_EULER, dt=float(dt), denoised_out=den_out), **model_args)
-                self._callback(callback, x_before, i, sigmas[i], den_out)
+                self._callback(callback, x_before, i, sigmas[i], den_out, sigma_hat)
             else:
                 # stage 1: d = to_ode(x), x_2 = x + d * dt (x itself is not touched)
                 den.fused_step(x, sigma_hat, plan, dict(sampler=CPD_EULER, dt=float(dt), x_out=x2, d_out=d1, denoised_out=den_out),
                                **model_args)
-                self._callback(callback, x, i, sigmas[i], den_out)
+                self._callback(callback, x, i, sigmas[i], den_out, sigma_hat)
                 # stage 2: d_2 = to_ode(x_2, sigma_{i+1}); x = x + ((d + d_2) / 2) * dt
                 den.fused_step(x2, sigmas[i + 1], plan, dict(sampler=CPD_HEUN2, dt=float(dt), x_base=x, x_out=x, d_prev=(d1,)),
                                **model_args)
@@ -71,19 +68,16 @@ class DPM2DiffusionSampler(KDiffusionSampler):
         model_args = {} if model_args is None else model_args
         callback = kwargs.get("callback", None)
         den, plan = self._begin(x, model_args, kwargs)
-        rng_compat = kwargs.get("rng_compat", True)
         den_out = torch.empty_like(x) if callback is not None else None
         x2 = torch.empty_like(x)
         for i in range(len(sigmas) - 1):
             model_args["t_idx"] = i
-            if rng_compat:
-                torch.randn_like(x)  # dpm2.py:40
-            sigma_hat = sigmas[i] * 1.0
+            sigma_hat = self._churn(x, sigmas, i, kwargs)  # dpm2.py:39-43
             sigma_mid = _sigma_mid(sigma_hat, sigmas[i + 1])
             dt_1 = sigma_mid - sigma_hat
             dt_2 = sigmas[i + 1] - sigma_hat
             den.fused_step(x, sigma_hat, plan, dict(sampler=CPD_EULER, dt=float(dt_1), x_out=x2, denoised_out=den_out), **model_args)
-            self._callback(callback, x, i, sigmas[i], den_out)
+            self._callback(callback, x, i, sigmas[i], den_out, sigma_hat)
             den.fused_step(x2, sigma_mid, plan, dict(sampler=CPD_EULER, dt=float(dt_2), x_base=x, x_out=x), **model_args)
         return x
 

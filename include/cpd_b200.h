@@ -103,6 +103,11 @@ typedef struct {
 
 cpd_status cpd_sampler_step(const cpd_step_params* p, void* stream);
 
+/* Stochastic churn of Karras et al. Algorithm 2 before the denoiser call (euler.py:43-46, huen.py:40-43, dpm2.py:40-43):
+ * x[i] = x[i] + (noise[i] * noise_mul) * scale with separately rounded fp32 operations (noise_mul = s_noise,
+ * scale = sqrt(sigma_hat^2 - sigma^2)); n elements, n % 4 == 0. */
+cpd_status cpd_add_noise(float* x, const float* noise, float noise_mul, float scale, int64_t n, void* stream);
+
 /*
  * Thresholding extensions on the device (samplers/extension/threshold.py; hooks denoiser.py:510-512, euler.py:55-56,
  * dpmpp.py:51-52,92-93).  The reference copies the tensor to the CPU for np.percentile every step.

@@ -185,6 +185,23 @@ def _run_cases(ref_shim, unet, out, c, uc, x_T, hw, steps, cases):
     return out
 
 
+CHURN_CASES = (("Euler", "karras", "epsilon", {"s_churn": 4.0, "s_noise": 1.003}), ("Huen", "karras", "epsilon", {"s_churn": 4.0}),
+               ("DPM2", "karras", "epsilon", {"s_churn": 9.0, "s_tmin": 0.5, "s_tmax": 6.0, "s_noise": 0.99}))
+
+
+def reference_sampling_churn(ref_shim):
+    """tests/golden/ref_sampling3.npz: stochastic churn (s_churn > 0: gamma > 0, noise added before the denoiser call)."""
+    from oracle.unet import UNetConfig, make_weights
+
+    cfg = UNetConfig.tiny()
+    hw, steps = 8, 6
+    unet = ref_shim.build_reference_unet(cfg)
+    unet.load_state_dict(make_weights(cfg, seed=0), strict=True)
+    unet.eval()
+    uc, embs, mask, c, x_T = make_case_inputs(cfg, hw)
+    return _run_cases(ref_shim, unet, {}, c, uc, x_T, hw, steps, CHURN_CASES)
+
+
 def reference_vae(ref_shim):
     """tests/golden/ref_vae.npz: the shimmed reference first-stage decoder (tiny config, seeded weights) on a seeded latent."""
     from oracle.vae import VAEConfig, make_weights
@@ -206,14 +223,16 @@ def main():
     import cpd.scheduler.k as K
 
     os.makedirs(GOLD, exist_ok=True)
-    if "--more-only" not in sys.argv and "--vae-only" not in sys.argv:
+    if not any(f in sys.argv for f in ("--more-only", "--vae-only", "--churn-only")):
         with open(os.path.join(GOLD, "schedule_kat.json"), "w") as f:
             json.dump(schedule_kats(K), f, indent=1)
-    if "--more-only" not in sys.argv and "--vae-only" not in sys.argv:
+    if not any(f in sys.argv for f in ("--more-only", "--vae-only", "--churn-only")):
         np.savez_compressed(os.path.join(GOLD, "ref_sampling.npz"), **reference_sampling(ref_shim))
-    if "--vae-only" not in sys.argv:
+    if "--vae-only" not in sys.argv and "--churn-only" not in sys.argv:
         np.savez_compressed(os.path.join(GOLD, "ref_sampling2.npz"), **reference_sampling_more(ref_shim))
-    np.savez_compressed(os.path.join(GOLD, "ref_vae.npz"), **reference_vae(ref_shim))
+    if "--churn-only" not in sys.argv:
+        np.savez_compressed(os.path.join(GOLD, "ref_vae.npz"), **reference_vae(ref_shim))
+    np.savez_compressed(os.path.join(GOLD, "ref_sampling3.npz"), **reference_sampling_churn(ref_shim))
     print("golden fixtures written to", GOLD)
 
 

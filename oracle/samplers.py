@@ -30,6 +30,21 @@ def threshold_apply(x, alg, threshold):
     return x.half().float()
 
 
+def _churn(x, sigmas, i, model_args, noise_sampler):
+    """Stochastic churn of Karras et al. Algorithm 2 as in euler.py:40-45 / huen.py:38-43 / dpm2.py:38-43: one randn_like per
+    step (drawn even when gamma = 0), sigma_hat = sigma * (gamma + 1), x += eps * sqrt(sigma_hat^2 - sigma^2) when gamma > 0."""
+    s_churn, s_tmin = model_args.get("s_churn", 0.0), model_args.get("s_tmin", 0.0)
+    s_tmax, s_noise = model_args.get("s_tmax", float("inf")), model_args.get("s_noise", 1.0)
+    gamma = min(s_churn / (len(sigmas) - 1), 2 ** 0.5 - 1) if s_tmin <= sigmas[i] <= s_tmax else 0.0
+    eps = None
+    if noise_sampler is not None:
+        eps = noise_sampler(x) * s_noise
+    sigma_hat = sigmas[i] * (gamma + 1)
+    if gamma > 0:
+        x = x + eps * (sigma_hat ** 2 - sigmas[i] ** 2) ** 0.5
+    return x, sigma_hat
+
+
 def _clip(x, model_args):
     if model_args.get("clip_sample", False):
         return threshold_apply(x, model_args.get("clip_sample_alg", "dynamic_thresholding"), model_args.get("clip_sample_thresh", 90))
@@ -54,9 +69,7 @@ def sample_euler(denoiser, x, sigmas, model_args, noise_sampler=None, callback=N
     s_in = x.new_ones([x.shape[0]])
     for i in range(len(sigmas) - 1):
         model_args["t_idx"] = i
-        if noise_sampler is not None:
-            noise_sampler(x)  # euler.py:43 draws (and discards, gamma = 0) one randn_like per step
-        sigma_hat = sigmas[i] * 1.0
+        x, sigma_hat = _churn(x, sigmas, i, model_args, noise_sampler)  # euler.py:42-46
         den = denoiser(x, sigma_hat * s_in, **model_args)
         d = to_ode(x, sigma_hat, den)
         if callback is not None:
@@ -117,9 +130,7 @@ def sample_heun(denoiser, x, sigmas, model_args, noise_sampler=None, callback=No
     s_in = x.new_ones([x.shape[0]])
     for i in range(len(sigmas) - 1):
         model_args["t_idx"] = i
-        if noise_sampler is not None:
-            noise_sampler(x)
-        sigma_hat = sigmas[i] * 1.0
+        x, sigma_hat = _churn(x, sigmas, i, model_args, noise_sampler)  # huen.py:39-43
         den = denoiser(x, sigma_hat * s_in, **model_args)
         d = to_ode(x, sigma_hat, den)
         if callback is not None:
@@ -142,9 +153,7 @@ def sample_dpm2(denoiser, x, sigmas, model_args, noise_sampler=None, callback=No
     s_in = x.new_ones([x.shape[0]])
     for i in range(len(sigmas) - 1):
         model_args["t_idx"] = i
-        if noise_sampler is not None:
-            noise_sampler(x)
-        sigma_hat = sigmas[i] * 1.0
+        x, sigma_hat = _churn(x, sigmas, i, model_args, noise_sampler)  # dpm2.py:39-43
         den = denoiser(x, sigma_hat * s_in, **model_args)
         d = to_ode(x, sigma_hat, den)
         if callback is not None:

@@ -765,3 +765,31 @@ def _oracle_side_kw(oracle, dtype=torch.bfloat16):
             o = oracle(x.to(dtype).float(), t.float(), ctx.to(dtype).float(), **k)
             return o, [o] * 12
     return Side()
+
+
+CHURN_CASES = [("Euler", "karras", "epsilon", {"s_churn": 4.0, "s_noise": 1.003}), ("Huen", "karras", "epsilon", {"s_churn": 4.0}),
+               ("DPM2", "karras", "epsilon", {"s_churn": 9.0, "s_tmin": 0.5, "s_tmax": 6.0, "s_noise": 0.99})]
+
+
+@pytest.mark.parametrize("name,sched,pred,extra", CHURN_CASES)
+def test_stochastic_churn_bit_exact_vs_reference_golden_fp32(cpd, golden_dir, name, sched, pred, extra):
+    """s_churn > 0 on the device (cpd_add_noise before the UNet call, sigma_hat > sigma through the fused step): UNet inputs,
+    denoised tensors and the final latent equal the shimmed reference's recorded run bit for bit."""
+    from complex_prompt_diffusion_b200 import samplers
+    z, c = load_case(golden_dir)
+    z3 = np.load(os.path.join(golden_dir, "ref_sampling3.npz"))
+    key = f"{name}|{sched}|{pred}".replace(" ", "_") + "|" + "|".join(f"{k}={v}" for k, v in extra.items())
+    unet = ReplayUNet(list(torch.from_numpy(z3[key + "|unet_out"])), torch.float32, DEV,
+                      expect_x=torch.from_numpy(z3[key + "|unet_x"]), expect_t=torch.from_numpy(z3[key + "|unet_t"]))
+    wrapper = samplers.make({"name": name, "args": {}}, {"model": {"unet": unet}})
+    noises = list(torch.from_numpy(z3[key + "|noise"]))
+    dens = []
+    out = wrapper.sampler.sample(steps=int(z["steps"]), batch_size=1, shape=[4, int(z["hw"]), int(z["hw"])],
+                                 x_T=torch.from_numpy(z["x_T"]).clone(), conditioning=c,
+                                 unconditional_conditioning=torch.from_numpy(z["uc"]),
+                                 unconditional_guidance_scale=float(z["guidance"]), scheduler=sched, pred_type=pred,
+                                 noise_sampler=lambda x: noises.pop(0), callback=lambda d: dens.append(d["eps"].clone().cpu()), **extra)
+    torch.cuda.synchronize()
+    assert unet.i == len(unet.outs) and not noises
+    assert torch.equal(torch.stack(dens), torch.from_numpy(z3[key + "|denoised"])), "per-step denoised differs"
+    assert torch.equal(out.cpu(), torch.from_numpy(z3[key + "|final"])), "final latent differs"

@@ -215,3 +215,25 @@ def test_oracle_vae_decoder_matches_reference(golden_dir):
     ref = torch.from_numpy(z["image"])
     rel = ((out - ref).norm() / ref.norm()).item()
     assert out.shape == ref.shape and rel < 1e-5, rel
+
+
+CHURN_CASES = [("Euler", "karras", "epsilon", {"s_churn": 4.0, "s_noise": 1.003}), ("Huen", "karras", "epsilon", {"s_churn": 4.0}),
+               ("DPM2", "karras", "epsilon", {"s_churn": 9.0, "s_tmin": 0.5, "s_tmax": 6.0, "s_noise": 0.99})]
+
+
+@pytest.mark.parametrize("name,sched,pred,extra", CHURN_CASES)
+def test_oracle_stochastic_churn_bit_exact_on_replayed_unet(golden_dir, name, sched, pred, extra):
+    """s_churn > 0 (gamma > 0: noise added before the denoiser call, sigma_hat > sigma) against runs of the shimmed reference
+    (tests/golden/ref_sampling3.npz)."""
+    z, c = _load_case(golden_dir)
+    z3 = np.load(os.path.join(golden_dir, "ref_sampling3.npz"))
+    key = more_key(name, sched, pred, extra)
+    unet = _ReplayUNet(torch.from_numpy(z3[key + "|unet_out"]), torch.from_numpy(z3[key + "|unet_x"]), torch.from_numpy(z3[key + "|unet_t"]))
+    den = OracleDenoiser(unet, dtype=torch.float32)
+    noises = list(torch.from_numpy(z3[key + "|noise"]))
+    dens = []
+    out = OS.sample(den, name, int(z["steps"]), torch.from_numpy(z["x_T"]).clone(), noise_sampler=lambda x: noises.pop(0),
+                    callback=lambda d: dens.append(d["eps"].clone()), conditioning=c, unconditional_conditioning=torch.from_numpy(z["uc"]),
+                    unconditional_guidance_scale=float(z["guidance"]), scheduler=sched, pred_type=pred, **extra)
+    assert torch.equal(torch.stack(dens), torch.from_numpy(z3[key + "|denoised"]))
+    assert torch.equal(out, torch.from_numpy(z3[key + "|final"]))

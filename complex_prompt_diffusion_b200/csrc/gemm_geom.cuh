@@ -28,7 +28,17 @@ struct ConvGeom {
   int rowvec_stride, ld_res, ldd;
   int out_fp16;    // D / residual element type: 1 = fp16, 0 = bf16
   uint32_t idesc;  // tcgen05 instruction descriptor (encodes the A / B element formats and the MMA shape)
+  // reciprocals of the divisors of the per-tile coordinate math (filled by fill_geometry; see qdiv)
+  float inv_box_rows, inv_bx, inv_by, inv_img_px, inv_tw;
 };
+
+// Integer division by a launch constant through its fp32 reciprocal: ~4 instructions instead of the ~40 of an IDIV sequence
+// (the TMA producer ran ten of those between two tiles: a ~1000-cycle bubble per tile in a loop that is the limiter of the
+// main loop).  Exact for n + d < 2^22 (|error| <= (n + d) * 2^-23 < 0.5 / d on (n + 0.5) / d); larger values divide normally.
+__device__ __forceinline__ int qdiv(int n, int d, float inv) {
+  if (n + d >= (1 << 22)) return n / d;
+  return (int)(((float)n + 0.5f) * inv);
+}
 
 // Row r (0..127) of CTA tile `m_tile` -> output pixel.  Returns false when the row is padding.
 struct RowCoord {
@@ -38,20 +48,21 @@ struct RowCoord {
 };
 __device__ __forceinline__ RowCoord row_coord(const ConvGeom& g, int m_tile, int r) {
   const int box_rows = g.tw * g.th * g.nb;
-  const int j = r / box_rows;
+  const int j = qdiv(r, box_rows, g.inv_box_rows);
   const int pidx = r - j * box_rows;
   const int s_idx = m_tile * g.nbox + j;
-  const int bx = s_idx % g.bx_count;
-  const int t2 = s_idx / g.bx_count;
-  const int by = t2 % g.by_count;
-  const int ng = t2 / g.by_count;
+  const int t2 = qdiv(s_idx, g.bx_count, g.inv_bx);
+  const int bx = s_idx - t2 * g.bx_count;
+  const int ng = qdiv(t2, g.by_count, g.inv_by);
+  const int by = t2 - ng * g.by_count;
   const int img_px = g.tw * g.th;
-  const int ib = pidx / img_px;
+  const int ib = qdiv(pidx, img_px, g.inv_img_px);
   const int p2 = pidx - ib * img_px;
+  const int py2 = qdiv(p2, g.tw, g.inv_tw);
   RowCoord rc;
   rc.n = ng * g.nb + ib;
-  rc.y = by * g.th + p2 / g.tw;
-  rc.x = bx * g.tw + p2 % g.tw;
+  rc.y = by * g.th + py2;
+  rc.x = bx * g.tw + (p2 - py2 * g.tw);
   rc.valid = (rc.n < g.n_img) && (rc.y < g.h_out) && (rc.x < g.w_out);
   rc.row = ((int64_t)rc.n * g.h_out + rc.y) * g.w_out + rc.x;
   if (g.m_valid > 0 && rc.row >= g.m_valid) rc.valid = false;
@@ -82,10 +93,10 @@ __device__ __forceinline__ BoxCoord box_coord(const ConvGeom& g, int m_tile, int
   const int csrc = b.src1 ? g.c1 : g.c0;
   b.c = (b.src1 ? cb - g.cb0 : cb) * BK + px * csrc;
   const int s_idx = m_tile * g.nbox + j;
-  const int bx = s_idx % g.bx_count;
-  const int t2 = s_idx / g.bx_count;
-  const int by = t2 % g.by_count;
-  const int ng = t2 / g.by_count;  // beyond n_img -> fully out of bounds -> zero fill
+  const int t2 = qdiv(s_idx, g.bx_count, g.inv_bx);
+  const int bx = s_idx - t2 * g.bx_count;
+  const int ng = qdiv(t2, g.by_count, g.inv_by);  // beyond n_img -> fully out of bounds -> zero fill
+  const int by = t2 - ng * g.by_count;
   b.x = bx * g.tw + dx;
   b.p = py;
   b.y = by * g.th + dy;

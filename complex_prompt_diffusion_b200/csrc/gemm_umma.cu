@@ -340,6 +340,11 @@ int fill_geometry(const cpd_gemm_params* p, ConvGeom* gp, CUtensorMap* map_a0, C
     g.bx_count = g.w_out / tw;
     g.by_count = g.h_out / th;
   }
+  g.inv_box_rows = 1.0f / (float)(g.tw * g.th * g.nb);
+  g.inv_bx = 1.0f / (float)g.bx_count;
+  g.inv_by = 1.0f / (float)g.by_count;
+  g.inv_img_px = 1.0f / (float)(g.tw * g.th);
+  g.inv_tw = 1.0f / (float)g.tw;
   const int64_t n_groups = (g.n_img + g.nb - 1) / g.nb;
   const int64_t total_boxes = n_groups * g.bx_count * g.by_count;
   *m_tiles_cta = (int)((total_boxes + g.nbox - 1) / g.nbox);

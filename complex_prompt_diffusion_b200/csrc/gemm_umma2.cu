@@ -51,6 +51,12 @@ __device__ unsigned long long cpd_dbg_ts[16];
       cpd_dbg_ts[i] = _t;                                                             \
     }                                                                                 \
   } while (0)
+// MMA issuer of CTA 0: clock64 after the full-barrier wait and after the issue of each k-iteration of its first 3 tiles
+__device__ long long cpd_dbg_mma[3][16][2];
+#define MMA_STAMP(ph)                                                                          \
+  do {                                                                                         \
+    if (blockIdx.x == 0 && lane == 0 && it < 3 && (kt - k0) < 16) cpd_dbg_mma[it][kt - k0][ph] = clock64(); \
+  } while (0)
 // epilogue chunk phases of the first two tiles (group 0 leader of CTA 0): [tile][chunk][phase], clock64
 __device__ long long cpd_dbg_epi[2][8][8];
 #define EPI_STAMP(ph)                                                                          \
@@ -62,6 +68,9 @@ __device__ long long cpd_dbg_epi[2][8][8];
   do {               \
   } while (0)
 #define EPI_STAMP(ph) \
+  do {                \
+  } while (0)
+#define MMA_STAMP(ph) \
   do {                \
   } while (0)
 #endif
@@ -125,9 +134,10 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
   const int splits = args.splits;
   const int total_tiles = args.m_tiles2 * n_tiles_c * splits;  // work units: (row block, column tile(s), K range)
   // (integer divisions cost ~50 cycles each, 64-bit ones several hundred: the common splits == 1 / single-column-tile cases skip them)
+  const float inv_splits = 1.0f / (float)splits, inv_ntc = 1.0f / (float)n_tiles_c;
   auto tile_mn = [&](int u, int& m2, int& n_tile) {
-    const int t = splits == 1 ? u : u / splits;
-    m2 = n_tiles_c == 1 ? t : t / n_tiles_c;
+    const int t = splits == 1 ? u : qdiv(u, splits, inv_splits);
+    m2 = n_tiles_c == 1 ? t : qdiv(t, n_tiles_c, inv_ntc);
     n_tile = (t - m2 * n_tiles_c) * MC + pair;
   };
   auto k_range = [&](int u, int& k0, int& k1) {
@@ -203,7 +213,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
         const BoxCoord b0 = box_coord(g, m_tile, 0, 4, 0);  // tap 4 = centre: no shift
         int k0, k1;
         k_range(t, k0, k1);
-        int tap = k0 / cbt, cb = k0 - tap * cbt;
+        int tap = k0 ? k0 / cbt : 0, cb = k0 - tap * cbt;  // k0 == 0 unless split-K
         int dy = 0, dx = 0, py = 0, px = 0;
         if (g.taps == 9) {
           const int ky = tap / 3, kx = tap - ky * 3;
@@ -293,6 +303,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
         for (int kt = k0; kt < k1; ++kt) {
           mbar_wait(&full_bar[stage], phase, 2);
           tc_fence_after();
+          MMA_STAMP(0);
           if (kt == k0 && t == cluster_id && lane == 0) CPD_STAMP(4);
           const uint64_t db = da + b_off;
           if (elect_one()) {
@@ -312,6 +323,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
             umma_commit_pair(&empty_bar[stage], (uint16_t)((1u << (2 * MC)) - 1));  // frees the stage cluster-wide
           }
           __syncwarp();
+          MMA_STAMP(1);
           accum = 1u;
           da += stage_step;
           if (++stage == stages) {
@@ -728,6 +740,9 @@ cpd_status launch2(const Gemm2Args& args, int smem_bytes, cudaStream_t stream) {
 #ifdef CPD_TIMELINE
 extern "C" int cpd_debug_gemm_timeline(unsigned long long* host16) {
   return (int)cudaMemcpyFromSymbol(host16, cpd_dbg_ts, sizeof(unsigned long long) * 16);
+}
+extern "C" int cpd_debug_gemm_mma(long long* host96) {
+  return (int)cudaMemcpyFromSymbol(host96, cpd_dbg_mma, sizeof(long long) * 96);
 }
 extern "C" int cpd_debug_gemm_epilogue(long long* host128) {
   return (int)cudaMemcpyFromSymbol(host128, cpd_dbg_epi, sizeof(long long) * 128);

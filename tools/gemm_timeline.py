@@ -15,13 +15,18 @@ def main():
     from complex_prompt_diffusion_b200 import ops
     ops.AUTOTUNE = False
     lib = ops.load()
-    for (M, N, K, v) in [(256, 160, 64, 160), (256, 160, 640, 160), (16384, 640, 640, 160)]:
+    from complex_prompt_diffusion_b200._lib import CPD_EPI_GEGLU
+    for (M, N, K, v) in [(256, 160, 64, 160), (256, 160, 640, 160), (16384, 640, 640, 160), (65536, 2560, 320, -1), (16384, 5120, 640, -1)]:
         a = torch.randn(M, K, device="cuda").half()
-        w = torch.randn(N, K, device="cuda").half()
-        o = torch.empty(M, N, device="cuda", dtype=torch.float16)
+        w = (torch.randn(N, K, device="cuda") / K ** 0.5).half()
+        geglu = v < 0
+        o = torch.empty(M, N // 2 if geglu else N, device="cuda", dtype=torch.float16)
         bias = torch.randn(N, device="cuda")
         for _ in range(5):
-            ops.gemm_conv(a, w, o, n_img=1, h=1, w=M, c0=K, n_out=N, bias=bias, variant=v)
+            if geglu:
+                ops.gemm_conv(a, w, o, n_img=1, h=1, w=M, c0=K, n_out=N, bias=bias, epilogue=CPD_EPI_GEGLU, geglu_block=256)
+            else:
+                ops.gemm_conv(a, w, o, n_img=1, h=1, w=M, c0=K, n_out=N, bias=bias, variant=v)
         torch.cuda.synchronize()
         ts = (C.c_ulonglong * 16)()
         lib.cpd_debug_gemm_timeline(ts)
@@ -30,6 +35,14 @@ def main():
             print(f"   {nm:40s} +{(ts[i] - ts[0]) / 1e3:7.2f} us")
         for i, nm in ((13, "producer: loop entered"), (11, "producer: first tile coordinates done"), (12, "producer: first empty-slot wait passed")):
             print(f"   {nm:40s} +{(ts[i] - ts[0]) / 1e3:7.2f} us")
+        mm = (C.c_longlong * 96)()
+        lib.cpd_debug_gemm_mma(mm)
+        for tile in range(3):
+            row = [(mm[(tile * 16 + k) * 2], mm[(tile * 16 + k) * 2 + 1]) for k in range(min(16, max(1, K // 64)))]
+            if row[0][0]:
+                t0 = mm[0]
+                print(f"   MMA issuer tile {tile}: " + " ".join(f"[{a - t0}->{b - t0}]" for a, b in row))
+        C.memset(C.addressof(mm), 0, C.sizeof(mm))
         ep = (C.c_longlong * 128)()
         lib.cpd_debug_gemm_epilogue(ep)
         names = ["chunk top", "buffer free", "tmem ld done", "bias added", "st.shared done", "proxy fence", "group barrier", "store issued"]

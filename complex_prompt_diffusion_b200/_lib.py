@@ -13,6 +13,8 @@ LIB_PATH = os.environ.get("CPD_B200_LIB", os.path.join(_HERE, "libcpd_b200.so"))
 CPD_F32, CPD_F16, CPD_BF16 = 0, 1, 2
 CPD_EULER, CPD_EULER_ANCESTRAL, CPD_DPMPP_2M, CPD_DENOISE_ONLY, CPD_HEUN2, CPD_LMS = 0, 1, 2, 3, 4, 5
 CPD_THRESH_DYNAMIC, CPD_THRESH_STATIC = 0, 1
+(CPD_THRESH_DYNANORMIC, CPD_THRESH_SCALED_DYNAMIC_PERC, CPD_THRESH_RENORM, CPD_THRESH_SCALED_NORM, CPD_THRESH_SPATIAL_NORM,
+ CPD_THRESH_SCALED_SPATIAL_NORM) = 2, 3, 4, 5, 6, 7
 CPD_PRED_EPSILON, CPD_PRED_VELOCITY = 0, 1
 CPD_EPI_NONE, CPD_EPI_GEGLU = 0, 1
 CPD_MAX_SUBPROMPTS = 16
@@ -34,7 +36,7 @@ class StepParams(C.Structure):
         ("dpm_c2", C.c_float), ("dpm_first", C.c_int), ("write_old", C.c_int),
         ("x_base", C.c_void_p), ("x_out", C.c_void_p), ("d_out", C.c_void_p), ("d_prev", C.c_void_p * 3),
         ("lms_coeff", C.c_float * 4), ("lms_order", C.c_int), ("noise_mul", C.c_float),
-        ("clip_scaled", C.c_void_p), ("scaled_out", C.c_void_p),
+        ("clip_scaled", C.c_void_p), ("scaled_out", C.c_void_p), ("scaled_in", C.c_void_p),
     ]
 
 
@@ -66,6 +68,7 @@ _SIGS = {
     "cpd_sampler_step": (C.c_int, [C.POINTER(StepParams), C.c_void_p]),
     "cpd_add_noise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int64, C.c_void_p]),
     "cpd_threshold": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]),
+    "cpd_threshold_ex": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
     "cpd_gemm_conv": (C.c_int, [C.POINTER(GemmParams), C.c_void_p]),
     "cpd_groupnorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                 C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -98,6 +98,7 @@ struct Gemm2Args {
                     // (no atomics: bit-reproducible) and applies the epilogue
   float* ws;        // [splits][rows][n_store] fp32
   int64_t ws_slice; // rows * n_store
+  int split_prod;   // 1: warp 2 issues the weight (B) loads, warp 0 only the activation (A) loads (CPD_GEMM_SPLIT_PROD)
 };
 
 // MC = 1: cluster = one CTA pair.  MC = 2: cluster = two CTA pairs working on the same 256 rows and adjacent column
@@ -253,8 +254,9 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
                 tma_load_5d_pair(sa + j * box_bytes, ma, &full_bar[stage], cc, bc.x + dx, py, bc.y + dy, bc.n);
               }
             }
-            for (int sub = 0; sub < args.nsub; ++sub)  // this CTA's half of every sub-tile's weight rows
-              tma_load_2d_pair(sa + A_BYTES + sub * (bn_half * 128), &args.map_b, &full_bar[stage], kt * BK, b_row + sub * args.bn);
+            if (!args.split_prod)
+              for (int sub = 0; sub < args.nsub; ++sub)  // this CTA's half of every sub-tile's weight rows
+                tma_load_2d_pair(sa + A_BYTES + sub * (bn_half * 128), &args.map_b, &full_bar[stage], kt * BK, b_row + sub * args.bn);
           }
           __syncwarp();
           if (kt == k0 && t == cluster_id && lane == 0) CPD_STAMP(3);
@@ -276,6 +278,36 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
               px = (kx == 0) ? 1 : kx - 1;
             }
           }
+        }
+      }
+    }
+  } else if (warp == 2 && args.split_prod) {
+    // ================= weight producer (both CTAs) =================
+    // Opt-in experiment (CPD_GEMM_SPLIT_PROD=1).  The same stage walk as warp 0, issuing only the B loads, to test whether
+    // the producer's issue slots are what the main loop waits for while the epilogue warps run
+    // (profiles/r01_gemm2_timeline_v2.txt).  Measured: 361.9 ms per generation with it, 361.5 ms without - the producer
+    // is NOT the limiter, so the default stays one producer warp.  The bytes land on the same full barrier; its expect_tx (warp 0) may arrive after these
+    // complete_tx - the phase cannot complete before both pending arrivals, so a transiently negative tx-count is fine.
+    const int bn_half = args.bn >> 1;
+    const int tile_w = args.bn * args.nsub;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+      int m2, n_tile;
+      tile_mn(t, m2, n_tile);
+      const int b_row = n_tile * tile_w + (int)rank * bn_half;
+      int k0, k1;
+      k_range(t, k0, k1);
+      for (int kt = k0; kt < k1; ++kt) {
+        mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+        uint8_t* sb = smem + stage * stage_bytes + A_BYTES;
+        if (elect_one())
+          for (int sub = 0; sub < args.nsub; ++sub)
+            tma_load_2d_pair(sb + sub * (bn_half * 128), &args.map_b, &full_bar[stage], kt * BK, b_row + sub * args.bn);
+        __syncwarp();
+        if (++stage == stages) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
@@ -786,6 +818,12 @@ cpd_status cpd_gemm_conv_2cta(const cpd_gemm_params* p, void* stream) {
     const char* e = getenv("CPD_GEMM_MC");
     mc_env = (e && e[0] == '1') ? 1 : 0;  // opt-in: measured equal to the pair cluster
   }
+  static int split_prod_env = -1;
+  if (split_prod_env < 0) {
+    const char* e = getenv("CPD_GEMM_SPLIT_PROD");
+    split_prod_env = (e && e[0] == '1') ? 1 : 0;
+  }
+  args.split_prod = split_prod_env;
   args.half_x = args.half_y = args.half_n = 0;
   args.map_a0h = args.map_a0;
   args.map_a1h = args.map_a1;

@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(256, VEC == 8 ? 3 : 4) sampler_step_kernel(con
       float scaled = h_round(__fmul_rn(sj, p.guidance));
       if (p.scaled_out) p.scaled_out[(int64_t)b * L + i + j] = scaled;
       if (p.clip_scaled) scaled = h_round(fminf(fmaxf(scaled, -clip), clip));  // x.float() -> clamp_ -> .half()
+      if (p.scaled_in) scaled = __ldg(p.scaled_in + (int64_t)b * L + i + j);  // thresholded by cpd_threshold_ex
       if (DT == CPD_F16) et[j] = h_round(__fadd_rn(eu.at(j), scaled));
       else et[j] = __fadd_rn(eu.at(j), scaled);
       if (p.pred_type == CPD_PRED_EPSILON) den[j] = __fsub_rn(x[j], __fmul_rn(p.sigma_hat, et[j]));

@@ -63,11 +63,12 @@ def _act(t, name, like=None):
 def sampler_step(eps, x, *, n_sub, weights, mask_scalars, masks, guidance, sampler, pred_type, sigma_hat, v_c_eps=0.0,
                  v_c_x_div=1.0, dt=0.0, sigma_up=0.0, dpm_ratio=0.0, dpm_expm1=0.0, dpm_c1=0.0, dpm_c2=0.0, dpm_first=1,
                  write_old=0, old_denoised=None, noise=None, denoised_out=None, eps_out=None, x_base=None, x_out=None, d_out=None,
-                 d_prev=(), lms_coeff=(), noise_mul=1.0, clip_scaled=None, scaled_out=None):
+                 d_prev=(), lms_coeff=(), noise_mul=1.0, clip_scaled=None, scaled_out=None, scaled_in=None):
     """eps: [n_images * (1 + n_sub), 4, h, w] (image-major rows); x: [n_images, 4, h, w] fp32, the UNet input; the updated
     sample goes to x_out (default: x, in place) and starts from x_base (default: x)."""
     _req(x, torch.float32, "x")
-    for name, t in (("x_base", x_base), ("x_out", x_out), ("d_out", d_out), ("clip_scaled", clip_scaled), ("scaled_out", scaled_out)):
+    for name, t in (("x_base", x_base), ("x_out", x_out), ("d_out", d_out), ("clip_scaled", clip_scaled), ("scaled_out", scaled_out),
+                    ("scaled_in", scaled_in)):
         _req(t, torch.float32, name)
     _req(old_denoised, torch.float32, "old_denoised")
     _req(noise, torch.float32, "noise")
@@ -124,6 +125,7 @@ def sampler_step(eps, x, *, n_sub, weights, mask_scalars, masks, guidance, sampl
     p.noise_mul = float(noise_mul)
     p.clip_scaled = clip_scaled.data_ptr() if clip_scaled is not None else None
     p.scaled_out = scaled_out.data_ptr() if scaled_out is not None else None
+    p.scaled_in = scaled_in.data_ptr() if scaled_in is not None else None
     with _Prof("sampler_step", 0.0):
         check(load().cpd_sampler_step(C.byref(p), stream_ptr()), "cpd_sampler_step")
     _count()
@@ -156,6 +158,24 @@ def threshold(x, bound, *, alg, threshold, clamp_inplace=True):
               "cpd_threshold")
     _count(2 if clamp_inplace else 1)
     return bound
+
+
+def threshold_ex(x, bound, *, alg, threshold):
+    """The non-clamp thresholding extensions in place on x: [n_images, C, h, w] fp32 (cpd_threshold_ex; threshold.py:87-286):
+    min-max rescaling, torch.quantile / np.percentile bounds, RMS and per-pixel channel-RMS rescaling, all per image on the
+    device; the result holds fp16-rounded values.  bound: [n_images] fp32, receives the per-image s."""
+    _req(x, torch.float32, "x")
+    _req(bound, torch.float32, "bound")
+    if x.ndim != 4:
+        raise RuntimeError(f"threshold_ex wants [n_images, C, h, w], got {tuple(x.shape)}")
+    n = x.shape[0]
+    if bound.numel() < n:
+        raise RuntimeError("bound must hold one fp32 value per image")
+    with _Prof("threshold", 0.0):
+        check(load().cpd_threshold_ex(ptr(x), n, x.shape[1], x.shape[2] * x.shape[3], int(alg), float(threshold), ptr(bound),
+                                      stream_ptr()), "cpd_threshold_ex")
+    _count()
+    return x
 
 
 AUTOTUNE = os.environ.get("CPD_GEMM_AUTOTUNE", "1") != "0"  # time the tile-shape variants of cpd_gemm_conv once per layer shape (first eager call) and keep the best

@@ -19,20 +19,43 @@ import torch
 
 from ... import ops
 from ..._lib import (CPD_DENOISE_ONLY, CPD_DPMPP_2M, CPD_EULER, CPD_EULER_ANCESTRAL, CPD_PRED_EPSILON, CPD_PRED_VELOCITY,
-                     CPD_THRESH_DYNAMIC, CPD_THRESH_STATIC)
+                     CPD_THRESH_DYNAMIC, CPD_THRESH_DYNANORMIC, CPD_THRESH_RENORM, CPD_THRESH_SCALED_DYNAMIC_PERC,
+                     CPD_THRESH_SCALED_NORM, CPD_THRESH_SCALED_SPATIAL_NORM, CPD_THRESH_SPATIAL_NORM, CPD_THRESH_STATIC)
 from ...scheduler.discrete import SigmaScheduler
 
 _UNSUPPORTED_TRUTHY = ("attn_guide", "return_attn", "clip_guidance", "score_corrector", "unconditional_guidance_blur", "depth_mask")
 
-# thresholding extensions that run on the device (samplers/extension/threshold.py:47-88); the other registered variants
-# (dynanormic / scaled / mean-centred ...) still raise
-THRESHOLD_ALGS = {"dynamic_thresholding": CPD_THRESH_DYNAMIC, "static_thresholding": CPD_THRESH_STATIC}
+# Thresholding extensions, all on the device (registered names of samplers/extension/threshold.py).  The first two are
+# clamps (the bound feeds the fused step directly); the others rewrite the tensor (cpd_threshold_ex).
+# "norm_thresholding" (threshold.py:182-205) reads an undefined x_max and cannot run in the reference either.
+THRESHOLD_ALGS = {"dynamic_thresholding": CPD_THRESH_DYNAMIC, "static_thresholding": CPD_THRESH_STATIC,
+                  "dynanormic_thresholding": CPD_THRESH_DYNANORMIC,
+                  "scaled_dynamic_perc_thresholding": CPD_THRESH_SCALED_DYNAMIC_PERC,
+                  "renorm_thresholding": CPD_THRESH_RENORM, "scaled_norm_thresholding": CPD_THRESH_SCALED_NORM,
+                  "spatial_norm_thresholding": CPD_THRESH_SPATIAL_NORM,
+                  "scaled_spatial_norm_thresholding": CPD_THRESH_SCALED_SPATIAL_NORM}
+_CLAMP_ALGS = (CPD_THRESH_DYNAMIC, CPD_THRESH_STATIC)
 
 
 def threshold_alg(name):
+    if name == "none":  # the base ScoreCorrector (threshold.py:7-45): identity
+        return None
     if name not in THRESHOLD_ALGS:
         raise NotImplementedError(f"thresholding algorithm {name!r} is not built on the device (have: {sorted(THRESHOLD_ALGS)})")
     return THRESHOLD_ALGS[name]
+
+
+def apply_threshold(x, bound, name, threshold):
+    """extension(x, threshold=...) of the reference, in place on x: [n_images, 4, h, w] fp32 (values end up rounded through
+    fp16, D10).  bound: [n_images] fp32 scratch."""
+    alg = threshold_alg(name)
+    if alg is None:
+        return x
+    if alg in _CLAMP_ALGS:
+        ops.threshold(x, bound, alg=alg, threshold=float(threshold), clamp_inplace=True)
+    else:
+        ops.threshold_ex(x, bound, alg=alg, threshold=float(threshold))
+    return x
 
 
 class ConditioningPlan:
@@ -214,18 +237,24 @@ class Denoiser(torch.nn.Module):
         common = dict(n_sub=plan.n_sub, weights=plan.weights, mask_scalars=plan.mask_scalars, masks=plan.masks,
                       guidance=self.guidance_scale(**kwargs), pred_type=pred, sigma_hat=sig,
                       v_c_eps=float(-sig_t / (sig_t ** 2 + 1) ** 0.5), v_c_x_div=float(sig_t ** 2 + 1))
-        clip = None
+        clip = scaled_in = None
         if kwargs.get("scaled_clip", kwargs.get("dynamic_scale_clip", False)):
             # Dynamic scale clip (denoiser.py:499-512): the scaled guidance term s * sum_e_t is thresholded before it is
             # added to e_u.  The reference runs np.percentile on a CPU copy every step; here a combine-only pass writes
             # the term, cpd_threshold finds the per-image bound on the device and the fused step clamps with it.
             alg = threshold_alg(kwargs.get("scaled_clip_alg", "dynamic_thresholding"))
             thr = kwargs.get("scaled_clip_threshold", kwargs.get("dynamic_scale_clip_threshold", 99.5))
-            scaled = torch.empty_like(x)
-            clip = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
-            ops.sampler_step(eps, x, sampler=CPD_DENOISE_ONLY, scaled_out=scaled, **common)
-            ops.threshold(scaled, clip, alg=alg, threshold=float(thr), clamp_inplace=False)
-        ops.sampler_step(eps, x, clip_scaled=clip, **common, **step)
+            if alg is not None:
+                scaled = torch.empty_like(x)
+                bound = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+                ops.sampler_step(eps, x, sampler=CPD_DENOISE_ONLY, scaled_out=scaled, **common)
+                if alg in _CLAMP_ALGS:
+                    ops.threshold(scaled, bound, alg=alg, threshold=float(thr), clamp_inplace=False)
+                    clip = bound
+                else:  # not a clamp: rewrite the term and feed it back
+                    ops.threshold_ex(scaled, bound, alg=alg, threshold=float(thr))
+                    scaled_in = scaled
+        ops.sampler_step(eps, x, clip_scaled=clip, scaled_in=scaled_in, **common, **step)
         return x
 
     @torch.no_grad()

@@ -85,12 +85,10 @@ class KDiffusionSampler:
         s = max(percentile(|x|), 1) per image, all on the device (the reference goes through np.percentile on the CPU)."""
         if not kwargs.get("clip_sample", False):
             return
-        from .. import ops
-        from .extension.denoiser import threshold_alg
-        alg = threshold_alg(kwargs.get("clip_sample_alg", "dynamic_thresholding"))
+        from .extension.denoiser import apply_threshold
         if getattr(self, "_clip_bound", None) is None or self._clip_bound.numel() < x.shape[0] or self._clip_bound.device != x.device:
             self._clip_bound = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
-        ops.threshold(x, self._clip_bound, alg=alg, threshold=float(kwargs.get("clip_sample_thresh", 90)), clamp_inplace=True)
+        apply_threshold(x, self._clip_bound, kwargs.get("clip_sample_alg", "dynamic_thresholding"), kwargs.get("clip_sample_thresh", 90))
 
     def _callback(self, callback, x_before, i, sigma, denoised, sigma_hat=None):
         if callback is not None:

@@ -99,6 +99,9 @@ typedef struct {
                                (denoiser.py:510-515, scaled_clip) */
   float* scaled_out;        /* optional [n_images][L] fp32 copy of half(s * sum_e_t) BEFORE clamping (input of the
                                percentile pass); with sampler = CPD_DENOISE_ONLY nothing else needs to be written */
+  const float* scaled_in;   /* optional [n_images][L]: the scaled guidance term already processed by a thresholding
+                               extension that is not a clamp (cpd_threshold_ex on a scaled_out copy); replaces
+                               s * sum_e_t in e_t = e_u + scaled (denoiser.py:510-515) */
 } cpd_step_params;
 
 cpd_status cpd_sampler_step(const cpd_step_params* p, void* stream);
@@ -122,6 +125,36 @@ cpd_status cpd_add_noise(float* x, const float* noise, float noise_mul, float sc
  */
 enum { CPD_THRESH_DYNAMIC = 0, CPD_THRESH_STATIC = 1 };
 cpd_status cpd_threshold(float* x, int n_images, int L, int alg, float threshold, int clamp_inplace, float* bound, void* stream);
+
+/*
+ * The other runnable thresholding extensions of samplers/extension/threshold.py, in place on x [n_images][channels][hw]
+ * (fp32 values; the result is rounded through fp16 because the reference returns x.half()).  One image = one independent
+ * trajectory (x.max() / x.min() / the quantile are per image; identical to the reference at its batch size of 1).
+ *   CPD_THRESH_DYNANORMIC            "dynanormic_thresholding" (:87-116): s = max(torch.quantile(|x|, q), 1); x = clamp(x, -s, s) / s
+ *   CPD_THRESH_SCALED_DYNAMIC_PERC   "scaled_dynamic_perc_thresholding" (:118-146): y = 2 (x - min) / (max - min) - 1;
+ *                                    s = max(np.percentile(|y|, threshold), 1); clamp; x = (max - min) (y + 1) / 2 + min
+ *   CPD_THRESH_RENORM                "renorm_thresholding" (:148-180): the same with torch.quantile
+ *   CPD_THRESH_SCALED_NORM           "scaled_norm_thresholding" (:207-237): thr = fl32(threshold / 100) * max;
+ *                                    s = max(sqrt(mean(y^2)), thr); y *= thr / s; unscale
+ *   CPD_THRESH_SPATIAL_NORM          "spatial_norm_thresholding" (:239-254): per pixel s = max(sqrt(mean_c x^2), threshold); x *= threshold / s
+ *   CPD_THRESH_SCALED_SPATIAL_NORM   "scaled_spatial_norm_thresholding" (:256-286): min-max rescaled, thr as in SCALED_NORM
+ * ("norm_thresholding", :182-205, reads an undefined x_max and cannot run in the reference.)
+ * threshold is the reference's Python float (a double): quantiles accept 0..1 or 1..100 (divided by 100 like :100-101).
+ * bound [n_images] receives the per-image s (the maximum over pixels for the spatial variants).
+ * The quantile variants are bit-exact against torch.quantile / np.percentile on the CPU.  The RMS variants agree to one
+ * fp16 ulp on rare rounding-boundary elements: the device uses the IEEE sqrt where torch's CPU sqrt goes through MKL VML
+ * (below 1 ulp, not correctly rounded), and SCALED_NORM's per-image mean is an fp64 fixed-order sum (the eager fp32
+ * summation order is not a contract).
+ */
+enum {
+  CPD_THRESH_DYNANORMIC = 2,
+  CPD_THRESH_SCALED_DYNAMIC_PERC = 3,
+  CPD_THRESH_RENORM = 4,
+  CPD_THRESH_SCALED_NORM = 5,
+  CPD_THRESH_SPATIAL_NORM = 6,
+  CPD_THRESH_SCALED_SPATIAL_NORM = 7
+};
+cpd_status cpd_threshold_ex(float* x, int n_images, int channels, int hw, int alg, double threshold, float* bound, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * UNet building blocks (all activations NHWC bf16 = row-major [pixels, channels]).  The Python host

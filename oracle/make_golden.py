@@ -215,6 +215,42 @@ def reference_vae(ref_shim):
     return {"z": z.numpy(), "image": img.numpy()}
 
 
+THRESHOLD_CASES = (("static_thresholding", 0.8), ("dynamic_thresholding", 99.0), ("dynamic_thresholding", 85.5),
+                   ("dynanormic_thresholding", 99.0), ("dynanormic_thresholding", 0.855),
+                   ("scaled_dynamic_perc_thresholding", 99.0), ("scaled_dynamic_perc_thresholding", 85.5),
+                   ("renorm_thresholding", 99.66), ("renorm_thresholding", 70.0),
+                   ("scaled_norm_thresholding", 60.0), ("scaled_norm_thresholding", 20.0),
+                   ("spatial_norm_thresholding", 1.5), ("spatial_norm_thresholding", 0.6),
+                   ("scaled_spatial_norm_thresholding", 60.0), ("scaled_spatial_norm_thresholding", 25.0))
+
+
+def threshold_inputs():
+    g = torch.Generator().manual_seed(77)
+    return [torch.randn(1, 4, 16, 16, generator=g) * 2.5, torch.randn(1, 4, 32, 24, generator=g) * 0.7 + 0.3,
+            torch.randn(1, 4, 64, 64, generator=g) * 1.3 - 0.2]
+
+
+def reference_thresholds(ref_shim):
+    """tests/golden/ref_threshold.npz: every runnable registered extension of samplers/extension/threshold.py called the
+    way denoiser.py:511-512 calls it (create(name)(x, threshold=t)) on seeded single-image inputs."""
+    from cpd.samplers.extension.registry import create
+    import cpd.samplers.extension.threshold  # noqa: F401  (registers the classes)
+
+    out = {}
+    for j, x in enumerate(threshold_inputs()):
+        out[f"x{j}"] = x.numpy()
+        for k, (name, thr) in enumerate(THRESHOLD_CASES):
+            y = create(name)(x.clone(), threshold=thr)
+            assert y.dtype == torch.float16
+            out[f"y{j}_{k}"] = y.numpy()  # fp16
+    try:
+        create("norm_thresholding")(threshold_inputs()[0], threshold=50.0)
+        raise SystemExit("norm_thresholding unexpectedly runs")
+    except NameError as e:
+        print("norm_thresholding:", e)
+    return out
+
+
 def main():
     sys.path.insert(0, os.path.dirname(HERE))
     from oracle import ref_shim
@@ -223,16 +259,20 @@ def main():
     import cpd.scheduler.k as K
 
     os.makedirs(GOLD, exist_ok=True)
-    if not any(f in sys.argv for f in ("--more-only", "--vae-only", "--churn-only")):
+    only = [f for f in sys.argv[1:] if f.endswith("-only")]
+    want = lambda flag: not only or flag in only
+    if not only:
         with open(os.path.join(GOLD, "schedule_kat.json"), "w") as f:
             json.dump(schedule_kats(K), f, indent=1)
-    if not any(f in sys.argv for f in ("--more-only", "--vae-only", "--churn-only")):
         np.savez_compressed(os.path.join(GOLD, "ref_sampling.npz"), **reference_sampling(ref_shim))
-    if "--vae-only" not in sys.argv and "--churn-only" not in sys.argv:
+    if want("--more-only"):
         np.savez_compressed(os.path.join(GOLD, "ref_sampling2.npz"), **reference_sampling_more(ref_shim))
-    if "--churn-only" not in sys.argv:
+    if want("--vae-only"):
         np.savez_compressed(os.path.join(GOLD, "ref_vae.npz"), **reference_vae(ref_shim))
-    np.savez_compressed(os.path.join(GOLD, "ref_sampling3.npz"), **reference_sampling_churn(ref_shim))
+    if want("--churn-only"):
+        np.savez_compressed(os.path.join(GOLD, "ref_sampling3.npz"), **reference_sampling_churn(ref_shim))
+    if want("--threshold-only"):
+        np.savez_compressed(os.path.join(GOLD, "ref_threshold.npz"), **reference_thresholds(ref_shim))
     print("golden fixtures written to", GOLD)
 
 

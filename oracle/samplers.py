@@ -16,17 +16,69 @@ import torch
 from .denoiser import append_dims
 
 
+def _minmax_scale(x):
+    """threshold.py:131-133 (and :160-163, :220-223, :269-272): global min-max rescaling to [-1, 1]."""
+    x_max, x_min = x.max(), x.min()
+    y = (x - x_min) / (x_max - x_min)
+    return 2 * y - 1., x_max, x_min
+
+
+def _minmax_unscale(y, x_max, x_min):
+    """threshold.py:144-145."""
+    y = (y + 1) / 2
+    return (x_max - x_min) * y + x_min
+
+
 def threshold_apply(x, alg, threshold):
-    """threshold.py:47-63 (static) / :65-88 (dynamic): returns fp32 values rounded through fp16 (D10)."""
+    """The registered thresholding extensions of threshold.py:7-286 on x: [B, C, h, w]; returns fp32 values rounded through
+    fp16 (D10: the reference returns x.half()).  "norm_thresholding" (:182-205) reads an undefined x_max (NameError in the
+    reference, D12) and is not restated.  Callers pass one image at a time (D7), so x.max() / x.min() / np.max over the
+    per-image percentiles are per image."""
     x = x.float().clone()
-    if alg == "static_thresholding":
-        s = threshold
-    elif alg == "dynamic_thresholding":
-        s = np.percentile(np.abs(x.cpu()), threshold, axis=tuple(range(1, x.ndim)))  # threshold.py:74-78
-        s = np.max(np.append(s, 1.0))  # :80
+    if alg == "none":  # :7-45
+        return x
+    if alg == "static_thresholding":  # :47-62
+        torch.clamp_(x, -1 * threshold, threshold)
+    elif alg == "dynamic_thresholding":  # :63-85
+        s = np.percentile(np.abs(x.cpu()), threshold, axis=tuple(range(1, x.ndim)))
+        s = np.max(np.append(s, 1.0))
+        torch.clamp_(x, -1 * s, s)
+    elif alg == "dynanormic_thresholding":  # :87-116
+        q = threshold / 100 if 1 < threshold <= 100 else threshold
+        s = torch.quantile(torch.abs(x).reshape((x.shape[0], -1)), q, dim=1)
+        s = torch.maximum(s, torch.ones_like(s))[(...,) + (None,) * (x.ndim - 1)]
+        x = torch.clamp(x, -s, s)
+        x = x / s
+    elif alg == "scaled_dynamic_perc_thresholding":  # :118-146
+        x, x_max, x_min = _minmax_scale(x)
+        s = np.percentile(np.abs(x.cpu()), threshold, axis=tuple(range(1, x.ndim)))
+        s = np.max(np.append(s, 1.0))
+        torch.clamp_(x, -1 * s, s)
+        x = _minmax_unscale(x, x_max, x_min)
+    elif alg == "renorm_thresholding":  # :148-180
+        x, x_max, x_min = _minmax_scale(x)
+        q = threshold / 100 if 1 < threshold <= 100 else threshold
+        s = torch.quantile(x.flatten(1).abs(), q, dim=-1)
+        s.clamp_(min=1.0)
+        torch.clamp_(x, -1 * s, s)  # broadcasts [B] against the last axis in the reference: only valid for B = 1 (D7)
+        x = _minmax_unscale(x, x_max, x_min)
+    elif alg == "scaled_norm_thresholding":  # :207-237
+        x, x_max, x_min = _minmax_scale(x)
+        thr = (threshold / 100) * x_max
+        s = x.pow(2).flatten(1).mean(1).sqrt().clamp(min=thr)
+        x = x * (thr / s)
+        x = _minmax_unscale(x, x_max, x_min)
+    elif alg == "spatial_norm_thresholding":  # :239-254
+        s = x.pow(2).mean(1, keepdim=True).sqrt().clamp(min=threshold)
+        x = x * (threshold / s)
+    elif alg == "scaled_spatial_norm_thresholding":  # :256-286
+        x, x_max, x_min = _minmax_scale(x)
+        thr = (threshold / 100) * x_max
+        s = x.pow(2).mean(1, keepdim=True).sqrt().clamp(min=thr)
+        x = x * (thr / s)
+        x = _minmax_unscale(x, x_max, x_min)
     else:
         raise NotImplementedError(alg)
-    torch.clamp_(x, -1 * s, s)
     return x.half().float()
 
 

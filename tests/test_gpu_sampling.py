@@ -542,6 +542,95 @@ def test_clip_sample_on_device_vs_oracle(cpd, name):
     assert torch.equal(out.cpu(), ref)
 
 
+_EXACT_THRESH = ("static_thresholding", "dynamic_thresholding", "dynanormic_thresholding", "scaled_dynamic_perc_thresholding",
+                 "renorm_thresholding")
+
+
+def _assert_thresholded(out, ref, name, what):
+    """Bit-exact for the quantile / clamp variants.  The RMS ("norm") variants take a square root: torch's CPU sqrt goes
+    through MKL VML (high-accuracy mode: below 1 ulp but NOT correctly rounded, e.g. sqrt(8.39655590057373f)), the device
+    uses the IEEE sqrt, and scaled_norm's per-image mean is an fp64 fixed-order sum there - so those are held to one fp16
+    ulp on the rare elements that sit on a rounding boundary."""
+    if name in _EXACT_THRESH:
+        assert torch.equal(out, ref), (what, float((out - ref).abs().max()))
+    else:
+        err = (out - ref).abs()
+        assert float((err / ref.abs().clamp_min(1e-3)).max()) <= 2.0 ** -10, what
+        assert float((err > 0).float().mean()) < 0.02, what
+
+
+def test_thresholding_extensions_vs_reference_golden(cpd, golden_dir):
+    """SURVEY.md 8-f row 1, the remaining registered variants (threshold.py:87-286) on the device against the outputs of
+    the reference's own classes (tests/golden/ref_threshold.npz)."""
+    from complex_prompt_diffusion_b200.samplers.extension.denoiser import apply_threshold
+    from oracle.make_golden import THRESHOLD_CASES
+    g = np.load(os.path.join(golden_dir, "ref_threshold.npz"))
+    for j in range(3):
+        x = torch.from_numpy(g[f"x{j}"])
+        for k, (name, thr) in enumerate(THRESHOLD_CASES):
+            xd = x.to(DEV).clone()
+            bound = torch.zeros(1, device=DEV)
+            apply_threshold(xd, bound, name, thr)
+            torch.cuda.synchronize()
+            _assert_thresholded(xd.cpu(), torch.from_numpy(g[f"y{j}_{k}"]).float(), name, (j, name, thr))
+    with pytest.raises(NotImplementedError):
+        apply_threshold(xd, bound, "norm_thresholding", 50.0)
+
+
+@pytest.mark.parametrize("shape", [(3, 4, 64, 64), (2, 4, 128, 128), (5, 4, 24, 40)])
+def test_thresholding_extensions_batched_vs_oracle(cpd, shape):
+    """Images are independent (one CTA each): a batch equals the oracle run image by image, at SD-1.5 / SDXL latent sizes."""
+    from complex_prompt_diffusion_b200.samplers.extension.denoiser import apply_threshold
+    from oracle.make_golden import THRESHOLD_CASES
+    from oracle.samplers import threshold_apply
+    g = torch.Generator().manual_seed(shape[2])
+    x = torch.randn(*shape, generator=g) * torch.tensor([0.5, 2.0, 1.0, 3.0, 0.8])[:shape[0]].view(-1, 1, 1, 1) + 0.1
+    for name, thr in THRESHOLD_CASES:
+        xd = x.to(DEV).clone()
+        bound = torch.zeros(shape[0], device=DEV)
+        apply_threshold(xd, bound, name, thr)
+        torch.cuda.synchronize()
+        ref = torch.cat([threshold_apply(x[b:b + 1], name, thr) for b in range(shape[0])])
+        _assert_thresholded(xd.cpu(), ref, name, (shape, name, thr))
+
+
+@pytest.mark.parametrize("alg,thr", [("renorm_thresholding", 97.0), ("dynanormic_thresholding", 99.0),
+                                     ("scaled_dynamic_perc_thresholding", 95.0), ("scaled_spatial_norm_thresholding", 40.0),
+                                     ("spatial_norm_thresholding", 1.2)])
+def test_scaled_clip_and_clip_sample_with_other_extensions_vs_oracle(cpd, alg, thr):
+    """The non-clamp extensions inside the loop: scaled_clip_alg rewrites s * sum_e_t (denoiser.py:510-512; DENOISE_ONLY pass
+    -> cpd_threshold_ex -> scaled_in of the fused step) and clip_sample_alg rewrites x after the update; bit-exact vs oracle."""
+    from complex_prompt_diffusion_b200 import samplers
+    from oracle.denoiser import OracleDenoiser
+    from oracle import samplers as OS
+    g = torch.Generator().manual_seed(21)
+    B, hw, steps, D = 2, 16, 4, 64
+    uc = torch.randn(1, 77, D, generator=g)
+    embs = [torch.randn(1, 77, D, generator=g) for _ in range(2)]
+    c = {"and": [(1.0, embs[0], None, 1)], "not": [(0.5, embs[1], None, 1)]}
+    x_T = torch.randn(B, 4, hw, hw, generator=g)
+    outs = [(torch.randn(B, 1, 4, hw, hw, generator=g) + 0.3 * torch.randn(B, 3, 4, hw, hw, generator=g)).reshape(B * 3, 4, hw, hw)
+            for _ in range(steps)]
+    kw = dict(conditioning=c, unconditional_conditioning=uc, unconditional_guidance_scale=7.5, scheduler="karras",
+              clip_sample=True, clip_sample_alg=alg, clip_sample_thresh=thr, scaled_clip=True, scaled_clip_alg=alg,
+              scaled_clip_threshold=thr)
+    for name in ("Euler", "DPM++ 2m"):
+        finals = []
+        for b in range(B):
+            unet = ReplayUNet([o.view(B, 3, 4, hw, hw)[b] for o in outs], torch.float32, "cpu")
+            finals.append(OS.sample(OracleDenoiser(unet, dtype=torch.float32), name, steps, x_T[b:b + 1].clone(), **dict(kw)))
+        ref = torch.cat(finals)
+        unet = ReplayUNet(outs, torch.float32, DEV)
+        wrapper = samplers.make({"name": name, "args": {}}, {"model": {"unet": unet}})
+        out = wrapper.sampler.sample(steps=steps, batch_size=B, shape=[4, hw, hw], x_T=x_T.clone(), **dict(kw))
+        torch.cuda.synchronize()
+        assert torch.isfinite(ref).all()
+        if alg in _EXACT_THRESH:
+            assert torch.equal(out.cpu(), ref), (name, alg, float((out.cpu() - ref).abs().max()))
+        else:  # sqrt rounding of the CPU library (see _assert_thresholded): fp16-ulp flips propagate through the steps
+            assert rel(out.cpu(), ref) <= 2e-3, (name, alg)
+
+
 def test_config5_frame_sequence_chain_vs_oracle(cpd):
     """BASELINE.json configs[4] at a CPU-checkable size: a frame sequence in independent segments; inside a segment frame i
     is an img2img sample (decode=True, denoising_strength, truncated schedule k_diffusion.py:64-70) started from frame i-1,

@@ -237,3 +237,18 @@ def test_oracle_stochastic_churn_bit_exact_on_replayed_unet(golden_dir, name, sc
                     unconditional_guidance_scale=float(z["guidance"]), scheduler=sched, pred_type=pred, **extra)
     assert torch.equal(torch.stack(dens), torch.from_numpy(z3[key + "|denoised"]))
     assert torch.equal(out, torch.from_numpy(z3[key + "|final"]))
+
+
+def test_oracle_thresholding_extensions_bit_exact_vs_reference(golden_dir):
+    """Every runnable registered extension of samplers/extension/threshold.py (oracle/make_golden.py --threshold-only ran
+    the reference's own classes): the restatement reproduces the reference's fp16 output bit for bit."""
+    from oracle.make_golden import THRESHOLD_CASES
+    from oracle.samplers import threshold_apply
+    g = np.load(os.path.join(golden_dir, "ref_threshold.npz"))
+    for j in range(3):
+        x = torch.from_numpy(g[f"x{j}"])
+        for k, (name, thr) in enumerate(THRESHOLD_CASES):
+            y = threshold_apply(x, name, thr)
+            assert torch.equal(y, torch.from_numpy(g[f"y{j}_{k}"]).float()), (j, name, thr)
+    with pytest.raises(NotImplementedError):
+        threshold_apply(x, "norm_thresholding", 50.0)  # D12: NameError in the reference

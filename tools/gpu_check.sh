@@ -8,7 +8,7 @@ if [ ${#groups[@]} -eq 0 ]; then groups=(step gemm conv attn misc unet e2e); fi
 rc=0
 for g in "${groups[@]}"; do
   case $g in
-    step) sel="tests/test_gpu_sampling.py -k 'fused_loop or denoiser_forward or unsupported or more_samplers or threshold or clip_sample or churn'";;
+    step) sel="tests/test_gpu_sampling.py -k 'fused_loop or denoiser_forward or unsupported or more_samplers or threshold or clip or churn'";;
     gemm) sel="tests/test_gpu_ops.py -k 'gemm or fp16_activations'";;
     conv) sel="tests/test_gpu_ops.py -k 'conv3x3 or conv1x1'";;
     attn) sel="tests/test_gpu_ops.py -k 'attention'";;

@@ -237,7 +237,8 @@ extern "C" cpd_status cpd_add_noise(float* x, const float* noise, float noise_mu
 extern "C" cpd_status cpd_sampler_step(const cpd_step_params* p, void* stream) {
   CPD_REQUIRE(p != nullptr, "cpd_sampler_step: null params");
   CPD_REQUIRE(p->eps && p->x, "cpd_sampler_step: eps and x must be non-null");
-  CPD_REQUIRE(p->n_sub >= 1 && p->n_sub <= CPD_MAX_SUBPROMPTS, "cpd_sampler_step: n_sub=%d out of range [1,%d]", p->n_sub,
+  // n_sub = 0: eps holds one row per image that already IS e_t (after a score corrector rewrote it, denoiser.py:517-518)
+  CPD_REQUIRE(p->n_sub >= 0 && p->n_sub <= CPD_MAX_SUBPROMPTS, "cpd_sampler_step: n_sub=%d out of range [0,%d]", p->n_sub,
               CPD_MAX_SUBPROMPTS);
   CPD_REQUIRE(p->hw > 0 && p->hw % 4 == 0, "cpd_sampler_step: hw=%d must be a positive multiple of 4", p->hw);
   CPD_REQUIRE(p->n_images >= 0, "cpd_sampler_step: n_images=%d", p->n_images);

@@ -81,7 +81,7 @@ def sampler_step(eps, x, *, n_sub, weights, mask_scalars, masks, guidance, sampl
     R = 1 + n_sub
     if eps.numel() != n_images * R * L:
         raise RuntimeError(f"eps has {eps.numel()} elements, expected {n_images}*{R}*{L}")
-    if n_sub < 1 or n_sub > CPD_MAX_SUBPROMPTS:
+    if n_sub < 0 or n_sub > CPD_MAX_SUBPROMPTS:  # 0: eps already is e_t, one row per image
         raise RuntimeError(f"n_sub={n_sub} out of range")
     p = StepParams()
     p.eps = eps.data_ptr()

@@ -23,7 +23,7 @@ from ..._lib import (CPD_DENOISE_ONLY, CPD_DPMPP_2M, CPD_EULER, CPD_EULER_ANCEST
                      CPD_THRESH_SCALED_NORM, CPD_THRESH_SCALED_SPATIAL_NORM, CPD_THRESH_SPATIAL_NORM, CPD_THRESH_STATIC)
 from ...scheduler.discrete import SigmaScheduler
 
-_UNSUPPORTED_TRUTHY = ("attn_guide", "return_attn", "clip_guidance", "score_corrector", "unconditional_guidance_blur", "depth_mask")
+_UNSUPPORTED_TRUTHY = ("attn_guide", "return_attn", "clip_guidance", "unconditional_guidance_blur", "depth_mask")
 
 # Thresholding extensions, all on the device (registered names of samplers/extension/threshold.py).  The first two are
 # clamps (the bound feeds the fused step directly); the others rewrite the tensor (cpd_threshold_ex).
@@ -254,6 +254,23 @@ class Denoiser(torch.nn.Module):
                 else:  # not a clamp: rewrite the term and feed it back
                     ops.threshold_ex(scaled, bound, alg=alg, threshold=float(thr))
                     scaled_in = scaled
+        corrector = kwargs.get("score_corrector", None)
+        if corrector is not None:
+            # denoiser.py:517-518: e_t = score_corrector.modify_score(e_t, x, t, c, **corrector_kwargs).  A combine-only
+            # pass materialises e_t, the corrector rewrites it (the registered extensions do so on the device,
+            # extension/threshold.py; any object with the reference's modify_score signature works), and the update runs
+            # on the rewritten row (n_sub = 0).
+            e_t = torch.empty_like(x)
+            ops.sampler_step(eps, x, sampler=CPD_DENOISE_ONLY, eps_out=e_t, clip_scaled=clip, scaled_in=scaled_in, **common)
+            ck = dict(kwargs.get("corrector_kwargs", None) or {})
+            ck["verbose"] = kwargs.get("verbose", False)  # :505
+            e_t = corrector.modify_score(e_t, x.clone(), self.scheduler.sigma_to_t(sig_t), kwargs.get("conditioning"), **ck)
+            if tuple(e_t.shape) != tuple(x.shape):
+                raise ValueError(f"score_corrector returned shape {tuple(e_t.shape)}, expected {tuple(x.shape)}")
+            e_t = e_t.to(x.device, torch.float32).contiguous()
+            single = dict(common, n_sub=0, weights=(), mask_scalars=(), masks=None)
+            ops.sampler_step(e_t, x, **single, **step)
+            return x
         ops.sampler_step(eps, x, clip_scaled=clip, scaled_in=scaled_in, **common, **step)
         return x
 

@@ -46,7 +46,8 @@ enum { CPD_PRED_EPSILON = 0, CPD_PRED_VELOCITY = 1 };
  * (denoised), and the update of euler.py:49-54 / euler.py:85-92 / dpmpp.py:42-54.
  *
  * eps holds the UNet outputs for `n_images` images x (1 + n_sub) rows x L elements
- * (L = 4 * hw); row 0 of each image is the unconditional row.  Element (b, r, i) lives at
+ * (L = 4 * hw); row 0 of each image is the unconditional row (n_sub = 0: the single row already is e_t, e.g. after a score
+ * corrector rewrote it, denoiser.py:517-518; the combine is skipped).  Element (b, r, i) lives at
  * eps + (b * eps_image_stride + r * eps_row_stride + i) elements.
  * All scalars are the fp32 values the reference computes on 0-dim tensors (host-side, see
  * complex_prompt_diffusion_b200/samplers/k_diffusion.py).

@@ -104,7 +104,13 @@ class OracleDenoiser:
             from .samplers import threshold_apply
             thr = kwargs.get("scaled_clip_threshold", kwargs.get("dynamic_scale_clip_threshold", 99.5))
             scaled_e_t = threshold_apply(scaled_e_t, kwargs.get("scaled_clip_alg", "dynamic_thresholding"), thr).half()
-        return e_t_uncond + scaled_e_t  # :515
+        e_t = e_t_uncond + scaled_e_t  # :515
+        corrector = kwargs.get("score_corrector", None)
+        if corrector is not None:  # :517-518
+            ck = dict(kwargs.get("corrector_kwargs", None) or {})
+            ck["verbose"] = kwargs.get("verbose", False)  # :505
+            e_t = corrector.modify_score(e_t, x, self.scheduler.sigma_to_t(sigma), c, **ck)
+        return e_t
 
     def __call__(self, x, sigma, **kwargs):
         """denoiser.py:528-544.  Returns the denoised sample (gamma = 0)."""

@@ -165,11 +165,17 @@ def _run_cases(ref_shim, unet, out, c, uc, x_T, hw, steps, cases):
 
         torch.randn_like = rec_randn_like
         torch.manual_seed(77)
+        call_extra = dict(extra)
+        if isinstance(call_extra.get("score_corrector"), tuple):  # (registered name, threshold_x, threshold_e): manager.py:84-90
+            from cpd.samplers.extension.registry import create
+            import cpd.samplers.extension.threshold  # noqa: F401
+            nm, tx, te = call_extra["score_corrector"]
+            call_extra["score_corrector"] = create(nm, threshold_x=tx, threshold_e=te)
         try:
             res = wrapper.sampler.sample(steps=steps, batch_size=1, shape=[4, hw, hw], x_T=x_T.clone(), conditioning=c,
                                          unconditional_conditioning=uc, unconditional_guidance_scale=7.5,
                                          scheduler=sched, device="cpu", silent=True, pred_type=pred,
-                                         callback=lambda d: dens.append(d["eps"].clone()), **extra)
+                                         callback=lambda d: dens.append(d["eps"].clone()), **call_extra)
         finally:
             torch.randn_like = real_randn_like
             unet.forward = orig_forward
@@ -200,6 +206,28 @@ def reference_sampling_churn(ref_shim):
     unet.eval()
     uc, embs, mask, c, x_T = make_case_inputs(cfg, hw)
     return _run_cases(ref_shim, unet, {}, c, uc, x_T, hw, steps, CHURN_CASES)
+
+
+CORRECTOR_CASES = (("Euler", "karras", "epsilon", {"score_corrector": ("static_thresholding", 1.5, 0.9)}),
+                   ("DPM++ 2m", "karras", "epsilon", {"score_corrector": ("dynamic_thresholding", 95.0, 97.0)}),
+                   ("Euler Ancestral", "karras", "epsilon", {"score_corrector": ("renorm_thresholding", None, 96.0)}),
+                   ("Huen", "karras", "epsilon", {"score_corrector": ("scaled_dynamic_perc_thresholding", 90.0, 95.0),
+                                                  "scaled_clip": True, "scaled_clip_alg": "dynanormic_thresholding",
+                                                  "scaled_clip_threshold": 99.0}))
+
+
+def reference_sampling_corrector(ref_shim):
+    """tests/golden/ref_sampling4.npz: the score_corrector hook (denoiser.py:517-518) with the registered thresholding
+    extensions built like manager.py:84-90, and a non-clamp scaled_clip_alg."""
+    from oracle.unet import UNetConfig, make_weights
+
+    cfg = UNetConfig.tiny()
+    hw, steps = 8, 6
+    unet = ref_shim.build_reference_unet(cfg)
+    unet.load_state_dict(make_weights(cfg, seed=0), strict=True)
+    unet.eval()
+    uc, embs, mask, c, x_T = make_case_inputs(cfg, hw)
+    return _run_cases(ref_shim, unet, {}, c, uc, x_T, hw, steps, CORRECTOR_CASES)
 
 
 def reference_vae(ref_shim):
@@ -271,6 +299,8 @@ def main():
         np.savez_compressed(os.path.join(GOLD, "ref_vae.npz"), **reference_vae(ref_shim))
     if want("--churn-only"):
         np.savez_compressed(os.path.join(GOLD, "ref_sampling3.npz"), **reference_sampling_churn(ref_shim))
+    if want("--corrector-only"):
+        np.savez_compressed(os.path.join(GOLD, "ref_sampling4.npz"), **reference_sampling_corrector(ref_shim))
     if want("--threshold-only"):
         np.savez_compressed(os.path.join(GOLD, "ref_threshold.npz"), **reference_thresholds(ref_shim))
     print("golden fixtures written to", GOLD)

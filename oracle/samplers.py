@@ -82,6 +82,21 @@ def threshold_apply(x, alg, threshold):
     return x.half().float()
 
 
+class OracleScoreCorrector:
+    """threshold.py:7-45 (ScoreCorrector.modify_score) over threshold_apply.  threshold_x thresholds x and drops the result
+    (x is a clone, denoiser.py:524); threshold_e rewrites e_t and returns it as fp16 like the reference's `.half()`."""
+
+    def __init__(self, alg, threshold_x=None, threshold_e=None):
+        self.alg, self.threshold_x, self.threshold_e = alg, threshold_x, threshold_e
+
+    def modify_score(self, e_t, x, t, c, **kwargs):
+        if self.threshold_x:
+            threshold_apply(x, self.alg, self.threshold_x)  # :20-23, result unused
+        if self.threshold_e:
+            e_t = threshold_apply(e_t, self.alg, self.threshold_e).half()  # :24-27
+        return e_t
+
+
 def _churn(x, sigmas, i, model_args, noise_sampler):
     """Stochastic churn of Karras et al. Algorithm 2 as in euler.py:40-45 / huen.py:38-43 / dpm2.py:38-43: one randn_like per
     step (drawn even when gamma = 0), sigma_hat = sigma * (gamma + 1), x += eps * sqrt(sigma_hat^2 - sigma^2) when gamma > 0."""

@@ -456,15 +456,18 @@ MORE_CASES = [("Huen", "karras", "epsilon", {}), ("DPM2", "karras", "epsilon", {
                                                  "scaled_clip_threshold": 0.5})]
 
 
-@pytest.mark.parametrize("name,sched,pred,extra", MORE_CASES)
-def test_more_samplers_bit_exact_vs_reference_golden_fp32(cpd, golden_dir, name, sched, pred, extra):
-    """The two-stage / multistep samplers and the Denoiser's scale clip, fed the UNet outputs the shimmed reference
-    recorded (tests/golden/ref_sampling2.npz): every UNet input (x * c_in, t), every denoised tensor and the final latent
-    equal the reference's bit for bit."""
+def _replay_reference_run(golden_dir, fixture, name, sched, pred, extra):
+    """Feed the sampler the UNet outputs the shimmed reference recorded in tests/golden/<fixture>: every UNet input
+    (x * c_in, t), every denoised tensor and the final latent must equal the reference's bit for bit."""
     from complex_prompt_diffusion_b200 import samplers
+    from complex_prompt_diffusion_b200.samplers.extension import create
     z, c = load_case(golden_dir)
-    z2 = np.load(os.path.join(golden_dir, "ref_sampling2.npz"))
+    z2 = np.load(os.path.join(golden_dir, fixture))
     key = f"{name}|{sched}|{pred}".replace(" ", "_") + ("|" + "|".join(f"{k}={v}" for k, v in extra.items()) if extra else "")
+    extra = dict(extra)
+    if isinstance(extra.get("score_corrector"), tuple):  # built like manager.py:84-90, from this package's registry
+        nm, tx, te = extra["score_corrector"]
+        extra["score_corrector"] = create(nm, threshold_x=tx, threshold_e=te)
     unet = ReplayUNet(list(torch.from_numpy(z2[key + "|unet_out"])), torch.float32, DEV,
                       expect_x=torch.from_numpy(z2[key + "|unet_x"]), expect_t=torch.from_numpy(z2[key + "|unet_t"]))
     wrapper = samplers.make({"name": name, "args": {}}, {"model": {"unet": unet}})
@@ -481,6 +484,60 @@ def test_more_samplers_bit_exact_vs_reference_golden_fp32(cpd, golden_dir, name,
     assert unet.i == len(unet.outs), "different number of UNet evaluations than the reference"
     assert torch.equal(torch.stack(dens), torch.from_numpy(z2[key + "|denoised"])), "per-step denoised differs"
     assert torch.equal(out.cpu(), torch.from_numpy(z2[key + "|final"])), "final latent differs"
+
+
+@pytest.mark.parametrize("name,sched,pred,extra", MORE_CASES)
+def test_more_samplers_bit_exact_vs_reference_golden_fp32(cpd, golden_dir, name, sched, pred, extra):
+    """The two-stage / multistep samplers and the Denoiser's scale clip (tests/golden/ref_sampling2.npz)."""
+    _replay_reference_run(golden_dir, "ref_sampling2.npz", name, sched, pred, extra)
+
+
+CORRECTOR_CASES = [("Euler", "karras", "epsilon", {"score_corrector": ("static_thresholding", 1.5, 0.9)}),
+                   ("DPM++ 2m", "karras", "epsilon", {"score_corrector": ("dynamic_thresholding", 95.0, 97.0)}),
+                   ("Euler Ancestral", "karras", "epsilon", {"score_corrector": ("renorm_thresholding", None, 96.0)}),
+                   ("Huen", "karras", "epsilon", {"score_corrector": ("scaled_dynamic_perc_thresholding", 90.0, 95.0),
+                                                  "scaled_clip": True, "scaled_clip_alg": "dynanormic_thresholding",
+                                                  "scaled_clip_threshold": 99.0})]
+
+
+@pytest.mark.parametrize("name,sched,pred,extra", CORRECTOR_CASES)
+def test_score_corrector_bit_exact_vs_reference_golden_fp32(cpd, golden_dir, name, sched, pred, extra):
+    """The score_corrector hook (denoiser.py:517-518) with the registered thresholding extensions rewriting e_t on the
+    device, and a non-clamp scaled_clip_alg, against runs of the shimmed reference (tests/golden/ref_sampling4.npz)."""
+    _replay_reference_run(golden_dir, "ref_sampling4.npz", name, sched, pred, extra)
+
+
+def test_score_corrector_accepts_a_foreign_object(cpd):
+    """Any object with the reference's modify_score(e_t, x, t, c, **kw) works as `score_corrector` (the hook is a plugin
+    point): one that returns e_t unchanged leaves the trajectory bit-identical, one that zeroes it turns Euler into x = x."""
+    from complex_prompt_diffusion_b200 import samplers
+    g = torch.Generator().manual_seed(4)
+    hw, steps, D = 8, 3, 64
+    uc = torch.randn(1, 77, D, generator=g)
+    c = {"and": [(1.0, torch.randn(1, 77, D, generator=g), None, 1)], "not": []}
+    x_T = torch.randn(1, 4, hw, hw, generator=g)
+    outs = [torch.randn(2, 4, hw, hw, generator=g) for _ in range(steps)]
+    seen = []
+
+    class Same:
+        def modify_score(self, e_t, x, t, c, **kw):
+            seen.append((tuple(e_t.shape), float(t), kw.get("verbose")))
+            return e_t
+
+    class Zero:
+        def modify_score(self, e_t, x, t, c, **kw):
+            return torch.zeros_like(e_t).half()
+
+    def run(corr):
+        wrapper = samplers.make({"name": "Euler", "args": {}}, {"model": {"unet": ReplayUNet(list(outs), torch.float32, DEV)}})
+        return wrapper.sampler.sample(steps=steps, batch_size=1, shape=[4, hw, hw], x_T=x_T.clone(), conditioning=c,
+                                      unconditional_conditioning=uc, unconditional_guidance_scale=5.0, scheduler="karras",
+                                      score_corrector=corr).cpu()
+    base, same, zero = run(None), run(Same()), run(Zero())
+    assert torch.equal(base, same) and len(seen) == steps and seen[0][0] == (1, 4, hw, hw) and seen[0][2] is False
+    sig0 = samplers.make({"name": "Euler", "args": {}}, {"model": {"unet": ReplayUNet(list(outs), torch.float32, DEV)}}
+                         ).sampler.denoiser.scheduler.get_sigmas("karras", steps)[0]
+    assert torch.equal(zero, x_T * float(sig0))  # e_t = 0: denoised = x, d = 0, x never moves
 
 
 @pytest.mark.parametrize("n,L,q", [(1, 4 * 64 * 64, 99.5), (3, 4 * 32 * 32, 90.0), (2, 4 * 128 * 128, 97.3), (5, 64, 50.0),

@@ -252,3 +252,35 @@ def test_oracle_thresholding_extensions_bit_exact_vs_reference(golden_dir):
             assert torch.equal(y, torch.from_numpy(g[f"y{j}_{k}"]).float()), (j, name, thr)
     with pytest.raises(NotImplementedError):
         threshold_apply(x, "norm_thresholding", 50.0)  # D12: NameError in the reference
+
+
+CORRECTOR_CASES = [("Euler", "karras", "epsilon", {"score_corrector": ("static_thresholding", 1.5, 0.9)}),
+                   ("DPM++ 2m", "karras", "epsilon", {"score_corrector": ("dynamic_thresholding", 95.0, 97.0)}),
+                   ("Euler Ancestral", "karras", "epsilon", {"score_corrector": ("renorm_thresholding", None, 96.0)}),
+                   ("Huen", "karras", "epsilon", {"score_corrector": ("scaled_dynamic_perc_thresholding", 90.0, 95.0),
+                                                  "scaled_clip": True, "scaled_clip_alg": "dynanormic_thresholding",
+                                                  "scaled_clip_threshold": 99.0})]
+
+
+@pytest.mark.parametrize("name,sched,pred,extra", CORRECTOR_CASES)
+def test_oracle_score_corrector_bit_exact_on_replayed_unet(golden_dir, name, sched, pred, extra):
+    """The score_corrector hook (denoiser.py:517-518) and a non-clamp scaled_clip_alg against runs of the shimmed reference
+    with its own extension classes (tests/golden/ref_sampling4.npz)."""
+    z, c = _load_case(golden_dir)
+    z4 = np.load(os.path.join(golden_dir, "ref_sampling4.npz"))
+    key = more_key(name, sched, pred, extra)
+    extra = dict(extra)
+    nm, tx, te = extra["score_corrector"]
+    extra["score_corrector"] = OS.OracleScoreCorrector(nm, tx, te)
+    unet = _ReplayUNet(torch.from_numpy(z4[key + "|unet_out"]), torch.from_numpy(z4[key + "|unet_x"]), torch.from_numpy(z4[key + "|unet_t"]))
+    den = OracleDenoiser(unet, dtype=torch.float32)
+    noises = list(torch.from_numpy(z4[key + "|noise"])) if (key + "|noise") in z4.files else []
+    dens = []
+    out = OS.sample(den, name, int(z["steps"]), torch.from_numpy(z["x_T"]).clone(),
+                    noise_sampler=(lambda x: noises.pop(0)) if noises else None,
+                    callback=lambda d: dens.append(d["eps"].clone()),
+                    conditioning=c, unconditional_conditioning=torch.from_numpy(z["uc"]),
+                    unconditional_guidance_scale=float(z["guidance"]), scheduler=sched, pred_type=pred, **extra)
+    assert unet.i == len(unet.outs)
+    assert torch.equal(torch.stack(dens), torch.from_numpy(z4[key + "|denoised"]))
+    assert torch.equal(out, torch.from_numpy(z4[key + "|final"]))

@@ -380,6 +380,21 @@ __device__ __forceinline__ float fast_ex2(float x) {  // MUFU.EX2, no range fix-
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x on the FMA pipe (no MUFU): round-to-nearest split x = n + f, |f| <= 0.5, by the 1.5 * 2^23 magic add; degree-3
+// minimax polynomial of 2^f (max relative error 7.5e-5, a third of a half-ulp of fp16); the integer n is added to the
+// exponent field.  8 FMA-pipe instructions.  x is clamped at -125 (result ~2^-125); x <= ~100.  The softmax of the
+// attention kernels is bound by the 16-lane MUFU pipe (a warp instruction occupies it for 8 cycles) while the FMA pipe
+// idles - in theory; measured, moving exponentials here made the attention kernel slower (attention_umma4.cu,
+// cpd_attention_split), so it is an opt-in experiment (CPD_ATTN_POLY).
+__device__ __forceinline__ float poly_ex2(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = __fadd_rn(x, 12582912.0f);
+  const float f = __fsub_rn(x, __fsub_rn(t, 12582912.0f));
+  float p = fmaf(0.055171459913253784f, f, 0.2426108568906784f);
+  p = fmaf(p, f, 0.6932609677314758f);
+  p = fmaf(p, f, 0.9999281167984009f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 // Exact-erf GELU (attention.py:98-100 uses F.gelu, the erf form) with erf from Abramowitz & Stegun 7.1.26

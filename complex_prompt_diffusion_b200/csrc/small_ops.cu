@@ -198,6 +198,121 @@ __global__ void __launch_bounds__(256) conv_out_kernel(const bf16* __restrict__ 
   }
 }
 
+// Output conv, tiled (the hot form: cout = 4).  The one-warp-per-pixel kernel above re-reads its weights from shared
+// memory for every pixel (4 wavefronts per 32 FMAs: shared-memory-pipe bound, 217 us at 16 x 64 x 64 x 320) and fetches
+// every input pixel nine times through L1.  Here a block owns a strip of up to 64 output pixels of one image row:
+//   * the 3 x (strip + 2) input pixels are staged once in shared memory, TRANSPOSED to [row][channel vector][pixel] so that
+//     the 32 lanes of a warp (= 32 consecutive pixels) read 512 contiguous bytes per tap;
+//   * the weights sit in shared memory as fp32 [tap][vector][cout][8] and are read as warp-wide BROADCASTS (one wavefront),
+//     each thread reusing them for its two pixels (lane and lane + 32);
+//   * the 8 warps split the channel vectors; their partial sums meet in shared memory and 256 threads write the
+//     4 x 64 outputs (NCHW, coalesced).
+// Persistent: the fp32 weights are staged once per block.
+constexpr int CO_TP = 64;  // strip length
+template <int NW>  // warps per block: they split the channel vectors
+__global__ void __launch_bounds__(32 * NW, 1) conv_out_tiled_kernel(const bf16* __restrict__ a, int n, int h, int w, int cin,
+                                                                 const bf16* __restrict__ wt, const float* __restrict__ bias,
+                                                                 void* __restrict__ out, int out_dtype, int f16, int pp) {
+  constexpr int COUT = 4;
+  pdl_launch_dependents();
+  extern __shared__ uint8_t sh_raw[];
+  const int nvec = cin / 8;
+  float* wsm = reinterpret_cast<float*>(sh_raw);                                   // [9][nvec][COUT][8] fp32
+  float* red = wsm + 9 * nvec * COUT * 8;                                           // [NW warps][COUT][CO_TP]
+  uint4* tile = reinterpret_cast<uint4*>(red + NW * COUT * CO_TP);                   // [3][nvec][pp] 16-byte channel vectors
+  // weights: global [COUT][9][cin] bf16 -> shared [tap][vec][o][8] fp32 (independent of the previous kernel: before the wait)
+  for (int i = threadIdx.x; i < COUT * 9 * nvec; i += blockDim.x) {
+    const int v = i % nvec, tap = (i / nvec) % 9, o = i / (nvec * 9);
+    const uint4 wv = __ldg(reinterpret_cast<const uint4*>(wt + ((int64_t)o * 9 + tap) * cin + v * 8));
+    const float2 f0 = unpack_bf16x2(wv.x), f1 = unpack_bf16x2(wv.y), f2 = unpack_bf16x2(wv.z), f3 = unpack_bf16x2(wv.w);
+    float4* dst = reinterpret_cast<float4*>(wsm + (((int64_t)tap * nvec + v) * COUT + o) * 8);
+    dst[0] = make_float4(f0.x, f0.y, f1.x, f1.y);
+    dst[1] = make_float4(f2.x, f2.y, f3.x, f3.y);
+  }
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int strips = (w + CO_TP - 1) / CO_TP;
+  const int64_t tiles = (int64_t)n * h * strips;
+  for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const int sx = (int)(t % strips);
+    const int yy = (int)((t / strips) % h);
+    const int nn = (int)(t / ((int64_t)strips * h));
+    const int x0 = sx * CO_TP;
+    const int tp = min(CO_TP, w - x0);  // pixels of this strip
+    __syncthreads();                    // the previous strip's tile / partial sums are no longer read
+    // stage rows yy - 1 .. yy + 1, pixels x0 - 1 .. x0 + tp (zero outside the image) with 16-byte cp.async (zero-fill for the
+    // padding): a warp takes a pixel, its lanes the channel vectors (coalesced global reads); the transposed destination has
+    // a lane stride of pp * 16 bytes, pp odd: no bank conflicts.  All copies of a thread are in flight together (a plain
+    // load -> store loop serialised ~30 L2 round trips per strip and cost more than the arithmetic).
+    for (int pidx = warp; pidx < 3 * (tp + 2); pidx += NW) {
+      const int r = pidx / (tp + 2), px = pidx - r * (tp + 2);
+      const int iy = yy + r - 1, ix = x0 + px - 1;
+      const bool inside = iy >= 0 && iy < h && ix >= 0 && ix < w;
+      const bf16* src = inside ? a + (((int64_t)nn * h + iy) * w + ix) * cin : a;
+      for (int v = lane; v < nvec; v += 32) {
+        const uint32_t dst = smem_u32(tile + ((int64_t)r * nvec + v) * pp + px);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src + v * 8), "r"(inside ? 16 : 0) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    float acc[2][COUT];
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) acc[q][o] = 0.f;
+    const int px0 = (lane < tp) ? lane : 0;               // lanes past a short strip recompute pixel 0 (never written out)
+    const int px1 = (lane + 32 < tp) ? lane + 32 : px0;   // second pixel of this lane (a duplicate when the strip is short)
+    for (int v = warp; v < nvec; v += NW) {
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int r = tap / 3, kx = tap % 3;
+        const uint4* trow = tile + ((int64_t)r * nvec + v) * pp + kx;
+        const uint4 a0 = trow[px0], a1 = trow[px1];
+        float f0[8], f1[8];
+        {
+          const uint32_t u0[4] = {a0.x, a0.y, a0.z, a0.w}, u1[4] = {a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 g0 = unpack_act2(u0[e], f16 != 0), g1 = unpack_act2(u1[e], f16 != 0);
+            f0[2 * e] = g0.x; f0[2 * e + 1] = g0.y;
+            f1[2 * e] = g1.x; f1[2 * e + 1] = g1.y;
+          }
+        }
+        const float4* wrow = reinterpret_cast<const float4*>(wsm + ((int64_t)tap * nvec + v) * COUT * 8);
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) {
+          const float4 wa = wrow[2 * o], wb = wrow[2 * o + 1];  // same address in every lane: broadcast
+          const float wf[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            acc[0][o] = fmaf(f0[e], wf[e], acc[0][o]);
+            acc[1][o] = fmaf(f1[e], wf[e], acc[1][o]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) {
+      red[(warp * COUT + o) * CO_TP + lane] = acc[0][o];
+      red[(warp * COUT + o) * CO_TP + lane + 32] = acc[1][o];
+    }
+    __syncthreads();
+    if (threadIdx.x < COUT * CO_TP) {
+      const int o = threadIdx.x / CO_TP, px = threadIdx.x % CO_TP;  // 256 threads = COUT x CO_TP outputs
+      if (px < tp) {
+        float v = bias ? __ldg(bias + o) : 0.f;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) v += red[(k * COUT + o) * CO_TP + px];
+        const int64_t oi = (((int64_t)nn * COUT + o) * h + yy) * w + x0 + px;
+        if (out_dtype == CPD_BF16) reinterpret_cast<bf16*>(out)[oi] = __float2bfloat16_rn(v);
+        else reinterpret_cast<float*>(out)[oi] = v;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) upsample2x_kernel(const bf16* __restrict__ a, int n, int h, int w, int c, bf16* __restrict__ out) {
   pdl_launch_dependents();
   pdl_wait();
@@ -373,6 +488,36 @@ extern "C" cpd_status cpd_conv_out(const void* a, int n, int h, int w, int cin, 
   const int64_t pixels = (int64_t)n * h * w;
   const size_t shm = (size_t)cout * 9 * cin * 2;
   cudaStream_t s = (cudaStream_t)stream;
+  if (cout == 4) {  // tiled kernel when its strip (3 rows x 66 pixels x cin) and the fp32 weights fit in shared memory
+    const int tp = w < CO_TP ? w : CO_TP;
+    const int pp = (tp + 2) | 1;  // odd pixel pitch: conflict-free transposed stores
+    static int tiled = -1, nw = 16;
+    if (tiled < 0) {
+      const char* e = getenv("CPD_CONV_OUT_TILED");
+      tiled = (e && e[0] == '0') ? 0 : 1;
+      const char* e2 = getenv("CPD_CONV_OUT_WARPS");
+      if (e2 && atoi(e2) == 8) nw = 8;
+    }
+    const size_t need = (size_t)9 * (cin / 8) * 4 * 8 * 4 + (size_t)nw * 4 * CO_TP * 4 + (size_t)3 * (cin / 8) * pp * 16;
+    if (tiled && need <= 227 * 1024) {
+      static bool cfg = false;
+      if (!cfg) {
+        CPD_CUDA_CHECK(cudaFuncSetAttribute(conv_out_tiled_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CPD_CUDA_CHECK(cudaFuncSetAttribute(conv_out_tiled_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        cfg = true;
+      }
+      const int64_t tiles = (int64_t)n * h * ((w + CO_TP - 1) / CO_TP);
+      const unsigned blocks = (unsigned)(tiles < 148 ? tiles : 148);
+      if (nw == 8)
+        CPD_CUDA_CHECK(cpd_launch(conv_out_tiled_kernel<8>, dim3(blocks), dim3(256), need, s, (const bf16*)a, n, h, w, cin, (const bf16*)wt, bias,
+                                  out, out_dtype, act_fp16, pp));
+      else
+        CPD_CUDA_CHECK(cpd_launch(conv_out_tiled_kernel<16>, dim3(blocks), dim3(512), need, s, (const bf16*)a, n, h, w, cin, (const bf16*)wt, bias,
+                                  out, out_dtype, act_fp16, pp));
+      CPD_CUDA_CHECK(cudaGetLastError());
+      return CPD_OK;
+    }
+  }
   unsigned blocks = (unsigned)((pixels + 7) / 8);
   if (blocks > 148 * 8) blocks = 148 * 8;  // persistent: weights staged once per block, full occupancy (64 warps per SM)
   if (cout == 4) {

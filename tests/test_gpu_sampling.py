@@ -138,6 +138,51 @@ def test_fused_loop_bit_exact_vs_oracle_half_eps(cpd, name, dtype, pred):
     assert torch.equal(out.cpu(), ref)
 
 
+@pytest.mark.parametrize("n_images,n_sub,h,w,dtype", [(0, 3, 8, 8, torch.float32), (2, 16, 1, 4, torch.float16), (3, 16, 6, 6, torch.bfloat16),
+                                                     (1, 1, 2, 2, torch.float32), (5, 7, 8, 12, torch.float16), (2, 0, 8, 8, torch.float32),
+                                                     (1, 16, 64, 64, torch.bfloat16)])
+def test_sampler_step_edge_cases_vs_oracle_combine(cpd, n_images, n_sub, h, w, dtype):
+    """cpd_sampler_step called directly at its limits: empty batch, the maximum of 16 sub-prompts (scalar and spatial masks,
+    negative weights), the smallest latent (hw = 4), sizes that are not multiples of 8 (4-wide path with 16-bit rows), and
+    n_sub = 0 (the row already is e_t).  Reference: the oracle's fp16 combine (denoiser.py:450-460) + e_t = e_u + s * sum
+    (:514-515) + denoised (:540) + the Euler update (euler.py:49-54), bit for bit."""
+    from complex_prompt_diffusion_b200 import ops
+    from complex_prompt_diffusion_b200._lib import CPD_EULER, CPD_PRED_EPSILON
+    from oracle.denoiser import combine_fp16
+    g = torch.Generator().manual_seed(1000 * n_sub + h * w)
+    R, L = 1 + n_sub, 4 * h * w
+    eps = (torch.randn(max(n_images, 1) * R, 4, h, w, generator=g)).to(dtype)[:n_images * R]
+    x = torch.randn(n_images, 4, h, w, generator=g)
+    weights = [float(v) for v in (torch.rand(n_sub, generator=g) * 2 - 0.7)]
+    mscal = [1.0 if k % 3 else 0.5 for k in range(n_sub)]
+    masks = [(torch.rand(1, 1, h, w, generator=g) > 0.4).float() if k % 2 else None for k in range(n_sub)]
+    guidance, sigma, dt = 7.5, 3.25, -1.125
+    den = torch.full_like(x, float("nan")).to(DEV)
+    xd = x.clone().to(DEV)
+    ops.sampler_step(eps.to(DEV).contiguous(), xd, n_sub=n_sub, weights=weights, mask_scalars=mscal,
+                     masks=[None if m is None else m.reshape(-1).to(DEV).contiguous() for m in masks], guidance=guidance,
+                     sampler=CPD_EULER, pred_type=CPD_PRED_EPSILON, sigma_hat=sigma, dt=dt, denoised_out=den)
+    torch.cuda.synchronize()
+    if n_images == 0:
+        assert xd.numel() == 0
+        return
+    sig = torch.tensor([sigma]).view(1, 1, 1, 1)  # sigmas[i] * s_in through append_dims: a 4-D fp32 tensor (promotes 16-bit e_t)
+    for b in range(n_images):
+        rows = eps[b * R:(b + 1) * R]
+        e_u = rows[0:1]
+        if n_sub:
+            e_masks = [torch.tensor(mscal[k]) if masks[k] is None else masks[k] for k in range(n_sub)]
+            sum_e = combine_fp16([rows[k + 1:k + 2] for k in range(n_sub)], e_u, [torch.tensor(wk) for wk in weights], e_masks)
+            e_t = e_u + guidance * sum_e
+        else:
+            e_t = e_u
+        d_ref = x[b:b + 1] - sig * e_t
+        d = (x[b:b + 1] - d_ref) / sig
+        x_ref = x[b:b + 1] + d * torch.tensor(dt)
+        assert torch.equal(den[b:b + 1].cpu(), d_ref.float()), (b, "denoised")
+        assert torch.equal(xd[b:b + 1].cpu(), x_ref.float()), (b, "x")
+
+
 def test_denoiser_forward_matches_oracle(cpd):
     from complex_prompt_diffusion_b200.samplers.extension.denoiser import Denoiser
     from oracle.denoiser import OracleDenoiser

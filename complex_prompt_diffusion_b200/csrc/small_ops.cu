@@ -132,6 +132,84 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
   }
 }
 
+// Input conv, four pixels per thread (cin = 4, w % 4 == 0: the latent input of every UNet here).  The kernel above reads its
+// weights from shared memory once per pixel (2 x LDS.128 per 8 multiply-adds: shared-memory-pipe bound, 43 us for 42 MB of
+// output); here a thread owns FOUR horizontally adjacent pixels x 8 output channels, so every weight vector is read once
+// per four pixels and every input value once per three taps.  Same accumulation order (ky, kx, c) as above: identical bits.
+__global__ void __launch_bounds__(256) conv_in4_kernel(const float* __restrict__ x, int n, int h, int w,
+                                                       const bf16* __restrict__ wt, const float* __restrict__ bias, int cout,
+                                                       float scale, const float* __restrict__ scale_ptr, int rpi, int f16,
+                                                       bf16* __restrict__ out) {
+  constexpr int CIN = 4;
+  pdl_launch_dependents();
+  extern __shared__ uint8_t sh_raw[];
+  float* ws = reinterpret_cast<float*>(sh_raw);  // [9 * CIN][cout]
+  const int taps = 9 * CIN;
+  for (int i = threadIdx.x; i < taps * cout; i += blockDim.x) {
+    const int co = i / taps, tp = i - co * taps;  // wt is [cout][9][cin]
+    ws[tp * cout + co] = __bfloat162float(wt[i]);
+  }
+  pdl_wait();
+  __syncthreads();
+  if (scale_ptr) scale = __ldg(scale_ptr);
+  const int cvecs = cout / 8, wq = w / 4;
+  const int total = n * h * wq * cvecs;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int cv = idx % cvecs;
+    const int g = idx / cvecs;
+    const int x0 = (g % wq) * 4;
+    const int yy = (g / wq) % h;
+    const int nn = g / (wq * h);
+    float acc[4][8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float b = bias ? __ldg(bias + cv * 8 + e) : 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q][e] = b;
+    }
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = yy + ky - 1;
+      if (iy < 0 || iy >= h) continue;
+      float xs[CIN][6];  // x0 - 1 .. x0 + 4 of this input row, scaled and rounded to the model dtype
+      bool ok[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const int ix = x0 - 1 + j;
+        ok[j] = ix >= 0 && ix < w;
+#pragma unroll
+        for (int c = 0; c < CIN; ++c)
+          xs[c][j] = ok[j] ? round_act(__fmul_rn(__ldg(x + (((int64_t)nn * CIN + c) * h + iy) * w + ix), scale), f16 != 0) : 0.f;
+      }
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) {
+          const float4 w0 = *reinterpret_cast<const float4*>(ws + ((ky * 3 + kx) * CIN + c) * cout + cv * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(ws + ((ky * 3 + kx) * CIN + c) * cout + cv * 8 + 4);
+          const float wf[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (!ok[q + kx]) continue;  // the per-pixel kernel skips taps outside the image (no + 0 * w: keeps -0 / NaN behaviour)
+            const float xv = xs[c][q + kx];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[q][e] += xv * wf[e];
+          }
+        }
+      }
+    }
+    const int64_t hw = (int64_t)h * w;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 o = make_uint4(pack_act2(acc[q][0], acc[q][1], f16 != 0), pack_act2(acc[q][2], acc[q][3], f16 != 0),
+                                 pack_act2(acc[q][4], acc[q][5], f16 != 0), pack_act2(acc[q][6], acc[q][7], f16 != 0));
+      const int64_t p_in = (int64_t)yy * w + x0 + q;
+      for (int rr = 0; rr < rpi; ++rr)
+        *reinterpret_cast<uint4*>(out + (((int64_t)nn * rpi + rr) * hw + p_in) * cout + cv * 8) = o;
+    }
+  }
+}
+
 // Output conv: NHWC bf16 (cin) -> 3x3 pad 1 -> NCHW (cout <= 8).  One warp per output pixel.
 template <int COUT>
 __global__ void __launch_bounds__(256) conv_out_kernel(const bf16* __restrict__ a, int n, int h, int w, int cin,
@@ -316,16 +394,21 @@ __global__ void __launch_bounds__(32 * NW, 1) conv_out_tiled_kernel(const bf16* 
 __global__ void __launch_bounds__(256) upsample2x_kernel(const bf16* __restrict__ a, int n, int h, int w, int c, bf16* __restrict__ out) {
   pdl_launch_dependents();
   pdl_wait();
+  // one thread per INPUT channel vector: read once, written to its 2 x 2 output pixels (a thread per output vector read
+  // every input four times and spent more instructions on 64-bit index divisions than on the copy)
   const int cvecs = c / 8;
-  const int64_t total = (int64_t)n * (2 * h) * (2 * w) * cvecs;
+  const int64_t total = (int64_t)n * h * w * cvecs;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int cv = (int)(idx % cvecs);
-    const int64_t pix = idx / cvecs;
-    const int ox = (int)(pix % (2 * w));
-    const int oy = (int)((pix / (2 * w)) % (2 * h));
-    const int nn = (int)(pix / ((int64_t)4 * w * h));
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(a + (((int64_t)nn * h + oy / 2) * w + ox / 2) * c + cv * 8));
-    *reinterpret_cast<uint4*>(out + pix * c + cv * 8) = v;
+    const int64_t pix = idx / cvecs;  // (nn * h + iy) * w + ix
+    const int cv = (int)(idx - pix * cvecs);
+    const int64_t row = pix / w;      // nn * h + iy
+    const int ix = (int)(pix - row * w);
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(a + pix * c + cv * 8));
+    bf16* o = out + ((2 * row) * (2 * w) + 2 * ix) * (int64_t)c + cv * 8;  // output rows 2 * (nn * h + iy), + 1
+    *reinterpret_cast<uint4*>(o) = v;
+    *reinterpret_cast<uint4*>(o + c) = v;
+    *reinterpret_cast<uint4*>(o + (int64_t)2 * w * c) = v;
+    *reinterpret_cast<uint4*>(o + (int64_t)2 * w * c + c) = v;
   }
 }
 
@@ -471,6 +554,19 @@ extern "C" cpd_status cpd_conv_in(const float* x, int n, int cin, int h, int w, 
       cfg = true;
     }
   }
+  if (cin == 4 && w % 4 == 0 && (int64_t)n * h * w * (cout / 8) < (int64_t)1 << 31) {
+    static bool cfg4 = false;
+    if (!cfg4) {
+      CPD_CUDA_CHECK(cudaFuncSetAttribute(conv_in4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      cfg4 = true;
+    }
+    int64_t blocks4 = (total / 4 + 255) / 256;
+    if (blocks4 > 148 * 2) blocks4 = 148 * 2;
+    CPD_CUDA_CHECK(cpd_launch(conv_in4_kernel, dim3((unsigned)blocks4), dim3(256), shm, (cudaStream_t)stream, x, n, h, w, (const bf16*)wt, bias, cout, scale,
+                              scale_ptr, rows_per_image, act_fp16, (bf16*)out));
+    CPD_CUDA_CHECK(cudaGetLastError());
+    return CPD_OK;
+  }
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 2) blocks = 148 * 2;  // each block stages the 9 x cin x cout weights once: few, long-lived blocks
   CPD_CUDA_CHECK(cpd_launch(conv_in_kernel, dim3((unsigned)blocks), dim3(256), shm, (cudaStream_t)stream, x, n, cin, h, w, (const bf16*)wt, bias, cout, scale, scale_ptr,
@@ -535,9 +631,9 @@ extern "C" cpd_status cpd_conv_out(const void* a, int n, int h, int w, int cin, 
 
 extern "C" cpd_status cpd_upsample2x(const void* a, int n, int h, int w, int c, void* out, void* stream) {
   CPD_REQUIRE(a && out && n > 0 && h > 0 && w > 0 && c % 8 == 0, "cpd_upsample2x: bad arguments");
-  const int64_t total = (int64_t)n * 4 * h * w * (c / 8);
+  const int64_t total = (int64_t)n * h * w * (c / 8);
   int64_t blocks = (total + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > 148 * 8) blocks = 148 * 8;
   CPD_CUDA_CHECK(cpd_launch(upsample2x_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (const bf16*)a, n, h, w, c, (bf16*)out));
   CPD_CUDA_CHECK(cudaGetLastError());
   return CPD_OK;

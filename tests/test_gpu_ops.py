@@ -275,6 +275,28 @@ def test_conv_in_out_upsample(ops):
     assert torch.equal(up.float(), ref3)
 
 
+@pytest.mark.parametrize("n,h,w,cout,rpi,act", [(4, 64, 64, 320, 4, torch.float16), (2, 8, 12, 64, 3, torch.bfloat16), (1, 6, 6, 64, 2, torch.float16),
+                                                 (1, 128, 128, 320, 2, torch.bfloat16), (3, 5, 4, 128, 1, torch.float16)])
+def test_conv_in_vs_torch(ops, n, h, w, cout, rpi, act):
+    """cpd_conv_in (unet.py:548 on x * c_in, denoiser.py:390-391): the four-pixels-per-thread kernel (w % 4 == 0) and the per-pixel
+    one (other widths), every conditioning-row copy, against torch's conv2d on the same rounded operands."""
+    g = torch.Generator().manual_seed(h * w + cout)
+    x = torch.randn(n, 4, h, w, generator=g)
+    wt = bf(torch.randn(cout, 4, 3, 3, generator=g) / 6)
+    bias = torch.randn(cout, generator=g)
+    out = torch.full((n * rpi, h, w, cout), float("nan"), dtype=act, device=DEV)
+    ops.conv_in(x.to(DEV), wt.permute(0, 2, 3, 1).contiguous().to(DEV), bias.to(DEV), out, n=n, cin=4, h=h, w=w, cout=cout, scale=0.37,
+                rows_per_image=rpi)
+    torch.backends.cudnn.allow_tf32 = False
+    ref = F.conv2d((x * 0.37).to(act).float().to(DEV), wt.float().to(DEV), bias.to(DEV), padding=1).permute(0, 2, 3, 1)
+    torch.cuda.synchronize()
+    o5 = out.view(n, rpi, h, w, cout)
+    assert torch.isfinite(o5.float()).all()
+    for r in range(rpi):
+        assert rel(o5[:, r], ref) < (4e-3 if act == torch.bfloat16 else 5e-4)
+        assert torch.equal(o5[:, r], o5[:, 0])
+
+
 @pytest.mark.parametrize("n,h,w,cin,act,odt", [(3, 64, 64, 320, torch.float16, torch.float32), (2, 24, 40, 320, torch.bfloat16, torch.float32),
                                                  (1, 96, 96, 320, torch.float16, torch.bfloat16), (2, 8, 8, 128, torch.bfloat16, torch.float32),
                                                  (1, 70, 130, 64, torch.float16, torch.float32), (1, 128, 128, 320, torch.float16, torch.float32)])

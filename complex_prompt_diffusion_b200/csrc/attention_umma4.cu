@@ -467,8 +467,9 @@ cpd_status cpd_attention_split(const cpd_attn_params* p, void* stream) {
   const size_t shm = (size_t)q_bytes + (size_t)stages * per_stage + 512 + XCH_BYTES + 1024;
   // Share of the exponentials computed on the FMA pipe: every POLY-th pair (CPD_ATTN_POLY = 0 | 2 | 3 | 4; see poly_ex2).
   // Measured on B200 (16 x 8 x 4096^2 d40): 724 us with none, 747 / 771 / 842 us with 25 / 33 / 50 % moved - the softmax warps
-  // are bound by instruction issue and latency, not by the MUFU pipe (69 % busy), so 8 FMA-pipe instructions per exponential
-  // cost more than they free.  Default: all on MUFU; the variants stay as an opt-in experiment.
+  // are bound by the length of their own serial instruction stream per key block, not by the MUFU pipe (71 % busy; issue
+  // slots 53 %), so 8 FMA-pipe instructions per exponential cost more than they free.  Default: all on MUFU; the variants
+  // stay as an opt-in experiment.
   static int poly = -1;
   if (poly < 0) {
     const char* e = getenv("CPD_ATTN_POLY");

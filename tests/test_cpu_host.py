@@ -146,3 +146,27 @@ def test_guidance_decay_matches_oracle():
     for t_idx in (0, 3, 5, 19):
         a = Denoiser.guidance_scale(unconditional_guidance_scale=7.5, t_idx=t_idx, total_steps=21, decaying_uc_scale=True)
         assert a == float(guidance_scale(7.5, t_idx, 21, True))
+
+
+def test_extension_registry_mirrors_the_reference_names():
+    """samplers/extension/registry.py + threshold.py:7-286: the same names resolve here, with the reference's constructor
+    (threshold_x, threshold_e) and methods; nothing runs on the CPU (the product has no CPU path: it must say so)."""
+    import torch
+    from complex_prompt_diffusion_b200.samplers.extension import create, lookup, make
+    names = {"none", "static_thresholding", "dynamic_thresholding", "dynanormic_thresholding", "scaled_dynamic_perc_thresholding",
+             "renorm_thresholding", "norm_thresholding", "scaled_norm_thresholding", "spatial_norm_thresholding",
+             "scaled_spatial_norm_thresholding"}
+    assert names <= set(lookup)
+    ext = make({"name": "dynamic_thresholding", "args": {"threshold_x": None, "threshold_e": 99.0}})  # manager.py:84-90
+    assert ext.threshold_x is None and ext.threshold_e == 99.0
+    for attr in ("apply", "modify_score", "_apply", "__call__"):
+        assert callable(getattr(ext, attr))
+    x = torch.zeros(1, 4, 8, 8)
+    assert create("none")(x) is x  # the identity extension
+    assert create("dynamic_thresholding").modify_score(x, x, 0, None) is x  # no threshold_e: e_t passes through
+    with pytest.raises(RuntimeError, match="runs on the device"):
+        create("static_thresholding")(x, threshold=0.5)
+    with pytest.raises(NotImplementedError):
+        create("norm_thresholding")(x, threshold=50.0)
+    with pytest.raises(KeyError):
+        create("no_such_extension")

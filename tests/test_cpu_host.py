@@ -42,6 +42,27 @@ def test_argument_validation_without_gpu(lib_path):
     gp.c0 = 100
     assert lib.cpd_gemm_conv(ctypes.byref(gp), None) != 0
     assert b"multiples of 64" in lib.cpd_last_error()
+    # thresholding entry points: null pointers, unknown algorithms, percentiles / quantiles outside their range
+    assert lib.cpd_threshold(None, 1, 64, _lib.CPD_THRESH_DYNAMIC, 99.0, 1, None, None) != 0
+    assert b"null pointer" in lib.cpd_last_error()
+    assert lib.cpd_threshold(16, 1, 64, 9, 99.0, 1, 16, None) != 0
+    assert b"unknown algorithm" in lib.cpd_last_error()
+    assert lib.cpd_threshold(16, 1, 64, _lib.CPD_THRESH_DYNAMIC, 101.0, 1, 16, None) != 0
+    assert b"outside [0, 100]" in lib.cpd_last_error()
+    assert lib.cpd_threshold(16, 1, 66, _lib.CPD_THRESH_STATIC, 1.0, 1, 16, None) != 0
+    assert b"multiple of 4" in lib.cpd_last_error()
+    assert lib.cpd_threshold_ex(16, 1, 4, 64, _lib.CPD_THRESH_STATIC, 1.0, 16, None) != 0  # the clamp variants live in cpd_threshold
+    assert b"unknown algorithm" in lib.cpd_last_error()
+    assert lib.cpd_threshold_ex(16, 1, 4, 64, _lib.CPD_THRESH_RENORM, 250.0, 16, None) != 0
+    assert b"outside [0, 1]" in lib.cpd_last_error()
+    assert lib.cpd_threshold_ex(16, 1, 0, 64, _lib.CPD_THRESH_RENORM, 0.9, 16, None) != 0
+    p2 = _lib.StepParams()
+    p2.eps = p2.x = 16
+    p2.n_sub, p2.hw = 17, 64
+    assert lib.cpd_sampler_step(ctypes.byref(p2), None) != 0
+    assert b"out of range [0,16]" in lib.cpd_last_error()
+    assert lib.cpd_threshold(16, 0, 64, _lib.CPD_THRESH_DYNAMIC, 99.0, 1, 16, None) == 0  # empty batch: nothing launched
+    assert lib.cpd_threshold_ex(16, 0, 4, 64, _lib.CPD_THRESH_RENORM, 0.9, 16, None) == 0
 
 
 def test_registry_and_wrapper_surface():

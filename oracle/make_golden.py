@@ -279,6 +279,52 @@ def reference_thresholds(ref_shim):
     return out
 
 
+PROMPT_STRINGS = ("a cat:1.5 a dog:0.5 trees", "x: y:abc z", "plain prompt without weights", ":5 rest", "a:2", "a:2 ", "red:1e-1 blue:-0.5",
+                  "one:1 two:2 three:3 tail:", "spaces  inside:0.25  double", "", "colon at end:", "a:b:c 1:2")
+MASK_SIZES = ("half", "third", "quarter", "fourth", "fifrth", "sixth", "seventh", "eigth", "ninth", "tenth", "2", "3", "5", "7", "10")
+MASK_DIRECTIONS = ("left", "l", "west", "right", "r", "top", "t", "north", "bottom", "bot", "south")
+MASK_MINORITIES = ("valid", "v", "show", "hidden", "h", "hide")
+MASK_SHAPES = ((512, 512), (512, 768), (768, 512), (1024, 1024), (256, 320))
+
+
+def mask_styles():
+    styles = [f"{d}_{sz}_{m}" for d in ("left", "r", "top", "bot") for sz in MASK_SIZES for m in ("valid", "hidden")]
+    styles += [f"{d}_third_{m}" for d in MASK_DIRECTIONS for m in MASK_MINORITIES]  # every alias once
+    return styles + ["left", "top_third", "right_quarter", "b"]
+
+
+def reference_prompts(ref_shim):
+    """tests/golden/ref_prompts.npz: WeightedPrompt._parse_prompt (prompts.py:546-589) and
+    CompositionalPrompt._parse_mask_style (:737-856) called unbound on stub instances (they only read self.opt.H / W).
+    Every mask of the reference is constant along one axis (checked here), so the fixture keeps its profile along the other."""
+    import types
+    import cpd.embeddings.prompts as P
+
+    out = {"prompt_strings": np.array(list(PROMPT_STRINGS))}
+    parsed = [P.WeightedPrompt._parse_prompt(None, t) for t in PROMPT_STRINGS]
+    out["prompt_parsed"] = np.array(json.dumps(parsed))
+    styles, cases, lines, axes = mask_styles(), [], [], []
+    for (H, W) in MASK_SHAPES:
+        stub = types.SimpleNamespace(opt=types.SimpleNamespace(H=H, W=W))
+        for st in styles:
+            m = P.CompositionalPrompt._parse_mask_style(stub, st)
+            assert m.dtype == torch.uint8 and tuple(m.shape) == (1, H // 8, W // 8)
+            horizontal = bool((m == m[:, :1, :]).all())  # constant along rows: the profile runs along x
+            line = m[0, 0, :] if horizontal else m[0, :, 0]
+            full = line.view(1, 1, -1).expand_as(m) if horizontal else line.view(1, -1, 1).expand_as(m)
+            assert torch.equal(full, m)
+            pad = np.full(128, 255, dtype=np.uint8)
+            pad[:line.numel()] = line.numpy()
+            cases.append(f"{H}x{W}|{st}")
+            lines.append(pad)
+            axes.append(2 if horizontal else 1)
+    out["mask_cases"] = np.array(cases)
+    out["mask_lines"] = np.stack(lines)
+    out["mask_axes"] = np.array(axes, dtype=np.uint8)
+    print("prompt strings", len(parsed), "mask cases", len(cases))
+    return out
+
+
 def main():
     sys.path.insert(0, os.path.dirname(HERE))
     from oracle import ref_shim
@@ -301,6 +347,8 @@ def main():
         np.savez_compressed(os.path.join(GOLD, "ref_sampling3.npz"), **reference_sampling_churn(ref_shim))
     if want("--corrector-only"):
         np.savez_compressed(os.path.join(GOLD, "ref_sampling4.npz"), **reference_sampling_corrector(ref_shim))
+    if want("--prompts-only"):
+        np.savez_compressed(os.path.join(GOLD, "ref_prompts.npz"), **reference_prompts(ref_shim))
     if want("--threshold-only"):
         np.savez_compressed(os.path.join(GOLD, "ref_threshold.npz"), **reference_thresholds(ref_shim))
     print("golden fixtures written to", GOLD)

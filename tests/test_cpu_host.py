@@ -191,3 +191,45 @@ def test_extension_registry_mirrors_the_reference_names():
         create("norm_thresholding")(x, threshold=50.0)
     with pytest.raises(KeyError):
         create("no_such_extension")
+
+
+def test_prompt_and_mask_parsing_match_the_reference(golden_dir):
+    """WeightedPrompt._parse_prompt (prompts.py:546-589) and CompositionalPrompt._parse_mask_style
+    (:737-856) against outputs of the reference's own methods (tests/golden/ref_prompts.npz, 12 strings, 950 mask styles x
+    latent shapes incl. every alias), and the composition dict of _build_embeddings (:622-648)."""
+    import json
+    import numpy as np
+    import torch
+    from complex_prompt_diffusion_b200.embeddings import CompositionalConditioning, parse_mask_style, parse_weighted_prompt
+    g = np.load(os.path.join(golden_dir, "ref_prompts.npz"))
+    parsed = json.loads(str(g["prompt_parsed"]))
+    for text, (prompts, weights) in zip(g["prompt_strings"].tolist(), parsed):
+        got_p, got_w = parse_weighted_prompt(text)
+        assert got_p == prompts and got_w == weights, text
+    for case, line, axis in zip(g["mask_cases"].tolist(), g["mask_lines"], g["mask_axes"]):
+        shape, style = case.split("|")
+        H, W = (int(v) for v in shape.split("x"))
+        m = parse_mask_style(style, H, W)
+        assert m.dtype == torch.uint8 and tuple(m.shape) == (1, H // 8, W // 8), case
+        n = m.shape[int(axis)]
+        ref = torch.from_numpy(line[:n].copy())
+        ref = ref.view(1, 1, n).expand_as(m) if axis == 2 else ref.view(1, n, 1).expand_as(m)
+        assert torch.equal(m, ref), case
+    for bad in ("perspective",):
+        with pytest.raises(NotImplementedError):
+            parse_mask_style(bad, 512, 512)
+    for bad in ("diagonal_half", "left_1_valid", "left_half_maybe"):
+        with pytest.raises(ValueError):
+            parse_mask_style(bad, 512, 512)
+    e = [torch.randn(1, 77, 16) for _ in range(4)]
+    comp = (CompositionalConditioning(e[0], scale=1.2, height=256, width=320)
+            .add_filter(e[1], strength=0.6).add_filter(e[2], strength=-0.4).add_filter(e[3], strength=0)
+            .add_masked_filter(e[3], "left_half_valid", strength=0.8).build())
+    assert [c[0] for c in comp["and"]] == [1.2, 0.6, 0.8] and [c[0] for c in comp["not"]] == [0.4]
+    assert comp["and"][0][1] is e[0] and comp["and"][0][3] == 1 and comp["not"][0][1] is e[2]
+    assert tuple(comp["and"][2][3].shape) == (1, 1, 32, 40) and int(comp["and"][2][3].sum()) == 32 * 20
+    with pytest.raises(ValueError, match="embedder"):
+        CompositionalConditioning("a text prompt")
+    texts = []
+    comp2 = CompositionalConditioning("base", embedder=lambda t: (texts.append(t), torch.zeros(1, 77, 8))[1]).add_weighted("cat:1.5 dog:-0.5 tree")
+    assert texts == ["base", "cat", "dog", "tree"] and [c[0] for c in comp2.build()["and"]] == [1, 1.5, 1.0] and comp2.build()["not"][0][0] == 0.5

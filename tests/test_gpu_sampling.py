@@ -183,6 +183,38 @@ def test_sampler_step_edge_cases_vs_oracle_combine(cpd, n_images, n_sub, h, w, d
         assert torch.equal(xd[b:b + 1].cpu(), x_ref.float()), (b, "x")
 
 
+def test_composition_built_from_mask_styles_runs_bit_exact(cpd):
+    """SURVEY.md 8-a row A13 end to end: a composition assembled with add_filter / add_masked_filter and mask-style strings
+    (prompts.py:706-856) is consumed by the Denoiser exactly like by the oracle (spatial masks on two sub-prompts, one
+    negation), B = 2, non-square latent."""
+    from complex_prompt_diffusion_b200 import samplers
+    from complex_prompt_diffusion_b200.embeddings import CompositionalConditioning
+    from oracle.denoiser import OracleDenoiser
+    from oracle import samplers as OS
+    g = torch.Generator().manual_seed(77)
+    B, h, w, steps, D = 2, 16, 24, 4, 64
+    uc = torch.randn(1, 77, D, generator=g)
+    e = [torch.randn(1, 77, D, generator=g) for _ in range(4)]
+    c = (CompositionalConditioning(e[0], scale=1.0, height=8 * h, width=8 * w)
+         .add_masked_filter(e[1], "left_third_valid", strength=0.7)
+         .add_masked_filter(e[2], "bot_quarter_hidden", strength=-0.5)
+         .add_filter(e[3], strength=0.3).build())
+    assert len(c["and"]) == 3 and len(c["not"]) == 1 and tuple(c["and"][1][3].shape) == (1, 1, h, w)
+    x_T = torch.randn(B, 4, h, w, generator=g)
+    outs = [(torch.randn(B, 1, 4, h, w, generator=g) + 0.3 * torch.randn(B, 5, 4, h, w, generator=g)).reshape(B * 5, 4, h, w)
+            for _ in range(steps)]
+    kw = dict(conditioning=c, unconditional_conditioning=uc, unconditional_guidance_scale=6.0, scheduler="karras")
+    finals = []
+    for b in range(B):
+        unet = ReplayUNet([o.view(B, 5, 4, h, w)[b] for o in outs], torch.float16, "cpu")
+        finals.append(OS.sample(OracleDenoiser(unet, dtype=torch.float16), "DPM++ 2m", steps, x_T[b:b + 1].clone(), **dict(kw)))
+    ref = torch.cat(finals)
+    wrapper = samplers.make({"name": "DPM++ 2m", "args": {}}, {"model": {"unet": ReplayUNet(outs, torch.float16, DEV)}})
+    out = wrapper.sampler.sample(steps=steps, batch_size=B, shape=[4, h, w], x_T=x_T.clone(), **dict(kw))
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), ref)
+
+
 def test_denoiser_forward_matches_oracle(cpd):
     from complex_prompt_diffusion_b200.samplers.extension.denoiser import Denoiser
     from oracle.denoiser import OracleDenoiser

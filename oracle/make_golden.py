@@ -10,6 +10,13 @@ What is pinned (the reference itself has no tests / golden vectors, SURVEY.md se
                                      the reference UNetModel (tiny config, seeded non-zero weights) for
                                      one image with N=3 weighted sub-prompts (2 conjunctions incl. a spatial
                                      mask, 1 negation): inputs, per-step UNet inputs/outputs, denoised tensors and final latents.
+  tests/golden/ref_sampling2.npz   - Heun / DPM2 / DPM2-a / DPM++ 2S-a / LMS and the Denoiser's scale clip (--more-only)
+  tests/golden/ref_sampling3.npz   - stochastic churn, s_churn > 0 (--churn-only)
+  tests/golden/ref_sampling4.npz   - score_corrector hook with the registered thresholding extensions (--corrector-only)
+  tests/golden/ref_sampling5.npz   - img2img branch, decode=True + denoising_strength (--img2img-only)
+  tests/golden/ref_threshold.npz   - every runnable thresholding extension on seeded tensors (--threshold-only)
+  tests/golden/ref_prompts.npz     - WeightedPrompt._parse_prompt / CompositionalPrompt._parse_mask_style (--prompts-only)
+  tests/golden/ref_vae.npz         - first-stage decoder (--vae-only)
 Runtime repairs applied to the reference objects (no source edits), see SURVEY.md 8-c:
   D1  SigmaScheduler.append_zero added (discrete.py:107 calls it, it is defined on another class, :765).
   D2  SigmaScheduler.sigmas is given KScheduler's training table and get_sigmas no longer overwrites it.
@@ -230,6 +237,25 @@ def reference_sampling_corrector(ref_shim):
     return _run_cases(ref_shim, unet, {}, c, uc, x_T, hw, steps, CORRECTOR_CASES)
 
 
+IMG2IMG_CASES = (("Euler", "karras", "epsilon", {"decode": True, "denoising_strength": 0.6}),
+                 ("DPM++ 2m", "karras", "epsilon", {"decode": True, "denoising_strength": 0.35}),
+                 ("Euler Ancestral", "exp", "epsilon", {"decode": True, "denoising_strength": 1.0}))
+
+
+def reference_sampling_img2img(ref_shim):
+    """tests/golden/ref_sampling5.npz: the decode=True branch of KDiffusionSampler.sample (k_diffusion.py:64-70: truncated
+    schedule, x = x_T + randn * sigmas[0] with the global CPU generator seeded by torch.manual_seed(77) right before)."""
+    from oracle.unet import UNetConfig, make_weights
+
+    cfg = UNetConfig.tiny()
+    hw, steps = 8, 6
+    unet = ref_shim.build_reference_unet(cfg)
+    unet.load_state_dict(make_weights(cfg, seed=0), strict=True)
+    unet.eval()
+    uc, embs, mask, c, x_T = make_case_inputs(cfg, hw)
+    return _run_cases(ref_shim, unet, {}, c, uc, x_T, hw, steps, IMG2IMG_CASES)
+
+
 def reference_vae(ref_shim):
     """tests/golden/ref_vae.npz: the shimmed reference first-stage decoder (tiny config, seeded weights) on a seeded latent."""
     from oracle.vae import VAEConfig, make_weights
@@ -347,6 +373,8 @@ def main():
         np.savez_compressed(os.path.join(GOLD, "ref_sampling3.npz"), **reference_sampling_churn(ref_shim))
     if want("--corrector-only"):
         np.savez_compressed(os.path.join(GOLD, "ref_sampling4.npz"), **reference_sampling_corrector(ref_shim))
+    if want("--img2img-only"):
+        np.savez_compressed(os.path.join(GOLD, "ref_sampling5.npz"), **reference_sampling_img2img(ref_shim))
     if want("--prompts-only"):
         np.savez_compressed(os.path.join(GOLD, "ref_prompts.npz"), **reference_prompts(ref_shim))
     if want("--threshold-only"):

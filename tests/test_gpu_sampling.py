@@ -551,6 +551,7 @@ def _replay_reference_run(golden_dir, fixture, name, sched, pred, extra):
     noises = list(torch.from_numpy(z2[key + "|noise"])) if (key + "|noise") in z2.files else []
     dens = []
     c_dev = {k: [(s, e, g_, m) for (s, e, g_, m) in v] for k, v in c.items()}
+    torch.manual_seed(77)  # the recorded runs were seeded like this (matters for the decode=True branch's initial noise)
     out = wrapper.sampler.sample(steps=int(z["steps"]), batch_size=1, shape=[4, int(z["hw"]), int(z["hw"])],
                                  x_T=torch.from_numpy(z["x_T"]).clone(), conditioning=c_dev,
                                  unconditional_conditioning=torch.from_numpy(z["uc"]),
@@ -582,6 +583,18 @@ def test_score_corrector_bit_exact_vs_reference_golden_fp32(cpd, golden_dir, nam
     """The score_corrector hook (denoiser.py:517-518) with the registered thresholding extensions rewriting e_t on the
     device, and a non-clamp scaled_clip_alg, against runs of the shimmed reference (tests/golden/ref_sampling4.npz)."""
     _replay_reference_run(golden_dir, "ref_sampling4.npz", name, sched, pred, extra)
+
+
+IMG2IMG_CASES = [("Euler", "karras", "epsilon", {"decode": True, "denoising_strength": 0.6}),
+                 ("DPM++ 2m", "karras", "epsilon", {"decode": True, "denoising_strength": 0.35}),
+                 ("Euler Ancestral", "exp", "epsilon", {"decode": True, "denoising_strength": 1.0})]
+
+
+@pytest.mark.parametrize("name,sched,pred,extra", IMG2IMG_CASES)
+def test_img2img_branch_bit_exact_vs_reference_golden_fp32(cpd, golden_dir, name, sched, pred, extra):
+    """decode=True (k_diffusion.py:64-70): truncated schedule, x = x_T + randn * sigmas[0], against runs of the shimmed
+    reference (tests/golden/ref_sampling5.npz)."""
+    _replay_reference_run(golden_dir, "ref_sampling5.npz", name, sched, pred, extra)
 
 
 def test_score_corrector_accepts_a_foreign_object(cpd):

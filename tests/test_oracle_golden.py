@@ -284,3 +284,31 @@ def test_oracle_score_corrector_bit_exact_on_replayed_unet(golden_dir, name, sch
     assert unet.i == len(unet.outs)
     assert torch.equal(torch.stack(dens), torch.from_numpy(z4[key + "|denoised"]))
     assert torch.equal(out, torch.from_numpy(z4[key + "|final"]))
+
+
+IMG2IMG_CASES = [("Euler", "karras", "epsilon", {"decode": True, "denoising_strength": 0.6}),
+                 ("DPM++ 2m", "karras", "epsilon", {"decode": True, "denoising_strength": 0.35}),
+                 ("Euler Ancestral", "exp", "epsilon", {"decode": True, "denoising_strength": 1.0})]
+
+
+@pytest.mark.parametrize("name,sched,pred,extra", IMG2IMG_CASES)
+def test_oracle_img2img_branch_bit_exact_on_replayed_unet(golden_dir, name, sched, pred, extra):
+    """The decode=True branch of KDiffusionSampler.sample (k_diffusion.py:64-70: schedule truncated by denoising_strength,
+    strength clamped at 0.999, x = x_T + randn * sigmas[0]) against runs of the shimmed reference (ref_sampling5.npz); the
+    initial noise is the first draw of the global CPU generator after torch.manual_seed(77), as in the recorded run."""
+    z, c = _load_case(golden_dir)
+    z5 = np.load(os.path.join(golden_dir, "ref_sampling5.npz"))
+    key = more_key(name, sched, pred, extra)
+    unet = _ReplayUNet(torch.from_numpy(z5[key + "|unet_out"]), torch.from_numpy(z5[key + "|unet_x"]), torch.from_numpy(z5[key + "|unet_t"]))
+    den = OracleDenoiser(unet, dtype=torch.float32)
+    noises = list(torch.from_numpy(z5[key + "|noise"])) if (key + "|noise") in z5.files else []
+    dens = []
+    torch.manual_seed(77)
+    out = OS.sample(den, name, int(z["steps"]), torch.from_numpy(z["x_T"]).clone(),
+                    noise_sampler=(lambda x: noises.pop(0)) if noises else None,
+                    callback=lambda d: dens.append(d["eps"].clone()),
+                    conditioning=c, unconditional_conditioning=torch.from_numpy(z["uc"]),
+                    unconditional_guidance_scale=float(z["guidance"]), scheduler=sched, pred_type=pred, **extra)
+    assert unet.i == len(unet.outs) and unet.i < int(z["steps"]), "truncated schedule: fewer evaluations than steps"
+    assert torch.equal(torch.stack(dens), torch.from_numpy(z5[key + "|denoised"]))
+    assert torch.equal(out, torch.from_numpy(z5[key + "|final"]))

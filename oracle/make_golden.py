@@ -10,6 +10,7 @@ What is pinned (the reference itself has no tests / golden vectors, SURVEY.md se
                                      the reference UNetModel (tiny config, seeded non-zero weights) for
                                      one image with N=3 weighted sub-prompts (2 conjunctions incl. a spatial
                                      mask, 1 negation): inputs, per-step UNet inputs/outputs, denoised tensors and final latents.
+  tests/golden/schedule_kat2.json  - SigmaScheduler.get_sigmas_{karras,exponential,quad,vp,sigmoid} of discrete.py (--schedule2-only)
   tests/golden/ref_sampling2.npz   - Heun / DPM2 / DPM2-a / DPM++ 2S-a / LMS and the Denoiser's scale clip (--more-only)
   tests/golden/ref_sampling3.npz   - stochastic churn, s_churn > 0 (--churn-only)
   tests/golden/ref_sampling4.npz   - score_corrector hook with the registered thresholding extensions (--corrector-only)
@@ -256,6 +257,26 @@ def reference_sampling_img2img(ref_shim):
     return _run_cases(ref_shim, unet, {}, c, uc, x_T, hw, steps, IMG2IMG_CASES)
 
 
+def schedule_kats_discrete():
+    """tests/golden/schedule_kat2.json: SigmaScheduler.get_sigmas_{karras, exponential, quad, vp, sigmoid}
+    (cpd/scheduler/discrete.py:21-85) called unbound (they read only their kwargs), float32 bit patterns as ints."""
+    import cpd.scheduler.discrete as D
+
+    S = D.SigmaScheduler
+    out = {}
+    for n in (1, 2, 10, 20, 30):
+        for alg, fn in (("karras", S.get_sigmas_karras), ("exp", S.get_sigmas_exponential), ("quad", S.get_sigmas_quad),
+                        ("vp", S.get_sigmas_vp), ("sigmoid", S.get_sigmas_sigmoid)):
+            for tag, kw in (("default", {}), ("wide", {"sigma_min": 0.03, "sigma_max": 14.6, "rho": 5.0})):
+                try:
+                    v = fn(None, n, device="cpu", **kw)
+                except Exception as e:  # noqa: BLE001
+                    out[f"{alg}|{n}|{tag}"] = {"error": type(e).__name__}
+                    continue
+                out[f"{alg}|{n}|{tag}"] = {"dtype": str(v.dtype), "bits": v.to(torch.float32).view(torch.int32).tolist()}
+    return out
+
+
 def reference_vae(ref_shim):
     """tests/golden/ref_vae.npz: the shimmed reference first-stage decoder (tiny config, seeded weights) on a seeded latent."""
     from oracle.vae import VAEConfig, make_weights
@@ -373,6 +394,9 @@ def main():
         np.savez_compressed(os.path.join(GOLD, "ref_sampling3.npz"), **reference_sampling_churn(ref_shim))
     if want("--corrector-only"):
         np.savez_compressed(os.path.join(GOLD, "ref_sampling4.npz"), **reference_sampling_corrector(ref_shim))
+    if want("--schedule2-only"):
+        with open(os.path.join(GOLD, "schedule_kat2.json"), "w") as f:
+            json.dump(schedule_kats_discrete(), f)
     if want("--img2img-only"):
         np.savez_compressed(os.path.join(GOLD, "ref_sampling5.npz"), **reference_sampling_img2img(ref_shim))
     if want("--prompts-only"):

@@ -233,3 +233,22 @@ def test_prompt_and_mask_parsing_match_the_reference(golden_dir):
     texts = []
     comp2 = CompositionalConditioning("base", embedder=lambda t: (texts.append(t), torch.zeros(1, 77, 8))[1]).add_weighted("cat:1.5 dog:-0.5 tree")
     assert texts == ["base", "cat", "dog", "tree"] and [c[0] for c in comp2.build()["and"]] == [1, 1.5, 1.0] and comp2.build()["not"][0][0] == 0.5
+
+
+def test_schedules_match_the_discrete_scheduler_of_the_reference(golden_dir):
+    """SigmaScheduler.get_sigmas_{karras, exponential, quad, vp, sigmoid} of cpd/scheduler/discrete.py:21-85
+    (tests/golden/schedule_kat2.json, n = 1 .. 30, default and non-default sigma_min / sigma_max / rho): the oracle and the
+    product scheduler return the same float32 bit patterns (get_sigmas appends the final 0)."""
+    import json
+    from complex_prompt_diffusion_b200.scheduler import SigmaScheduler
+    from oracle.schedule import OracleSchedule
+    kat = json.load(open(os.path.join(golden_dir, "schedule_kat2.json")))
+    s, o = SigmaScheduler(), OracleSchedule()
+    wide = {"sigma_min": 0.03, "sigma_max": 14.6, "rho": 5.0}
+    for key, ref in kat.items():
+        alg, n, tag = key.split("|")
+        kw = dict(wide) if tag == "wide" else {}
+        for impl in (s, o):
+            sig = impl.get_sigmas(alg, int(n), **kw)
+            assert sig.dtype == torch.float32 and float(sig[-1]) == 0.0, key
+            assert sig[:-1].view(torch.int32).tolist() == ref["bits"], (key, type(impl).__name__)

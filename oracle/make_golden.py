@@ -15,6 +15,7 @@ What is pinned (the reference itself has no tests / golden vectors, SURVEY.md se
   tests/golden/ref_sampling3.npz   - stochastic churn, s_churn > 0 (--churn-only)
   tests/golden/ref_sampling4.npz   - score_corrector hook with the registered thresholding extensions (--corrector-only)
   tests/golden/ref_sampling5.npz   - img2img branch, decode=True + denoising_strength (--img2img-only)
+  tests/golden/ref_sampling6.npz   - decaying guidance scale, decaying_uc_scale* (--decay-only)
   tests/golden/ref_threshold.npz   - every runnable thresholding extension on seeded tensors (--threshold-only)
   tests/golden/ref_prompts.npz     - WeightedPrompt._parse_prompt / CompositionalPrompt._parse_mask_style (--prompts-only)
   tests/golden/ref_vae.npz         - first-stage decoder (--vae-only)
@@ -277,6 +278,25 @@ def schedule_kats_discrete():
     return out
 
 
+DECAY_CASES = (("Euler", "karras", "epsilon", {"decaying_uc_scale": True}),
+               ("DPM++ 2m", "karras", "epsilon", {"decaying_uc_scale": True, "decaying_uc_scale_start": 0, "decaying_uc_scale_min": 3}),
+               ("Huen", "exp", "epsilon", {"decaying_uc_scale": True, "decaying_uc_scale_start": 2, "decaying_uc_scale_min": 0.5}))
+
+
+def reference_sampling_decay(ref_shim):
+    """tests/golden/ref_sampling6.npz: decaying guidance scale (denoiser.py:477-494; t_idx from the sampler loops, total_steps
+    = len(sigmas) from KDiffusionSampler.sample)."""
+    from oracle.unet import UNetConfig, make_weights
+
+    cfg = UNetConfig.tiny()
+    hw, steps = 8, 6
+    unet = ref_shim.build_reference_unet(cfg)
+    unet.load_state_dict(make_weights(cfg, seed=0), strict=True)
+    unet.eval()
+    uc, embs, mask, c, x_T = make_case_inputs(cfg, hw)
+    return _run_cases(ref_shim, unet, {}, c, uc, x_T, hw, steps, DECAY_CASES)
+
+
 def reference_vae(ref_shim):
     """tests/golden/ref_vae.npz: the shimmed reference first-stage decoder (tiny config, seeded weights) on a seeded latent."""
     from oracle.vae import VAEConfig, make_weights
@@ -394,6 +414,8 @@ def main():
         np.savez_compressed(os.path.join(GOLD, "ref_sampling3.npz"), **reference_sampling_churn(ref_shim))
     if want("--corrector-only"):
         np.savez_compressed(os.path.join(GOLD, "ref_sampling4.npz"), **reference_sampling_corrector(ref_shim))
+    if want("--decay-only"):
+        np.savez_compressed(os.path.join(GOLD, "ref_sampling6.npz"), **reference_sampling_decay(ref_shim))
     if want("--schedule2-only"):
         with open(os.path.join(GOLD, "schedule_kat2.json"), "w") as f:
             json.dump(schedule_kats_discrete(), f)

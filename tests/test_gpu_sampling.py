@@ -597,6 +597,18 @@ def test_img2img_branch_bit_exact_vs_reference_golden_fp32(cpd, golden_dir, name
     _replay_reference_run(golden_dir, "ref_sampling5.npz", name, sched, pred, extra)
 
 
+DECAY_CASES = [("Euler", "karras", "epsilon", {"decaying_uc_scale": True}),
+               ("DPM++ 2m", "karras", "epsilon", {"decaying_uc_scale": True, "decaying_uc_scale_start": 0, "decaying_uc_scale_min": 3}),
+               ("Huen", "exp", "epsilon", {"decaying_uc_scale": True, "decaying_uc_scale_start": 2, "decaying_uc_scale_min": 0.5})]
+
+
+@pytest.mark.parametrize("name,sched,pred,extra", DECAY_CASES)
+def test_guidance_decay_bit_exact_vs_reference_golden_fp32(cpd, golden_dir, name, sched, pred, extra):
+    """Decaying guidance scale (denoiser.py:477-494: the scale depends on t_idx / total_steps, so the fused step gets a new
+    guidance scalar every step) against runs of the shimmed reference (tests/golden/ref_sampling6.npz)."""
+    _replay_reference_run(golden_dir, "ref_sampling6.npz", name, sched, pred, extra)
+
+
 def test_score_corrector_accepts_a_foreign_object(cpd):
     """Any object with the reference's modify_score(e_t, x, t, c, **kw) works as `score_corrector` (the hook is a plugin
     point): one that returns e_t unchanged leaves the trajectory bit-identical, one that zeroes it turns Euler into x = x."""

@@ -312,3 +312,25 @@ def test_oracle_img2img_branch_bit_exact_on_replayed_unet(golden_dir, name, sche
     assert unet.i == len(unet.outs) and unet.i < int(z["steps"]), "truncated schedule: fewer evaluations than steps"
     assert torch.equal(torch.stack(dens), torch.from_numpy(z5[key + "|denoised"]))
     assert torch.equal(out, torch.from_numpy(z5[key + "|final"]))
+
+
+DECAY_CASES = [("Euler", "karras", "epsilon", {"decaying_uc_scale": True}),
+               ("DPM++ 2m", "karras", "epsilon", {"decaying_uc_scale": True, "decaying_uc_scale_start": 0, "decaying_uc_scale_min": 3}),
+               ("Huen", "exp", "epsilon", {"decaying_uc_scale": True, "decaying_uc_scale_start": 2, "decaying_uc_scale_min": 0.5})]
+
+
+@pytest.mark.parametrize("name,sched,pred,extra", DECAY_CASES)
+def test_oracle_guidance_decay_bit_exact_on_replayed_unet(golden_dir, name, sched, pred, extra):
+    """Decaying guidance scale (denoiser.py:477-494) against runs of the shimmed reference (tests/golden/ref_sampling6.npz)."""
+    z, c = _load_case(golden_dir)
+    z6 = np.load(os.path.join(golden_dir, "ref_sampling6.npz"))
+    key = more_key(name, sched, pred, extra)
+    unet = _ReplayUNet(torch.from_numpy(z6[key + "|unet_out"]), torch.from_numpy(z6[key + "|unet_x"]), torch.from_numpy(z6[key + "|unet_t"]))
+    den = OracleDenoiser(unet, dtype=torch.float32)
+    dens = []
+    out = OS.sample(den, name, int(z["steps"]), torch.from_numpy(z["x_T"]).clone(), callback=lambda d: dens.append(d["eps"].clone()),
+                    conditioning=c, unconditional_conditioning=torch.from_numpy(z["uc"]),
+                    unconditional_guidance_scale=float(z["guidance"]), scheduler=sched, pred_type=pred, **extra)
+    assert unet.i == len(unet.outs)
+    assert torch.equal(torch.stack(dens), torch.from_numpy(z6[key + "|denoised"]))
+    assert torch.equal(out, torch.from_numpy(z6[key + "|final"]))

@@ -16,6 +16,7 @@ What is pinned (the reference itself has no tests / golden vectors, SURVEY.md se
   tests/golden/ref_sampling4.npz   - score_corrector hook with the registered thresholding extensions (--corrector-only)
   tests/golden/ref_sampling5.npz   - img2img branch, decode=True + denoising_strength (--img2img-only)
   tests/golden/ref_sampling6.npz   - decaying guidance scale, decaying_uc_scale* (--decay-only)
+  tests/golden/ref_noise.npz       - NoiseGenerator seed modes and draws (--noise-only)
   tests/golden/ref_threshold.npz   - every runnable thresholding extension on seeded tensors (--threshold-only)
   tests/golden/ref_prompts.npz     - WeightedPrompt._parse_prompt / CompositionalPrompt._parse_mask_style (--prompts-only)
   tests/golden/ref_vae.npz         - first-stage decoder (--vae-only)
@@ -297,6 +298,31 @@ def reference_sampling_decay(ref_shim):
     return _run_cases(ref_shim, unet, {}, c, uc, x_T, hw, steps, DECAY_CASES)
 
 
+NOISE_CASES = (("iter", 41, 5), ("constant", 7, 5), ("c", 123456, 5), ("loop", 9, 5), ("l", 0, 3), ("random", 5, 5))
+
+
+def reference_noise(ref_shim):
+    """tests/golden/ref_noise.npz: cpd/noise.py NoiseGenerator - the seed property under every seed mode and sample()
+    (noise.py:34-46,86-93), six draws each; "random" mode after random.seed(2024); plus sample(seed=explicit)."""
+    import random
+    import cpd.noise as N
+
+    out = {"build_cycle_mod_5": np.array(N.build_cycle_mod(5)), "build_cycle_mod_3": np.array(N.build_cycle_mod(3))}
+    for mode, seed, cyc in NOISE_CASES:
+        random.seed(2024)
+        ng = N.NoiseGenerator((1, 4, 4, 4), "cpu", seed=seed, seed_mode=mode, cycle_size=cyc)
+        draws, seeds = [], []
+        for _ in range(6):
+            draws.append(ng.sample().numpy())
+            seeds.append(ng.last_seed)
+        out[f"{mode}|{seed}|{cyc}|draws"] = np.stack(draws)
+        out[f"{mode}|{seed}|{cyc}|seeds"] = np.array(seeds)
+    ng = N.NoiseGenerator((2, 4, 8, 8), "cpu", seed=3)
+    out["explicit|99"] = ng.sample(seed=99).numpy()
+    out["explicit|after"] = np.array([ng.last_seed])
+    return out
+
+
 def reference_vae(ref_shim):
     """tests/golden/ref_vae.npz: the shimmed reference first-stage decoder (tiny config, seeded weights) on a seeded latent."""
     from oracle.vae import VAEConfig, make_weights
@@ -414,6 +440,8 @@ def main():
         np.savez_compressed(os.path.join(GOLD, "ref_sampling3.npz"), **reference_sampling_churn(ref_shim))
     if want("--corrector-only"):
         np.savez_compressed(os.path.join(GOLD, "ref_sampling4.npz"), **reference_sampling_corrector(ref_shim))
+    if want("--noise-only"):
+        np.savez_compressed(os.path.join(GOLD, "ref_noise.npz"), **reference_noise(ref_shim))
     if want("--decay-only"):
         np.savez_compressed(os.path.join(GOLD, "ref_sampling6.npz"), **reference_sampling_decay(ref_shim))
     if want("--schedule2-only"):

@@ -252,3 +252,30 @@ def test_schedules_match_the_discrete_scheduler_of_the_reference(golden_dir):
             sig = impl.get_sigmas(alg, int(n), **kw)
             assert sig.dtype == torch.float32 and float(sig[-1]) == 0.0, key
             assert sig[:-1].view(torch.int32).tolist() == ref["bits"], (key, type(impl).__name__)
+
+
+def test_noise_generator_matches_the_reference(golden_dir):
+    """cpd/noise.py NoiseGenerator (seed property under iter / constant / loop / random, sample(),
+    noise.py:34-46,86-93) - seeds and drawn tensors identical to the reference's (tests/golden/ref_noise.npz); the oracle's
+    restricted generator agrees on the modes it restates."""
+    import random
+    import numpy as np
+    from complex_prompt_diffusion_b200.noise import NoiseGenerator, build_cycle_mod
+    from oracle.samplers import OracleNoiseGenerator
+    g = np.load(os.path.join(golden_dir, "ref_noise.npz"))
+    assert build_cycle_mod(5) == g["build_cycle_mod_5"].tolist() and build_cycle_mod(3) == g["build_cycle_mod_3"].tolist()
+    cases = sorted({k.rsplit("|", 1)[0] for k in g.files if k.endswith("|draws")})
+    assert len(cases) == 6
+    for case in cases:
+        mode, seed, cyc = case.split("|")
+        random.seed(2024)
+        ng = NoiseGenerator((1, 4, 4, 4), "cpu", seed=int(seed), seed_mode=mode, cycle_size=int(cyc))
+        og = OracleNoiseGenerator((1, 4, 4, 4), "cpu", seed=int(seed), seed_mode=mode) if mode in ("iter", "constant", "c") else None
+        for k in range(6):
+            x = ng.sample()
+            assert ng.last_seed == int(g[case + "|seeds"][k]), (case, k)
+            assert torch.equal(x, torch.from_numpy(g[case + "|draws"][k])), (case, k)
+            if og is not None:
+                assert torch.equal(og.sample(), x)
+    ng = NoiseGenerator((2, 4, 8, 8), "cpu", seed=3)
+    assert torch.equal(ng.sample(seed=99), torch.from_numpy(g["explicit|99"])) and ng.last_seed == int(g["explicit|after"][0])

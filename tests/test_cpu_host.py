@@ -72,6 +72,29 @@ def test_registry_and_wrapper_surface():
         samplers.make({"name": "nope", "args": {}})
     with pytest.raises(ValueError):
         samplers.create(3)
+    # DiffusionSamplerWrapper (diffusion.py:51-111): defaults, to_json layout, shape = [C, W // 8, H // 8] (W before H)
+    from complex_prompt_diffusion_b200.samplers.diffusion import DiffusionSamplerWrapper
+    calls = []
+
+    class Inner:
+        def __init__(self, model):
+            self.model = model
+
+        def sample(self, **kw):
+            calls.append(kw)
+            return ("latents", "aux")
+
+    wr = DiffusionSamplerWrapper("Euler", constructor=Inner, model={"unet": None}, width=768, height=512, steps=30, scale=5.0)
+    assert wr.to_json() == {"name": "Euler", "args": {"batch_size": 1, "width": 768, "height": 512, "z_channels": 4, "scale": 5.0,
+                                                       "use_start_code": False, "steps": 30, "eta": 0, "temperature": 1,
+                                                       "denoising_strength": 0.0}}
+    assert wr.sample(conditioning="c", scheduler="karras") == "latents"
+    kw = calls[-1]
+    assert kw["shape"] == [4, 96, 64] and kw["steps"] == 30 and kw["batch_size"] == 1 and kw["conditioning"] == "c"
+    assert kw["unconditional_guidance_scale"] == 5.0 and kw["eta"] == 0 and kw["temperature"] == 1 and kw["x_T"] is None
+    wr2 = DiffusionSamplerWrapper("Euler", constructor=Inner, model=None, use_start_code=True, batch_size=2)
+    wr2.sample()
+    assert tuple(calls[-1]["x_T"].shape) == (2, 4, 64, 64)
 
 
 def test_product_has_no_cpu_fallback():

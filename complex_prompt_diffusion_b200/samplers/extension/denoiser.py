@@ -98,10 +98,58 @@ class ConditioningPlan:
         self.context = torch.cat([f.to(device) for f in factors]).contiguous()  # [1 + N, tokens, D]
 
 
+class ReferenceUNetAdapter:
+    """Lets the Denoiser drive ANY model with the reference's UNet call signature (denoiser.py:397-407):
+    `unet(x [R*B, 4, h, w], timesteps [R*B], context [R*B, tokens, D], return_attn=True, ...) -> (out, skips)`, a bare tensor,
+    or an object with `.sample` - e.g. the reference's own UNetModel or a diffusers-style module already living on the GPU.
+    It builds the batch of denoiser.py:384-393 (x * c_in broadcast over the rows, the timestep repeated, the context rows
+    tiled per image) on the device.  This is the compatibility path; `models.unet.UNetModel` provides `forward_rows` itself."""
+
+    def __init__(self, unet):
+        self.unet = unet
+        p = next(iter(unet.parameters()))
+        self.dtype, self.device = p.dtype, p.device
+        self.eps_dtype = p.dtype
+        self._ctx, self._y = None, None
+
+    def parameters(self):
+        return self.unet.parameters()
+
+    def set_context(self, ctx):
+        self._ctx = ctx.to(self.device, self.dtype)
+
+    def set_vector(self, y):
+        self._y = y.to(self.device, self.dtype)
+
+    @torch.no_grad()
+    def forward_rows(self, x, c_in, t, rows_per_image, inject=None):
+        B, R = x.shape[0], rows_per_image
+        if self._ctx is None or self._ctx.shape[0] != R:
+            raise RuntimeError("ReferenceUNetAdapter: set_context must be called with one context row per conditioning row")
+        x_in = (x * torch.tensor(c_in, dtype=torch.float32, device=x.device)).to(self.dtype)  # denoiser.py:390-391
+        x_in = x_in[:, None].expand(B, R, *x.shape[1:]).reshape(B * R, *x.shape[1:])
+        t_in = torch.full((B * R,), t, dtype=self.dtype, device=self.device)  # :384,393
+        ctx = self._ctx[None].expand(B, *self._ctx.shape).reshape(B * R, *self._ctx.shape[1:])
+        kw = {"return_attn": True}
+        if self._y is not None:
+            kw["y"] = self._y[None].expand(B, *self._y.shape).reshape(B * R, -1)
+        if inject:
+            kw.update(inject_feats=inject.get("feats"), inject_feats_stop=inject.get("feats_stop", 10),
+                      inject_attns=inject.get("attns"), inject_attns_stop=inject.get("attns_stop", 10))
+        out = self.unet(x_in, t_in, ctx, **kw)
+        if isinstance(out, (tuple, list)):
+            out = out[0]
+        if hasattr(out, "sample"):  # :404-405
+            out = out.sample
+        return out.contiguous()
+
+
 class Denoiser(torch.nn.Module):
     def __init__(self, unet, vae=None, tokenizer=None, clip_model=None, decode=None, quantize=False, **kwargs):
         super().__init__()
         self.name = kwargs.get("name", "Denoiser")
+        if not hasattr(unet, "forward_rows"):  # a model with the reference's call signature
+            unet = ReferenceUNetAdapter(unet)
         p = next(iter(unet.parameters()))
         self.dtype, self.device = p.dtype, p.device
         if self.device.type != "cuda":

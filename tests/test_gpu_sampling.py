@@ -609,6 +609,71 @@ def test_guidance_decay_bit_exact_vs_reference_golden_fp32(cpd, golden_dir, name
     _replay_reference_run(golden_dir, "ref_sampling6.npz", name, sched, pred, extra)
 
 
+@pytest.mark.parametrize("style", ["tuple", "sample_attr", "tensor"])
+def test_denoiser_drives_a_model_with_the_reference_call_signature(cpd, style):
+    """any model called like the reference's UNet - unet(x, timesteps, context, return_attn=True) returning
+    (out, skips), an object with `.sample` (denoiser.py:404-405) or a bare tensor - plugs into the samplers through
+    ReferenceUNetAdapter; the same module on the CPU under the oracle gives the same latents (fp32, conv rounding only)."""
+    import types
+    from complex_prompt_diffusion_b200 import samplers
+    from oracle.denoiser import OracleDenoiser
+    from oracle import samplers as OS
+
+    class TinyModel(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            gg = torch.Generator().manual_seed(11)
+            self.conv = torch.nn.Conv2d(4, 4, 3, padding=1)
+            self.proj = torch.nn.Linear(32, 4)
+            for p_ in self.parameters():
+                p_.data = torch.randn(p_.shape, generator=gg) * 0.2
+
+        def forward(self, x, timesteps, context, return_attn=False, **kw):
+            out = self.conv(x) + self.proj(context.mean(1))[:, :, None, None] + 1e-3 * timesteps[:, None, None, None]
+            if style == "tuple":
+                return out, [out] * 12
+            if style == "sample_attr":
+                return types.SimpleNamespace(sample=out), [out] * 12
+            return out
+
+    class CpuSide:  # the oracle expects (out, skips)
+        def __init__(self, m):
+            self.m = m
+
+        def parameters(self):
+            return self.m.parameters()
+
+        def __call__(self, x, t, ctx, **kw):
+            o = self.m(x, t, ctx)
+            o = o[0] if isinstance(o, tuple) else o
+            o = o.sample if hasattr(o, "sample") else o
+            return o, [o] * 12
+
+    g = torch.Generator().manual_seed(5)
+    B, hw, steps = 2, 8, 4
+    uc = torch.randn(1, 77, 32, generator=g)
+    e = [torch.randn(1, 77, 32, generator=g) for _ in range(2)]
+    c = {"and": [(1.0, e[0], None, 1)], "not": [(0.5, e[1], None, 1)]}
+    x_T = torch.randn(B, 4, hw, hw, generator=g)
+    kw = dict(conditioning=c, unconditional_conditioning=uc, unconditional_guidance_scale=4.0, scheduler="karras")
+    model = TinyModel().eval()
+    ref = torch.cat([OS.sample(OracleDenoiser(CpuSide(model), dtype=torch.float32), "DPM++ 2m", steps, x_T[b:b + 1].clone(), **dict(kw))
+                     for b in range(B)])
+    gpu_model = TinyModel().eval().to(DEV)
+    wrapper = samplers.make({"name": "DPM++ 2m", "args": {}}, {"model": {"unet": gpu_model}})
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False  # the toy model's own conv / linear
+    try:
+        out = wrapper.sampler.sample(steps=steps, batch_size=B, shape=[4, hw, hw], x_T=x_T.clone(), **dict(kw))
+        torch.cuda.synchronize()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    # One Denoiser call agrees to 1e-7 (tests/debug_adapter.py).  Over a trajectory the toy model's fp32 outputs differ in
+    # the last bits between cuDNN and the CPU, and its eps values reach ~25 where an fp16 ulp is 0.016: the fp16 delta of the
+    # combine (denoiser.py:450-460) turns a few of those last-bit differences into one-ulp flips (3.7e-4 overall here).
+    assert rel(out, ref) < 2e-3
+
+
 def test_score_corrector_accepts_a_foreign_object(cpd):
     """Any object with the reference's modify_score(e_t, x, t, c, **kw) works as `score_corrector` (the hook is a plugin
     point): one that returns e_t unchanged leaves the trajectory bit-identical, one that zeroes it turns Euler into x = x."""

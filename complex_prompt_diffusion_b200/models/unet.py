@@ -564,7 +564,15 @@ class UNetModel:
             raise ValueError("timesteps must have one entry per row of x")
         if n > 32:
             raise NotImplementedError("more than 32 rows with distinct timesteps: use forward_rows")
-        return self._forward_impl(x, 1.0, 1, t_rows, shared_t=False, return_skips=bool(kwargs.get("return_attn", False)),
-                                  inject=inject, return_feats=bool(kwargs.get("return_feat", False)))
+        res = self._forward_impl(x, 1.0, 1, t_rows, shared_t=False, return_skips=bool(kwargs.get("return_attn", False)),
+                                 inject=inject, return_feats=bool(kwargs.get("return_feat", False)))
+
+        # The executor returns views of its reusable activation buffers; this entry point mirrors the reference module, whose
+        # results stay valid across calls, so hand out copies (the fast path, forward_rows, keeps returning the buffer).
+        def own(v):
+            if isinstance(v, torch.Tensor):
+                return v.clone()
+            return type(v)(own(e) for e in v) if isinstance(v, (list, tuple)) else v
+        return own(res)
 
     __call__ = forward

@@ -16,6 +16,7 @@ What is pinned (the reference itself has no tests / golden vectors, SURVEY.md se
   tests/golden/ref_sampling4.npz   - score_corrector hook with the registered thresholding extensions (--corrector-only)
   tests/golden/ref_sampling5.npz   - img2img branch, decode=True + denoising_strength (--img2img-only)
   tests/golden/ref_sampling6.npz   - decaying guidance scale, decaying_uc_scale* (--decay-only)
+  tests/golden/ref_unet_inject.npz - UNetModel with return_attn / return_feat / inject_attns / inject_feats (--inject-only)
   tests/golden/ref_noise.npz       - NoiseGenerator seed modes and draws (--noise-only)
   tests/golden/ref_threshold.npz   - every runnable thresholding extension on seeded tensors (--threshold-only)
   tests/golden/ref_prompts.npz     - WeightedPrompt._parse_prompt / CompositionalPrompt._parse_mask_style (--prompts-only)
@@ -323,6 +324,35 @@ def reference_noise(ref_shim):
     return out
 
 
+def reference_unet_injection(ref_shim):
+    """tests/golden/ref_unet_inject.npz: the shimmed reference UNetModel (tiny config, seeded weights) with return_attn /
+    return_feat and with inject_attns / inject_feats and their *_stop indices (unet.py:774-813).  The injected tensors are
+    scaled copies of the model's own skip / feature tensors, so a test can rebuild them from its own forward pass."""
+    from oracle.unet import UNetConfig, make_weights
+
+    cfg = UNetConfig.tiny()
+    unet = ref_shim.build_reference_unet(cfg)
+    unet.load_state_dict(make_weights(cfg, seed=0), strict=True)
+    unet.eval()
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(2, 4, 8, 8, generator=g)
+    t = torch.tensor([731.0, 12.5])
+    ctx = torch.randn(2, 77, cfg.context_dim, generator=g)
+    with torch.no_grad():
+        out, skips, feats = unet(x, t, ctx, return_attn=True, return_feat=True)
+        inj_a = [s_ * 0.5 for s_ in skips]
+        inj_f = [skips[0] * 0.3] + [f_ * 0.7 for f_ in feats[:-1]]
+        out_a = unet(x, t, ctx, inject_attns=inj_a, inject_attns_stop=5)
+        out_f = unet(x, t, ctx, inject_feats=inj_f, inject_feats_stop=3)
+        out_af, skips_af = unet(x, t, ctx, return_attn=True, inject_attns=inj_a, inject_attns_stop=12, inject_feats=inj_f, inject_feats_stop=7)
+    print("unet injection: plain std", float(out.std()), "attn-injected", float(out_a.std()), "feat-injected", float(out_f.std()))
+    return {"x": x.numpy(), "t": t.numpy(), "ctx": ctx.numpy(), "out": out.numpy(), "out_a": out_a.numpy(), "out_f": out_f.numpy(),
+            "out_af": out_af.numpy(), "n_skips": np.array(len(skips)), "n_feats": np.array(len(feats)),
+            "skip_shapes": np.array([list(s_.shape) for s_ in skips]), "feat_shapes": np.array([list(f_.shape) for f_ in feats]),
+            "skip0": skips[0].numpy(), "skip_last": skips[-1].numpy(), "feat_last": feats[-1].numpy(),
+            "returned_skip0_af": skips_af[0].numpy()}
+
+
 def reference_vae(ref_shim):
     """tests/golden/ref_vae.npz: the shimmed reference first-stage decoder (tiny config, seeded weights) on a seeded latent."""
     from oracle.vae import VAEConfig, make_weights
@@ -440,6 +470,8 @@ def main():
         np.savez_compressed(os.path.join(GOLD, "ref_sampling3.npz"), **reference_sampling_churn(ref_shim))
     if want("--corrector-only"):
         np.savez_compressed(os.path.join(GOLD, "ref_sampling4.npz"), **reference_sampling_corrector(ref_shim))
+    if want("--inject-only"):
+        np.savez_compressed(os.path.join(GOLD, "ref_unet_inject.npz"), **reference_unet_injection(ref_shim))
     if want("--noise-only"):
         np.savez_compressed(os.path.join(GOLD, "ref_noise.npz"), **reference_noise(ref_shim))
     if want("--decay-only"):

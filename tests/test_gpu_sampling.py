@@ -1068,6 +1068,34 @@ def test_feature_and_skip_injection(cpd):
     assert r < 2e-2
 
 
+def test_unet_injection_vs_reference_unet_golden(cpd, golden_dir):
+    """The product UNetModel (tiny config, seeded weights rounded to bf16 by the packer) against the shimmed reference UNetModel's
+    own outputs with return_attn / return_feat / inject_attns / inject_feats (tests/golden/ref_unet_inject.npz, fp32
+    reference): 1e-2 on the plain outputs, 2e-2 on the injected runs; list lengths, shapes and which run differs from the plain one are exact."""
+    z = np.load(os.path.join(golden_dir, "ref_unet_inject.npz"))
+    cfg, _oracle, gpu = _unet_pair("tiny", torch.float32)
+    x, t, ctx = (torch.from_numpy(z[k]).to(DEV) for k in ("x", "t", "ctx"))
+    out, skips, feats = gpu(x, t, ctx, return_attn=True, return_feat=True)
+    torch.cuda.synchronize()
+    assert len(skips) == int(z["n_skips"]) and len(feats) == int(z["n_feats"])
+    assert [list(s.shape) for s in skips] == z["skip_shapes"].tolist() and [list(f.shape) for f in feats] == z["feat_shapes"].tolist()
+    assert rel(out, torch.from_numpy(z["out"])) < 1e-2 and rel(skips[0], torch.from_numpy(z["skip0"])) < 1e-2
+    assert rel(feats[-1], torch.from_numpy(z["feat_last"])) < 1e-2
+    inj_a = [s.float() * 0.5 for s in skips]
+    inj_f = [skips[0].float() * 0.3] + [f.float() * 0.7 for f in feats[:-1]]
+    out_a = gpu(x, t, ctx, inject_attns=inj_a, inject_attns_stop=5)
+    out_f = gpu(x, t, ctx, inject_feats=inj_f, inject_feats_stop=3)
+    out_af = gpu(x, t, ctx, inject_attns=inj_a, inject_attns_stop=12, inject_feats=inj_f, inject_feats_stop=7)
+    torch.cuda.synchronize()
+    for got, key in ((out_a, "out_a"), (out_f, "out_f"), (out_af, "out_af")):
+        got = got[0] if isinstance(got, tuple) else got
+        # the injected tensors are the product's own (16-bit) skips / features and its weights are bf16-rounded, the reference
+        # ran in fp32 on fp32 weights: 1.2e-2 on the attn-injected run; the bound is the final-latent tolerance of the task
+        assert rel(got, torch.from_numpy(z[key])) < 2e-2, key
+    # the injections matter at this tolerance: each injected run is far from the plain one
+    assert rel(torch.from_numpy(z["out_a"]), torch.from_numpy(z["out"])) > 3e-2 and rel(torch.from_numpy(z["out_f"]), torch.from_numpy(z["out"])) > 3e-2
+
+
 def _oracle_side_kw(oracle, dtype=torch.bfloat16):
     class Side:  # oracle UNet with the product's dtype boundaries, forwarding the injection kwargs
         def parameters(self):

@@ -334,3 +334,30 @@ def test_oracle_guidance_decay_bit_exact_on_replayed_unet(golden_dir, name, sche
     assert unet.i == len(unet.outs)
     assert torch.equal(torch.stack(dens), torch.from_numpy(z6[key + "|denoised"]))
     assert torch.equal(out, torch.from_numpy(z6[key + "|final"]))
+
+
+def test_oracle_unet_injection_matches_reference_unet(golden_dir):
+    """unet.py:774-813: return_attn (the 12 skip tensors, deepest first), return_feat, inject_attns / inject_feats with their
+    *_stop indices - the oracle UNet against the shimmed reference UNetModel on the same seeded weights
+    (tests/golden/ref_unet_inject.npz).  The injected tensors are rebuilt from the oracle's own forward pass."""
+    z = np.load(os.path.join(golden_dir, "ref_unet_inject.npz"))
+    cfg = UNetConfig.tiny()
+    unet = OracleUNet(cfg, make_weights(cfg, seed=0))
+    x, t, ctx = (torch.from_numpy(z[k]) for k in ("x", "t", "ctx"))
+
+    def close(a, b):
+        b = torch.from_numpy(b)
+        return a.shape == b.shape and ((a - b).norm() / b.norm()).item() < 1e-5
+
+    out, skips, feats = unet(x, t, ctx, return_attn=True, return_feat=True)
+    assert len(skips) == int(z["n_skips"]) and len(feats) == int(z["n_feats"])
+    assert [list(s.shape) for s in skips] == z["skip_shapes"].tolist() and [list(f.shape) for f in feats] == z["feat_shapes"].tolist()
+    assert close(out, z["out"]) and close(skips[0], z["skip0"]) and close(skips[-1], z["skip_last"]) and close(feats[-1], z["feat_last"])
+    inj_a = [s * 0.5 for s in skips]
+    inj_f = [skips[0] * 0.3] + [f * 0.7 for f in feats[:-1]]
+    out_a = unet(x, t, ctx, inject_attns=inj_a, inject_attns_stop=5)
+    out_f = unet(x, t, ctx, inject_feats=inj_f, inject_feats_stop=3)
+    out_af, skips_af = unet(x, t, ctx, return_attn=True, inject_attns=inj_a, inject_attns_stop=12, inject_feats=inj_f, inject_feats_stop=7)
+    assert close(out_a, z["out_a"]) and close(out_f, z["out_f"]) and close(out_af, z["out_af"])
+    assert close(skips_af[0], z["returned_skip0_af"])  # return_attn reports the ORIGINAL skip, not the injected one (:802-808)
+    assert not close(out_a, z["out"]) and not close(out_f, z["out"])

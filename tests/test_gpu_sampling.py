@@ -789,7 +789,7 @@ def test_thresholding_extensions_vs_reference_golden(cpd, golden_dir):
     from complex_prompt_diffusion_b200.samplers.extension.denoiser import apply_threshold
     from oracle.make_golden import THRESHOLD_CASES
     g = np.load(os.path.join(golden_dir, "ref_threshold.npz"))
-    for j in range(3):
+    for j in range(2):
         x = torch.from_numpy(g[f"x{j}"])
         for k, (name, thr) in enumerate(THRESHOLD_CASES):
             xd = x.to(DEV).clone()

@@ -267,9 +267,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) attention_kernel(const __grid_
 
 }  // namespace
 
-cpd_status cpd_attention_2tile(const cpd_attn_params* p, void* stream);       // attention_umma2.cu
 cpd_status cpd_attention_persistent(const cpd_attn_params* p, void* stream);  // attention_umma3.cu
 cpd_status cpd_attention_split(const cpd_attn_params* p, void* stream);       // attention_umma4.cu
+cpd_status cpd_attention_cross(const cpd_attn_params* p, void* stream);       // attention_umma5.cu
+
+static bool env_off(const char* name) {
+  const char* e = getenv(name);
+  return e && e[0] == '0';
+}
 
 extern "C" cpd_status cpd_attention(const cpd_attn_params* p, void* stream) {
   CPD_REQUIRE(p && p->q && p->k && p->vt && p->o, "cpd_attention: null pointer");
@@ -278,16 +283,15 @@ extern "C" cpd_status cpd_attention(const cpd_attn_params* p, void* stream) {
   CPD_REQUIRE(p->ldq % 8 == 0 && p->ldk % 8 == 0 && p->ldvt % 8 == 0 && p->ldo % 8 == 0, "cpd_attention: leading dims must be multiples of 8");
   CPD_REQUIRE(((uintptr_t)p->o & 15) == 0, "cpd_attention: o must be 16-byte aligned");
   CPD_REQUIRE(p->d_head >= 0 && p->d_head <= p->dpad, "cpd_attention: d_head=%d must be in [0, dpad=%d]", p->d_head, p->dpad);
-  if (p->d_head > 0) {  // two query tiles per CTA, P in tensor memory; falls through when the shape is outside its domain
-    static int persist = -1;  // CPD_ATTN_PERSIST=0: one CTA per work item (attention_umma2.cu) instead of the persistent kernel
-    if (persist < 0) {
-      const char* e = getenv("CPD_ATTN_PERSIST");
-      persist = (e && e[0] == '0') ? 0 : 1;
-    }
-    static int split = -1;  // CPD_ATTN_SPLIT=0: never the split-row kernel (attention_umma4.cu)
-    if (split < 0) {
-      const char* e = getenv("CPD_ATTN_SPLIT");
-      split = (e && e[0] == '0') ? 0 : 1;
+  if (p->d_head > 0) {
+    // Dispatch by shape (each kernel returns CPD_ERR_UNSUPPORTED outside its domain): one key block (the 77-token context)
+    // -> attention5; head dims <= 63 with many key blocks (the 4096^2 d = 40 self-attention) -> attention4 (split rows);
+    // everything else with more than 128 query rows -> attention3 (persistent two-tile); the rest -> the one-tile kernel below.
+    // CPD_ATTN_CROSS=0 / CPD_ATTN_SPLIT=0 / CPD_ATTN_PERSIST=0 take a kernel out of the chain (A/B measurements).
+    static const bool cross = !env_off("CPD_ATTN_CROSS"), split = !env_off("CPD_ATTN_SPLIT"), persist = !env_off("CPD_ATTN_PERSIST");
+    if (cross) {
+      const cpd_status st5 = cpd_attention_cross(p, stream);
+      if (st5 != CPD_ERR_UNSUPPORTED) return st5;
     }
     if (split) {
       const cpd_status st4 = cpd_attention_split(p, stream);
@@ -297,8 +301,6 @@ extern "C" cpd_status cpd_attention(const cpd_attn_params* p, void* stream) {
       const cpd_status st3 = cpd_attention_persistent(p, stream);
       if (st3 != CPD_ERR_UNSUPPORTED) return st3;
     }
-    const cpd_status st2 = cpd_attention_2tile(p, stream);
-    if (st2 != CPD_ERR_UNSUPPORTED) return st2;
   }
   AttnArgs a;
   a.o = (bf16*)p->o;
@@ -331,11 +333,7 @@ extern "C" cpd_status cpd_attention(const cpd_attn_params* p, void* stream) {
   const size_t shm = (size_t)a.datoms * ATOM_BYTES + (size_t)a.kv_stages * (a.datoms * ATOM_BYTES + 2 * p->dpad * 128) +
                      2 * ATOM_BYTES + 256 + 1024;
   CPD_REQUIRE(shm <= 227 * 1024, "cpd_attention: shared memory %zu exceeds 227 KB", shm);
-  static size_t configured = 0;
-  if (shm > configured) {
-    CPD_CUDA_CHECK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-    configured = 227 * 1024;
-  }
+  CPD_SMEM_OPTIN(attention_kernel, 227 * 1024);
   dim3 grid((p->nq + BQ - 1) / BQ, p->heads, p->batch);
   CPD_CUDA_CHECK(cpd_launch(attention_kernel, dim3(grid), dim3(NUM_THREADS), shm, (cudaStream_t)stream, a));
   CPD_CUDA_CHECK(cudaGetLastError());

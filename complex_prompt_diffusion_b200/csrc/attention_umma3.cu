@@ -506,11 +506,7 @@ static cpd_status launch_attention3(const cpd_attn_params* p, int dv, void* stre
     if ((rc = cpd_make_tmap_bf16(&a.map_vt, p->vt, 2, dims, str, box))) return rc;
   }
   const size_t shm = (size_t)q_bytes + (size_t)stages * per_stage + 512 + 1024;
-  static bool configured = false;
-  if (!configured) {
-    CPD_CUDA_CHECK(cudaFuncSetAttribute(attention3_kernel<NT, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-    configured = true;
-  }
+  CPD_SMEM_OPTIN((attention3_kernel<NT, BKV>), 227 * 1024);
   const int ctas = a.items < 148 ? a.items : 148;
   CPD_CUDA_CHECK(cpd_launch(attention3_kernel<NT, BKV>, dim3(ctas), dim3(64 + NT * 128), shm, (cudaStream_t)stream, a));
   return CPD_OK;
@@ -522,14 +518,7 @@ cpd_status cpd_attention_persistent(const cpd_attn_params* p, void* stream) {
   if (d <= 0 || d > p->dpad || p->nq <= BQ) return CPD_ERR_UNSUPPORTED;
   const int dv = (d + 1 + 15) / 16 * 16;
   if (dv > 128) return CPD_ERR_UNSUPPORTED;
-  // Four 128-row tiles x 64-key blocks (O_t in 64 TMEM columns: dv <= 64) is built and tested but measured SLOWER
-  // (1254 vs 838 us on 16 x 8 x 4096^2, d = 40): the single MMA issuer warp spends ~1500 cycles of barrier / fence / commit
-  // latency per (tile, key block) and cannot feed four tiles (profiles/r01_attn_timelines.txt).  Opt-in: CPD_ATTN_4TILE=1.
-  static int four = -1;
-  if (four < 0) {
-    const char* e = getenv("CPD_ATTN_4TILE");
-    four = (e && e[0] == '1') ? 1 : 0;
-  }
-  if (four && dv <= 64 && p->nk > 128 && p->nq >= 4 * BQ) return launch_attention3<4, 64>(p, dv, stream);
+  // (A four-tile x 64-key-block instantiation was measured in round 1 - 1254 vs 838 us on 16 x 8 x 4096^2, d = 40: the single
+  // MMA issuer warp cannot feed four tiles - and removed; profiles/r01_attn_timelines.txt.)
   return launch_attention3<2, 128>(p, dv, stream);
 }

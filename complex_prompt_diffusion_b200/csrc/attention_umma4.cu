@@ -32,7 +32,6 @@ constexpr int NUM_THREADS = 64 + 2 * SPLIT * 128 + 32;  // warp 0 TMA, warp 1 is
 constexpr int ISSUER1_WARP = 2 + 2 * SPLIT * 4;
 constexpr int MAX_STAGES = 4;
 constexpr float RESCALE_TAU = 8.0f;    // lazy O rescale threshold (log2 domain)
-constexpr int ATTN_POLY_DEFAULT = 0;   // see cpd_attention_split
 
 struct Attn4Args {
   CUtensorMap map_q, map_k, map_vt;
@@ -73,7 +72,7 @@ __device__ __forceinline__ void tmem_st32_4(uint32_t taddr, const uint32_t* r) {
 // SEP = true : P in its own TMEM columns (per tile S 128 | P 64 | O 64: head dims <= 63), S(j+1) runs ahead of the softmax.
 // SEP = false: P overwrites S in place (per tile S/P 128, O 128 in the upper half: head dims <= 111); S(j+1) follows P V(j)
 //              on the in-order tensor pipe - the split rows and the per-tile issuers still apply.
-template <bool SEP, int POLY>  // POLY: every POLY-th pair of exponentials goes to the FMA pipe (poly_ex2); 0 = all on MUFU
+template <bool SEP, bool F16>  // F16: the activation format (fp16 / bf16) as a compile-time constant: one F2FP per packed pair
 __global__ void __launch_bounds__(NUM_THREADS, 1) attention4_kernel(const __grid_constant__ Attn4Args a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -106,7 +105,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention4_kernel(const __grid
   const int b = blockIdx.z;
   const int bkv = b % a.kv_batch;
   const int nblk = (a.nk + BKV - 1) / BKV;
-  const bool f16 = a.fp16 != 0;
+  constexpr bool f16 = F16;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&a.map_q);
@@ -287,9 +286,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention4_kernel(const __grid
       float mx0 = -INFINITY, mx1 = -INFINITY;
       if (full) {
 #pragma unroll
-        for (int e = 0; e < CW; e += 2) {
-          mx0 = fmaxf(mx0, __uint_as_float(s[e]));
-          mx1 = fmaxf(mx1, __uint_as_float(s[e + 1]));
+        for (int e = 0; e < CW; e += 4) {  // FMNMX3: two new elements per instruction, two independent chains
+          mx0 = fmax3(mx0, __uint_as_float(s[e]), __uint_as_float(s[e + 1]));
+          mx1 = fmax3(mx1, __uint_as_float(s[e + 2]), __uint_as_float(s[e + 3]));
         }
       } else {
 #pragma unroll
@@ -343,10 +342,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention4_kernel(const __grid
         for (int e = 0; e < CW; e += 2) {
           const float x0 = fmaf(__uint_as_float(s[e]), a.scale_log2, neg_m);
           const float x1 = fmaf(__uint_as_float(s[e + 1]), a.scale_log2, neg_m);
-          const bool on_fma = POLY > 0 && ((e >> 1) % (POLY > 0 ? POLY : 1)) == (POLY > 0 ? POLY : 1) - 1;  // compile-time per unrolled e
-          const float p0 = on_fma ? poly_ex2(x0) : fast_ex2(x0);
-          const float p1 = on_fma ? poly_ex2(x1) : fast_ex2(x1);
-          s[e >> 1] = pack_act2(p0, p1, f16);
+          s[e >> 1] = pack_act2(fast_ex2(x0), fast_ex2(x1), f16);
         }
       } else {
 #pragma unroll
@@ -465,35 +461,21 @@ cpd_status cpd_attention_split(const cpd_attn_params* p, void* stream) {
     if ((rc = cpd_make_tmap_bf16(&a.map_vt, p->vt, 2, dims, str, box))) return rc;
   }
   const size_t shm = (size_t)q_bytes + (size_t)stages * per_stage + 512 + XCH_BYTES + 1024;
-  // Share of the exponentials computed on the FMA pipe: every POLY-th pair (CPD_ATTN_POLY = 0 | 2 | 3 | 4; see poly_ex2).
-  // Measured on B200 (16 x 8 x 4096^2 d40): 724 us with none, 747 / 771 / 842 us with 25 / 33 / 50 % moved - the softmax warps
-  // are bound by the length of their own serial instruction stream per key block, not by the MUFU pipe (71 % busy; issue
-  // slots 53 %), so 8 FMA-pipe instructions per exponential cost more than they free.  Default: all on MUFU; the variants
-  // stay as an opt-in experiment.
-  static int poly = -1;
-  if (poly < 0) {
-    const char* e = getenv("CPD_ATTN_POLY");
-    poly = e ? atoi(e) : ATTN_POLY_DEFAULT;
-    if (poly != 0 && poly != 2 && poly != 3 && poly != 4) poly = ATTN_POLY_DEFAULT;
-  }
-  static bool configured = false;
-  if (!configured) {
-    const int lim = (int)(227 * 1024);
-    CPD_CUDA_CHECK(cudaFuncSetAttribute(attention4_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-    CPD_CUDA_CHECK(cudaFuncSetAttribute(attention4_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-    CPD_CUDA_CHECK(cudaFuncSetAttribute(attention4_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-    CPD_CUDA_CHECK(cudaFuncSetAttribute(attention4_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-    CPD_CUDA_CHECK(cudaFuncSetAttribute(attention4_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-    configured = true;
-  }
+  // (Moving a share of the exponentials to an FMA-pipe polynomial was measured in round 1 - 747 / 771 / 842 us against 724 us
+  // with 25 / 33 / 50 % moved - and removed: the softmax warps are bound by their own instruction stream, not by the MUFU pipe.)
+  const int lim = (int)(227 * 1024);
+  CPD_SMEM_OPTIN((attention4_kernel<true, true>), lim);
+  CPD_SMEM_OPTIN((attention4_kernel<true, false>), lim);
+  CPD_SMEM_OPTIN((attention4_kernel<false, true>), lim);
+  CPD_SMEM_OPTIN((attention4_kernel<false, false>), lim);
   dim3 grid((p->nq + 2 * BQ - 1) / (2 * BQ), p->heads, p->batch);
   const dim3 block(NUM_THREADS);
   cudaStream_t st = (cudaStream_t)stream;
-  if (!sep) CPD_CUDA_CHECK(cpd_launch(attention4_kernel<false, 0>, grid, block, shm, st, a));
-  else if (poly == 2) CPD_CUDA_CHECK(cpd_launch(attention4_kernel<true, 2>, grid, block, shm, st, a));
-  else if (poly == 3) CPD_CUDA_CHECK(cpd_launch(attention4_kernel<true, 3>, grid, block, shm, st, a));
-  else if (poly == 4) CPD_CUDA_CHECK(cpd_launch(attention4_kernel<true, 4>, grid, block, shm, st, a));
-  else CPD_CUDA_CHECK(cpd_launch(attention4_kernel<true, 0>, grid, block, shm, st, a));
+  const bool f16 = p->act_fp16 != 0;
+  if (sep && f16) CPD_CUDA_CHECK(cpd_launch(attention4_kernel<true, true>, grid, block, shm, st, a));
+  else if (sep) CPD_CUDA_CHECK(cpd_launch(attention4_kernel<true, false>, grid, block, shm, st, a));
+  else if (f16) CPD_CUDA_CHECK(cpd_launch(attention4_kernel<false, true>, grid, block, shm, st, a));
+  else CPD_CUDA_CHECK(cpd_launch(attention4_kernel<false, false>, grid, block, shm, st, a));
   CPD_CUDA_CHECK(cudaGetLastError());
   return CPD_OK;
 }

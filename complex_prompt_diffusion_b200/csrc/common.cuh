@@ -38,6 +38,19 @@ void cpd_set_error(const char* fmt, ...);
     }                                             \
   } while (0)
 
+// Opt a kernel in to > 48 KB of dynamic shared memory once PER DEVICE (the attribute is per device, and a process may drive
+// several GPUs): `kernel` in parentheses when it is a template specialisation with commas.
+#define CPD_SMEM_OPTIN(kernel, bytes)                                                                          \
+  do {                                                                                                         \
+    static unsigned long long _cpd_done = 0;                                                                   \
+    int _cpd_dev = 0;                                                                                          \
+    CPD_CUDA_CHECK(cudaGetDevice(&_cpd_dev));                                                                  \
+    if (!((_cpd_done >> (_cpd_dev & 63)) & 1ull)) {                                                            \
+      CPD_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      _cpd_done |= 1ull << (_cpd_dev & 63);                                                                    \
+    }                                                                                                          \
+  } while (0)
+
 // Every kernel is launched with programmatic stream serialization (PDL): it may start while its predecessor in the
 // stream is still draining, runs its data-independent prologue (barrier init, TMEM allocation, tensor-map prefetch,
 // weight staging) and blocks in pdl_wait() until the predecessor has completed and flushed.  CPD_PDL=0 disables it.
@@ -374,6 +387,11 @@ __device__ __forceinline__ uint32_t pack_act2(float lo, float hi, bool f16) { re
 __device__ __forceinline__ float2 unpack_act2(uint32_t u, bool f16) { return f16 ? unpack_f16x2(u) : unpack_bf16x2(u); }
 __device__ __forceinline__ float round_act(float v, bool f16) {
   return f16 ? __half2float(__float2half_rn(v)) : __bfloat162float(__float2bfloat16_rn(v));
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {  // FMNMX3 (sm_100): one instruction
+  float m;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(m) : "f"(a), "f"(b), "f"(c));
+  return m;
 }
 __device__ __forceinline__ float fast_ex2(float x) {  // MUFU.EX2, no range fix-ups (inputs are <= ~8 here)
   float y;

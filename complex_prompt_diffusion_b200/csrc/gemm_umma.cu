@@ -228,11 +228,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_conv_kernel(const __grid_
 template <int BN, int STAGES>
 cpd_status launch(const GemmArgs& args, int m_tiles, int n_tiles, cudaStream_t s) {
   using L = SmemLayout<BN, STAGES>;
-  static bool configured = false;
-  if (!configured) {
-    CPD_CUDA_CHECK(cudaFuncSetAttribute(gemm_conv_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    configured = true;
-  }
+  CPD_SMEM_OPTIN((gemm_conv_kernel<BN, STAGES>), L::TOTAL);
   CPD_CUDA_CHECK(cpd_launch(gemm_conv_kernel<BN, STAGES>, dim3(dim3(m_tiles, n_tiles)), dim3(NUM_THREADS), L::TOTAL, s, args));
   CPD_CUDA_CHECK(cudaGetLastError());
   return CPD_OK;

@@ -755,11 +755,7 @@ TileChoice pick_tiles(int m_tiles2, int n_out, int num_k, bool geglu, int geglu_
 
 template <int MC>
 cpd_status launch2(const Gemm2Args& args, int smem_bytes, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    CPD_CUDA_CHECK(cudaFuncSetAttribute(gemm2_kernel<MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
+  CPD_SMEM_OPTIN(gemm2_kernel<MC>, 227 * 1024);
   const long steps = (long)args.m_tiles2 * (args.n_tiles / MC) * args.splits;
   const int max_clusters = MC == 2 ? 33 : NUM_SM_PAIRS;
   const int clusters = (int)(steps < max_clusters ? steps : max_clusters);

@@ -625,11 +625,7 @@ extern "C" cpd_status cpd_groupnorm(const void* a0, const void* a1, int c0, int 
           const dim3 grid(C / slab_c, n_img);
 #define CPD_GN_FUSED_LAUNCH(F, VV)                                                                                        \
   do {                                                                                                                    \
-    static bool attr = false;                                                                                             \
-    if (!attr) {                                                                                                          \
-      CPD_CUDA_CHECK(cudaFuncSetAttribute(gn_fused_kernel<F, VV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-      attr = true;                                                                                                        \
-    }                                                                                                                     \
+    CPD_SMEM_OPTIN((gn_fused_kernel<F, VV>), 200 * 1024);                                                                 \
     CPD_CUDA_CHECK(cpd_launch(gn_fused_kernel<F, VV>, grid, dim3(threads), shm, s, (const bf16*)a0, (const bf16*)a1, c0, c1, hw, \
                               slab_c, gamma, beta, eps, silu, (bf16*)out));                                               \
   } while (0)
@@ -672,11 +668,7 @@ extern "C" cpd_status cpd_groupnorm(const void* a0, const void* a1, int c0, int 
             const dim3 grid((C / slab_c) * CLs, n_img);
 #define CPD_GN_CL_LAUNCH(F, VV, CC)                                                                                        \
   do {                                                                                                                     \
-    static bool attr = false;                                                                                              \
-    if (!attr) {                                                                                                           \
-      CPD_CUDA_CHECK(cudaFuncSetAttribute(gn_cluster_kernel<F, VV, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
-      attr = true;                                                                                                         \
-    }                                                                                                                      \
+    CPD_SMEM_OPTIN((gn_cluster_kernel<F, VV, CC>), 200 * 1024);                                                            \
     CPD_CUDA_CHECK(cpd_launch(gn_cluster_kernel<F, VV, CC>, grid, dim3(threads), shm, s, (const bf16*)a0, (const bf16*)a1, c0, c1, \
                               hw, slab_c, gamma, beta, eps, silu, (bf16*)out));                                            \
   } while (0)
@@ -723,14 +715,10 @@ extern "C" cpd_status cpd_groupnorm(const void* a0, const void* a1, int c0, int 
   const size_t shm = ring_bytes + sizeof(float) * (2 * C + 2 * GROUPS);
   const size_t shm_stats = ring_bytes + sizeof(float) * 2 * C * lanes;
   CPD_REQUIRE(shm_stats <= 160 * 1024 && shm <= 160 * 1024, "cpd_groupnorm: C=%d needs %zu bytes of shared memory", C, shm_stats);
-  static bool cfg = false;
-  if (!cfg) {
-    CPD_CUDA_CHECK(cudaFuncSetAttribute(gn_stats_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    CPD_CUDA_CHECK(cudaFuncSetAttribute(gn_stats_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    CPD_CUDA_CHECK(cudaFuncSetAttribute(gn_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    CPD_CUDA_CHECK(cudaFuncSetAttribute(gn_apply_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    cfg = true;
-  }
+  CPD_SMEM_OPTIN(gn_stats_kernel<true>, 160 * 1024);
+  CPD_SMEM_OPTIN(gn_stats_kernel<false>, 160 * 1024);
+  CPD_SMEM_OPTIN(gn_apply_kernel<true>, 160 * 1024);
+  CPD_SMEM_OPTIN(gn_apply_kernel<false>, 160 * 1024);
   const dim3 grid(chunks, n_img);
   if (act_fp16) {
     CPD_CUDA_CHECK(cpd_launch(gn_stats_kernel<true>, grid, dim3(threads), shm_stats, s, (const bf16*)a0, (const bf16*)a1, c0, c1, hw, px_per_block, stats));

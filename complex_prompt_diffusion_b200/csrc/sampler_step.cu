@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256, VEC == 8 ? 3 : 4) sampler_step_kernel(con
     }
     float et[VEC], den[VEC], xn[VEC];
     const float clip = (FULL && p.clip_scaled) ? __ldg(p.clip_scaled + b) : 0.f;
-    const float nmul = p.noise_mul == 0.f ? 1.f : p.noise_mul;
+    const float nmul = p.noise_mul;  // used as given: 0 adds no noise (temperature = 0, dpmpp.py:111)
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       const float sj = (j & 1) ? __high2float(sum[j >> 1]) : __low2float(sum[j >> 1]);

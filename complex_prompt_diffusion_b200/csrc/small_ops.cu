@@ -523,11 +523,7 @@ extern "C" cpd_status cpd_small_linear(const void* x, int m, int k, const void* 
   const int blocks = (n + 7) / 8;
 #define LAUNCH_SL(MT)                                                                                                         \
   do {                                                                                                                        \
-    static bool cfg = false;                                                                                                  \
-    if (!cfg) {                                                                                                               \
-      CPD_CUDA_CHECK(cudaFuncSetAttribute(small_linear_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); \
-      cfg = true;                                                                                                             \
-    }                                                                                                                         \
+    CPD_SMEM_OPTIN(small_linear_kernel<MT>, 160 * 1024);                                                                      \
     CPD_CUDA_CHECK(cpd_launch(small_linear_kernel<MT>, dim3(blocks), dim3(256), shm, s, (const bf16*)x, m, k, (const bf16*)w, b, n, silu_in, out_f32,           \
                                                       (bf16*)out_bf16, ld_out));                                              \
   } while (0)
@@ -547,19 +543,9 @@ extern "C" cpd_status cpd_conv_in(const float* x, int n, int cin, int h, int w, 
   const int64_t total = (int64_t)n * h * w * (cout / 8);
   const size_t shm = (size_t)9 * cin * cout * sizeof(float);
   CPD_REQUIRE(shm <= 100 * 1024, "cpd_conv_in: cin=%d x cout=%d weights do not fit 100 KB of shared memory", cin, cout);
-  {
-    static bool cfg = false;
-    if (!cfg) {
-      CPD_CUDA_CHECK(cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      cfg = true;
-    }
-  }
+  CPD_SMEM_OPTIN(conv_in_kernel, 100 * 1024);
   if (cin == 4 && w % 4 == 0 && (int64_t)n * h * w * (cout / 8) < (int64_t)1 << 31) {
-    static bool cfg4 = false;
-    if (!cfg4) {
-      CPD_CUDA_CHECK(cudaFuncSetAttribute(conv_in4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      cfg4 = true;
-    }
+    CPD_SMEM_OPTIN(conv_in4_kernel, 100 * 1024);
     int64_t blocks4 = (total / 4 + 255) / 256;
     if (blocks4 > 148 * 2) blocks4 = 148 * 2;
     CPD_CUDA_CHECK(cpd_launch(conv_in4_kernel, dim3((unsigned)blocks4), dim3(256), shm, (cudaStream_t)stream, x, n, h, w, (const bf16*)wt, bias, cout, scale,
@@ -596,12 +582,8 @@ extern "C" cpd_status cpd_conv_out(const void* a, int n, int h, int w, int cin, 
     }
     const size_t need = (size_t)9 * (cin / 8) * 4 * 8 * 4 + (size_t)nw * 4 * CO_TP * 4 + (size_t)3 * (cin / 8) * pp * 16;
     if (tiled && need <= 227 * 1024) {
-      static bool cfg = false;
-      if (!cfg) {
-        CPD_CUDA_CHECK(cudaFuncSetAttribute(conv_out_tiled_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        CPD_CUDA_CHECK(cudaFuncSetAttribute(conv_out_tiled_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        cfg = true;
-      }
+      CPD_SMEM_OPTIN(conv_out_tiled_kernel<8>, 227 * 1024);
+      CPD_SMEM_OPTIN(conv_out_tiled_kernel<16>, 227 * 1024);
       const int64_t tiles = (int64_t)n * h * ((w + CO_TP - 1) / CO_TP);
       const unsigned blocks = (unsigned)(tiles < 148 ? tiles : 148);
       if (nw == 8)
@@ -617,12 +599,10 @@ extern "C" cpd_status cpd_conv_out(const void* a, int n, int h, int w, int cin, 
   unsigned blocks = (unsigned)((pixels + 7) / 8);
   if (blocks > 148 * 8) blocks = 148 * 8;  // persistent: weights staged once per block, full occupancy (64 warps per SM)
   if (cout == 4) {
-    static bool cfg = false;
-    if (!cfg) { CPD_CUDA_CHECK(cudaFuncSetAttribute(conv_out_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfg = true; }
+    CPD_SMEM_OPTIN(conv_out_kernel<4>, 200 * 1024);
     CPD_CUDA_CHECK(cpd_launch(conv_out_kernel<4>, dim3(blocks), dim3(256), shm, s, (const bf16*)a, n, h, w, cin, (const bf16*)wt, bias, out, out_dtype, act_fp16));
   } else {
-    static bool cfg = false;
-    if (!cfg) { CPD_CUDA_CHECK(cudaFuncSetAttribute(conv_out_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfg = true; }
+    CPD_SMEM_OPTIN(conv_out_kernel<8>, 200 * 1024);
     CPD_CUDA_CHECK(cpd_launch(conv_out_kernel<8>, dim3(blocks), dim3(256), shm, s, (const bf16*)a, n, h, w, cin, (const bf16*)wt, bias, out, out_dtype, act_fp16));
   }
   CPD_CUDA_CHECK(cudaGetLastError());

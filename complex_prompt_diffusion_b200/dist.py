@@ -64,28 +64,65 @@ def partition(batch: int, rows_total: int, world: int, rank: int) -> Partition:
     return Partition(world, rank, [g], rows, members, rows_total)
 
 
+class RowGatherPlan:
+    """Preallocated buffers of the per-step eps all-gather (one `all_gather_into_tensor` on the compute stream, no per-step
+    allocation, list or cat): `send` [max_rows, L] is what this rank contributes, `recv` [size * max_rows, L] what it
+    receives.  When every active rank owns the same number of rows and no rank idles, `recv` already IS the row-ordered
+    [rows_total, L] result; otherwise one index_select with a fixed index picks the valid rows."""
+
+    def __init__(self, part: Partition, L: int, dtype, device):
+        size = len(part.group_ranks)
+        self.active = min(size, part.rows_total)
+        self.max_rows = -(-part.rows_total // self.active)
+        self.send = torch.zeros(self.max_rows, L, dtype=dtype, device=device)
+        self.recv = torch.empty(size * self.max_rows, L, dtype=dtype, device=device)
+        rb, re_ = divmod(part.rows_total, self.active)
+        idx = []
+        for local in range(self.active):
+            n = rb + (1 if local < re_ else 0)
+            idx += [local * self.max_rows + k for k in range(n)]
+        self.direct = idx == list(range(part.rows_total)) and size * self.max_rows == part.rows_total
+        self.index = None if self.direct else torch.tensor(idx, dtype=torch.long, device=device)
+        self.key = (tuple(part.group_ranks), part.rows_total, L, dtype, torch.device(device))
+
+
+_ROW_PLANS = {}
+_GROUPS = {}  # world size -> {member ranks: process group}
+
+
 def allgather_eps_rows(local_rows: torch.Tensor, part: Partition, group=None) -> torch.Tensor:
     """local_rows: [len(part.rows), L] eps rows this rank computed for its image.  Returns [rows_total, L] on every
-    rank of the group (row order 0..rows_total-1).  Uses all_gather on a padded buffer (row counts differ by <= 1)."""
+    rank of the group (row order 0..rows_total-1): a preallocated `all_gather_into_tensor` (row counts differ by <= 1, so
+    every rank sends max_rows rows; ranks with fewer leave the tail of their block unused)."""
     import torch.distributed as dist
     if not part.needs_allgather:
         return local_rows
-    size = len(part.group_ranks)
-    active = min(size, part.rows_total)
-    max_rows = -(-part.rows_total // active)
     if local_rows.ndim != 2:
         raise ValueError("allgather_eps_rows expects [rows, L]; idle ranks pass an empty [0, L] tensor")
     L = local_rows.shape[1]
-    buf = local_rows.new_zeros(max_rows, L)
-    buf[: local_rows.shape[0]] = local_rows
-    out = [torch.empty_like(buf) for _ in range(size)]
-    dist.all_gather(out, buf, group=group)
-    rows = []
-    for local in range(active):
-        rb, re_ = divmod(part.rows_total, active)
-        n = rb + (1 if local < re_ else 0)
-        rows.append(out[local][:n])
-    return torch.cat(rows)
+    key = (tuple(part.group_ranks), part.rows_total, L, local_rows.dtype, local_rows.device)
+    plan = _ROW_PLANS.get(key)
+    if plan is None:
+        plan = _ROW_PLANS[key] = RowGatherPlan(part, L, local_rows.dtype, local_rows.device)
+    if local_rows.shape[0]:
+        plan.send[: local_rows.shape[0]].copy_(local_rows)
+    dist.all_gather_into_tensor(plan.recv, plan.send, group=group)
+    return plan.recv if plan.direct else plan.recv.index_select(0, plan.index)
+
+
+def shared_noise_sampler(base, group, src):
+    """Row-sharded groups step a REPLICATED x: every stochastic draw (ancestral noise, churn, the img2img start noise) must
+    be the same tensor on every rank of the group.  The group leader (global rank `src`) draws - through the caller's
+    `noise_sampler` if there is one - and broadcasts; the other ranks' own draws are discarded (their RNG streams still
+    advance in step)."""
+    import torch.distributed as dist
+
+    def draw(x):
+        n = base(x) if base is not None else torch.randn_like(x)
+        n = n.to(x.device, torch.float32).contiguous()
+        dist.broadcast(n, src=src, group=group)
+        return n
+    return draw
 
 
 def gather_images(local_x: torch.Tensor, batch: int, world: int, group=None) -> torch.Tensor:
@@ -116,18 +153,29 @@ def sample_sharded(wrapper, *, steps, batch, shape, x_T, conditioning, unconditi
     groups = None
     if batch < world:
         # one NCCL sub-group per image (every rank must create every group, in the same order)
-        groups, seen = {}, set()
+        # (communicators are cached: creating one costs far more than a whole generation)
+        groups, seen = _GROUPS.setdefault(world, {}), set()
         for r in range(world):
             members = tuple(partition(batch, rows_total, world, r).group_ranks)
             if members not in seen:
                 seen.add(members)
-                groups[members] = dist.new_group(list(members)) if len(members) > 1 else None
-        sampler.denoiser.set_row_partition(part, groups[tuple(part.group_ranks)])
+                if members not in groups:
+                    groups[members] = dist.new_group(list(members)) if len(members) > 1 else None
+        grp = groups[tuple(part.group_ranks)]
+        sampler.denoiser.set_row_partition(part, grp)
+        if len(part.group_ranks) > 1:  # one draw per group, not per rank (ancestral / churn / img2img noise)
+            shared = shared_noise_sampler(kw.get("noise_sampler"), grp, part.group_ranks[0])
+            kw["noise_sampler"] = shared
+            sampler.noise_sync = shared
     else:
         sampler.denoiser.set_row_partition(None)
+        sampler.noise_sync = None
     mine = x_T[part.images]
-    out = sampler.sample(steps=steps, batch_size=len(part.images), shape=shape, x_T=mine, conditioning=conditioning,
-                         unconditional_conditioning=unconditional_conditioning, **kw)
+    try:
+        out = sampler.sample(steps=steps, batch_size=len(part.images), shape=shape, x_T=mine, conditioning=conditioning,
+                             unconditional_conditioning=unconditional_conditioning, **kw)
+    finally:
+        sampler.noise_sync = None
     if batch >= world:
         return gather_images(out, batch, world)
     # row-sharded: every rank of a group holds the same image; gather one copy per image

@@ -9,9 +9,9 @@ synchronisation happens inside a step (the reference has five).
 
 Differences that are deliberate repairs of reference defects: the image batch may be > 1 and
 means B independent batch-1 trajectories (D7); sigma is passed once (D3); no hard-coded `.cuda()` (D6).
-Branches that are outside the hot-path scope (attention guidance, CLIP guidance, score correctors, dynamic
-scale clipping, unconditional blur, feature/attention injection, depth masks, gamma > 0) raise
-NotImplementedError when requested instead of being silently ignored.
+Built on the device: dynamic / static scale clipping and every runnable thresholding extension, the score-corrector
+hook, feature / skip injection, the decaying guidance scale.  CLIP guidance (a backward pass through VAE + CLIP) and
+gamma > 0 (defective in the reference, D8) raise NotImplementedError when requested instead of being silently ignored.
 """
 import math
 
@@ -191,8 +191,14 @@ class Denoiser(torch.nn.Module):
         for (scale, emb, _guide, mask) in entries:
             items += [scale, emb, mask]
         for t in items:
-            out.append(t._version if isinstance(t, torch.Tensor) else (float(t) if isinstance(t, (int, float)) else None))
+            # (object, version): the object itself is held by the key, so an entry REPLACED by a fresh tensor of the same
+            # layout (version 0 again) is seen as a different object - never compare id()s of objects that may have died
+            out.append((t, t._version) if isinstance(t, torch.Tensor) else (None, float(t) if isinstance(t, (int, float)) else None))
         return out
+
+    @staticmethod
+    def _same_versions(a, b):
+        return len(a) == len(b) and all(x[0] is y[0] and x[1] == y[1] for x, y in zip(a, b))
 
     def plan_conditioning(self, c, uc, hw_shape, y=None, force=False):
         """`y` (extension for UNets with vector conditioning, i.e. SDXL - not expressible by the reference): tensor
@@ -206,7 +212,7 @@ class Denoiser(torch.nn.Module):
             raise ValueError("conditioning must be a dict with an 'and' list (CompositionalPrompt._build_embeddings)")
         key = (c, uc, y, tuple(hw_shape), self._versions(c, uc, y))
         k0 = self._plan_key
-        same = (not force and k0 is not None and k0[0] is c and k0[1] is uc and k0[2] is y and k0[3] == key[3] and k0[4] == key[4])
+        same = (not force and k0 is not None and k0[0] is c and k0[1] is uc and k0[2] is y and k0[3] == key[3] and self._same_versions(k0[4], key[4]))
         if not same:
             self._plan = ConditioningPlan(c, uc, self.dtype, self.device, hw_shape)
             self._plan_key = key
@@ -251,10 +257,19 @@ class Denoiser(torch.nn.Module):
         return dict(feats=kwargs.get("inject_feats"), feats_stop=kwargs.get("inject_feats_stop", 10),
                     attns=kwargs.get("inject_attns"), attns_stop=kwargs.get("inject_attns_stop", 10))
 
+    @staticmethod
+    def _one_sigma(sigma):
+        """All images of a batch share the schedule (B independent trajectories, D7): a per-image sigma vector must hold one
+        value.  Returns a 1-element fp32 CPU tensor."""
+        sig = torch.as_tensor(sigma, dtype=torch.float32).reshape(-1).cpu()
+        if sig.numel() > 1 and not bool((sig == sig[0]).all()):
+            raise ValueError("Denoiser: the images of a batch must share one sigma (got a vector with different values)")
+        return sig[:1]
+
     def unet_rows(self, x, sigma, plan, inject=None):
         """Run the UNet on the (1 + N) conditioning rows of every image: returns eps rows [B*(1+N), 4, h, w]
         (image-major).  x: [B,4,h,w] fp32; sigma: 0-dim/1-element fp32 CPU tensor (same for all images)."""
-        sig = torch.as_tensor(sigma, dtype=torch.float32).reshape(-1)[:1].cpu()
+        sig = self._one_sigma(sigma)
         c_in = 1 / (sig ** 2 + 1 ** 2) ** 0.5  # get_scalings, fp32 like denoiser.py:390
         t = self.scheduler.sigma_to_t(sig).to(self.dtype).float()  # fp64 -> model dtype (P3, denoiser.py:393)
         if self._part is None:
@@ -275,11 +290,12 @@ class Denoiser(torch.nn.Module):
         full = D.allgather_eps_rows(local, self._part, group=self._group)
         return full.reshape(1 + plan.n_sub, *x.shape[1:]).contiguous()
 
-    def fused_step(self, x, sigma, plan, step, **kwargs):
+    def fused_step(self, x, sigma, plan, step, eps=None, **kwargs):
         """One UNet evaluation + ONE fused kernel: CFG combine, denoised, sampler update (x updated in place).
-        `step` is a dict of the fp32 scalars for cpd_sampler_step."""
-        eps = self.unet_rows(x, sigma, plan, inject=self._inject(kwargs))
-        sig = float(torch.as_tensor(sigma, dtype=torch.float32).reshape(-1)[0])
+        `step` is a dict of the fp32 scalars for cpd_sampler_step; `eps` = already evaluated UNet rows (skips the UNet)."""
+        if eps is None:
+            eps = self.unet_rows(x, sigma, plan, inject=self._inject(kwargs))
+        sig = float(self._one_sigma(sigma)[0])
         sig_t = torch.tensor([sig], dtype=torch.float32)
         pred = CPD_PRED_VELOCITY if kwargs.get("pred_type", "epsilon") == "velocity" else CPD_PRED_EPSILON
         common = dict(n_sub=plan.n_sub, weights=plan.weights, mask_scalars=plan.mask_scalars, masks=plan.masks,
@@ -321,6 +337,19 @@ class Denoiser(torch.nn.Module):
             return x
         ops.sampler_step(eps, x, clip_scaled=clip, scaled_in=scaled_in, **common, **step)
         return x
+
+    @torch.no_grad()
+    def evaluate(self, x, sigma, **kwargs):
+        """One Denoiser evaluation with its intermediates (parity checks: tests, bench.py's `parity` key): the UNet rows
+        [B * (1 + N), 4, h, w] (denoiser.py:397-402, :439), the combined e_t (:515) and the denoised sample (:540/:542)."""
+        self._check_kwargs(kwargs)
+        x = x.to(self.device, torch.float32).contiguous()
+        plan = self.plan_conditioning(kwargs.get("conditioning"), kwargs.get("unconditional_conditioning"), x.shape[-2:],
+                                      y=kwargs.get("y"))
+        rows = self.unet_rows(x, sigma, plan, inject=self._inject(kwargs)).clone()
+        e_t, denoised = torch.empty_like(x), torch.empty_like(x)
+        self.fused_step(x.clone(), sigma, plan, dict(sampler=CPD_DENOISE_ONLY, denoised_out=denoised, eps_out=e_t), eps=rows, **kwargs)
+        return dict(rows=rows, e_t=e_t, denoised=denoised)
 
     @torch.no_grad()
     def forward(self, x, sigma, **kwargs):

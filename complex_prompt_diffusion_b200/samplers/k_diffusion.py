@@ -13,6 +13,7 @@ from .extension.denoiser import Denoiser
 class KDiffusionSampler:
     def __init__(self, model, name="sample_heun"):
         self.name = name
+        self.noise_sync = None  # dist.sample_sharded: replaces a locally drawn noise tensor by the row-sharding group's shared draw
         self.denoiser = Denoiser(model["unet"], model.get("vae"), model.get("tokenizer"), model.get("clip_new_model"),
                                  model.get("decode"))
 
@@ -34,6 +35,8 @@ class KDiffusionSampler:
             t_enc = int((1 - min(strength, 0.999)) * steps)
             sigmas = sigmas[steps - t_enc - 1:]
             noise = torch.randn([batch_size] + list(shape))
+            if self.noise_sync is not None:  # row-sharded group: every rank must start from the same noised image
+                noise = self.noise_sync(noise.to(dev)).cpu()
             x = x_T.to(dev, torch.float32) + (noise * sigmas[0]).to(dev, torch.float32)
         else:
             if x_T is None:

@@ -92,7 +92,7 @@ typedef struct {
   const float* d_prev[3];   /* CPD_HEUN2: d of stage 1 in d_prev[0]; CPD_LMS: d_{i-1}, d_{i-2}, d_{i-3} */
   float lms_coeff[4];       /* CPD_LMS: coefficients of d_i, d_{i-1}, d_{i-2}, d_{i-3} (linear_multistep_coeff) */
   int lms_order;            /* CPD_LMS: min(i + 1, order), 1..4 */
-  float noise_mul;          /* noise is multiplied by this (s_noise / temperature) before sigma_up; 0 is read as 1 */
+  float noise_mul;          /* noise is multiplied by this (s_noise / temperature) before sigma_up; used as given (set 1 for plain noise) */
   /* Thresholding extensions (samplers/extension/threshold.py:65-88 "dynamic_thresholding", 47-63 "static_thresholding"),
    * with the clamp bound s = max(percentile(|.|), 1) computed ON THE DEVICE by cpd_abs_percentile_max1: */
   const float* clip_scaled; /* optional DEVICE array [n_images] (from cpd_threshold): the scaled guidance term s * sum_e_t of

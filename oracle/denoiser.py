@@ -127,6 +127,8 @@ class OracleDenoiser:
         else:
             raise ValueError(pred_type)
         if self.trace is not None:
+            self.trace[-1]["x"] = x.detach().float().clone()
+            self.trace[-1]["sigma"] = torch.as_tensor(sigma).detach().clone()
             self.trace[-1]["eps"] = eps.detach().float().clone()
             self.trace[-1]["denoised"] = sample.detach().float().clone()
         return sample

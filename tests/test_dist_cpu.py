@@ -65,7 +65,21 @@ def _worker(rank, world, port, q):
         x = torch.arange(5 * 4, dtype=torch.float32).view(5, 4)
         got2 = D.gather_images(x[pi.images].clone(), 5, world)
         ok2 = torch.equal(got2, x)
-        q.put((rank, ok1, ok2))
+        # twice through the cached plan (preallocated buffers are reused), equal row counts: 4 rows over 2 ranks
+        part4 = D.partition(1, 4, world, rank)
+        full4 = torch.arange(4 * L, dtype=torch.float32).view(4, L) + 100.0
+        for rep in range(2):
+            ok1 = ok1 and torch.equal(D.allgather_eps_rows((full4 + rep)[part4.rows].clone(), part4), full4 + rep)
+        # group-shared noise (row-sharded stochastic samplers): per-rank RNG streams differ, the draw must not
+        torch.manual_seed(1234 + rank)
+        draw = D.shared_noise_sampler(None, None, 0)
+        n1, n2 = draw(torch.zeros(2, 3)), draw(torch.zeros(2, 3))
+        gathered = [torch.empty_like(n1) for _ in range(world)]
+        dist.all_gather(gathered, torch.cat([n1, n2])[:2])
+        ok3 = all(torch.equal(g, gathered[0]) for g in gathered) and not torch.equal(n1, n2)
+        custom = D.shared_noise_sampler(lambda x: torch.full_like(x, float(rank + 7)), None, 0)
+        ok3 = ok3 and torch.equal(custom(torch.zeros(4)), torch.full((4,), 7.0))
+        q.put((rank, ok1, ok2 and ok3))
     finally:
         dist.destroy_process_group()
 

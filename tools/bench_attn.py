@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 SHAPES = [  # B, H, Nq, Nk, d
     (16, 8, 4096, 4096, 40), (16, 8, 1024, 1024, 80), (16, 8, 256, 256, 160), (16, 8, 4096, 77, 40), (16, 8, 1024, 77, 80),
-    (8, 5, 9216, 9216, 64),
+    (8, 5, 9216, 9216, 64), (16, 8, 256, 77, 160), (8, 5, 9216, 77, 64), (16, 10, 1024, 77, 64),
 ]
 
 
@@ -26,6 +26,7 @@ def main():
         dpad = (d + 15) // 16 * 16
         nk_pad = (Nk + 15) // 16 * 16
         ip = H * dpad
+        kvb = 4 if (Nk == 77 and B % 4 == 0) else B  # cross-attention: the context rows are shared by the images of a batch
         q = torch.zeros(B * Nq, H, dpad, device="cuda", dtype=torch.float16)
         k = torch.zeros(B * nk_pad, H, dpad, device="cuda", dtype=torch.float16)
         q[..., :d] = torch.randn(B * Nq, H, d, device="cuda")
@@ -36,7 +37,7 @@ def main():
 
         def run():
             ops.attention(q, k, vt, o, ldq=ip, ldk=ip, ldvt=B * nk_pad, ldo=ip, batch=B, heads=H, nq=Nq, nk=Nk, nk_pad=nk_pad, dpad=dpad,
-                          scale=d ** -0.5, d_head=d)
+                          scale=d ** -0.5, d_head=d, kv_batch=kvb)
         for _ in range(3):
             run()
         torch.cuda.synchronize()

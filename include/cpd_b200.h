@@ -207,9 +207,20 @@ typedef struct {
   int geglu_block; /* CPD_EPI_GEGLU: interleave block of wt rows (128 or 256; 0 = 128) */
   float* splitk_ws;         /* optional fp32 scratch for split-K launches (variant >= 10000): >= S * pixels * n_out floats */
   int64_t splitk_ws_floats; /* (one slice per K range, summed in a fixed order by the finalize kernel: no atomics) */
+  void* tune_scratch;       /* optional scratch the size of d: with variant 0 an unseen problem shape is first TIMED on every */
+  int64_t tune_scratch_bytes; /* applicable tile variant (output redirected here, CUDA events, synchronous) and the fastest is */
+                            /* remembered per shape; NULL = no timing (tuned table if the shape is known, else the cost model) */
 } cpd_gemm_params;
 
 cpd_status cpd_gemm_conv(const cpd_gemm_params* p, void* stream);
+
+/* The per-shape variant table behind variant 0.  Timing picks between candidates that are often within a few per cent, so two
+ * processes can choose differently (different fp32 summation order at the 1e-7 level): export the table of one process and
+ * import it into the others (ranks of a job) - or set CPD_GEMM_AUTOTUNE=0 - when bit-identical results across processes
+ * matter.  Export writes a NUL-terminated text ("k0,k1,...=variant" lines) and returns the bytes needed (call with cap = 0
+ * to size the buffer); import merges a text into the table and returns the number of entries read or -1. */
+int64_t cpd_gemm_tune_export(char* buf, int64_t cap);
+int cpd_gemm_tune_import(const char* text);
 
 /*
  * GroupNorm(32 groups) [+ SiLU] over NHWC bf16, fp32 statistics (models/util.py:95-105, attention.py:89-90).
@@ -288,6 +299,89 @@ cpd_status cpd_softmax_rows(const void* x, int rows, int cols, int64_t ld, float
  * 1 / scale_factor of decode_first_stage folded in: out[n][o][p] = b[o] + sum_c w[o][c] * (x[n][c][p] * scale). */
 cpd_status cpd_pointwise_small(const float* x, int n, int cin, int cout, int64_t hw, const float* w, const float* b, float scale,
                                float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Plan-level UNet entry points: ONE call evaluates the whole UNet of cpd/models/unet.py:765-831.
+ * The plan owns the packed weights, the text-context K / V^T cache, every workspace buffer and (optionally) a CUDA graph of
+ * the ~850 kernel launches of an evaluation.  A non-Python host needs nothing else:
+ *     cpd_unet_plan_create -> cpd_pack_weights (once per state_dict entry) -> cpd_cache_context_kv (once per prompt)
+ *     -> cpd_unet_forward (once per sampler step) -> cpd_unet_plan_destroy.
+ * One plan per device (the device current at creation); re-entrant per plan, not thread-safe on one plan.
+ * Device memory is allocated at creation, while packing, when a context is cached and the FIRST time a new
+ * (rows, h, w) shape is evaluated (workspace + optional graph capture) - never inside a steady-state forward.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct cpd_unet_plan cpd_unet_plan;
+
+#define CPD_UNET_MAX_LEVELS 8
+typedef struct {
+  /* constructor arguments of UNetModel (unet.py:415-470; config-1.49.yaml:27-42, v2-inference.yaml:20-37) */
+  int in_channels, out_channels, model_channels, num_res_blocks;
+  int n_levels;
+  int channel_mult[CPD_UNET_MAX_LEVELS];
+  int n_attention_resolutions;
+  int attention_resolutions[CPD_UNET_MAX_LEVELS]; /* downsample factors (1, 2, 4, ...) that carry a SpatialTransformer */
+  int num_heads;          /* used when num_head_channels == -1 */
+  int num_head_channels;  /* -1 or the fixed head width (SD-2.x / SDXL: 64) */
+  int transformer_depth[CPD_UNET_MAX_LEVELS];     /* per level; the middle block uses the last level's (the reference has one int) */
+  int context_dim;
+  int use_linear_in_transformer; /* accepted for the state_dict shapes: a 1x1 conv and a Linear are the same GEMM here */
+  int adm_in_channels;    /* > 0: vector conditioning y through label_emb (SDXL extension), 0 otherwise */
+  int act_fp16;           /* inter-kernel activations / tensor-core operands: 1 = fp16 (default of the Python host), 0 = bf16 */
+  int eps_dtype;          /* CPD_F32 or CPD_BF16: element type of the eps output */
+  int use_cuda_graph;     /* 1: every (shape, rows) is captured once into a CUDA graph owned by the plan and replayed */
+} cpd_unet_config;
+
+cpd_status cpd_unet_plan_create(const cpd_unet_config* cfg, cpd_unet_plan** plan);
+void cpd_unet_plan_destroy(cpd_unet_plan* plan);
+
+/* One state_dict entry under its REFERENCE name ("input_blocks.1.0.in_layers.2.weight", ...; cpd/models/unet.py,
+ * attention.py).  `data` holds `numel` elements of dtype CPD_F32 / CPD_F16 / CPD_BF16 on the host (on_device = 0) or the
+ * device (1).  Every value is first rounded to the model dtype (bf16, manager.py:25-36), then packed for the kernels:
+ * conv weights K-major [Cout][ky][kx][Cin], head dims padded to multiples of 16, Q | K of self-attention fused, GEGLU
+ * rows interleaved per 256-column tile, the 22 emb_layers concatenated.  Unknown names return CPD_ERR_INVALID. */
+cpd_status cpd_pack_weights(cpd_unet_plan* plan, const char* name, const void* data, int dtype, int64_t numel, int on_device);
+/* Number of state_dict entries the plan still misses (0 = ready); the first missing name is left in cpd_last_error(). */
+int cpd_unet_plan_missing_weights(cpd_unet_plan* plan);
+
+/* Text context [rows][tokens][context_dim] (device, dtype CPD_F32 / CPD_F16 / CPD_BF16): rounded to the model dtype
+ * (denoiser.py:373-385) and projected ONCE through every cross-attention layer's to_k / to_v (attention.py:283-296); the
+ * K / V^T buffers are persistent (stable addresses), so captured graphs stay valid across prompts of the same layout.
+ * UNet row r attends to context row (r % rows). */
+cpd_status cpd_cache_context_kv(cpd_unet_plan* plan, const void* context, int dtype, int rows, int tokens, void* stream);
+/* Vector conditioning y [rows][adm_in_channels] (device) of UNets with adm_in_channels > 0; UNet row r uses y row (r % rows). */
+cpd_status cpd_unet_set_vector(cpd_unet_plan* plan, const void* y, int dtype, int rows, void* stream);
+
+typedef struct {
+  const float* x;        /* device fp32 NCHW [n_images][in_channels][h][w]: the UNSCALED latents (k_diffusion.py:73-74) */
+  int n_images, h, w;
+  int rows_per_image;    /* every image is evaluated on this many conditioning rows sharing x * c_in (denoiser.py:383-391) */
+  const float* c_in;     /* DEVICE pointer to the input scale 1 / sqrt(sigma^2 + 1) (denoiser.py:390), or NULL for 1 */
+  const float* t;        /* DEVICE pointer to the timestep(s), already rounded to the model dtype (denoiser.py:393) */
+  int t_count;           /* 1: shared by all rows (the Denoiser's call); n_images * rows_per_image: one per row */
+  void* eps;             /* device output [n_images * rows_per_image][out_channels][h][w] (image-major rows) in the plan's
+                            eps_dtype, or NULL: the result stays in the plan's own buffer (cpd_unet_plan_buffer "eps") */
+  /* unet.py:806-813 (feature / skip injection) and :802-804,816-817 (return_attn / return_feat); all optional: */
+  const void* const* inject_skips; /* [n output blocks] NHWC activations replacing the popped skip tensor, or NULL entries */
+  const void* const* inject_feats; /* [n output blocks] NHWC activations replacing h before the block, or NULL entries */
+  int no_graph;          /* 1: launch the kernels directly even if the plan uses CUDA graphs (also implied by injection and
+                            by a stream that is being captured by the caller) */
+} cpd_unet_io;
+
+/* eps = UNet(x * c_in, t, cached context) for n_images * rows_per_image rows: unet.py:765-831 with the blocks of
+ * :249-280, attention.py:280-348,485-490,526-537 and models/util.py:65-85,103-105. */
+cpd_status cpd_unet_forward(cpd_unet_plan* plan, const cpd_unet_io* io, void* stream);
+
+/* A named buffer of the plan after a forward: "eps", "<block>.out" (e.g. "input_blocks.4.1.out", NHWC activations: the skip
+ * tensors of return_attn and the features of return_feat), packed weights under their packed names.  *ptr / *numel (elements)
+ * receive the device pointer and size; the buffer with the largest size is returned when several shapes were evaluated. */
+cpd_status cpd_unet_plan_buffer(cpd_unet_plan* plan, const char* name, void** ptr, int64_t* numel);
+/* Kernels launched by the last cpd_unet_forward / cpd_cache_context_kv of this plan (graph replays count their nodes). */
+int64_t cpd_unet_plan_launches(cpd_unet_plan* plan);
+
+/* ---- debug aids (not part of the product path; NULL / never called in production) ---------------------------------------- */
+/* clock64 stamps of CTA 0's first 8 work items of every following cross-attention launch go to dev_buf (192 int64 on the
+ * device); NULL switches it off (tools/attn5_timeline.py). */
+void cpd_debug_attention_cross_timeline(long long* dev_buf);
 
 #ifdef __cplusplus
 }

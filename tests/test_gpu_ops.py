@@ -166,8 +166,9 @@ def test_conv1x1_two_sources(ops):
                                          (2, 3, 300, 700, 40), (1, 2, 1000, 330, 48), (1, 1, 129, 257, 16), (2, 2, 512, 384, 63)])
 @pytest.mark.parametrize("two_tile", [False, True])
 def test_attention(ops, B, H, Nq, Nk, d, two_tile):
-    """two_tile=True passes d_head, which selects the two-query-tile kernel with P in tensor memory (attention_umma2.cu)
-    whenever nq > 128 and d_head <= 111; other shapes fall through to the one-tile kernel."""
+    """two_tile=True passes d_head, which opens the shape dispatch of cpd_attention (one key block -> attention_umma5.cu,
+    d <= 63 with many key blocks -> attention_umma4.cu, otherwise the persistent two-tile kernel attention_umma3.cu);
+    d_head = 0 and shapes outside those domains run the one-tile kernel."""
     g = torch.Generator().manual_seed(B * Nq + d)
     dpad = (d + 15) // 16 * 16
     nk_pad = Nk if Nk % 16 == 0 else (Nk + 15) // 16 * 16
@@ -189,6 +190,39 @@ def test_attention(ops, B, H, Nq, Nk, d, two_tile):
     print(f"attention B{B} H{H} {Nq}x{Nk} d{d} two_tile={two_tile}: rel {r:.3e}")
     assert torch.isfinite(o.float()).all()
     assert r < 1e-2
+    if dpad != d:
+        assert (o[..., d:] == 0).all()
+
+
+@pytest.mark.parametrize("B,kvb,H,Nq,d,dtype", [(4, 2, 8, 512, 40, torch.float16), (8, 4, 5, 1024, 64, torch.float16), (4, 4, 8, 1024, 80, torch.bfloat16),
+                                                (6, 3, 8, 384, 40, torch.float16), (2, 1, 10, 256, 64, torch.bfloat16), (4, 2, 8, 320, 40, torch.float16),
+                                                (16, 4, 8, 4096, 40, torch.float16)])
+def test_cross_attention_shared_context(ops, B, kvb, H, Nq, d, dtype):
+    """The cross-attention kernel (attention_umma5.cu): 77 context tokens, K / V^T of `kvb` context rows shared by the B query
+    batches (query batch b reads context row b % kvb, denoiser.py:385), fp16 and bf16 activations, the two-tile (d = 40) and
+    one-tile (d = 64 with 128-byte swizzled staging rows, d = 80) instantiations, and a shape that falls back (nq = 320)."""
+    g = torch.Generator().manual_seed(B * Nq + d + kvb)
+    Nk, nk_pad = 77, 80
+    dpad = (d + 15) // 16 * 16
+    q = torch.randn(B, Nq, H, d, generator=g).to(dtype)
+    k = torch.randn(kvb, Nk, H, d, generator=g).to(dtype)
+    v = torch.randn(kvb, Nk, H, d, generator=g).to(dtype)
+    qp = torch.zeros(B, Nq, H, dpad, dtype=dtype); qp[..., :d] = q
+    kp = torch.zeros(kvb, nk_pad, H, dpad, dtype=dtype); kp[:, :Nk, :, :d] = k
+    vp = torch.zeros(kvb, nk_pad, H, dpad, dtype=dtype); vp[:, :Nk, :, :d] = v
+    vt = vp.permute(2, 3, 0, 1).reshape(H * dpad, kvb * nk_pad).contiguous().to(DEV)
+    o = torch.full((B, Nq, H, dpad), float("nan"), dtype=dtype, device=DEV)
+    ops.attention(qp.to(DEV), kp.to(DEV), vt, o, ldq=H * dpad, ldk=H * dpad, ldvt=kvb * nk_pad, ldo=H * dpad, batch=B, heads=H,
+                  nq=Nq, nk=Nk, nk_pad=nk_pad, dpad=dpad, scale=d ** -0.5, d_head=d, kv_batch=kvb)
+    torch.cuda.synchronize()
+    idx = torch.arange(B) % kvb
+    qf = q.float().to(DEV).permute(0, 2, 1, 3)
+    kf, vf = k.float().to(DEV)[idx].permute(0, 2, 1, 3), v.float().to(DEV)[idx].permute(0, 2, 1, 3)
+    ref = torch.softmax(qf @ kf.transpose(-1, -2) * d ** -0.5, dim=-1) @ vf
+    r = rel(o[..., :d].permute(0, 2, 1, 3), ref)
+    print(f"cross-attention B{B} kv{kvb} H{H} {Nq}x77 d{d} {dtype}: rel {r:.3e}")
+    assert torch.isfinite(o.float()).all()
+    assert r < (4e-3 if dtype == torch.float16 else 1e-2)
     if dpad != d:
         assert (o[..., d:] == 0).all()
 

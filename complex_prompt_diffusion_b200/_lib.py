@@ -50,6 +50,29 @@ class GemmParams(C.Structure):
         ("d", C.c_void_p), ("ldd", C.c_int), ("epilogue", C.c_int), ("variant", C.c_int), ("m_valid", C.c_int),
         ("a_fp16", C.c_int), ("b_fp16", C.c_int), ("out_fp16", C.c_int), ("geglu_block", C.c_int),
         ("splitk_ws", C.c_void_p), ("splitk_ws_floats", C.c_int64),
+        ("tune_scratch", C.c_void_p), ("tune_scratch_bytes", C.c_int64),
+    ]
+
+
+CPD_UNET_MAX_LEVELS = 8
+
+
+class UNetConfig(C.Structure):  # cpd_unet_config
+    _fields_ = [
+        ("in_channels", C.c_int), ("out_channels", C.c_int), ("model_channels", C.c_int), ("num_res_blocks", C.c_int),
+        ("n_levels", C.c_int), ("channel_mult", C.c_int * CPD_UNET_MAX_LEVELS),
+        ("n_attention_resolutions", C.c_int), ("attention_resolutions", C.c_int * CPD_UNET_MAX_LEVELS),
+        ("num_heads", C.c_int), ("num_head_channels", C.c_int), ("transformer_depth", C.c_int * CPD_UNET_MAX_LEVELS),
+        ("context_dim", C.c_int), ("use_linear_in_transformer", C.c_int), ("adm_in_channels", C.c_int),
+        ("act_fp16", C.c_int), ("eps_dtype", C.c_int), ("use_cuda_graph", C.c_int),
+    ]
+
+
+class UNetIO(C.Structure):  # cpd_unet_io
+    _fields_ = [
+        ("x", C.c_void_p), ("n_images", C.c_int), ("h", C.c_int), ("w", C.c_int), ("rows_per_image", C.c_int),
+        ("c_in", C.c_void_p), ("t", C.c_void_p), ("t_count", C.c_int), ("eps", C.c_void_p),
+        ("inject_skips", C.POINTER(C.c_void_p)), ("inject_feats", C.POINTER(C.c_void_p)), ("no_graph", C.c_int),
     ]
 
 
@@ -86,6 +109,24 @@ _SIGS = {
     "cpd_softmax_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_float, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
     "cpd_pointwise_small": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
                                       C.c_void_p]),
+    "cpd_gemm_tune_export": (C.c_int64, [C.c_char_p, C.c_int64]),
+    "cpd_gemm_tune_import": (C.c_int, [C.c_char_p]),
+    # plan-level UNet
+    "cpd_unet_plan_create": (C.c_int, [C.POINTER(UNetConfig), C.POINTER(C.c_void_p)]),
+    "cpd_unet_plan_destroy": (None, [C.c_void_p]),
+    "cpd_pack_weights": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int64, C.c_int]),
+    "cpd_unet_plan_missing_weights": (C.c_int, [C.c_void_p]),
+    "cpd_cache_context_kv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "cpd_unet_set_vector": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "cpd_unet_forward": (C.c_int, [C.c_void_p, C.POINTER(UNetIO), C.c_void_p]),
+    "cpd_unet_plan_buffer": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "cpd_unet_plan_launches": (C.c_int64, [C.c_void_p]),
+    "cpd_unet_plan_tap": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                    C.POINTER(C.c_int)]),
+    "cpd_unet_plan_blocks": (C.c_int, [C.c_void_p, C.c_int]),
+    "cpd_unet_plan_set_profile": (None, [C.c_void_p, C.c_int]),
+    "cpd_unet_plan_profile_dump": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "cpd_debug_attention_cross_timeline": (None, [C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGS)
@@ -115,8 +156,25 @@ def check(status, what):
         raise RuntimeError(f"{what} failed (status {status}): {msg}")
 
 
-def stream_ptr():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream_ptr(device=None):
+    """The current torch stream of `device` (default: the current device).  Callers that own a device (UNetModel, Denoiser)
+    wrap their launches in `torch.cuda.device(...)`, so the current device IS the tensors' device."""
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class DeviceView:
+    """A raw device pointer owned by the C library (a plan buffer) as a zero-copy torch tensor, through
+    __cuda_array_interface__.  16-bit buffers are exposed as int16 and re-viewed in the activation dtype."""
+
+    def __init__(self, ptr, numel, itemsize):
+        typestr = {2: "<i2", 4: "<f4", 8: "<f8"}[itemsize]
+        self.__cuda_array_interface__ = {"shape": (int(numel),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def device_tensor(ptr, numel, dtype, device):
+    with torch.cuda.device(device):
+        t = torch.as_tensor(DeviceView(ptr, numel, torch.empty(0, dtype=dtype).element_size()), device=device)
+    return t.view(dtype) if t.dtype != dtype else t
 
 
 def ptr(t):

@@ -427,7 +427,8 @@ static cpd_status gemm_conv_1cta(const cpd_gemm_params* p, void* stream) {
   return launch<128, 3>(args, m_tiles, n_tiles, s);
 }
 
-extern "C" cpd_status cpd_gemm_conv(const cpd_gemm_params* p, void* stream) {
+// variant -> kernel (gemm_tune.cu resolves variant 0 through the per-shape table first)
+cpd_status cpd_gemm_conv_dispatch(const cpd_gemm_params* p, void* stream) {
   CPD_REQUIRE(p != nullptr, "cpd_gemm_conv: null params");
   if (p->variant == 1 || p->variant == 2) return gemm_conv_1cta(p, stream);
   return cpd_gemm_conv_2cta(p, stream);

@@ -1,29 +1,32 @@
 """UNetModel: the Stable-Diffusion UNet forward on B200, same call signature as the reference
 `cpd/models/unet.py:415-831` (`forward(x, timesteps, context, y=None, return_attn=..., ...)`) and the same
-`state_dict` parameter names, but executed as a static plan of hand-written sm_100a kernels
-(libcpd_b200.so) over NHWC bf16 activations:
+`state_dict` parameter names.  This class is a BINDING: the executor - weight packing, the text-context K / V^T cache,
+every workspace buffer, the sequencing of the ~850 kernel launches of an evaluation and the CUDA graph that replays
+them - lives behind the plan-level C ABI of libcpd_b200.so (`cpd_unet_plan_create`, `cpd_pack_weights`,
+`cpd_cache_context_kv`, `cpd_unet_forward`; include/cpd_b200.h, csrc/unet_plan.cu).  PyTorch supplies device memory
+for the inputs / outputs and the CUDA stream.
 
   3x3 / 1x1 convs and every Linear  -> cpd_gemm_conv   (tcgen05 implicit GEMM, TMA-fed, fused bias /
                                        time-embedding / residual / GEGLU epilogues)
-  self- and cross-attention          -> cpd_attention   (fused flash-style kernel, tcgen05 + TMEM)
+  self- and cross-attention          -> cpd_attention   (fused flash-style kernels, tcgen05 + TMEM)
   GroupNorm(+SiLU), LayerNorm        -> cpd_groupnorm / cpd_layernorm
-  timestep embedding + emb MLPs      -> cpd_timestep_embedding / cpd_small_linear (all 22 ResBlock emb
-                                       projections batched in one launch)
+  timestep embedding + emb MLPs      -> cpd_timestep_embedding / cpd_small_linear
   4->C input conv, C->4 output conv  -> cpd_conv_in / cpd_conv_out
 
-The skip concat (unet.py:814) is never materialised: GroupNorm and the 1x1 skip conv read both sources.
-Text-context K/V projections are step-invariant and cached per prompt (`set_context`).
 Weights are bf16 (the model dtype of BASELINE.json's bf16 configs); GroupNorm statistics are fp32
-(models/util.py:103-105), accumulation is fp32 in TMEM.
+(models/util.py:103-105), accumulation is fp32 in TMEM.  There is no CPU or PyTorch fallback.
 """
+import ctypes as C
+
 import torch
 
 from .. import ops
-from .._lib import CPD_EPI_GEGLU, CPD_EPI_NONE
+from .._lib import CPD_BF16, CPD_F32, DTYPE_CODE, UNetConfig, UNetIO, check, device_tensor, load, stream_ptr
 
 
 def _enumerate_blocks(cfg):
-    """Block structure built by the reference constructor (unet.py:545-727)."""
+    """Block structure built by the reference constructor (unet.py:545-727); host-side copy used by the synthetic-model
+    fixtures (parameter shapes, FLOP enumerator).  The executor's own copy is csrc/unet_plan.cu:enumerate_blocks."""
     mc = cfg["model_channels"]
     inputs = [[("conv_in", cfg["in_channels"], mc)]]
     chans = [mc]
@@ -62,16 +65,11 @@ def _enumerate_blocks(cfg):
     return inputs, middle, outputs
 
 
-def _round16(d):
-    return (d + 15) // 16 * 16
-
-
 class UNetModel:
     DEFAULTS = dict(image_size=32, in_channels=4, model_channels=320, out_channels=4, num_res_blocks=2,
                     attention_resolutions=(4, 2, 1), channel_mult=(1, 2, 4, 4), num_heads=8, num_head_channels=-1,
                     transformer_depth=1, context_dim=768, use_linear_in_transformer=False, use_spatial_transformer=True,
                     legacy=False, adm_in_channels=0)
-    GEGLU_BLOCK = 256
 
     def __init__(self, state_dict=None, device="cuda", act_dtype=torch.float16, eps_dtype=torch.float32, use_cuda_graph=True,
                  **config):
@@ -87,175 +85,94 @@ class UNetModel:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("UNetModel runs on CUDA only: there is no CPU fallback for the hot path")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.dtype = torch.bfloat16  # model (weight) dtype
         if act_dtype not in (torch.float16, torch.bfloat16):
             raise ValueError("act_dtype must be torch.float16 or torch.bfloat16")
-        # Inter-kernel activations are 16-bit.  fp16 (default) has 3 more mantissa bits than bf16; tcgen05
-        # kind::f16 multiplies fp16 activations with bf16 weights at the same rate ("precision").
+        if eps_dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("eps_dtype must be torch.float32 or torch.bfloat16")
+        # Inter-kernel activations are 16-bit.  fp16 (default) has 3 more mantissa bits than bf16; tcgen05 kind::f16 runs
+        # both at the same rate ("precision").
         self.act_dtype = act_dtype
         self.eps_dtype = eps_dtype
         self.model_channels = cfg["model_channels"]
-        self.inputs, self.middle, self.outputs = _enumerate_blocks(cfg)
-        self.w = {}
-        self._ws = {}
-        self._graphs = {}
+        self.adm = int(cfg["adm_in_channels"])
         self.use_cuda_graph = bool(use_cuda_graph)
-        self._ctx = None
+        self.inputs, self.middle, self.outputs = _enumerate_blocks(cfg)
+        self._lib = load()
+        c = UNetConfig()
+        c.in_channels, c.out_channels, c.model_channels = cfg["in_channels"], cfg["out_channels"], cfg["model_channels"]
+        c.num_res_blocks = cfg["num_res_blocks"]
+        mult = list(cfg["channel_mult"])
+        c.n_levels = len(mult)
+        td = cfg["transformer_depth"]
+        for i, m in enumerate(mult):
+            c.channel_mult[i] = int(m)
+            c.transformer_depth[i] = int(td if isinstance(td, int) else list(td)[min(i, len(td) - 1)])
+        ar = list(cfg["attention_resolutions"])
+        c.n_attention_resolutions = len(ar)
+        for i, a in enumerate(ar):
+            c.attention_resolutions[i] = int(a)
+        c.num_heads, c.num_head_channels = int(cfg["num_heads"]), int(cfg["num_head_channels"])
+        c.context_dim, c.use_linear_in_transformer = int(cfg["context_dim"]), int(bool(cfg["use_linear_in_transformer"]))
+        c.adm_in_channels = self.adm
+        c.act_fp16 = int(act_dtype == torch.float16)
+        c.eps_dtype = DTYPE_CODE[eps_dtype]
+        c.use_cuda_graph = int(self.use_cuda_graph)
+        self._plan = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(self._lib.cpd_unet_plan_create(C.byref(c), C.byref(self._plan)), "cpd_unet_plan_create")
+        self._static = {}   # (shape, rows) -> static input / scalar / output buffers of the graph-replayed fast path
         self._ctx_key = None
-        self._y = None  # vector conditioning rows (SDXL), bf16 [rows, adm_in_channels], stable address
+        self._ctx_shape = None
         self._y_key = None
+        self._y_rows = 0
         self._probe = torch.zeros(1, dtype=self.dtype, device=self.device)
         if state_dict is not None:
             self.load_state_dict(state_dict)
 
+    def __del__(self):
+        plan, lib = getattr(self, "_plan", None), getattr(self, "_lib", None)
+        if plan is not None and plan.value and lib is not None:
+            lib.cpd_unet_plan_destroy(plan)
+            self._plan = None
+
     # ---- nn.Module-like surface used by the Denoiser ------------------------------------------------
     def parameters(self):
         yield self._probe
-        for v in self.w.values():
-            if isinstance(v, torch.Tensor):
-                yield v
 
     def heads(self, ch):
         if self.cfg["num_head_channels"] == -1:
             return self.cfg["num_heads"], ch // self.cfg["num_heads"]
         return ch // self.cfg["num_head_channels"], self.cfg["num_head_channels"]
 
-    # ---- weight packing (once) ---------------------------------------------------------------------
+    def _stream(self):
+        return stream_ptr(self.device)
+
+    # ---- weights: packed once by the library ---------------------------------------------------------
     def load_state_dict(self, sd, strict=True):
-        dev = self.device
-        W = {}
-
-        def bf(t):
-            return t.detach().to(torch.bfloat16)
-
-        def f32(name):  # 1-D parameters are used in fp32 after rounding to the model dtype
-            return bf(sd[name]).float().contiguous().to(dev)
-
-        def conv3(name):  # [Cout, Cin, 3, 3] -> [Cout, 3, 3, Cin]
-            return bf(sd[name]).permute(0, 2, 3, 1).contiguous().to(dev)
-
-        def mat(name):  # [out, in] or [out, in, 1, 1]
-            t = bf(sd[name])
-            return t.reshape(t.shape[0], t.shape[1]).contiguous().to(dev)
-
-        def pad_rows(t, heads, d, dpad):  # [heads*d, K] -> [heads*dpad, K] (zero rows)
-            if d == dpad:
-                return t
-            out = torch.zeros(heads, dpad, t.shape[1], dtype=t.dtype)
-            out[:, :d] = t.reshape(heads, d, t.shape[1])
-            return out.reshape(heads * dpad, t.shape[1])
-
-        def pad_cols(t, heads, d, dpad):  # [N, heads*d] -> [N, heads*dpad]
-            if d == dpad:
-                return t
-            out = torch.zeros(t.shape[0], heads, dpad, dtype=t.dtype)
-            out[:, :, :d] = t.reshape(t.shape[0], heads, d)
-            return out.reshape(t.shape[0], heads * dpad)
-
-        ted = self.model_channels * 4
-        W["te0.w"], W["te0.b"] = mat("time_embed.0.weight"), f32("time_embed.0.bias")
-        W["te2.w"], W["te2.b"] = mat("time_embed.2.weight"), f32("time_embed.2.bias")
-        self.adm = int(self.cfg["adm_in_channels"])
-        if self.adm:
-            # emb = time_embed(t_emb) + label_emb(y) (SDXL extension) is ONE small linear over [SiLU(e1) | SiLU(l1)]:
-            # the second layers are concatenated along K and their biases summed
-            W["lab0.w"], W["lab0.b"] = mat("label_emb.0.0.weight"), f32("label_emb.0.0.bias")
-            W["te2lab2.w"] = torch.cat([bf(sd["time_embed.2.weight"]), bf(sd["label_emb.0.2.weight"])], dim=1).contiguous().to(dev)
-            W["te2lab2.b"] = (bf(sd["time_embed.2.bias"]).float() + bf(sd["label_emb.0.2.bias"]).float()).contiguous().to(dev)
-        emb_w, emb_b, emb_off = [], [], {}
-        off = 0
-
-        def res(p, cin, cout):
-            nonlocal off
-            W[p + "gn1.g"], W[p + "gn1.b"] = f32(p + "in_layers.0.weight"), f32(p + "in_layers.0.bias")
-            W[p + "conv1.w"], W[p + "conv1.b"] = conv3(p + "in_layers.2.weight"), f32(p + "in_layers.2.bias")
-            emb_w.append(bf(sd[p + "emb_layers.1.weight"]))
-            emb_b.append(bf(sd[p + "emb_layers.1.bias"]).float())
-            emb_off[p] = off
-            off += cout
-            W[p + "gn2.g"], W[p + "gn2.b"] = f32(p + "out_layers.0.weight"), f32(p + "out_layers.0.bias")
-            W[p + "conv2.w"], W[p + "conv2.b"] = conv3(p + "out_layers.3.weight"), f32(p + "out_layers.3.bias")
-            if cin != cout:
-                W[p + "skip.w"], W[p + "skip.b"] = mat(p + "skip_connection.weight"), f32(p + "skip_connection.bias")
-
-        def attn(p, ch, depth):
-            W[p + "norm.g"], W[p + "norm.b"] = f32(p + "norm.weight"), f32(p + "norm.bias")
-            W[p + "proj_in.w"], W[p + "proj_in.b"] = mat(p + "proj_in.weight"), f32(p + "proj_in.bias")
-            W[p + "proj_out.w"], W[p + "proj_out.b"] = mat(p + "proj_out.weight"), f32(p + "proj_out.bias")
-            for d in range(depth):
-                tblock(p + f"transformer_blocks.{d}.", ch)
-
-        def tblock(b, ch):
-            nh, dh = self.heads(ch)
-            dpad = _round16(dh)
-            for n in ("norm1", "norm2", "norm3"):
-                W[b + n + ".g"], W[b + n + ".b"] = f32(b + n + ".weight"), f32(b + n + ".bias")
-            q1 = pad_rows(bf(sd[b + "attn1.to_q.weight"]), nh, dh, dpad)
-            k1 = pad_rows(bf(sd[b + "attn1.to_k.weight"]), nh, dh, dpad)
-            W[b + "attn1.qk.w"] = torch.cat([q1, k1]).contiguous().to(dev)  # fused Q|K projection
-            W[b + "attn1.v.w"] = pad_rows(bf(sd[b + "attn1.to_v.weight"]), nh, dh, dpad).contiguous().to(dev)
-            W[b + "attn1.out.w"] = pad_cols(bf(sd[b + "attn1.to_out.0.weight"]), nh, dh, dpad).contiguous().to(dev)
-            W[b + "attn1.out.b"] = f32(b + "attn1.to_out.0.bias")
-            W[b + "attn2.q.w"] = pad_rows(bf(sd[b + "attn2.to_q.weight"]), nh, dh, dpad).contiguous().to(dev)
-            W[b + "attn2.k.w"] = pad_rows(bf(sd[b + "attn2.to_k.weight"]), nh, dh, dpad).contiguous().to(dev)
-            W[b + "attn2.v.w"] = pad_rows(bf(sd[b + "attn2.to_v.weight"]), nh, dh, dpad).contiguous().to(dev)
-            W[b + "attn2.out.w"] = pad_cols(bf(sd[b + "attn2.to_out.0.weight"]), nh, dh, dpad).contiguous().to(dev)
-            W[b + "attn2.out.b"] = f32(b + "attn2.to_out.0.bias")
-            # GEGLU: interleave [128 value rows | 128 gate rows] per 256-column tile (cpd_gemm_conv CPD_EPI_GEGLU,
-            # geglu_block = 256 = the CTA-pair kernel's tile width)
-            w1, b1 = bf(sd[b + "ff.net.0.proj.weight"]), bf(sd[b + "ff.net.0.proj.bias"]).float()
-            inner4 = w1.shape[0] // 2
-            hb = self.GEGLU_BLOCK // 2
-            assert inner4 % hb == 0
-            wv, wg = w1[:inner4].reshape(inner4 // hb, hb, -1), w1[inner4:].reshape(inner4 // hb, hb, -1)
-            W[b + "ff1.w"] = torch.cat([wv, wg], dim=1).reshape(2 * inner4, -1).contiguous().to(dev)
-            bv, bg = b1[:inner4].reshape(inner4 // hb, hb), b1[inner4:].reshape(inner4 // hb, hb)
-            W[b + "ff1.b"] = torch.cat([bv, bg], dim=1).reshape(2 * inner4).contiguous().to(dev)
-            W[b + "ff2.w"], W[b + "ff2.b"] = mat(b + "ff.net.2.weight"), f32(b + "ff.net.2.bias")
-
-        def block(prefix, layers):
-            for j, l in enumerate(layers):
-                p = f"{prefix}{j}."
-                if l[0] == "conv_in":
-                    W[p + "w"], W[p + "b"] = conv3(p + "weight"), f32(p + "bias")
-                elif l[0] == "res":
-                    res(p, l[1], l[2])
-                elif l[0] == "attn":
-                    attn(p, l[1], l[2])
-                elif l[0] == "down":
-                    W[p + "w"], W[p + "b"] = conv3(p + "op.weight"), f32(p + "op.bias")
-                elif l[0] == "up":
-                    W[p + "w"], W[p + "b"] = conv3(p + "conv.weight"), f32(p + "conv.bias")
-
-        for i, layers in enumerate(self.inputs):
-            block(f"input_blocks.{i}.", layers)
-        block("middle_block.", self.middle)
-        for i, layers in enumerate(self.outputs):
-            block(f"output_blocks.{i}.", layers)
-        W["out.gn.g"], W["out.gn.b"] = f32("out.0.weight"), f32("out.0.bias")
-        W["out.w"], W["out.b"] = conv3("out.2.weight"), f32("out.2.bias")
-        W["emb_all.w"] = torch.cat(emb_w).contiguous().to(dev)
-        W["emb_all.b"] = torch.cat(emb_b).contiguous().to(dev)
-        self.emb_off, self.emb_total, self.ted = emb_off, off, ted
-        # tcgen05 kind::f16 needs A and B in the SAME 16-bit format (mixed fp16 x bf16 raises an illegal-instruction
-        # trap on sm_100a), so tensor-core weights are stored in the activation dtype.  bf16 -> fp16 is exact for
-        # every weight with |w| >= 2^-14 (fp16 has the wider mantissa); smaller ones move by < 3e-8 absolute.
-        cuda_core = {"te0.w", "te2.w", "emb_all.w", "input_blocks.0.0.w", "out.w", "lab0.w", "te2lab2.w"}
-        for key in list(W):
-            if key.endswith(".w") and key not in cuda_core:
-                W[key] = W[key].to(self.act_dtype)
-        self.w = W
+        """`sd`: the reference's state_dict (names of cpd/models/unet.py / attention.py).  Every entry is handed to
+        cpd_pack_weights under its reference name; entries the UNet configuration does not have are rejected when `strict`."""
+        with torch.cuda.device(self.device):
+            for name, t in sd.items():
+                t = t.detach()
+                if t.dtype not in DTYPE_CODE:
+                    t = t.float()
+                t = t.contiguous()
+                rc = self._lib.cpd_pack_weights(self._plan, name.encode(), C.c_void_p(t.data_ptr()), DTYPE_CODE[t.dtype], t.numel(),
+                                                int(t.is_cuda))
+                if rc != 0:
+                    msg = self._lib.cpd_last_error().decode("utf-8", "replace")
+                    if "is not a parameter" in msg and not strict:
+                        continue
+                    raise RuntimeError(f"cpd_pack_weights({name}) failed (status {rc}): {msg}")
+            missing = self._lib.cpd_unet_plan_missing_weights(self._plan)
+            if missing and strict:
+                raise KeyError(f"{missing} state_dict entries are missing, first: "
+                               f"{self._lib.cpd_last_error().decode('utf-8', 'replace')}")
+        self._ctx_key = None  # the cached K / V^T were projected with the old weights
         return self
-
-    # ---- workspace ---------------------------------------------------------------------------------
-    def _buf(self, name, numel, dtype=None):
-        dtype = self.act_dtype if dtype is None else dtype
-        key = (name, numel, dtype)
-        t = self._ws.get(key)
-        if t is None:
-            t = torch.empty(numel, dtype=dtype, device=self.device)
-            self._ws[key] = t
-        return t
 
     # ---- text context: step-invariant K / V^T of every cross-attention layer ---------------------------
     def set_context(self, context):
@@ -263,36 +180,24 @@ class UNetModel:
         # The cache is keyed on the tensor OBJECT (kept alive here, so its storage cannot be recycled for another prompt)
         # and its version counter - never on data_ptr(): the caching allocator hands the address of a freed context to
         # the next one of the same shape.
-        key = (context, context._version)
         if self._ctx_key is not None and self._ctx_key[0] is context and self._ctx_key[1] == context._version:
             return
-        # the reference casts the context to the model dtype first (denoiser.py:373-385), then it is an activation
-        ctx = context.to(self.device, torch.bfloat16).to(self.act_dtype)
-        rc, ntok, D = ctx.shape
-        nk_pad = (ntok + 15) // 16 * 16
-        ctx_pad = self._buf("ctx_pad", rc * nk_pad * D).view(rc, nk_pad, D)
-        ctx_pad.zero_()
-        ctx_pad[:, :ntok] = ctx
-        kv = {}
-        for prefix, layers in self._all_blocks():
-            for j, l in enumerate(layers):
-                if l[0] != "attn":
-                    continue
-                for d in range(l[2]):
-                    b = f"{prefix}{j}.transformer_blocks.{d}."
-                    wk, wv = self.w[b + "attn2.k.w"], self.w[b + "attn2.v.w"]
-                    ip = wk.shape[0]
-                    # persistent buffers (stable addresses: captured CUDA graphs stay valid across prompts)
-                    kc = self._buf(b + "kc", rc * nk_pad * ip).view(rc * nk_pad, ip)
-                    vt = self._buf(b + "vt", ip * rc * nk_pad).view(ip, rc * nk_pad)
-                    ops.gemm_conv(ctx_pad, wk, kc, n_img=1, h=1, w=rc * nk_pad, c0=D, n_out=ip)
-                    ops.gemm_conv(wv, ctx_pad, vt, n_img=1, h=1, w=ip, c0=D, n_out=rc * nk_pad)
-                    kv[b] = (kc, vt)
-        self._ctx = dict(rc=rc, ntok=ntok, nk_pad=nk_pad, kv=kv, keep=ctx_pad)
-        self._ctx_key = key
+        ctx = context.detach().to(self.device)
+        if ctx.dtype not in DTYPE_CODE:
+            ctx = ctx.float()
+        ctx = ctx.contiguous()
+        if ctx.ndim != 3 or ctx.shape[2] != self.cfg["context_dim"]:
+            raise ValueError(f"context must be [rows, tokens, {self.cfg['context_dim']}], got {tuple(ctx.shape)}")
+        with torch.cuda.device(self.device):
+            check(self._lib.cpd_cache_context_kv(self._plan, C.c_void_p(ctx.data_ptr()), DTYPE_CODE[ctx.dtype], ctx.shape[0], ctx.shape[1],
+                                                 self._stream()), "cpd_cache_context_kv")
+        ops.LAUNCHES += int(self._lib.cpd_unet_plan_launches(self._plan))
+        self._ctx_key = (context, context._version)
+        self._ctx_shape = (ctx.shape[0], ctx.shape[1])
+        self._keep_ctx = ctx  # read asynchronously by the pack kernel
 
     def set_vector(self, y):
-        """Vector conditioning of the SDXL extension: y [Ry, adm_in_channels]; UNet row b uses y row (b % Ry).  Kept in a
+        """Vector conditioning of the SDXL extension: y [Ry, adm_in_channels]; UNet row b uses y row (b % Ry).  Kept by the plan in a
         persistent bf16 buffer (the model dtype), so captured graphs stay valid when the prompt changes."""
         if not self.adm:
             if y is not None:
@@ -300,255 +205,148 @@ class UNetModel:
             return
         if y is None:
             raise ValueError(f"this UNet needs vector conditioning y [rows, {self.adm}]")
-        key = (y, y._version)  # object identity + version (see set_context)
         if self._y_key is not None and self._y_key[0] is y and self._y_key[1] == y._version:
             return
         if y.ndim != 2 or y.shape[1] != self.adm:
             raise ValueError(f"y must be [rows, {self.adm}], got {tuple(y.shape)}")
-        buf = self._buf("y", y.shape[0] * self.adm, torch.bfloat16).view(y.shape[0], self.adm)
-        buf.copy_(y.to(self.device, torch.bfloat16))
-        self._y, self._y_key = buf, key
+        yd = y.detach().to(self.device)
+        if yd.dtype not in DTYPE_CODE:
+            yd = yd.float()
+        yd = yd.contiguous()
+        with torch.cuda.device(self.device):
+            check(self._lib.cpd_unet_set_vector(self._plan, C.c_void_p(yd.data_ptr()), DTYPE_CODE[yd.dtype], yd.shape[0], self._stream()),
+                  "cpd_unet_set_vector")
+        ops.LAUNCHES += 1
+        self._y_key, self._y_rows, self._keep_y = (y, y._version), yd.shape[0], yd
 
-    def _all_blocks(self):
-        for i, layers in enumerate(self.inputs):
-            yield f"input_blocks.{i}.", layers
-        yield "middle_block.", self.middle
-        for i, layers in enumerate(self.outputs):
-            yield f"output_blocks.{i}.", layers
+    # ---- plan buffers as torch tensors (zero-copy views of library-owned memory) -------------------------
+    def plan_buffer(self, name, dtype=None):
+        """A named buffer of the plan (packed weights, workspace, "<block>.out" activations) as a flat torch view."""
+        ptr, n = C.c_void_p(), C.c_int64()
+        check(self._lib.cpd_unet_plan_buffer(self._plan, name.encode(), C.byref(ptr), C.byref(n)), "cpd_unet_plan_buffer")
+        return device_tensor(ptr.value, n.value, self.act_dtype if dtype is None else dtype, self.device)
 
-    # ---- layers --------------------------------------------------------------------------------------
-    def _res(self, p, x0, x1, c0, c1, cout, R, h, w, emb_all, emb_stride, stats):
-        W = self.w
-        hw = h * w
-        cin = c0 + c1
-        gn = self._buf("gn", R * hw * cin)
-        ops.groupnorm(x0, W[p + "gn1.g"], W[p + "gn1.b"], gn, stats, n_img=R, hw=hw, c0=c0, a1=x1, c1=c1, eps=1e-5, silu=True)
-        h1 = self._buf("h1", R * hw * cout)
-        ops.gemm_conv(gn, W[p + "conv1.w"], h1, n_img=R, h=h, w=w, c0=cin, n_out=cout, ksize=3, bias=W[p + "conv1.b"],
-                      rowvec=emb_all[self.emb_off[p]:], rowvec_stride=emb_stride)
-        gn2 = self._buf("gn", R * hw * cout)
-        ops.groupnorm(h1, W[p + "gn2.g"], W[p + "gn2.b"], gn2, stats, n_img=R, hw=hw, c0=cout, eps=1e-5, silu=True)
-        if cin != cout:
-            skip = self._buf("skip", R * hw * cout)
-            ops.gemm_conv(x0, W[p + "skip.w"], skip, n_img=R, h=h, w=w, c0=c0, a1=x1, c1=c1, n_out=cout, ksize=1,
-                          bias=W[p + "skip.b"])
-        else:
-            skip = x0
-        out = self._buf(p + "out", R * hw * cout)
-        ops.gemm_conv(gn2, W[p + "conv2.w"], out, n_img=R, h=h, w=w, c0=cout, n_out=cout, ksize=3, bias=W[p + "conv2.b"],
-                      residual=skip, ld_res=cout)
+    def _tap(self, which, index, rows):
+        """Output of a block of the last forward as an NCHW view [rows, c, h, w] of the plan's NHWC buffer."""
+        ptr, c, h, w = C.c_void_p(), C.c_int(), C.c_int(), C.c_int()
+        check(self._lib.cpd_unet_plan_tap(self._plan, which, index, C.byref(ptr), C.byref(c), C.byref(h), C.byref(w)), "cpd_unet_plan_tap")
+        t = device_tensor(ptr.value, rows * c.value * h.value * w.value, self.act_dtype, self.device)
+        return t.view(rows, h.value, w.value, c.value).permute(0, 3, 1, 2)
+
+    def profile(self, on):
+        """Per-launch CUDA-event timing of the following eager forwards (bench.py's roofline leg)."""
+        self._lib.cpd_unet_plan_set_profile(self._plan, int(bool(on)))
+
+    def profile_records(self):
+        """[(kind, label, microseconds, flops)] of the launches recorded since profile(True)."""
+        n = self._lib.cpd_unet_plan_profile_dump(self._plan, None, 0)
+        buf = C.create_string_buffer(int(n))
+        self._lib.cpd_unet_plan_profile_dump(self._plan, buf, n)
+        out = []
+        for line in buf.value.decode().splitlines():
+            kind, label, us, fl = line.split("\t")
+            out.append((kind, label, float(us), float(fl)))
         return out
-
-    def _attn(self, p, x, ch, R, h, w, stats, depth=1):
-        W = self.w
-        hw = h * w
-        T = R * hw
-        nh, dh = self.heads(ch)
-        dpad = _round16(dh)
-        ip = nh * dpad
-        scale = dh ** -0.5
-        gn = self._buf("gn", T * ch)
-        ops.groupnorm(x, W[p + "norm.g"], W[p + "norm.b"], gn, stats, n_img=R, hw=hw, c0=ch, eps=1e-6, silu=False)
-        hcur = self._buf("tr.h", T * ch)
-        ops.gemm_conv(gn, W[p + "proj_in.w"], hcur, n_img=1, h=1, w=T, c0=ch, n_out=ch, bias=W[p + "proj_in.b"])
-        ln = self._buf("tr.ln", T * ch)
-        for d in range(depth):
-            b = p + f"transformer_blocks.{d}."
-            # --- self-attention
-            ops.layernorm(hcur, W[b + "norm1.g"], W[b + "norm1.b"], ln, rows=T, c=ch)
-            qk = self._buf("tr.qk", T * 2 * ip)
-            ops.gemm_conv(ln, W[b + "attn1.qk.w"], qk, n_img=1, h=1, w=T, c0=ch, n_out=2 * ip)
-            vt = self._buf("tr.vt", ip * T)
-            ops.gemm_conv(W[b + "attn1.v.w"], ln, vt, n_img=1, h=1, w=ip, c0=ch, n_out=T)
-            o = self._buf("tr.o", T * ip)
-            ops.attention(qk, qk[ip:], vt, o, ldq=2 * ip, ldk=2 * ip, ldvt=T, ldo=ip, batch=R, heads=nh, nq=hw, nk=hw, nk_pad=hw,
-                          dpad=dpad, scale=scale, d_head=dh)
-            ops.gemm_conv(o, W[b + "attn1.out.w"], hcur, n_img=1, h=1, w=T, c0=ip, n_out=ch, bias=W[b + "attn1.out.b"],
-                          residual=hcur, ld_res=ch)
-            # --- cross-attention (K / V^T cached per prompt)
-            ctx = self._ctx
-            if ctx is None:
-                raise RuntimeError("UNetModel: no text context set (call set_context or pass `context`)")
-            kc, vtc = ctx["kv"][b]
-            ops.layernorm(hcur, W[b + "norm2.g"], W[b + "norm2.b"], ln, rows=T, c=ch)
-            q2 = self._buf("tr.q2", T * ip)
-            ops.gemm_conv(ln, W[b + "attn2.q.w"], q2, n_img=1, h=1, w=T, c0=ch, n_out=ip)
-            ops.attention(q2, kc, vtc, o, ldq=ip, ldk=ip, ldvt=ctx["rc"] * ctx["nk_pad"], ldo=ip, batch=R, heads=nh, nq=hw,
-                          nk=ctx["ntok"], nk_pad=ctx["nk_pad"], dpad=dpad, scale=scale, kv_batch=ctx["rc"], d_head=dh)
-            ops.gemm_conv(o, W[b + "attn2.out.w"], hcur, n_img=1, h=1, w=T, c0=ip, n_out=ch, bias=W[b + "attn2.out.b"],
-                          residual=hcur, ld_res=ch)
-            # --- GEGLU feed-forward
-            ops.layernorm(hcur, W[b + "norm3.g"], W[b + "norm3.b"], ln, rows=T, c=ch)
-            ff = self._buf("tr.ff", T * 4 * ch)
-            ops.gemm_conv(ln, W[b + "ff1.w"], ff, n_img=1, h=1, w=T, c0=ch, n_out=8 * ch, bias=W[b + "ff1.b"], epilogue=CPD_EPI_GEGLU,
-                          geglu_block=self.GEGLU_BLOCK)
-            ops.gemm_conv(ff, W[b + "ff2.w"], hcur, n_img=1, h=1, w=T, c0=4 * ch, n_out=ch, bias=W[b + "ff2.b"], residual=hcur,
-                          ld_res=ch)
-        out = self._buf(p + "out", T * ch)
-        ops.gemm_conv(hcur, W[p + "proj_out.w"], out, n_img=1, h=1, w=T, c0=ch, n_out=ch, bias=W[p + "proj_out.b"],
-                      residual=x, ld_res=ch)
-        return out
-
-    def _run_block(self, prefix, layers, hcur, skip, R, h, w, emb_all, emb_stride, stats):
-        """Returns (tensor, channels, h, w).  `skip` = (tensor, channels) second source of the first ResBlock or None."""
-        W = self.w
-        ch = None
-        for j, l in enumerate(layers):
-            p = f"{prefix}{j}."
-            if l[0] == "res":
-                if skip is not None and j == 0:
-                    hcur = self._res(p, hcur, skip[0], l[3], l[4], l[2], R, h, w, emb_all, emb_stride, stats)
-                else:
-                    hcur = self._res(p, hcur, None, l[1], 0, l[2], R, h, w, emb_all, emb_stride, stats)
-                ch = l[2]
-            elif l[0] == "attn":
-                hcur = self._attn(p, hcur, l[1], R, h, w, stats, l[2])
-                ch = l[1]
-            elif l[0] == "down":
-                ch = l[1]
-                out = self._buf(p + "out", R * (h // 2) * (w // 2) * ch)
-                ops.gemm_conv(hcur, W[p + "w"], out, n_img=R, h=h, w=w, c0=ch, n_out=ch, ksize=3, stride=2, bias=W[p + "b"])
-                hcur, h, w = out, h // 2, w // 2
-            elif l[0] == "up":
-                ch = l[1]
-                up = self._buf("up", R * 4 * h * w * ch)
-                ops.upsample2x(hcur, up, n=R, h=h, w=w, c=ch)
-                h, w = 2 * h, 2 * w
-                out = self._buf(p + "out", R * h * w * ch)
-                ops.gemm_conv(up, W[p + "w"], out, n_img=R, h=h, w=w, c0=ch, n_out=ch, ksize=3, bias=W[p + "b"])
-                hcur = out
-        return hcur, ch, h, w
 
     # ---- forward ---------------------------------------------------------------------------------------
-    def _embeddings(self, t_rows, y_rows=None):
-        """t_rows: fp32 device tensor [m] (already rounded to the model dtype); y_rows: bf16 [m, adm] or None.
-        Returns fp32 [m, emb_total]."""
-        W = self.w
-        m = t_rows.numel()
-        mc, ted = self.model_channels, self.ted
-        temb = self._buf("temb", m * mc, torch.bfloat16)
-        ops.timestep_embedding(t_rows, temb, dim=mc, round_t_bf16=False)
-        emb = self._buf("emb", m * ted, torch.bfloat16)
-        if self.adm:
-            e1l1 = self._buf("e1l1", m * 2 * ted, torch.bfloat16)  # [m][SiLU inputs of time_embed.2 | label_emb.0.2]
-            ops.small_linear(temb, W["te0.w"], W["te0.b"], m=m, k=mc, n=ted, out_bf16=e1l1, ld_out=2 * ted)
-            ops.small_linear(y_rows, W["lab0.w"], W["lab0.b"], m=m, k=self.adm, n=ted, out_bf16=e1l1[ted:], ld_out=2 * ted)
-            ops.small_linear(e1l1, W["te2lab2.w"], W["te2lab2.b"], m=m, k=2 * ted, n=ted, silu_in=True, out_bf16=emb)
-        else:
-            e1 = self._buf("e1", m * ted, torch.bfloat16)
-            ops.small_linear(temb, W["te0.w"], W["te0.b"], m=m, k=mc, n=ted, out_bf16=e1)
-            ops.small_linear(e1, W["te2.w"], W["te2.b"], m=m, k=ted, n=ted, silu_in=True, out_bf16=emb)
-        emb_all = self._buf("emb_all", m * self.emb_total, torch.float32)
-        ops.small_linear(emb, W["emb_all.w"], W["emb_all.b"], m=m, k=ted, n=self.emb_total, silu_in=True, out_f32=emb_all)
-        return emb_all
-
-    def _nhwc(self, t, name, R, c, h, w):
-        """A caller-provided NCHW tensor [R, c, h, w] -> NHWC activation buffer (feature / skip injection, unet.py:806-813)."""
+    def _nhwc(self, t, R, c, h, w):
+        """A caller-provided NCHW tensor [R, c, h, w] -> NHWC activation tensor (feature / skip injection, unet.py:806-813)."""
         t = torch.as_tensor(t)
         if tuple(t.shape) != (R, c, h, w):
             raise ValueError(f"injected tensor has shape {tuple(t.shape)}, expected {(R, c, h, w)}")
-        buf = self._buf(name, R * h * w * c)
-        buf.view(R, h, w, c).copy_(t.to(self.device).permute(0, 2, 3, 1))
-        return buf
+        return t.to(self.device, self.act_dtype).permute(0, 2, 3, 1).contiguous()
 
-    def _forward_impl(self, x, scale, rows_per_image, t_rows, shared_t, return_skips=False, scale_dev=None, inject=None,
-                      return_feats=False):
-        W = self.w
-        B, cin, h, w = x.shape
+    def _run(self, x, rows_per_image, c_in_dev, t_dev, t_count, eps, inject=None, no_graph=False):
+        """One cpd_unet_forward call.  x: fp32 [B, C, h, w] device tensor; c_in_dev / t_dev: device scalars; eps: output tensor."""
+        B, _cin, h, w = x.shape
         R = B * rows_per_image
-        stats = self._buf("gn.stats", R * 64 * ops.GN_MAX_CHUNKS, torch.float64)
-        if self.adm:
-            # vector conditioning differs per conditioning row: one embedding row per UNet row (t repeated when shared)
-            if self._y is None:
-                raise RuntimeError("UNetModel: no vector conditioning set (call set_vector or pass `y`)")
-            if R > 16:
-                raise NotImplementedError("more than 16 UNet rows per evaluation with vector conditioning (shard the batch)")
-            y_rows = self._buf("y_rows", R * self.adm, torch.bfloat16).view(R, self.adm)
-            ry = self._y.shape[0]
-            if R % ry:
-                raise ValueError(f"{R} UNet rows are not a multiple of the {ry} vector-conditioning rows")
-            y_rows.copy_(self._y.repeat(R // ry, 1))
-            if shared_t:
-                t_all = self._buf("t_rows", R, torch.float32)
-                t_all.copy_(t_rows.reshape(1).expand(R))
-                t_rows, shared_t = t_all, False
-            emb_all = self._embeddings(t_rows, y_rows)
-        else:
-            emb_all = self._embeddings(t_rows)
-        emb_stride = 0 if shared_t else self.emb_total
+        io = UNetIO()
+        io.x, io.n_images, io.h, io.w, io.rows_per_image = x.data_ptr(), B, h, w, rows_per_image
+        io.c_in = c_in_dev.data_ptr() if c_in_dev is not None else None
+        io.t, io.t_count = t_dev.data_ptr(), t_count
+        io.eps = eps.data_ptr()
+        io.no_graph = int(bool(no_graph))
+        keep = []
+        if inject:
+            # shapes of the popped skip tensors / decoder inputs come from the plan's own record of the last forward: run the
+            # geometry from the block structure instead (channels of the input blocks, spatial size per level)
+            n_out = len(self.outputs)
+            skips = (C.c_void_p * n_out)()
+            feats = (C.c_void_p * n_out)()
+            geo = self._decoder_geometry(h, w)
+            for i in range(n_out):
+                (sc, sh, sw), (fc, fh, fw) = geo[i]
+                if inject.get("attns") is not None and inject.get("attns_stop", 10) > i:  # unet.py:806-809: replace the skip tensor
+                    tns = self._nhwc(inject["attns"][i], R, sc, sh, sw)
+                    keep.append(tns)
+                    skips[i] = tns.data_ptr()
+                if inject.get("feats") is not None and inject.get("feats_stop", 10) > i:  # unet.py:810-813: replace h
+                    tns = self._nhwc(inject["feats"][i], R, fc, fh, fw)
+                    keep.append(tns)
+                    feats[i] = tns.data_ptr()
+            io.inject_skips = C.cast(skips, C.POINTER(C.c_void_p))
+            io.inject_feats = C.cast(feats, C.POINTER(C.c_void_p))
+            keep += [skips, feats]
+        with torch.cuda.device(self.device):
+            check(self._lib.cpd_unet_forward(self._plan, C.byref(io), self._stream()), "cpd_unet_forward")
+        ops.LAUNCHES += int(self._lib.cpd_unet_plan_launches(self._plan))
+        self._keep_inject = keep  # read asynchronously
+        return eps
+
+    def _decoder_geometry(self, h, w):
+        """Per output block: (channels, h, w) of the popped skip tensor and of the decoder state entering the block."""
         mc = self.model_channels
-        h0 = self._buf("input_blocks.0.out", R * h * w * mc)
-        ops.conv_in(x, W["input_blocks.0.0.w"], W["input_blocks.0.0.b"], h0, n=B, cin=cin, h=h, w=w, cout=mc, scale=scale,
-                    rows_per_image=rows_per_image, scale_dev=scale_dev)
-        hs = [(h0, mc, h, w)]
-        hcur, ch = h0, mc
-        for i, layers in enumerate(self.inputs[1:], start=1):
-            hcur, ch, h, w = self._run_block(f"input_blocks.{i}.", layers, hcur, None, R, h, w, emb_all, emb_stride, stats)
-            hs.append((hcur, ch, h, w))
-        hcur, ch, h, w = self._run_block("middle_block.", self.middle, hcur, None, R, h, w, emb_all, emb_stride, stats)
-        skips, feats = [], []
-        inject = inject or {}
-        for i, layers in enumerate(self.outputs):
-            s, sc, sh, sw = hs.pop()
-            assert (sh, sw) == (h, w)
-            if return_skips:
-                skips.append(s.view(R, sh, sw, sc).permute(0, 3, 1, 2))
-            if inject.get("attns") is not None and inject.get("attns_stop", 10) > i:  # unet.py:806-809: replace the skip tensor
-                s = self._nhwc(inject["attns"][i], f"inject.skip.{i}", R, sc, sh, sw)
-            if inject.get("feats") is not None and inject.get("feats_stop", 10) > i:  # unet.py:810-813: replace h
-                hcur = self._nhwc(inject["feats"][i], f"inject.h.{i}", R, ch, h, w)
-            hcur, ch, h, w = self._run_block(f"output_blocks.{i}.", layers, hcur, (s, sc), R, h, w, emb_all, emb_stride, stats)
-            if return_feats:  # unet.py:816-817
-                feats.append(hcur.view(R, h, w, ch).permute(0, 3, 1, 2).float().clone())
-        gn = self._buf("gn", R * h * w * ch)
-        ops.groupnorm(hcur, W["out.gn.g"], W["out.gn.b"], gn, stats, n_img=R, hw=h * w, c0=ch, eps=1e-5, silu=True)
-        cout = self.cfg["out_channels"]
-        out = self._buf("eps", R * cout * h * w, self.eps_dtype).view(R, cout, h, w)
-        ops.conv_out(gn, W["out.w"], W["out.b"], out, n=R, h=h, w=w, cin=ch, cout=cout)
-        if return_feats:
-            return (out, skips, feats) if return_skips else (out, feats)
-        return (out, skips) if return_skips else out
+        hs = [(mc, h, w)]
+        ch, ch_h, ch_w = mc, h, w
+        for layers in self.inputs[1:]:
+            for l in layers:
+                if l[0] == "res":
+                    ch = l[2]
+                elif l[0] == "down":
+                    ch_h, ch_w = ch_h // 2, ch_w // 2
+            hs.append((ch, ch_h, ch_w))
+        geo = []
+        for layers in self.outputs:
+            s = hs.pop()
+            geo.append((s, (ch, ch_h, ch_w)))
+            for l in layers:
+                if l[0] == "res":
+                    ch = l[2]
+                elif l[0] == "up":
+                    ch_h, ch_w = 2 * ch_h, 2 * ch_w
+        return geo
 
     @torch.no_grad()
     def forward_rows(self, x, c_in, t, rows_per_image, inject=None):
         """Fast path used by the Denoiser: x [B,4,h,w] fp32 (unscaled), every image is evaluated on
         `rows_per_image` conditioning rows sharing x * c_in and the timestep t (denoiser.py:383-393).
-        Returns eps rows [B*rows_per_image, 4, h, w] (eps_dtype), image-major."""
-        if not self.use_cuda_graph or ops.PROFILE is not None or inject:
-            # eager: profiling, or feature / skip injection (caller tensors change per call: not part of the captured graph)
-            t_rows = torch.full((1,), float(t), dtype=torch.float32, device=self.device)
-            return self._forward_impl(x.contiguous(), float(c_in), rows_per_image, t_rows, shared_t=True, inject=inject)
-        # One CUDA graph per (shape, rows, context layout): the ~850 kernel launches of an evaluation are replayed with a
-        # single cudaGraphLaunch; the per-step scalars (c_in, t) and x live in static device buffers.
-        ctx = self._ctx
-        key = (tuple(x.shape), rows_per_image, None if ctx is None else (ctx["rc"], ctx["ntok"]),
-               None if self._y is None else tuple(self._y.shape))
-        g = self._graphs.get(key)
-        if g is None:
+        Returns eps rows [B*rows_per_image, 4, h, w] (eps_dtype), image-major.  The result lives in a buffer that the next
+        call with the same shape overwrites."""
+        if self._ctx_key is None:
+            raise RuntimeError("UNetModel: no text context set (call set_context or pass `context`)")
+        if self.adm and not self._y_rows:
+            raise RuntimeError("UNetModel: no vector conditioning set (call set_vector or pass `y`)")
+        key = (tuple(x.shape), rows_per_image)
+        st = self._static.get(key)
+        if st is None:
+            # static buffers: the plan's CUDA graph of this shape is captured on THESE addresses and replayed per step; the
+            # per-step scalars (c_in, t) live in a 2-float device buffer
+            B, cout = x.shape[0], self.cfg["out_channels"]
             st = dict(x=torch.empty(tuple(x.shape), dtype=torch.float32, device=self.device),
-                      sc=torch.empty(2, dtype=torch.float32, device=self.device))  # [c_in, t]
-            st["x"].copy_(x)
-            st["sc"].copy_(torch.tensor([float(c_in), float(t)], dtype=torch.float32))
-            # eager warm-up: allocates every workspace buffer and configures the kernels outside the capture
-            self._forward_impl(st["x"], 1.0, rows_per_image, st["sc"][1:2], shared_t=True, scale_dev=st["sc"][0:1])
-            torch.cuda.synchronize(self.device)
-            n0 = ops.LAUNCHES
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                out = self._forward_impl(st["x"], 1.0, rows_per_image, st["sc"][1:2], shared_t=True, scale_dev=st["sc"][0:1])
-            st.update(graph=graph, out=out, launches=ops.LAUNCHES - n0)
-            g = self._graphs[key] = st
-        g["x"].copy_(x, non_blocking=True)
-        g["sc"][0:1].fill_(float(c_in))  # scalars travel by value in the fill kernels' parameters (no host buffer to race on)
-        g["sc"][1:2].fill_(float(t))
-        g["graph"].replay()
-        ops.LAUNCHES += g["launches"]
-        return g["out"]
+                      sc=torch.empty(2, dtype=torch.float32, device=self.device),
+                      eps=torch.empty(B * rows_per_image, cout, x.shape[2], x.shape[3], dtype=self.eps_dtype, device=self.device))
+            self._static[key] = st
+        st["x"].copy_(x, non_blocking=True)
+        st["sc"][0:1].fill_(float(c_in))  # scalars travel by value in the fill kernels' parameters (no host buffer to race on)
+        st["sc"][1:2].fill_(float(t))
+        return self._run(st["x"], rows_per_image, st["sc"][0:1], st["sc"][1:2], 1, st["eps"], inject=inject,
+                         no_graph=not self.use_cuda_graph)
 
     @torch.no_grad()
     def forward(self, x, timesteps=None, context=None, y=None, **kwargs):
         """Reference call signature (unet.py:765): x [N,4,h,w], timesteps [N], context [N or Rc, tokens, D].
-        Returns out [N,4,h,w] (bf16) or (out, skips) when return_attn=True (the 12 skip tensors, unet.py:802-804)."""
+        Returns out [N,4,h,w] (eps_dtype) or (out, skips) when return_attn=True (the 12 skip tensors, unet.py:802-804);
+        with return_feat=True the per-output-block features are appended (unet.py:816-817).  Results are owned tensors."""
         if y is not None or self.adm:
             self.set_vector(y)
         inject = None
@@ -557,6 +355,8 @@ class UNetModel:
                           attns=kwargs.get("inject_attns"), attns_stop=kwargs.get("inject_attns_stop", 10))
         if context is not None:
             self.set_context(context)
+        if self._ctx_key is None:
+            raise RuntimeError("UNetModel: no text context set (call set_context or pass `context`)")
         n = x.shape[0]
         x = x.to(self.device, torch.float32).contiguous()
         t_rows = torch.as_tensor(timesteps).to(self.device, torch.float32).reshape(-1).contiguous()
@@ -564,15 +364,16 @@ class UNetModel:
             raise ValueError("timesteps must have one entry per row of x")
         if n > 32:
             raise NotImplementedError("more than 32 rows with distinct timesteps: use forward_rows")
-        res = self._forward_impl(x, 1.0, 1, t_rows, shared_t=False, return_skips=bool(kwargs.get("return_attn", False)),
-                                 inject=inject, return_feats=bool(kwargs.get("return_feat", False)))
-
-        # The executor returns views of its reusable activation buffers; this entry point mirrors the reference module, whose
-        # results stay valid across calls, so hand out copies (the fast path, forward_rows, keeps returning the buffer).
-        def own(v):
-            if isinstance(v, torch.Tensor):
-                return v.clone()
-            return type(v)(own(e) for e in v) if isinstance(v, (list, tuple)) else v
-        return own(res)
+        out = torch.empty(n, self.cfg["out_channels"], x.shape[2], x.shape[3], dtype=self.eps_dtype, device=self.device)
+        self._run(x, 1, None, t_rows, n, out, inject=inject, no_graph=True)
+        want_skips, want_feats = bool(kwargs.get("return_attn", False)), bool(kwargs.get("return_feat", False))
+        if not (want_skips or want_feats):
+            return out
+        # the reference pops the skip tensors in decoder order (unet.py:801-804): last input block first
+        skips = [self._tap(0, i, n).clone() for i in reversed(range(len(self.inputs)))] if want_skips else None
+        feats = [self._tap(2, i, n).float().clone() for i in range(len(self.outputs))] if want_feats else None
+        if want_feats:
+            return (out, skips, feats) if want_skips else (out, feats)
+        return out, skips
 
     __call__ = forward

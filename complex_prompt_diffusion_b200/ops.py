@@ -180,13 +180,12 @@ def threshold_ex(x, bound, *, alg, threshold):
     return x
 
 
-AUTOTUNE = os.environ.get("CPD_GEMM_AUTOTUNE", "1") != "0"  # time the tile-shape variants of cpd_gemm_conv once per layer shape (first eager call) and keep the best
-_TUNED = {}          # shape key -> variant code
-_TUNE_CANDIDATES = (160, 128, 96, 192, 224, 256, 64, 2160, 2128, 2256, 2096, 2192, 1, 2)  # 1, 2: one-tile-per-CTA kernel
-_TUNE_SPLITK = (20160, 30160, 40160, 22160, 32160, 42160, 20128, 40128)  # small-M layers: split-K x tile shape
+# Tile-variant selection of cpd_gemm_conv lives in the library (csrc/gemm_tune.cu): with variant 0 an unseen problem shape is timed on
+# every applicable variant the first time it is launched outside stream capture (CPD_GEMM_AUTOTUNE=0 switches that off) - this
+# module only lends the scratch output and the split-K workspace.
 _SPLITK_WS = {}      # device index -> fp32 scratch for the split-K partial tiles
 _SPLITK_FLOATS = 32 * 1024 * 1024
-_TUNE_ROUNDS, _TUNE_REPS = 2, 5
+_TUNE_SCRATCH = {}   # device index -> byte scratch at least as large as the largest GEMM output seen
 
 
 def _splitk_ws(device):
@@ -196,45 +195,30 @@ def _splitk_ws(device):
     return ws
 
 
-def _tune_gemm(key, p, out, residual):
-    """Try every tile-shape variant on this exact problem (output redirected to a scratch tensor so that in-place residual
-    launches stay idempotent), CUDA-event timed; returns the fastest variant code."""
+def _tune_scratch(device, nbytes):
+    t = _TUNE_SCRATCH.get(device.index)
+    if t is None or t.numel() < nbytes:
+        if torch.cuda.is_current_stream_capturing():
+            return t
+        t = _TUNE_SCRATCH[device.index] = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    return t
+
+
+def gemm_tune_table():
+    """The library's per-shape variant table as text (cpd_gemm_tune_export): broadcast it from rank 0 and `gemm_tune_import` it on
+    the other ranks when every process must pick identical tile variants (bit-identical results across ranks)."""
     lib = load()
-    scratch = torch.empty_like(out)
-    real_d = p.d
-    p.d = scratch.data_ptr()
-    cands = (p.geglu_block,) if p.epilogue == CPD_EPI_GEGLU else _TUNE_CANDIDATES
-    rows = p.n_img * (p.h_in // p.stride) * (p.w_in // p.stride)
-    k_iters = p.ksize * p.ksize * (p.c0 + p.c1) // 64
-    if p.epilogue != CPD_EPI_GEGLU and -(-rows // 256) * -(-p.n_out // 160) <= 40 and k_iters >= 32:
-        cands = cands + _TUNE_SPLITK  # too few tiles for 74 SM pairs: also try split-K
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    times = {}
-    for rnd in range(_TUNE_ROUNDS):  # candidates are often within a few per cent: keep the minimum over interleaved rounds
-        for v in cands:
-            if v % 1000 >= p.n_out + 32 and v % 1000 > 64:  # tile much wider than N: all padding
-                continue
-            if rnd and v not in times:
-                continue
-            p.variant = v
-            if lib.cpd_gemm_conv(C.byref(p), stream_ptr()) != 0:
-                continue  # variant not applicable to this shape
-            e0.record()
-            for _ in range(_TUNE_REPS):
-                lib.cpd_gemm_conv(C.byref(p), stream_ptr())
-            e1.record()
-            e1.synchronize()
-            times[v] = min(times.get(v, float("inf")), e0.elapsed_time(e1) / _TUNE_REPS)
-    best, best_t = 0, float("inf")
-    for v in cands:  # ties go to the earlier candidate
-        if v in times and times[v] < best_t:
-            best, best_t = v, times[v]
-    p.d = real_d
-    _TUNED[key] = best
-    if os.environ.get("CPD_GEMM_DEBUG"):
-        print(f"tuned gemm rows={rows} N={p.n_out} K={p.ksize * p.ksize * (p.c0 + p.c1)} epi={p.epilogue} res={residual is not None}: "
-              f"variant {best} ({best_t * 1e3:.1f} us)", flush=True)
-    return best
+    n = lib.cpd_gemm_tune_export(None, 0)
+    buf = C.create_string_buffer(int(n))
+    lib.cpd_gemm_tune_export(buf, n)
+    return buf.value.decode()
+
+
+def gemm_tune_import(text):
+    n = load().cpd_gemm_tune_import(text.encode())
+    if n < 0:
+        raise RuntimeError("cpd_gemm_tune_import: malformed table")
+    return n
 
 
 def gemm_conv(a0, wt, out, *, n_img, h, w, c0, n_out, a1=None, c1=0, ksize=1, stride=1, bias=None, rowvec=None,
@@ -263,12 +247,10 @@ def gemm_conv(a0, wt, out, *, n_img, h, w, c0, n_out, a1=None, c1=0, ksize=1, st
     ws = _splitk_ws(out.device)
     p.splitk_ws, p.splitk_ws_floats = ws.data_ptr(), ws.numel()
     p.geglu_block = geglu_block if epilogue == CPD_EPI_GEGLU else 0
-    if variant == 0 and AUTOTUNE:
-        key = (n_img, h, w, c0, c1, n_out, ksize, stride, epilogue, p.geglu_block, residual is not None, rowvec is not None, a_f16, m_valid)
-        variant = _TUNED.get(key)
-        if variant is None:
-            variant = 0 if torch.cuda.is_current_stream_capturing() else _tune_gemm(key, p, out, residual)
-        p.variant = variant
+    if variant == 0:
+        sc = _tune_scratch(out.device, out.numel() * out.element_size())
+        if sc is not None:
+            p.tune_scratch, p.tune_scratch_bytes = sc.data_ptr(), sc.numel()
     flops = 2.0 * n_img * (h // stride) * (w // stride) * n_out * ksize * ksize * (c0 + c1)
     label = f"M={n_img * (h // stride) * (w // stride)} N={n_out} K={ksize * ksize * (c0 + c1)}" + (" geglu" if epilogue else "")
     with _Prof("gemm_conv", flops, label):
@@ -371,7 +353,8 @@ def attention(q, k, vt, o, *, ldq, ldk, ldvt, ldo, batch, heads, nq, nk, nk_pad,
     p.q, p.ldq, p.k, p.ldk, p.vt, p.ldvt, p.o, p.ldo = q.data_ptr(), ldq, k.data_ptr(), ldk, vt.data_ptr(), ldvt, o.data_ptr(), ldo
     p.batch, p.heads, p.nq, p.nk, p.nk_pad, p.dpad, p.scale = batch, heads, nq, nk, nk_pad, dpad, float(scale)
     p.kv_batch, p.act_fp16, p.d_head = kv_batch, f16, d_head
-    with _Prof("attention", 4.0 * batch * heads * nq * nk * dpad, f"B={batch} H={heads} nq={nq} nk={nk} d={dpad}"):
+    d_alg = d_head if d_head > 0 else dpad  # algorithmic work counts the REAL head dim, not the padded one
+    with _Prof("attention", 4.0 * batch * heads * nq * nk * d_alg, f"B={batch} H={heads} nq={nq} nk={nk} d={d_alg}"):
         check(load().cpd_attention(C.byref(p), stream_ptr()), "cpd_attention")
     _count()
     return o

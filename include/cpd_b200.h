@@ -377,6 +377,16 @@ cpd_status cpd_unet_forward(cpd_unet_plan* plan, const cpd_unet_io* io, void* st
 cpd_status cpd_unet_plan_buffer(cpd_unet_plan* plan, const char* name, void** ptr, int64_t* numel);
 /* Kernels launched by the last cpd_unet_forward / cpd_cache_context_kv of this plan (graph replays count their nodes). */
 int64_t cpd_unet_plan_launches(cpd_unet_plan* plan);
+/* Output of block `index` of the LAST forward as an NHWC activation tensor [rows][h][w][channels]: which = 0 input blocks (the
+ * 12 skip tensors `return_attn` hands back, unet.py:802-804), 1 the middle block, 2 output blocks (`return_feat`, :816-817).
+ * cpd_unet_plan_blocks(plan, which) = how many blocks there are. */
+cpd_status cpd_unet_plan_tap(cpd_unet_plan* plan, int which, int index, void** ptr, int* channels, int* h, int* w);
+int cpd_unet_plan_blocks(cpd_unet_plan* plan, int which);
+/* Per-launch CUDA-event timing of eager forwards (bench.py's roofline leg, tools/profile_layers.py): on = 1 clears the records
+ * and brackets every following kernel-level call with events (graphs are bypassed while it is on); the dump synchronises the
+ * device and writes "kind\tlabel\tmicroseconds\tflops" lines (NUL-terminated), returning the bytes needed. */
+void cpd_unet_plan_set_profile(cpd_unet_plan* plan, int on);
+int64_t cpd_unet_plan_profile_dump(cpd_unet_plan* plan, char* buf, int64_t cap);
 
 /* ---- debug aids (not part of the product path; NULL / never called in production) ---------------------------------------- */
 /* clock64 stamps of CTA 0's first 8 work items of every following cross-attention launch go to dev_buf (192 int64 on the

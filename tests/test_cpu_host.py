@@ -56,6 +56,22 @@ def test_argument_validation_without_gpu(lib_path):
     assert lib.cpd_threshold_ex(16, 1, 4, 64, _lib.CPD_THRESH_RENORM, 250.0, 16, None) != 0
     assert b"outside [0, 1]" in lib.cpd_last_error()
     assert lib.cpd_threshold_ex(16, 1, 0, 64, _lib.CPD_THRESH_RENORM, 0.9, 16, None) != 0
+    # plan-level entry points: configuration errors are caught before anything touches the device
+    assert lib.cpd_unet_plan_create(None, None) != 0
+    assert b"null argument" in lib.cpd_last_error()
+    cfg, plan = _lib.UNetConfig(), ctypes.c_void_p()
+    cfg.n_levels, cfg.model_channels = 2, 100
+    assert lib.cpd_unet_plan_create(ctypes.byref(cfg), ctypes.byref(plan)) != 0 and not plan.value
+    assert b"multiple of 64" in lib.cpd_last_error()
+    assert lib.cpd_unet_forward(None, None, None) != 0
+    assert lib.cpd_pack_weights(None, b"x", None, 0, 0, 0) != 0
+    # the tuned-variant table round-trips through its text form
+    assert lib.cpd_gemm_tune_import(b"1,1,4096,320,0,320,1,1,0,0,0,0,1,0=160\n") == 1
+    n = lib.cpd_gemm_tune_export(None, 0)
+    buf = ctypes.create_string_buffer(int(n))
+    lib.cpd_gemm_tune_export(buf, n)
+    assert b"1,1,4096,320,0,320,1,1,0,0,0,0,1,0=160" in buf.value
+    assert lib.cpd_gemm_tune_import(b"garbage") == -1
     p2 = _lib.StepParams()
     p2.eps = p2.x = 16
     p2.n_sub, p2.hw = 17, 64

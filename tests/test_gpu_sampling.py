@@ -260,10 +260,13 @@ def _unet_pair(cfg_name, dtype_oracle, act_dtype=torch.float16):
 def _layer_report(oracle, gpu, R):
     rows = []
     for name, ref in oracle.taps.items():
-        for key, buf in gpu._ws.items():
-            if key[0] == name + ".out" and buf.numel() == ref.numel():
-                got = buf.view(R, ref.shape[2], ref.shape[3], ref.shape[1]).permute(0, 3, 1, 2)
-                rows.append((name, rel(got, ref)))
+        try:
+            buf = gpu.plan_buffer(name + ".out")  # NHWC activation buffer of the plan (cpd_unet_plan_buffer)
+        except RuntimeError:
+            continue
+        if buf.numel() == ref.numel():
+            got = buf.view(R, ref.shape[2], ref.shape[3], ref.shape[1]).permute(0, 3, 1, 2)
+            rows.append((name, rel(got, ref)))
     return rows
 
 

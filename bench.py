@@ -10,7 +10,10 @@ A "step" is ONE full generation of the workload batch through the drop-in path:
   = 20 x 16 = 320 UNet row-evaluations (257 TFLOP algorithmic) per step and per GPU.
 `value` = images/s over all GPUs with inputs resident in HBM; `e2e` = the same through the public sampler API
 with HOST inputs (pinned x_T and embeddings copied H2D, final latents read D2H inside the timed region).
-Multi-GPU: images are sharded across ranks (weak scaling: 4 images per GPU), no data-path collective.
+Multi-GPU: images are sharded across ranks (weak scaling: 4 images per GPU), no data-path collective; at N > 1 a second
+timed leg (`strong_scaling`) runs a FIXED global batch of 4 through dist.sample_sharded - image-sharded down to one image per
+GPU, then the (1 + N) conditioning rows of an image sharded over a rank group with an NCCL all-gather of eps every step.
+`parity` = the GPU's first sampler step of image 0 against the CPU oracle's (the run the cpu_baseline leg times anyway).
 """
 import argparse
 import json
@@ -27,10 +30,10 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one gemm2_kernel launch (conv3x3 16x64x64 320->320, ncu --set full,
-# profiles/r01_ncu_full_v3.txt): 43.9 MB + 8.4 MB; algorithmic bytes of that launch = 42 MB in + 42 MB out + 1.8 MB weights
-# (most of the output is still in the 126 MB L2 when the launch ends, so its write-back is not seen inside the launch).
-NCU_TRAFFIC = {"bytes_per_launch": 52.31e6, "launch": "conv3x3 M=65536 N=320 K=2880", "source": "profiles/r01_ncu_full_v3.txt"}
+# roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel INSIDE the timed step, taken
+# from the committed ncu capture of this same command (tools/capture_profiles.sh writes profiles/r02_traffic.json: which launch,
+# its bytes, the .ncu-rep it came from).  null when no capture is committed - it is never a constant typed into this file.
+TRAFFIC_FILE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_traffic.json")
 
 WORKLOAD = dict(workload="SD-1.5 512px (64x64 latent), DPM++ 2M Karras 20 steps, 3 weighted sub-prompts + uncond, batch 4",
                 model="sd15", latent=64, sampler="DPM++ 2m", scheduler="karras", sampler_steps=20, n_sub=3, batch=4,
@@ -55,6 +58,8 @@ def parse():
     ap.add_argument("--act-dtype", default="fp16", choices=["fp16", "bf16"],
                     help="16-bit format of the inter-kernel activations / tensor-core operands (same tensor rate; fp16 keeps 3 more mantissa bits)")
     ap.add_argument("--no-decode", action="store_true", help="skip the extra latents -> images (VAE decode) measurement")
+    ap.add_argument("--no-bf16-leg", action="store_true", help="skip the short bf16-activation leg (N = 1 only)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the fixed-global-batch (strong scaling) leg at N > 1")
     return ap.parse_args()
 
 
@@ -143,15 +148,26 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------ CPU arm
 def cpu_sample(cfg_name, latent, n_sub, sampler_steps_sample, threads, sampler="DPM++ 2m", pred_type="epsilon", total_steps=None):
     """Times the oracle port on the host cores on a BOUNDED sample: `sampler_steps_sample` sampler steps of ONE
-    image (each = 1 + n_sub UNet row-evaluations, fp32), returns seconds per (image x sampler-step)."""
+    image (each = 1 + n_sub UNet row-evaluations, fp32 arithmetic on the bf16-rounded weights - the model dtype - with the
+    product's dtype boundaries).  Returns (seconds per image x sampler-step, the oracle's per-step trace)."""
     from oracle.unet import OracleUNet, make_weights
     from oracle.denoiser import OracleDenoiser
     from oracle import samplers as OS
     torch.set_num_threads(threads)
     cfg = oracle_cfg(cfg_name)
-    unet = OracleUNet(cfg, make_weights(cfg, seed=0))
+    unet = OracleUNet(cfg, {k: v.to(torch.bfloat16).float() for k, v in make_weights(cfg, seed=0).items()})
+
+    class Side:  # the product's dtype boundaries: bf16 context / t / x, fp32 eps out
+        def parameters(self):
+            return iter([torch.zeros(1, dtype=torch.bfloat16)])
+
+        def __call__(self, x, t, ctx, y=None, **k):
+            kw = {} if y is None else {"y": y.to(torch.bfloat16).float()}
+            o = unet(x.to(torch.bfloat16).float(), t.float(), ctx.to(torch.bfloat16).float(), **kw)
+            return o, [o] * 12
     uc, c, x_T = make_inputs(cfg, latent, 1, n_sub)
-    den = OracleDenoiser(unet)
+    den = OracleDenoiser(Side(), dtype=torch.bfloat16)
+    den.trace = []
     sig = den.scheduler.get_sigmas("karras", total_steps or WORKLOAD["sampler_steps"])
     x = x_T * sig[0]
     kw = dict(conditioning=c, unconditional_conditioning=uc, unconditional_guidance_scale=WORKLOAD["guidance"], total_steps=len(sig),
@@ -165,7 +181,7 @@ def cpu_sample(cfg_name, latent, n_sub, sampler_steps_sample, threads, sampler="
     else:
         OS.SAMPLERS[sampler](den, x, sig[:sampler_steps_sample + 1], kw, lambda t: torch.randn_like(t))
     dt = time.perf_counter() - t0
-    return dt / sampler_steps_sample
+    return dt / sampler_steps_sample, den.trace
 
 
 def run_reference(args):
@@ -173,11 +189,11 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample_steps = 1
+    sample_steps = 2  # at least two sampler steps of the workload, extrapolated linearly
     for _ in range(args.warmup if args.latent <= 16 else 0):
         cpu_sample(args.model, args.latent, args.n_sub, sample_steps, threads, args.sampler, args.pred_type, args.sampler_steps)
-    times = [cpu_sample(args.model, args.latent, args.n_sub, sample_steps, threads, args.sampler, args.pred_type, args.sampler_steps)
-             for _ in range(max(1, min(args.steps, 3)))]
+    times = [cpu_sample(args.model, args.latent, args.n_sub, sample_steps, threads, args.sampler, args.pred_type, args.sampler_steps)[0]
+             for _ in range(max(1, min(args.steps, 2)))]
     per_img_step = sum(times) / len(times)
     sec_per_batch = per_img_step * args.sampler_steps * args.batch
     ips = args.batch / sec_per_batch
@@ -212,6 +228,7 @@ def run_b200(args):
     unet = UNetModel(sd, device=dev, use_cuda_graph=not args.no_graph, act_dtype=act, **fixtures.unet_kwargs(args.model))
     del sd
     n_sub, B, S = args.n_sub, args.batch, args.sampler_steps
+    R_rows = 1 + n_sub
     uc, c, x_T = make_inputs(cfg, args.latent, B, n_sub, seed=rank)
     wrapper = samplers.make({"name": args.sampler, "args": {}}, {"model": {"unet": unet}})
     kw = dict(unconditional_guidance_scale=WORKLOAD["guidance"], scheduler=WORKLOAD["scheduler"], rng_compat=False, pred_type=args.pred_type)
@@ -272,7 +289,7 @@ def run_b200(args):
         from complex_prompt_diffusion_b200.models.vae import VAEDecoder
         vcfg = fixtures.VAE_PRESETS["sd"]
         vae = VAEDecoder(fixtures.random_state_dict(fixtures.vae_param_shapes(vcfg), seed=0), device=dev, **vcfg)
-        img_h = torch.empty(B, 3, args.latent * 8, args.latent * 8).pin_memory()
+        img_h = torch.empty(B, args.latent * 8, args.latent * 8, 3, dtype=torch.uint8).pin_memory()
 
     def step_e2e_images():
         xd = x_T_h.to(dev, non_blocking=True)
@@ -280,7 +297,7 @@ def run_b200(args):
         cd = {k: [(s, e.to(dev, non_blocking=True), g_, m) for (s, e, g_, m) in v] for k, v in c_h.items()}
         lat = wrapper.sampler.sample(steps=S, batch_size=B, shape=[4, args.latent, args.latent], x_T=xd, conditioning=cd,
                                      unconditional_conditioning=ucd, **dict(kw))
-        img_h.copy_(vae.decode(lat, unscale=True), non_blocking=True)
+        img_h.copy_(vae.decode_to_uint8(lat, unscale=True), non_blocking=True)  # prompts.py:324-334,472-475
         torch.cuda.current_stream().synchronize()
         return img_h
 
@@ -311,6 +328,58 @@ def run_b200(args):
             step_e2e_images()
         ms_img = timed(step_e2e_images, args.steps)
 
+    # Strong scaling: a FIXED global batch of 4 images on N GPUs - N = 2: two images per GPU, N = 4: one image
+    # per GPU (no collective), N = 8: the 4 conditioning rows of an image sharded over a group of 2 ranks, eps rows
+    # all-gathered over NCCL every step, every rank stepping the replicated x redundantly.
+    strong = None
+    if world > 1 and not args.no_strong and not os.environ.get("CPD_BENCH_NCU"):
+        import torch.distributed as dist
+        from complex_prompt_diffusion_b200 import dist as D
+        GB = WORKLOAD["batch"]
+        uc_s, c_s, x_s = make_inputs(cfg, args.latent, GB, n_sub, seed=0)  # the SAME global inputs on every rank
+        uc_s = uc_s.to(dev)
+        c_s = {k: [(s_, e.to(dev), g_, m) for (s_, e, g_, m) in v] for k, v in c_s.items()}
+        x_s = x_s.to(dev)
+        skw = dict(kw)
+        if y is not None:
+            skw["y"] = make_y(cfg, n_sub, seed=0).to(dev)
+        part = D.partition(GB, R_rows, world, rank)
+
+        def step_strong():
+            return D.sample_sharded(wrapper, steps=S, batch=GB, shape=[4, args.latent, args.latent], x_T=x_s, conditioning=c_s,
+                                    unconditional_conditioning=uc_s, world=world, rank=rank, **dict(skw))
+        for _ in range(2):
+            step_strong()
+        n_st = max(2, min(args.steps, 5))
+        ms_st = timed(step_strong, n_st)
+        wrapper.sampler.denoiser.set_row_partition(None)
+        ag_us = None
+        if part.needs_allgather:  # the collective alone: one eps all-gather of this rank group, CUDA-event timed
+            grp = D._GROUPS[world][tuple(part.group_ranks)]
+            local = torch.randn(len(part.rows), 4 * args.latent * args.latent, device=dev).to(unet.eps_dtype)
+            for _ in range(5):
+                D.allgather_eps_rows(local, part, group=grp)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(50):
+                D.allgather_eps_rows(local, part, group=grp)
+            e1.record()
+            torch.cuda.synchronize()
+            t_ag = torch.tensor([e0.elapsed_time(e1) * 1e3 / 50], device=dev)
+            dist.all_reduce(t_ag, op=dist.ReduceOp.MAX)
+            ag_us = float(t_ag)
+        per_gpu_weak = (B * args.steps / (ms / 1e3))  # images/s of ONE GPU at 4 images per GPU (this run's weak leg, max over ranks)
+        ips_strong = GB * n_st / (ms_st / 1e3)
+        mode = ("images sharded, no collective" if GB >= world else
+                f"rows sharded: {len(part.group_ranks)} ranks per image, {max(1, len(part.rows))} row(s) per rank, NCCL all-gather of eps per step")
+        strong = {"global_batch": GB, "images_per_s": ips_strong, "ms_per_generation": ms_st / n_st, "steps": n_st, "mode": mode,
+                  "units_per_gpu": f"{max(1, GB // world)} image(s) x {len(part.rows)} row(s)", "allgather_us_per_step": ag_us,
+                  "efficiency_vs_n1": ips_strong / (world * per_gpu_weak),
+                  "efficiency_note": "images/s of the fixed batch / (N x the per-GPU images/s of this run's weak leg at 4 images per GPU)",
+                  "limiter": ("small-M GEMM efficiency: R x hw rows per GPU shrink from 65536 to 16384 / 8192 at the 64x64 level, the 16x16 "
+                              "and 8x8 levels cannot fill 74 SM pairs; the all-gather itself is latency-bound (allgather_us_per_step)")}
+
     imgs = B * world * args.steps
     ips = imgs / (ms / 1e3)
     ips_e2e = imgs / (ms_e2e / 1e3)
@@ -319,54 +388,122 @@ def run_b200(args):
     flops_row = fixtures.unet_flops(cfg, args.latent, args.latent)
     pk = peaks()
 
-    # dominant kernel (tcgen05 implicit-GEMM conv / GEMM): per-launch CUDA-event timing over one more step
+    # dominant kernel (tcgen05 implicit-GEMM conv / GEMM): per-launch CUDA-event timing over one more step (the plan brackets
+    # every kernel-level call with events while profiling is on; the fused step is timed by ops.PROFILE)
     roof, roof_sampler = None, None
     if rank == 0:
         ops.PROFILE = []
+        unet.profile(True)
         step_resident()
         torch.cuda.synchronize()
+        recs = unet.profile_records()  # (kind, label, us, flops)
+        unet.profile(False)
         prof, ops.PROFILE = ops.PROFILE, None
-        g_ms = sum(a.elapsed_time(b) for (k_, a, b, f, _l) in prof if k_ == "gemm_conv")
-        g_fl = sum(f for (k_, a, b, f, _l) in prof if k_ == "gemm_conv")
-        g_n = sum(1 for (k_, a, b, f, _l) in prof if k_ == "gemm_conv")
-        at_ms = sum(a.elapsed_time(b) for (k_, a, b, f, _l) in prof if k_ == "attention")
-        at_fl = sum(f for (k_, a, b, f, _l) in prof if k_ == "attention")
+        recs += [(k_, _l, a.elapsed_time(b) * 1e3, f) for (k_, a, b, f, _l) in prof]
+        g_ms = sum(us for (k_, _l, us, f) in recs if k_ == "gemm_conv") / 1e3
+        g_fl = sum(f for (k_, _l, us, f) in recs if k_ == "gemm_conv")
+        g_n = sum(1 for (k_, _l, us, f) in recs if k_ == "gemm_conv")
+        at_ms = sum(us for (k_, _l, us, f) in recs if k_ == "attention") / 1e3
+        at_fl = sum(f for (k_, _l, us, f) in recs if k_ == "attention")
         breakdown = {}
-        for (k_, a, b, f, _l) in prof:
-            breakdown[k_] = breakdown.get(k_, 0.0) + a.elapsed_time(b)
+        for (k_, _l, us, f) in recs:
+            breakdown[k_] = breakdown.get(k_, 0.0) + us / 1e3
         # GEMM launches grouped by shape class: where the tensor time goes
         by_shape = {}
-        for (k_, a, b, f, _l) in prof:
+        for (k_, _l, us, f) in recs:
             if k_ == "gemm_conv":
-                key = f"{f / 1e9:.1f}GF"
-                d = by_shape.setdefault(key, [0, 0.0])
+                d = by_shape.setdefault(f"{f / 1e9:.1f}GF", [0, 0.0])
                 d[0] += 1
-                d[1] += a.elapsed_time(b)
+                d[1] += us / 1e3
         top = sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:12]
+        by_attn = {}
+        for (k_, _l, us, f) in recs:
+            if k_ == "attention":
+                d = by_attn.setdefault(_l, [0, 0.0])
+                d[0] += 1
+                d[1] += us / 1e3
         sys.stderr.write("per-op-kind ms in one step: " + json.dumps({k: round(v, 2) for k, v in breakdown.items()}) + "\n")
         sys.stderr.write("top GEMM shape classes (GFLOP per launch: [launches, ms, TFLOP/s]): " + json.dumps(
             {k: [v[0], round(v[1], 2), round(float(k[:-2]) * v[0] / v[1], 1)] for k, v in top}) + "\n")
+        sys.stderr.write("attention shapes ([launches, ms]): " + json.dumps({k: [v[0], round(v[1], 2)] for k, v in by_attn.items()}) + "\n")
         achieved = g_fl / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
-        roof = {"bound": "tensor", "kernel": "gemm_conv_kernel (tcgen05 implicit-GEMM conv / GEMM)", "achieved": achieved,
+        traffic = json.load(open(TRAFFIC_FILE)) if os.path.exists(TRAFFIC_FILE) else None
+        roof = {"bound": "tensor", "kernel": "gemm2_kernel (persistent CTA-pair tcgen05 implicit-GEMM conv / GEMM)", "achieved": achieved,
                 "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
-                "traffic": NCU_TRAFFIC["bytes_per_launch"], "traffic_detail": NCU_TRAFFIC,
+                "traffic": traffic["bytes_per_launch"] if traffic else None, "traffic_detail": traffic,
                 "peak_source": pk["source"] + " (sustained bf16)", "launches_per_step": g_n,
                 "avg_launch_us": g_ms * 1e3 / max(g_n, 1), "share_of_step": g_ms / (ms / args.steps),
                 "breakdown_ms_per_step": {k: round(v, 3) for k, v in breakdown.items()},
                 "attention_tflops": at_fl / (at_ms / 1e3) / 1e12 if at_ms > 0 else None,
+                "attention_flops": "algorithmic: 4 B H Nq Nk d with the REAL head dim",
                 "attention_share_of_step": at_ms / (ms / args.steps),
                 "unet_tflops_whole_step": evals_per_step * flops_row / (ms / args.steps / 1e3) / 1e12,
-                "unet_frac_of_peak_whole_step": evals_per_step * flops_row / (ms / args.steps / 1e3) / 1e12 / pk["tf_sustained"]}
+                "unet_frac_of_peak_whole_step": evals_per_step * flops_row / (ms / args.steps / 1e3) / 1e12 / pk["tf_sustained"],
+                "unet_frac_of_burst_peak_whole_step": evals_per_step * flops_row / (ms / args.steps / 1e3) / 1e12 / pk["tf_burst"]}
         roof_sampler = sampler_roofline(ops, dev, pk)
 
-    cpu = None
+    # CPU baseline (the oracle port on the host cores, a bounded sample) and, from the same oracle run, PARITY of the named
+    # configuration at its named size: the GPU evaluates the oracle's own x_0 / sigma_0 (image 0, same seeded inputs)
+    cpu, parity = None, None
     if rank == 0 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        per = cpu_sample(args.model, args.latent, n_sub, 1, threads, args.sampler, args.pred_type, S)
+        n_cpu_steps = 2 if args.latent >= 64 else 4
+        per, trace = cpu_sample(args.model, args.latent, n_sub, n_cpu_steps, threads, args.sampler, args.pred_type, S)
         sec_batch = per * S * B
         cpu = {"value": B / sec_batch, "unit": "images/s", "cores": threads, "kind": "port",
-               "sample": f"1 sampler step of 1 image ({R} fp32 UNet row-evals, oracle port) = {per:.2f} s, extrapolated linearly to "
-                         f"{S} steps x {B} images"}
+               "sample": f"{n_cpu_steps} sampler steps of 1 image ({R} fp32 UNet row-evals each, oracle port) = {per:.2f} s per step, "
+                         f"extrapolated linearly to {S} steps x {B} images"}
+        den = wrapper.sampler.denoiser
+
+        def rel(a, b):
+            a, b = a.detach().float().cpu(), b.detach().float().cpu()
+            return float((a - b).norm() / b.norm().clamp_min(1e-30))
+        uc0, c0, _x = make_inputs(cfg, args.latent, 1, n_sub, seed=0)  # exactly the oracle's prompt (rank 0's inputs)
+        pkw = dict(conditioning={k: [(s_, e.to(dev), g_, m) for (s_, e, g_, m) in v] for k, v in c0.items()},
+                   unconditional_conditioning=uc0.to(dev), unconditional_guidance_scale=WORKLOAD["guidance"], pred_type=args.pred_type,
+                   total_steps=S + 1)
+        if y is not None:
+            pkw["y"] = make_y(cfg, n_sub, seed=0).to(dev)
+        steps_par = []
+        for i_, tr in enumerate(trace):
+            ev = den.evaluate(tr["x"].to(dev), tr["sigma"].reshape(-1)[:1], **dict(pkw, t_idx=i_))
+            torch.cuda.synchronize()
+            lo, hi = den.scheduler.sigma_to_idx(torch.as_tensor(tr["sigma"], dtype=torch.float32).reshape(-1)[:1])
+            steps_par.append({"rows_rel_l2": [rel(ev["rows"][r_], tr["unet_out"][r_]) for r_ in range(tr["unet_out"].shape[0])],
+                              "eps_rel_l2": rel(ev["e_t"], tr["eps"]), "denoised_rel_l2": rel(ev["denoised"], tr["denoised"]),
+                              "low_idx": int(lo.reshape(-1)[0]), "high_idx": int(hi.reshape(-1)[0]),
+                              "low_idx_equal": int(lo.reshape(-1)[0]) == int(tr["low_idx"].reshape(-1)[0]) and
+                              int(hi.reshape(-1)[0]) == int(tr["high_idx"].reshape(-1)[0])})
+        parity = {"what": f"GPU vs CPU oracle on the oracle's own x_i / sigma_i: the first {len(trace)} sampler steps of image 0 at the named size "
+                          f"({args.model} {args.latent}x{args.latent}, {R} rows); rows = the UNet outputs, eps = the combined e_t",
+                  "eps_rel_l2": max(sp["eps_rel_l2"] for sp in steps_par),
+                  "rows_rel_l2": max(max(sp["rows_rel_l2"]) for sp in steps_par),
+                  "denoised_rel_l2": max(sp["denoised_rel_l2"] for sp in steps_par),
+                  "low_idx_equal": all(sp["low_idx_equal"] for sp in steps_par), "tolerance": 1e-2, "steps": steps_par}
+        parity["ok"] = bool(parity["eps_rel_l2"] <= 1e-2 and parity["rows_rel_l2"] <= 1e-2 and parity["low_idx_equal"])
+
+    # bf16 activations (BASELINE.json words config 2 as "bf16"): the same kernels run bf16 operands at the same tensor rate, but
+    # the per-step eps error of ANY bf16-activation evaluation of this UNet is ~1.3e-2 (> the 1e-2 gate), so the headline runs fp16
+    # activations (which is also what the reference's own GPU path does, manager.py:25-36).  One short timed leg for the record.
+    bf16_leg = None
+    if rank == 0 and world == 1 and args.act_dtype == "fp16" and not args.no_bf16_leg and not os.environ.get("CPD_BENCH_NCU"):
+        del unet, wrapper
+        torch.cuda.empty_cache()
+        sd2 = fixtures.random_state_dict(fixtures.unet_param_shapes(cfg), seed=0)
+        unet_b = UNetModel(sd2, device=dev, use_cuda_graph=not args.no_graph, act_dtype=torch.bfloat16, **fixtures.unet_kwargs(args.model))
+        del sd2
+        wb = samplers.make({"name": args.sampler, "args": {}}, {"model": {"unet": unet_b}})
+
+        def step_b():
+            return wb.sampler.sample(steps=S, batch_size=B, shape=[4, args.latent, args.latent], x_T=x_T_d, conditioning=c_d,
+                                     unconditional_conditioning=uc_d, **dict(kw))
+        for _ in range(2):
+            step_b()
+        ms_b = timed(step_b, 2)
+        bf16_leg = {"images_per_s": B * 2 / (ms_b / 1e3), "steps": 2,
+                    "note": "bf16 activations: per-step eps rel-L2 ~1.3e-2 vs the oracle (tests/test_gpu_sampling.py "
+                            "test_unet_forward_vs_oracle, tolerance 2e-2 for this mode) - above the north-star 1e-2 gate"}
+
     if rank == 0:
         line = {"metric": "images_per_s", "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.act_dtype,
@@ -375,19 +512,25 @@ def run_b200(args):
                                l2="working set (1.7 GB weights + activations) larger than L2; no flush needed",
                                precision=("bf16 model weights converted once to fp16 tensor-core operands, fp16 activations, fp32 "
                                           "accumulation and norm statistics (same tensor rate as bf16, 3 more mantissa bits: "
-                                          "needed for the <=1e-2 per-step eps tolerance)") if args.act_dtype == "fp16" else
+                                          "needed for the <=1e-2 per-step eps tolerance; bf16 activations FAIL that gate at ~1.3e-2 "
+                                          "and are reported under bf16_activations)") if args.act_dtype == "fp16" else
                                          ("bf16 model weights and bf16 activations, fp32 accumulation and norm statistics "
                                           "(per-step eps error ~1.3e-2: the noise floor of any bf16 evaluation of this UNet)"),
-                               executor="one CUDA graph per UNet evaluation (~850 kernels, PDL edges), replayed per sampler step"),
+                               executor="C++ plan (cpd_unet_forward): one CUDA graph per UNet evaluation (~850 kernels, PDL edges), replayed per sampler step"),
                 "unet_evals_per_s": evals_per_step * world * args.steps / (ms / 1e3),
                 "e2e": {"value": ips_e2e, "unit": "images/s",
                         "h2d_bytes_per_step": int(x_T_h.numel() * 4 + uc_h.numel() * 4 + sum(e.numel() * 4 for v in c_h.values() for (_, e, _, _) in v)),
                         "d2h_bytes_per_step": int(out_h.numel() * 4)},
-                "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_sampler_step": roof_sampler, "cpu_baseline": cpu}
+                "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_sampler_step": roof_sampler, "cpu_baseline": cpu,
+                "parity": parity}
         if ms_img is not None:
             line["e2e_decoded_images"] = {"value": imgs / (ms_img / 1e3), "unit": "images/s",
-                                          "what": "e2e plus the first-stage decoder (latents -> 512 px images, fp32 images read back D2H)",
-                                          "d2h_bytes_per_step": int(img_h.numel() * 4)}
+                                          "what": "e2e plus the first-stage decoder (latents -> 512 px images, uint8 images read back D2H)",
+                                          "d2h_bytes_per_step": int(img_h.numel() * img_h.element_size())}
+        if strong is not None:
+            line["strong_scaling"] = strong
+        if bf16_leg is not None:
+            line["bf16_activations"] = bf16_leg
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist
@@ -395,32 +538,42 @@ def run_b200(args):
 
 
 def sampler_roofline(ops, dev, pk):
-    """Fused sampler-step kernel at a saturating synthetic batch (>= 256 MB of traffic, larger than L2) and at the
-    named shape (latency)."""
+    """Fused sampler-step kernel at a saturating synthetic batch and at the named shape (latency).  The saturating leg ROTATES
+    three disjoint buffer sets (277 MB each, 830 MB in all against 126 MB of L2), so no launch finds its operands in L2 and
+    the DRAM traffic equals the algorithmic bytes: `frac` is a DRAM-bandwidth fraction, not an L2-assisted one (round 1 reused
+    one set back to back and ncu showed 236 MB of DRAM traffic for 277 MB of algorithmic bytes)."""
     from complex_prompt_diffusion_b200._lib import CPD_DPMPP_2M, CPD_PRED_EPSILON
     res = {}
-    for tag, B in (("saturating", 704), ("named_shape", 4)):
+    for tag, B, nsets in (("saturating", 704, 3), ("named_shape", 4, 1)):
         hw, n_sub = 64 * 64, 3
-        eps = torch.randn(B * 4, 4, 64, 64, device=dev).to(torch.bfloat16)
-        x = torch.randn(B, 4, 64, 64, device=dev)
-        old = torch.randn(B, 4, 64, 64, device=dev)
+        sets = []
+        for _ in range(nsets):
+            eps = torch.randn(B * 4, 4, 64, 64, device=dev).to(torch.bfloat16)
+            sets.append((eps, torch.randn(B, 4, 64, 64, device=dev), torch.randn(B, 4, 64, 64, device=dev)))
         args = dict(n_sub=n_sub, weights=[1.0, 0.6, -0.4], mask_scalars=[1.0] * 3, masks=[None] * 3, guidance=7.5, sampler=CPD_DPMPP_2M,
                     pred_type=CPD_PRED_EPSILON, sigma_hat=2.0, dpm_ratio=0.8, dpm_expm1=-0.2, dpm_c1=1.5, dpm_c2=0.5, dpm_first=0,
-                    write_old=1, old_denoised=old)
-        for _ in range(3):
-            ops.sampler_step(eps, x, **args)
+                    write_old=1)
+        for k in range(3 * nsets):
+            eps, x, old = sets[k % nsets]
+            ops.sampler_step(eps, x, old_denoised=old, **args)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n = 20
+        n = 21
         torch.cuda.synchronize()
         e0.record()
-        for _ in range(n):
-            ops.sampler_step(eps, x, **args)
+        for k in range(n):
+            eps, x, old = sets[k % nsets]
+            ops.sampler_step(eps, x, old_denoised=old, **args)
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / n
         bytes_per = (4 * 2 + 4 + 4 + 4 + 4) * 4 * hw * B  # R*2 (eps bf16) + x r/w + old r/w  (BASELINE.md section 3)
-        res[tag] = {"images": B, "bytes": bytes_per, "us_per_launch": us, "achieved_gbs": bytes_per / us / 1e3,
+        res[tag] = {"images": B, "bytes": bytes_per, "buffer_sets_rotated": nsets, "us_per_launch": us, "achieved_gbs": bytes_per / us / 1e3,
                     "frac_of_hbm_peak": bytes_per / us / 1e3 / pk["hbm"]}
+        del sets
+    res["frac"] = res["saturating"]["frac_of_hbm_peak"]
+    res["dram_frac"] = res["saturating"]["frac_of_hbm_peak"]
+    res["dram_frac_note"] = ("operands rotate over 3 disjoint 277 MB sets, so DRAM bytes = algorithmic bytes; the ncu dram__bytes counters of "
+                             "the same launches are under profiles/ (r02_ncu_sampler_step.txt)")
     res["bound"] = "hbm"
     res["peak"] = pk["hbm"]
     res["unit"] = "GB/s"

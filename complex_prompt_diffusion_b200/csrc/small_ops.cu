@@ -647,3 +647,30 @@ extern "C" cpd_status cpd_pointwise_small(const float* x, int n, int cin, int co
   CPD_CUDA_CHECK(cudaGetLastError());
   return CPD_OK;
 }
+
+// ---- latents -> images tail (cpd/embeddings/prompts.py:472-475): imgs = clamp((x + 1) / 2, 0, 1).permute(0, 2, 3, 1).mul(255).to(uint8)
+__global__ void __launch_bounds__(256) images_to_uint8_kernel(const float* __restrict__ x, int n, int c, int64_t hw, int ld_c,
+                                                              uint8_t* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t total = (int64_t)n * hw;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / hw, p = i - b * hw;
+    for (int ch = 0; ch < c; ++ch) {
+      float v = __fdiv_rn(__fadd_rn(x[(b * ld_c + ch) * hw + p], 1.0f), 2.0f);
+      v = fminf(fmaxf(v, 0.0f), 1.0f);
+      out[i * c + ch] = (uint8_t)__fmul_rn(v, 255.0f);  // float -> uint8 truncates like torch's .to(torch.uint8)
+    }
+  }
+}
+
+extern "C" cpd_status cpd_images_to_uint8(const float* x, int n, int c, int64_t hw, int ld_c, uint8_t* out, void* stream) {
+  CPD_REQUIRE(x && out, "cpd_images_to_uint8: null pointer");
+  CPD_REQUIRE(n >= 0 && c >= 1 && c <= 8 && hw > 0 && ld_c >= c, "cpd_images_to_uint8: n=%d c=%d ld_c=%d", n, c, ld_c);
+  if (n == 0) return CPD_OK;
+  int64_t blocks = ((int64_t)n * hw + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  CPD_CUDA_CHECK(cpd_launch(images_to_uint8_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, x, n, c, hw, ld_c, out));
+  CPD_CUDA_CHECK(cudaGetLastError());
+  return CPD_OK;
+}

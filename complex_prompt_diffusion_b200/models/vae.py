@@ -199,4 +199,13 @@ class VAEDecoder:
         ops.conv_out(gn, W["out.w"], W["out.b"], out4, n=B, h=h, w=w, cin=C, cout=4)
         return out4[:, : cfg["out_ch"]]
 
+    def decode_to_uint8(self, z, unscale=True):
+        """Latents -> display images: decode, then the reference's tail `clamp((x + 1) / 2, 0, 1).permute(0, 2, 3, 1).mul(255)
+        .to(uint8)` (prompts.py:324-334,472-475) as one kernel.  Returns uint8 [B, H, W, out_ch] on the device."""
+        img = self.decode(z, unscale=unscale)  # a view of the 4-channel fp32 buffer
+        B, c, H, Wd = img.shape
+        out = self._buf("image.u8", B * H * Wd * c, torch.uint8).view(B, H, Wd, c)
+        ops.images_to_uint8(img, out, ld_c=4)
+        return out
+
     __call__ = decode

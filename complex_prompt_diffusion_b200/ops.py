@@ -380,3 +380,20 @@ def pointwise_small(x, w, b, out, *, n, cin, cout, hw, scale=1.0):
               "cpd_pointwise_small")
     _count()
     return out
+
+
+def images_to_uint8(x, out, *, ld_c=None):
+    """out[n, h, w, c] = uint8(clamp((x[n, c, h, w] + 1) / 2, 0, 1) * 255) (prompts.py:472-475); x fp32 NCHW whose images are
+    `ld_c` channels apart (the decoder's 4-channel buffer holding 3-channel images)."""
+    if not x.is_cuda or x.dtype != torch.float32:
+        raise RuntimeError("x must be a CUDA fp32 tensor")
+    if out.dtype != torch.uint8 or not out.is_cuda or not out.is_contiguous():
+        raise RuntimeError("out must be a contiguous CUDA uint8 tensor")
+    n, c, h, w = x.shape
+    ld_c = c if ld_c is None else ld_c
+    if x.stride() != (ld_c * h * w, h * w, w, 1):
+        raise RuntimeError("x must be NCHW with an image stride of ld_c * h * w")
+    with _Prof("small", 0.0):
+        check(load().cpd_images_to_uint8(ptr(x), n, c, h * w, ld_c, ptr(out), stream_ptr()), "cpd_images_to_uint8")
+    _count()
+    return out

@@ -300,6 +300,11 @@ cpd_status cpd_softmax_rows(const void* x, int rows, int cols, int64_t ld, float
 cpd_status cpd_pointwise_small(const float* x, int n, int cin, int cout, int64_t hw, const float* w, const float* b, float scale,
                                float* out, void* stream);
 
+/* The latents -> images tail after the decoder (cpd/embeddings/prompts.py:472-475):
+ * out[n][p][ch] = uint8(clamp((x[n][ch][p] + 1) / 2, 0, 1) * 255), i.e. NCHW fp32 in (channel stride of an image = hw, image
+ * stride = ld_c * hw: the decoder's 4-channel output buffer holds 3-channel images), NHWC uint8 out; c <= 8. */
+cpd_status cpd_images_to_uint8(const float* x, int n, int c, int64_t hw, int ld_c, uint8_t* out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Plan-level UNet entry points: ONE call evaluates the whole UNet of cpd/models/unet.py:765-831.
  * The plan owns the packed weights, the text-context K / V^T cache, every workspace buffer and (optionally) a CUDA graph of

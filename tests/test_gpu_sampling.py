@@ -1031,6 +1031,33 @@ def test_vae_decode_vs_oracle(cpd, B, hw):
     assert rel(out2, ref) < 1e-2
 
 
+def test_vae_decode_sd_size_vs_oracle_and_uint8_tail(cpd):
+    """The SD-size first-stage decoder (ch 128, mult 1-2-4-4, 49.5 M parameters) on one 64x64 latent -> 512x512 image against the
+    oracle, and the reference's latents -> images tail (prompts.py:324-334,472-475: z / 0.18215, decode, clamp((x + 1) / 2, 0, 1)
+    * 255 -> uint8) bit-exact against torch on the GPU's own decoded image."""
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    cfg, oracle, gpu = _vae_pair("sd")
+    z = torch.randn(1, 4, 64, 64, generator=torch.Generator().manual_seed(64))
+    ref = oracle(z)
+    out = gpu.decode(z.to(DEV)).clone()
+    torch.cuda.synchronize()
+    r = rel(out, ref)
+    print(f"vae decode SD-size 64x64 -> {tuple(out.shape)}: rel-L2 {r:.3e}")
+    assert out.shape == ref.shape == (1, 3, 512, 512) and torch.isfinite(out).all()
+    assert r < 1e-2
+    u8 = gpu.decode_to_uint8((z * 0.18215).to(DEV), unscale=True).clone()
+    torch.cuda.synchronize()
+    img = gpu.decode((z * 0.18215).to(DEV), unscale=True).clone().cpu()
+    want = torch.clamp((img + 1.0) / 2.0, min=0.0, max=1.0).permute(0, 2, 3, 1).mul(255).to(torch.uint8)
+    assert u8.shape == (1, 512, 512, 3) and u8.dtype == torch.uint8
+    assert torch.equal(u8.cpu(), want), "uint8 image tail differs from the reference expression"
+    # and against the oracle image: at most one grey level apart except at rounding boundaries
+    want_ref = torch.clamp((ref + 1.0) / 2.0, min=0.0, max=1.0).permute(0, 2, 3, 1).mul(255).to(torch.uint8)
+    diff = (u8.cpu().int() - want_ref.int()).abs()
+    print(f"uint8 image vs oracle image: max grey-level difference {int(diff.max())}, differing pixels {float((diff > 0).float().mean()):.3%}")
+    assert int(diff.max()) <= 3
+
+
 def test_vae_decode_golden_reference_image(cpd, golden_dir):
     """The same decoder against the image the shimmed REFERENCE produced (fp32 weights there, bf16-rounded here)."""
     cfg, _, gpu = _vae_pair("tiny")

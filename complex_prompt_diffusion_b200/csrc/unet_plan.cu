@@ -122,6 +122,20 @@ __global__ void __launch_bounds__(256) repeat_rows_kernel(const void* __restrict
   }
 }
 
+// dst[(b * reps + r)][i] = src[b][i]: an activation tensor computed once per IMAGE broadcast to the image's conditioning rows
+// (16-byte vectors; per_image = 16-byte vectors per image)
+__global__ void __launch_bounds__(256) expand_images_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int n_images, int reps,
+                                                            int64_t per_image) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t total = (int64_t)n_images * per_image;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / per_image, k = i - b * per_image;
+    const uint4 v = src[i];
+    for (int r = 0; r < reps; ++r) dst[(b * reps + r) * per_image + k] = v;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host-side structures
 struct DevBuf {
   void* p = nullptr;
@@ -200,6 +214,7 @@ struct cpd_unet_plan {
   Tap tap_mid;
   DevBuf tune_scratch, splitk;
   cudaStream_t cap_stream = nullptr;
+  bool share_prefix = true;  // CPD_UNET_SHARE_PREFIX=0: evaluate every row through the whole network (A/B measurements)
   // profiling (eager launches bracketed by events)
   bool profile = false;
   std::vector<ProfRec> prof;
@@ -758,84 +773,133 @@ cpd_status res_block(FwdCtx& F, const std::string& p, Act x0, Act x1, int cout, 
   return CPD_OK;
 }
 
-cpd_status attn_block(FwdCtx& F, const std::string& p, Act x, int depth, Act* outp) {
+// SpatialTransformer (attention.py:506-537) in four pieces, so that the executor can run the part in front of the first
+// cross-attention once per IMAGE (see forward_impl): pre = GroupNorm + proj_in; self = x + attn1(LN1(x)); rest = cross-attention +
+// GEGLU feed-forward; post = proj_out + x_in.
+struct AttnDims {
+  int ch, hw, nh, dh, dpad, ip;
+  int64_t T;
+};
+cpd_status attn_dims(FwdCtx& F, int ch, AttnDims* d) {
+  d->ch = ch;
+  d->hw = F.h * F.w;
+  d->T = (int64_t)F.R * d->hw;
+  CPD_REQUIRE(d->T < (1ll << 31), "cpd_unet_forward: %lld tokens per evaluation exceed the GEMM row limit", (long long)d->T);
+  heads_of(F.P->cfg, ch, &d->nh, &d->dh);
+  d->dpad = round16(d->dh);
+  d->ip = d->nh * d->dpad;
+  return CPD_OK;
+}
+
+cpd_status attn_pre(FwdCtx& F, const std::string& p, Act x, void** hcur_out) {
   cpd_unet_plan* P = F.P;
-  const int ch = x.c, hw = F.h * F.w;
-  const int64_t T = (int64_t)F.R * hw;
-  CPD_REQUIRE(T < (1ll << 31), "cpd_unet_forward: %lld tokens per evaluation exceed the GEMM row limit", (long long)T);
-  int nh, dh;
-  heads_of(P->cfg, ch, &nh, &dh);
-  const int dpad = round16(dh), ip = nh * dpad;
-  void *gn, *hcur, *ln, *qk, *vt, *o, *q2, *ff, *out;
-  PLAN_CHECK(ws_get(P, "gn", T * ch, 2, &gn));
-  PLAN_CHECK(groupnorm(P, F.st, x.p, nullptr, ch, 0, F.R, hw, p + "norm.g", p + "norm.b", 1e-6f, 0, F.stats, gn));
-  PLAN_CHECK(ws_get(P, "tr.h", T * ch, 2, &hcur));
+  AttnDims D;
+  PLAN_CHECK(attn_dims(F, x.c, &D));
+  void *gn, *hcur;
+  PLAN_CHECK(ws_get(P, "gn", D.T * D.ch, 2, &gn));
+  PLAN_CHECK(groupnorm(P, F.st, x.p, nullptr, D.ch, 0, F.R, D.hw, p + "norm.g", p + "norm.b", 1e-6f, 0, F.stats, gn));
+  PLAN_CHECK(ws_get(P, "tr.h", D.T * D.ch, 2, &hcur));
+  GemmOpt g;
+  g.bias = (const float*)W(P, p + "proj_in.b");
+  PLAN_CHECK(gemm(P, F.st, gn, W(P, p + "proj_in.w"), hcur, 1, 1, (int)D.T, D.ch, D.ch, g));
+  *hcur_out = hcur;
+  return CPD_OK;
+}
+
+// x = attn1(LN1(x)) + x (attention.py:485-487)
+cpd_status tblock_self(FwdCtx& F, const std::string& b, void* hcur, int ch) {
+  cpd_unet_plan* P = F.P;
+  AttnDims D;
+  PLAN_CHECK(attn_dims(F, ch, &D));
+  const int64_t T = D.T;
+  const int ip = D.ip;
+  void *ln, *qk, *vt, *o;
+  PLAN_CHECK(ws_get(P, "tr.ln", T * ch, 2, &ln));
+  PLAN_CHECK(layernorm(P, F.st, hcur, (int)T, ch, b + "norm1.g", b + "norm1.b", ln));
+  PLAN_CHECK(ws_get(P, "tr.qk", T * 2 * ip, 2, &qk));
+  PLAN_CHECK(gemm(P, F.st, ln, W(P, b + "attn1.qk.w"), qk, 1, 1, (int)T, ch, 2 * ip));
+  PLAN_CHECK(ws_get(P, "tr.vt", (int64_t)ip * T, 2, &vt));
+  PLAN_CHECK(gemm(P, F.st, W(P, b + "attn1.v.w"), ln, vt, 1, 1, ip, ch, (int)T));  // V^T = Wv LN(x)^T
+  PLAN_CHECK(ws_get(P, "tr.o", T * ip, 2, &o));
+  PLAN_CHECK(attention(P, F.st, qk, 2 * ip, (const uint16_t*)qk + ip, 2 * ip, vt, (int)T, o, ip, F.R, D.nh, D.hw, D.hw, D.hw, D.dpad, D.dh, 0));
+  GemmOpt g;
+  g.bias = (const float*)W(P, b + "attn1.out.b");
+  g.residual = hcur;
+  g.ld_res = ch;
+  return gemm(P, F.st, o, W(P, b + "attn1.out.w"), hcur, 1, 1, (int)T, ip, ch, g);
+}
+
+// x = attn2(LN2(x), context) + x (K / V^T cached per prompt); x = ff(LN3(x)) + x (attention.py:488-490, 92-118)
+cpd_status tblock_rest(FwdCtx& F, const std::string& b, void* hcur, int ch) {
+  cpd_unet_plan* P = F.P;
+  AttnDims D;
+  PLAN_CHECK(attn_dims(F, ch, &D));
+  const int64_t T = D.T;
+  const int ip = D.ip;
+  CPD_REQUIRE(P->have_ctx, "cpd_unet_forward: no text context cached (call cpd_cache_context_kv first)");
+  void *ln, *o, *kc, *vtc, *q2, *ff;
+  PLAN_CHECK(ws_get(P, "tr.ln", T * ch, 2, &ln));
+  PLAN_CHECK(ws_get(P, "tr.o", T * ip, 2, &o));
+  PLAN_CHECK(ws_get(P, b + "kc", (int64_t)P->rc * P->nk_pad * ip, 2, &kc));
+  PLAN_CHECK(ws_get(P, b + "vt", (int64_t)ip * P->rc * P->nk_pad, 2, &vtc));
+  PLAN_CHECK(layernorm(P, F.st, hcur, (int)T, ch, b + "norm2.g", b + "norm2.b", ln));
+  PLAN_CHECK(ws_get(P, "tr.q2", T * ip, 2, &q2));
+  PLAN_CHECK(gemm(P, F.st, ln, W(P, b + "attn2.q.w"), q2, 1, 1, (int)T, ch, ip));
+  PLAN_CHECK(attention(P, F.st, q2, ip, kc, ip, vtc, P->rc * P->nk_pad, o, ip, F.R, D.nh, D.hw, P->ntok, P->nk_pad, D.dpad, D.dh, P->rc));
   {
     GemmOpt g;
-    g.bias = (const float*)W(P, p + "proj_in.b");
-    PLAN_CHECK(gemm(P, F.st, gn, W(P, p + "proj_in.w"), hcur, 1, 1, (int)T, ch, ch, g));
+    g.bias = (const float*)W(P, b + "attn2.out.b");
+    g.residual = hcur;
+    g.ld_res = ch;
+    PLAN_CHECK(gemm(P, F.st, o, W(P, b + "attn2.out.w"), hcur, 1, 1, (int)T, ip, ch, g));
   }
-  PLAN_CHECK(ws_get(P, "tr.ln", T * ch, 2, &ln));
+  PLAN_CHECK(layernorm(P, F.st, hcur, (int)T, ch, b + "norm3.g", b + "norm3.b", ln));
+  PLAN_CHECK(ws_get(P, "tr.ff", T * 4 * ch, 2, &ff));
+  {
+    GemmOpt g;
+    g.bias = (const float*)W(P, b + "ff1.b");
+    g.epilogue = CPD_EPI_GEGLU;
+    PLAN_CHECK(gemm(P, F.st, ln, W(P, b + "ff1.w"), ff, 1, 1, (int)T, ch, 8 * ch, g));
+  }
+  GemmOpt g;
+  g.bias = (const float*)W(P, b + "ff2.b");
+  g.residual = hcur;
+  g.ld_res = ch;
+  return gemm(P, F.st, ff, W(P, b + "ff2.w"), hcur, 1, 1, (int)T, 4 * ch, ch, g);
+}
+
+cpd_status attn_post(FwdCtx& F, const std::string& p, Act x, void* hcur, Act* outp) {
+  cpd_unet_plan* P = F.P;
+  const int64_t T = (int64_t)F.R * F.h * F.w;
+  void* out;
+  PLAN_CHECK(ws_get(P, p + "out", T * x.c, 2, &out));
+  GemmOpt g;
+  g.bias = (const float*)W(P, p + "proj_out.b");
+  g.residual = x.p;  // x + x_in (attention.py:537)
+  g.ld_res = x.c;
+  PLAN_CHECK(gemm(P, F.st, hcur, W(P, p + "proj_out.w"), out, 1, 1, (int)T, x.c, x.c, g));
+  outp->p = out;
+  outp->c = x.c;
+  return CPD_OK;
+}
+
+cpd_status attn_block(FwdCtx& F, const std::string& p, Act x, int depth, Act* outp) {
+  void* hcur;
+  PLAN_CHECK(attn_pre(F, p, x, &hcur));
   for (int d = 0; d < depth; ++d) {
     const std::string b = p + "transformer_blocks." + std::to_string(d) + ".";
-    // --- self-attention: x = attn1(LN1(x)) + x (attention.py:485-487)
-    PLAN_CHECK(layernorm(P, F.st, hcur, (int)T, ch, b + "norm1.g", b + "norm1.b", ln));
-    PLAN_CHECK(ws_get(P, "tr.qk", T * 2 * ip, 2, &qk));
-    PLAN_CHECK(gemm(P, F.st, ln, W(P, b + "attn1.qk.w"), qk, 1, 1, (int)T, ch, 2 * ip));
-    PLAN_CHECK(ws_get(P, "tr.vt", (int64_t)ip * T, 2, &vt));
-    PLAN_CHECK(gemm(P, F.st, W(P, b + "attn1.v.w"), ln, vt, 1, 1, ip, ch, (int)T));  // V^T = Wv LN(x)^T
-    PLAN_CHECK(ws_get(P, "tr.o", T * ip, 2, &o));
-    PLAN_CHECK(attention(P, F.st, qk, 2 * ip, (const uint16_t*)qk + ip, 2 * ip, vt, (int)T, o, ip, F.R, nh, hw, hw, hw, dpad, dh, 0));
-    {
-      GemmOpt g;
-      g.bias = (const float*)W(P, b + "attn1.out.b");
-      g.residual = hcur;
-      g.ld_res = ch;
-      PLAN_CHECK(gemm(P, F.st, o, W(P, b + "attn1.out.w"), hcur, 1, 1, (int)T, ip, ch, g));
-    }
-    // --- cross-attention: x = attn2(LN2(x), context) + x; K / V^T cached per prompt
-    CPD_REQUIRE(P->have_ctx, "cpd_unet_forward: no text context cached (call cpd_cache_context_kv first)");
-    void *kc, *vtc;
-    PLAN_CHECK(ws_get(P, b + "kc", (int64_t)P->rc * P->nk_pad * ip, 2, &kc));
-    PLAN_CHECK(ws_get(P, b + "vt", (int64_t)ip * P->rc * P->nk_pad, 2, &vtc));
-    PLAN_CHECK(layernorm(P, F.st, hcur, (int)T, ch, b + "norm2.g", b + "norm2.b", ln));
-    PLAN_CHECK(ws_get(P, "tr.q2", T * ip, 2, &q2));
-    PLAN_CHECK(gemm(P, F.st, ln, W(P, b + "attn2.q.w"), q2, 1, 1, (int)T, ch, ip));
-    PLAN_CHECK(attention(P, F.st, q2, ip, kc, ip, vtc, P->rc * P->nk_pad, o, ip, F.R, nh, hw, P->ntok, P->nk_pad, dpad, dh, P->rc));
-    {
-      GemmOpt g;
-      g.bias = (const float*)W(P, b + "attn2.out.b");
-      g.residual = hcur;
-      g.ld_res = ch;
-      PLAN_CHECK(gemm(P, F.st, o, W(P, b + "attn2.out.w"), hcur, 1, 1, (int)T, ip, ch, g));
-    }
-    // --- GEGLU feed-forward: x = ff(LN3(x)) + x (attention.py:92-118)
-    PLAN_CHECK(layernorm(P, F.st, hcur, (int)T, ch, b + "norm3.g", b + "norm3.b", ln));
-    PLAN_CHECK(ws_get(P, "tr.ff", T * 4 * ch, 2, &ff));
-    {
-      GemmOpt g;
-      g.bias = (const float*)W(P, b + "ff1.b");
-      g.epilogue = CPD_EPI_GEGLU;
-      PLAN_CHECK(gemm(P, F.st, ln, W(P, b + "ff1.w"), ff, 1, 1, (int)T, ch, 8 * ch, g));
-    }
-    {
-      GemmOpt g;
-      g.bias = (const float*)W(P, b + "ff2.b");
-      g.residual = hcur;
-      g.ld_res = ch;
-      PLAN_CHECK(gemm(P, F.st, ff, W(P, b + "ff2.w"), hcur, 1, 1, (int)T, 4 * ch, ch, g));
-    }
+    PLAN_CHECK(tblock_self(F, b, hcur, x.c));
+    PLAN_CHECK(tblock_rest(F, b, hcur, x.c));
   }
-  PLAN_CHECK(ws_get(P, p + "out", T * ch, 2, &out));
-  {
-    GemmOpt g;
-    g.bias = (const float*)W(P, p + "proj_out.b");
-    g.residual = x.p;  // x + x_in (attention.py:537)
-    g.ld_res = ch;
-    PLAN_CHECK(gemm(P, F.st, hcur, W(P, p + "proj_out.w"), out, 1, 1, (int)T, ch, ch, g));
-  }
-  outp->p = out;
-  outp->c = ch;
+  return attn_post(F, p, x, hcur, outp);
+}
+
+cpd_status expand_images(cpd_unet_plan* P, cudaStream_t st, const void* src, void* dst, int n_images, int reps, int64_t elems_per_image) {
+  OpScope op(P, st, "expand", "", 0.0, 1);
+  const int64_t per_image = elems_per_image * 2 / 16;
+  int64_t blocks = (n_images * per_image + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  CPD_CUDA_CHECK(cpd_launch(expand_images_kernel, dim3((unsigned)blocks), dim3(256), 0, st, (const uint4*)src, (uint4*)dst, n_images, reps, per_image));
   return CPD_OK;
 }
 
@@ -971,7 +1035,52 @@ cpd_status forward_impl(cpd_unet_plan* P, const cpd_unet_io* io, void* eps_out, 
   Act hcur{h0, mc};
   hs.push_back({hcur, h, w});
   P->tap_in[0] = Tap{h0, mc, h, w};
-  for (size_t i = 1; i < P->inputs.size(); ++i) {
+  size_t first_block = 1;
+  // The rows of an image share x * c_in and t (denoiser.py:383-393) and differ only in their text context, so every activation
+  // in front of the FIRST cross-attention - the input conv, the ResBlock of input block 1 and, inside its SpatialTransformer,
+  // GroupNorm, proj_in, LN1 and the whole self-attention (at 64 x 64 the most expensive attention of the network) - is
+  // identical for the (1 + N) rows of an image.  It is evaluated ONCE per image and broadcast to the rows right before the
+  // cross-attention; the result is bit-identical to evaluating every row.  (Not with per-row timesteps, vector conditioning or
+  // injected tensors, where the rows do differ.)
+  const bool share = rpi > 1 && shared_t && !P->adm && !io->inject_skips && !io->inject_feats && P->inputs.size() > 1 &&
+                     P->inputs[1].layers.size() == 2 && P->inputs[1].layers[0].kind == L_RES && P->inputs[1].layers[1].kind == L_ATTN &&
+                     P->share_prefix;
+  if (share) {
+    const Block& blk = P->inputs[1];
+    const std::string pr = blk.prefix + "0.", pa = blk.prefix + "1.";
+    const int cout = blk.layers[0].b, depth = blk.layers[1].b;
+    const int64_t hw = (int64_t)h * w;
+    void* h0b;
+    PLAN_CHECK(ws_get(P, "input_blocks.0.0.out", (int64_t)B * hw * mc, 2, &h0b));
+    {
+      OpScope op(P, st, "conv_in", "", 0.0, 1);
+      PLAN_CHECK(cpd_conv_in(io->x, B, c.in_channels, h, w, W(P, "input_blocks.0.0.w"), (const float*)W(P, "input_blocks.0.0.b"), mc, 1.0f,
+                             io->c_in, 1, c.act_fp16, h0b, st));
+    }
+    FwdCtx Fb{P, st, B, h, w, emb_all, 0, (double*)stats};
+    Act xres_b, xres;
+    PLAN_CHECK(res_block(Fb, pr, Act{h0b, mc}, Act(), cout, &xres_b));
+    void *hb, *hr, *xr;
+    PLAN_CHECK(attn_pre(Fb, pa, xres_b, &hb));
+    const std::string b0 = pa + "transformer_blocks.0.";
+    PLAN_CHECK(tblock_self(Fb, b0, hb, cout));
+    PLAN_CHECK(ws_get(P, pr + "out", (int64_t)R * hw * cout, 2, &xr));
+    PLAN_CHECK(expand_images(P, st, xres_b.p, xr, B, rpi, hw * cout));
+    PLAN_CHECK(ws_get(P, "tr.h", (int64_t)R * hw * cout, 2, &hr));
+    PLAN_CHECK(expand_images(P, st, hb, hr, B, rpi, hw * cout));
+    xres = Act{xr, cout};
+    PLAN_CHECK(tblock_rest(F, b0, hr, cout));
+    for (int d = 1; d < depth; ++d) {
+      const std::string bd = pa + "transformer_blocks." + std::to_string(d) + ".";
+      PLAN_CHECK(tblock_self(F, bd, hr, cout));
+      PLAN_CHECK(tblock_rest(F, bd, hr, cout));
+    }
+    PLAN_CHECK(attn_post(F, pa, xres, hr, &hcur));
+    hs.push_back({hcur, F.h, F.w});
+    P->tap_in[1] = Tap{hcur.p, hcur.c, F.h, F.w};
+    first_block = 2;
+  }
+  for (size_t i = first_block; i < P->inputs.size(); ++i) {
     PLAN_CHECK(run_block(F, P->inputs[i], hcur, Act(), &hcur));
     hs.push_back({hcur, F.h, F.w});
     P->tap_in[i] = Tap{hcur.p, hcur.c, F.h, F.w};
@@ -1033,6 +1142,10 @@ extern "C" cpd_status cpd_unet_plan_create(const cpd_unet_config* cfg, cpd_unet_
   P->mc = cfg->model_channels;
   P->ted = 4 * cfg->model_channels;
   P->adm = cfg->adm_in_channels;
+  {
+    const char* e = getenv("CPD_UNET_SHARE_PREFIX");
+    P->share_prefix = !(e && e[0] == '0');
+  }
   enumerate_blocks(P);
   cpd_status st = build_specs(P);
   if (st == CPD_OK) st = alloc_dev(&P->splitk, 32ll * 1024 * 1024, 4, false);  // fp32 partial tiles of split-K launches

@@ -35,7 +35,7 @@ constexpr int NUM_SM_PAIRS = 74;
 
 constexpr int CHUNK_COLS = 32;                     // output columns per staging chunk (64-byte rows, SWIZZLE_64B)
 constexpr int CHUNK_BYTES = BM * CHUNK_COLS * 2;   // 8 KB
-constexpr int STAGING_BUFS = 3;                    // per epilogue group
+constexpr int STAGING_BUFS = 4;                    // per epilogue group (3 left the residual prefetch one chunk short: ~2000-cycle waits, profiles/r02_gemm_timeline.txt)
 constexpr int STAGING_BYTES = EPI_GROUPS * STAGING_BUFS * CHUNK_BYTES;
 constexpr int BIAS_FLOATS = 512;                   // widest tile: 2 sub-tiles x 256 columns
 constexpr int BIAS_BYTES = EPI_GROUPS * 2 * BIAS_FLOATS * 4;  // per group, double-buffered by tile parity
@@ -104,7 +104,9 @@ struct Gemm2Args {
 // MC = 1: cluster = one CTA pair.  MC = 2: cluster = two CTA pairs working on the same 256 rows and adjacent column
 // tiles; each CTA loads only HALF of its 128-row A tile and TMA-multicasts it to the same-rank CTA of the other pair,
 // halving the L2 -> SM traffic of the A operand (the main loop is L2-bandwidth-bound).
-template <int MC>
+// OF16: the element type of D / the residual (fp16 or bf16) as a compile-time constant - with a runtime flag every F2FP of
+// the epilogue was emitted twice under complementary predicates.
+template <int MC, bool OF16>
 __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
     gemm2_kernel(const __grid_constant__ Gemm2Args args) {
   extern __shared__ uint8_t smem_raw[];
@@ -375,7 +377,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
     // 32-column chunks.  Per chunk: TMEM load -> epilogue math -> wait until the staging buffer is free (or, with a
     // residual, until its tile has landed there) -> swizzled st.shared -> arrive on chunk_ready.  The store warp (warp 3)
     // issues the TMA store, recycles the buffers and prefetches the residual tiles.
-    const bool of16 = g.out_fp16 != 0;
+    constexpr bool of16 = OF16;
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
     const int grp = (warp - FIRST_EPI_WARP) >> 2;   // epilogue group
     const int r = q * 32 + lane;                    // row within this CTA's 128-row tile
@@ -418,7 +420,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
             if (col_first + idx + 1 < g.n_out) v.y = __ldg(args.bias + col_first + idx + 1);
             if (col_first + idx + 2 < g.n_out) v.z = __ldg(args.bias + col_first + idx + 2);
           }
-          *reinterpret_cast<float4*>(my_bias + idx) = v;
+          sts128f(smem_u32(my_bias + idx), v);
         }
         if (rv && (lane < ((bias_w + 31) >> 5)) && col_first + lane * 32 < g.n_out)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(rv + col_first + lane * 32));
@@ -476,8 +478,8 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
           for (int e = 0; e < 32; e += 4) {
             float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bg = bv;
             if (bias_v) {
-              bv = *reinterpret_cast<const float4*>(bias_v + e);
-              bg = *reinterpret_cast<const float4*>(bias_v + (bn >> 1) + e);
+              bv = lds128f(smem_u32(bias_v + e));
+              bg = lds128f(smem_u32(bias_v + (bn >> 1) + e));
             }
             const uint32_t a01 = pack_act2(__uint_as_float(va[e]) + bv.x, __uint_as_float(va[e + 1]) + bv.y, of16);
             const uint32_t a23 = pack_act2(__uint_as_float(va[e + 2]) + bv.z, __uint_as_float(va[e + 3]) + bv.w, of16);
@@ -497,7 +499,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
             if (args.bias) {
 #pragma unroll
               for (int e = 0; e < 32; e += 4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(my_bias + ch * CHUNK_COLS + e);
+                const float4 b4 = lds128f(smem_u32(my_bias + ch * CHUNK_COLS + e));
                 f[e] += b4.x; f[e + 1] += b4.y; f[e + 2] += b4.z; f[e + 3] += b4.w;
               }
             }
@@ -512,7 +514,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
               if (col0 + e < g.n_store) {
-                if (args.bias) f[e] += my_bias[ch * CHUNK_COLS + e];
+                if (args.bias) f[e] += lds32f(smem_u32(my_bias + ch * CHUNK_COLS + e));
                 if (rv) f[e] += __ldg(rv + col0 + e);
               }
             }
@@ -526,7 +528,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
           mbar_wait(&my_res_bar[buf], (uint32_t)((kc / STAGING_BUFS) & 1), 5);
 #pragma unroll
           for (int c16 = 0; c16 < 4; ++c16) {
-            const uint4 rr = *reinterpret_cast<const uint4*>(my_row + ((c16 ^ sw) << 4));
+            const uint4 rr = lds128(smem_u32(my_row) + ((c16 ^ sw) << 4));
             const float2 r0 = unpack_act2(rr.x, of16), r1 = unpack_act2(rr.y, of16), r2 = unpack_act2(rr.z, of16),
                          r3 = unpack_act2(rr.w, of16);
             f[c16 * 8 + 0] += r0.x; f[c16 * 8 + 1] += r0.y; f[c16 * 8 + 2] += r1.x; f[c16 * 8 + 3] += r1.y;
@@ -544,8 +546,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
         }
 #pragma unroll
         for (int c16 = 0; c16 < 4; ++c16)
-          *reinterpret_cast<uint4*>(my_row + ((c16 ^ sw) << 4)) =
-              make_uint4(packed[c16 * 4], packed[c16 * 4 + 1], packed[c16 * 4 + 2], packed[c16 * 4 + 3]);
+          sts128(smem_u32(my_row) + ((c16 ^ sw) << 4), make_uint4(packed[c16 * 4], packed[c16 * 4 + 1], packed[c16 * 4 + 2], packed[c16 * 4 + 3]));
         EPI_STAMP(4);
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
         EPI_STAMP(5);
@@ -753,13 +754,13 @@ TileChoice pick_tiles(int m_tiles2, int n_out, int num_k, bool geglu, int geglu_
   return best;
 }
 
-template <int MC>
+template <int MC, bool OF16>
 cpd_status launch2(const Gemm2Args& args, int smem_bytes, cudaStream_t stream) {
-  CPD_SMEM_OPTIN(gemm2_kernel<MC>, 227 * 1024);
+  CPD_SMEM_OPTIN((gemm2_kernel<MC, OF16>), 227 * 1024);
   const long steps = (long)args.m_tiles2 * (args.n_tiles / MC) * args.splits;
   const int max_clusters = MC == 2 ? 33 : NUM_SM_PAIRS;
   const int clusters = (int)(steps < max_clusters ? steps : max_clusters);
-  CPD_CUDA_CHECK(cpd_launch(gemm2_kernel<MC>, dim3(2 * MC * clusters), dim3(NUM_THREADS2), smem_bytes, stream, args));
+  CPD_CUDA_CHECK(cpd_launch(gemm2_kernel<MC, OF16>, dim3(2 * MC * clusters), dim3(NUM_THREADS2), smem_bytes, stream, args));
   return CPD_OK;
 }
 
@@ -809,16 +810,23 @@ cpd_status cpd_gemm_conv_2cta(const cpd_gemm_params* p, void* stream) {
     force_nsub = 1;
     force_bn = variant;
   }
-  static int mc_env = -1;
-  if (mc_env < 0) {
-    const char* e = getenv("CPD_GEMM_MC");
-    mc_env = (e && e[0] == '1') ? 1 : 0;  // opt-in: measured equal to the pair cluster
+  // Two round-1 experiments that measured no gain stay behind a build flag (make EXPERIMENTAL=1): the 4-CTA cluster with
+  // TMA-multicast A (CPD_GEMM_MC=1 / variant 1000 + BN: equal to the CTA pair) and a second TMA producer warp for the weights
+  // (CPD_GEMM_SPLIT_PROD=1: 361.9 vs 361.5 ms per generation).
+  int mc_env = 0, split_prod_env = 0;
+#ifdef CPD_EXPERIMENTAL
+  {
+    static int mc_e = -1, sp_e = -1;
+    if (mc_e < 0) {
+      const char* e = getenv("CPD_GEMM_MC");
+      mc_e = (e && e[0] == '1') ? 1 : 0;
+      e = getenv("CPD_GEMM_SPLIT_PROD");
+      sp_e = (e && e[0] == '1') ? 1 : 0;
+    }
+    mc_env = mc_e;
+    split_prod_env = sp_e;
   }
-  static int split_prod_env = -1;
-  if (split_prod_env < 0) {
-    const char* e = getenv("CPD_GEMM_SPLIT_PROD");
-    split_prod_env = (e && e[0] == '1') ? 1 : 0;
-  }
+#endif
   args.split_prod = split_prod_env;
   args.half_x = args.half_y = args.half_n = 0;
   args.map_a0h = args.map_a0;
@@ -899,8 +907,13 @@ cpd_status cpd_gemm_conv_2cta(const cpd_gemm_params* p, void* stream) {
   }
 
   const int smem_bytes = stages * args.stage_bytes + STAGING_BYTES + BIAS_BYTES + 512 + 1024;
-  if (mc == 2) return launch2<2>(args, smem_bytes, (cudaStream_t)stream);
-  const cpd_status st = launch2<1>(args, smem_bytes, (cudaStream_t)stream);
+  const bool of16 = p->out_fp16 != 0;
+#ifdef CPD_EXPERIMENTAL
+  if (mc == 2) return of16 ? launch2<2, true>(args, smem_bytes, (cudaStream_t)stream) : launch2<2, false>(args, smem_bytes, (cudaStream_t)stream);
+#else
+  CPD_REQUIRE(mc == 1, "cpd_gemm_conv: the 4-CTA multicast cluster (variant 1000 + BN) is compiled only with -DCPD_EXPERIMENTAL");
+#endif
+  const cpd_status st = of16 ? launch2<1, true>(args, smem_bytes, (cudaStream_t)stream) : launch2<1, false>(args, smem_bytes, (cudaStream_t)stream);
   if (st != CPD_OK || splits == 1) return st;
   const int64_t vecs = out_rows * (g.n_store / 8);
   int blocks = (int)((vecs + 255) / 256);

@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""Phase timeline of one gemm2_kernel launch (needs a TIMELINE=1 build: make -C complex_prompt_diffusion_b200/csrc clean all TIMELINE=1)."""
+"""Phase timeline of one gemm2_kernel launch.  Needs the TIMELINE=1 build that lives beside the product library:
+    make -C complex_prompt_diffusion_b200/csrc TIMELINE=1 BUILD=build_tl OUT=../libcpd_b200_tl.so
+    CPD_B200_LIB=complex_prompt_diffusion_b200/libcpd_b200_tl.so python tools/gemm_timeline.py"""
 import ctypes as C
 import os
 import sys
@@ -13,21 +15,35 @@ NAMES = ["entry", "cluster sync 1", "setup done (alloc, barriers, sync 2)", "fir
 
 def main():
     from complex_prompt_diffusion_b200 import ops
-    ops.AUTOTUNE = False
     lib = ops.load()
+    for nm in ("cpd_debug_gemm_timeline", "cpd_debug_gemm_mma", "cpd_debug_gemm_epilogue"):
+        getattr(lib, nm).restype = C.c_int
     from complex_prompt_diffusion_b200._lib import CPD_EPI_GEGLU
-    for (M, N, K, v) in [(256, 160, 64, 160), (256, 160, 640, 160), (16384, 640, 640, 160), (65536, 2560, 320, -1), (16384, 5120, 640, -1)]:
+    # (M, N, K, variant (< 0: GEGLU), residual)
+    for (M, N, K, v, res) in [(256, 160, 64, 160, False), (65536, 320, 320, 2160, True), (65536, 320, 320, 160, True), (65536, 768, 320, 2128, False),
+                              (16384, 640, 640, 160, True), (65536, 2560, 320, -1, False), (65536, 320, 1280, 2160, True)]:
         a = torch.randn(M, K, device="cuda").half()
         w = (torch.randn(N, K, device="cuda") / K ** 0.5).half()
         geglu = v < 0
         o = torch.empty(M, N // 2 if geglu else N, device="cuda", dtype=torch.float16)
+        r = torch.randn(M, N, device="cuda").half() if res else None
         bias = torch.randn(N, device="cuda")
         for _ in range(5):
             if geglu:
                 ops.gemm_conv(a, w, o, n_img=1, h=1, w=M, c0=K, n_out=N, bias=bias, epilogue=CPD_EPI_GEGLU, geglu_block=256)
             else:
-                ops.gemm_conv(a, w, o, n_img=1, h=1, w=M, c0=K, n_out=N, bias=bias, variant=v)
+                ops.gemm_conv(a, w, o, n_img=1, h=1, w=M, c0=K, n_out=N, bias=bias, variant=v, residual=r, ld_res=N if res else 0)
         torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            if geglu:
+                ops.gemm_conv(a, w, o, n_img=1, h=1, w=M, c0=K, n_out=N, bias=bias, epilogue=CPD_EPI_GEGLU, geglu_block=256)
+            else:
+                ops.gemm_conv(a, w, o, n_img=1, h=1, w=M, c0=K, n_out=N, bias=bias, variant=v, residual=r, ld_res=N if res else 0)
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"== M={M} N={N} K={K} variant={v} residual={res}: {e0.elapsed_time(e1) * 100:.1f} us per launch")
         ts = (C.c_ulonglong * 16)()
         lib.cpd_debug_gemm_timeline(ts)
         print(f"M={M} N={N} K={K}:")
@@ -45,7 +61,7 @@ def main():
         C.memset(C.addressof(mm), 0, C.sizeof(mm))
         ep = (C.c_longlong * 128)()
         lib.cpd_debug_gemm_epilogue(ep)
-        names = ["chunk top", "buffer free", "tmem ld done", "bias added", "st.shared done", "proxy fence", "group barrier", "store issued"]
+        names = ["chunk top", "top2", "tmem ld done", "math done", "st.shared done", "proxy fence", "arrived", "end"]
         for tile in range(2):
             for ch in range(8):
                 row = [ep[(tile * 8 + ch) * 8 + ph] for ph in range(8)]

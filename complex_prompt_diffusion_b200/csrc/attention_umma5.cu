@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(64 + NT * 128, 2) attention5_kernel(const __gr
           const float v1 = (c + 2 * e + 1 < DH) ? __uint_as_float(o[c + 2 * e + 1]) * inv_l : 0.f;
           w[e] = pack_act2(v0, v1, f16);
         }
-        *reinterpret_cast<uint4*>(my_row + ((((uint32_t)(c >> 3)) ^ swz) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        sts128(smem_u32(my_row) + ((((uint32_t)(c >> 3)) ^ swz) << 4), make_uint4(w[0], w[1], w[2], w[3]));
       }
       fence_proxy_async_smem();          // generic-proxy writes -> visible to the TMA engine
       named_bar_sync(1 + t, 128);        // the tile's 128 rows are staged

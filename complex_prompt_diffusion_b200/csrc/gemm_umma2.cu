@@ -24,7 +24,11 @@
 namespace {
 using namespace cpd_gemm;
 
-constexpr int EPI_WARPS = 8;   // 12 (three groups, 128-register cap, two staging buffers each) measured SLOWER: 240 vs 229.5 ms of GEMM time per generation
+// Two epilogue groups.  More were measured twice and are slower: round 1, 12 warps under a 128-register cap: 240 vs 229.5 ms of
+// GEMM time per generation; round 2, 12 warps with setmaxnreg (40 registers for warps 0-3, 152 for the epilogue, 80 bytes of
+// spills): 352.2 vs 329.2 ms per generation, every shape class slower including the main-loop-bound 3x3 convs (1191 vs 1325
+// TFLOP/s) - the extra staging buffers cost a pipeline stage and the extra warps issue slots the producer / MMA warps need.
+constexpr int EPI_WARPS = 8;
 constexpr int EPI_GROUPS = EPI_WARPS / 4;            // one warp per TMEM lane quarter in each group
 constexpr int FIRST_EPI_WARP = 4;
 constexpr int NUM_THREADS2 = 32 * (FIRST_EPI_WARP + EPI_WARPS);
@@ -194,6 +198,8 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
   pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
   if (threadIdx.x == 0) CPD_STAMP(2);
 
+  // warps 0-3: TMA producer, MMA issuer, TMEM allocator, store warp; warps 4-11: epilogue
+  if (warp < FIRST_EPI_WARP) {
   if (warp == 0) {
     // ================= TMA producer (both CTAs) =================
     // One thread; the loop body must stay far below the MMA time of a stage (BN/2 * 4 cycles), so everything that
@@ -371,7 +377,91 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
         if (t == cluster_id && lane == 0) CPD_STAMP(5);
       }
     }
-  } else if (warp >= FIRST_EPI_WARP) {
+  } else if (warp == 3 && lane < EPI_GROUPS && splits == 1) {
+    // ================= store warp: lane g serves epilogue group g =================
+    // The TMA store of a finished chunk (~650 cycles to issue), the wait for older stores to release their staging
+    // buffers and the residual prefetch used to sit in the epilogue leader's path behind a 128-thread barrier, i.e. on
+    // the critical path of every chunk (2200 cycles per 128 x 32 chunk, more than the main loop of any layer with
+    // K <= 1280).  Here the 128 epilogue threads only arrive on chunk_ready and go on; this thread issues the store,
+    // frees the buffer of the previous chunk once it has been read (buf_free, or by loading the next residual tile into
+    // it) and keeps STAGING_BUFS residual tiles in flight.
+    const int grp = lane;
+    const bool geglu = g.epilogue == CPD_EPI_GEGLU;
+    const int bn = args.bn;
+    const int out_w = geglu ? (bn >> 1) : bn * args.nsub;
+    const int nch = out_w / CHUNK_COLS;
+    const int c_lo = grp * (nch / EPI_GROUPS) + min(grp, nch % EPI_GROUPS);  // contiguous, sizes differ by at most one
+    const int c_hi = c_lo + nch / EPI_GROUPS + (grp < nch % EPI_GROUPS ? 1 : 0);
+    const int box_rows = g.tw * g.th * g.nb;
+    uint8_t* my_staging = staging + grp * STAGING_BUFS * CHUNK_BYTES;
+    uint64_t* my_res_bar = res_bar + grp * STAGING_BUFS;
+    uint64_t* my_ready = chunk_ready + grp * STAGING_BUFS;
+    uint64_t* my_free = buf_free + grp * STAGING_BUFS;
+    const bool has_res = args.residual != nullptr;
+    if (c_lo < c_hi) {
+      auto issue_residual = [&](int t, int ch, int buf) {
+        int m2, n_tile;
+        tile_mn(t, m2, n_tile);
+        const int col0 = n_tile * out_w + ch * CHUNK_COLS;
+        mbar_arrive_expect_tx(&my_res_bar[buf], CHUNK_BYTES);
+        for (int j = 0; j < g.nbox; ++j) {
+          const BoxCoord bc = box_coord(g, m2 * 2 + (int)rank, j, 4, 0);
+          tma_load_4d(my_staging + buf * CHUNK_BYTES + j * box_rows * (CHUNK_COLS * 2), &args.map_res, &my_res_bar[buf], col0, bc.x,
+                      bc.y, bc.n);
+        }
+      };
+      int t_r = cluster_id, ch_r = c_lo, kc_r = 0;  // residual prefetch cursor
+      auto advance_r = [&]() {
+        ++kc_r;
+        if (++ch_r == c_hi) {
+          ch_r = c_lo;
+          t_r += num_clusters;
+        }
+      };
+      if (has_res)
+        for (int i = 0; i < STAGING_BUFS && t_r < total_tiles; ++i) {
+          issue_residual(t_r, ch_r, kc_r % STAGING_BUFS);
+          advance_r();
+        }
+      int kc = 0;
+      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+        int m2, n_tile;
+        tile_mn(t, m2, n_tile);
+        const int m_tile = m2 * 2 + (int)rank;
+        const BoxCoord bc0 = box_coord(g, m_tile, 0, 4, 0);  // once per tile: the chunks differ only in their column
+        for (int ch = c_lo; ch < c_hi; ++ch, ++kc) {
+          const int buf = kc % STAGING_BUFS;
+          const uint8_t* sbuf = my_staging + buf * CHUNK_BYTES;
+          const int col0 = n_tile * out_w + ch * CHUNK_COLS;
+          mbar_wait(&my_ready[buf], (uint32_t)((kc / STAGING_BUFS) & 1), 7);
+          if (col0 < g.n_store) {
+            tma_store_4d(&args.map_d, sbuf, col0, bc0.x, bc0.y, bc0.n);
+            for (int j = 1; j < g.nbox; ++j) {
+              const BoxCoord bc = box_coord(g, m_tile, j, 4, 0);
+              tma_store_4d(&args.map_d, sbuf + j * box_rows * (CHUNK_COLS * 2), col0, bc.x, bc.y, bc.n);
+            }
+          }
+          bulk_commit_group();
+          if (kc >= 1) {
+            bulk_wait_group_read<1>();  // every store but the one just issued has been read: chunk kc - 1's buffer is free
+            const int prev = (kc - 1) % STAGING_BUFS;
+            if (has_res) {
+              if (t_r < total_tiles) {
+                issue_residual(t_r, ch_r, prev);  // kc_r == kc + STAGING_BUFS - 1: this IS the buffer that chunk will use
+                advance_r();
+              }
+            } else {
+              mbar_arrive(&my_free[prev]);
+            }
+          }
+        }
+      }
+      // the staging buffers must outlive the TMA engine's READS of them; the global writes themselves are complete (and
+      // visible to the next kernel) at grid completion like any other store
+      bulk_wait_group_read<0>();
+    }
+  }
+  } else {
     // ================= epilogue (warps 4..11 of both CTAs) =================
     // EPI_GROUPS groups of 4 warps (one warp per TMEM lane quarter); group `grp` owns a contiguous share of the tile's
     // 32-column chunks.  Per chunk: TMEM load -> epilogue math -> wait until the staging buffer is free (or, with a
@@ -568,89 +658,6 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
       }
     }
     if (leader && grp == 0) CPD_STAMP(8);
-  } else if (warp == 3 && lane < EPI_GROUPS && splits == 1) {
-    // ================= store warp: lane g serves epilogue group g =================
-    // The TMA store of a finished chunk (~650 cycles to issue), the wait for older stores to release their staging
-    // buffers and the residual prefetch used to sit in the epilogue leader's path behind a 128-thread barrier, i.e. on
-    // the critical path of every chunk (2200 cycles per 128 x 32 chunk, more than the main loop of any layer with
-    // K <= 1280).  Here the 128 epilogue threads only arrive on chunk_ready and go on; this thread issues the store,
-    // frees the buffer of the previous chunk once it has been read (buf_free, or by loading the next residual tile into
-    // it) and keeps STAGING_BUFS residual tiles in flight.
-    const int grp = lane;
-    const bool geglu = g.epilogue == CPD_EPI_GEGLU;
-    const int bn = args.bn;
-    const int out_w = geglu ? (bn >> 1) : bn * args.nsub;
-    const int nch = out_w / CHUNK_COLS;
-    const int c_lo = grp * (nch / EPI_GROUPS) + min(grp, nch % EPI_GROUPS);  // contiguous, sizes differ by at most one
-    const int c_hi = c_lo + nch / EPI_GROUPS + (grp < nch % EPI_GROUPS ? 1 : 0);
-    const int box_rows = g.tw * g.th * g.nb;
-    uint8_t* my_staging = staging + grp * STAGING_BUFS * CHUNK_BYTES;
-    uint64_t* my_res_bar = res_bar + grp * STAGING_BUFS;
-    uint64_t* my_ready = chunk_ready + grp * STAGING_BUFS;
-    uint64_t* my_free = buf_free + grp * STAGING_BUFS;
-    const bool has_res = args.residual != nullptr;
-    if (c_lo < c_hi) {
-      auto issue_residual = [&](int t, int ch, int buf) {
-        int m2, n_tile;
-        tile_mn(t, m2, n_tile);
-        const int col0 = n_tile * out_w + ch * CHUNK_COLS;
-        mbar_arrive_expect_tx(&my_res_bar[buf], CHUNK_BYTES);
-        for (int j = 0; j < g.nbox; ++j) {
-          const BoxCoord bc = box_coord(g, m2 * 2 + (int)rank, j, 4, 0);
-          tma_load_4d(my_staging + buf * CHUNK_BYTES + j * box_rows * (CHUNK_COLS * 2), &args.map_res, &my_res_bar[buf], col0, bc.x,
-                      bc.y, bc.n);
-        }
-      };
-      int t_r = cluster_id, ch_r = c_lo, kc_r = 0;  // residual prefetch cursor
-      auto advance_r = [&]() {
-        ++kc_r;
-        if (++ch_r == c_hi) {
-          ch_r = c_lo;
-          t_r += num_clusters;
-        }
-      };
-      if (has_res)
-        for (int i = 0; i < STAGING_BUFS && t_r < total_tiles; ++i) {
-          issue_residual(t_r, ch_r, kc_r % STAGING_BUFS);
-          advance_r();
-        }
-      int kc = 0;
-      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
-        int m2, n_tile;
-        tile_mn(t, m2, n_tile);
-        const int m_tile = m2 * 2 + (int)rank;
-        const BoxCoord bc0 = box_coord(g, m_tile, 0, 4, 0);  // once per tile: the chunks differ only in their column
-        for (int ch = c_lo; ch < c_hi; ++ch, ++kc) {
-          const int buf = kc % STAGING_BUFS;
-          const uint8_t* sbuf = my_staging + buf * CHUNK_BYTES;
-          const int col0 = n_tile * out_w + ch * CHUNK_COLS;
-          mbar_wait(&my_ready[buf], (uint32_t)((kc / STAGING_BUFS) & 1), 7);
-          if (col0 < g.n_store) {
-            tma_store_4d(&args.map_d, sbuf, col0, bc0.x, bc0.y, bc0.n);
-            for (int j = 1; j < g.nbox; ++j) {
-              const BoxCoord bc = box_coord(g, m_tile, j, 4, 0);
-              tma_store_4d(&args.map_d, sbuf + j * box_rows * (CHUNK_COLS * 2), col0, bc.x, bc.y, bc.n);
-            }
-          }
-          bulk_commit_group();
-          if (kc >= 1) {
-            bulk_wait_group_read<1>();  // every store but the one just issued has been read: chunk kc - 1's buffer is free
-            const int prev = (kc - 1) % STAGING_BUFS;
-            if (has_res) {
-              if (t_r < total_tiles) {
-                issue_residual(t_r, ch_r, prev);  // kc_r == kc + STAGING_BUFS - 1: this IS the buffer that chunk will use
-                advance_r();
-              }
-            } else {
-              mbar_arrive(&my_free[prev]);
-            }
-          }
-        }
-      }
-      // the staging buffers must outlive the TMA engine's READS of them; the global writes themselves are complete (and
-      // visible to the next kernel) at grid completion like any other store
-      bulk_wait_group_read<0>();
-    }
   }
 
   __syncwarp();

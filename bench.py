@@ -524,7 +524,8 @@ def run_b200(args):
                                           "and are reported under bf16_activations)") if args.act_dtype == "fp16" else
                                          ("bf16 model weights and bf16 activations, fp32 accumulation and norm statistics "
                                           "(per-step eps error ~1.3e-2: the noise floor of any bf16 evaluation of this UNet)"),
-                               executor="C++ plan (cpd_unet_forward): one CUDA graph per UNet evaluation (~850 kernels, PDL edges), replayed per sampler step"),
+                               executor="one CUDA graph per SAMPLER STEP: [cpd_step_select -> C++ UNet plan (cpd_unet_forward, ~850 kernels, PDL edges) -> "
+                                        "cpd_sampler_step], per-step scalars read from a device table, replayed 20 times per generation"),
                 "unet_evals_per_s": evals_per_step * world * args.steps / (ms / 1e3),
                 "e2e": {"value": ips_e2e, "unit": "images/s",
                         "h2d_bytes_per_step": int(x_T_h.numel() * 4 + uc_h.numel() * 4 + sum(e.numel() * 4 for v in c_h.values() for (_, e, _, _) in v)),
@@ -567,11 +568,25 @@ def sampler_roofline(ops, dev, pk):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n = 21
         torch.cuda.synchronize()
-        e0.record()
-        for k in range(n):
-            eps, x, old = sets[k % nsets]
-            ops.sampler_step(eps, x, old_denoised=old, **args)
-        e1.record()
+        if tag == "named_shape":
+            # latency of the kernel at the named shape as the sampler runs it: inside a captured graph (the product's step graph),
+            # not through 21 Python -> ctypes launches (which measure the host: ~16 us per call)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                for k in range(n):
+                    eps, x, old = sets[k % nsets]
+                    ops.sampler_step(eps, x, old_denoised=old, **args)
+            graph.replay()
+            torch.cuda.synchronize()
+            e0.record()
+            graph.replay()
+            e1.record()
+        else:
+            e0.record()
+            for k in range(n):
+                eps, x, old = sets[k % nsets]
+                ops.sampler_step(eps, x, old_denoised=old, **args)
+            e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / n
         bytes_per = (4 * 2 + 4 + 4 + 4 + 4) * 4 * hw * B  # R*2 (eps bf16) + x r/w + old r/w  

@@ -37,6 +37,16 @@ class StepParams(C.Structure):
         ("x_base", C.c_void_p), ("x_out", C.c_void_p), ("d_out", C.c_void_p), ("d_prev", C.c_void_p * 3),
         ("lms_coeff", C.c_float * 4), ("lms_order", C.c_int), ("noise_mul", C.c_float),
         ("clip_scaled", C.c_void_p), ("scaled_out", C.c_void_p), ("scaled_in", C.c_void_p),
+        ("dyn", C.c_void_p),
+    ]
+
+
+class StepScalars(C.Structure):  # cpd_step_scalars: one row of the per-schedule device table (64 bytes)
+    _fields_ = [
+        ("c_in", C.c_float), ("t", C.c_float), ("guidance", C.c_float), ("sigma_hat", C.c_float), ("v_c_eps", C.c_float),
+        ("v_c_x_div", C.c_float), ("dt", C.c_float), ("sigma_up", C.c_float), ("dpm_ratio", C.c_float), ("dpm_expm1", C.c_float),
+        ("dpm_c1", C.c_float), ("dpm_c2", C.c_float), ("dpm_first", C.c_int), ("write_old", C.c_int), ("noise_mul", C.c_float),
+        ("reserved", C.c_int),
     ]
 
 
@@ -89,6 +99,7 @@ _SIGS = {
     "cpd_last_error": (C.c_char_p, []),
     "cpd_abi_version": (C.c_int, []),
     "cpd_sampler_step": (C.c_int, [C.POINTER(StepParams), C.c_void_p]),
+    "cpd_step_select": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cpd_add_noise": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int64, C.c_void_p]),
     "cpd_threshold": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]),
     "cpd_threshold_ex": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),

@@ -78,6 +78,15 @@ __global__ void __launch_bounds__(256, VEC == 8 ? 3 : 4) sampler_step_kernel(con
   pdl_launch_dependents();
   pdl_wait();
   const cpd_step_params& p = args.p;
+  // per-step scalars: by value, or the "current" row of a device table (a captured graph replayed once per step)
+  cpd_step_scalars sc;
+  if (p.dyn) {
+    sc = *p.dyn;  // uniform 64-byte load
+  } else {
+    sc.guidance = p.guidance; sc.sigma_hat = p.sigma_hat; sc.v_c_eps = p.v_c_eps; sc.v_c_x_div = p.v_c_x_div; sc.dt = p.dt;
+    sc.sigma_up = p.sigma_up; sc.dpm_ratio = p.dpm_ratio; sc.dpm_expm1 = p.dpm_expm1; sc.dpm_c1 = p.dpm_c1; sc.dpm_c2 = p.dpm_c2;
+    sc.dpm_first = p.dpm_first; sc.write_old = p.write_old; sc.noise_mul = p.noise_mul;
+  }
   const int L = 4 * p.hw;
   const int vec_per_img = L / VEC;
   const int64_t total = (int64_t)p.n_images * vec_per_img;
@@ -94,7 +103,7 @@ __global__ void __launch_bounds__(256, VEC == 8 ? 3 : 4) sampler_step_kernel(con
 #pragma unroll
     for (int j = 0; j < VEC; ++j) aux[j] = 0.f;
     if (p.sampler == CPD_DPMPP_2M) {
-      if (!p.dpm_first) load_f32<VEC>(p.old_denoised + (int64_t)b * L + i, aux);
+      if (!sc.dpm_first) load_f32<VEC>(p.old_denoised + (int64_t)b * L + i, aux);
       else if (FULL && p.noise) load_f32<VEC>(p.noise + (int64_t)b * L + i, aux);  // DPM++ 2S ancestral: noise after the update
     } else if (p.sampler == CPD_EULER_ANCESTRAL) {
       load_f32<VEC>(p.noise + (int64_t)b * L + i, aux);
@@ -145,18 +154,18 @@ __global__ void __launch_bounds__(256, VEC == 8 ? 3 : 4) sampler_step_kernel(con
     }
     float et[VEC], den[VEC], xn[VEC];
     const float clip = (FULL && p.clip_scaled) ? __ldg(p.clip_scaled + b) : 0.f;
-    const float nmul = p.noise_mul;  // used as given: 0 adds no noise (temperature = 0, dpmpp.py:111)
+    const float nmul = sc.noise_mul;  // used as given: 0 adds no noise (temperature = 0, dpmpp.py:111)
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       const float sj = (j & 1) ? __high2float(sum[j >> 1]) : __low2float(sum[j >> 1]);
-      float scaled = h_round(__fmul_rn(sj, p.guidance));
+      float scaled = h_round(__fmul_rn(sj, sc.guidance));
       if (FULL && p.scaled_out) p.scaled_out[(int64_t)b * L + i + j] = scaled;
       if (FULL && p.clip_scaled) scaled = h_round(fminf(fmaxf(scaled, -clip), clip));  // x.float() -> clamp_ -> .half()
       if (FULL && p.scaled_in) scaled = __ldg(p.scaled_in + (int64_t)b * L + i + j);  // thresholded by cpd_threshold_ex
       if (DT == CPD_F16) et[j] = h_round(__fadd_rn(eu.at(j), scaled));
       else et[j] = __fadd_rn(eu.at(j), scaled);
-      if (p.pred_type == CPD_PRED_EPSILON) den[j] = __fsub_rn(x[j], __fmul_rn(p.sigma_hat, et[j]));
-      else den[j] = __fadd_rn(__fmul_rn(et[j], p.v_c_eps), __fdiv_rn(x[j], p.v_c_x_div));
+      if (p.pred_type == CPD_PRED_EPSILON) den[j] = __fsub_rn(x[j], __fmul_rn(sc.sigma_hat, et[j]));
+      else den[j] = __fadd_rn(__fmul_rn(et[j], sc.v_c_eps), __fdiv_rn(x[j], sc.v_c_x_div));
     }
     // xb: the sample the update starts from (the UNet input unless this is the second stage of a two-stage sampler)
     float xb[VEC];
@@ -170,19 +179,19 @@ __global__ void __launch_bounds__(256, VEC == 8 ? 3 : 4) sampler_step_kernel(con
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
         float dd = den[j];
-        if (!p.dpm_first) dd = __fsub_rn(__fmul_rn(p.dpm_c1, den[j]), __fmul_rn(p.dpm_c2, aux[j]));
-        xn[j] = __fsub_rn(__fmul_rn(p.dpm_ratio, xb[j]), __fmul_rn(p.dpm_expm1, dd));
-        if (FULL && p.dpm_first && p.noise) xn[j] = __fadd_rn(xn[j], __fmul_rn(__fmul_rn(aux[j], nmul), p.sigma_up));  // dpmpp.py:111
+        if (!sc.dpm_first) dd = __fsub_rn(__fmul_rn(sc.dpm_c1, den[j]), __fmul_rn(sc.dpm_c2, aux[j]));
+        xn[j] = __fsub_rn(__fmul_rn(sc.dpm_ratio, xb[j]), __fmul_rn(sc.dpm_expm1, dd));
+        if (FULL && sc.dpm_first && p.noise) xn[j] = __fadd_rn(xn[j], __fmul_rn(__fmul_rn(aux[j], nmul), sc.sigma_up));  // dpmpp.py:111
       }
-      if (p.write_old) store_f32<VEC>(p.old_denoised + (int64_t)b * L + i, den);
+      if (sc.write_old) store_f32<VEC>(p.old_denoised + (int64_t)b * L + i, den);
     } else {
       float d[VEC];
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) d[j] = __fdiv_rn(__fsub_rn(x[j], den[j]), p.sigma_hat);  // to_ode
+      for (int j = 0; j < VEC; ++j) d[j] = __fdiv_rn(__fsub_rn(x[j], den[j]), sc.sigma_hat);  // to_ode
       if (FULL && p.d_out) store_f32<VEC>(p.d_out + (int64_t)b * L + i, d);
       if (FULL && p.sampler == CPD_HEUN2) {
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) xn[j] = __fadd_rn(xb[j], __fmul_rn(__fdiv_rn(__fadd_rn(aux[j], d[j]), 2.0f), p.dt));
+        for (int j = 0; j < VEC; ++j) xn[j] = __fadd_rn(xb[j], __fmul_rn(__fdiv_rn(__fadd_rn(aux[j], d[j]), 2.0f), sc.dt));
       } else if (FULL && p.sampler == CPD_LMS) {
         float acc[VEC];  // sum(coeff * d ...) of lms.py:52: 0 + c0 * d_i, then + c1 * d_{i-1}, ... left to right
 #pragma unroll
@@ -198,8 +207,8 @@ __global__ void __launch_bounds__(256, VEC == 8 ? 3 : 4) sampler_step_kernel(con
       } else {
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-          xn[j] = __fadd_rn(xb[j], __fmul_rn(d[j], p.dt));
-          if (p.sampler == CPD_EULER_ANCESTRAL) xn[j] = __fadd_rn(xn[j], __fmul_rn(__fmul_rn(aux[j], nmul), p.sigma_up));
+          xn[j] = __fadd_rn(xb[j], __fmul_rn(d[j], sc.dt));
+          if (p.sampler == CPD_EULER_ANCESTRAL) xn[j] = __fadd_rn(xn[j], __fmul_rn(__fmul_rn(aux[j], nmul), sc.sigma_up));
         }
       }
     }
@@ -237,6 +246,22 @@ extern "C" cpd_status cpd_add_noise(float* x, const float* noise, float noise_mu
   return CPD_OK;
 }
 
+__global__ void step_select_kernel(const cpd_step_scalars* __restrict__ table, int n_steps, int* counter, cpd_step_scalars* current) {
+  pdl_launch_dependents();
+  pdl_wait();
+  if (threadIdx.x == 0) {
+    const int i = *counter;
+    *current = table[i < n_steps ? i : n_steps - 1];
+    *counter = i + 1;
+  }
+}
+
+extern "C" cpd_status cpd_step_select(const cpd_step_scalars* table, int n_steps, int* counter, cpd_step_scalars* current, void* stream) {
+  CPD_REQUIRE(table && counter && current && n_steps > 0, "cpd_step_select: null pointer or empty table");
+  CPD_CUDA_CHECK(cpd_launch(step_select_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, table, n_steps, counter, current));
+  return CPD_OK;
+}
+
 extern "C" cpd_status cpd_sampler_step(const cpd_step_params* p, void* stream) {
   CPD_REQUIRE(p != nullptr, "cpd_sampler_step: null params");
   CPD_REQUIRE(p->eps && p->x, "cpd_sampler_step: eps and x must be non-null");
@@ -254,7 +279,7 @@ extern "C" cpd_status cpd_sampler_step(const cpd_step_params* p, void* stream) {
   CPD_REQUIRE(p->pred_type == CPD_PRED_EPSILON || p->pred_type == CPD_PRED_VELOCITY, "cpd_sampler_step: unknown pred_type %d",
               p->pred_type);
   CPD_REQUIRE(p->sampler != CPD_EULER_ANCESTRAL || p->noise, "cpd_sampler_step: ancestral sampler needs noise");
-  CPD_REQUIRE(p->sampler != CPD_DPMPP_2M || p->old_denoised || (p->dpm_first && !p->write_old),
+  CPD_REQUIRE(p->sampler != CPD_DPMPP_2M || p->old_denoised || (!p->dyn && p->dpm_first && !p->write_old),
               "cpd_sampler_step: DPM++ 2M needs old_denoised");
   if (p->n_images == 0) return CPD_OK;  // empty batch: nothing to do
   StepArgs args;

@@ -63,7 +63,7 @@ def _act(t, name, like=None):
 def sampler_step(eps, x, *, n_sub, weights, mask_scalars, masks, guidance, sampler, pred_type, sigma_hat, v_c_eps=0.0,
                  v_c_x_div=1.0, dt=0.0, sigma_up=0.0, dpm_ratio=0.0, dpm_expm1=0.0, dpm_c1=0.0, dpm_c2=0.0, dpm_first=1,
                  write_old=0, old_denoised=None, noise=None, denoised_out=None, eps_out=None, x_base=None, x_out=None, d_out=None,
-                 d_prev=(), lms_coeff=(), noise_mul=1.0, clip_scaled=None, scaled_out=None, scaled_in=None):
+                 d_prev=(), lms_coeff=(), noise_mul=1.0, clip_scaled=None, scaled_out=None, scaled_in=None, dyn=None):
     """eps: [n_images * (1 + n_sub), 4, h, w] (image-major rows); x: [n_images, 4, h, w] fp32, the UNet input; the updated
     sample goes to x_out (default: x, in place) and starts from x_base (default: x)."""
     _req(x, torch.float32, "x")
@@ -128,6 +128,7 @@ def sampler_step(eps, x, *, n_sub, weights, mask_scalars, masks, guidance, sampl
     p.clip_scaled = clip_scaled.data_ptr() if clip_scaled is not None else None
     p.scaled_out = scaled_out.data_ptr() if scaled_out is not None else None
     p.scaled_in = scaled_in.data_ptr() if scaled_in is not None else None
+    p.dyn = dyn.data_ptr() if dyn is not None else None  # device row of per-step scalars (cpd_step_select) overriding the by-value ones
     with _Prof("sampler_step", 0.0):
         check(load().cpd_sampler_step(C.byref(p), stream_ptr()), "cpd_sampler_step")
     _count()

@@ -33,6 +33,12 @@ class DPMPlusPlus2mDiffusionSampler(KDiffusionSampler):
         model_args = {} if model_args is None else model_args
         callback = kwargs.get("callback", None)
         den, plan = self._begin(x, model_args, kwargs)
+        if self._step_graph_ok(plan, model_args, kwargs):
+            rows = []
+            for i in range(len(sigmas) - 1):
+                ratio, em, c1, c2, first = dpmpp_2m_scalars(sigmas, i, have_history=i > 0)
+                rows.append(dict(dpm_ratio=ratio, dpm_expm1=em, dpm_c1=c1, dpm_c2=c2, dpm_first=first, write_old=1))
+            return self._graph_loop(x, sigmas, plan, CPD_DPMPP_2M, rows, model_args)
         old = torch.empty_like(x)
         den_out = torch.empty_like(x) if callback is not None else None
         for i in range(len(sigmas) - 1):

@@ -29,6 +29,10 @@ class EulerDiffusionSampler(KDiffusionSampler):
         model_args = {} if model_args is None else model_args
         callback = kwargs.get("callback", None)
         den, plan = self._begin(x, model_args, kwargs)
+        if self._step_graph_ok(plan, model_args, kwargs) and not kwargs.get("s_churn", 0.0) and not kwargs.get("rng_compat", True):
+            # gamma = 0 on every step and no RNG draw to reproduce: one captured graph per step (k_diffusion._graph_loop)
+            rows = [dict(dt=float(sigmas[i + 1] - sigmas[i] * 1)) for i in range(len(sigmas) - 1)]
+            return self._graph_loop(x, sigmas, plan, CPD_EULER, rows, model_args)
         den_out = torch.empty_like(x) if callback is not None else None
         for i in range(len(sigmas) - 1):
             model_args["t_idx"] = i
@@ -53,6 +57,13 @@ class EulerAncestralDiffusionSampler(KDiffusionSampler):
         callback = kwargs.get("callback", None)
         noise_sampler = kwargs.get("noise_sampler", None)  # default reproduces torch.randn_like(x) call order
         den, plan = self._begin(x, model_args, kwargs)
+        if self._step_graph_ok(plan, model_args, kwargs):
+            rows = []
+            for i in range(len(sigmas) - 1):
+                sigma_down, sigma_up = get_ancestral_step(sigmas[i], sigmas[i + 1])
+                rows.append(dict(dt=float(sigma_down - sigmas[i]), sigma_up=float(sigma_up)))
+            draw = noise_sampler if noise_sampler is not None else torch.randn_like
+            return self._graph_loop(x, sigmas, plan, CPD_EULER_ANCESTRAL, rows, model_args, noise_fn=lambda t: draw(t).contiguous())
         den_out = torch.empty_like(x) if callback is not None else None
         for i in range(len(sigmas) - 1):
             model_args["t_idx"] = i

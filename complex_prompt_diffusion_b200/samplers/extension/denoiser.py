@@ -266,6 +266,18 @@ class Denoiser(torch.nn.Module):
             raise ValueError("Denoiser: the images of a batch must share one sigma (got a vector with different values)")
         return sig[:1]
 
+    def step_scalars(self, sigma, **kwargs):
+        """The per-step scalars of one Denoiser evaluation exactly as unet_rows / fused_step compute them (fp32 torch expressions
+        on 0-dim tensors like the reference's): c_in (denoiser.py:390), t in the model dtype (:393), the guidance scale after its
+        optional decay (:475-494), sigma_hat and the v-prediction coefficients (:540-542)."""
+        sig = self._one_sigma(sigma)
+        c_in = 1 / (sig ** 2 + 1 ** 2) ** 0.5
+        t = self.scheduler.sigma_to_t(sig).to(self.dtype).float()
+        s = float(sig[0])
+        sig_t = torch.tensor([s], dtype=torch.float32)
+        return dict(c_in=float(c_in), t=float(t), guidance=self.guidance_scale(**kwargs), sigma_hat=s,
+                    v_c_eps=float(-sig_t / (sig_t ** 2 + 1) ** 0.5), v_c_x_div=float(sig_t ** 2 + 1))
+
     def unet_rows(self, x, sigma, plan, inject=None):
         """Run the UNet on the (1 + N) conditioning rows of every image: returns eps rows [B*(1+N), 4, h, w]
         (image-major).  x: [B,4,h,w] fp32; sigma: 0-dim/1-element fp32 CPU tensor (same for all images)."""

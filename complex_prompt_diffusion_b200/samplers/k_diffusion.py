@@ -5,15 +5,20 @@ All per-step scalars are computed once on the host with the same fp32 torch expr
 evaluates on 0-dim tensors, then each step is one UNet evaluation plus one fused CUDA kernel
 (`Denoiser.fused_step`).  B images are B independent trajectories sharing the schedule.
 """
+import ctypes as C
+
 import torch
 
 from .extension.denoiser import Denoiser
+
+STEP_TABLE_ROWS = 1024  # capacity of the per-schedule device table of step scalars (rows of 64 bytes)
 
 
 class KDiffusionSampler:
     def __init__(self, model, name="sample_heun"):
         self.name = name
         self.noise_sync = None  # dist.sample_sharded: replaces a locally drawn noise tensor by the row-sharding group's shared draw
+        self._step_graphs = {}  # one captured CUDA graph per (shape, prompt layout, sampler): select scalars -> UNet -> fused step
         self.denoiser = Denoiser(model["unet"], model.get("vae"), model.get("tokenizer"), model.get("clip_new_model"),
                                  model.get("decode"))
 
@@ -96,6 +101,88 @@ class KDiffusionSampler:
     def _callback(self, callback, x_before, i, sigma, denoised, sigma_hat=None):
         if callback is not None:
             callback({"x": x_before, "i": i, "sigma": sigma, "sigma_hat": sigma if sigma_hat is None else sigma_hat, "eps": denoised})
+
+    # ---- one CUDA graph per sampler step ---------------------------------------------------------------
+    def _step_graph_ok(self, plan, model_args, kwargs):
+        """The whole step - [cpd_step_select -> cpd_unet_forward -> cpd_sampler_step] - replays as ONE captured graph when
+        nothing in it needs the host between the kernels: the library's UNet (not a foreign model behind the adapter), no row
+        sharding, no per-step callback / thresholding / score corrector / injection, no spatial masks."""
+        from ..models.unet import UNetModel
+        den = self.denoiser
+        if not isinstance(den.unet, UNetModel) or not den.unet.use_cuda_graph or den._part is not None:
+            return False
+        if not kwargs.get("step_graph", True) or kwargs.get("callback") is not None or kwargs.get("clip_sample", False):
+            return False
+        if model_args.get("scaled_clip", model_args.get("dynamic_scale_clip", False)) or model_args.get("score_corrector") is not None:
+            return False
+        if den._inject(model_args) is not None or any(m is not None for m in plan.masks):
+            return False
+        return True
+
+    def _graph_loop(self, x, sigmas, plan, sampler, rows, model_args, noise_fn=None):
+        """Run the schedule through one captured graph per step.  `rows[i]` = dict of the step's fused-step scalars (dt, sigma_up,
+        dpm_*, write_old, noise_mul); the Denoiser's own scalars are added here.  All scalars of the schedule go to the device in
+        ONE table at the start; per step the host only replays the graph (plus the noise draw of ancestral samplers)."""
+        from .. import ops
+        from .._lib import StepScalars, check, load, stream_ptr, CPD_PRED_EPSILON, CPD_PRED_VELOCITY
+        den, unet, dev = self.denoiser, self.denoiser.unet, x.device
+        n = len(sigmas) - 1
+        if n > STEP_TABLE_ROWS:
+            raise ValueError(f"more than {STEP_TABLE_ROWS} sampler steps")
+        table = (StepScalars * n)()
+        for i in range(n):
+            model_args["t_idx"] = i
+            sc = dict(den.step_scalars(rows[i].get("sigma", sigmas[i]), **model_args))
+            sc.update({k: v for k, v in rows[i].items() if k != "sigma"})
+            r = table[i]
+            r.noise_mul, r.dpm_first = 1.0, 1
+            for k, v in sc.items():
+                setattr(r, k, v)
+        pred = CPD_PRED_VELOCITY if model_args.get("pred_type", "epsilon") == "velocity" else CPD_PRED_EPSILON
+        R = 1 + plan.n_sub
+        key = (tuple(x.shape), plan.n_sub, tuple(plan.weights), tuple(plan.mask_scalars), int(sampler), pred, unet._ctx_shape, unet._y_rows,
+               noise_fn is not None)
+        st = self._step_graphs.get(key)
+        lib = load()
+        with torch.cuda.device(dev):
+            if st is None:
+                if len(self._step_graphs) >= 4:  # prompts with new weights re-capture: keep the cache small
+                    self._step_graphs.pop(next(iter(self._step_graphs)))
+                st = dict(x=torch.empty_like(x), old=torch.empty_like(x), noise=torch.zeros_like(x) if noise_fn is not None else None,
+                          eps=torch.empty(x.shape[0] * R, *x.shape[1:], dtype=unet.eps_dtype, device=dev),
+                          counter=torch.zeros(1, dtype=torch.int32, device=dev), cur=torch.zeros(16, dtype=torch.float32, device=dev),
+                          table=torch.zeros(STEP_TABLE_ROWS * 16, dtype=torch.float32, device=dev),
+                          host=torch.zeros(STEP_TABLE_ROWS * 16, dtype=torch.float32).pin_memory())
+                st["x"].copy_(x)
+                st["cur"][0] = 1.0
+
+                def one_step():
+                    check(lib.cpd_step_select(C.c_void_p(st["table"].data_ptr()), STEP_TABLE_ROWS, C.c_void_p(st["counter"].data_ptr()),
+                                              C.c_void_p(st["cur"].data_ptr()), stream_ptr(dev)), "cpd_step_select")
+                    ops._count()
+                    unet._run(st["x"], R, st["cur"][0:1], st["cur"][1:2], 1, st["eps"], no_graph=True)
+                    ops.sampler_step(st["eps"], st["x"], n_sub=plan.n_sub, weights=plan.weights, mask_scalars=plan.mask_scalars, masks=plan.masks,
+                                     guidance=0.0, sampler=sampler, pred_type=pred, sigma_hat=1.0, old_denoised=st["old"], noise=st["noise"],
+                                     dyn=st["cur"])
+                # eager warm-up of the UNet shape (allocates the plan's workspace, times the GEMM variants), then the capture
+                unet._run(st["x"], R, st["cur"][0:1], st["cur"][1:2], 1, st["eps"], no_graph=True)
+                torch.cuda.synchronize(dev)
+                n0 = ops.LAUNCHES
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    one_step()
+                st.update(graph=graph, launches=ops.LAUNCHES - n0)
+                self._step_graphs[key] = st
+            st["host"][: n * 16].copy_(torch.frombuffer(bytearray(bytes(table)), dtype=torch.float32))
+            st["table"][: n * 16].copy_(st["host"][: n * 16], non_blocking=True)
+            st["x"].copy_(x, non_blocking=True)
+            st["counter"].zero_()
+            for i in range(n):
+                if noise_fn is not None:
+                    st["noise"].copy_(noise_fn(st["x"]).to(dev, torch.float32), non_blocking=True)
+                st["graph"].replay()
+                ops.LAUNCHES += st["launches"]
+            return st["x"].clone()
 
     def _sampling(self, x, sigmas, model_args=None, **kwargs):
         raise NotImplementedError()

@@ -52,6 +52,19 @@ enum { CPD_PRED_EPSILON = 0, CPD_PRED_VELOCITY = 1 };
  * All scalars are the fp32 values the reference computes on 0-dim tensors (host-side, see
  * complex_prompt_diffusion_b200/samplers/k_diffusion.py).
  */
+/* The per-step scalars of a sampler step as ONE row of a device table (cpd_step_select): a host fills a table for the whole
+ * schedule at the start of sample() - the same fp32 values it would pass by value - and a captured CUDA graph of
+ * [cpd_step_select -> cpd_unet_forward -> cpd_sampler_step] then replays once per step with no host work in between. */
+typedef struct {
+  float c_in;               /* UNet input scale 1 / sqrt(sigma^2 + 1) (denoiser.py:390) */
+  float t;                  /* timestep, rounded to the model dtype (denoiser.py:393) */
+  float guidance, sigma_hat, v_c_eps, v_c_x_div, dt, sigma_up;  /* as in cpd_step_params */
+  float dpm_ratio, dpm_expm1, dpm_c1, dpm_c2;
+  int dpm_first, write_old;
+  float noise_mul;
+  int reserved;
+} cpd_step_scalars;
+
 typedef struct {
   const void* eps;
   int eps_dtype;            /* CPD_F32 / CPD_F16 / CPD_BF16 */
@@ -103,9 +116,17 @@ typedef struct {
   const float* scaled_in;   /* optional [n_images][L]: the scaled guidance term already processed by a thresholding
                                extension that is not a clamp (cpd_threshold_ex on a scaled_out copy); replaces
                                s * sum_e_t in e_t = e_u + scaled (denoiser.py:510-515) */
+  const cpd_step_scalars* dyn; /* optional DEVICE pointer: guidance, sigma_hat, v_c_*, dt, sigma_up, dpm_*, write_old and noise_mul are
+                               read from it by the kernel instead of from the fields above (the "current" row cpd_step_select
+                               wrote), so one captured launch serves every step of a schedule */
 } cpd_step_params;
 
 cpd_status cpd_sampler_step(const cpd_step_params* p, void* stream);
+
+/* current[0] = table[min(*counter, n_steps - 1)]; *counter += 1 - one tiny kernel at the head of a captured sampler-step graph.
+ * table, counter and current are device memory; &current->c_in and &current->t feed cpd_unet_forward's c_in / t, current feeds
+ * cpd_step_params.dyn. */
+cpd_status cpd_step_select(const cpd_step_scalars* table, int n_steps, int* counter, cpd_step_scalars* current, void* stream);
 
 /* Stochastic churn of Karras et al. Algorithm 2 before the denoiser call (euler.py:43-46, huen.py:40-43, dpm2.py:40-43):
  * x[i] = x[i] + (noise[i] * noise_mul) * scale with separately rounded fp32 operations (noise_mul = s_noise,

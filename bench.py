@@ -394,7 +394,9 @@ def run_b200(args):
     if rank == 0:
         ops.PROFILE = []
         unet.profile(True)
-        step_resident()
+        # (eager launches: the per-step CUDA graph is bypassed so that every kernel-level call can be bracketed by events)
+        wrapper.sampler.sample(steps=S, batch_size=B, shape=[4, args.latent, args.latent], x_T=x_T_d, conditioning=c_d,
+                               unconditional_conditioning=uc_d, step_graph=False, **dict(kw))
         torch.cuda.synchronize()
         recs = unet.profile_records()  # (kind, label, us, flops)
         unet.profile(False)

@@ -120,6 +120,12 @@ _SIGS = {
     "cpd_softmax_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_float, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
     "cpd_pointwise_small": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p,
                                       C.c_void_p]),
+    "cpd_gaussian_blur": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                    C.c_void_p]),
+    "cpd_channel_mean": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "cpd_percentile": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    "cpd_attn_guide": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "cpd_images_to_uint8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "cpd_gemm_tune_export": (C.c_int64, [C.c_char_p, C.c_int64]),
     "cpd_gemm_tune_import": (C.c_int, [C.c_char_p]),

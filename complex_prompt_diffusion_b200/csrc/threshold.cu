@@ -12,6 +12,22 @@ namespace {
 // 4-pass most-significant-digit radix select (256-bin shared-memory histogram of the elements that match the prefix found
 // so far; integer atomics: the counts are exact and order-independent).  The two order statistics around the virtual index
 // (n - 1) * q / 100 are interpolated in fp32 the way numpy's _lerp does.
+// ABS = false: the percentile of the SIGNED values (attention-guidance saliency mask, denoiser.py:411): keys are the
+// order-preserving unsigned image of the float bits (negative: all bits flipped, non-negative: sign bit set); the result is
+// the interpolated percentile itself (no max with 1).
+template <bool ABS>
+__device__ __forceinline__ unsigned pct_key(float v) {
+  const unsigned u = __float_as_uint(v);
+  if (ABS) return u & 0x7fffffffu;
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+template <bool ABS>
+__device__ __forceinline__ float pct_value(unsigned key) {
+  if (ABS) return __uint_as_float(key);
+  return __uint_as_float((key & 0x80000000u) ? (key & 0x7fffffffu) : ~key);
+}
+
+template <bool ABS>
 __global__ void __launch_bounds__(1024) abs_percentile_kernel(const float* __restrict__ x, int L, int k_lo, int k_hi, float t,
                                                               float* __restrict__ bound) {
   __shared__ unsigned hist[256];
@@ -35,7 +51,7 @@ __global__ void __launch_bounds__(1024) abs_percentile_kernel(const float* __res
       __syncthreads();
       const unsigned prefix = s_prefix;
       for (int i = threadIdx.x; i < L; i += blockDim.x) {
-        const unsigned key = __float_as_uint(xi[i]) & 0x7fffffffu;
+        const unsigned key = pct_key<ABS>(xi[i]);
         if ((key & mask) == prefix) atomicAdd(&hist[(key >> (8 * pass)) & 255u], 1u);
       }
       __syncthreads();
@@ -52,7 +68,7 @@ __global__ void __launch_bounds__(1024) abs_percentile_kernel(const float* __res
       mask |= 0xffu << (8 * pass);
       __syncthreads();
     }
-    stat[which] = __uint_as_float(s_prefix);
+    stat[which] = pct_value<ABS>(s_prefix);
     __syncthreads();
   }
   if (threadIdx.x == 0) {
@@ -60,7 +76,7 @@ __global__ void __launch_bounds__(1024) abs_percentile_kernel(const float* __res
     const float diff = __fsub_rn(b, a);
     float r = __fadd_rn(a, __fmul_rn(diff, t));                                  // numpy _lerp
     if (t >= 0.5f) r = __fsub_rn(b, __fmul_rn(diff, __fsub_rn(1.0f, t)));
-    bound[blockIdx.x] = fmaxf(r, 1.0f);                                           // np.max(np.append(s, 1.0))
+    bound[blockIdx.x] = ABS ? fmaxf(r, 1.0f) : r;                                 // np.max(np.append(s, 1.0)) for the clamp bound
   }
 }
 
@@ -320,7 +336,7 @@ extern "C" cpd_status cpd_threshold(float* x, int n_images, int L, int alg, floa
     int k_hi = k_lo + 1;
     if (vi >= (float)(L - 1)) k_lo = k_hi = L - 1;  // _get_indexes: at or above the last index -> the maximum
     const float t = vi - (float)(int)floorf(vi);
-    CPD_CUDA_CHECK(cpd_launch(abs_percentile_kernel, dim3(n_images), dim3(1024), 0, s, (const float*)x, L, k_lo, k_hi, t, bound));
+    CPD_CUDA_CHECK(cpd_launch(abs_percentile_kernel<true>, dim3(n_images), dim3(1024), 0, s, (const float*)x, L, k_lo, k_hi, t, bound));
   } else {
     CPD_CUDA_CHECK(cpd_launch(fill_bound_kernel, dim3((n_images + 127) / 128), dim3(128), 0, s, bound, n_images, threshold));
   }
@@ -331,5 +347,21 @@ extern "C" cpd_status cpd_threshold(float* x, int n_images, int L, int alg, floa
     CPD_CUDA_CHECK(cpd_launch(clamp_half_kernel, dim3(bx, n_images), dim3(256), 0, s, x, L / 4, (const float*)bound));
     CPD_CUDA_CHECK(cudaGetLastError());
   }
+  return CPD_OK;
+}
+
+// np.percentile(x, q) of n signed fp32 values (one CTA; linear interpolation, virtual index in fp32 like numpy >= 2 on a float32
+// array): out[0].  The saliency-mask threshold of the attention guidance (denoiser.py:411).
+extern "C" cpd_status cpd_percentile(const float* x, int n, float q, float* out, void* stream) {
+  CPD_REQUIRE(x && out, "cpd_percentile: null pointer");
+  CPD_REQUIRE(n > 0 && q >= 0.f && q <= 100.f, "cpd_percentile: n=%d q=%f", n, (double)q);
+  volatile float q32 = q / 100.0f;
+  volatile float vi = (float)(n - 1) * q32;
+  int k_lo = (int)floorf(vi);
+  int k_hi = k_lo + 1;
+  if (vi >= (float)(n - 1)) k_lo = k_hi = n - 1;
+  const float t = vi - (float)(int)floorf(vi);
+  CPD_CUDA_CHECK(cpd_launch(abs_percentile_kernel<false>, dim3(1), dim3(1024), 0, (cudaStream_t)stream, x, n, k_lo, k_hi, t, out));
+  CPD_CUDA_CHECK(cudaGetLastError());
   return CPD_OK;
 }

@@ -398,3 +398,56 @@ def images_to_uint8(x, out, *, ld_c=None):
         check(load().cpd_images_to_uint8(ptr(x), n, c, h * w, ld_c, ptr(out), stream_ptr()), "cpd_images_to_uint8")
     _count()
     return out
+
+
+# ---- guidance branches of the Denoiser (csrc/guidance.cu) ---------------------------------------------------------------
+def gaussian_taps(kernel_size, sigma):
+    """The 1-D taps of torchvision's _get_gaussian_kernel1d (fp32 torch ops on the host, as the reference evaluates them)."""
+    half = (kernel_size - 1) * 0.5
+    xs = torch.linspace(-half, half, steps=kernel_size, dtype=torch.float32)
+    pdf = torch.exp(-0.5 * (xs / sigma).pow(2))
+    return (pdf / pdf.sum()).contiguous()
+
+
+def gaussian_blur(src, dst, *, kernel_size, sigma, planes_per_image=None, img_stride_src=None, img_stride_dst=None):
+    """dst = GaussianBlur(kernel_size, sigma)(src) per plane, reflect padding.  src / dst: fp32 [n, planes, h, w]-shaped memory
+    whose images may be strided (img_stride_* in elements; default: contiguous)."""
+    if src.dtype != torch.float32 or dst.dtype != torch.float32 or not src.is_cuda or not dst.is_cuda:
+        raise RuntimeError("gaussian_blur works on CUDA fp32 tensors")
+    n, planes, h, w = src.shape
+    taps = gaussian_taps(kernel_size, sigma)
+    with _Prof("guidance", 0.0):
+        check(load().cpd_gaussian_blur(ptr(src), ptr(dst), n, planes_per_image or planes, int(img_stride_src or planes * h * w),
+                                       int(img_stride_dst or planes * h * w), h, w, C.c_void_p(taps.data_ptr()), kernel_size, stream_ptr()),
+              "cpd_gaussian_blur")
+    _count()
+    return dst
+
+
+def channel_mean(a, out, *, pixels, c):
+    f16 = _act(a, "a")
+    _req(out, torch.float32, "out")
+    with _Prof("guidance", 0.0):
+        check(load().cpd_channel_mean(ptr(a), int(pixels), int(c), f16, ptr(out), stream_ptr()), "cpd_channel_mean")
+    _count()
+    return out
+
+
+def percentile(x, out, *, q):
+    _req(x, torch.float32, "x")
+    _req(out, torch.float32, "out")
+    with _Prof("guidance", 0.0):
+        check(load().cpd_percentile(ptr(x), int(x.numel()), float(q), ptr(out), stream_ptr()), "cpd_percentile")
+    _count()
+    return out
+
+
+def attn_guide(stage, out, *, n_images, hw, x=None, eps_u=None, eps_stride=0, mask_mean=None, mask_img_stride=0, pct=None, blur=None,
+               sum16=None, e_attn=None, sigma_hat=0.0, c_in=1.0, mode=2, scale=1.0, guidance=1.0):
+    src = eps_u if eps_u is not None else e_attn
+    with _Prof("guidance", 0.0):
+        check(load().cpd_attn_guide(int(stage), int(n_images), int(hw), ptr(x), ptr(eps_u), DTYPE_CODE[src.dtype], int(eps_stride), ptr(mask_mean),
+                                    int(mask_img_stride), ptr(pct), ptr(blur), ptr(sum16), ptr(e_attn), float(sigma_hat), float(c_in), int(mode),
+                                    float(scale), float(guidance), ptr(out), stream_ptr()), "cpd_attn_guide")
+    _count()
+    return out

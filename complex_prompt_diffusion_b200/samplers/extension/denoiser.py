@@ -10,7 +10,8 @@ synchronisation happens inside a step (the reference has five).
 Differences that are deliberate repairs of reference defects: the image batch may be > 1 and
 means B independent batch-1 trajectories (D7); sigma is passed once (D3); no hard-coded `.cuda()` (D6).
 Built on the device: dynamic / static scale clipping and every runnable thresholding extension, the score-corrector
-hook, feature / skip injection, the decaying guidance scale.  CLIP guidance (a backward pass through VAE + CLIP) and
+hook, feature / skip injection, the decaying guidance scale, the unconditional blur (:333-337,441-442), attention guidance
+(:341-350,404-435,461-462) and the depth mask (:358-360,386-388).  CLIP guidance (a backward pass through VAE + CLIP) and
 gamma > 0 (defective in the reference, D8) raise NotImplementedError when requested instead of being silently ignored.
 """
 import math
@@ -23,7 +24,7 @@ from ..._lib import (CPD_DENOISE_ONLY, CPD_DPMPP_2M, CPD_EULER, CPD_EULER_ANCEST
                      CPD_THRESH_SCALED_NORM, CPD_THRESH_SCALED_SPATIAL_NORM, CPD_THRESH_SPATIAL_NORM, CPD_THRESH_STATIC)
 from ...scheduler.discrete import SigmaScheduler
 
-_UNSUPPORTED_TRUTHY = ("attn_guide", "return_attn", "clip_guidance", "unconditional_guidance_blur", "depth_mask")
+_UNSUPPORTED_TRUTHY = ("clip_guidance",)  # a backward pass through VAE + CLIP (denoiser.py:76-265): out of the hot-path scope
 
 # Thresholding extensions, all on the device (registered names of samplers/extension/threshold.py).  The first two are
 # clamps (the bound feeds the fused step directly); the others rewrite the tensor (cpd_threshold_ex).
@@ -247,6 +248,78 @@ class Denoiser(torch.nn.Module):
                 s = max(kwargs.get("decaying_uc_scale_min", 2), s - s * (math.log(t_idx + 1 - start) / math.log(total)))
         return float(s)
 
+    @staticmethod
+    def guidance_branches(**kwargs):
+        """Which optional branches are active at this schedule index (denoiser.py:333-337,341-343): both switch on for the last
+        `rounds` indices only.  Returns (uc_blur_kernel_size or None, attention-guidance settings dict or None)."""
+        t_idx, total = kwargs.get("t_idx", 0), kwargs.get("total_steps", 1000)
+        blur_k = None
+        if kwargs.get("unconditional_guidance_blur", False) and t_idx > (total - kwargs.get("unconditional_guidance_blur_rounds", int(total / 10))):
+            blur_k = int(kwargs.get("unconditional_guidance_blur_k", 7))
+        guide = None
+        if kwargs.get("attn_guide", kwargs.get("return_attn", False)) and \
+                t_idx > (total - kwargs.get("attn_guide_rounds", kwargs.get("return_attn_rounds", 4))):
+            guide = dict(mode=kwargs.get("attn_guide_mode", 2), idx=kwargs.get("attn_guide_idx", kwargs.get("return_attn_idx", -1)),
+                         scale=kwargs.get("attn_guide_scale", 1.1),
+                         threshold=kwargs.get("attn_guide_mask_threshold", kwargs.get("attn_mask_threshold", 90)),
+                         blur_k=int(kwargs.get("attn_guide_blur_k", 31)))
+            if guide["mode"] not in (1, 2):
+                raise ValueError(f"attn_guide_mode must be 1 or 2, got {guide['mode']}")
+        return blur_k, guide
+
+    @staticmethod
+    def wants_host_between_kernels(kwargs):
+        """True when a step needs host decisions between its kernels (the optional guidance branches, the depth mask): such steps
+        cannot be replayed as one captured graph."""
+        return bool(kwargs.get("unconditional_guidance_blur", False) or kwargs.get("attn_guide", kwargs.get("return_attn", False)) or
+                    kwargs.get("depth_mask", None) is not None)
+
+    @staticmethod
+    def _random_blur_sigma():
+        """torchvision GaussianBlur(kernel_size) draws its sigma from U(0.1, 2.0) with the global CPU generator on every call
+        (GaussianBlur.get_params): the same draw, so a seeded run consumes the RNG like the reference."""
+        return torch.empty(1).uniform_(0.1, 2.0).item()
+
+    def _attention_guidance(self, x, eps, plan, guide, sig, c_in, **kwargs):
+        """denoiser.py:404-435: saliency mask from the channel mean of a skip tensor, blurred denoised sample blended into the
+        latent under the mask, one extra UNet evaluation of the guided latent on the unconditional context.  Returns e_attn
+        [B, 4, h, w] (eps dtype).  Everything runs on the device."""
+        from ...models.unet import UNetModel
+        unet = self.unet
+        if not isinstance(unet, UNetModel):
+            raise NotImplementedError("attention guidance needs the library's UNetModel (it reads the skip tensors of the plan)")
+        if self._part is not None:
+            raise NotImplementedError("attention guidance together with row sharding")
+        B, R = x.shape[0], 1 + plan.n_sub
+        hw = x.shape[2] * x.shape[3]
+        n_in = len(unet.inputs)
+        idx = guide["idx"] % n_in  # index into the POPPED skip list: 0 = last input block ... -1 = the input conv's output
+        src = unet._tap(0, n_in - 1 - idx, B * R)  # NCHW view of the NHWC buffer: [B*R, c, h, w]
+        if tuple(src.shape[2:]) != tuple(x.shape[2:]):
+            raise ValueError(f"attn_guide_idx={guide['idx']} selects a {tuple(src.shape[2:])} tensor; the mask must have the latent's size {tuple(x.shape[2:])}")
+        cch = src.shape[1]
+        nhwc = src.permute(0, 2, 3, 1)  # the plan's own contiguous NHWC memory
+        mean = torch.empty(B * R, hw, dtype=torch.float32, device=x.device)
+        ops.channel_mean(nhwc, mean, pixels=B * R * hw, c=cch)
+        pct = torch.empty(B, dtype=torch.float32, device=x.device)
+        for b in range(B):  # np.percentile over ALL rows of the image's mask tensor (:411)
+            ops.percentile(mean[b * R:(b + 1) * R].reshape(-1), pct[b:b + 1], q=float(guide["threshold"]))
+        L = 4 * hw
+        sample = torch.empty_like(x)
+        ops.attn_guide(0, sample, n_images=B, hw=hw, x=x, eps_u=eps, eps_stride=R * L, sigma_hat=sig)
+        blurred = torch.empty_like(x)
+        ops.gaussian_blur(sample, blurred, kernel_size=guide["blur_k"], sigma=self._random_blur_sigma())
+        guide_x = torch.empty_like(x)
+        ops.attn_guide(1, guide_x, n_images=B, hw=hw, x=x, eps_u=eps, eps_stride=R * L, mask_mean=mean, mask_img_stride=R * hw, pct=pct,
+                       blur=blurred, sigma_hat=sig, c_in=c_in, mode=guide["mode"])
+        # :362,430: the guided latent is evaluated at t = sigma_to_t(sigma) in fp64 -> fp32 (NOT rounded to the model dtype) on
+        # the unconditional context; afterwards the prompt's context rows are cached again
+        t64 = self.scheduler.sigma_to_t(torch.tensor([sig], dtype=torch.float32))
+        uc_ctx = plan.context[0:1]
+        e_attn = unet.forward(guide_x, timesteps=t64.to(torch.float32).expand(B), context=uc_ctx)
+        unet.set_context(plan.context)
+        return e_attn.contiguous()
+
     # ---- device-side --------------------------------------------------------------------------------
     @staticmethod
     def _inject(kwargs):
@@ -278,12 +351,18 @@ class Denoiser(torch.nn.Module):
         return dict(c_in=float(c_in), t=float(t), guidance=self.guidance_scale(**kwargs), sigma_hat=s,
                     v_c_eps=float(-sig_t / (sig_t ** 2 + 1) ** 0.5), v_c_x_div=float(sig_t ** 2 + 1))
 
-    def unet_rows(self, x, sigma, plan, inject=None):
+    def unet_rows(self, x, sigma, plan, inject=None, depth_mask=None):
         """Run the UNet on the (1 + N) conditioning rows of every image: returns eps rows [B*(1+N), 4, h, w]
         (image-major).  x: [B,4,h,w] fp32; sigma: 0-dim/1-element fp32 CPU tensor (same for all images)."""
         sig = self._one_sigma(sigma)
         c_in = 1 / (sig ** 2 + 1 ** 2) ** 0.5  # get_scalings, fp32 like denoiser.py:390
         t = self.scheduler.sigma_to_t(sig).to(self.dtype).float()  # fp64 -> model dtype (P3, denoiser.py:393)
+        if depth_mask is not None:
+            # :358-360,386-388: the depth map rides along as an extra input channel of a depth-conditioned UNet (in_channels = 5)
+            # and is scaled by c_in with the latent; the same map for every image of the batch
+            d = torch.as_tensor(depth_mask).to(x.device, torch.float32)
+            d = d.reshape(-1, *d.shape[-3:]) if d.ndim >= 3 else d.reshape(1, 1, *d.shape)
+            x = torch.cat([x, d[:1].expand(x.shape[0], -1, -1, -1)], dim=1).contiguous()
         if self._part is None:
             if inject:
                 return self.unet.forward_rows(x, float(c_in), float(t), rows_per_image=1 + plan.n_sub, inject=inject)
@@ -306,15 +385,40 @@ class Denoiser(torch.nn.Module):
         """One UNet evaluation + ONE fused kernel: CFG combine, denoised, sampler update (x updated in place).
         `step` is a dict of the fp32 scalars for cpd_sampler_step; `eps` = already evaluated UNet rows (skips the UNet)."""
         if eps is None:
-            eps = self.unet_rows(x, sigma, plan, inject=self._inject(kwargs))
+            eps = self.unet_rows(x, sigma, plan, inject=self._inject(kwargs), depth_mask=kwargs.get("depth_mask", None))
         sig = float(self._one_sigma(sigma)[0])
+        blur_k, guide = self.guidance_branches(**kwargs)
+        e_attn = None
+        if guide is not None:  # before the blur: the reference builds the guided latent from the unblurred out[0] (:419-435)
+            sig32 = torch.tensor([sig], dtype=torch.float32)
+            e_attn = self._attention_guidance(x, eps, plan, guide, sig, float(1 / (sig32 ** 2 + 1 ** 2) ** 0.5), **kwargs)
+        if blur_k is not None:  # :441-442: e_t_uncond = GaussianBlur(k)(e_t_uncond), a new random sigma per call
+            B, R = x.shape[0], 1 + plan.n_sub
+            rows = eps.view(B, R, *x.shape[1:])
+            if rows.dtype != torch.float32:
+                raise NotImplementedError("the unconditional blur runs on fp32 eps rows (UNetModel(eps_dtype=torch.float32))")
+            blurred = torch.empty_like(x)
+            ops.gaussian_blur(rows[:, 0], blurred, kernel_size=blur_k, sigma=self._random_blur_sigma(), img_stride_src=R * x[0].numel())
+            rows[:, 0].copy_(blurred)
         sig_t = torch.tensor([sig], dtype=torch.float32)
         pred = CPD_PRED_VELOCITY if kwargs.get("pred_type", "epsilon") == "velocity" else CPD_PRED_EPSILON
         common = dict(n_sub=plan.n_sub, weights=plan.weights, mask_scalars=plan.mask_scalars, masks=plan.masks,
                       guidance=self.guidance_scale(**kwargs), pred_type=pred, sigma_hat=sig,
                       v_c_eps=float(-sig_t / (sig_t ** 2 + 1) ** 0.5), v_c_x_div=float(sig_t ** 2 + 1))
         clip = scaled_in = None
-        if kwargs.get("scaled_clip", kwargs.get("dynamic_scale_clip", False)):
+        if e_attn is not None:
+            # :461-462,514: sum_e_t = e_attn + scale * (sum_e_t - e_attn) in fp32 (an fp16 tensor minus an fp32 one promotes), then
+            # the guidance scale.  A combine-only pass with guidance 1 hands out the fp16 sum itself.
+            sum16 = torch.empty_like(x)
+            ops.sampler_step(eps, x, sampler=CPD_DENOISE_ONLY, scaled_out=sum16, **dict(common, guidance=1.0))
+            scaled_in = torch.empty_like(x)
+            ops.attn_guide(2, scaled_in, n_images=x.shape[0], hw=x.shape[2] * x.shape[3], sum16=sum16, e_attn=e_attn, scale=guide["scale"],
+                           guidance=common["guidance"])
+            if kwargs.get("scaled_clip", kwargs.get("dynamic_scale_clip", False)):  # :499-512 on the mixed term
+                bound = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+                apply_threshold(scaled_in, bound, kwargs.get("scaled_clip_alg", "dynamic_thresholding"),
+                                kwargs.get("scaled_clip_threshold", kwargs.get("dynamic_scale_clip_threshold", 99.5)))
+        elif kwargs.get("scaled_clip", kwargs.get("dynamic_scale_clip", False)):
             # Dynamic scale clip (denoiser.py:499-512): the scaled guidance term s * sum_e_t is thresholded before it is
             # added to e_u.  The reference runs np.percentile on a CPU copy every step; here a combine-only pass writes
             # the term, cpd_threshold finds the per-image bound on the device and the fused step clamps with it.
@@ -358,7 +462,7 @@ class Denoiser(torch.nn.Module):
         x = x.to(self.device, torch.float32).contiguous()
         plan = self.plan_conditioning(kwargs.get("conditioning"), kwargs.get("unconditional_conditioning"), x.shape[-2:],
                                       y=kwargs.get("y"))
-        rows = self.unet_rows(x, sigma, plan, inject=self._inject(kwargs)).clone()
+        rows = self.unet_rows(x, sigma, plan, inject=self._inject(kwargs), depth_mask=kwargs.get("depth_mask", None)).clone()
         e_t, denoised = torch.empty_like(x), torch.empty_like(x)
         self.fused_step(x.clone(), sigma, plan, dict(sampler=CPD_DENOISE_ONLY, denoised_out=denoised, eps_out=e_t), eps=rows, **kwargs)
         return dict(rows=rows, e_t=e_t, denoised=denoised)

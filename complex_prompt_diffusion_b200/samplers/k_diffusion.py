@@ -115,7 +115,7 @@ class KDiffusionSampler:
             return False
         if model_args.get("scaled_clip", model_args.get("dynamic_scale_clip", False)) or model_args.get("score_corrector") is not None:
             return False
-        if den._inject(model_args) is not None or any(m is not None for m in plan.masks):
+        if den._inject(model_args) is not None or any(m is not None for m in plan.masks) or den.wants_host_between_kernels(model_args):
             return False
         return True
 

@@ -321,6 +321,29 @@ cpd_status cpd_softmax_rows(const void* x, int rows, int cols, int64_t ld, float
 cpd_status cpd_pointwise_small(const float* x, int n, int cin, int cout, int64_t hw, const float* w, const float* b, float scale,
                                float* out, void* stream);
 
+/* ---- optional guidance branches of the Denoiser, all on the device -----------------------------------
+ * Depthwise Gaussian blur of fp32 planes with reflect padding = torchvision.transforms.GaussianBlur as used for the
+ * unconditional blur (denoiser.py:337,441-442) and the attention-guidance blur (:350,420): the 2-D kernel is the outer product of
+ * the 1-D taps (each product rounded to fp32, like torch.mm), fp32 accumulation.  Plane p of image b lives at
+ * src + b * img_stride_src + p * h * w.  taps: HOST array of ksize fp32 values (odd ksize <= 63; h, w > ksize / 2). */
+cpd_status cpd_gaussian_blur(const float* src, float* dst, int n_images, int planes_per_image, int64_t img_stride_src,
+                             int64_t img_stride_dst, int h, int w, const float* taps, int ksize, void* stream);
+/* out[px] = mean over the c channels of an NHWC activation tensor [pixels][c] (attn.mean(1, keepdims=True), denoiser.py:408). */
+cpd_status cpd_channel_mean(const void* a, int64_t pixels, int c, int act_fp16, float* out, void* stream);
+/* out[0] = np.percentile(x[0..n), q) of SIGNED fp32 values (linear interpolation; the saliency threshold, denoiser.py:411). */
+cpd_status cpd_percentile(const float* x, int n, float q, float* out, void* stream);
+/* The elementwise stages of attention guidance over n_images images of 4 * hw elements (denoiser.py:412-429,461-462,514):
+ *   stage 0: out = x - sigma_hat * e_u                                          (the denoised sample that gets blurred)
+ *   stage 1: m = mean > pct ? 1 : (mean < pct ? 0 : mean);  bx = blur + sigma_hat / e_u;
+ *            out = [bx * m (* c_in if mode 2)] + x * (1 - m)   (* c_in if mode 1)            (the guided latent)
+ *   stage 2: out = guidance * (e_attn + scale * (sum16 - e_attn))               (the mixed, scaled guidance term)
+ * e_u of image b starts at eps_u + b * eps_stride elements (eps_dtype); mask_mean holds the channel means of the saliency
+ * source, the row of image b at mask_mean + b * mask_img_stride; pct[b] its percentile. */
+cpd_status cpd_attn_guide(int stage, int n_images, int hw, const float* x, const void* eps_u, int eps_dtype, int64_t eps_stride,
+                          const float* mask_mean, int64_t mask_img_stride, const float* pct, const float* blur, const float* sum16,
+                          const void* e_attn, float sigma_hat, float c_in, int mode, float scale, float guidance, float* out,
+                          void* stream);
+
 /* The latents -> images tail after the decoder (cpd/embeddings/prompts.py:472-475):
  * out[n][p][ch] = uint8(clamp((x[n][ch][p] + 1) / 2, 0, 1) * 255), i.e. NCHW fp32 in (channel stride of an image = hw, image
  * stride = ld_c * hw: the decoder's 4-channel output buffer holds 3-channel images), NHWC uint8 out; c <= 8. */

@@ -16,6 +16,7 @@ What is pinned (the reference itself has no tests / golden vectors, SURVEY.md se
   tests/golden/ref_sampling4.npz   - score_corrector hook with the registered thresholding extensions (--corrector-only)
   tests/golden/ref_sampling5.npz   - img2img branch, decode=True + denoising_strength (--img2img-only)
   tests/golden/ref_sampling6.npz   - decaying guidance scale, decaying_uc_scale* (--decay-only)
+  tests/golden/ref_sampling7.npz   - unconditional blur, attention guidance, depth mask branches of the Denoiser (--guidance-only)
   tests/golden/ref_unet_inject.npz - UNetModel with return_attn / return_feat / inject_attns / inject_feats (--inject-only)
   tests/golden/ref_noise.npz       - NoiseGenerator seed modes and draws (--noise-only)
   tests/golden/ref_threshold.npz   - every runnable thresholding extension on seeded tensors (--threshold-only)
@@ -260,6 +261,78 @@ def reference_sampling_img2img(ref_shim):
     return _run_cases(ref_shim, unet, {}, c, uc, x_T, hw, steps, IMG2IMG_CASES)
 
 
+GUIDANCE_CASES = (
+    ("Euler", "karras", "epsilon", {"unconditional_guidance_blur": True, "unconditional_guidance_blur_rounds": 4}),
+    ("DPM++ 2m", "karras", "epsilon", {"attn_guide": True}),  # defaults: mode 2, rounds 4, threshold 90, blur k 31, scale 1.1
+    ("Euler", "karras", "epsilon", {"attn_guide": True, "attn_guide_mode": 1, "attn_guide_blur_k": 7, "attn_guide_mask_threshold": 75,
+                                    "attn_guide_scale": 1.3, "attn_guide_rounds": 3, "unconditional_guidance_blur": True,
+                                    "unconditional_guidance_blur_k": 5, "unconditional_guidance_blur_rounds": 3}),
+    ("DPM++ 2m", "karras", "velocity", {"depth_mask": True}),
+)
+
+
+def reference_sampling_guidance(ref_shim):
+    """tests/golden/ref_sampling7.npz: the Denoiser's unconditional blur (denoiser.py:333-337,441-442), attention guidance
+    (:341-350,404-435,461-462) and depth mask (:358-360,386-388) branches on the shimmed reference with the tiny UNet at 16 x 16
+    (the 31-tap blur needs reflect padding of 15 < 16).  Every UNet call is recorded (input, timestep, output and, for
+    return_attn calls, the skip tensor the saliency mask is taken from) so that the oracle can be replayed bit-exactly.  The
+    blur's random sigma comes from the global torch RNG (torchvision GaussianBlur.get_params), seeded with 77 per case."""
+    import dataclasses
+    from oracle.unet import UNetConfig, make_weights
+
+    hw, steps = 16, 6
+    out = {}
+    for name, sched, pred, extra in GUIDANCE_CASES:
+        cfg = UNetConfig.tiny()
+        depth = bool(extra.get("depth_mask"))
+        if depth:
+            cfg = dataclasses.replace(cfg, in_channels=5)
+        unet = ref_shim.build_reference_unet(cfg)
+        unet.load_state_dict(make_weights(cfg, seed=0), strict=True)
+        unet.eval()
+        uc, embs, mask, c, x_T = make_case_inputs(UNetConfig.tiny(), hw)
+        if "x_T" not in out:
+            out.update({"x_T": x_T.numpy(), "uc": uc.numpy(), "embs": torch.cat(embs).numpy(), "mask": mask.numpy(),
+                        "scales": np.array([1.0, 0.6, 0.4]), "steps": np.array(steps), "hw": np.array(hw), "guidance": np.array(7.5)})
+        wrapper = build_reference_sampler(name, unet)
+        calls, dens = [], []
+        orig_forward = unet.forward
+        idx = extra.get("attn_guide_idx", -1)
+
+        def rec_forward(x, t, ctx, **k):
+            r = orig_forward(x, t, ctx, **k)
+            o = r[0] if isinstance(r, tuple) else r
+            # the saliency source is only ever used through its channel mean (denoiser.py:408): record that ([R, 1, h, w]); a
+            # one-channel tensor replays it bit-exactly (the mean over one channel is the value itself)
+            calls.append((x.clone(), t.clone().double(), o.clone(), r[1][idx].mean(1, keepdims=True) if isinstance(r, tuple) else None))
+            return r
+
+        unet.forward = rec_forward
+        call_extra = dict(extra)
+        if depth:
+            g = torch.Generator().manual_seed(4321)
+            call_extra["depth_mask"] = torch.rand(1, 1, hw, hw, generator=g)
+            out["depth_mask"] = call_extra["depth_mask"].numpy()
+        torch.manual_seed(77)
+        try:
+            res = wrapper.sampler.sample(steps=steps, batch_size=1, shape=[4, hw, hw], x_T=x_T.clone(), conditioning=c,
+                                         unconditional_conditioning=uc, unconditional_guidance_scale=7.5, scheduler=sched,
+                                         device="cpu", silent=True, pred_type=pred, callback=lambda d: dens.append(d["eps"].clone()),
+                                         **call_extra)
+        finally:
+            unet.forward = orig_forward
+        key = f"{name}|{sched}|{pred}".replace(" ", "_") + "|" + "|".join(f"{k}={v}" for k, v in extra.items())
+        out[key + "|final"] = res.numpy()
+        out[key + "|denoised"] = torch.stack(dens).numpy()
+        out[key + "|n_calls"] = np.array(len(calls))
+        for i, (x, t, o, sk) in enumerate(calls):
+            out[f"{key}|call{i}|x"], out[f"{key}|call{i}|t"], out[f"{key}|call{i}|out"] = x.numpy(), t.numpy(), o.numpy()
+            if sk is not None and extra.get("attn_guide"):
+                out[f"{key}|call{i}|skip"] = sk.numpy()
+        print(key, "final std", float(res.std()), "unet calls", len(calls))
+    return out
+
+
 def schedule_kats_discrete():
     """tests/golden/schedule_kat2.json: SigmaScheduler.get_sigmas_{karras, exponential, quad, vp, sigmoid}
     (cpd/scheduler/discrete.py:21-85) called unbound (they read only their kwargs), float32 bit patterns as ints."""
@@ -461,6 +534,8 @@ def main():
         with open(os.path.join(GOLD, "schedule_kat.json"), "w") as f:
             json.dump(schedule_kats(K), f, indent=1)
         np.savez_compressed(os.path.join(GOLD, "ref_sampling.npz"), **reference_sampling(ref_shim))
+    if want("--guidance-only"):
+        np.savez_compressed(os.path.join(GOLD, "ref_sampling7.npz"), **reference_sampling_guidance(ref_shim))
     if want("--more-only"):
         np.savez_compressed(os.path.join(GOLD, "ref_sampling2.npz"), **reference_sampling_more(ref_shim))
     if want("--vae-only"):

@@ -361,3 +361,49 @@ def test_oracle_unet_injection_matches_reference_unet(golden_dir):
     assert close(out_a, z["out_a"]) and close(out_f, z["out_f"]) and close(out_af, z["out_af"])
     assert close(skips_af[0], z["returned_skip0_af"])  # return_attn reports the ORIGINAL skip, not the injected one (:802-808)
     assert not close(out_a, z["out"]) and not close(out_f, z["out"])
+
+
+# ------------------------------------------------------------------------------ guidance branches
+def _guidance_cases():
+    from oracle.make_golden import GUIDANCE_CASES
+    return list(GUIDANCE_CASES)
+
+
+@pytest.mark.parametrize("name,sched,pred,extra", _guidance_cases())
+def test_oracle_guidance_branches_bit_exact_on_replayed_unet(golden_dir, name, sched, pred, extra):
+    """The oracle's unconditional-blur / attention-guidance / depth-mask restatement (oracle/denoiser.py) against runs of the
+    shimmed reference (tests/golden/ref_sampling7.npz): every UNet input the reference produced (x * c_in incl. the depth
+    channel, the timestep, the guided latent of the extra evaluation) and the final latent are reproduced bit for bit when the
+    recorded UNet outputs and saliency sources are replayed.  The blur's random sigma comes from the global torch RNG, seeded
+    like the generator script (the reference's Euler also draws its unused churn noise from it every step)."""
+    z = np.load(os.path.join(golden_dir, "ref_sampling7.npz"))
+    embs, mask, sc = torch.from_numpy(z["embs"]), torch.from_numpy(z["mask"]), z["scales"]
+    c = {"and": [(float(sc[0]), embs[0:1], None, 1), (float(sc[1]), embs[1:2], None, mask)], "not": [(float(sc[2]), embs[2:3], None, 1)]}
+    key = f"{name}|{sched}|{pred}".replace(" ", "_") + "|" + "|".join(f"{k}={v}" for k, v in extra.items())
+
+    class Replay:
+        i = 0
+
+        def parameters(self):
+            return iter([torch.zeros(1)])
+
+        def __call__(self, x, t, ctx, **kw):
+            k = f"{key}|call{self.i}"
+            assert torch.equal(x, torch.from_numpy(z[k + "|x"])), f"UNet input x of call {self.i} differs from the reference's"
+            assert torch.equal(t.double(), torch.from_numpy(z[k + "|t"])), f"UNet input t of call {self.i} differs from the reference's"
+            o = torch.from_numpy(z[k + "|out"])
+            sk = torch.from_numpy(z[k + "|skip"]) if (k + "|skip") in z.files else o
+            self.i += 1
+            return o, [sk] * 12
+
+    ex = dict(extra)
+    if ex.get("depth_mask"):
+        ex["depth_mask"] = torch.from_numpy(z["depth_mask"])
+    den = OracleDenoiser(Replay())
+    torch.manual_seed(77)
+    out = OS.sample(den, name, int(z["steps"]), torch.from_numpy(z["x_T"]).clone(),
+                    noise_sampler=(lambda x: torch.randn_like(x)) if name == "Euler" else None, conditioning=c,
+                    unconditional_conditioning=torch.from_numpy(z["uc"]), unconditional_guidance_scale=float(z["guidance"]),
+                    scheduler=sched, pred_type=pred, **ex)
+    assert den.unet.i == int(z[key + "|n_calls"])
+    assert torch.equal(out, torch.from_numpy(z[key + "|final"]))

@@ -19,6 +19,8 @@ SHAPES = [  # (name, n_img, h, w, cin, cout, ksize)
     ("lin 4096x1280x1280", 1, 1, 4096, 1280, 1280, 1),
     ("lin 65536x320x1280", 1, 1, 65536, 1280, 320, 1),
     ("lin 8192x8192x8192", 1, 1, 8192, 8192, 8192, 1),
+    ("geglu 65536x320->2560", 1, 1, 65536, 320, 2560, -1),  # ksize -1: the GEGLU epilogue (ff.net.0, attention.py:92-100)
+    ("lin 65536x320x768 (q|k)", 1, 1, 65536, 320, 768, 1),
 ]
 
 
@@ -32,16 +34,22 @@ def main():
     for i, (name, n, h, w, cin, cout, ks) in enumerate(SHAPES):
         if a.only >= 0 and i != a.only:
             continue
+        geglu = ks < 0
+        ks = abs(ks)
         M = n * h * w
         sets = max(2, min(8, int(200e6 // (M * (cin + cout) * 2 + cout * cin * ks * ks * 2)) + 1))
         xs = [torch.randn(M, cin, device="cuda").to(torch.float16) for _ in range(sets)]
         ws = [(torch.randn(cout, ks * ks * cin, device="cuda") / (ks * ks * cin) ** 0.5).to(torch.float16) for _ in range(sets)]
-        outs = [torch.empty(M, cout, device="cuda", dtype=torch.float16) for _ in range(sets)]
+        outs = [torch.empty(M, cout // 2 if geglu else cout, device="cuda", dtype=torch.float16) for _ in range(sets)]
         bias = torch.randn(cout, device="cuda")
 
         def run(j):
-            ops.gemm_conv(xs[j % sets], ws[j % sets], outs[j % sets], n_img=n, h=h, w=w, c0=cin, n_out=cout, ksize=ks, bias=bias,
-                          variant=a.variant)
+            if geglu:
+                ops.gemm_conv(xs[j % sets], ws[j % sets], outs[j % sets], n_img=n, h=h, w=w, c0=cin, n_out=cout, bias=bias,
+                              epilogue=ops.CPD_EPI_GEGLU, geglu_block=256)
+            else:
+                ops.gemm_conv(xs[j % sets], ws[j % sets], outs[j % sets], n_img=n, h=h, w=w, c0=cin, n_out=cout, ksize=ks, bias=bias,
+                              variant=a.variant)
         for j in range(3):
             run(j)
         torch.cuda.synchronize()

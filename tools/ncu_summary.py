@@ -7,6 +7,11 @@ import sys
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes.sum.per_second",
         "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        # tcgen05 on B200: the legacy sm__inst_executed_pipe_tensor* / sm__ops_path_tensor_op_hmma* counters stay at 0; the tensor
+        # pipe's busy cycles show up in the TriageCompute group (realtime counters) and the TMEM pipe has its own instruction counter
+        "TPC.TriageCompute.sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg",
+        "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active", "sm__cycles_elapsed.avg", "sm__cycles_active.avg",
         "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "sm__cycles_elapsed.avg.per_second"]
@@ -19,9 +24,17 @@ def main(path):
     ki = hdr.index("Kernel Name")
     for r in rows[2:]:
         print(f"== {r[ki][:100]}")
+        vals = {}
         for h, u, v in zip(hdr, units, r):
             if h in WANT:
                 print(f"   {h:75s} {v:>16s} {u}")
+                vals[h] = v
+        try:  # tensor-pipe utilisation = busy cycles of the (h)mma sub-pipe, which executes tcgen05.mma kind::f16, over elapsed cycles
+            busy = float(vals["TPC.TriageCompute.sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg"].replace(",", ""))
+            el = float(vals["sm__cycles_elapsed.avg"].replace(",", ""))
+            print(f"   {'tensor pipe busy (hmma sub-pipe cycles / elapsed cycles)':75s} {100.0 * busy / el:16.2f} %")
+        except (KeyError, ValueError, ZeroDivisionError):
+            pass
 
 
 if __name__ == "__main__":

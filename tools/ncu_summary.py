@@ -32,7 +32,8 @@ def main(path):
         try:  # tensor-pipe utilisation = busy cycles of the (h)mma sub-pipe, which executes tcgen05.mma kind::f16, over elapsed cycles
             busy = float(vals["TPC.TriageCompute.sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg"].replace(",", ""))
             el = float(vals["sm__cycles_elapsed.avg"].replace(",", ""))
-            print(f"   {'tensor pipe busy (hmma sub-pipe cycles / elapsed cycles)':75s} {100.0 * busy / el:16.2f} %")
+            # the TriageCompute counter is per TPC (two SMs): halve it for the per-SM busy fraction
+            print(f"   {'tensor pipe busy per SM (TPC hmma sub-pipe busy cycles / 2 / elapsed cycles)':75s} {50.0 * busy / el:16.2f} %")
         except (KeyError, ValueError, ZeroDivisionError):
             pass
 

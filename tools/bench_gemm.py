@@ -21,6 +21,12 @@ SHAPES = [  # (name, n_img, h, w, cin, cout, ksize)
     ("lin 8192x8192x8192", 1, 1, 8192, 8192, 8192, 1),
     ("geglu 65536x320->2560", 1, 1, 65536, 320, 2560, -1),  # ksize -1: the GEGLU epilogue (ff.net.0, attention.py:92-100)
     ("lin 65536x320x768 (q|k)", 1, 1, 65536, 320, 768, 1),
+    # small-M levels (config 3: two rows of SD-2.1 at 96 x 96; strong-scaled config 2)
+    ("conv3 2x12^2 1280->1280", 2, 12, 12, 1280, 1280, 3),
+    ("conv3 2x12^2 2560->1280", 2, 12, 12, 2560, 1280, 3),
+    ("conv3 2x24^2 1280->1280", 2, 24, 24, 1280, 1280, 3),
+    ("lin 18432x320x320", 1, 1, 18432, 320, 320, 1),
+    ("conv3 2x96^2 320->320", 2, 96, 96, 320, 320, 3),
 ]
 
 

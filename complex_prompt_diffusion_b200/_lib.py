@@ -61,6 +61,9 @@ class GemmParams(C.Structure):
         ("a_fp16", C.c_int), ("b_fp16", C.c_int), ("out_fp16", C.c_int), ("geglu_block", C.c_int),
         ("splitk_ws", C.c_void_p), ("splitk_ws_floats", C.c_int64),
         ("tune_scratch", C.c_void_p), ("tune_scratch_bytes", C.c_int64),
+        ("ln_sums_out", C.c_void_p), ("ln_parts_out", C.POINTER(C.c_int)), ("ln_sums", C.c_void_p), ("ln_parts", C.c_int),
+        ("ln_ld", C.c_int64), ("ln_g", C.c_void_p), ("ln_c", C.c_int), ("ln_eps", C.c_float),
+        ("d_t", C.c_void_p), ("dt_col0", C.c_int), ("ldd_t", C.c_int64),
     ]
 
 

@@ -392,6 +392,9 @@ __device__ __forceinline__ float lds32f(uint32_t addr) {
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void sts128f(uint32_t addr, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
@@ -463,6 +466,22 @@ __device__ __forceinline__ float gelu_fast_f(float x) {
   const float erf_z = copysignf(erf_abs, z);
   const float hx = 0.5f * x;
   return fmaf(hx, erf_z, hx);
+}
+// GELU in the logistic form x * sigmoid(2 u(x)), u = x * p(min(x^2, 36)) with a degree-4 minimax p fitted to the erf form
+// (attention.py:98-100 uses F.gelu = 0.5 x (1 + erf(x / sqrt 2))): |error| <= 3.4e-6 over every fp16 input (tools/fit_gelu.py;
+// the half-ulp of a 16-bit result is >= 2.4e-4 |v|), 2 MUFU (ex2, rcp) + 9 FMA-pipe instructions where the Abramowitz-Stegun
+// erf of gelu_fast_f needs 2 + 13.  The coefficients carry the factor -2 log2(e); the clamp keeps p monotone beyond |x| = 6,
+// where the result is x or 0 to fp32 precision (ex2 -> 0 or +inf, rcp(+inf) = 0: no NaN for finite x).
+__device__ __forceinline__ float gelu_sig_f(float x) {
+  const float t = fminf(x * x, 36.0f);
+  float p = fmaf(t, -3.2289963530e-06f, 8.8238257537e-05f);
+  p = fmaf(p, t, 3.6027394776e-04f);
+  p = fmaf(p, t, -1.0522668698e-01f);
+  p = fmaf(p, t, -2.3020453906e+00f);
+  const float e = fast_ex2(x * p);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
 }
 // (a0 * b0, a1 * b1) of two packed 16-bit pairs, rounded once to the activation format (one HMUL2)
 __device__ __forceinline__ uint32_t mul_act2(uint32_t a, uint32_t b, bool f16) {

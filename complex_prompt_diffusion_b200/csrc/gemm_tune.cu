@@ -28,7 +28,9 @@ std::mutex g_mu;
 
 TuneKey make_key(const cpd_gemm_params* p) {
   return TuneKey{p->n_img, p->h_in, p->w_in, p->c0, p->c1, p->n_out, p->ksize, p->stride, p->epilogue,
-                 p->epilogue == CPD_EPI_GEGLU ? p->geglu_block : 0, p->residual != nullptr, p->rowvec != nullptr, p->a_fp16, p->m_valid};
+                 p->epilogue == CPD_EPI_GEGLU ? p->geglu_block : 0,
+                 (p->residual != nullptr) | ((p->ln_sums_out != nullptr) << 1) | ((p->ln_sums != nullptr) << 2) | ((p->d_t != nullptr) << 3),
+                 p->rowvec != nullptr, p->a_fp16, p->m_valid};
 }
 
 bool autotune_on() {

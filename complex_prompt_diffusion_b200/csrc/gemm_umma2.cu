@@ -42,7 +42,7 @@ constexpr int CHUNK_BYTES = BM * CHUNK_COLS * 2;   // 8 KB
 constexpr int STAGING_BUFS = 4;                    // per epilogue group (3 left the residual prefetch one chunk short: ~2000-cycle waits, profiles/r02_gemm_timeline.txt)
 constexpr int STAGING_BYTES = EPI_GROUPS * STAGING_BUFS * CHUNK_BYTES;
 constexpr int BIAS_FLOATS = 512;                   // widest tile: 2 sub-tiles x 256 columns
-constexpr int BIAS_BYTES = EPI_GROUPS * 2 * BIAS_FLOATS * 4;  // per group, double-buffered by tile parity
+constexpr int BIAS_BYTES = 2 * EPI_GROUPS * 2 * BIAS_FLOATS * 4;  // bias and (folded LayerNorm) g: per group, double-buffered by tile parity
 
 #ifdef CPD_TIMELINE
 // Debug build (make TIMELINE=1): CTA 0 stamps %globaltimer at the phases of its first tile (tools/gemm_timeline.py)
@@ -103,6 +103,16 @@ struct Gemm2Args {
   float* ws;        // [splits][rows][n_store] fp32
   int64_t ws_slice; // rows * n_store
   int split_prod;   // 1: warp 2 issues the weight (B) loads, warp 0 only the activation (A) loads (CPD_GEMM_SPLIT_PROD)
+  // LayerNorm folded into the GEMM (cpd_gemm_params.ln_*): consumer side (ln_in) and producer side (ln_out)
+  const float2* ln_in;
+  int ln_parts;
+  int64_t ln_ld;
+  const float* ln_g;
+  float ln_inv_c, ln_eps;
+  float2* ln_out;
+  // transposed tail: chunks whose first column is >= dt_col0 go to d_t through map_dt (128 rows x 32 columns -> 32 x 128)
+  CUtensorMap map_dt;
+  int dt_col0;      // < 0: off
 };
 
 // MC = 1: cluster = one CTA pair.  MC = 2: cluster = two CTA pairs working on the same 256 rows and adjacent column
@@ -110,15 +120,20 @@ struct Gemm2Args {
 // halving the L2 -> SM traffic of the A operand (the main loop is L2-bandwidth-bound).
 // OF16: the element type of D / the residual (fp16 or bf16) as a compile-time constant - with a runtime flag every F2FP of
 // the epilogue was emitted twice under complementary predicates.
-template <int MC, bool OF16>
+// FEAT: epilogue features as compile-time bits (the plain instantiation must not pay for them: with runtime flags the
+// epilogue-bound K = 320 linears lost 17 %): 1 = folded-LayerNorm consumer, 2 = folded-LayerNorm producer, 4 = transposed tail.
+constexpr int FEAT_LN_IN = 1, FEAT_LN_OUT = 2, FEAT_DT = 4;
+template <int MC, bool OF16, int FEAT>
 __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
     gemm2_kernel(const __grid_constant__ Gemm2Args args) {
+  constexpr bool ln_in = (FEAT & FEAT_LN_IN) != 0, ln_out = (FEAT & FEAT_LN_OUT) != 0, has_dt = (FEAT & FEAT_DT) != 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stages = args.stages;
   const int stage_bytes = args.stage_bytes;
   uint8_t* staging = smem + stages * stage_bytes;
   float* bias_s = reinterpret_cast<float*>(staging + STAGING_BYTES);  // [EPI_GROUPS][2][BIAS_FLOATS]
+  float* g_s = bias_s + EPI_GROUPS * 2 * BIAS_FLOATS;                 // same shape: g of a folded LayerNorm
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + STAGING_BYTES + BIAS_BYTES);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tmem_full = empty_bar + MAX_STAGES;
@@ -140,6 +155,10 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
   const int n_tiles_c = args.n_tiles / MC;         // column tiles per cluster step (host guarantees divisibility)
   const int splits = args.splits;
   const int total_tiles = args.m_tiles2 * n_tiles_c * splits;  // work units: (row block, column tile(s), K range)
+  // Work units are dealt round-robin: the 74 clusters work on 74 neighbouring tiles at any time.  (A CONTIGUOUS range per cluster -
+  // consecutive tiles sharing their 256 rows, so that per-row epilogue state is loaded once per row block - was measured and is
+  // slower: 65536 x 768 x 320 61-65 -> 76 us, 65536 x 320 x 320 29.6 -> 31.4 us on the same box.)
+  const int t_begin = cluster_id, t_end = total_tiles, t_step = num_clusters;
   // (integer divisions cost ~50 cycles each, 64-bit ones several hundred: the common splits == 1 / single-column-tile cases skip them)
   const float inv_splits = 1.0f / (float)splits, inv_ntc = 1.0f / (float)n_tiles_c;
   auto tile_mn = [&](int u, int& m2, int& n_tile) {
@@ -170,6 +189,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
     if (g.cb1 > 0) tma_prefetch_desc(&args.map_a1);
     tma_prefetch_desc(&args.map_d);
     if (args.residual) tma_prefetch_desc(&args.map_res);
+    if (has_dt) tma_prefetch_desc(&args.map_dt);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < EPI_GROUPS * STAGING_BUFS; ++s) {
@@ -213,7 +233,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
       uint32_t phase = 0;
       const uint16_t mc_mask = (uint16_t)(0x5u << rank);  // same-rank CTAs of both pairs
       if (lane == 0) CPD_STAMP(13);
-      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+      for (int t = t_begin; t < t_end; t += t_step) {
         int m2, n_tile;
         tile_mn(t, m2, n_tile);
         const int m_tile = m2 * 2 + (int)rank;
@@ -236,10 +256,10 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
             px = (kx == 0) ? 1 : kx - 1;
           }
         }
-        if (t == cluster_id && lane == 0) CPD_STAMP(11);
+        if (t == t_begin && lane == 0) CPD_STAMP(11);
         for (int kt = k0; kt < k1; ++kt) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-          if (kt == k0 && t == cluster_id && lane == 0) CPD_STAMP(12);
+          if (kt == k0 && t == t_begin && lane == 0) CPD_STAMP(12);
           uint8_t* sa = smem + stage * stage_bytes;
           const bool src1 = cb >= g.cb0;
           const CUtensorMap* ma = src1 ? &args.map_a1 : &args.map_a0;
@@ -267,7 +287,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
                 tma_load_2d_pair(sa + A_BYTES + sub * (bn_half * 128), &args.map_b, &full_bar[stage], kt * BK, b_row + sub * args.bn);
           }
           __syncwarp();
-          if (kt == k0 && t == cluster_id && lane == 0) CPD_STAMP(3);
+          if (kt == k0 && t == t_begin && lane == 0) CPD_STAMP(3);
           if (++stage == stages) {
             stage = 0;
             phase ^= 1;
@@ -300,7 +320,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
     const int tile_w = args.bn * args.nsub;
     int stage = 0;
     uint32_t phase = 0;
-    for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+    for (int t = t_begin; t < t_end; t += t_step) {
       int m2, n_tile;
       tile_mn(t, m2, n_tile);
       const int b_row = n_tile * tile_w + (int)rank * bn_half;
@@ -331,7 +351,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
       uint32_t phase = 0;
       uint64_t da = desc0;
       int it = 0;
-      for (int t = cluster_id; t < total_tiles; t += num_clusters, ++it) {
+      for (int t = t_begin; t < t_end; t += t_step, ++it) {
         const int acc = two_acc ? (it & 1) : 0;
         const uint32_t acc_phase = (uint32_t)((two_acc ? (it >> 1) : it) & 1);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 4);  // epilogue has drained this accumulator
@@ -344,7 +364,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
           mbar_wait(&full_bar[stage], phase, 2);
           tc_fence_after();
           MMA_STAMP(0);
-          if (kt == k0 && t == cluster_id && lane == 0) CPD_STAMP(4);
+          if (kt == k0 && t == t_begin && lane == 0) CPD_STAMP(4);
           const uint64_t db = da + b_off;
           if (elect_one()) {
             // +2 in the address field = 32 bytes = 16 elements along K inside the 128-byte swizzle atom
@@ -374,7 +394,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
         }
         if (elect_one()) umma_commit_pair(&tmem_full[acc], (uint16_t)(3u << (2 * pair)));  // accumulator complete, both CTAs of the pair
         __syncwarp();
-        if (t == cluster_id && lane == 0) CPD_STAMP(5);
+        if (t == t_begin && lane == 0) CPD_STAMP(5);
       }
     }
   } else if (warp == 3 && lane < EPI_GROUPS && splits == 1) {
@@ -410,21 +430,21 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
                       bc.y, bc.n);
         }
       };
-      int t_r = cluster_id, ch_r = c_lo, kc_r = 0;  // residual prefetch cursor
+      int t_r = t_begin, ch_r = c_lo, kc_r = 0;  // residual prefetch cursor
       auto advance_r = [&]() {
         ++kc_r;
         if (++ch_r == c_hi) {
           ch_r = c_lo;
-          t_r += num_clusters;
+          t_r += t_step;
         }
       };
       if (has_res)
-        for (int i = 0; i < STAGING_BUFS && t_r < total_tiles; ++i) {
+        for (int i = 0; i < STAGING_BUFS && t_r < t_end; ++i) {
           issue_residual(t_r, ch_r, kc_r % STAGING_BUFS);
           advance_r();
         }
       int kc = 0;
-      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+      for (int t = t_begin; t < t_end; t += t_step) {
         int m2, n_tile;
         tile_mn(t, m2, n_tile);
         const int m_tile = m2 * 2 + (int)rank;
@@ -434,7 +454,13 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
           const uint8_t* sbuf = my_staging + buf * CHUNK_BYTES;
           const int col0 = n_tile * out_w + ch * CHUNK_COLS;
           mbar_wait(&my_ready[buf], (uint32_t)((kc / STAGING_BUFS) & 1), 7);
-          if (col0 < g.n_store) {
+          if (has_dt && col0 >= args.dt_col0) {
+            // two [32 columns][64 rows] halves -> d_t[column][row].  Row = m_tile * 128 (plain GEMM: one 128-row box per CTA tile),
+            // NOT bc0.x: for a CTA tile beyond the last row box_coord wraps x to 0 and moves the tile into the (out-of-bounds)
+            // image coordinate, which this 2-D map does not have.
+            tma_store_2d(&args.map_dt, sbuf, m_tile * BM, col0 - args.dt_col0);
+            tma_store_2d(&args.map_dt, sbuf + CHUNK_BYTES / 2, m_tile * BM + 64, col0 - args.dt_col0);
+          } else if (col0 < g.n_store) {
             tma_store_4d(&args.map_d, sbuf, col0, bc0.x, bc0.y, bc0.n);
             for (int j = 1; j < g.nbox; ++j) {
               const BoxCoord bc = box_coord(g, m_tile, j, 4, 0);
@@ -446,7 +472,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
             bulk_wait_group_read<1>();  // every store but the one just issued has been read: chunk kc - 1's buffer is free
             const int prev = (kc - 1) % STAGING_BUFS;
             if (has_res) {
-              if (t_r < total_tiles) {
+              if (t_r < t_end) {
                 issue_residual(t_r, ch_r, prev);  // kc_r == kc + STAGING_BUFS - 1: this IS the buffer that chunk will use
                 advance_r();
               }
@@ -486,7 +512,11 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
 
     int kc = 0;  // chunks processed by this group so far (staging buffer = kc % 3, residual barrier parity = (kc / 3) & 1)
     int it = 0;
-    for (int t = cluster_id; t < total_tiles; t += num_clusters, ++it) {
+    float ln_rstd = 1.f, ln_nm = 0.f;  // folded LayerNorm: this thread's row of the current row block
+    int ln_m2 = -1;
+    float2 ln_pf0 = make_float2(0.f, 0.f), ln_pf1 = ln_pf0, ln_pf2 = ln_pf0, ln_pf3 = ln_pf0;  // prefetched parts of the next tile's row
+    bool ln_pf_valid = false;
+    for (int t = t_begin; t < t_end; t += t_step, ++it) {
       int m2, n_tile;
       tile_mn(t, m2, n_tile);
       const int m_tile = m2 * 2 + (int)rank;
@@ -498,6 +528,59 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
       // with one group barrier per tile a warp is at most one tile ahead of the slowest reader.
       const int bias_w = geglu ? bn : out_w;  // floats of bias per tile
       float* my_bias = bias_s + (grp * 2 + (it & 1)) * BIAS_FLOATS;
+      float* my_g = g_s + (grp * 2 + (it & 1)) * BIAS_FLOATS;
+      // folded LayerNorm, consumer side: mean / rstd of this thread's row from the producer's partial sums (summed in part order).
+      // The epilogue is the busy stage of the K <= 1280 linears, so an L2 round trip at the top of every tile is exposed
+      // (measured: +20 % on 65536 x 1152 x 320): the first four parts of the NEXT tile's row are requested here, one tile ahead.
+      if (ln_in && m2 != ln_m2) {
+        ln_m2 = m2;
+        float s1 = 0.f, s2 = 0.f;
+        if (rc.valid) {
+          const float2* lp = args.ln_in + rc.row;
+          const float2 z = make_float2(0.f, 0.f);
+          if (!ln_pf_valid) {  // first tile of this CTA
+            ln_pf0 = __ldg(lp);
+            ln_pf1 = args.ln_parts > 1 ? __ldg(lp + args.ln_ld) : z;
+            ln_pf2 = args.ln_parts > 2 ? __ldg(lp + 2 * args.ln_ld) : z;
+            ln_pf3 = args.ln_parts > 3 ? __ldg(lp + 3 * args.ln_ld) : z;
+          }
+          s1 = ((ln_pf0.x + ln_pf1.x) + ln_pf2.x) + ln_pf3.x;
+          s2 = ((ln_pf0.y + ln_pf1.y) + ln_pf2.y) + ln_pf3.y;
+          for (int pi = 4; pi < args.ln_parts; pi += 4) {  // wide rows (N >= 640 producers): four loads in flight at a time
+            const float2 v0 = __ldg(lp + (int64_t)pi * args.ln_ld);
+            const float2 v1 = pi + 1 < args.ln_parts ? __ldg(lp + (int64_t)(pi + 1) * args.ln_ld) : z;
+            const float2 v2 = pi + 2 < args.ln_parts ? __ldg(lp + (int64_t)(pi + 2) * args.ln_ld) : z;
+            const float2 v3 = pi + 3 < args.ln_parts ? __ldg(lp + (int64_t)(pi + 3) * args.ln_ld) : z;
+            s1 += v0.x; s2 += v0.y;
+            s1 += v1.x; s2 += v1.y;
+            s1 += v2.x; s2 += v2.y;
+            s1 += v3.x; s2 += v3.y;
+          }
+        }
+        const float mean = s1 * args.ln_inv_c;
+        const float var = fmaxf(fmaf(s2, args.ln_inv_c, -mean * mean), 0.f);
+        ln_rstd = rsqrtf(var + args.ln_eps);
+        ln_nm = -mean * ln_rstd;
+      }
+      if (ln_in) {
+        ln_pf_valid = false;
+        const int t_next = t + t_step;
+        if (t_next < t_end) {
+          int m2n, ntn;
+          tile_mn(t_next, m2n, ntn);
+          if (m2n != m2) {
+            const RowCoord rn = row_coord(g, m2n * 2 + (int)rank, r);
+            ln_pf_valid = true;  // (rows beyond the valid range: zeros, never used)
+            const float2 z = make_float2(0.f, 0.f);
+            const float2* lp = args.ln_in + rn.row;
+            ln_pf0 = rn.valid ? __ldg(lp) : z;
+            ln_pf1 = rn.valid && args.ln_parts > 1 ? __ldg(lp + args.ln_ld) : z;
+            ln_pf2 = rn.valid && args.ln_parts > 2 ? __ldg(lp + 2 * args.ln_ld) : z;
+            ln_pf3 = rn.valid && args.ln_parts > 3 ? __ldg(lp + 3 * args.ln_ld) : z;
+          }
+        }
+      }
+      float ln_s1 = 0.f, ln_s2 = 0.f;  // producer side: this thread's row over this group's columns of the tile
       if (args.bias) {
         const int col_first = n_tile * bias_w;
         const int idx = r * 4;
@@ -511,6 +594,11 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
             if (col_first + idx + 2 < g.n_out) v.z = __ldg(args.bias + col_first + idx + 2);
           }
           sts128f(smem_u32(my_bias + idx), v);
+          if (ln_in) {  // g[n] of the folded LayerNorm, same columns (n_out % 4 == 0 for folded launches)
+            float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (col_first + idx + 3 < g.n_out) gv = __ldg(reinterpret_cast<const float4*>(args.ln_g + col_first + idx));
+            sts128f(smem_u32(my_g + idx), gv);
+          }
         }
         if (rv && (lane < ((bias_w + 31) >> 5)) && col_first + lane * 32 < g.n_out)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(rv + col_first + lane * 32));
@@ -520,7 +608,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
       const uint32_t acc_phase = (uint32_t)((two_acc ? (it >> 1) : it) & 1);
       mbar_wait(&tmem_full[acc], acc_phase, 3);
       tc_fence_after();
-      if (t == cluster_id && leader && grp == 0) CPD_STAMP(6);
+      if (t == t_begin && leader && grp == 0) CPD_STAMP(6);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS);
 
       if (splits > 1) {
@@ -560,25 +648,45 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
         if (geglu) {
           // tile columns [0, bn/2) = value, [bn/2, bn) = gate.  The reference rounds the projection to the model dtype,
           // applies gelu (rounded), then multiplies in the model dtype (attention.py:98-100): value and gelu(gate) are
-          // packed to 16 bit and multiplied with one HMUL2 per pair.
+          // packed to 16 bit and multiplied with one HMUL2 per pair.  (The gate is NOT rounded to 16 bit in front of the
+          // gelu - three instructions per pair, and the fp32 value is the more exact one.)
           uint32_t va[32], vg[32];
           tmem_ld32(taddr + ch * CHUNK_COLS, va);
           tmem_ld32(taddr + (bn >> 1) + ch * CHUNK_COLS, vg);
           tmem_ld_wait();
           const float* bias_v = args.bias ? my_bias + ch * CHUNK_COLS : nullptr;  // shared memory (broadcast reads)
+          if (ln_in) {  // value / gate = rstd * (acc - mean * g) + b'
+            const float* g_v = my_g + ch * CHUNK_COLS;
 #pragma unroll
-          for (int e = 0; e < 32; e += 4) {
-            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bg = bv;
-            if (bias_v) {
-              bv = lds128f(smem_u32(bias_v + e));
-              bg = lds128f(smem_u32(bias_v + (bn >> 1) + e));
+            for (int e = 0; e < 32; e += 4) {
+              const float4 bv = lds128f(smem_u32(bias_v + e)), bg = lds128f(smem_u32(bias_v + (bn >> 1) + e));
+              const float4 gv = lds128f(smem_u32(g_v + e)), gg = lds128f(smem_u32(g_v + (bn >> 1) + e));
+              const uint32_t a01 = pack_act2(fmaf(__uint_as_float(va[e]), ln_rstd, fmaf(ln_nm, gv.x, bv.x)),
+                                             fmaf(__uint_as_float(va[e + 1]), ln_rstd, fmaf(ln_nm, gv.y, bv.y)), of16);
+              const uint32_t a23 = pack_act2(fmaf(__uint_as_float(va[e + 2]), ln_rstd, fmaf(ln_nm, gv.z, bv.z)),
+                                             fmaf(__uint_as_float(va[e + 3]), ln_rstd, fmaf(ln_nm, gv.w, bv.w)), of16);
+              const float g0 = fmaf(__uint_as_float(vg[e]), ln_rstd, fmaf(ln_nm, gg.x, bg.x));
+              const float g1 = fmaf(__uint_as_float(vg[e + 1]), ln_rstd, fmaf(ln_nm, gg.y, bg.y));
+              const float g2 = fmaf(__uint_as_float(vg[e + 2]), ln_rstd, fmaf(ln_nm, gg.z, bg.z));
+              const float g3 = fmaf(__uint_as_float(vg[e + 3]), ln_rstd, fmaf(ln_nm, gg.w, bg.w));
+              packed[e >> 1] = mul_act2(a01, pack_act2(gelu_sig_f(g0), gelu_sig_f(g1), of16), of16);
+              packed[(e >> 1) + 1] = mul_act2(a23, pack_act2(gelu_sig_f(g2), gelu_sig_f(g3), of16), of16);
             }
-            const uint32_t a01 = pack_act2(__uint_as_float(va[e]) + bv.x, __uint_as_float(va[e + 1]) + bv.y, of16);
-            const uint32_t a23 = pack_act2(__uint_as_float(va[e + 2]) + bv.z, __uint_as_float(va[e + 3]) + bv.w, of16);
-            const float2 g01 = unpack_act2(pack_act2(__uint_as_float(vg[e]) + bg.x, __uint_as_float(vg[e + 1]) + bg.y, of16), of16);
-            const float2 g23 = unpack_act2(pack_act2(__uint_as_float(vg[e + 2]) + bg.z, __uint_as_float(vg[e + 3]) + bg.w, of16), of16);
-            packed[e >> 1] = mul_act2(a01, pack_act2(gelu_fast_f(g01.x), gelu_fast_f(g01.y), of16), of16);
-            packed[(e >> 1) + 1] = mul_act2(a23, pack_act2(gelu_fast_f(g23.x), gelu_fast_f(g23.y), of16), of16);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+              float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bg = bv;
+              if (bias_v) {
+                bv = lds128f(smem_u32(bias_v + e));
+                bg = lds128f(smem_u32(bias_v + (bn >> 1) + e));
+              }
+              const uint32_t a01 = pack_act2(__uint_as_float(va[e]) + bv.x, __uint_as_float(va[e + 1]) + bv.y, of16);
+              const uint32_t a23 = pack_act2(__uint_as_float(va[e + 2]) + bv.z, __uint_as_float(va[e + 3]) + bv.w, of16);
+              const float g0 = __uint_as_float(vg[e]) + bg.x, g1 = __uint_as_float(vg[e + 1]) + bg.y;
+              const float g2 = __uint_as_float(vg[e + 2]) + bg.z, g3 = __uint_as_float(vg[e + 3]) + bg.w;
+              packed[e >> 1] = mul_act2(a01, pack_act2(gelu_sig_f(g0), gelu_sig_f(g1), of16), of16);
+              packed[(e >> 1) + 1] = mul_act2(a23, pack_act2(gelu_sig_f(g2), gelu_sig_f(g3), of16), of16);
+            }
           }
         } else {
           uint32_t v[32];
@@ -588,7 +696,17 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
 #pragma unroll
           for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
           if (col0 + CHUNK_COLS <= g.n_store) {
-            if (args.bias) {
+            if (ln_in) {  // rstd * (acc - mean * g) + b'  (host: folded launches always carry the folded bias)
+#pragma unroll
+              for (int e = 0; e < 32; e += 4) {
+                const float4 b4 = lds128f(smem_u32(my_bias + ch * CHUNK_COLS + e));
+                const float4 g4 = lds128f(smem_u32(my_g + ch * CHUNK_COLS + e));
+                f[e] = fmaf(f[e], ln_rstd, fmaf(ln_nm, g4.x, b4.x));
+                f[e + 1] = fmaf(f[e + 1], ln_rstd, fmaf(ln_nm, g4.y, b4.y));
+                f[e + 2] = fmaf(f[e + 2], ln_rstd, fmaf(ln_nm, g4.z, b4.z));
+                f[e + 3] = fmaf(f[e + 3], ln_rstd, fmaf(ln_nm, g4.w, b4.w));
+              }
+            } else if (args.bias) {
 #pragma unroll
               for (int e = 0; e < 32; e += 4) {
                 const float4 b4 = lds128f(smem_u32(my_bias + ch * CHUNK_COLS + e));
@@ -627,6 +745,13 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
             f[c16 * 8 + 4] += r2.x; f[c16 * 8 + 5] += r2.y; f[c16 * 8 + 6] += r3.x; f[c16 * 8 + 7] += r3.y;
           }
         }
+        if (ln_out && !geglu) {  // folded LayerNorm, producer side (host: n_store % 32 == 0, so every chunk is full)
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            ln_s1 += f[e];
+            ln_s2 = fmaf(f[e], f[e], ln_s2);
+          }
+        }
         if (!geglu) {
 #pragma unroll
           for (int c16 = 0; c16 < 4; ++c16) {
@@ -636,9 +761,29 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
             packed[c16 * 4 + 3] = pack_act2(f[c16 * 8 + 6], f[c16 * 8 + 7], of16);
           }
         }
+        if (has_dt && col0 >= args.dt_col0) {
+          // Staging = two [32 columns][64 rows] halves (4 KB each, one TMA store each), 128B-swizzled.  Lanes r, r ^ 1 exchange
+          // their packed pairs so that every lane writes whole 32-bit words {row r & ~1, row r | 1} of one column: the even lane
+          // column 2j, the odd lane column 2j' + 1 with j' = j ^ 2 - columns whose swizzle phases differ in bit 2, so the 32 words
+          // of a store instruction fall into 32 different banks.
+          const bool odd = (lane & 1) != 0;
+          const int t = r & 63;                                     // row within the half
+          const uint32_t half_base = smem_u32(sbuf) + (uint32_t)(r >> 6) * (CHUNK_BYTES / 2);
+          const uint32_t c16 = (uint32_t)(t >> 3), in16 = (uint32_t)((t & 6) * 2);  // 16-byte piece of the row, byte inside it (word-aligned)
 #pragma unroll
-        for (int c16 = 0; c16 < 4; ++c16)
-          sts128(smem_u32(my_row) + ((c16 ^ sw) << 4), make_uint4(packed[c16 * 4], packed[c16 * 4 + 1], packed[c16 * 4 + 2], packed[c16 * 4 + 3]));
+          for (int j = 0; j < 16; ++j) {
+            const uint32_t send = odd ? packed[j] : packed[j ^ 2];
+            const uint32_t got = __shfl_xor_sync(0xffffffffu, send, 1);
+            // even: {mine[j].lo, partner[j].lo} -> column 2j; odd: {partner[j^2].hi, mine[j^2].hi} -> column 2(j^2) + 1
+            const uint32_t word = odd ? __byte_perm(got, packed[j ^ 2], 0x7632) : __byte_perm(packed[j], got, 0x5410);
+            const uint32_t col = odd ? (uint32_t)(2 * (j ^ 2) + 1) : (uint32_t)(2 * j);
+            sts32(half_base + col * 128u + ((c16 ^ (col & 7u)) << 4) + in16, word);
+          }
+        } else {
+#pragma unroll
+          for (int c16 = 0; c16 < 4; ++c16)
+            sts128(smem_u32(my_row) + ((c16 ^ sw) << 4), make_uint4(packed[c16 * 4], packed[c16 * 4 + 1], packed[c16 * 4 + 2], packed[c16 * 4 + 3]));
+        }
         EPI_STAMP(4);
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
         EPI_STAMP(5);
@@ -650,9 +795,10 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
         }
         mbar_arrive(&chunk_ready[grp * STAGING_BUFS + buf]);  // the store warp issues the TMA store: nobody waits here
         EPI_STAMP(6);
-        if (t == cluster_id && grp == 0 && ch == c_lo && leader) CPD_STAMP(7);
+        if (t == t_begin && grp == 0 && ch == c_lo && leader) CPD_STAMP(7);
         EPI_STAMP(7);
       }
+      if (ln_out && rc.valid) args.ln_out[(int64_t)(n_tile * EPI_GROUPS + grp) * args.ln_ld + rc.row] = make_float2(ln_s1, ln_s2);
       if (c_lo == c_hi) {  // this group has no chunk in the tile (single-chunk tiles): still release the accumulator
         tc_fence_before();
         __syncwarp();
@@ -763,14 +909,27 @@ TileChoice pick_tiles(int m_tiles2, int n_out, int num_k, bool geglu, int geglu_
   return best;
 }
 
-template <int MC, bool OF16>
+template <int MC, bool OF16, int FEAT>
 cpd_status launch2(const Gemm2Args& args, int smem_bytes, cudaStream_t stream) {
-  CPD_SMEM_OPTIN((gemm2_kernel<MC, OF16>), 227 * 1024);
+  CPD_SMEM_OPTIN((gemm2_kernel<MC, OF16, FEAT>), 227 * 1024);
   const long steps = (long)args.m_tiles2 * (args.n_tiles / MC) * args.splits;
   const int max_clusters = MC == 2 ? 33 : NUM_SM_PAIRS;
   const int clusters = (int)(steps < max_clusters ? steps : max_clusters);
-  CPD_CUDA_CHECK(cpd_launch(gemm2_kernel<MC, OF16>, dim3(2 * MC * clusters), dim3(NUM_THREADS2), smem_bytes, stream, args));
+  CPD_CUDA_CHECK(cpd_launch(gemm2_kernel<MC, OF16, FEAT>, dim3(2 * MC * clusters), dim3(NUM_THREADS2), smem_bytes, stream, args));
   return CPD_OK;
+}
+template <bool OF16>
+cpd_status launch2_feat(const Gemm2Args& args, int feat, int smem_bytes, cudaStream_t stream) {
+  switch (feat) {
+    case 0: return launch2<1, OF16, 0>(args, smem_bytes, stream);
+    case FEAT_LN_IN: return launch2<1, OF16, FEAT_LN_IN>(args, smem_bytes, stream);
+    case FEAT_LN_OUT: return launch2<1, OF16, FEAT_LN_OUT>(args, smem_bytes, stream);
+    case FEAT_DT: return launch2<1, OF16, FEAT_DT>(args, smem_bytes, stream);
+    case FEAT_LN_IN | FEAT_DT: return launch2<1, OF16, FEAT_LN_IN | FEAT_DT>(args, smem_bytes, stream);
+    default: break;
+  }
+  cpd_set_error("cpd_gemm_conv: unsupported combination of folded-LayerNorm / transposed-tail options (%d)", feat);
+  return CPD_ERR_UNSUPPORTED;
 }
 
 }  // namespace
@@ -896,12 +1055,45 @@ cpd_status cpd_gemm_conv_2cta(const cpd_gemm_params* p, void* stream) {
     CPD_REQUIRE(g.n_store % 8 == 0 && splits <= args.num_k, "cpd_gemm_conv: bad split-K configuration (splits=%d, k-iterations=%d)",
                 splits, args.num_k);
   }
+  // LayerNorm folded into the GEMM / transposed tail (cpd_gemm_params.ln_*, d_t)
+  const bool ln_any = p->ln_sums_out != nullptr || p->ln_sums != nullptr;
+  CPD_REQUIRE(!(ln_any || p->d_t) || (splits == 1 && mc == 1), "cpd_gemm_conv: the folded LayerNorm / transposed tail need the plain pair kernel (no split-K, no multicast cluster)");
+  args.ln_in = reinterpret_cast<const float2*>(p->ln_sums);
+  args.ln_parts = p->ln_parts;
+  args.ln_ld = p->ln_ld;
+  args.ln_g = p->ln_g;
+  args.ln_inv_c = p->ln_c > 0 ? 1.0f / (float)p->ln_c : 0.f;
+  args.ln_eps = p->ln_eps;
+  args.ln_out = reinterpret_cast<float2*>(p->ln_sums_out);
+  if (p->ln_sums) {
+    CPD_REQUIRE(p->ln_g && p->bias && p->ln_parts > 0 && p->ln_c > 0 && p->ln_ld >= out_rows && g.n_store % 32 == 0 && p->n_out % 4 == 0 && !p->rowvec,
+                "cpd_gemm_conv: a folded-LayerNorm consumer needs ln_g, the folded bias, ln_parts / ln_c > 0, ln_ld >= rows, N %% 32 == 0 and no rowvec");
+  }
+  if (p->ln_sums_out) {
+    CPD_REQUIRE(!geglu && p->ln_ld >= out_rows && g.n_store % 32 == 0, "cpd_gemm_conv: a folded-LayerNorm producer needs a plain epilogue, ln_ld >= rows and N %% 32 == 0");
+    if (p->ln_parts_out) *p->ln_parts_out = args.n_tiles * EPI_GROUPS;
+  }
+  args.dt_col0 = -1;
+  args.map_dt = args.map_a0;
+  if (p->d_t) {
+    CPD_REQUIRE(!geglu && !p->residual && g.taps == 1 && g.nbox == 1 && g.h_out == 1 && g.n_img == 1 && g.tw == BM && p->dt_col0 % 32 == 0 &&
+                    p->dt_col0 >= 0 && p->dt_col0 < p->n_out && g.n_store % 32 == 0 && p->ldd_t >= out_rows && out_rows % 8 == 0,
+                "cpd_gemm_conv: the transposed tail needs a plain GEMM without residual, dt_col0 %% 32 == 0, rows %% 8 == 0 (the TMA store "
+                "clips in 16-byte pieces) and ldd_t >= rows");
+    uint64_t dims[2] = {(uint64_t)out_rows, (uint64_t)(p->n_out - p->dt_col0)};
+    uint64_t str[1] = {(uint64_t)p->ldd_t * 2};
+    uint32_t box[2] = {(uint32_t)(BM / 2), (uint32_t)CHUNK_COLS};  // 64 rows = 128 bytes: one 128B-swizzle span
+    rc = cpd_make_tmap16(&args.map_dt, p->d_t, 2, dims, str, box, 128);
+    if (rc) return rc;
+    args.dt_col0 = p->dt_col0;
+  }
   args.splits = splits;
   args.ws = p->splitk_ws;
   args.ws_slice = out_rows * g.n_store;
   {  // output / residual views (c, x, y, n), 64-byte swizzle, box = 32 columns x one pixel box
     const uint64_t rows_x = (uint64_t)((p->m_valid > 0 && g.h_out == 1 && g.n_img == 1) ? p->m_valid : g.w_out);
-    uint64_t dims[4] = {(uint64_t)g.n_store, rows_x, (uint64_t)g.h_out, (uint64_t)g.n_img};
+    // (with a transposed tail the columns from dt_col0 on never go through this map: d may be only dt_col0 columns wide)
+    uint64_t dims[4] = {(uint64_t)(p->d_t ? p->dt_col0 : g.n_store), rows_x, (uint64_t)g.h_out, (uint64_t)g.n_img};
     uint32_t box[4] = {(uint32_t)CHUNK_COLS, (uint32_t)g.tw, (uint32_t)g.th, (uint32_t)g.nb};
     uint64_t str[3] = {(uint64_t)p->ldd * 2, (uint64_t)g.w_out * p->ldd * 2, (uint64_t)g.h_out * g.w_out * p->ldd * 2};
     rc = cpd_make_tmap16(&args.map_d, p->d, 4, dims, str, box, 64);
@@ -918,11 +1110,12 @@ cpd_status cpd_gemm_conv_2cta(const cpd_gemm_params* p, void* stream) {
   const int smem_bytes = stages * args.stage_bytes + STAGING_BYTES + BIAS_BYTES + 512 + 1024;
   const bool of16 = p->out_fp16 != 0;
 #ifdef CPD_EXPERIMENTAL
-  if (mc == 2) return of16 ? launch2<2, true>(args, smem_bytes, (cudaStream_t)stream) : launch2<2, false>(args, smem_bytes, (cudaStream_t)stream);
+  if (mc == 2) return of16 ? launch2<2, true, 0>(args, smem_bytes, (cudaStream_t)stream) : launch2<2, false, 0>(args, smem_bytes, (cudaStream_t)stream);
 #else
   CPD_REQUIRE(mc == 1, "cpd_gemm_conv: the 4-CTA multicast cluster (variant 1000 + BN) is compiled only with -DCPD_EXPERIMENTAL");
 #endif
-  const cpd_status st = of16 ? launch2<1, true>(args, smem_bytes, (cudaStream_t)stream) : launch2<1, false>(args, smem_bytes, (cudaStream_t)stream);
+  const int feat = (p->ln_sums ? FEAT_LN_IN : 0) | (p->ln_sums_out ? FEAT_LN_OUT : 0) | (p->d_t ? FEAT_DT : 0);
+  const cpd_status st = of16 ? launch2_feat<true>(args, feat, smem_bytes, (cudaStream_t)stream) : launch2_feat<false>(args, feat, smem_bytes, (cudaStream_t)stream);
   if (st != CPD_OK || splits == 1) return st;
   const int64_t vecs = out_rows * (g.n_store / 8);
   int blocks = (int)((vecs + 255) / 256);

@@ -137,6 +137,51 @@ __global__ void __launch_bounds__(256) expand_images_kernel(const uint4* __restr
 }
 
 // ------------------------------------------------------------------------------------------------ host-side structures
+// LayerNorm folded into the weights of the GEMM that consumes it (cpd_gemm_params.ln_*): one block per output row n,
+//   wf[n][k] = round16(W[n][k] * gamma[k]),  g[n] = sum_k wf[n][k],  bf[n] = sum_k W[n][k] * beta[k] + bias[n]
+// (g from the ROUNDED wf, so that rstd * (x wf^T - mean * g) is exactly rstd * ((x - mean) wf^T)).  Fixed-order reduction.
+__global__ void __launch_bounds__(128) ln_fold_kernel(const uint16_t* __restrict__ w, int cols, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, const float* __restrict__ bias, int f16,
+                                                      uint16_t* __restrict__ wf, float* __restrict__ g, float* __restrict__ bf) {
+  const int n = blockIdx.x;
+  const uint16_t* wr = w + (int64_t)n * cols;
+  uint16_t* wo = wf + (int64_t)n * cols;
+  float gs = 0.f, bs = 0.f;
+  for (int k = threadIdx.x; k < cols; k += blockDim.x) {
+    const float wv = f16 ? __half2float(__ushort_as_half(wr[k])) : __bfloat162float(__ushort_as_bfloat16(wr[k]));
+    const float prod = wv * gamma[k];
+    uint16_t o;
+    float r;
+    if (f16) {
+      const __half h = __float2half_rn(prod);
+      o = __half_as_ushort(h);
+      r = __half2float(h);
+    } else {
+      const __nv_bfloat16 h = __float2bfloat16_rn(prod);
+      o = __bfloat16_as_ushort(h);
+      r = __bfloat162float(h);
+    }
+    wo[k] = o;
+    gs += r;
+    bs = fmaf(wv, beta[k], bs);
+  }
+  __shared__ float red[2][128];
+  red[0][threadIdx.x] = gs;
+  red[1][threadIdx.x] = bs;
+  __syncthreads();
+  for (int off = 64; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) {
+      red[0][threadIdx.x] += red[0][threadIdx.x + off];
+      red[1][threadIdx.x] += red[1][threadIdx.x + off];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    g[n] = red[0][0];
+    bf[n] = red[1][0] + (bias ? bias[n] : 0.f);
+  }
+}
+
 struct DevBuf {
   void* p = nullptr;
   int64_t numel = 0;
@@ -174,6 +219,12 @@ struct ProfRec {
   std::string label;
   double flops;
   cudaEvent_t e0, e1;
+};
+
+struct FoldJob {  // one ln_fold_kernel launch (buffer names in cpd_unet_plan::w)
+  std::string w, gamma, beta, bias, wf, g, bf;
+  int64_t rows = 0, dst_row0 = 0;
+  int cols = 0;
 };
 
 struct WeightSpec {
@@ -214,6 +265,11 @@ struct cpd_unet_plan {
   Tap tap_mid;
   DevBuf tune_scratch, splitk;
   cudaStream_t cap_stream = nullptr;
+  // LayerNorm folding (CPD_UNET_FOLD_LN=0: every LayerNorm as its own kernel, A/B measurements)
+  std::vector<FoldJob> folds;
+  bool fold_ln = true, fold_dirty = true;
+  int fold_geglu_min_ch = 640;
+  int64_t fold_min_rows = 2048;  // levels with fewer tokens keep the LayerNorm kernels (their GEMMs want split-K / one-tile variants)
   bool share_prefix = true;  // CPD_UNET_SHARE_PREFIX=0: evaluate every row through the whole network (A/B measurements)
   // profiling (eager launches bracketed by events)
   bool profile = false;
@@ -533,6 +589,22 @@ cpd_status build_specs(cpd_unet_plan* P) {
     }
     B.mat(b + "ff.net.2.weight", b + "ff2.w", ch, 4 * (int64_t)ch, act);
     B.vec(b + "ff.net.2.bias", b + "ff2.b", ch);
+    // folded copies (LayerNorm applied by the consumer GEMM's epilogue): filled by ensure_folded once the weights are loaded
+    auto fold = [&](const std::string& w, const char* norm, const std::string& bias, const std::string& dst, int64_t rows, int64_t row0,
+                    int64_t rows_total) {
+      B.dest(dst + ".wf", rows_total * ch, act);
+      B.dest(dst + ".g", rows_total, CPD_F32);
+      B.dest(dst + ".bf", rows_total, CPD_F32);
+      FoldJob j;
+      j.w = w; j.gamma = b + norm + ".g"; j.beta = b + norm + ".b"; j.bias = bias;
+      j.wf = dst + ".wf"; j.g = dst + ".g"; j.bf = dst + ".bf";
+      j.rows = rows; j.dst_row0 = row0; j.cols = ch;
+      P->folds.push_back(j);
+    };
+    fold(b + "attn1.qk.w", "norm1", "", b + "attn1.qkv", 2 * ip, 0, 3 * ip);   // fused Q | K | V projection of LN1(x)
+    fold(b + "attn1.v.w", "norm1", "", b + "attn1.qkv", ip, 2 * ip, 3 * ip);
+    fold(b + "attn2.q.w", "norm2", "", b + "attn2.q", ip, 0, ip);
+    fold(b + "ff1.w", "norm3", b + "ff1.b", b + "ff1", 8 * (int64_t)ch, 0, 8 * (int64_t)ch);
   };
   auto attn = [&](const std::string& p, int ch, int depth) {
     B.vec(p + "norm.weight", p + "norm.g", ch);
@@ -633,6 +705,17 @@ struct GemmOpt {
   const void* residual = nullptr;
   int ld_res = 0;
   int epilogue = CPD_EPI_NONE;
+  // folded LayerNorm (cpd_gemm_params.ln_*): producer side / consumer side; transposed tail
+  float* ln_out = nullptr;
+  int* ln_parts_out = nullptr;
+  const float* ln_in = nullptr;
+  int ln_parts = 0;
+  int64_t ln_ld = 0;
+  const float* ln_g = nullptr;
+  void* d_t = nullptr;
+  int dt_col0 = 0;
+  int64_t ldd_t = 0;
+  int ldd = 0;  // 0: n_out (n_out / 2 for GEGLU)
 };
 
 cpd_status ensure_scratch(cpd_unet_plan* P, int64_t bytes, cudaStream_t st) {
@@ -666,8 +749,19 @@ cpd_status gemm(cpd_unet_plan* P, cudaStream_t st, const void* a0, const void* w
   p.residual = o.residual;
   p.ld_res = o.ld_res;
   p.d = out;
-  p.ldd = o.epilogue == CPD_EPI_GEGLU ? n_out / 2 : n_out;
+  p.ldd = o.ldd ? o.ldd : (o.epilogue == CPD_EPI_GEGLU ? n_out / 2 : n_out);
   p.epilogue = o.epilogue;
+  p.ln_sums_out = o.ln_out;
+  p.ln_parts_out = o.ln_parts_out;
+  p.ln_sums = o.ln_in;
+  p.ln_parts = o.ln_parts;
+  p.ln_ld = o.ln_ld;
+  p.ln_g = o.ln_g;
+  p.ln_c = o.ksize * o.ksize * (c0 + o.c1);
+  p.ln_eps = 1e-5f;  // nn.LayerNorm default (attention.py:476-478)
+  p.d_t = o.d_t;
+  p.dt_col0 = o.dt_col0;
+  p.ldd_t = o.ldd_t;
   p.variant = 0;
   p.a_fp16 = p.b_fp16 = p.out_fp16 = P->cfg.act_fp16;
   p.geglu_block = o.epilogue == CPD_EPI_GEGLU ? GEGLU_BLOCK : 0;
@@ -728,7 +822,57 @@ struct FwdCtx {
   const float* emb_all;
   int emb_stride;
   double* stats;
+  // folded LayerNorm: per-row partial sums of the transformer's residual stream `tr.h`, written by the GEMM that produced it
+  // (ln_parts == 0: none - the next LayerNorm runs as its own kernel)
+  float* lnp = nullptr;
+  int ln_parts = 0;
+  int64_t ln_ld = 0;
 };
+
+// Folded copies of the weights behind LN1 / LN2 / LN3 (see ln_fold_kernel); after any cpd_pack_weights.
+cpd_status ensure_folded(cpd_unet_plan* P, cudaStream_t st) {
+  if (!P->fold_dirty) return CPD_OK;
+  for (const FoldJob& j : P->folds) {
+    const uint16_t* w = (const uint16_t*)W(P, j.w);
+    uint16_t* wf = (uint16_t*)W(P, j.wf);
+    float* g = (float*)W(P, j.g);
+    float* bf = (float*)W(P, j.bf);
+    CPD_REQUIRE(w && wf && g && bf && W(P, j.gamma) && W(P, j.beta), "cpd_unet_forward: folded-LayerNorm buffers of %s are missing", j.w.c_str());
+    ln_fold_kernel<<<(unsigned)j.rows, 128, 0, st>>>(w, j.cols, (const float*)W(P, j.gamma), (const float*)W(P, j.beta),
+                                                      j.bias.empty() ? nullptr : (const float*)W(P, j.bias), P->cfg.act_fp16,
+                                                      wf + j.dst_row0 * j.cols, g + j.dst_row0, bf + j.dst_row0);
+    CPD_CUDA_CHECK(cudaGetLastError());
+  }
+  P->fold_dirty = false;
+  return CPD_OK;
+}
+
+// The GEMM that writes the residual stream also emits its rows' partial sums when the level is large enough to fold.
+void ln_producer(FwdCtx& F, GemmOpt& g) {
+  F.ln_parts = 0;
+  if (!F.lnp) return;
+  g.ln_out = F.lnp;
+  g.ln_parts_out = &F.ln_parts;
+  g.ln_ld = F.ln_ld;
+}
+void ln_consumer(FwdCtx& F, GemmOpt& g, const float* gvec, const float* bias_folded) {
+  g.ln_in = F.lnp;
+  g.ln_parts = F.ln_parts;
+  g.ln_ld = F.ln_ld;
+  g.ln_g = gvec;
+  g.bias = bias_folded;
+}
+cpd_status ln_setup(FwdCtx& F, int64_t T, int ch) {
+  F.lnp = nullptr;
+  F.ln_parts = 0;
+  if (!F.P->fold_ln || T < F.P->fold_min_rows) return CPD_OK;
+  void* b;
+  const int64_t max_parts = 2 * ((ch + 63) / 64);  // narrowest tile the tuner may pick: 64 columns x two epilogue groups
+  PLAN_CHECK(ws_get(F.P, "tr.lnpart", max_parts * T * 2, 4, &b));
+  F.lnp = (float*)b;
+  F.ln_ld = T;
+  return CPD_OK;
+}
 
 cpd_status res_block(FwdCtx& F, const std::string& p, Act x0, Act x1, int cout, Act* outp) {
   cpd_unet_plan* P = F.P;
@@ -801,6 +945,8 @@ cpd_status attn_pre(FwdCtx& F, const std::string& p, Act x, void** hcur_out) {
   PLAN_CHECK(ws_get(P, "tr.h", D.T * D.ch, 2, &hcur));
   GemmOpt g;
   g.bias = (const float*)W(P, p + "proj_in.b");
+  PLAN_CHECK(ln_setup(F, D.T, D.ch));
+  ln_producer(F, g);
   PLAN_CHECK(gemm(P, F.st, gn, W(P, p + "proj_in.w"), hcur, 1, 1, (int)D.T, D.ch, D.ch, g));
   *hcur_out = hcur;
   return CPD_OK;
@@ -814,18 +960,31 @@ cpd_status tblock_self(FwdCtx& F, const std::string& b, void* hcur, int ch) {
   const int64_t T = D.T;
   const int ip = D.ip;
   void *ln, *qk, *vt, *o;
-  PLAN_CHECK(ws_get(P, "tr.ln", T * ch, 2, &ln));
-  PLAN_CHECK(layernorm(P, F.st, hcur, (int)T, ch, b + "norm1.g", b + "norm1.b", ln));
   PLAN_CHECK(ws_get(P, "tr.qk", T * 2 * ip, 2, &qk));
-  PLAN_CHECK(gemm(P, F.st, ln, W(P, b + "attn1.qk.w"), qk, 1, 1, (int)T, ch, 2 * ip));
   PLAN_CHECK(ws_get(P, "tr.vt", (int64_t)ip * T, 2, &vt));
-  PLAN_CHECK(gemm(P, F.st, W(P, b + "attn1.v.w"), ln, vt, 1, 1, ip, ch, (int)T));  // V^T = Wv LN(x)^T
+  if (F.ln_parts > 0 && T % 8 == 0) {
+    // ONE projection Q | K | V of the raw residual stream: LN1 is applied by the epilogue (folded weights), the V columns leave
+    // transposed (V^T [ip][T] is the attention kernels' operand) - no LayerNorm kernel, no second (transposed) GEMM
+    GemmOpt g;
+    ln_consumer(F, g, (const float*)W(P, b + "attn1.qkv.g"), (const float*)W(P, b + "attn1.qkv.bf"));
+    g.ldd = 2 * ip;
+    g.d_t = vt;
+    g.dt_col0 = 2 * ip;
+    g.ldd_t = T;
+    PLAN_CHECK(gemm(P, F.st, hcur, W(P, b + "attn1.qkv.wf"), qk, 1, 1, (int)T, ch, 3 * ip, g));
+  } else {
+    PLAN_CHECK(ws_get(P, "tr.ln", T * ch, 2, &ln));
+    PLAN_CHECK(layernorm(P, F.st, hcur, (int)T, ch, b + "norm1.g", b + "norm1.b", ln));
+    PLAN_CHECK(gemm(P, F.st, ln, W(P, b + "attn1.qk.w"), qk, 1, 1, (int)T, ch, 2 * ip));
+    PLAN_CHECK(gemm(P, F.st, W(P, b + "attn1.v.w"), ln, vt, 1, 1, ip, ch, (int)T));  // V^T = Wv LN(x)^T
+  }
   PLAN_CHECK(ws_get(P, "tr.o", T * ip, 2, &o));
   PLAN_CHECK(attention(P, F.st, qk, 2 * ip, (const uint16_t*)qk + ip, 2 * ip, vt, (int)T, o, ip, F.R, D.nh, D.hw, D.hw, D.hw, D.dpad, D.dh, 0));
   GemmOpt g;
   g.bias = (const float*)W(P, b + "attn1.out.b");
   g.residual = hcur;
   g.ld_res = ch;
+  ln_producer(F, g);  // LN2 reads these rows next
   return gemm(P, F.st, o, W(P, b + "attn1.out.w"), hcur, 1, 1, (int)T, ip, ch, g);
 }
 
@@ -842,20 +1001,34 @@ cpd_status tblock_rest(FwdCtx& F, const std::string& b, void* hcur, int ch) {
   PLAN_CHECK(ws_get(P, "tr.o", T * ip, 2, &o));
   PLAN_CHECK(ws_get(P, b + "kc", (int64_t)P->rc * P->nk_pad * ip, 2, &kc));
   PLAN_CHECK(ws_get(P, b + "vt", (int64_t)ip * P->rc * P->nk_pad, 2, &vtc));
-  PLAN_CHECK(layernorm(P, F.st, hcur, (int)T, ch, b + "norm2.g", b + "norm2.b", ln));
   PLAN_CHECK(ws_get(P, "tr.q2", T * ip, 2, &q2));
-  PLAN_CHECK(gemm(P, F.st, ln, W(P, b + "attn2.q.w"), q2, 1, 1, (int)T, ch, ip));
+  if (F.ln_parts > 0) {
+    GemmOpt g;
+    ln_consumer(F, g, (const float*)W(P, b + "attn2.q.g"), (const float*)W(P, b + "attn2.q.bf"));
+    PLAN_CHECK(gemm(P, F.st, hcur, W(P, b + "attn2.q.wf"), q2, 1, 1, (int)T, ch, ip, g));
+  } else {
+    PLAN_CHECK(layernorm(P, F.st, hcur, (int)T, ch, b + "norm2.g", b + "norm2.b", ln));
+    PLAN_CHECK(gemm(P, F.st, ln, W(P, b + "attn2.q.w"), q2, 1, 1, (int)T, ch, ip));
+  }
   PLAN_CHECK(attention(P, F.st, q2, ip, kc, ip, vtc, P->rc * P->nk_pad, o, ip, F.R, D.nh, D.hw, P->ntok, P->nk_pad, D.dpad, D.dh, P->rc));
   {
     GemmOpt g;
     g.bias = (const float*)W(P, b + "attn2.out.b");
     g.residual = hcur;
     g.ld_res = ch;
+    ln_producer(F, g);  // LN3 reads these rows next
     PLAN_CHECK(gemm(P, F.st, o, W(P, b + "attn2.out.w"), hcur, 1, 1, (int)T, ip, ch, g));
   }
-  PLAN_CHECK(layernorm(P, F.st, hcur, (int)T, ch, b + "norm3.g", b + "norm3.b", ln));
   PLAN_CHECK(ws_get(P, "tr.ff", T * 4 * ch, 2, &ff));
-  {
+  // (the GEGLU epilogue is the busy stage of ff1 when K = ch is small: at 320 channels the two extra FMAs per element cost
+  // more (65536 x 2560 x 320: 130 -> 164 us) than the LayerNorm kernel they replace (20 us))
+  if (F.ln_parts > 0 && ch >= P->fold_geglu_min_ch) {
+    GemmOpt g;
+    ln_consumer(F, g, (const float*)W(P, b + "ff1.g"), (const float*)W(P, b + "ff1.bf"));
+    g.epilogue = CPD_EPI_GEGLU;
+    PLAN_CHECK(gemm(P, F.st, hcur, W(P, b + "ff1.wf"), ff, 1, 1, (int)T, ch, 8 * ch, g));
+  } else {
+    PLAN_CHECK(layernorm(P, F.st, hcur, (int)T, ch, b + "norm3.g", b + "norm3.b", ln));
     GemmOpt g;
     g.bias = (const float*)W(P, b + "ff1.b");
     g.epilogue = CPD_EPI_GEGLU;
@@ -865,6 +1038,7 @@ cpd_status tblock_rest(FwdCtx& F, const std::string& b, void* hcur, int ch) {
   g.bias = (const float*)W(P, b + "ff2.b");
   g.residual = hcur;
   g.ld_res = ch;
+  ln_producer(F, g);  // LN1 of the next transformer block of this SpatialTransformer (depth > 1), if any
   return gemm(P, F.st, ff, W(P, b + "ff2.w"), hcur, 1, 1, (int)T, 4 * ch, ch, g);
 }
 
@@ -1069,6 +1243,7 @@ cpd_status forward_impl(cpd_unet_plan* P, const cpd_unet_io* io, void* eps_out, 
     PLAN_CHECK(ws_get(P, "tr.h", (int64_t)R * hw * cout, 2, &hr));
     PLAN_CHECK(expand_images(P, st, hb, hr, B, rpi, hw * cout));
     xres = Act{xr, cout};
+    PLAN_CHECK(ln_setup(F, (int64_t)R * hw, cout));  // the expanded rows carry no statistics: LN2 of this block runs as a kernel
     PLAN_CHECK(tblock_rest(F, b0, hr, cout));
     for (int d = 1; d < depth; ++d) {
       const std::string bd = pa + "transformer_blocks." + std::to_string(d) + ".";
@@ -1145,6 +1320,12 @@ extern "C" cpd_status cpd_unet_plan_create(const cpd_unet_config* cfg, cpd_unet_
   {
     const char* e = getenv("CPD_UNET_SHARE_PREFIX");
     P->share_prefix = !(e && e[0] == '0');
+    e = getenv("CPD_UNET_FOLD_LN");
+    P->fold_ln = !(e && e[0] == '0');
+    e = getenv("CPD_UNET_FOLD_MIN_ROWS");
+    if (e && atoll(e) > 0) P->fold_min_rows = atoll(e);
+    e = getenv("CPD_UNET_FOLD_GEGLU_MIN_CH");
+    if (e && atoi(e) > 0) P->fold_geglu_min_ch = atoi(e);
   }
   enumerate_blocks(P);
   cpd_status st = build_specs(P);
@@ -1212,6 +1393,7 @@ extern "C" cpd_status cpd_pack_weights(cpd_unet_plan* P, const char* name, const
     return rc;
   }
   s.loaded = true;
+  P->fold_dirty = true;
   // the packed weights changed: captured graphs stay valid (same addresses), the context cache does not (its K / V^T were
   // computed from the old to_k / to_v)
   if (strstr(name, "attn2.to_k") || strstr(name, "attn2.to_v")) P->have_ctx = false;
@@ -1309,6 +1491,10 @@ extern "C" cpd_status cpd_unet_forward(cpd_unet_plan* P, const cpd_unet_io* io, 
   cudaStream_t st = (cudaStream_t)stream;
   P->launches = 0;
   const bool outer_capture = stream_capturing(st);
+  if (P->fold_dirty) {
+    CPD_REQUIRE(!outer_capture, "cpd_unet_forward: the first evaluation after cpd_pack_weights must not run inside a stream capture");
+    PLAN_CHECK(ensure_folded(P, st));
+  }
   const bool inject = io->inject_skips != nullptr || io->inject_feats != nullptr;
   void* eps = io->eps;
   P->allow_alloc = !outer_capture;

@@ -223,8 +223,12 @@ def gemm_tune_import(text):
 
 
 def gemm_conv(a0, wt, out, *, n_img, h, w, c0, n_out, a1=None, c1=0, ksize=1, stride=1, bias=None, rowvec=None,
-              rowvec_stride=0, residual=None, ld_res=0, ldd=None, epilogue=CPD_EPI_NONE, variant=0, m_valid=0, geglu_block=128):
-    """a0/a1 and wt are 16-bit (fp16 or bf16, independently); out/residual share one 16-bit dtype."""
+              rowvec_stride=0, residual=None, ld_res=0, ldd=None, epilogue=CPD_EPI_NONE, variant=0, m_valid=0, geglu_block=128,
+              ln_sums_out=None, ln_sums=None, ln_parts=0, ln_g=None, ln_eps=1e-5, d_t=None, dt_col0=0):
+    """a0/a1 and wt are 16-bit (fp16 or bf16, independently); out/residual share one 16-bit dtype.
+    Folded LayerNorm (cpd_gemm_params.ln_*): a producer passes ln_sums_out = fp32 [max_parts, rows, 2] and gets (out, number of
+    parts written) back; a consumer passes ln_sums, ln_parts,
+    ln_g (and wt = gamma . W, bias = W beta + b).  d_t [n_out - dt_col0, rows]: columns from dt_col0 on are stored transposed."""
     a_f16 = _act(a0, "a0")
     _act(a1, "a1", like=a0.dtype)
     b_f16 = _act(wt, "wt")
@@ -252,11 +256,25 @@ def gemm_conv(a0, wt, out, *, n_img, h, w, c0, n_out, a1=None, c1=0, ksize=1, st
         sc = _tune_scratch(out.device, out.numel() * out.element_size())
         if sc is not None:
             p.tune_scratch, p.tune_scratch_bytes = sc.data_ptr(), sc.numel()
+    parts_out = C.c_int(0)
+    if ln_sums_out is not None:
+        _req(ln_sums_out, torch.float32, "ln_sums_out")
+        p.ln_sums_out, p.ln_parts_out, p.ln_ld = ln_sums_out.data_ptr(), C.pointer(parts_out), ln_sums_out.shape[1]
+    if ln_sums is not None:
+        _req(ln_sums, torch.float32, "ln_sums")
+        _req(ln_g, torch.float32, "ln_g")
+        p.ln_sums, p.ln_parts, p.ln_ld, p.ln_g = ln_sums.data_ptr(), ln_parts, ln_sums.shape[1], ln_g.data_ptr()
+        p.ln_c, p.ln_eps = ksize * ksize * (c0 + c1), ln_eps
+    if d_t is not None:
+        _act(d_t, "d_t", like=out.dtype)
+        p.d_t, p.dt_col0, p.ldd_t = d_t.data_ptr(), dt_col0, d_t.shape[1]
     flops = 2.0 * n_img * (h // stride) * (w // stride) * n_out * ksize * ksize * (c0 + c1)
     label = f"M={n_img * (h // stride) * (w // stride)} N={n_out} K={ksize * ksize * (c0 + c1)}" + (" geglu" if epilogue else "")
     with _Prof("gemm_conv", flops, label):
         check(load().cpd_gemm_conv(C.byref(p), stream_ptr()), "cpd_gemm_conv")
     _count()
+    if ln_sums_out is not None:
+        return out, parts_out.value
     return out
 
 

@@ -231,6 +231,26 @@ typedef struct {
   void* tune_scratch;       /* optional scratch the size of d: with variant 0 an unseen problem shape is first TIMED on every */
   int64_t tune_scratch_bytes; /* applicable tile variant (output redirected here, CUDA events, synchronous) and the fastest is */
                             /* remembered per shape; NULL = no timing (tuned table if the shape is known, else the cost model) */
+  /* --- LayerNorm folded into the neighbouring GEMMs (attention.py:476-490: x + attn(norm(x)), x + ff(norm(x))) ---------------
+   * LN is affine per row, so LN(x) W^T + b = rstd_m * (x (gamma . W)^T - mean_m * g) + (W beta + b) with g[n] = sum_k (gamma . W)[n][k]:
+   * the CONSUMER GEMM runs on the raw residual stream with pre-scaled weights and applies the per-row scale / shift in its
+   * epilogue; the PRODUCER GEMM that wrote the residual stream emits per-row partial (sum, sum of squares) of its output, one
+   * float2 per (column tile, epilogue group) and row, laid out [part][ln_ld] (rows contiguous: coalesced), summed by the consumer
+   * in a fixed order.  Pair kernel only (no split-K, no one-tile variants); n_out % 32 == 0 for a producer. */
+  float* ln_sums_out;       /* producer: float2 [parts][ln_ld] or NULL */
+  int* ln_parts_out;        /* producer: HOST int that receives the number of parts this launch writes */
+  const float* ln_sums;     /* consumer: the producer's partials, or NULL */
+  int ln_parts;             /* consumer: number of parts to sum */
+  int64_t ln_ld;            /* rows per part (>= output rows), both sides */
+  const float* ln_g;        /* consumer: fp32 [n_out], row sums of the folded weights (wt = gamma . W; bias = W beta + b is required) */
+  int ln_c;                 /* consumer: normalised channels (the K of the GEMM) */
+  float ln_eps;
+  /* --- transposed tail: columns [dt_col0, n_out) of D are stored TRANSPOSED into d_t[(n - dt_col0)][m] (leading dimension ldd_t
+   * elements, m = output row) instead of d: the V^T operand of the self-attention comes out of the fused Q | K | V projection.
+   * Plain GEMMs (ksize 1, n_img = h_in = 1) on the pair kernel only; dt_col0 % 32 == 0.  NULL = off. */
+  void* d_t;
+  int dt_col0;
+  int64_t ldd_t;
 } cpd_gemm_params;
 
 cpd_status cpd_gemm_conv(const cpd_gemm_params* p, void* stream);

@@ -100,6 +100,81 @@ def test_gemm_geglu(ops, M, C, block, variant):
     assert r < 6e-3
 
 
+def _ln_fold_operands(g, K, N, act):
+    """LayerNorm parameters and a projection, plus the folded forms the consumer GEMM takes (unet_plan.cu: ln_fold_kernel)."""
+    gamma = bf(1.0 + 0.3 * torch.randn(K, generator=g)).float()
+    beta = bf(0.2 * torch.randn(K, generator=g)).float()
+    w = bf(torch.randn(N, K, generator=g) / math.sqrt(K)).float()
+    b = bf(0.1 * torch.randn(N, generator=g)).float()
+    wf = (w * gamma).to(act)
+    return gamma, beta, w, b, wf, wf.float().sum(1), w @ beta + b
+
+
+@pytest.mark.parametrize("M,K,N,pv,cv,act", [(4096, 320, 384, 0, 0, torch.float16), (65536, 320, 1152, 160, 192, torch.float16),
+                                             (5000, 640, 1920, 2160, 128, torch.float16), (4096, 1280, 3840, 64, 256, torch.bfloat16),
+                                             (16384, 640, 640, 2128, 2160, torch.float16), (304, 320, 320, 96, 0, torch.float16),
+                                             (128, 320, 320, 160, 2160, torch.float16), (640, 320, 1152, 0, 160, torch.float16)])
+def test_gemm_folded_layernorm_and_transposed_tail(ops, M, K, N, pv, cv, act):
+    """x = a W0^T + b0 + res (producer, emits the rows' partial sums); then LN(x) W^T + b through the folded consumer:
+    rstd * (x (gamma . W)^T - mean * g) + (W beta + b), its last third stored transposed (the fused Q | K | V projection of
+    attention.py:476-487).  Reference: torch LayerNorm on the stored x."""
+    g = torch.Generator().manual_seed(M + K + N)
+    a = torch.randn(M, K, generator=g).to(act).to(DEV)
+    w0 = (torch.randn(K, K, generator=g) / math.sqrt(K)).to(act).to(DEV)
+    b0 = torch.randn(K, generator=g).to(DEV)
+    res = (2.0 * torch.randn(M, K, generator=g) + 0.7).to(act).to(DEV)  # non-zero row means
+    x = torch.full((M, K), float("nan"), dtype=act, device=DEV)
+    max_parts = 2 * ((K + 63) // 64)
+    sums = torch.full((max_parts, M + 8, 2), float("nan"), device=DEV)
+    _, parts = ops.gemm_conv(a, w0, x, n_img=1, h=1, w=M, c0=K, n_out=K, bias=b0, residual=res, ld_res=K, variant=pv, ln_sums_out=sums)
+    torch.cuda.synchronize()
+    assert 0 < parts <= max_parts
+    xf = x.float()
+    s = sums[:parts, :M].sum(0)
+    assert rel(s[:, 0], xf.sum(1)) < 2e-3 and rel(s[:, 1], (xf * xf).sum(1)) < 2e-3
+    gamma, beta, w, b, wf, gvec, bfold = _ln_fold_operands(g, K, N, act)
+    ref = F.layer_norm(xf, (K,), gamma.to(DEV), beta.to(DEV), 1e-5) @ w.to(DEV).t() + b.to(DEV)
+    n_t = N // 3 // 32 * 32
+    out = torch.full((M, N - n_t), float("nan"), dtype=act, device=DEV)
+    out_t = torch.full((n_t, (M + 15) // 8 * 8), float("nan"), dtype=act, device=DEV)
+    ops.gemm_conv(x, wf.to(DEV), out, n_img=1, h=1, w=M, c0=K, n_out=N, ldd=N - n_t, bias=bfold.to(DEV), variant=cv, ln_sums=sums,
+                  ln_parts=parts, ln_g=gvec.to(DEV), d_t=out_t, dt_col0=N - n_t)
+    torch.cuda.synchronize()
+    r0, r1 = rel(out, ref[:, :N - n_t]), rel(out_t[:, :M].t(), ref[:, N - n_t:])
+    print(f"folded LN {M}x{N}x{K} producer v{pv} ({parts} parts) consumer v{cv}: rel {r0:.3e}, transposed tail {r1:.3e}")
+    assert torch.isnan(out_t[:, M:].float()).all()  # nothing written beyond the valid rows
+    tol = 2e-2 if act == torch.bfloat16 else 4e-3
+    assert r0 < tol and r1 < tol
+
+
+@pytest.mark.parametrize("M,C", [(4096, 320), (16384, 640)])
+def test_gemm_geglu_folded_layernorm(ops, M, C):
+    g = torch.Generator().manual_seed(M + C)
+    act = torch.float16
+    x = (1.5 * torch.randn(M, C, generator=g) - 0.4).to(act).to(DEV)
+    xf = x.float()
+    parts = 3
+    sums = torch.zeros(parts, M, 2, device=DEV)  # the producer's layout: any split of the row sums over the parts
+    cuts = [0, 96, 224, C]
+    for i in range(parts):
+        sums[i, :, 0] = xf[:, cuts[i]:cuts[i + 1]].sum(1)
+        sums[i, :, 1] = (xf[:, cuts[i]:cuts[i + 1]] ** 2).sum(1)
+    gamma, beta, w, b, wf, gvec, bfold = _ln_fold_operands(g, C, 8 * C, act)
+    inner4, hb = 4 * C, 128
+
+    def inter(t):  # [128 value rows | 128 gate rows] per 256-column tile
+        return torch.cat([t[:inner4].reshape(-1, hb, *t.shape[1:]), t[inner4:].reshape(-1, hb, *t.shape[1:])], dim=1).reshape(t.shape).contiguous()
+    out = torch.empty(M, inner4, dtype=act, device=DEV)
+    ops.gemm_conv(x, inter(wf).to(DEV), out, n_img=1, h=1, w=M, c0=C, n_out=8 * C, bias=inter(bfold).to(DEV), epilogue=ops.CPD_EPI_GEGLU,
+                  geglu_block=256, ln_sums=sums, ln_parts=parts, ln_g=inter(gvec).to(DEV))
+    torch.cuda.synchronize()
+    y = F.layer_norm(xf, (C,), gamma.to(DEV), beta.to(DEV), 1e-5) @ w.to(DEV).t() + b.to(DEV)
+    ref = y[:, :inner4] * F.gelu(y[:, inner4:])
+    r = rel(out, ref)
+    print(f"geglu + folded LN M{M} C{C}: rel {r:.3e}")
+    assert r < 4e-3
+
+
 @pytest.mark.parametrize("n,h,w,c0,c1,cout,stride,variant", [
     (2, 16, 16, 64, 0, 128, 1, 1), (1, 64, 64, 320, 0, 320, 1, 0), (3, 8, 8, 128, 64, 256, 1, 2), (2, 32, 32, 64, 0, 64, 2, 1),
     (4, 8, 8, 1280, 1280, 1280, 1, 0), (2, 16, 16, 128, 0, 128, 2, 2), (1, 24, 24, 64, 0, 64, 1, 1), (2, 12, 12, 64, 64, 128, 1, 1),

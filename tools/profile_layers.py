@@ -47,16 +47,16 @@ def main():
         torch.cuda.profiler.stop()
         return
     agg = collections.OrderedDict()
+    unet.profile(True)  # plan-level records: eager launches bracketed by CUDA events inside cpd_unet_forward
     for _ in range(a.reps):
-        ops.PROFILE = []
         unet.forward_rows(x, 0.5, 500.0, a.rows)
         torch.cuda.synchronize()
-        prof, ops.PROFILE = ops.PROFILE, None
-        for kind, s, e, fl, label in prof:
-            d = agg.setdefault((kind, label), [0, 0.0, 0.0])
-            d[0] += 1
-            d[1] += s.elapsed_time(e)
-            d[2] += fl
+    for kind, label, us, fl in unet.profile_records():
+        d = agg.setdefault((kind, label), [0, 0.0, 0.0])
+        d[0] += 1
+        d[1] += us / 1e3
+        d[2] += fl
+    unet.profile(False)
     tot = sum(v[1] for v in agg.values()) / a.reps
     print(f"sum of per-launch event times: {tot:.3f} ms")
     kinds = collections.defaultdict(float)

@@ -63,7 +63,7 @@ class GemmParams(C.Structure):
         ("tune_scratch", C.c_void_p), ("tune_scratch_bytes", C.c_int64),
         ("ln_sums_out", C.c_void_p), ("ln_parts_out", C.POINTER(C.c_int)), ("ln_sums", C.c_void_p), ("ln_parts", C.c_int),
         ("ln_ld", C.c_int64), ("ln_g", C.c_void_p), ("ln_c", C.c_int), ("ln_eps", C.c_float),
-        ("d_t", C.c_void_p), ("dt_col0", C.c_int), ("ldd_t", C.c_int64),
+        ("d_t", C.c_void_p), ("dt_col0", C.c_int), ("ldd_t", C.c_int64), ("gn_sums_out", C.c_void_p),
     ]
 
 
@@ -109,6 +109,8 @@ _SIGS = {
     "cpd_gemm_conv": (C.c_int, [C.POINTER(GemmParams), C.c_void_p]),
     "cpd_groupnorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                 C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cpd_groupnorm_apply": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     "cpd_layernorm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p,
                                 C.c_void_p]),
     "cpd_timestep_embedding": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

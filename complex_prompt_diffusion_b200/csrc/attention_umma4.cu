@@ -33,6 +33,30 @@ constexpr int ISSUER1_WARP = 2 + 2 * SPLIT * 4;
 constexpr int MAX_STAGES = 4;
 constexpr float RESCALE_TAU = 8.0f;    // lazy O rescale threshold (log2 domain)
 
+#ifdef CPD_TIMELINE
+// Debug build (make TIMELINE=1): CTA 0 stamps clock64 at the phases of key blocks 8..15 (tools/attn4_timeline.py):
+// softmax warps [tile][half][block][phase] (lane 0 of lane quarter 0), issuer warps [tile][block][phase]
+__device__ long long cpd_dbg_attn4[2][2][8][8];
+__device__ long long cpd_dbg_mma4[2][8][8];
+#define A4_STAMP(ph)                                                                                              \
+  do {                                                                                                            \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && qd == 0 && lane == 0 && j >= 8 && j < 16)       \
+      cpd_dbg_attn4[t][hf][j - 8][ph] = clock64();                                                                \
+  } while (0)
+#define M4_STAMP(ph)                                                                                              \
+  do {                                                                                                            \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && j >= 8 && j < 16)                   \
+      cpd_dbg_mma4[t][j - 8][ph] = clock64();                                                                     \
+  } while (0)
+#else
+#define A4_STAMP(ph) \
+  do {               \
+  } while (0)
+#define M4_STAMP(ph) \
+  do {               \
+  } while (0)
+#endif
+
 struct Attn4Args {
   CUtensorMap map_q, map_k, map_vt;
   bf16* o;
@@ -226,15 +250,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention4_kernel(const __grid
         st_n = 0;
         ph_n ^= 1;
       }
+      M4_STAMP(0);
       if (sep && j + 1 < nblk) {  // S_t(j+1) as soon as both halves of S_t(j) sit in registers
         mbar_wait(&s_free[t], (uint32_t)(j & 1), 25);
+        M4_STAMP(1);
         mbar_wait(&k_full[st_n], ph_n, 20);
         tc_fence_after();
         issue_s(st_n);
+        M4_STAMP(2);
       }
       mbar_wait(&v_full[st], ph, 23);
       mbar_wait(&p_full[t], (uint32_t)(j & 1), 22);
       tc_fence_after();
+      M4_STAMP(3);
       if (elect_one()) {
         const int kv_valid = min(BKV, a.nk - j * BKV);
         const int ksteps_o = (kv_valid + 15) / 16;
@@ -247,6 +275,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention4_kernel(const __grid
         umma_commit(&v_empty[st]);
       }
       __syncwarp();
+      M4_STAMP(4);
       if (!sep && j + 1 < nblk) {  // aliased: S_t(j+1) overwrites P_t(j), so it follows P V_t(j) on the in-order tensor pipe
         mbar_wait(&k_full[st_n], ph_n, 20);
         tc_fence_after();
@@ -272,12 +301,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention4_kernel(const __grid
     float m_used = -INFINITY;
     for (int j = 0; j < nblk; ++j) {
       const int kv_valid = min(BKV, a.nk - j * BKV);
+      A4_STAMP(0);
       mbar_wait(&s_full[t], (uint32_t)(j & 1), 30);
       tc_fence_after();
+      A4_STAMP(1);
       uint32_t s[CW];
       tmem_ld32(tS + col0, reinterpret_cast<uint32_t(&)[32]>(s[0]));
       tmem_ld32(tS + col0 + 32, reinterpret_cast<uint32_t(&)[32]>(s[32]));
       tmem_ld_wait();
+      A4_STAMP(2);
       if (sep) {  // this half of the S row now lives in registers: once both halves do, the tensor pipe may write S_t(j+1)
         tc_fence_before();
         mbar_arrive(&s_free[t]);
@@ -307,6 +339,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention4_kernel(const __grid
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(slot + (hf ^ 1) * 512) : "memory");
         mx = fmaxf(mx, other);
       }
+      A4_STAMP(3);
       const float m_blk = mx * a.scale_log2;
       float alpha = 1.0f;
       bool need = false;
@@ -354,14 +387,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention4_kernel(const __grid
           s[e >> 1] = pack_act2(p0, p1, f16);
         }
       }
+      A4_STAMP(4);
       if (!pv_waited) {
         mbar_wait(&pv_done[t], (uint32_t)((j - 1) & 1), 31);
         tc_fence_after();
       }
+      A4_STAMP(5);
       tmem_st32_4(tP + hf * (CW / 2), &s[0]);  // 16-bit P: two elements per TMEM column
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[t]);
+      A4_STAMP(6);
     }
     // ---- epilogue: O / l -> global (l = O[:, d], accumulated by the ones row of V^T) ----
     mbar_wait(&pv_done[t], (uint32_t)((nblk - 1) & 1), 32);
@@ -405,6 +441,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attention4_kernel(const __grid
 }
 
 }  // namespace
+
+#ifdef CPD_TIMELINE
+extern "C" int cpd_debug_attn4_timeline(long long* soft256, long long* mma128) {
+  int rc = (int)cudaMemcpyFromSymbol(soft256, cpd_dbg_attn4, sizeof(long long) * 256);
+  if (rc) return rc;
+  return (int)cudaMemcpyFromSymbol(mma128, cpd_dbg_mma4, sizeof(long long) * 128);
+}
+#endif
 
 // Returns CPD_ERR_UNSUPPORTED when the shape is outside this kernel's domain (the caller falls back).
 cpd_status cpd_attention_split(const cpd_attn_params* p, void* stream) {

@@ -400,7 +400,8 @@ int make_b_map(const cpd_gemm_params* p, int taps, int box_rows, CUtensorMap* ma
 // 1-CTA tiles (variant 1: 128 x 128, variant 2: 128 x 256), one tile per CTA.  Kept as the simple baseline the
 // persistent CTA-pair kernel (gemm_umma2.cu) is checked against; variant 0 (auto) dispatches to the pair kernel.
 static cpd_status gemm_conv_1cta(const cpd_gemm_params* p, void* stream) {
-  CPD_REQUIRE(!p->ln_sums && !p->ln_sums_out && !p->d_t, "cpd_gemm_conv: the one-tile kernels (variants 1, 2) have neither the folded LayerNorm nor the transposed tail");
+  CPD_REQUIRE(!p->ln_sums && !p->ln_sums_out && !p->d_t && !p->gn_sums_out,
+              "cpd_gemm_conv: the one-tile kernels (variants 1, 2) have neither the folded LayerNorm, the transposed tail nor the GroupNorm statistics");
   GemmArgs args;
   ConvGeom& g = args.g;
   int m_tiles = 0;

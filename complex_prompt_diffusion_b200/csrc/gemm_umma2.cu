@@ -113,6 +113,7 @@ struct Gemm2Args {
   // transposed tail: chunks whose first column is >= dt_col0 go to d_t through map_dt (128 rows x 32 columns -> 32 x 128)
   CUtensorMap map_dt;
   int dt_col0;      // < 0: off
+  long long* gn_out;  // [n_img][n_out][2] fixed-point sum / sum of squares of D (cpd_gemm_params.gn_sums_out)
 };
 
 // MC = 1: cluster = one CTA pair.  MC = 2: cluster = two CTA pairs working on the same 256 rows and adjacent column
@@ -121,12 +122,14 @@ struct Gemm2Args {
 // OF16: the element type of D / the residual (fp16 or bf16) as a compile-time constant - with a runtime flag every F2FP of
 // the epilogue was emitted twice under complementary predicates.
 // FEAT: epilogue features as compile-time bits (the plain instantiation must not pay for them: with runtime flags the
-// epilogue-bound K = 320 linears lost 17 %): 1 = folded-LayerNorm consumer, 2 = folded-LayerNorm producer, 4 = transposed tail.
-constexpr int FEAT_LN_IN = 1, FEAT_LN_OUT = 2, FEAT_DT = 4;
+// epilogue-bound K = 320 linears lost 17 %): 1 = folded-LayerNorm consumer, 2 = folded-LayerNorm producer, 4 = transposed tail,
+// 8 = GroupNorm statistics of D (per image and channel, fixed-point integer atomics).
+constexpr int FEAT_LN_IN = 1, FEAT_LN_OUT = 2, FEAT_DT = 4, FEAT_GN_OUT = 8;
 template <int MC, bool OF16, int FEAT>
 __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
     gemm2_kernel(const __grid_constant__ Gemm2Args args) {
   constexpr bool ln_in = (FEAT & FEAT_LN_IN) != 0, ln_out = (FEAT & FEAT_LN_OUT) != 0, has_dt = (FEAT & FEAT_DT) != 0;
+  constexpr bool gn_out = (FEAT & FEAT_GN_OUT) != 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stages = args.stages;
@@ -761,6 +764,35 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
             packed[c16 * 4 + 3] = pack_act2(f[c16 * 8 + 6], f[c16 * 8 + 7], of16);
           }
         }
+        if (gn_out && !geglu && col0 + CHUNK_COLS <= g.n_store) {
+          // GroupNorm statistics of this chunk: the warp's 32 rows x 32 columns are reduced over the ROWS by a transposing
+          // butterfly (lane l ends up with column l: 31 shuffles per statistic, no shared memory, no barrier), the column sums go
+          // to the per-(image, channel) accumulators as 64-bit fixed point - integer atomics are exact and order-independent.
+          // f[] is dead after the packing above; the conv producers have the epilogue slack for these ~300 instructions.
+          float q[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            if (!rc.valid) f[e] = 0.f;
+            q[e] = f[e] * f[e];
+          }
+#pragma unroll
+          for (int sft = 16; sft >= 1; sft >>= 1) {
+            const bool up = (lane & sft) != 0;
+#pragma unroll
+            for (int i = 0; i < sft; ++i) {
+              const float send_f = up ? f[i] : f[i + sft], keep_f = up ? f[i + sft] : f[i];
+              const float send_q = up ? q[i] : q[i + sft], keep_q = up ? q[i + sft] : q[i];
+              f[i] = keep_f + __shfl_xor_sync(0xffffffffu, send_f, sft);
+              q[i] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, sft);
+            }
+          }
+          const int n_w = __shfl_sync(0xffffffffu, rc.n, 0);  // host: the 32 rows of a warp belong to one image
+          if (__shfl_sync(0xffffffffu, (int)rc.valid, 0)) {
+            unsigned long long* acc = reinterpret_cast<unsigned long long*>(args.gn_out) + ((int64_t)n_w * g.n_store + col0 + lane) * 2;
+            atomicAdd(acc, (unsigned long long)__float2ll_rn(f[0] * 16777216.0f));
+            atomicAdd(acc + 1, (unsigned long long)__float2ll_rn(q[0] * 4096.0f));
+          }
+        }
         if (has_dt && col0 >= args.dt_col0) {
           // Staging = two [32 columns][64 rows] halves (4 KB each, one TMA store each), 128B-swizzled.  Lanes r, r ^ 1 exchange
           // their packed pairs so that every lane writes whole 32-bit words {row r & ~1, row r | 1} of one column: the even lane
@@ -926,6 +958,7 @@ cpd_status launch2_feat(const Gemm2Args& args, int feat, int smem_bytes, cudaStr
     case FEAT_LN_OUT: return launch2<1, OF16, FEAT_LN_OUT>(args, smem_bytes, stream);
     case FEAT_DT: return launch2<1, OF16, FEAT_DT>(args, smem_bytes, stream);
     case FEAT_LN_IN | FEAT_DT: return launch2<1, OF16, FEAT_LN_IN | FEAT_DT>(args, smem_bytes, stream);
+    case FEAT_GN_OUT: return launch2<1, OF16, FEAT_GN_OUT>(args, smem_bytes, stream);
     default: break;
   }
   cpd_set_error("cpd_gemm_conv: unsupported combination of folded-LayerNorm / transposed-tail options (%d)", feat);
@@ -1073,6 +1106,10 @@ cpd_status cpd_gemm_conv_2cta(const cpd_gemm_params* p, void* stream) {
     CPD_REQUIRE(!geglu && p->ln_ld >= out_rows && g.n_store % 32 == 0, "cpd_gemm_conv: a folded-LayerNorm producer needs a plain epilogue, ln_ld >= rows and N %% 32 == 0");
     if (p->ln_parts_out) *p->ln_parts_out = args.n_tiles * EPI_GROUPS;
   }
+  args.gn_out = p->gn_sums_out;
+  if (p->gn_sums_out)
+    CPD_REQUIRE(!geglu && splits == 1 && mc == 1 && g.n_store % 32 == 0 && (g.tw * g.th) % 32 == 0 && !ln_any && !p->d_t,
+                "cpd_gemm_conv: GroupNorm statistics need the plain pair kernel, N %% 32 == 0 and 32-row groups inside one image");
   args.dt_col0 = -1;
   args.map_dt = args.map_a0;
   if (p->d_t) {
@@ -1114,7 +1151,7 @@ cpd_status cpd_gemm_conv_2cta(const cpd_gemm_params* p, void* stream) {
 #else
   CPD_REQUIRE(mc == 1, "cpd_gemm_conv: the 4-CTA multicast cluster (variant 1000 + BN) is compiled only with -DCPD_EXPERIMENTAL");
 #endif
-  const int feat = (p->ln_sums ? FEAT_LN_IN : 0) | (p->ln_sums_out ? FEAT_LN_OUT : 0) | (p->d_t ? FEAT_DT : 0);
+  const int feat = (p->ln_sums ? FEAT_LN_IN : 0) | (p->ln_sums_out ? FEAT_LN_OUT : 0) | (p->d_t ? FEAT_DT : 0) | (p->gn_sums_out ? FEAT_GN_OUT : 0);
   const cpd_status st = of16 ? launch2_feat<true>(args, feat, smem_bytes, (cudaStream_t)stream) : launch2_feat<false>(args, feat, smem_bytes, (cudaStream_t)stream);
   if (st != CPD_OK || splits == 1) return st;
   const int64_t vecs = out_rows * (g.n_store / 8);

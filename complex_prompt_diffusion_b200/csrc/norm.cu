@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(512, 2) gn_stats_kernel(const bf16* __restrict
 template <bool F16>
 __global__ void __launch_bounds__(512, 2) gn_apply_kernel(const bf16* __restrict__ a0, const bf16* __restrict__ a1, int c0,
                                                        int c1, int hw, int px_per_block, const double* __restrict__ partial,
+                                                       const long long* __restrict__ chan_sums,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        float eps, int silu, bf16* __restrict__ out) {
   extern __shared__ __align__(16) float sh_raw[];  // ring[RING][blockDim.x] of uint4, scale[C], shift[C], group stats
@@ -147,10 +148,22 @@ __global__ void __launch_bounds__(512, 2) gn_apply_kernel(const bf16* __restrict
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     for (int g = warp; g < GROUPS; g += nwarps) {
       double S = 0.0, SS = 0.0;
-      for (int k = lane; k < (int)gridDim.x; k += 32) {
-        const double2 pp = *reinterpret_cast<const double2*>(partial + (((int64_t)n * gridDim.x + k) * GROUPS + g) * 2);
-        S += pp.x;
-        SS += pp.y;
+      if (chan_sums) {
+        // statistics emitted by the producing GEMM (cpd_gemm_params.gn_sums_out): exact fixed-point sums per (image, channel)
+        long long s1 = 0, s2 = 0;
+        for (int c = lane; c < cpg; c += 32) {
+          const longlong2 pp = *reinterpret_cast<const longlong2*>(chan_sums + ((int64_t)n * C + g * cpg + c) * 2);
+          s1 += pp.x;
+          s2 += pp.y;
+        }
+        S = (double)s1 * (1.0 / 16777216.0);
+        SS = (double)s2 * (1.0 / 4096.0);
+      } else {
+        for (int k = lane; k < (int)gridDim.x; k += 32) {
+          const double2 pp = *reinterpret_cast<const double2*>(partial + (((int64_t)n * gridDim.x + k) * GROUPS + g) * 2);
+          S += pp.x;
+          SS += pp.y;
+        }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -723,12 +736,44 @@ extern "C" cpd_status cpd_groupnorm(const void* a0, const void* a1, int c0, int 
   if (act_fp16) {
     CPD_CUDA_CHECK(cpd_launch(gn_stats_kernel<true>, grid, dim3(threads), shm_stats, s, (const bf16*)a0, (const bf16*)a1, c0, c1, hw, px_per_block, stats));
     CPD_CUDA_CHECK(cpd_launch(gn_apply_kernel<true>, grid, dim3(threads), shm, s, (const bf16*)a0, (const bf16*)a1, c0, c1, hw, px_per_block,
-                              (const double*)stats, gamma, beta, eps, silu, (bf16*)out));
+                              (const double*)stats, (const long long*)nullptr, gamma, beta, eps, silu, (bf16*)out));
   } else {
     CPD_CUDA_CHECK(cpd_launch(gn_stats_kernel<false>, grid, dim3(threads), shm_stats, s, (const bf16*)a0, (const bf16*)a1, c0, c1, hw, px_per_block, stats));
     CPD_CUDA_CHECK(cpd_launch(gn_apply_kernel<false>, grid, dim3(threads), shm, s, (const bf16*)a0, (const bf16*)a1, c0, c1, hw, px_per_block,
-                              (const double*)stats, gamma, beta, eps, silu, (bf16*)out));
+                              (const double*)stats, (const long long*)nullptr, gamma, beta, eps, silu, (bf16*)out));
   }
+  CPD_CUDA_CHECK(cudaGetLastError());
+  return CPD_OK;
+}
+
+// GroupNorm from the producer's statistics: the apply pass alone (one read + one write of the tensor).
+extern "C" cpd_status cpd_groupnorm_apply(const void* x, int c, int n_img, int hw, const float* gamma, const float* beta, float eps,
+                                          int silu, int act_fp16, const long long* chan_sums, void* out, void* stream) {
+  CPD_REQUIRE(x && gamma && beta && chan_sums && out, "cpd_groupnorm_apply: null pointer");
+  CPD_REQUIRE(c > 0 && c % 8 == 0 && c % GROUPS == 0 && c <= 4096, "cpd_groupnorm_apply: bad channel count %d", c);
+  CPD_REQUIRE(n_img > 0 && hw > 0, "cpd_groupnorm_apply: empty input");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int vec_per_px = c / 8;
+  int lanes = 256 / vec_per_px;
+  if (lanes < 1) lanes = 1;
+  if (lanes > hw) lanes = hw;
+  const int threads = ((lanes * vec_per_px + 31) / 32) * 32;
+  CPD_REQUIRE(threads <= 512, "cpd_groupnorm_apply: C=%d too large", c);
+  int chunks = (148 * 4 + n_img - 1) / n_img;  // one wave of ~4 blocks per SM over all images, >= 8 pixels per pixel lane
+  int px_per_block = (hw + chunks - 1) / chunks;
+  if (px_per_block < 8 * lanes) px_per_block = 8 * lanes;
+  chunks = (hw + px_per_block - 1) / px_per_block;
+  const size_t shm = (size_t)RING * threads * 16 + sizeof(float) * (2 * c + 2 * GROUPS);
+  CPD_REQUIRE(shm <= 160 * 1024, "cpd_groupnorm_apply: C=%d needs %zu bytes of shared memory", c, shm);
+  CPD_SMEM_OPTIN(gn_apply_kernel<true>, 160 * 1024);
+  CPD_SMEM_OPTIN(gn_apply_kernel<false>, 160 * 1024);
+  const dim3 grid(chunks, n_img);
+  if (act_fp16)
+    CPD_CUDA_CHECK(cpd_launch(gn_apply_kernel<true>, grid, dim3(threads), shm, s, (const bf16*)x, (const bf16*)nullptr, c, 0, hw, px_per_block,
+                              (const double*)nullptr, chan_sums, gamma, beta, eps, silu, (bf16*)out));
+  else
+    CPD_CUDA_CHECK(cpd_launch(gn_apply_kernel<false>, grid, dim3(threads), shm, s, (const bf16*)x, (const bf16*)nullptr, c, 0, hw, px_per_block,
+                              (const double*)nullptr, chan_sums, gamma, beta, eps, silu, (bf16*)out));
   CPD_CUDA_CHECK(cudaGetLastError());
   return CPD_OK;
 }

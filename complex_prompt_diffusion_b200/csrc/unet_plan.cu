@@ -270,6 +270,16 @@ struct cpd_unet_plan {
   bool fold_ln = true, fold_dirty = true;
   int fold_geglu_min_ch = 640;
   int64_t fold_min_rows = 2048;  // levels with fewer tokens keep the LayerNorm kernels (their GEMMs want split-K / one-tile variants)
+  // GroupNorm statistics from the producing conv's epilogue (cpd_gemm_params.gn_sums_out): one zeroed arena of fixed-point
+  // accumulators per forward, handed out in launch order.  OPT-IN (CPD_UNET_GN_STATS=1): measured on B200 (tools/bench_gnstats.py)
+  // the ~300 extra epilogue instructions per 128 x 32 chunk are NOT hidden behind the main loop of the 3x3 convolutions (64 x 64:
+  // 91 -> 103 us per conv against 33.8 -> 20.2 us for the GroupNorm; 32 x 32: +5 us against -6 us; 16 x 16: +2.4 against -0.3):
+  // break-even at best, 15.8 vs 15.4 ms per 16-row evaluation.  The default keeps every GroupNorm's own statistics pass.
+  bool gn_stats = false;
+  int64_t gn_min_rows = 4096;
+  DevBuf gn_arena;                 // int64 accumulators
+  std::vector<void*> gn_retired;   // outgrown arenas: captured graphs may still point into them
+  int64_t gn_used = 0, gn_need = 0;  // bytes handed out in the current forward / by the last complete one
   bool share_prefix = true;  // CPD_UNET_SHARE_PREFIX=0: evaluate every row through the whole network (A/B measurements)
   // profiling (eager launches bracketed by events)
   bool profile = false;
@@ -716,6 +726,7 @@ struct GemmOpt {
   int dt_col0 = 0;
   int64_t ldd_t = 0;
   int ldd = 0;  // 0: n_out (n_out / 2 for GEGLU)
+  long long* gn_out = nullptr;  // GroupNorm statistics of the output (fixed-point accumulators, zeroed)
 };
 
 cpd_status ensure_scratch(cpd_unet_plan* P, int64_t bytes, cudaStream_t st) {
@@ -762,6 +773,7 @@ cpd_status gemm(cpd_unet_plan* P, cudaStream_t st, const void* a0, const void* w
   p.d_t = o.d_t;
   p.dt_col0 = o.dt_col0;
   p.ldd_t = o.ldd_t;
+  p.gn_sums_out = o.gn_out;
   p.variant = 0;
   p.a_fp16 = p.b_fp16 = p.out_fp16 = P->cfg.act_fp16;
   p.geglu_block = o.epilogue == CPD_EPI_GEGLU ? GEGLU_BLOCK : 0;
@@ -779,9 +791,13 @@ cpd_status gemm(cpd_unet_plan* P, cudaStream_t st, const void* a0, const void* w
 }
 
 cpd_status groupnorm(cpd_unet_plan* P, cudaStream_t st, const void* a0, const void* a1, int c0, int c1, int n_img, int hw, const std::string& g,
-                     const std::string& b, float eps, int silu, double* stats, void* out) {
+                     const std::string& b, float eps, int silu, double* stats, void* out, const long long* chan_sums = nullptr) {
   char label[64];
-  snprintf(label, sizeof(label), "n=%d hw=%d C=%d", n_img, hw, c0 + c1);
+  snprintf(label, sizeof(label), "%sn=%d hw=%d C=%d", chan_sums && !a1 ? "apply " : "", n_img, hw, c0 + c1);
+  if (chan_sums && !a1) {  // the producer's epilogue already reduced the statistics: normalise only
+    OpScope op(P, st, "groupnorm", label, 0.0, 1);
+    return cpd_groupnorm_apply(a0, c0, n_img, hw, (const float*)W(P, g), (const float*)W(P, b), eps, silu, P->cfg.act_fp16, chan_sums, out, st);
+  }
   OpScope op(P, st, "groupnorm", label, 0.0, 2);
   return cpd_groupnorm(a0, a1, c0, c1, n_img, hw, (const float*)W(P, g), (const float*)W(P, b), eps, silu, P->cfg.act_fp16, stats, out, st);
 }
@@ -813,7 +829,19 @@ cpd_status attention(cpd_unet_plan* P, cudaStream_t st, const void* q, int ldq, 
 struct Act {  // an NHWC activation tensor
   void* p = nullptr;
   int c = 0;
+  const long long* gn = nullptr;  // its GroupNorm statistics, when the GEMM that produced it emitted them
 };
+
+// Accumulators for the GroupNorm statistics of one [n][hw][c] tensor, or NULL (level too small, arena not yet sized: the consumer
+// then computes its own statistics).  The demand is recorded either way; cpd_unet_forward sizes the arena from it.
+long long* gn_alloc(cpd_unet_plan* P, int n, int hw, int c) {
+  if (!P->gn_stats || (int64_t)n * hw < P->gn_min_rows || hw % 32 != 0 || c % 32 != 0) return nullptr;
+  const int64_t bytes = (int64_t)n * c * 2 * sizeof(long long);
+  const int64_t off = P->gn_used;
+  P->gn_used += bytes;
+  if (!P->gn_arena.p || P->gn_used > P->gn_arena.numel) return nullptr;
+  return reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(P->gn_arena.p) + off);
+}
 
 struct FwdCtx {
   cpd_unet_plan* P;
@@ -880,18 +908,20 @@ cpd_status res_block(FwdCtx& F, const std::string& p, Act x0, Act x1, int cout, 
   const int64_t T = (int64_t)F.R * hw;
   void *gn, *h1, *gn2, *out;
   PLAN_CHECK(ws_get(P, "gn", T * cin, 2, &gn));
-  PLAN_CHECK(groupnorm(P, F.st, x0.p, x1.p, x0.c, x1.c, F.R, hw, p + "gn1.g", p + "gn1.b", 1e-5f, 1, F.stats, gn));
+  PLAN_CHECK(groupnorm(P, F.st, x0.p, x1.p, x0.c, x1.c, F.R, hw, p + "gn1.g", p + "gn1.b", 1e-5f, 1, F.stats, gn, x1.p ? nullptr : x0.gn));
   PLAN_CHECK(ws_get(P, "h1", T * cout, 2, &h1));
+  long long* h1_gn = gn_alloc(P, F.R, hw, cout);
   {
     GemmOpt o;
     o.ksize = 3;
+    o.gn_out = h1_gn;
     o.bias = (const float*)W(P, p + "conv1.b");
     o.rowvec = F.emb_all + P->emb_off[p];  // h + emb_out[:, :, None, None] (unet.py:266-274) in the epilogue
     o.rowvec_stride = F.emb_stride;
     PLAN_CHECK(gemm(P, F.st, gn, W(P, p + "conv1.w"), h1, F.R, F.h, F.w, cin, cout, o));
   }
   PLAN_CHECK(ws_get(P, "gn", T * cout, 2, &gn2));
-  PLAN_CHECK(groupnorm(P, F.st, h1, nullptr, cout, 0, F.R, hw, p + "gn2.g", p + "gn2.b", 1e-5f, 1, F.stats, gn2));
+  PLAN_CHECK(groupnorm(P, F.st, h1, nullptr, cout, 0, F.R, hw, p + "gn2.g", p + "gn2.b", 1e-5f, 1, F.stats, gn2, h1_gn));
   const void* skip = x0.p;
   if (cin != cout) {  // 1x1 skip conv over both concat sources (unet.py:247)
     void* sk;
@@ -904,9 +934,11 @@ cpd_status res_block(FwdCtx& F, const std::string& p, Act x0, Act x1, int cout, 
     skip = sk;
   }
   PLAN_CHECK(ws_get(P, p + "out", T * cout, 2, &out));
+  long long* out_gn = gn_alloc(P, F.R, hw, cout);  // the GroupNorm of the next ResBlock / SpatialTransformer reads this tensor
   {
     GemmOpt o;
     o.ksize = 3;
+    o.gn_out = out_gn;
     o.bias = (const float*)W(P, p + "conv2.b");
     o.residual = skip;
     o.ld_res = cout;
@@ -914,6 +946,7 @@ cpd_status res_block(FwdCtx& F, const std::string& p, Act x0, Act x1, int cout, 
   }
   outp->p = out;
   outp->c = cout;
+  outp->gn = out_gn;
   return CPD_OK;
 }
 
@@ -941,7 +974,7 @@ cpd_status attn_pre(FwdCtx& F, const std::string& p, Act x, void** hcur_out) {
   PLAN_CHECK(attn_dims(F, x.c, &D));
   void *gn, *hcur;
   PLAN_CHECK(ws_get(P, "gn", D.T * D.ch, 2, &gn));
-  PLAN_CHECK(groupnorm(P, F.st, x.p, nullptr, D.ch, 0, F.R, D.hw, p + "norm.g", p + "norm.b", 1e-6f, 0, F.stats, gn));
+  PLAN_CHECK(groupnorm(P, F.st, x.p, nullptr, D.ch, 0, F.R, D.hw, p + "norm.g", p + "norm.b", 1e-6f, 0, F.stats, gn, x.gn));
   PLAN_CHECK(ws_get(P, "tr.h", D.T * D.ch, 2, &hcur));
   GemmOpt g;
   g.bias = (const float*)W(P, p + "proj_in.b");
@@ -1054,6 +1087,7 @@ cpd_status attn_post(FwdCtx& F, const std::string& p, Act x, void* hcur, Act* ou
   PLAN_CHECK(gemm(P, F.st, hcur, W(P, p + "proj_out.w"), out, 1, 1, (int)T, x.c, x.c, g));
   outp->p = out;
   outp->c = x.c;
+  outp->gn = nullptr;
   return CPD_OK;
 }
 
@@ -1096,8 +1130,10 @@ cpd_status run_block(FwdCtx& F, const Block& blk, Act hcur, Act skip, Act* outp)
       o.ksize = 3;
       o.stride = 2;
       o.bias = (const float*)W(P, p + "b");
+      o.gn_out = gn_alloc(P, F.R, (F.h / 2) * (F.w / 2), l.a);
       PLAN_CHECK(gemm(P, F.st, hcur.p, W(P, p + "w"), out, F.R, F.h, F.w, l.a, l.a, o));
       hcur.p = out;
+      hcur.gn = o.gn_out;
       F.h /= 2;
       F.w /= 2;
     } else if (l.kind == L_UP) {
@@ -1115,6 +1151,7 @@ cpd_status run_block(FwdCtx& F, const Block& blk, Act hcur, Act skip, Act* outp)
       o.bias = (const float*)W(P, p + "b");
       PLAN_CHECK(gemm(P, F.st, up, W(P, p + "w"), out, F.R, F.h, F.w, l.a, l.a, o));
       hcur.p = out;
+      hcur.gn = nullptr;
     }
   }
   *outp = hcur;
@@ -1163,6 +1200,8 @@ cpd_status forward_impl(cpd_unet_plan* P, const cpd_unet_io* io, void* eps_out, 
   const float* t_rows = io->t;
   void* stats;
   PLAN_CHECK(ws_get(P, "gn.stats", (int64_t)R * 64 * CPD_GN_MAX_CHUNKS, 8, &stats));
+  P->gn_used = 0;
+  if (P->gn_arena.p) CPD_CUDA_CHECK(cudaMemsetAsync(P->gn_arena.p, 0, (size_t)P->gn_arena.numel, st));  // one node per forward
   float* emb_all = nullptr;
   int m_emb = shared_t ? 1 : R;
   if (P->adm) {
@@ -1194,7 +1233,16 @@ cpd_status forward_impl(cpd_unet_plan* P, const cpd_unet_io* io, void* eps_out, 
   const int mc = P->mc;
   void* h0;
   PLAN_CHECK(ws_get(P, "input_blocks.0.0.out", (int64_t)R * h * w * mc, 2, &h0));
-  {
+  // The rows of an image share x * c_in and t (denoiser.py:383-393) and differ only in their text context, so every activation
+  // in front of the FIRST cross-attention - the input conv, the ResBlock of input block 1 and, inside its SpatialTransformer,
+  // GroupNorm, proj_in, LN1 and the whole self-attention (at 64 x 64 the most expensive attention of the network) - is
+  // identical for the (1 + N) rows of an image.  It is evaluated ONCE per image and broadcast to the rows right before the
+  // cross-attention; the result is bit-identical to evaluating every row.  (Not with per-row timesteps, vector conditioning or
+  // injected tensors, where the rows do differ.)
+  const bool share = rpi > 1 && shared_t && !P->adm && !io->inject_skips && !io->inject_feats && P->inputs.size() > 1 &&
+                     P->inputs[1].layers.size() == 2 && P->inputs[1].layers[0].kind == L_RES && P->inputs[1].layers[1].kind == L_ATTN &&
+                     P->share_prefix;
+  if (!share) {
     OpScope op(P, st, "conv_in", "", 0.0, 1);
     PLAN_CHECK(cpd_conv_in(io->x, B, c.in_channels, h, w, W(P, "input_blocks.0.0.w"), (const float*)W(P, "input_blocks.0.0.b"), mc, 1.0f,
                            io->c_in, rpi, c.act_fp16, h0, st));
@@ -1210,15 +1258,6 @@ cpd_status forward_impl(cpd_unet_plan* P, const cpd_unet_io* io, void* eps_out, 
   hs.push_back({hcur, h, w});
   P->tap_in[0] = Tap{h0, mc, h, w};
   size_t first_block = 1;
-  // The rows of an image share x * c_in and t (denoiser.py:383-393) and differ only in their text context, so every activation
-  // in front of the FIRST cross-attention - the input conv, the ResBlock of input block 1 and, inside its SpatialTransformer,
-  // GroupNorm, proj_in, LN1 and the whole self-attention (at 64 x 64 the most expensive attention of the network) - is
-  // identical for the (1 + N) rows of an image.  It is evaluated ONCE per image and broadcast to the rows right before the
-  // cross-attention; the result is bit-identical to evaluating every row.  (Not with per-row timesteps, vector conditioning or
-  // injected tensors, where the rows do differ.)
-  const bool share = rpi > 1 && shared_t && !P->adm && !io->inject_skips && !io->inject_feats && P->inputs.size() > 1 &&
-                     P->inputs[1].layers.size() == 2 && P->inputs[1].layers[0].kind == L_RES && P->inputs[1].layers[1].kind == L_ATTN &&
-                     P->share_prefix;
   if (share) {
     const Block& blk = P->inputs[1];
     const std::string pr = blk.prefix + "0.", pa = blk.prefix + "1.";
@@ -1231,6 +1270,8 @@ cpd_status forward_impl(cpd_unet_plan* P, const cpd_unet_io* io, void* eps_out, 
       PLAN_CHECK(cpd_conv_in(io->x, B, c.in_channels, h, w, W(P, "input_blocks.0.0.w"), (const float*)W(P, "input_blocks.0.0.b"), mc, 1.0f,
                              io->c_in, 1, c.act_fp16, h0b, st));
     }
+    // the R-row input-conv output (the skip tensor of the last output block) is the per-image one repeated: a copy, not a second conv
+    PLAN_CHECK(expand_images(P, st, h0b, h0, B, rpi, hw * mc));
     FwdCtx Fb{P, st, B, h, w, emb_all, 0, (double*)stats};
     Act xres_b, xres;
     PLAN_CHECK(res_block(Fb, pr, Act{h0b, mc}, Act(), cout, &xres_b));
@@ -1267,14 +1308,21 @@ cpd_status forward_impl(cpd_unet_plan* P, const cpd_unet_io* io, void* eps_out, 
     hs.pop_back();
     CPD_REQUIRE(s.h == F.h && s.w == F.w, "cpd_unet_forward: skip tensor %zu is %dx%d, the decoder is at %dx%d (h, w must be multiples of %d)", i, s.h,
                 s.w, F.h, F.w, 1 << (c.n_levels - 1));
-    if (io->inject_skips && io->inject_skips[i]) s.a.p = const_cast<void*>(io->inject_skips[i]);  // unet.py:806-809
-    if (io->inject_feats && io->inject_feats[i]) hcur.p = const_cast<void*>(io->inject_feats[i]);  // unet.py:810-813
+    if (io->inject_skips && io->inject_skips[i]) {  // unet.py:806-809
+      s.a.p = const_cast<void*>(io->inject_skips[i]);
+      s.a.gn = nullptr;
+    }
+    if (io->inject_feats && io->inject_feats[i]) {  // unet.py:810-813
+      hcur.p = const_cast<void*>(io->inject_feats[i]);
+      hcur.gn = nullptr;
+    }
     PLAN_CHECK(run_block(F, P->outputs[i], hcur, s.a, &hcur));
     P->tap_out[i] = Tap{hcur.p, hcur.c, F.h, F.w};
   }
   void* gn;
   PLAN_CHECK(ws_get(P, "gn", (int64_t)R * F.h * F.w * hcur.c, 2, &gn));
-  PLAN_CHECK(groupnorm(P, st, hcur.p, nullptr, hcur.c, 0, R, F.h * F.w, "out.gn.g", "out.gn.b", 1e-5f, 1, (double*)stats, gn));
+  PLAN_CHECK(groupnorm(P, st, hcur.p, nullptr, hcur.c, 0, R, F.h * F.w, "out.gn.g", "out.gn.b", 1e-5f, 1, (double*)stats, gn, hcur.gn));
+  P->gn_need = P->gn_used;
   {
     OpScope op(P, st, "conv_out", "", 0.0, 1);
     PLAN_CHECK(cpd_conv_out(gn, R, F.h, F.w, hcur.c, W(P, "out.w"), (const float*)W(P, "out.b"), c.out_channels, eps_out, c.eps_dtype,
@@ -1324,6 +1372,8 @@ extern "C" cpd_status cpd_unet_plan_create(const cpd_unet_config* cfg, cpd_unet_
     P->fold_ln = !(e && e[0] == '0');
     e = getenv("CPD_UNET_FOLD_MIN_ROWS");
     if (e && atoll(e) > 0) P->fold_min_rows = atoll(e);
+    e = getenv("CPD_UNET_GN_STATS");
+    P->gn_stats = e && e[0] == '1';
     e = getenv("CPD_UNET_FOLD_GEGLU_MIN_CH");
     if (e && atoi(e) > 0) P->fold_geglu_min_ch = atoi(e);
   }
@@ -1351,6 +1401,8 @@ extern "C" void cpd_unet_plan_destroy(cpd_unet_plan* P) {
   if (P->y.p) cudaFree(P->y.p);
   if (P->tune_scratch.p) cudaFree(P->tune_scratch.p);
   if (P->splitk.p) cudaFree(P->splitk.p);
+  if (P->gn_arena.p) cudaFree(P->gn_arena.p);
+  for (void* q : P->gn_retired) cudaFree(q);
   if (P->cap_stream) cudaStreamDestroy(P->cap_stream);
   for (auto& r : P->prof) {
     cudaEventDestroy(r.e0);
@@ -1501,10 +1553,25 @@ extern "C" cpd_status cpd_unet_forward(cpd_unet_plan* P, const cpd_unet_io* io, 
   if (!eps) PLAN_CHECK(ws_get(P, "eps", (int64_t)R * P->cfg.out_channels * io->h * io->w, eps_elt(P->cfg), &eps));
   P->allow_alloc = true;
   const bool use_graph = P->cfg.use_cuda_graph && !io->no_graph && !inject && !outer_capture && !P->profile;
+  // The arena of GroupNorm accumulators is sized from the demand the previous pass over this shape recorded; a pass that finds
+  // it too small still computes correctly (its GroupNorms reduce their own statistics).
+  auto grow_gn_arena = [&]() -> cpd_status {
+    if (P->gn_need <= P->gn_arena.numel) return CPD_OK;
+    if (P->gn_arena.p) P->gn_retired.push_back(P->gn_arena.p);  // captured graphs may still point into the old arena
+    P->gn_arena.p = nullptr;
+    return alloc_dev(&P->gn_arena, P->gn_need, 1, true);
+  };
   if (!use_graph) {
     P->capturing = outer_capture;
     P->allow_alloc = !outer_capture;
-    const cpd_status rc = forward_impl(P, io, eps, st);
+    cpd_status rc = forward_impl(P, io, eps, st);
+    if (rc == CPD_OK && !outer_capture && P->gn_need > P->gn_arena.numel) {
+      // first evaluation of a larger shape: size the arena and evaluate again, so that the launches that use it are tuned before
+      // a host captures this shape into a graph of its own (samplers/k_diffusion.py: one eager evaluation, then the capture)
+      CPD_CUDA_CHECK(cudaStreamSynchronize(st));
+      rc = grow_gn_arena();
+      if (rc == CPD_OK) rc = forward_impl(P, io, eps, st);
+    }
     P->capturing = false;
     P->allow_alloc = true;
     return rc;
@@ -1531,6 +1598,11 @@ extern "C" cpd_status cpd_unet_forward(cpd_unet_plan* P, const cpd_unet_io* io, 
     P->allow_alloc = true;
     PLAN_CHECK(forward_impl(P, io, eps, st));
     CPD_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (P->gn_need > P->gn_arena.numel) {  // first evaluation of a larger shape: size the arena, then tune the launches that use it
+      PLAN_CHECK(grow_gn_arena());
+      PLAN_CHECK(forward_impl(P, io, eps, st));
+      CPD_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
     P->launches = 0;
     P->capturing = true;
     P->allow_alloc = false;

@@ -224,11 +224,12 @@ def gemm_tune_import(text):
 
 def gemm_conv(a0, wt, out, *, n_img, h, w, c0, n_out, a1=None, c1=0, ksize=1, stride=1, bias=None, rowvec=None,
               rowvec_stride=0, residual=None, ld_res=0, ldd=None, epilogue=CPD_EPI_NONE, variant=0, m_valid=0, geglu_block=128,
-              ln_sums_out=None, ln_sums=None, ln_parts=0, ln_g=None, ln_eps=1e-5, d_t=None, dt_col0=0):
+              ln_sums_out=None, ln_sums=None, ln_parts=0, ln_g=None, ln_eps=1e-5, d_t=None, dt_col0=0, gn_sums_out=None):
     """a0/a1 and wt are 16-bit (fp16 or bf16, independently); out/residual share one 16-bit dtype.
     Folded LayerNorm (cpd_gemm_params.ln_*): a producer passes ln_sums_out = fp32 [max_parts, rows, 2] and gets (out, number of
     parts written) back; a consumer passes ln_sums, ln_parts,
-    ln_g (and wt = gamma . W, bias = W beta + b).  d_t [n_out - dt_col0, rows]: columns from dt_col0 on are stored transposed."""
+    ln_g (and wt = gamma . W, bias = W beta + b).  d_t [n_out - dt_col0, rows]: columns from dt_col0 on are stored transposed.
+    gn_sums_out: int64 [n_img, n_out, 2], zeroed by the caller: fixed-point GroupNorm statistics of the output (groupnorm_apply)."""
     a_f16 = _act(a0, "a0")
     _act(a1, "a1", like=a0.dtype)
     b_f16 = _act(wt, "wt")
@@ -265,6 +266,9 @@ def gemm_conv(a0, wt, out, *, n_img, h, w, c0, n_out, a1=None, c1=0, ksize=1, st
         _req(ln_g, torch.float32, "ln_g")
         p.ln_sums, p.ln_parts, p.ln_ld, p.ln_g = ln_sums.data_ptr(), ln_parts, ln_sums.shape[1], ln_g.data_ptr()
         p.ln_c, p.ln_eps = ksize * ksize * (c0 + c1), ln_eps
+    if gn_sums_out is not None:
+        _req(gn_sums_out, torch.int64, "gn_sums_out")
+        p.gn_sums_out = gn_sums_out.data_ptr()
     if d_t is not None:
         _act(d_t, "d_t", like=out.dtype)
         p.d_t, p.dt_col0, p.ldd_t = d_t.data_ptr(), dt_col0, d_t.shape[1]
@@ -291,6 +295,20 @@ def groupnorm(a0, gamma, beta, out, stats, *, n_img, hw, c0, a1=None, c1=0, eps=
         check(load().cpd_groupnorm(ptr(a0), ptr(a1), c0, c1, n_img, hw, ptr(gamma), ptr(beta), float(eps), int(silu), f16, ptr(stats),
                                    ptr(out), stream_ptr()), "cpd_groupnorm")
     _count(2)
+    return out
+
+
+def groupnorm_apply(x, gamma, beta, out, chan_sums, *, n_img, hw, c, eps=1e-5, silu=True):
+    """GroupNorm(32) from the fixed-point statistics a producing GEMM emitted (gemm_conv(gn_sums_out=...))."""
+    f16 = _act(x, "x")
+    _act(out, "out", like=x.dtype)
+    _req(gamma, torch.float32, "gamma")
+    _req(beta, torch.float32, "beta")
+    _req(chan_sums, torch.int64, "chan_sums")
+    with _Prof("groupnorm", 0.0, f"apply n={n_img} hw={hw} C={c}"):
+        check(load().cpd_groupnorm_apply(ptr(x), c, n_img, hw, ptr(gamma), ptr(beta), float(eps), int(silu), f16, ptr(chan_sums), ptr(out),
+                                         stream_ptr()), "cpd_groupnorm_apply")
+    _count()
     return out
 
 

@@ -251,6 +251,12 @@ typedef struct {
   void* d_t;
   int dt_col0;
   int64_t ldd_t;
+  /* --- GroupNorm statistics of D from the epilogue that writes it (models/util.py:95-105: the next GroupNorm then only
+   * normalises - cpd_groupnorm_apply - instead of reading the tensor twice): per (image, channel) sum and sum of squares in
+   * 64-bit FIXED POINT (sum * 2^24, sum of squares * 2^12), added with integer atomics - exact and order-independent, so the
+   * result is bit-reproducible.  [n_img][n_out][2]; the caller zeroes it before the launch.  Pair kernel only (no split-K, no
+   * one-tile variants, no GEGLU); every 32 consecutive rows of a CTA tile must belong to one image (th * tw % 32 == 0). */
+  long long* gn_sums_out;
 } cpd_gemm_params;
 
 cpd_status cpd_gemm_conv(const cpd_gemm_params* p, void* stream);
@@ -272,6 +278,10 @@ int cpd_gemm_tune_import(const char* text);
 cpd_status cpd_groupnorm(const void* a0, const void* a1, int c0, int c1, int n_img, int hw, const float* gamma,
                          const float* beta, float eps, int silu, int act_fp16, double* stats, void* out, void* stream);
 
+/* GroupNorm(32) (+ SiLU) from per-(image, channel) fixed-point statistics emitted by the producing GEMM (cpd_gemm_params.gn_sums_out):
+ * one read + one write of the tensor.  x, out: NHWC 16-bit [n_img][hw][c]. */
+cpd_status cpd_groupnorm_apply(const void* x, int c, int n_img, int hw, const float* gamma, const float* beta, float eps, int silu,
+                               int act_fp16, const long long* chan_sums, void* out, void* stream);
 /* LayerNorm over the last dim of [rows][c] (attention.py:476-478), eps 1e-5.
  * act_fp16 (here and below): activation tensors are 16-bit, 1 = fp16, 0 = bf16.  Weights are always bf16. */
 cpd_status cpd_layernorm(const void* x, int rows, int c, const float* gamma, const float* beta, float eps, int act_fp16,

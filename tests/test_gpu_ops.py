@@ -147,6 +147,44 @@ def test_gemm_folded_layernorm_and_transposed_tail(ops, M, K, N, pv, cv, act):
     assert r0 < tol and r1 < tol
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout,ks,res,variant,act", [(16, 64, 64, 320, 320, 3, True, 0, torch.float16), (3, 32, 32, 64, 640, 3, False, 160, torch.float16),
+                                                              (5, 16, 16, 128, 1280, 3, True, 256, torch.bfloat16), (2, 8, 8, 64, 128, 3, False, 0, torch.float16),
+                                                              (4, 32, 32, 640, 640, 1, True, 2160, torch.float16), (3, 16, 24, 64, 96, 3, False, 96, torch.float16)])
+def test_gemm_groupnorm_statistics_and_apply(ops, n, h, w, cin, cout, ks, res, variant, act):
+    """A conv / GEMM emits the GroupNorm statistics of its output (fixed-point integer atomics); cpd_groupnorm_apply then
+    normalises in one pass.  Reference: F.group_norm (+ SiLU) on the stored output (models/util.py:95-105)."""
+    g = torch.Generator().manual_seed(n * h + cin + cout)
+    x = torch.randn(n, h, w, cin, generator=g).to(act).to(DEV)
+    wt = (torch.randn(cout, ks * ks * cin, generator=g) / math.sqrt(ks * ks * cin)).to(act).to(DEV)
+    bias = (torch.randn(cout, generator=g) + 0.5).to(DEV)
+    r = (torch.randn(n * h * w, cout, generator=g)).to(act).to(DEV) if res else None
+    out = torch.empty(n * h * w, cout, dtype=act, device=DEV)
+    sums = torch.zeros(n, cout, 2, dtype=torch.int64, device=DEV)
+    ops.gemm_conv(x, wt, out, n_img=n, h=h, w=w, c0=cin, n_out=cout, ksize=ks, bias=bias, residual=r, ld_res=cout if res else 0,
+                  variant=variant, gn_sums_out=sums)
+    if variant == 0:  # the tuner re-zeroes the accumulators in front of the real launch; a second (table) launch adds again
+        sums.zero_()
+        ops.gemm_conv(x, wt, out, n_img=n, h=h, w=w, c0=cin, n_out=cout, ksize=ks, bias=bias, residual=r, ld_res=cout if res else 0,
+                      variant=variant, gn_sums_out=sums)
+    torch.cuda.synchronize()
+    of = out.float().reshape(n, h * w, cout)
+    s1 = sums[:, :, 0].double() / 2 ** 24
+    s2 = sums[:, :, 1].double() / 2 ** 12
+    e1 = (s1 - of.double().sum(1)).abs().max().item() / max(1.0, of.double().sum(1).abs().max().item())
+    e2 = (s2 - (of.double() ** 2).sum(1)).abs().max().item() / (of.double() ** 2).sum(1).max().item()
+    print(f"GN statistics {n}x{h}x{w} {cin}->{cout} k{ks} v{variant}: sum err {e1:.2e}, sum-of-squares err {e2:.2e}")
+    assert e1 < 2e-3 and e2 < 2e-3  # (the sums are of the fp32 values in front of the 16-bit rounding)
+    gamma = (1.0 + 0.2 * torch.randn(cout, generator=g)).to(DEV)
+    beta = (0.1 * torch.randn(cout, generator=g)).to(DEV)
+    y = torch.empty_like(out)
+    ops.groupnorm_apply(out, gamma, beta, y, sums, n_img=n, hw=h * w, c=cout, eps=1e-5, silu=True)
+    torch.cuda.synchronize()
+    ref = F.silu(F.group_norm(of.permute(0, 2, 1), 32, gamma, beta, 1e-5)).permute(0, 2, 1).reshape(n * h * w, cout)
+    rr = rel(y, ref)
+    print(f"   groupnorm_apply rel {rr:.3e}")
+    assert rr < (2e-2 if act == torch.bfloat16 else 4e-3)
+
+
 @pytest.mark.parametrize("M,C", [(4096, 320), (16384, 640)])
 def test_gemm_geglu_folded_layernorm(ops, M, C):
     g = torch.Generator().manual_seed(M + C)

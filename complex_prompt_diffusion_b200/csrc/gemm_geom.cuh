@@ -63,7 +63,7 @@ __device__ __forceinline__ RowCoord row_coord(const ConvGeom& g, int m_tile, int
   rc.n = ng * g.nb + ib;
   rc.y = by * g.th + py2;
   rc.x = bx * g.tw + (p2 - py2 * g.tw);
-  rc.valid = (rc.n < g.n_img) && (rc.y < g.h_out) && (rc.x < g.w_out);
+  rc.valid = (j < g.nbox) && (rc.n < g.n_img) && (rc.y < g.h_out) && (rc.x < g.w_out);  // rows beyond the tile's boxes are padding
   rc.row = ((int64_t)rc.n * g.h_out + rc.y) * g.w_out + rc.x;
   if (g.m_valid > 0 && rc.row >= g.m_valid) rc.valid = false;
   return rc;

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_conv_kernel(const __grid_
         mbar_wait(&empty_bar[stage], phase ^ 1, 1);
         uint8_t* sa = smem + stage * L::STAGE_BYTES;
         uint8_t* sb = sa + L::A_BYTES;
-        mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+        mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(g.nbox * box_bytes + (L::STAGE_BYTES - L::A_BYTES)));  // boxes may cover < 128 rows
         for (int j = 0; j < g.nbox; ++j) {
           const BoxCoord bc = box_coord(g, m_tile, j, tap, cb);
           tma_load_5d(sa + j * box_bytes, bc.src1 ? &args.map_a1 : &args.map_a0, &full_bar[stage], bc.c, bc.x, bc.p, bc.y, bc.n);
@@ -238,22 +238,33 @@ cpd_status launch(const GemmArgs& args, int m_tiles, int n_tiles, cudaStream_t s
 
 namespace cpd_gemm {
 
-// Box of output pixels covered by one TMA load: nb images x th rows x tw columns with tw | w, th | h, a multiple of
-// 8 rows (one swizzle atom) that divides 128, as large as possible.  nb > 1 only when the box spans whole images.
+// Box of output pixels covered by one TMA load: nb images x th rows x tw columns, tw | w, a multiple of 8 rows (one swizzle
+// atom), at most 128 rows; a CTA tile takes floor(128 / rows) boxes.  nb > 1 only when the box spans whole images.
+// th need NOT divide h and the rows need not divide 128 (round 2): the last box of an image then hangs over its bottom edge
+// (TMA zero-fills the loads and clips the stores) and the tile's remaining rows are padding (row_coord: valid = false).  What
+// this buys: a 12 x 12 image (SD-2.1 at 96 x 96, level 3) is two boxes of 12 x 10 - ONE TMA load per k-iteration and CTA - where
+// the exact tiling needed eight 4 x 4 boxes (2700 instead of ~600 cycles per k-iteration: the single-thread TMA issue was the
+// limiter, 65 us per 3x3 conv).  Cost model: tiles x (1 + 0.35 per extra box), ties to the fuller tile.
 static bool choose_box(int h, int w, int n_img, int* tw, int* th, int* nb) {
-  int best = 0;
+  double best_cost = 1e30;
+  int best_px = 0;
   *tw = *th = *nb = 0;
   for (int a = 1; a <= 128 && a <= w; ++a) {
     if (w % a) continue;
     for (int b = 1; a * b <= 128 && b <= h; ++b) {
-      if (h % b) continue;
       const int max_n = (a == w && b == h) ? 128 / (a * b) : 1;
       for (int c = 1; c <= max_n; c *= 2) {
         const int px = a * b * c;
-        if (128 % px || px % 8) continue;
+        if (px % 8 || px > 128) continue;
         if (c > 1 && c > 2 * n_img) continue;  // do not pad tiny batches with many empty images
-        if (px > best || (px == best && c < *nb) || (px == best && c == *nb && a > *tw)) {
-          best = px;
+        const int nbox = 128 / px;
+        const long boxes = (long)((n_img + c - 1) / c) * (w / a) * ((h + b - 1) / b);
+        const long tiles = (boxes + nbox - 1) / nbox;
+        const double cost = (double)tiles * (1.0 + 0.35 * (nbox - 1));
+        const int fill = px * nbox;
+        if (cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && (fill > best_px || (fill == best_px && a > *tw)))) {
+          best_cost = cost;
+          best_px = fill;
           *tw = a;
           *th = b;
           *nb = c;
@@ -261,7 +272,7 @@ static bool choose_box(int h, int w, int n_img, int* tw, int* th, int* nb) {
       }
     }
   }
-  return best > 0;
+  return best_px > 0;
 }
 
 // NHWC activation view (c, x, parity, y, n) with a box of nb images x th rows x tw columns x 64 channels
@@ -332,9 +343,9 @@ int fill_geometry(const cpd_gemm_params* p, ConvGeom* gp, CUtensorMap* map_a0, C
     g.tw = tw;
     g.th = th;
     g.nb = nb;
-    g.nbox = 128 / (tw * th * nb);
+    g.nbox = 128 / (tw * th * nb);            // floor: the rows beyond nbox boxes are padding
     g.bx_count = g.w_out / tw;
-    g.by_count = g.h_out / th;
+    g.by_count = (g.h_out + th - 1) / th;     // the last box of an image may hang over its bottom edge
   }
   g.inv_box_rows = 1.0f / (float)(g.tw * g.th * g.nb);
   g.inv_bx = 1.0f / (float)g.bx_count;

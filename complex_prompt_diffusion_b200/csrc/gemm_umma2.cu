@@ -229,7 +229,8 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
     // needs a division is hoisted to once per tile and the (tap, channel-block) walk is incremental.
     {
       const int box_bytes = g.tw * g.th * g.nb * 128;
-      const uint32_t tx_bytes = 2u * (uint32_t)stage_bytes;
+      // both CTAs' bytes land on the leader's barrier; the boxes of a tile may cover fewer than 128 rows (gemm_umma.cu: choose_box)
+      const uint32_t tx_bytes = 2u * (uint32_t)(stage_bytes - A_BYTES + g.nbox * box_bytes);
       const int bn_half = args.bn >> 1;
       const int tile_w = args.bn * args.nsub;
       int stage = 0;
@@ -426,7 +427,7 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
         int m2, n_tile;
         tile_mn(t, m2, n_tile);
         const int col0 = n_tile * out_w + ch * CHUNK_COLS;
-        mbar_arrive_expect_tx(&my_res_bar[buf], CHUNK_BYTES);
+        mbar_arrive_expect_tx(&my_res_bar[buf], (uint32_t)(g.nbox * box_rows * (CHUNK_COLS * 2)));
         for (int j = 0; j < g.nbox; ++j) {
           const BoxCoord bc = box_coord(g, m2 * 2 + (int)rank, j, 4, 0);
           tma_load_4d(my_staging + buf * CHUNK_BYTES + j * box_rows * (CHUNK_COLS * 2), &args.map_res, &my_res_bar[buf], col0, bc.x,

@@ -15,10 +15,31 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--variants", default="0")
+    ap.add_argument("--profile", default="", choices=["", "qkv", "producer"],
+                    help="launch only the fused Q | K | V projection (folded LayerNorm + transposed tail) or the residual GEMM that emits "
+                         "the partial sums, 6 times, at the 64 x 64 shape: for `ncu -k regex:gemm2_kernel -s 4 -c 1`")
     a = ap.parse_args()
     from complex_prompt_diffusion_b200 import ops
     dev = "cuda"
     f16 = torch.float16
+    if a.profile:
+        M, K, N, nt = (65536, 320, 1152, 384) if a.profile == "qkv" else (65536, 384, 320, 0)
+        x = torch.randn(M, K, device=dev).to(f16)
+        w = (torch.randn(N, K, device=dev) / math.sqrt(K)).to(f16)
+        bias, gvec = torch.randn(N, device=dev), torch.randn(N, device=dev)
+        sums = torch.rand(10, M, 2, device=dev) + 1.0
+        sums[:, :, 1] += 400.0
+        out = torch.empty(M, N - nt, device=dev, dtype=f16)
+        out_t = torch.empty(max(nt, 1), M, device=dev, dtype=f16)
+        res = torch.randn(M, N, device=dev).to(f16)
+        for _ in range(6):
+            if a.profile == "qkv":
+                ops.gemm_conv(x, w, out, n_img=1, h=1, w=M, c0=K, n_out=N, bias=bias, ldd=N - nt, d_t=out_t, dt_col0=N - nt, ln_sums=sums, ln_parts=4,
+                              ln_g=gvec, variant=192)
+            else:
+                ops.gemm_conv(x, w, out, n_img=1, h=1, w=M, c0=K, n_out=N, bias=bias, residual=res, ld_res=N, ln_sums_out=sums, variant=160)
+        torch.cuda.synchronize()
+        return
 
     def timeit(fn):
         for j in range(3):

@@ -24,6 +24,8 @@ cap gemm_conv3_64_320 gemm2_kernel 3 1 python tools/bench_gemm.py --only 0 --rep
 cap gemm_lin_65536_320_320 gemm2_kernel 3 1 python tools/bench_gemm.py --only 4 --reps 2
 cap gemm_lin_16384_640_640 gemm2_kernel 3 1 python tools/bench_gemm.py --only 5 --reps 2
 cap gemm_geglu_65536_320_2560 gemm2_kernel 3 1 python tools/bench_gemm.py --only 9 --reps 2
+cap gemm_qkv_folded_ln_transposed_tail_65536_320_1152 gemm2_kernel 4 1 python tools/bench_fold.py --profile qkv
+cap gemm_residual_ln_partial_sums_65536_384_320 gemm2_kernel 4 1 python tools/bench_fold.py --profile producer
 cap attention_self_4096_d40 attention4_kernel 3 1 python tools/bench_attn.py --only 0 --reps 2
 cap attention_cross_4096x77_d40 attention5_kernel 3 1 python tools/bench_attn.py --only 3 --reps 2
 cap groupnorm "gn_" 6 4 python tools/bench_norm.py --only gn --reps 2

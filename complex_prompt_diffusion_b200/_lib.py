@@ -107,6 +107,8 @@ _SIGS = {
     "cpd_threshold": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p]),
     "cpd_threshold_ex": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
     "cpd_gemm_conv": (C.c_int, [C.POINTER(GemmParams), C.c_void_p]),
+    "cpd_gemm_set_autotune": (None, [C.c_int]),
+    "cpd_gemm_tune_clear": (None, []),
     "cpd_groupnorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                 C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cpd_groupnorm_apply": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int,

@@ -34,13 +34,13 @@ TuneKey make_key(const cpd_gemm_params* p) {
                  p->rowvec != nullptr, p->a_fp16, p->m_valid};
 }
 
+int g_autotune = -1;  // -1: not yet read from the environment
 bool autotune_on() {
-  static int on = -1;
-  if (on < 0) {
+  if (g_autotune < 0) {
     const char* e = getenv("CPD_GEMM_AUTOTUNE");
-    on = (e && e[0] == '0') ? 0 : 1;
+    g_autotune = (e && e[0] == '0') ? 0 : 1;
   }
-  return on != 0;
+  return g_autotune != 0;
 }
 
 // pair-kernel tile widths, two-sub-tile tiles (2000 + BN), the one-tile-per-CTA kernels (1, 2); split-K x tile for small-M layers
@@ -143,6 +143,15 @@ extern "C" cpd_status cpd_gemm_conv(const cpd_gemm_params* p, void* stream) {
     }
   }
   return cpd_gemm_conv_dispatch(p, stream);  // cost model (pick_tiles)
+}
+
+// Runtime switch of the per-shape timing (the environment variable CPD_GEMM_AUTOTUNE only sets the initial state) and a way to
+// forget the table: jobs that need the SAME tile variants for every batch size (bit-identical images whatever they are batched
+// with) switch the timing off and clear the table, or import one table everywhere.
+extern "C" void cpd_gemm_set_autotune(int on) { g_autotune = on ? 1 : 0; }
+extern "C" void cpd_gemm_tune_clear(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_table.clear();
 }
 
 extern "C" int64_t cpd_gemm_tune_export(char* buf, int64_t cap) {

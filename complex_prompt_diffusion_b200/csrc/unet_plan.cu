@@ -269,7 +269,10 @@ struct cpd_unet_plan {
   std::vector<FoldJob> folds;
   bool fold_ln = true, fold_dirty = true;
   int fold_geglu_min_ch = 640;
-  int64_t fold_min_rows = 2048;  // levels with fewer tokens keep the LayerNorm kernels (their GEMMs want split-K / one-tile variants)
+  // Levels with fewer pixels PER IMAGE keep the LayerNorm kernels (their GEMMs want split-K / one-tile variants).  The decision
+  // must not depend on the batch or on the rows per image: an image has to come out the same whatever it is batched with
+  // (tools/check_rowshard.py: image-sharded and row-sharded runs are bit-identical to the single-GPU run).
+  int fold_min_hw = 256;
   // GroupNorm statistics from the producing conv's epilogue (cpd_gemm_params.gn_sums_out): one zeroed arena of fixed-point
   // accumulators per forward, handed out in launch order.  OPT-IN (CPD_UNET_GN_STATS=1): measured on B200 (tools/bench_gnstats.py)
   // the ~300 extra epilogue instructions per 128 x 32 chunk are NOT hidden behind the main loop of the 3x3 convolutions (64 x 64:
@@ -893,7 +896,7 @@ void ln_consumer(FwdCtx& F, GemmOpt& g, const float* gvec, const float* bias_fol
 cpd_status ln_setup(FwdCtx& F, int64_t T, int ch) {
   F.lnp = nullptr;
   F.ln_parts = 0;
-  if (!F.P->fold_ln || T < F.P->fold_min_rows) return CPD_OK;
+  if (!F.P->fold_ln || F.h * F.w < F.P->fold_min_hw) return CPD_OK;
   void* b;
   const int64_t max_parts = 2 * ((ch + 63) / 64);  // narrowest tile the tuner may pick: 64 columns x two epilogue groups
   PLAN_CHECK(ws_get(F.P, "tr.lnpart", max_parts * T * 2, 4, &b));
@@ -1284,7 +1287,13 @@ cpd_status forward_impl(cpd_unet_plan* P, const cpd_unet_io* io, void* eps_out, 
     PLAN_CHECK(ws_get(P, "tr.h", (int64_t)R * hw * cout, 2, &hr));
     PLAN_CHECK(expand_images(P, st, hb, hr, B, rpi, hw * cout));
     xres = Act{xr, cout};
-    PLAN_CHECK(ln_setup(F, (int64_t)R * hw, cout));  // the expanded rows carry no statistics: LN2 of this block runs as a kernel
+    // the partial sums of the per-image rows are repeated like the rows themselves ([part][image] -> [part][image][row]), so that
+    // LN2 of this block is folded exactly as it is when every row is evaluated (results independent of the sharing)
+    PLAN_CHECK(ln_setup(F, (int64_t)R * hw, cout));
+    if (F.lnp && Fb.lnp && Fb.ln_parts > 0) {
+      PLAN_CHECK(expand_images(P, st, Fb.lnp, F.lnp, Fb.ln_parts * B, rpi, hw * 4));  // float2 per row = four 16-bit units
+      F.ln_parts = Fb.ln_parts;
+    }
     PLAN_CHECK(tblock_rest(F, b0, hr, cout));
     for (int d = 1; d < depth; ++d) {
       const std::string bd = pa + "transformer_blocks." + std::to_string(d) + ".";
@@ -1370,8 +1379,8 @@ extern "C" cpd_status cpd_unet_plan_create(const cpd_unet_config* cfg, cpd_unet_
     P->share_prefix = !(e && e[0] == '0');
     e = getenv("CPD_UNET_FOLD_LN");
     P->fold_ln = !(e && e[0] == '0');
-    e = getenv("CPD_UNET_FOLD_MIN_ROWS");
-    if (e && atoll(e) > 0) P->fold_min_rows = atoll(e);
+    e = getenv("CPD_UNET_FOLD_MIN_HW");
+    if (e && atoi(e) > 0) P->fold_min_hw = atoi(e);
     e = getenv("CPD_UNET_GN_STATS");
     P->gn_stats = e && e[0] == '1';
     e = getenv("CPD_UNET_FOLD_GEGLU_MIN_CH");

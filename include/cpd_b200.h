@@ -261,6 +261,10 @@ typedef struct {
 
 cpd_status cpd_gemm_conv(const cpd_gemm_params* p, void* stream);
 
+/* Runtime switch of the per-shape timing of cpd_gemm_conv's variant 0 (initial state: CPD_GEMM_AUTOTUNE, default on) and a reset of
+ * the tuned table.  With the timing off variant 0 resolves through the deterministic cost model. */
+void cpd_gemm_set_autotune(int on);
+void cpd_gemm_tune_clear(void);
 /* The per-shape variant table behind variant 0.  Timing picks between candidates that are often within a few per cent, so two
  * processes can choose differently (different fp32 summation order at the 1e-7 level): export the table of one process and
  * import it into the others (ranks of a job) - or set CPD_GEMM_AUTOTUNE=0 - when bit-identical results across processes

@@ -371,6 +371,44 @@ def test_unet_forward_rows_equals_forward(cpd):
     assert rel(a.float().cpu(), b.float().cpu()) < 5e-3
 
 
+def test_unet_rows_do_not_depend_on_the_batch_or_on_the_shared_prefix(cpd, monkeypatch):
+    """An image must come out bit-identical whatever it is batched with (image-sharded and row-sharded multi-GPU runs rely on it):
+    the choices the executor makes per level - LayerNorm folded into the GEMMs or not, the prefix in front of the first
+    cross-attention evaluated once per image or per row - may depend on the level, never on the batch or the rows per image."""
+    from complex_prompt_diffusion_b200.models.unet import UNetModel
+    from complex_prompt_diffusion_b200.models import fixtures
+    cfg = fixtures.UNET_PRESETS["tiny"]
+    sd = fixtures.random_state_dict(fixtures.unet_param_shapes(cfg), seed=3)
+    from complex_prompt_diffusion_b200 import _lib
+    lib = _lib.load()
+    lib.cpd_gemm_set_autotune(0)  # timed tile choices differ per shape, and a split-K variant changes the summation order
+    lib.cpd_gemm_tune_clear()
+    try:
+        _rows_invariance(monkeypatch, UNetModel, fixtures, cfg, sd)
+    finally:
+        lib.cpd_gemm_set_autotune(1)
+
+
+def _rows_invariance(monkeypatch, UNetModel, fixtures, cfg, sd):
+    shared = UNetModel(sd, device=DEV, **fixtures.unet_kwargs("tiny"))
+    monkeypatch.setenv("CPD_UNET_SHARE_PREFIX", "0")
+    every_row = UNetModel(sd, device=DEV, **fixtures.unet_kwargs("tiny"))
+    g = torch.Generator().manual_seed(1)
+    B, R, hw = 3, 2, 32
+    x = torch.randn(B, 4, hw, hw, generator=g).to(DEV)
+    ctx = torch.randn(R, 77, cfg["context_dim"], generator=g).to(DEV)
+    outs = []
+    for m in (shared, every_row):
+        m.set_context(ctx)
+        outs.append(m.forward_rows(x, 0.3, 421.0, R).float().clone())
+    assert torch.equal(outs[0], outs[1]), "the shared prefix changed the result"
+    one = shared.forward_rows(x[1:2].contiguous(), 0.3, 421.0, R).float().clone()
+    assert torch.equal(one, outs[0][R:2 * R]), "an image depends on the batch it is evaluated in"
+    shared.set_context(ctx[1:2].contiguous())
+    row = shared.forward_rows(x, 0.3, 421.0, 1).float().clone()  # one conditioning row per image: the row-sharded layout
+    assert torch.equal(row, outs[0][1::R]), "a row depends on the other rows of its image"
+
+
 @pytest.mark.parametrize("name,steps", [("DPM++ 2m", 6), ("Euler", 6), ("Euler Ancestral", 6)])
 def test_end_to_end_sampling_vs_oracle_bf16(cpd, name, steps):
     """Whole drop-in path on the GPU (bf16 UNet kernels) vs the oracle run with bf16-rounded weights:

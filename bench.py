@@ -526,7 +526,7 @@ def run_b200(args):
                                           "and are reported under bf16_activations)") if args.act_dtype == "fp16" else
                                          ("bf16 model weights and bf16 activations, fp32 accumulation and norm statistics "
                                           "(per-step eps error ~1.3e-2: the noise floor of any bf16 evaluation of this UNet)"),
-                               executor="one CUDA graph per SAMPLER STEP: [cpd_step_select -> C++ UNet plan (cpd_unet_forward, ~850 kernels, PDL edges) -> "
+                               executor="one CUDA graph per SAMPLER STEP: [cpd_step_select -> C++ UNet plan (cpd_unet_forward, ~350 kernels, PDL edges) -> "
                                         "cpd_sampler_step], per-step scalars read from a device table, replayed 20 times per generation"),
                 "unet_evals_per_s": evals_per_step * world * args.steps / (ms / 1e3),
                 "e2e": {"value": ips_e2e, "unit": "images/s",

@@ -448,6 +448,267 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(640, 1)
   }
 }
 
+// ---- GroupNorm, single pass with the slab in SHARED memory (round 2, end): one block owns a pixel range of (image, slab of whole
+// groups); the slab's pixels are split over a cluster of CL blocks when they do not fit one block.  Every thread fetches its
+// 16-byte vectors with cp.async into slots only it reads (no register cost: any number in flight, two to four blocks per SM, so
+// one block's loads overlap another's arithmetic and stores - an SM ingests ~46 B / clk, 1/148 of what the L2 delivers, so every
+// SM has to be loading all the time).  The first version of this kernel executed 20 instructions per element (ncu: issue slots
+// 54 % busy, DRAM 19 %), 43 % of them outside the two passes over the data - so this one is built around the instruction count:
+// * grid = (cluster rank, slab, image) and multiply-shift divisions by the host's magic numbers: no integer division;
+// * packed fp32 arithmetic (FADD2 / FFMA2, sm_100) in both passes;
+// * a vector of 8 channels lies in at most two groups (an even number of channels per group), so a thread ends with four sums
+//   (S, SS of its first and of its second group); lanes that hold the same channel vector are folded with shuffles, one lane per
+//   (vector, warp) writes them to shared memory and 2 x (groups of the slab) threads add them up in a fixed order in fp64;
+// * cluster blocks exchange the per-group partials through distributed shared memory, one (group, rank) pair per thread, summed
+//   by a butterfly over the ranks: every block gets the same bits, and nothing depends on timing (bit-reproducible).
+// Slabs are 32-byte-sector aligned where the channel count allows (80 channels at 10 / 20 / 40 channels per group), so no sector
+// is fetched by two blocks.
+template <bool F16, bool SILU>
+__global__ void __launch_bounds__(512, 2)  // <= 64 registers: four blocks of 256 threads or two of 512 per SM
+    gn_slab_kernel(const bf16* __restrict__ a0, const bf16* __restrict__ a1, int c0, int c1, int hw, int slab_c, int lanes, int ppc,
+                   uint32_t magic_vps, uint32_t magic_cpg, int hdr, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   float eps, bf16* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char slab_raw[];
+  double* part = reinterpret_cast<double*>(slab_raw);        // [groups of the slab][2]: this block's (S, SS)
+  float* gstat = reinterpret_cast<float*>(slab_raw + 128);   // [groups of the slab][2]: mean, rstd
+  float4* red = reinterpret_cast<float4*>(slab_raw + 192);   // [vector of the slab][warp]: (S, SS) of its two groups
+  pdl_launch_dependents();
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int C = c0 + c1;
+  const int cpg = C >> 5;
+  const int vps = slab_c >> 3;
+  const int gslab = (int)(((uint32_t)slab_c * magic_cpg) >> 16);
+  const int cl = gridDim.x, rank = blockIdx.x;  // the cluster spans the grid's x dimension
+  const int ch0 = blockIdx.y * slab_c;
+  const int n = blockIdx.z;
+  const int p_begin = rank * ppc, p_end = min(hw, p_begin + ppc);
+  const int pl = (int)(((uint32_t)tid * magic_vps) >> 16);  // tid / vps
+  const int cv = tid - pl * vps;
+  const int ch = ch0 + cv * 8;
+  // pairs [0, split2) of the vector's four channel pairs belong to group gA of the slab, the rest to gA + 1
+  const int gA = (int)(((uint32_t)(cv * 8) * magic_cpg) >> 16);
+  const int split2 = min(4, ((gA + 1) * cpg - cv * 8) >> 1);
+  // the affine parameters are weights: not written by the previous kernel, fetched in front of the dependency wait
+  const float4 gm0 = __ldg(reinterpret_cast<const float4*>(gamma + ch)), gm1 = __ldg(reinterpret_cast<const float4*>(gamma + ch + 4));
+  const float4 bt0 = __ldg(reinterpret_cast<const float4*>(beta + ch)), bt1 = __ldg(reinterpret_cast<const float4*>(beta + ch + 4));
+  const bf16* src;
+  int cs, coff;
+  if (ch < c0) { src = a0; cs = c0; coff = ch; } else { src = a1; cs = c1; coff = ch - c0; }
+  const uint32_t slot0 = smem_u32(slab_raw + hdr) + tid * 16, sstep = T * 16;
+  int np = 0;  // pixels of this thread
+  pdl_wait();
+  if (pl < lanes) {
+    const char* gp = reinterpret_cast<const char*>(src + ((int64_t)n * hw + p_begin + pl) * cs + coff);
+    const int64_t gstep = (int64_t)lanes * cs * 2;
+    uint32_t sa = slot0;
+    for (int p = p_begin + pl; p < p_end; p += lanes, ++np, sa += sstep, gp += gstep)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gp) : "memory");
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  float2 s[4], q[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) s[e] = q[e] = make_float2(0.f, 0.f);
+#pragma unroll 4
+  for (int j = 0; j < np; ++j) {
+    const uint4 v = lds128(slot0 + j * sstep);
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = unpack_act2(u[e], F16);
+      s[e] = __fadd2_rn(s[e], f);
+      q[e] = __ffma2_rn(f, f, q[e]);
+    }
+  }
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);  // (S, SS) of group gA, (S, SS) of group gA + 1
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float a = s[e].x + s[e].y, b = q[e].x + q[e].y;
+    if (e < split2) { acc.x += a; acc.y += b; } else { acc.z += a; acc.w += b; }
+  }
+  const int warp = tid >> 5, lane = tid & 31, nwarps = T >> 5;
+  const float4 own = acc;  // lanes l, l + vps, l + 2 vps, ... of a warp hold the same channel vector: lane l < vps adds them up
+  for (int k = vps; k < 32; k += vps) {
+    const float x = __shfl_down_sync(0xffffffffu, own.x, k), y = __shfl_down_sync(0xffffffffu, own.y, k);
+    const float z = __shfl_down_sync(0xffffffffu, own.z, k), w = __shfl_down_sync(0xffffffffu, own.w, k);
+    if (lane + k < 32) { acc.x += x; acc.y += y; acc.z += z; acc.w += w; }
+  }
+  if (lane < vps) red[cv * nwarps + warp] = acc;
+  __syncthreads();
+  if (tid < 2 * gslab) {  // fixed order over the vectors of the group and the warps
+    const int g = tid >> 1, st = tid & 1;
+    const int cv_lo = (g * cpg) >> 3, cv_hi = ((g + 1) * cpg - 1) >> 3;
+    const float* redf = reinterpret_cast<const float*>(red);
+    double a = 0.0;
+    for (int c = cv_lo; c <= cv_hi; ++c) {
+      const int gc = (int)(((uint32_t)(c * 8) * magic_cpg) >> 16);
+      const float* col = redf + (size_t)c * nwarps * 4 + (gc == g ? st : 2 + st);
+      for (int w = 0; w < nwarps; ++w) a += (double)col[w * 4];
+    }
+    part[tid] = a;
+  }
+  if (cl > 1) cluster_sync_all(); else __syncthreads();  // every block's partials are written (and visible cluster-wide)
+  if (tid < gslab * cl) {  // thread (group, rank) fetches one pair; the ranks of a group are neighbouring lanes (cl = 2^k)
+    const int lg = __ffs(cl) - 1;
+    const int g = tid >> lg, r = tid & (cl - 1);
+    double S, SS;
+    if (cl > 1) {
+      uint32_t raddr;
+      unsigned long long b0, b1;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(part + g * 2)), "r"(r));
+      asm volatile("ld.shared::cluster.b64 %0, [%1];" : "=l"(b0) : "r"(raddr));
+      asm volatile("ld.shared::cluster.b64 %0, [%1];" : "=l"(b1) : "r"(raddr + 8));
+      S = __longlong_as_double((long long)b0);
+      SS = __longlong_as_double((long long)b1);
+      const int here = gslab * cl - (tid & ~31);  // threads of this warp inside the branch: whole groups of cl lanes
+      const unsigned mask = here >= 32 ? 0xffffffffu : (1u << here) - 1u;
+      for (int o = 1; o < cl; o <<= 1) {
+        S += __shfl_xor_sync(mask, S, o);
+        SS += __shfl_xor_sync(mask, SS, o);
+      }
+    } else {
+      S = part[2 * g];
+      SS = part[2 * g + 1];
+    }
+    if (r == 0) {
+      const double cnt = (double)hw * cpg;
+      const double mean = S / cnt;
+      double var = SS / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      gstat[2 * g] = (float)mean;
+      gstat[2 * g + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+  }
+  if (cl > 1) cluster_sync_all(); else __syncthreads();  // nobody leaves while a peer may still read its partials; orders gstat
+  if (np == 0) return;
+  float2 sc[4], sf[4];
+  {
+    const int gB = min(gA + 1, gslab - 1);
+    const float mA = gstat[2 * gA], rA = gstat[2 * gA + 1], mB = gstat[2 * gB], rB = gstat[2 * gB + 1];
+    const float gm[8] = {gm0.x, gm0.y, gm0.z, gm0.w, gm1.x, gm1.y, gm1.z, gm1.w};
+    const float bt[8] = {bt0.x, bt0.y, bt0.z, bt0.w, bt1.x, bt1.y, bt1.z, bt1.w};
+    // SiLU(y) = h + h tanh(h) with h = y / 2: the halving is folded into scale and shift (exact)
+    const float half = SILU ? 0.5f : 1.0f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float r = (e < split2 ? rA : rB) * half, m = e < split2 ? mA : mB;
+      sc[e].x = r * gm[2 * e];
+      sc[e].y = r * gm[2 * e + 1];
+      sf[e].x = fmaf(-m, sc[e].x, half * bt[2 * e]);
+      sf[e].y = fmaf(-m, sc[e].y, half * bt[2 * e + 1]);
+    }
+  }
+  char* op = reinterpret_cast<char*>(out + ((int64_t)n * hw + p_begin + pl) * C + ch);
+  const int64_t ostep = (int64_t)lanes * C * 2;
+#pragma unroll 2
+  for (int j = 0; j < np; ++j, op += ostep) {
+    const uint4 v = lds128(slot0 + j * sstep);
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float2 y = __ffma2_rn(unpack_act2(u[e], F16), sc[e], sf[e]);
+      if (SILU) {
+        float2 t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(y.x));
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(y.y));
+        y = __ffma2_rn(y, t, y);
+      }
+      o[e] = pack_act2(y.x, y.y, F16);
+    }
+    *reinterpret_cast<uint4*>(op) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// Launch with an optional cluster dimension (the cluster size is a runtime choice of the shape) and programmatic dependent launch.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_clustered(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (cl > 1) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = cl;
+    at[na].val.clusterDim.y = 1;
+    at[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (cpd_pdl_enabled()) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e && e[0] ? atoi(e) : dflt;
+}
+
+// Shape -> (slab channels, cluster size, pixel lanes, threads, slots per thread) of gn_slab_kernel; false = the shape does not fit.
+struct SlabChoice { int slab_c, cl, lanes, threads, slots, ppc, hdr; uint32_t magic_vps, magic_cpg; size_t smem; };
+// x / d == (x * magic) >> 16 for every x < limit?  (the kernel divides thread ids by the vectors per pixel and channels by the group size)
+bool magic_div(int d, int limit, uint32_t* magic) {
+  const uint32_t m = (65536u + d - 1) / d;
+  for (int x = 0; x < limit; ++x)
+    if ((int)(((uint32_t)x * m) >> 16) != x / d) return false;
+  *magic = m;
+  return true;
+}
+bool choose_slab(int C, int hw, SlabChoice* o) {
+  const int cpg = C / GROUPS;
+  if (cpg < 4 || cpg % 2 || (cpg < 8 && cpg != 4)) return false;  // a vector of 8 channels: at most two groups, split at an even channel
+  auto lcm = [](int a, int b) { int x = a, y = b; while (y) { const int t = x % y; x = y; y = t; } return a / x * b; };
+  static int small_kb = -1, big_kb = -1, last_kb = -1, unaligned_first = 0, tmax_small = 256, tmax_big = 256;
+  if (small_kb < 0) {
+    small_kb = env_int("CPD_GN_SLAB_KB", 48);         // preferred block size: four blocks per SM
+    big_kb = env_int("CPD_GN_SLAB_BIG_KB", 100);      // two blocks per SM
+    last_kb = env_int("CPD_GN_SLAB_LAST_KB", 0);      // one block per SM: measured slower than the two-kernel path (16 x 4096 x 960)
+    unaligned_first = env_int("CPD_GN_SLAB_UNALIGNED", 0);
+    tmax_small = env_int("CPD_GN_SLAB_T", 256);       // threads per block: fewer threads = more vectors each = less fixed cost
+    tmax_big = env_int("CPD_GN_SLAB_BIG_T", 256);
+  }
+  int slabs[2] = {lcm(cpg, 16), lcm(cpg, 8)};  // [0]: sector-aligned (32 bytes), [1]: the smallest slab of whole groups and vectors
+  while (slabs[0] * 2 < 128 && slabs[0] * 2 <= C && (slabs[0] * 2) / cpg <= 8) slabs[0] *= 2;  // at least a 128-byte line per pixel
+  // candidate order: aligned small, aligned big, unaligned small, unaligned big, then the one-block-per-SM sizes
+  const int a = unaligned_first ? 1 : 0, u = 1 - a;
+  const int order[6][2] = {{a, small_kb}, {a, big_kb}, {u, small_kb}, {u, big_kb}, {a, last_kb}, {u, last_kb}};
+  for (const auto& cand : order) {
+    const int slab_c = slabs[cand[0]], limit_kb = cand[1];
+    if (limit_kb <= 0 || C % slab_c || slab_c / cpg > 8) continue;
+    const int vps = slab_c / 8;
+    int tmax = limit_kb <= small_kb ? tmax_small : tmax_big;
+    if (tmax > 512) tmax = 512;
+    if (vps > 32 || vps > tmax) continue;
+    uint32_t mv, mc;
+    if (!magic_div(vps, 512, &mv) || !magic_div(cpg, slab_c + 1, &mc)) continue;
+    for (int cl : {1, 2, 4, 8}) {
+      if (cl > hw) break;
+      const int ppc = (hw + cl - 1) / cl;
+      if ((int64_t)ppc * slab_c * 2 > (int64_t)limit_kb * 1024) continue;
+      int lanes = tmax / vps;
+      if (lanes > ppc) lanes = ppc;
+      const int slots = (ppc + lanes - 1) / lanes;
+      lanes = (ppc + slots - 1) / slots;
+      const int threads = ((lanes * vps + 31) / 32) * 32;
+      if (threads < 2 * (slab_c / cpg) || threads < (slab_c / cpg) * cl) continue;  // the reduction's (group, statistic) / (group, rank) threads
+      const int hdr = 192 + vps * (threads / 32) * 16;
+      const size_t smem = (size_t)hdr + (size_t)slots * threads * 16;
+      if (smem > 220 * 1024) continue;
+      *o = {slab_c, cl, lanes, threads, slots, ppc, hdr, mv, mc, smem};
+      return true;
+    }
+  }
+  return false;
+}
+
 // ---- LayerNorm: one warp per R rows (all loads of the R rows issued before the first use), rows in registers -----
 template <int MAXV, int R>  // max 16-byte vectors per lane, rows per warp
 __global__ void __launch_bounds__(256, 4) layernorm_kernel(const bf16* __restrict__ x, int rows, int c,
@@ -614,6 +875,26 @@ extern "C" cpd_status cpd_groupnorm(const void* a0, const void* a1, int c0, int 
   CPD_REQUIRE(c1 == 0 || a1, "cpd_groupnorm: c1 > 0 needs a1");
   CPD_REQUIRE(n_img > 0 && hw > 0, "cpd_groupnorm: empty input");
   cudaStream_t s = (cudaStream_t)stream;
+  {  // single pass with the slab in shared memory, split over a cluster where needed (CPD_GN_SLAB=0: the older kernels below)
+    static int slab_on = -1;
+    if (slab_on < 0) slab_on = env_int("CPD_GN_SLAB", 1);
+    SlabChoice sc;
+    if (slab_on && n_img <= 65535 && choose_slab(C, hw, &sc)) {
+      const dim3 grid(sc.cl, C / sc.slab_c, n_img);  // the cluster is the grid's x dimension
+#define CPD_GN_SLAB_LAUNCH(F, S)                                                                                                  \
+  do {                                                                                                                            \
+    CPD_SMEM_OPTIN((gn_slab_kernel<F, S>), 220 * 1024);                                                                           \
+    CPD_CUDA_CHECK(launch_clustered(gn_slab_kernel<F, S>, grid, dim3(sc.threads), sc.smem, s, sc.cl, (const bf16*)a0,             \
+                                    (const bf16*)a1, c0, c1, hw, sc.slab_c, sc.lanes, sc.ppc, sc.magic_vps, sc.magic_cpg, sc.hdr, \
+                                    gamma, beta, eps, (bf16*)out));                                                               \
+  } while (0)
+      if (act_fp16) { if (silu) CPD_GN_SLAB_LAUNCH(true, true); else CPD_GN_SLAB_LAUNCH(true, false); }
+      else { if (silu) CPD_GN_SLAB_LAUNCH(false, true); else CPD_GN_SLAB_LAUNCH(false, false); }
+#undef CPD_GN_SLAB_LAUNCH
+      CPD_CUDA_CHECK(cudaGetLastError());
+      return CPD_OK;
+    }
+  }
   {  // single-pass kernel when (image, slab of whole groups) fits the register file of one block
     const int cpg = C / GROUPS;
     int slab_c = cpg;

@@ -339,7 +339,12 @@ def test_cross_attention_shared_context(ops, B, kvb, H, Nq, d, dtype):
 
 # ------------------------------------------------------------------------------------------------ norms / small ops
 @pytest.mark.parametrize("n,hw,c0,c1,silu,eps", [(2, 4096, 320, 0, True, 1e-5), (3, 64, 1280, 1280, True, 1e-5), (1, 1024, 640, 320, False, 1e-6),
-                                                  (2, 256, 64, 0, True, 1e-5), (16, 4096, 320, 320, True, 1e-5)])
+                                                  (2, 256, 64, 0, True, 1e-5), (16, 4096, 320, 320, True, 1e-5),
+                                                  # shared-memory slab kernel: cluster sizes 1 / 2 / 4 / 8, ragged pixel ranges, slabs that
+                                                  # straddle the two inputs, 4 / 16 / 30 / 60 channels per group, the one-block-per-SM size
+                                                  (2, 9216, 320, 0, True, 1e-5), (2, 576, 640, 640, True, 1e-5), (4, 144, 1280, 0, False, 1e-5),
+                                                  (1, 1024, 1280, 640, True, 1e-5), (2, 4096, 640, 320, True, 1e-5), (2, 256, 128, 0, True, 1e-6),
+                                                  (1, 100, 512, 0, False, 1e-6), (3, 7, 320, 0, True, 1e-5), (2, 2304, 320, 0, True, 1e-5)])
 def test_groupnorm(ops, n, hw, c0, c1, silu, eps):
     g = torch.Generator().manual_seed(hw + c0)
     C = c0 + c1

@@ -10,7 +10,8 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-GN = [(16, 4096, 320), (16, 1024, 640), (16, 256, 1280), (16, 64, 1280), (16, 4096, 640), (16, 256, 2560), (16, 1024, 1920)]
+GN = [(16, 4096, 320), (16, 1024, 640), (16, 256, 1280), (16, 64, 1280), (16, 4096, 640), (16, 256, 2560), (16, 1024, 1920),
+      (16, 4096, 960), (4, 4096, 320), (16, 1024, 960), (2, 9216, 320), (2, 2304, 640)]
 LN = [(65536, 320), (16384, 640), (4096, 1280)]
 
 
@@ -39,10 +40,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=24)
     ap.add_argument("--only", default="")
+    ap.add_argument("--gn-index", type=int, default=-1, help="run only this entry of the GroupNorm shape list")
     a = ap.parse_args()
     from complex_prompt_diffusion_b200 import ops
     dev = "cuda"
-    for (n, hw, C) in GN if a.only in ("", "gn") else []:
+    gn = GN if a.gn_index < 0 else [GN[a.gn_index]]
+    for (n, hw, C) in gn if a.only in ("", "gn") else []:
         nbuf = max(2, int(400e6 // (n * hw * C * 2)) + 1)
         nbuf = min(nbuf, 24)
         xs = [torch.randn(n * hw, C, device=dev).to(torch.float16) for _ in range(nbuf)]

@@ -483,6 +483,23 @@ __device__ __forceinline__ float gelu_sig_f(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
   return x * r;
 }
+// Two gates at once with packed fp32 arithmetic (FMUL2 / FFMA2 / FADD2, sm_100): the same IEEE operations per lane as
+// gelu_sig_f - bit-identical results - in 14 issue slots per pair instead of 22.
+__device__ __forceinline__ float2 gelu_sig_f2(float2 x) {
+  float2 t = __fmul2_rn(x, x);
+  t.x = fminf(t.x, 36.0f);
+  t.y = fminf(t.y, 36.0f);
+  float2 p = __ffma2_rn(t, make_float2(-3.2289963530e-06f, -3.2289963530e-06f), make_float2(8.8238257537e-05f, 8.8238257537e-05f));
+  p = __ffma2_rn(p, t, make_float2(3.6027394776e-04f, 3.6027394776e-04f));
+  p = __ffma2_rn(p, t, make_float2(-1.0522668698e-01f, -1.0522668698e-01f));
+  p = __ffma2_rn(p, t, make_float2(-2.3020453906e+00f, -2.3020453906e+00f));
+  const float2 xp = __fmul2_rn(x, p);
+  const float2 e = __fadd2_rn(make_float2(fast_ex2(xp.x), fast_ex2(xp.y)), make_float2(1.0f, 1.0f));
+  float2 r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(e.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(e.y));
+  return __fmul2_rn(x, r);
+}
 // (a0 * b0, a1 * b1) of two packed 16-bit pairs, rounded once to the activation format (one HMUL2)
 __device__ __forceinline__ uint32_t mul_act2(uint32_t a, uint32_t b, bool f16) {
   if (f16) {

@@ -665,16 +665,21 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
             for (int e = 0; e < 32; e += 4) {
               const float4 bv = lds128f(smem_u32(bias_v + e)), bg = lds128f(smem_u32(bias_v + (bn >> 1) + e));
               const float4 gv = lds128f(smem_u32(g_v + e)), gg = lds128f(smem_u32(g_v + (bn >> 1) + e));
-              const uint32_t a01 = pack_act2(fmaf(__uint_as_float(va[e]), ln_rstd, fmaf(ln_nm, gv.x, bv.x)),
-                                             fmaf(__uint_as_float(va[e + 1]), ln_rstd, fmaf(ln_nm, gv.y, bv.y)), of16);
-              const uint32_t a23 = pack_act2(fmaf(__uint_as_float(va[e + 2]), ln_rstd, fmaf(ln_nm, gv.z, bv.z)),
-                                             fmaf(__uint_as_float(va[e + 3]), ln_rstd, fmaf(ln_nm, gv.w, bv.w)), of16);
-              const float g0 = fmaf(__uint_as_float(vg[e]), ln_rstd, fmaf(ln_nm, gg.x, bg.x));
-              const float g1 = fmaf(__uint_as_float(vg[e + 1]), ln_rstd, fmaf(ln_nm, gg.y, bg.y));
-              const float g2 = fmaf(__uint_as_float(vg[e + 2]), ln_rstd, fmaf(ln_nm, gg.z, bg.z));
-              const float g3 = fmaf(__uint_as_float(vg[e + 3]), ln_rstd, fmaf(ln_nm, gg.w, bg.w));
-              packed[e >> 1] = mul_act2(a01, pack_act2(gelu_sig_f(g0), gelu_sig_f(g1), of16), of16);
-              packed[(e >> 1) + 1] = mul_act2(a23, pack_act2(gelu_sig_f(g2), gelu_sig_f(g3), of16), of16);
+              // packed fp32 pairs (FFMA2 / FMUL2 / FADD2, sm_100): the same operations per lane - bit-identical - in about two
+              // thirds of the issue slots (65536 x 2560 x 320: 139 -> 131 us).  The plain bias / residual / LayerNorm-sum epilogues
+              // were measured 1-3 % SLOWER with packed arithmetic (register-pair moves) and keep scalar instructions.
+              const float2 rs2 = make_float2(ln_rstd, ln_rstd), nm2 = make_float2(ln_nm, ln_nm);
+              const float2 v01 = __ffma2_rn(make_float2(__uint_as_float(va[e]), __uint_as_float(va[e + 1])), rs2,
+                                            __ffma2_rn(nm2, make_float2(gv.x, gv.y), make_float2(bv.x, bv.y)));
+              const float2 v23 = __ffma2_rn(make_float2(__uint_as_float(va[e + 2]), __uint_as_float(va[e + 3])), rs2,
+                                            __ffma2_rn(nm2, make_float2(gv.z, gv.w), make_float2(bv.z, bv.w)));
+              const float2 g01 = __ffma2_rn(make_float2(__uint_as_float(vg[e]), __uint_as_float(vg[e + 1])), rs2,
+                                            __ffma2_rn(nm2, make_float2(gg.x, gg.y), make_float2(bg.x, bg.y)));
+              const float2 g23 = __ffma2_rn(make_float2(__uint_as_float(vg[e + 2]), __uint_as_float(vg[e + 3])), rs2,
+                                            __ffma2_rn(nm2, make_float2(gg.z, gg.w), make_float2(bg.z, bg.w)));
+              const float2 y01 = gelu_sig_f2(g01), y23 = gelu_sig_f2(g23);
+              packed[e >> 1] = mul_act2(pack_act2(v01.x, v01.y, of16), pack_act2(y01.x, y01.y, of16), of16);
+              packed[(e >> 1) + 1] = mul_act2(pack_act2(v23.x, v23.y, of16), pack_act2(y23.x, y23.y, of16), of16);
             }
           } else {
 #pragma unroll
@@ -684,12 +689,13 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
                 bv = lds128f(smem_u32(bias_v + e));
                 bg = lds128f(smem_u32(bias_v + (bn >> 1) + e));
               }
-              const uint32_t a01 = pack_act2(__uint_as_float(va[e]) + bv.x, __uint_as_float(va[e + 1]) + bv.y, of16);
-              const uint32_t a23 = pack_act2(__uint_as_float(va[e + 2]) + bv.z, __uint_as_float(va[e + 3]) + bv.w, of16);
-              const float g0 = __uint_as_float(vg[e]) + bg.x, g1 = __uint_as_float(vg[e + 1]) + bg.y;
-              const float g2 = __uint_as_float(vg[e + 2]) + bg.z, g3 = __uint_as_float(vg[e + 3]) + bg.w;
-              packed[e >> 1] = mul_act2(a01, pack_act2(gelu_sig_f(g0), gelu_sig_f(g1), of16), of16);
-              packed[(e >> 1) + 1] = mul_act2(a23, pack_act2(gelu_sig_f(g2), gelu_sig_f(g3), of16), of16);
+              const float2 v01 = __fadd2_rn(make_float2(__uint_as_float(va[e]), __uint_as_float(va[e + 1])), make_float2(bv.x, bv.y));
+              const float2 v23 = __fadd2_rn(make_float2(__uint_as_float(va[e + 2]), __uint_as_float(va[e + 3])), make_float2(bv.z, bv.w));
+              const float2 g01 = __fadd2_rn(make_float2(__uint_as_float(vg[e]), __uint_as_float(vg[e + 1])), make_float2(bg.x, bg.y));
+              const float2 g23 = __fadd2_rn(make_float2(__uint_as_float(vg[e + 2]), __uint_as_float(vg[e + 3])), make_float2(bg.z, bg.w));
+              const float2 y01 = gelu_sig_f2(g01), y23 = gelu_sig_f2(g23);
+              packed[e >> 1] = mul_act2(pack_act2(v01.x, v01.y, of16), pack_act2(y01.x, y01.y, of16), of16);
+              packed[(e >> 1) + 1] = mul_act2(pack_act2(v23.x, v23.y, of16), pack_act2(y23.x, y23.y, of16), of16);
             }
           }
         } else {

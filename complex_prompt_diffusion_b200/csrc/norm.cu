@@ -218,236 +218,6 @@ __global__ void __launch_bounds__(512, 2) gn_apply_kernel(const bf16* __restrict
   }
 }
 
-// ---- GroupNorm, single pass for slabs that fit the register file: one block owns every pixel of (image, slab of whole
-// groups whose channel count is a multiple of 8).  The slab is read once into registers (<= V 16-byte vectors per thread),
-// reduced (fp32 per thread -> fp32 over pixel lanes -> fp64 over the channels of a group, fixed order), normalised from the
-// registers and written: one read + one write of the tensor, one launch.
-template <bool F16, int V>
-__global__ void __launch_bounds__(640, 1) gn_fused_kernel(const bf16* __restrict__ a0, const bf16* __restrict__ a1, int c0,
-                                                          int c1, int hw, int slab_c, const float* __restrict__ gamma,
-                                                          const float* __restrict__ beta, float eps, int silu,
-                                                          bf16* __restrict__ out) {
-  extern __shared__ __align__(16) float sh[];  // [lanes][2][slab_c] partial sums, then scale[slab_c], shift[slab_c]
-  pdl_launch_dependents();
-  pdl_wait();
-  const int C = c0 + c1;
-  const int cpg = C / GROUPS;
-  const int vps = slab_c / 8;  // vectors per pixel of the slab
-  const int lanes = blockDim.x / vps;
-  const int n = blockIdx.y;
-  const int ch0 = blockIdx.x * slab_c;  // first channel of the slab (slabs never straddle a0 | a1)
-  const int cv = threadIdx.x % vps;
-  const int pl = threadIdx.x / vps;
-  const int ch = ch0 + cv * 8;
-  const bf16* src;
-  int cs, coff;
-  if (ch < c0) { src = a0; cs = c0; coff = ch; } else { src = a1; cs = c1; coff = ch - c0; }
-  const bf16* base = src + ((int64_t)n * hw + pl) * cs + coff;
-  const int64_t step = (int64_t)lanes * cs;
-  uint4 raw[V];
-#pragma unroll
-  for (int j = 0; j < V; ++j) {
-    raw[j] = make_uint4(0, 0, 0, 0);  // zeros add nothing to the sums
-    if (pl + j * lanes < hw) raw[j] = __ldg(reinterpret_cast<const uint4*>(base + j * step));
-  }
-  float s[8], ss[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) s[e] = ss[e] = 0.f;
-#pragma unroll
-  for (int j = 0; j < V; ++j) {
-    const uint32_t u[4] = {raw[j].x, raw[j].y, raw[j].z, raw[j].w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 f = unpack_act2(u[e], F16);
-      s[2 * e] += f.x; ss[2 * e] += f.x * f.x;
-      s[2 * e + 1] += f.y; ss[2 * e + 1] += f.y * f.y;
-    }
-  }
-  {
-    float* mine = sh + (size_t)pl * 2 * slab_c + cv * 8;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      mine[e] = s[e];
-      mine[slab_c + e] = ss[e];
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * slab_c; i += blockDim.x) {
-    float acc = sh[i];
-    for (int l = 1; l < lanes; ++l) acc += sh[(size_t)l * 2 * slab_c + i];
-    sh[i] = acc;
-  }
-  __syncthreads();
-  float* gstat = sh + 2 * slab_c;  // [groups of the slab][2] (lane 1's region: free after the lane reduction... kept separate)
-  const int gslab = slab_c / cpg;
-  if (threadIdx.x < gslab) {
-    const int g = threadIdx.x;
-    double S = 0.0, SS = 0.0;
-    for (int c = 0; c < cpg; ++c) {
-      S += (double)sh[g * cpg + c];
-      SS += (double)sh[slab_c + g * cpg + c];
-    }
-    const double cnt = (double)hw * cpg;
-    const double mean = S / cnt;
-    double var = SS / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    gstat[2 * g] = (float)mean;
-    gstat[2 * g + 1] = (float)(1.0 / sqrt(var + (double)eps));
-  }
-  __syncthreads();
-  float sc[8], sf[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int cl = cv * 8 + e;  // channel inside the slab
-    const int g = (int)__fdividef((float)cl + 0.5f, (float)cpg);
-    const float k = gstat[2 * g + 1] * __ldg(gamma + ch0 + cl);
-    sc[e] = k;
-    sf[e] = __ldg(beta + ch0 + cl) - gstat[2 * g] * k;
-  }
-  bf16* obase = out + ((int64_t)n * hw + pl) * C + ch;
-  const int64_t ostep = (int64_t)lanes * C;
-#pragma unroll
-  for (int j = 0; j < V; ++j) {
-    if (pl + j * lanes < hw) {
-      const uint32_t u[4] = {raw[j].x, raw[j].y, raw[j].z, raw[j].w};
-      uint32_t o[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = unpack_act2(u[e], F16);
-        float y0 = f.x * sc[2 * e] + sf[2 * e];
-        float y1 = f.y * sc[2 * e + 1] + sf[2 * e + 1];
-        if (silu) { y0 = silu_tanh_f(y0); y1 = silu_tanh_f(y1); }
-        o[e] = pack_act2(y0, y1, F16);
-      }
-      *reinterpret_cast<uint4*>(obase + j * ostep) = make_uint4(o[0], o[1], o[2], o[3]);
-    }
-  }
-}
-
-// ---- GroupNorm, single pass over a thread-block CLUSTER: the slab of (image, whole groups) that does not fit one block's
-// register file is split by pixel range over CL blocks; each block keeps its share in registers, the per-group partial sums
-// are exchanged through distributed shared memory (fixed rank order: bit-reproducible), and every block normalises its own
-// share.  One read + one write of the tensor where the two-kernel path reads it twice.
-template <bool F16, int V, int CL>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(640, 1)
-    gn_cluster_kernel(const bf16* __restrict__ a0, const bf16* __restrict__ a1, int c0, int c1, int hw, int slab_c,
-                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu, bf16* __restrict__ out) {
-  extern __shared__ __align__(16) float sh[];  // [lanes][2][slab_c] partial sums; then [groups of the slab][2] doubles at the front
-  pdl_launch_dependents();
-  pdl_wait();
-  const int C = c0 + c1;
-  const int cpg = C / GROUPS;
-  const int vps = slab_c / 8;
-  const int lanes = blockDim.x / vps;
-  const int n = blockIdx.y;
-  const int rank = (int)cluster_ctarank();
-  const int ch0 = (blockIdx.x / CL) * slab_c;
-  const int ppc = (hw + CL - 1) / CL;  // pixels per block of the cluster
-  const int p_begin = rank * ppc, p_end = min(hw, p_begin + ppc);
-  const int cv = threadIdx.x % vps;
-  const int pl = threadIdx.x / vps;
-  const int ch = ch0 + cv * 8;
-  const bf16* src;
-  int cs, coff;
-  if (ch < c0) { src = a0; cs = c0; coff = ch; } else { src = a1; cs = c1; coff = ch - c0; }
-  const bf16* base = src + ((int64_t)n * hw + p_begin + pl) * cs + coff;
-  const int64_t step = (int64_t)lanes * cs;
-  const bool active = pl < lanes;
-  uint4 raw[V];
-#pragma unroll
-  for (int j = 0; j < V; ++j) {
-    raw[j] = make_uint4(0, 0, 0, 0);
-    if (active && p_begin + pl + j * lanes < p_end) raw[j] = __ldg(reinterpret_cast<const uint4*>(base + j * step));
-  }
-  float s[8], ss[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) s[e] = ss[e] = 0.f;
-#pragma unroll
-  for (int j = 0; j < V; ++j) {
-    const uint32_t u[4] = {raw[j].x, raw[j].y, raw[j].z, raw[j].w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 f = unpack_act2(u[e], F16);
-      s[2 * e] += f.x; ss[2 * e] += f.x * f.x;
-      s[2 * e + 1] += f.y; ss[2 * e + 1] += f.y * f.y;
-    }
-  }
-  if (active) {
-    float* mine = sh + (size_t)pl * 2 * slab_c + cv * 8;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      mine[e] = s[e];
-      mine[slab_c + e] = ss[e];
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * slab_c; i += blockDim.x) {
-    float acc = sh[i];
-    for (int l = 1; l < lanes; ++l) acc += sh[(size_t)l * 2 * slab_c + i];
-    sh[i] = acc;
-  }
-  __syncthreads();
-  const int gslab = slab_c / cpg;
-  double* part = reinterpret_cast<double*>(sh + 2 * slab_c);  // [gslab][2]: this block's partial (S, SS) per group
-  if (threadIdx.x < 2 * gslab) {
-    const int g = threadIdx.x >> 1, st = threadIdx.x & 1;
-    double acc = 0.0;
-    for (int c = 0; c < cpg; ++c) acc += (double)sh[st * slab_c + g * cpg + c];
-    part[g * 2 + st] = acc;
-  }
-  cluster_sync_all();  // every block's partials are written and visible cluster-wide
-  float* gstat = sh + 2 * slab_c + 4 * gslab + 4;  // [gslab][2] floats behind the doubles
-  if (threadIdx.x < gslab) {
-    const int g = threadIdx.x;
-    double S = 0.0, SS = 0.0;
-    const uint32_t laddr = smem_u32(part + g * 2);
-    for (int r = 0; r < CL; ++r) {  // fixed order over the cluster ranks
-      uint32_t raddr;
-      unsigned long long b0, b1;
-      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(r));
-      asm volatile("ld.shared::cluster.b64 %0, [%1];" : "=l"(b0) : "r"(raddr));
-      asm volatile("ld.shared::cluster.b64 %0, [%1];" : "=l"(b1) : "r"(raddr + 8));
-      S += __longlong_as_double((long long)b0);
-      SS += __longlong_as_double((long long)b1);
-    }
-    const double cnt = (double)hw * cpg;
-    const double mean = S / cnt;
-    double var = SS / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    gstat[2 * g] = (float)mean;
-    gstat[2 * g + 1] = (float)(1.0 / sqrt(var + (double)eps));
-  }
-  cluster_sync_all();  // nobody leaves (or reuses its partials) while a peer may still read them; also orders gstat
-  if (!active) return;
-  float sc[8], sf[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int cl = cv * 8 + e;
-    const int g = (int)__fdividef((float)cl + 0.5f, (float)cpg);
-    const float k = gstat[2 * g + 1] * __ldg(gamma + ch0 + cl);
-    sc[e] = k;
-    sf[e] = __ldg(beta + ch0 + cl) - gstat[2 * g] * k;
-  }
-  bf16* obase = out + ((int64_t)n * hw + p_begin + pl) * C + ch;
-  const int64_t ostep = (int64_t)lanes * C;
-#pragma unroll
-  for (int j = 0; j < V; ++j) {
-    if (p_begin + pl + j * lanes < p_end) {
-      const uint32_t u[4] = {raw[j].x, raw[j].y, raw[j].z, raw[j].w};
-      uint32_t o[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = unpack_act2(u[e], F16);
-        float y0 = f.x * sc[2 * e] + sf[2 * e];
-        float y1 = f.y * sc[2 * e + 1] + sf[2 * e + 1];
-        if (silu) { y0 = silu_tanh_f(y0); y1 = silu_tanh_f(y1); }
-        o[e] = pack_act2(y0, y1, F16);
-      }
-      *reinterpret_cast<uint4*>(obase + j * ostep) = make_uint4(o[0], o[1], o[2], o[3]);
-    }
-  }
-}
-
 // ---- GroupNorm, single pass with the slab in SHARED memory (round 2, end): one block owns a pixel range of (image, slab of whole
 // groups); the slab's pixels are split over a cluster of CL blocks when they do not fit one block.  Every thread fetches its
 // 16-byte vectors with cp.async into slots only it reads (no register cost: any number in flight, two to four blocks per SM, so
@@ -464,7 +234,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(640, 1)
 // Slabs are 32-byte-sector aligned where the channel count allows (80 channels at 10 / 20 / 40 channels per group), so no sector
 // is fetched by two blocks.
 template <bool F16, bool SILU>
-__global__ void __launch_bounds__(512, 2)  // <= 64 registers: four blocks of 256 threads or two of 512 per SM
+__global__ void __launch_bounds__(256, 4)
     gn_slab_kernel(const bf16* __restrict__ a0, const bf16* __restrict__ a1, int c0, int c1, int hw, int slab_c, int lanes, int ppc,
                    uint32_t magic_vps, uint32_t magic_cpg, int hdr, const float* __restrict__ gamma, const float* __restrict__ beta,
                    float eps, bf16* __restrict__ out) {
@@ -666,26 +436,16 @@ bool choose_slab(int C, int hw, SlabChoice* o) {
   const int cpg = C / GROUPS;
   if (cpg < 4 || cpg % 2 || (cpg < 8 && cpg != 4)) return false;  // a vector of 8 channels: at most two groups, split at an even channel
   auto lcm = [](int a, int b) { int x = a, y = b; while (y) { const int t = x % y; x = y; y = t; } return a / x * b; };
-  static int small_kb = -1, big_kb = -1, last_kb = -1, unaligned_first = 0, tmax_small = 256, tmax_big = 256;
-  if (small_kb < 0) {
-    small_kb = env_int("CPD_GN_SLAB_KB", 48);         // preferred block size: four blocks per SM
-    big_kb = env_int("CPD_GN_SLAB_BIG_KB", 100);      // two blocks per SM
-    last_kb = env_int("CPD_GN_SLAB_LAST_KB", 0);      // one block per SM: measured slower than the two-kernel path (16 x 4096 x 960)
-    unaligned_first = env_int("CPD_GN_SLAB_UNALIGNED", 0);
-    tmax_small = env_int("CPD_GN_SLAB_T", 256);       // threads per block: fewer threads = more vectors each = less fixed cost
-    tmax_big = env_int("CPD_GN_SLAB_BIG_T", 256);
-  }
+  // Measured on the SD-1.5 / SD-2.1 shapes (profiles/r02_gn_slab_bench.txt): blocks of <= 48 KB and 256 threads, four per SM, else
+  // <= 100 KB, two per SM; 512-thread blocks, unaligned slabs first and one 200 KB block per SM were all slower.
+  const int small_kb = 48, big_kb = 100, tmax = 256;
   int slabs[2] = {lcm(cpg, 16), lcm(cpg, 8)};  // [0]: sector-aligned (32 bytes), [1]: the smallest slab of whole groups and vectors
   while (slabs[0] * 2 < 128 && slabs[0] * 2 <= C && (slabs[0] * 2) / cpg <= 8) slabs[0] *= 2;  // at least a 128-byte line per pixel
-  // candidate order: aligned small, aligned big, unaligned small, unaligned big, then the one-block-per-SM sizes
-  const int a = unaligned_first ? 1 : 0, u = 1 - a;
-  const int order[6][2] = {{a, small_kb}, {a, big_kb}, {u, small_kb}, {u, big_kb}, {a, last_kb}, {u, last_kb}};
+  const int order[4][2] = {{0, small_kb}, {0, big_kb}, {1, small_kb}, {1, big_kb}};
   for (const auto& cand : order) {
     const int slab_c = slabs[cand[0]], limit_kb = cand[1];
-    if (limit_kb <= 0 || C % slab_c || slab_c / cpg > 8) continue;
+    if (C % slab_c || slab_c / cpg > 8) continue;
     const int vps = slab_c / 8;
-    int tmax = limit_kb <= small_kb ? tmax_small : tmax_big;
-    if (tmax > 512) tmax = 512;
     if (vps > 32 || vps > tmax) continue;
     uint32_t mv, mc;
     if (!magic_div(vps, 512, &mv) || !magic_div(cpg, slab_c + 1, &mc)) continue;
@@ -875,7 +635,7 @@ extern "C" cpd_status cpd_groupnorm(const void* a0, const void* a1, int c0, int 
   CPD_REQUIRE(c1 == 0 || a1, "cpd_groupnorm: c1 > 0 needs a1");
   CPD_REQUIRE(n_img > 0 && hw > 0, "cpd_groupnorm: empty input");
   cudaStream_t s = (cudaStream_t)stream;
-  {  // single pass with the slab in shared memory, split over a cluster where needed (CPD_GN_SLAB=0: the older kernels below)
+  {  // single pass with the slab in shared memory, split over a cluster where needed (CPD_GN_SLAB=0 or a shape that does not fit: the two kernels below)
     static int slab_on = -1;
     if (slab_on < 0) slab_on = env_int("CPD_GN_SLAB", 1);
     SlabChoice sc;
@@ -893,100 +653,6 @@ extern "C" cpd_status cpd_groupnorm(const void* a0, const void* a1, int c0, int 
 #undef CPD_GN_SLAB_LAUNCH
       CPD_CUDA_CHECK(cudaGetLastError());
       return CPD_OK;
-    }
-  }
-  {  // single-pass kernel when (image, slab of whole groups) fits the register file of one block
-    const int cpg = C / GROUPS;
-    int slab_c = cpg;
-    while (slab_c % 8) slab_c += cpg;  // smallest multiple of cpg that is a multiple of 8
-    const int vps = slab_c / 8;
-    const bool whole = C % slab_c == 0 && c0 % slab_c == 0;
-    static int fused_on = -1;  // CPD_GN_FUSED=0 keeps the two-kernel path (A/B measurements)
-    if (fused_on < 0) {
-      const char* e = getenv("CPD_GN_FUSED");
-      fused_on = (e && e[0] == '0') ? 0 : 1;
-    }
-    if (fused_on && whole && vps <= 20) {
-      int V = 0, lanes = 0;
-      for (int v : {8, 4, 2, 10}) {  // most loads in flight per thread with 128..640 threads per block
-        const int l = (hw + v - 1) / v;
-        if (l * vps <= 640 && (l * vps >= 128 || v == 2)) { V = v; lanes = l; break; }
-      }
-      if (V) {
-        const int threads = lanes * vps;
-        const size_t shm = sizeof(float) * ((size_t)2 * slab_c * lanes + 2 * slab_c + 2 * GROUPS);
-        if (shm <= 200 * 1024) {
-          const dim3 grid(C / slab_c, n_img);
-#define CPD_GN_FUSED_LAUNCH(F, VV)                                                                                        \
-  do {                                                                                                                    \
-    CPD_SMEM_OPTIN((gn_fused_kernel<F, VV>), 200 * 1024);                                                                 \
-    CPD_CUDA_CHECK(cpd_launch(gn_fused_kernel<F, VV>, grid, dim3(threads), shm, s, (const bf16*)a0, (const bf16*)a1, c0, c1, hw, \
-                              slab_c, gamma, beta, eps, silu, (bf16*)out));                                               \
-  } while (0)
-          if (act_fp16) {
-            if (V == 2) CPD_GN_FUSED_LAUNCH(true, 2); else if (V == 4) CPD_GN_FUSED_LAUNCH(true, 4);
-            else if (V == 8) CPD_GN_FUSED_LAUNCH(true, 8); else CPD_GN_FUSED_LAUNCH(true, 10);
-          } else {
-            if (V == 2) CPD_GN_FUSED_LAUNCH(false, 2); else if (V == 4) CPD_GN_FUSED_LAUNCH(false, 4);
-            else if (V == 8) CPD_GN_FUSED_LAUNCH(false, 8); else CPD_GN_FUSED_LAUNCH(false, 10);
-          }
-#undef CPD_GN_FUSED_LAUNCH
-          CPD_CUDA_CHECK(cudaGetLastError());
-          return CPD_OK;
-        }
-      }
-      // the slab does not fit one block: split its pixels over a cluster of 8 / 4 / 2 blocks (distributed shared memory)
-      // Measured SLOWER than the two-kernel path (16 x 4096 x 320: 40.8 vs 26.7 us, 16 x 4096 x 640: 81 vs 55 us): a slab is
-      // an 80-byte slice of every 640-byte pixel row, so every 128-byte line is fetched by two or three different clusters,
-      // and 640-thread blocks at 96 registers leave one block per SM.  Opt-in: CPD_GN_CLUSTER=1.
-      static int cluster_on = -1;
-      if (cluster_on < 0) {
-        const char* e = getenv("CPD_GN_CLUSTER");
-        cluster_on = (e && e[0] == '1') ? 1 : 0;
-      }
-      if (cluster_on && !V) {
-        int CLs = 0, Vc = 0, lanes_c = 0;
-        for (int cl : {8, 4, 2}) {
-          const int ppc = (hw + cl - 1) / cl;
-          for (int v : {8, 10}) {
-            const int l = (ppc + v - 1) / v;
-            if (l * vps <= 640 && l * vps >= 128) { CLs = cl; Vc = v; lanes_c = l; break; }
-          }
-          if (CLs) break;
-        }
-        if (CLs) {
-          const int threads = ((lanes_c * vps + 31) / 32) * 32;  // whole warps: cluster barriers are executed by every thread
-          const int lanes_k = threads / vps;  // what the kernel derives from blockDim.x
-          const size_t shm = sizeof(float) * ((size_t)2 * slab_c * lanes_k + 2 * slab_c + 8 * GROUPS + 8);
-          if (threads <= 640 && shm <= 200 * 1024) {
-            const dim3 grid((C / slab_c) * CLs, n_img);
-#define CPD_GN_CL_LAUNCH(F, VV, CC)                                                                                        \
-  do {                                                                                                                     \
-    CPD_SMEM_OPTIN((gn_cluster_kernel<F, VV, CC>), 200 * 1024);                                                            \
-    CPD_CUDA_CHECK(cpd_launch(gn_cluster_kernel<F, VV, CC>, grid, dim3(threads), shm, s, (const bf16*)a0, (const bf16*)a1, c0, c1, \
-                              hw, slab_c, gamma, beta, eps, silu, (bf16*)out));                                            \
-  } while (0)
-#define CPD_GN_CL_V(F, CC)                                       \
-  do {                                                           \
-    if (Vc == 8) CPD_GN_CL_LAUNCH(F, 8, CC);                     \
-    else CPD_GN_CL_LAUNCH(F, 10, CC);                            \
-  } while (0)
-#define CPD_GN_CL_C(F)                                           \
-  do {                                                           \
-    if (CLs == 8) CPD_GN_CL_V(F, 8);                             \
-    else if (CLs == 4) CPD_GN_CL_V(F, 4);                        \
-    else CPD_GN_CL_V(F, 2);                                      \
-  } while (0)
-            if (act_fp16) CPD_GN_CL_C(true);
-            else CPD_GN_CL_C(false);
-#undef CPD_GN_CL_C
-#undef CPD_GN_CL_V
-#undef CPD_GN_CL_LAUNCH
-            CPD_CUDA_CHECK(cudaGetLastError());
-            return CPD_OK;
-          }
-        }
-      }
     }
   }
   const int vec_per_px = C / 8;

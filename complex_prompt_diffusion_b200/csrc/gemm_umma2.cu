@@ -616,22 +616,39 @@ __global__ void __cluster_dims__(2 * MC, 1, 1) __launch_bounds__(NUM_THREADS2, 1
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * ACC_COLS);
 
       if (splits > 1) {
-        // split-K: add this unit's fp32 partial tile into the workspace; bias / residual / conversion happen in the
-        // finalize kernel once every K range has been added
+        // split-K: store this unit's fp32 partial tile in its workspace slice; bias / residual / conversion happen in the
+        // finalize kernel once every K range has been stored.  A thread owns a ROW of the tile: stored directly its 32 columns
+        // are eight 16-byte pieces at a row stride (32 different lines per store instruction: 8.6 us of a 42 us launch in the
+        // timeline of 1024 x 1280 x 11520).  So the warp's 32 x 32 block goes through the group's staging buffers - idle in
+        // split-K launches, the store warp does not run - swizzled like the 16-bit chunks, and leaves as whole 128-byte lines:
+        // instruction i writes columns 4 (lane % 8) .. + 3 of rows 4 i + lane / 8.
+        const uint32_t wbuf = smem_u32(my_staging) + (uint32_t)q * 4096u;  // 32 rows x 128 bytes per warp (4 warps: 2 staging buffers)
+        int rows_i[8];  // workspace row of this lane's row in store instruction i (-1: padding row)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int src = 4 * i + (lane >> 3);
+          const int rr = __shfl_sync(0xffffffffu, (int)rc.row, src);
+          const int vv = __shfl_sync(0xffffffffu, (int)rc.valid, src);
+          rows_i[i] = vv ? rr : -1;
+        }
+        const int c16 = lane & 7;
         for (int ch = c_lo; ch < c_hi; ++ch) {
           uint32_t v[32];
           tmem_ld32(taddr + ch * CHUNK_COLS, v);
           tmem_ld_wait();
           const int col0 = n_tile * out_w + ch * CHUNK_COLS;
-          if (rc.valid) {
-            float* wrow = args.ws + (int64_t)(t % splits) * args.ws_slice + rc.row * g.n_store + col0;
 #pragma unroll
-            for (int e = 0; e < 32; e += 4) {
-              if (col0 + e < g.n_store)
-                *reinterpret_cast<float4*>(wrow + e) = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
-                                                                   __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
-            }
+          for (int c = 0; c < 8; ++c)
+            sts128(wbuf + (uint32_t)lane * 128u + (uint32_t)((c ^ (lane & 7)) << 4), make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+          __syncwarp();
+          float* wbase = args.ws + (int64_t)(t % splits) * args.ws_slice + col0 + c16 * 4;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rl = 4 * i + (lane >> 3);
+            const uint4 x = lds128(wbuf + (uint32_t)rl * 128u + (uint32_t)((c16 ^ (rl & 7)) << 4));
+            if (rows_i[i] >= 0 && col0 + c16 * 4 < g.n_store) *reinterpret_cast<uint4*>(wbase + (int64_t)rows_i[i] * g.n_store) = x;
           }
+          __syncwarp();  // the block is overwritten by the next chunk
         }
         tc_fence_before();
         __syncwarp();
@@ -868,12 +885,29 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(const float* __res
   pdl_wait();
   const int vec_per_row = n_store / 8;
   const int64_t total = rows * vec_per_row;
+  const bool small = total < (1ll << 31);  // 32-bit index arithmetic (a 64-bit division costs ~100 instructions per item)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = i / vec_per_row;
+    const int64_t row = small ? (int64_t)((uint32_t)i / (uint32_t)vec_per_row) : i / vec_per_row;
     const int col = (int)(i - row * vec_per_row) * 8;
     float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int sp = 0; sp < splits; ++sp) {
-      const float4* wp = reinterpret_cast<const float4*>(ws + sp * ws_slice + row * n_store + col);
+    const float* w0 = ws + row * n_store + col;
+    int sp = 0;
+    for (; sp + 4 <= splits; sp += 4) {  // four slices in flight, added in slice order (bit-identical to the one-by-one loop)
+      float4 a[4][2];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4* wp = reinterpret_cast<const float4*>(w0 + (sp + k) * ws_slice);
+        a[k][0] = wp[0];
+        a[k][1] = wp[1];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        f[0] += a[k][0].x; f[1] += a[k][0].y; f[2] += a[k][0].z; f[3] += a[k][0].w;
+        f[4] += a[k][1].x; f[5] += a[k][1].y; f[6] += a[k][1].z; f[7] += a[k][1].w;
+      }
+    }
+    for (; sp < splits; ++sp) {
+      const float4* wp = reinterpret_cast<const float4*>(w0 + sp * ws_slice);
       const float4 a0 = wp[0], a1 = wp[1];
       f[0] += a0.x; f[1] += a0.y; f[2] += a0.z; f[3] += a0.w;
       f[4] += a1.x; f[5] += a1.y; f[6] += a1.z; f[7] += a1.w;

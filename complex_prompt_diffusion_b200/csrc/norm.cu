@@ -469,6 +469,12 @@ bool choose_slab(int C, int hw, SlabChoice* o) {
   return false;
 }
 
+bool slab_enabled() {
+  static int slab_on = -1;
+  if (slab_on < 0) slab_on = env_int("CPD_GN_SLAB", 1);
+  return slab_on != 0;
+}
+
 // ---- LayerNorm: one warp per R rows (all loads of the R rows issued before the first use), rows in registers -----
 template <int MAXV, int R>  // max 16-byte vectors per lane, rows per warp
 __global__ void __launch_bounds__(256, 4) layernorm_kernel(const bf16* __restrict__ x, int rows, int c,
@@ -636,10 +642,8 @@ extern "C" cpd_status cpd_groupnorm(const void* a0, const void* a1, int c0, int 
   CPD_REQUIRE(n_img > 0 && hw > 0, "cpd_groupnorm: empty input");
   cudaStream_t s = (cudaStream_t)stream;
   {  // single pass with the slab in shared memory, split over a cluster where needed (CPD_GN_SLAB=0 or a shape that does not fit: the two kernels below)
-    static int slab_on = -1;
-    if (slab_on < 0) slab_on = env_int("CPD_GN_SLAB", 1);
     SlabChoice sc;
-    if (slab_on && n_img <= 65535 && choose_slab(C, hw, &sc)) {
+    if (slab_enabled() && n_img <= 65535 && choose_slab(C, hw, &sc)) {
       const dim3 grid(sc.cl, C / sc.slab_c, n_img);  // the cluster is the grid's x dimension
 #define CPD_GN_SLAB_LAUNCH(F, S)                                                                                                  \
   do {                                                                                                                            \
@@ -691,6 +695,13 @@ extern "C" cpd_status cpd_groupnorm(const void* a0, const void* a1, int c0, int 
   }
   CPD_CUDA_CHECK(cudaGetLastError());
   return CPD_OK;
+}
+
+// Kernel launches cpd_groupnorm makes for this shape: 1 (shared-memory slab kernel) or 2 (statistics + apply).
+extern "C" int cpd_groupnorm_launches(int c, int n_img, int hw) {
+  SlabChoice sc;
+  if (c <= 0 || c % GROUPS || n_img <= 0 || hw <= 0) return 0;
+  return slab_enabled() && n_img <= 65535 && choose_slab(c, hw, &sc) ? 1 : 2;
 }
 
 // GroupNorm from the producer's statistics: the apply pass alone (one read + one write of the tensor).

@@ -801,7 +801,7 @@ cpd_status groupnorm(cpd_unet_plan* P, cudaStream_t st, const void* a0, const vo
     OpScope op(P, st, "groupnorm", label, 0.0, 1);
     return cpd_groupnorm_apply(a0, c0, n_img, hw, (const float*)W(P, g), (const float*)W(P, b), eps, silu, P->cfg.act_fp16, chan_sums, out, st);
   }
-  OpScope op(P, st, "groupnorm", label, 0.0, 2);
+  OpScope op(P, st, "groupnorm", label, 0.0, cpd_groupnorm_launches(c0 + c1, n_img, hw));
   return cpd_groupnorm(a0, a1, c0, c1, n_img, hw, (const float*)W(P, g), (const float*)W(P, b), eps, silu, P->cfg.act_fp16, stats, out, st);
 }
 

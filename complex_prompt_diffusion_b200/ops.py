@@ -294,7 +294,7 @@ def groupnorm(a0, gamma, beta, out, stats, *, n_img, hw, c0, a1=None, c1=0, eps=
     with _Prof("groupnorm", 0.0, f"n={n_img} hw={hw} C={c0 + c1}"):
         check(load().cpd_groupnorm(ptr(a0), ptr(a1), c0, c1, n_img, hw, ptr(gamma), ptr(beta), float(eps), int(silu), f16, ptr(stats),
                                    ptr(out), stream_ptr()), "cpd_groupnorm")
-    _count(2)
+    _count(load().cpd_groupnorm_launches(c0 + c1, n_img, hw))  # 1: shared-memory slab kernel, 2: statistics + apply
     return out
 
 

@@ -276,11 +276,15 @@ int cpd_gemm_tune_import(const char* text);
 /*
  * GroupNorm(32 groups) [+ SiLU] over NHWC bf16, fp32 statistics (models/util.py:95-105, attention.py:89-90).
  * Input channels may come from two tensors (skip concat).  stats: fp64 scratch of n_img * CPD_GN_MAX_CHUNKS * 64
- * doubles (per-chunk partial sums, reduced in a fixed order: no atomics, bit-reproducible).  out: bf16 [n_img*hw][c0 + c1].
+ * doubles (per-chunk partial sums of the two-launch path, reduced in a fixed order; the one-launch kernel reduces in shared /
+ * distributed shared memory in a fixed order: no atomics on either path, bit-reproducible).  out: 16-bit [n_img*hw][c0 + c1].
  */
 #define CPD_GN_MAX_CHUNKS 64
 cpd_status cpd_groupnorm(const void* a0, const void* a1, int c0, int c1, int n_img, int hw, const float* gamma,
                          const float* beta, float eps, int silu, int act_fp16, double* stats, void* out, void* stream);
+/* How many kernels cpd_groupnorm launches for c = c0 + c1 channels: 1 when the (image, group slab) tiles fit the shared-memory /
+ * cluster kernel (one read + one write of the tensor; `stats` is then unused), 2 (statistics + apply) otherwise; 0 = bad shape. */
+int cpd_groupnorm_launches(int c, int n_img, int hw);
 
 /* GroupNorm(32) (+ SiLU) from per-(image, channel) fixed-point statistics emitted by the producing GEMM (cpd_gemm_params.gn_sums_out):
  * one read + one write of the tensor.  x, out: NHWC 16-bit [n_img][hw][c]. */

@@ -81,6 +81,28 @@ def test_argument_validation_without_gpu(lib_path):
     assert lib.cpd_threshold_ex(16, 0, 4, 64, _lib.CPD_THRESH_RENORM, 0.9, 16, None) == 0
 
 
+def test_groupnorm_launch_plan_without_gpu(lib_path):
+    """cpd_groupnorm_launches is pure host logic: every GroupNorm shape of the SD-1.5 / SD-2.1 / SDXL UNets and of the first-stage
+    decoder's 64 x 64 level takes the one-launch shared-memory kernel (1); shapes whose (image, group slab) cannot be split into
+    resident blocks, group sizes a vector of 8 channels cannot be split on, and bad arguments do not (2 / 0)."""
+    lib = ctypes.CDLL(lib_path)
+    f = lib.cpd_groupnorm_launches
+    f.restype = ctypes.c_int
+    f.argtypes = [ctypes.c_int] * 3
+    for hw in (64, 144, 256, 576, 1024, 2304, 4096, 9216):
+        for c in (320, 640, 1280, 2560):
+            if (c, hw) != (2560, 9216):  # 80 channels per group at 96 x 96: a 1.5 MB slab (no UNet has it)
+                assert f(c, 16, hw) == 1, (c, hw)
+    assert f(2560, 16, 9216) == 2
+    for c, hw in ((960, 1024), (1920, 1024), (1920, 256), (2560, 64), (512, 4096), (128, 1024)):
+        assert f(c, 4, hw) == 1, (c, hw)
+    assert f(960, 16, 4096) == 2      # a 960 KB slab: not even a cluster of 8 blocks holds it
+    assert f(128, 1, 512 * 512) == 2  # first-stage decoder at full resolution
+    assert f(96, 2, 256) == 2 and f(480, 2, 256) == 2  # 3 / 15 channels per group
+    assert f(320, 70000, 64) == 2     # more images than the grid's z dimension
+    assert f(100, 1, 64) == 0 and f(320, 0, 64) == 0 and f(320, 1, 0) == 0
+
+
 def test_registry_and_wrapper_surface():
     from complex_prompt_diffusion_b200 import samplers
     assert {"Euler", "Euler Ancestral", "DPM++ 2m"} <= set(samplers.lookup)

@@ -236,12 +236,12 @@ __global__ void __launch_bounds__(512, 2) gn_apply_kernel(const bf16* __restrict
 template <bool F16, bool SILU>
 __global__ void __launch_bounds__(256, 4)
     gn_slab_kernel(const bf16* __restrict__ a0, const bf16* __restrict__ a1, int c0, int c1, int hw, int slab_c, int lanes, int ppc,
-                   uint32_t magic_vps, uint32_t magic_cpg, int hdr, const float* __restrict__ gamma, const float* __restrict__ beta,
-                   float eps, bf16* __restrict__ out) {
+                   uint32_t magic_vps, uint32_t magic_cpg, int hdr, int half, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, float eps, bf16* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char slab_raw[];
-  double* part = reinterpret_cast<double*>(slab_raw);        // [groups of the slab][2]: this block's (S, SS)
-  float* gstat = reinterpret_cast<float*>(slab_raw + 128);   // [groups of the slab][2]: mean, rstd
-  float4* red = reinterpret_cast<float4*>(slab_raw + 192);   // [vector of the slab][warp]: (S, SS) of its two groups
+  double* part = reinterpret_cast<double*>(slab_raw);        // [cluster rank][groups of the slab][2]: every block's (S, SS), pushed by its owner
+  float* gstat = reinterpret_cast<float*>(slab_raw + 1024);  // [groups of the slab][2]: mean, rstd
+  float4* red = reinterpret_cast<float4*>(slab_raw + 1088);  // [vector of the slab][warp]: (S, SS) of its two groups
   pdl_launch_dependents();
   const int tid = threadIdx.x, T = blockDim.x;
   const int C = c0 + c1;
@@ -249,6 +249,9 @@ __global__ void __launch_bounds__(256, 4)
   const int vps = slab_c >> 3;
   const int gslab = (int)(((uint32_t)slab_c * magic_cpg) >> 16);
   const int cl = gridDim.x, rank = blockIdx.x;  // the cluster spans the grid's x dimension
+  // "I am running": a peer may store into this block's shared memory only once the block executes; the matching wait sits in front
+  // of the first such store, by which time every block has long arrived (split arrive / wait: nobody stalls here)
+  if (cl > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
   const int ch0 = blockIdx.y * slab_c;
   const int n = blockIdx.z;
   const int p_begin = rank * ppc, p_end = min(hw, p_begin + ppc);
@@ -267,20 +270,26 @@ __global__ void __launch_bounds__(256, 4)
   const uint32_t slot0 = smem_u32(slab_raw + hdr) + tid * 16, sstep = T * 16;
   int np = 0;  // pixels of this thread
   pdl_wait();
+  int np1 = 0;  // ... of which in the first of the two cp.async groups (the sums of the first half run while the second half lands)
   if (pl < lanes) {
     const char* gp = reinterpret_cast<const char*>(src + ((int64_t)n * hw + p_begin + pl) * cs + coff);
     const int64_t gstep = (int64_t)lanes * cs * 2;
     uint32_t sa = slot0;
-    for (int p = p_begin + pl; p < p_end; p += lanes, ++np, sa += sstep, gp += gstep)
+    int p = p_begin + pl;
+    for (; p < p_end && np < half; p += lanes, ++np, sa += sstep, gp += gstep)
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gp) : "memory");
+    np1 = np;
+    cp_async_commit();
+    for (; p < p_end; p += lanes, ++np, sa += sstep, gp += gstep)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gp) : "memory");
+  } else {
+    cp_async_commit();
   }
   cp_async_commit();
-  cp_async_wait<0>();
   float2 s[4], q[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) s[e] = q[e] = make_float2(0.f, 0.f);
-#pragma unroll 4
-  for (int j = 0; j < np; ++j) {
+  auto accumulate = [&](int j) {
     const uint4 v = lds128(slot0 + j * sstep);
     const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -289,7 +298,13 @@ __global__ void __launch_bounds__(256, 4)
       s[e] = __fadd2_rn(s[e], f);
       q[e] = __ffma2_rn(f, f, q[e]);
     }
-  }
+  };
+  cp_async_wait<1>();
+#pragma unroll 4
+  for (int j = 0; j < np1; ++j) accumulate(j);
+  cp_async_wait<0>();
+#pragma unroll 4
+  for (int j = np1; j < np; ++j) accumulate(j);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);  // (S, SS) of group gA, (S, SS) of group gA + 1
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
@@ -305,6 +320,7 @@ __global__ void __launch_bounds__(256, 4)
   }
   if (lane < vps) red[cv * nwarps + warp] = acc;
   __syncthreads();
+  if (cl > 1) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");  // every block of the cluster has started
   if (tid < 2 * gslab) {  // fixed order over the vectors of the group and the warps
     const int g = tid >> 1, st = tid & 1;
     const int cv_lo = (g * cpg) >> 3, cv_hi = ((g + 1) * cpg - 1) >> 3;
@@ -315,41 +331,36 @@ __global__ void __launch_bounds__(256, 4)
       const float* col = redf + (size_t)c * nwarps * 4 + (gc == g ? st : 2 + st);
       for (int w = 0; w < nwarps; ++w) a += (double)col[w * 4];
     }
-    part[tid] = a;
-  }
-  if (cl > 1) cluster_sync_all(); else __syncthreads();  // every block's partials are written (and visible cluster-wide)
-  if (tid < gslab * cl) {  // thread (group, rank) fetches one pair; the ranks of a group are neighbouring lanes (cl = 2^k)
-    const int lg = __ffs(cl) - 1;
-    const int g = tid >> lg, r = tid & (cl - 1);
-    double S, SS;
+    // PUSH the partial into every block of the cluster (distributed shared memory stores, fire and forget): after ONE cluster
+    // barrier each block holds all partials and reduces them locally - nobody reads a peer's memory afterwards, so no second
+    // cluster barrier has to keep the blocks alive for each other.
     if (cl > 1) {
-      uint32_t raddr;
-      unsigned long long b0, b1;
-      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(part + g * 2)), "r"(r));
-      asm volatile("ld.shared::cluster.b64 %0, [%1];" : "=l"(b0) : "r"(raddr));
-      asm volatile("ld.shared::cluster.b64 %0, [%1];" : "=l"(b1) : "r"(raddr + 8));
-      S = __longlong_as_double((long long)b0);
-      SS = __longlong_as_double((long long)b1);
-      const int here = gslab * cl - (tid & ~31);  // threads of this warp inside the branch: whole groups of cl lanes
-      const unsigned mask = here >= 32 ? 0xffffffffu : (1u << here) - 1u;
-      for (int o = 1; o < cl; o <<= 1) {
-        S += __shfl_xor_sync(mask, S, o);
-        SS += __shfl_xor_sync(mask, SS, o);
+      const uint32_t laddr = smem_u32(part + rank * 16 + tid);
+      for (int r = 0; r < cl; ++r) {
+        uint32_t raddr;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(r));
+        asm volatile("st.shared::cluster.b64 [%0], %1;" ::"r"(raddr), "l"(__double_as_longlong(a)) : "memory");
       }
     } else {
-      S = part[2 * g];
-      SS = part[2 * g + 1];
-    }
-    if (r == 0) {
-      const double cnt = (double)hw * cpg;
-      const double mean = S / cnt;
-      double var = SS / cnt - mean * mean;
-      if (var < 0.0) var = 0.0;
-      gstat[2 * g] = (float)mean;
-      gstat[2 * g + 1] = (float)(1.0 / sqrt(var + (double)eps));
+      part[tid] = a;
     }
   }
-  if (cl > 1) cluster_sync_all(); else __syncthreads();  // nobody leaves while a peer may still read its partials; orders gstat
+  if (cl > 1) cluster_sync_all(); else __syncthreads();  // every block's partials have landed here (release / acquire at cluster scope)
+  if (tid < gslab) {
+    const int g = tid;
+    double S = 0.0, SS = 0.0;
+    for (int r = 0; r < cl; ++r) {  // fixed order over the cluster ranks: the same bits in every block
+      S += part[r * 16 + 2 * g];
+      SS += part[r * 16 + 2 * g + 1];
+    }
+    const double cnt = (double)hw * cpg;
+    const double mean = S / cnt;
+    double var = SS / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    gstat[2 * g] = (float)mean;
+    gstat[2 * g + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
   if (np == 0) return;
   float2 sc[4], sf[4];
   {
@@ -458,8 +469,8 @@ bool choose_slab(int C, int hw, SlabChoice* o) {
       const int slots = (ppc + lanes - 1) / lanes;
       lanes = (ppc + slots - 1) / slots;
       const int threads = ((lanes * vps + 31) / 32) * 32;
-      if (threads < 2 * (slab_c / cpg) || threads < (slab_c / cpg) * cl) continue;  // the reduction's (group, statistic) / (group, rank) threads
-      const int hdr = 192 + vps * (threads / 32) * 16;
+      if (threads < 2 * (slab_c / cpg)) continue;  // the reduction's (group, statistic) threads
+      const int hdr = 1088 + vps * (threads / 32) * 16;
       const size_t smem = (size_t)hdr + (size_t)slots * threads * 16;
       if (smem > 220 * 1024) continue;
       *o = {slab_c, cl, lanes, threads, slots, ppc, hdr, mv, mc, smem};
@@ -649,8 +660,8 @@ extern "C" cpd_status cpd_groupnorm(const void* a0, const void* a1, int c0, int 
   do {                                                                                                                            \
     CPD_SMEM_OPTIN((gn_slab_kernel<F, S>), 220 * 1024);                                                                           \
     CPD_CUDA_CHECK(launch_clustered(gn_slab_kernel<F, S>, grid, dim3(sc.threads), sc.smem, s, sc.cl, (const bf16*)a0,             \
-                                    (const bf16*)a1, c0, c1, hw, sc.slab_c, sc.lanes, sc.ppc, sc.magic_vps, sc.magic_cpg, sc.hdr, \
-                                    gamma, beta, eps, (bf16*)out));                                                               \
+                                    (const bf16*)a1, c0, c1, hw, sc.slab_c, sc.lanes, sc.ppc, sc.magic_vps, sc.magic_cpg, sc.hdr,  \
+                                    (sc.slots + 1) / 2, gamma, beta, eps, (bf16*)out));                                                               \
   } while (0)
       if (act_fp16) { if (silu) CPD_GN_SLAB_LAUNCH(true, true); else CPD_GN_SLAB_LAUNCH(true, false); }
       else { if (silu) CPD_GN_SLAB_LAUNCH(false, true); else CPD_GN_SLAB_LAUNCH(false, false); }

@@ -229,8 +229,10 @@ __global__ void __launch_bounds__(512, 2) gn_apply_kernel(const bf16* __restrict
 // * a vector of 8 channels lies in at most two groups (an even number of channels per group), so a thread ends with four sums
 //   (S, SS of its first and of its second group); lanes that hold the same channel vector are folded with shuffles, one lane per
 //   (vector, warp) writes them to shared memory and 2 x (groups of the slab) threads add them up in a fixed order in fp64;
-// * cluster blocks exchange the per-group partials through distributed shared memory, one (group, rank) pair per thread, summed
-//   by a butterfly over the ranks: every block gets the same bits, and nothing depends on timing (bit-reproducible).
+// * cluster blocks PUSH their per-group partials into every block of the cluster (distributed shared memory stores), meet at ONE
+//   cluster barrier and add the ranks' partials locally in rank order: every block gets the same bits, nothing depends on timing
+//   (bit-reproducible), and nobody reads a peer's memory after the barrier, so blocks leave independently;
+// * the loads are two cp.async groups: the sums of the first half run while the second half lands.
 // Slabs are 32-byte-sector aligned where the channel count allows (80 channels at 10 / 20 / 40 channels per group), so no sector
 // is fetched by two blocks.
 template <bool F16, bool SILU>
